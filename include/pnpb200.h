@@ -1,0 +1,211 @@
+/*
+ * pnpb200.h -- C ABI of the B200-native batched PnP solver (libpnpb200.so).
+ *
+ * The reference (Benson516/pnp_solver_test) is pure Python and has no FFI boundary: its
+ * boundary is the class PNP_SOLVER in scripts/PNP_SOLVER_LIB.py.  Every entry point below
+ * names the reference interface it replaces (file:line, relative to the reference root).
+ * The Python mirror of that class (pnp_solver_test_b200/solver.py) binds these symbols with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  No torch types.
+ *  - Pointers marked [device] are CUDA device pointers owned by the caller, 16-byte aligned;
+ *    [host] are ordinary host pointers read during the call.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *    stream) unless stated otherwise.  The library allocates nothing persistent except inside
+ *    a pnpb200_pipeline (host entry point), which the caller creates and destroys.
+ *  - Return value: 0 on success, a negative PNPB200_E* code otherwise.  Like the reference,
+ *    the numeric path never raises: a diverged solve returns garbage R/t and a large res_norm.
+ *  - dtype selects BOTH the I/O element type of the float arrays and the arithmetic type.
+ *    FP64 is the parity mode (the reference is float64 only).
+ */
+#ifndef PNPB200_H
+#define PNPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNPB200_VERSION 100
+
+/* method: which single-pattern solver of the reference to run */
+#define PNPB200_METHOD_QEIF       0  /* solve_pnp_QEIF_single_pattern,          PNP_SOLVER_LIB.py:2771-3025 (what solve_pnp() dispatches to, :179) */
+#define PNPB200_METHOD_LM         1  /* solve_pnp_LM_single_pattern,            PNP_SOLVER_LIB.py:2567-2769 */
+#define PNPB200_METHOD_LINEAR_F2  2  /* solve_pnp_formulation_2_single_pattern, PNP_SOLVER_LIB.py:693-953   */
+#define PNPB200_METHOD_LINEAR_F1  3  /* solve_pnp_single_pattern,               PNP_SOLVER_LIB.py:205-430   */
+
+#define PNPB200_DTYPE_F64 0
+#define PNPB200_DTYPE_F32 1
+
+/* execution shape (0 = let the library choose from n) */
+#define PNPB200_MAP_AUTO    0
+#define PNPB200_MAP_THREAD  1   /* one problem per thread, correspondences staged in shared memory */
+#define PNPB200_MAP_WARP    32  /* one problem per warp, shuffle-reduced normal equations          */
+
+#define PNPB200_OK          0
+#define PNPB200_EINVAL     -1   /* bad argument (null pointer, n < 1, unknown method/dtype, ...)   */
+#define PNPB200_ECUDA      -2   /* a CUDA runtime call failed; see pnpb200_last_error()            */
+#define PNPB200_ENODEVICE  -3   /* no usable CUDA device                                           */
+#define PNPB200_ETOOLARGE  -4   /* n exceeds what the selected mapping can hold                    */
+
+#define PNPB200_MAX_PATTERNS 8
+#define PNPB200_REPORT_WIDTH 16
+
+/* Solver constants.  The reference hard-codes these inline; defaults reproduce it. */
+typedef struct pnpb200_params {
+    int32_t max_it;        /* 14      PNP_SOLVER_LIB.py:2635 (LM), :2857 (QEIF)                   */
+    int32_t linear_it;     /* 3       :223 (F1), :762 (F2)                                         */
+    double  lm_lambda;     /* 1e-5    :2631  constant damping                                      */
+    double  exit_tol;      /* 1e-2    :2952  QEIF early exit on |d res / res|                      */
+    double  f_weight;      /* 225.68  :2845  focal length used in the measurement weight (NOT K)   */
+    double  meas_sigma_px; /* 3.0     :2846                                                        */
+    double  proc_q;        /* 1e-1    :2792  process noise, quaternion states                      */
+    double  proc_d;        /* 1e-2    :2793  process noise, delta states                           */
+    double  omega0;        /* 1e-5    :2836  initial information                                   */
+    double  res_old0;      /* 1e-7    :2863                                                        */
+    int32_t mapping;       /* PNPB200_MAP_*                                                        */
+    int32_t reserved;
+} pnpb200_params;
+
+/* Synthetic workload description (random_stress_test.py:246-258, LM_noise_test.py:141-189). */
+typedef struct pnpb200_synth {
+    uint64_t seed;            /* Philox4x32-10 key; the counter is the GLOBAL problem index        */
+    double   angle_range_deg; /* 45    roll, pitch, yaw ~ U(-a, a)                                 */
+    double   depth_min_m;     /* 0.20                                                              */
+    double   depth_max_m;     /* 2.25                                                              */
+    double   fov_max_deg;     /* 45    t = depth * [tan U(-f,f), tan U(-f,f), 1]                   */
+    int32_t  is_quantized;    /* round pixels to multiples of quantize_q (np.around)               */
+    int32_t  reserved;
+    double   quantize_q;      /* 1.0                                                               */
+    double   noise_sigma_px;  /* 0 = none; Gaussian pixel noise added after quantisation           */
+} pnpb200_synth;
+
+int pnpb200_version(void);
+const char* pnpb200_last_error(void);          /* text of the last CUDA error seen by this thread */
+int pnpb200_default_params(pnpb200_params* p);
+int pnpb200_default_synth(pnpb200_synth* s);
+int pnpb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+
+/*
+ * The hot path.  Replaces the per-problem loop around PNP_SOLVER.solve_pnp
+ * (PNP_SOLVER_LIB.py:144-203; callers random_stress_test.py:322, LM_noise_test.py:312,
+ * face_variation_test.py:431) and the solve_pnp_*_single_pattern methods it dispatches to.
+ * One launch does, per problem: correspondence packing and K^-1 normalisation
+ * (f2_get_P :3260, f2_get_B_xy :3291), the selected solver for each of the n_patterns patterns,
+ * the arg-min over patterns on res_norm (strict <, first wins; :185), (R, t) reconstruction
+ * (:3500 / :3542 / :4158) and Euler extraction (:4474).
+ *
+ *   uv        [device] [B, n_total, 2] pixels (u, v); the homogeneous coordinate is 1
+ *   pattern   [device] [n_patterns, n_total, 3] metres, shared by all problems
+ *   point_index [host] n indices into 0..n_total-1 selecting (and ordering) the landmarks the
+ *             solver sees -- the LM_key_list of PNP_SOLVER_LIB.py:156 -- or NULL for all n_total
+ *   K         [host] [3,3] row-major camera matrix (np_K_camera_est)
+ *   params    [host] or NULL for defaults
+ *   R [B,9]  t [B,3]  euler_deg [B,3] = (roll, yaw, pitch)  res_norm [B]      [device], dtype
+ *   iters [B]  best_pattern [B]                                           [device], int32
+ *             (any output pointer may be NULL to skip it)
+ */
+int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n,
+                        const void* uv, const void* pattern, int n_patterns,
+                        const int32_t* point_index, const double* K,
+                        const pnpb200_params* params,
+                        void* R, void* t, void* euler_deg, void* res_norm,
+                        int32_t* iters, int32_t* best_pattern, void* stream);
+
+/*
+ * Same, from HOST buffers (pageable or pinned), chunked and double-buffered through a
+ * caller-created pipeline so that H2D copies, the solve kernel and D2H copies overlap.
+ * This is the call the drop-in PNP_SOLVER.solve_pnp_batch() makes for NumPy inputs and what
+ * bench.py times as `e2e`.  Blocks until the results are in the host buffers.
+ */
+typedef struct pnpb200_pipeline pnpb200_pipeline;
+int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_problems, int n_total,
+                            int n_patterns, int n_streams);
+int pnpb200_pipeline_destroy(pnpb200_pipeline* p);
+int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n,
+                             const void* uv_host, const void* pattern_host,
+                             const int32_t* point_index, const double* K,
+                             const pnpb200_params* params,
+                             void* R, void* t, void* euler_deg, void* res_norm,
+                             int32_t* iters, int32_t* best_pattern);
+
+/*
+ * Euler <-> R, batched on the device.
+ * Replaces get_rotation_matrix_from_Euler (PNP_SOLVER_LIB.py:4442-4472) and
+ * get_Euler_from_rotation_matrix (:4474-4517).  euler = (roll, yaw, pitch).
+ */
+int pnpb200_R_from_euler(int dtype, int64_t B, const void* euler, int is_degree, void* R, void* stream);
+int pnpb200_euler_from_R(int dtype, int64_t B, const void* R, int is_degree, void* euler, void* stream);
+
+/*
+ * Pinhole projection of a pattern, batched.  Replaces perspective_projection (:4532-4557) and
+ * perspective_projection_golden_landmarks (:4586-4621): K (R theta + t) / |z|, optional
+ * rounding to a grid (np.around = half to even).  uvw: [B, n, 3] homogeneous pixels.
+ */
+int pnpb200_project(int dtype, int64_t B, int n, const void* pattern, const double* K,
+                    const void* R, const void* t, int is_quantized, double quantize_q,
+                    void* uvw, void* stream);
+
+/*
+ * Synthetic workload generator, FP64 internally.  Problems b0 .. b0+B-1 of a global
+ * counter-based stream, so a shard reproduces exactly the slice of the unsharded run.
+ *   uv [B,n,2] (dtype)   gt [B,4] = (distance m, roll, pitch, yaw deg) (f64)
+ *   R_gt [B,9], t_gt [B,3] (f64, may be NULL)
+ * Workload definition: random_stress_test.py:246-290 (+ LM_noise_test.py noise).
+ */
+int pnpb200_synth_batch(int dtype, int64_t b0, int64_t B, int n, const void* pattern_f64,
+                        const double* K, const pnpb200_synth* cfg,
+                        void* uv, double* gt, double* R_gt, double* t_gt, void* stream);
+
+/*
+ * Error reporting per problem.  Replaces check_if_the_sample_passed (TEST_TOOLBOX.py:55-62),
+ * cal_LM_error_distances (:252-286), the error fields of compare_result_and_generate_result_dict
+ * (:396-463) and the glue at random_stress_test.py:353-377.  Always FP64 outputs.
+ *   report [B,16]: 0 depth_err(m) 1 roll_err 2 pitch_err 3 yaw_err (deg)
+ *                  4,5 LM_GT avg,max  6,7 predict_LM avg,max  8,9 predict_GT avg,max (x distance_GT)
+ *                  10 t3_est 11 distance_GT 12 roll_est 13 pitch_est 14 yaw_est 15 reserved
+ *   flags [B,4] = depth, roll, pitch, yaw passed;  max_idx [B,3] = landmark index of each max
+ *   bounds [host] 4 doubles (10 cm, 10, 10, 10 deg in the reference)
+ */
+int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const void* uv,
+                         const double* K, const void* R, const void* t, const void* euler_deg,
+                         const double* gt, const double* bounds,
+                         double* report, int32_t* flags, int32_t* max_idx, void* stream);
+
+/*
+ * Error statistics, two passes so that shards can be combined with two small all-reduces
+ * (TEST_TOOLBOX.get_statistic_of_result, TEST_TOOLBOX.py:892-937).
+ *   est, gt: [B] strided views (element stride in doubles) of FP64 device data; gt may be NULL
+ *   class_id: [B] int32 device or NULL (all in class 0); n_class classes
+ *   pass 1 -> sums1 [n_class,4]  = n, sum(est/gt), sum(e), 0            (SUM-reducible)
+ *   pass 2 (given mean[n_class]) -> sums2 [n_class,4] = sum((e-m)^2), sum|e|, sum|e-m|, max|e-m|
+ *                                  (first three SUM-reducible, last MAX-reducible)
+ */
+int pnpb200_stats_pass1(int64_t B, const double* est, int64_t est_stride, const double* gt,
+                        int64_t gt_stride, const int32_t* class_id, int n_class,
+                        double* sums1, void* stream);
+int pnpb200_stats_pass2(int64_t B, const double* est, int64_t est_stride, const double* gt,
+                        int64_t gt_stride, const int32_t* class_id, int n_class,
+                        const double* mean, double* sums2, void* stream);
+
+/*
+ * Ground-truth classification, np.digitize(value, bins) (TEST_TOOLBOX.classify_drpy,
+ * TEST_TOOLBOX.py:239-247): class = number of bins b with b <= value.  values: FP64 device,
+ * element stride in doubles; bins [host], ascending, n_bins <= 32; class_id [B] int32 device.
+ */
+int pnpb200_classify(int64_t B, const double* values, int64_t stride, double scale,
+                     const double* bins, int n_bins, int32_t* class_id, void* stream);
+
+/*
+ * FMA-pipe microbenchmark used by bench.py for the roofline denominator (MEASURED_PEAKS.json
+ * has no FP64/FP32 FMA figure).  Runs `iters` dependent-chain-free FMAs per thread on a full
+ * grid and returns the device-timed rate in FLOP/s (2 per FMA).  Synchronous.
+ */
+int pnpb200_fma_peak(int dtype, int iters, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNPB200_H */

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (read-only, from
+/root/reference/scripts) on seeded inputs.  Run in the build container only; the GPU box has
+no /root/reference, the committed .npz files are what travels.
+
+    python oracle/make_golden.py            # writes tests/golden/, prints oracle-vs-reference diffs
+
+What is stored per case (SURVEY.md section 8c recipe):
+  uv [B,n,2] pixels in pattern key order, pattern [n,3], K, R, t, t3, euler (roll,yaw,pitch),
+  res_norm, iters (counted by wrapping QEKF_get_hx_H / EKF2_get_hx_H on the instance; the
+  linear solvers always run 3), `iters_stable` (same count under the perturbation below), and a per-problem `stable` tag: the reference is re-run with the
+  pixels multiplied by (1 +/- 1e-13) and stable = max(|dR|, |dt|/|t3|) < 1e-10.  LM is not
+  contractive on ~15 % of inputs; parity is only well-posed where stable.
+Inputs follow random_stress_test.py:246-258 draw order from numpy default_rng(seed) and the
+reference's own perspective_projection_golden_landmarks (quantised and exact variants).
+"""
+import contextlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/scripts"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    sys.path.insert(0, REF)
+    warnings.simplefilter("ignore")
+    with contextlib.redirect_stdout(io.StringIO()):
+        import PNP_SOLVER_LIB as PNPS  # noqa
+        import TEST_TOOLBOX as TTBX  # noqa
+    return PNPS, TTBX
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def draw_pose(rng):
+    """random_stress_test.py:246-258"""
+    roll = rng.uniform(-45.0, 45.0, None)
+    pitch = rng.uniform(-45.0, 45.0, None)
+    yaw = rng.uniform(-45.0, 45.0, None)
+    depth = rng.uniform(20, 225, None) / 100.0
+    fov_x = rng.uniform(-45.0, 45.0, None)
+    fov_y = rng.uniform(-45.0, 45.0, None)
+    t = np.zeros((3, 1))
+    t[0, 0] = depth * np.tan(np.deg2rad(fov_x))
+    t[1, 0] = depth * np.tan(np.deg2rad(fov_y))
+    t[2, 0] = depth
+    return roll, pitch, yaw, depth, t
+
+
+def dict_from_uv(keys, uv):
+    return {k: np.array([[uv[i, 0]], [uv[i, 1]], [1.0]]) for i, k in enumerate(keys)}
+
+
+def call_method(solver, method, pts, pattern_np, key_list):
+    """Returns (R, t, t3, roll, yaw, pitch, res_norm, iters)."""
+    counter = {"n": 0}
+    name = {"qeif": "QEKF_get_hx_H", "lm": "EKF2_get_hx_H"}.get(method)
+    if name:
+        orig = getattr(solver, name)
+
+        def wrapped(*a, **k):
+            counter["n"] += 1
+            return orig(*a, **k)
+        setattr(solver, name, wrapped)
+    try:
+        if method == "qeif":
+            r = solver.solve_pnp_QEIF_single_pattern(pts, pattern_np, LM_key_list=key_list)
+        elif method == "lm":
+            r = solver.solve_pnp_LM_single_pattern(pts, pattern_np)
+        elif method == "linear_f2":
+            r = solver.solve_pnp_formulation_2_single_pattern(pts, pattern_np)
+        elif method == "linear_f1":
+            r = solver.solve_pnp_single_pattern(pts, pattern_np)
+        else:
+            raise ValueError(method)
+    finally:
+        if name:
+            delattr(solver, name)
+    iters = counter["n"] if name else 3
+    R, t, t3, roll, yaw, pitch, res = r
+    return (np.array(R), np.array(t).reshape(3), float(t3), float(roll), float(yaw), float(pitch),
+            float(res), iters)
+
+
+def run_case(PNPS, TTBX, tag, method, pattern_dict, key_list, B, seed, quantized, with_stability=True):
+    from pnp_solver_test_b200 import patterns as pt
+    K = pt.default_camera_matrix()
+    solver_gt = quiet(PNPS.PNP_SOLVER, K, [pattern_dict], [1.0], verbose=False)
+    solver = quiet(PNPS.PNP_SOLVER, K, [pattern_dict], [1.0], verbose=False)
+    keys_all = list(pattern_dict.keys())
+    keys = keys_all if key_list is None else list(key_list)
+    pattern_np_full = solver.np_point_3d_pretransfer_dict_list[0]
+    rng = np.random.default_rng(seed)
+    n = len(keys)
+    uv = np.zeros((B, n, 2))
+    gt = np.zeros((B, 4))
+    Rg = np.zeros((B, 3, 3))
+    tg = np.zeros((B, 3))
+    R = np.zeros((B, 3, 3))
+    t = np.zeros((B, 3))
+    eul = np.zeros((B, 3))
+    res = np.zeros(B)
+    iters = np.zeros(B, np.int32)
+    stable = np.ones(B, bool)
+    iters_stable = np.ones(B, bool)
+    sens = np.zeros(B)
+    for b in range(B):
+        roll, pitch, yaw, depth, tt = draw_pose(rng)
+        R_gt = solver_gt.get_rotation_matrix_from_Euler(roll, yaw, pitch, is_degree=True)
+        pts_all = quiet(solver_gt.perspective_projection_golden_landmarks, R_gt, tt, is_quantized=quantized,
+                        is_pretrans_points=False, is_returning_homogeneous_vec=True)
+        uv[b] = np.array([[pts_all[k][0, 0], pts_all[k][1, 0]] for k in keys])
+        gt[b] = (depth, roll, pitch, yaw)
+        Rg[b], tg[b] = R_gt, tt.reshape(3)
+        # the solver sees exactly the n selected points, in `keys` order
+        pts = dict_from_uv(keys, uv[b])
+        pat = {k: pattern_np_full[k] for k in keys}
+        out = quiet(call_method, solver, method, pts, pat, None)
+        R[b], t[b], _, r_, y_, p_, res[b], iters[b] = out
+        eul[b] = (r_, y_, p_)
+        if with_stability:
+            worst = 0.0
+            for sgn in (+1.0, -1.0):
+                pts2 = dict_from_uv(keys, uv[b] * (1.0 + sgn * 1e-13))
+                o2 = quiet(call_method, solver, method, pts2, pat, None)
+                d = max(np.abs(o2[0] - R[b]).max(), np.abs(o2[1] - t[b]).max() / abs(t[b, 2]))
+                worst = max(worst, d)
+                iters_stable[b] &= (o2[7] == iters[b])
+            sens[b] = worst
+            stable[b] = worst < 1e-10
+    P = np.array([pattern_np_full[k].reshape(3) for k in keys])
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), method=method, K=K, pattern=P, uv=uv, gt=gt,
+                        R_gt=Rg, t_gt=tg, R=R, t=t, euler=eul, res_norm=res, iters=iters,
+                        stable=stable, iters_stable=iters_stable, sens=sens, quantized=quantized, seed=seed)
+    return dict(method=method, K=K, pattern=P, uv=uv, R=R, t=t, euler=eul, res_norm=res, iters=iters,
+                stable=stable, iters_stable=iters_stable)
+
+
+def compare_with_oracle(tag, g):
+    from oracle import oracle as orc
+    o = orc.solve_batch(str(g["method"]), g["uv"], g["pattern"], g["K"])
+    st = g["stable"]
+    dR = np.abs(o["R"] - g["R"]).reshape(len(st), -1).max(axis=1)
+    dt = np.abs(o["t"] - g["t"]).max(axis=1) / np.abs(g["t"][:, 2])
+    de = np.abs(o["euler"] - g["euler"]).max(axis=1)
+    dres = np.abs(o["res_norm"] - g["res_norm"]) / np.maximum(np.abs(g["res_norm"]), 1e-6)
+    it_eq = (o["iters"] == g["iters"]) | ~g["iters_stable"]
+    print("%-28s B=%4d stable=%4d | stable: dR %.2e dt %.2e deuler %.2e dres %.2e | iters equal %d/%d | unstable max dR %.2e"
+          % (tag, len(st), st.sum(), dR[st].max(), dt[st].max(), de[st].max(), dres[st].max(), it_eq.sum(),
+             len(st), dR[~st].max() if (~st).any() else 0.0))
+
+
+def euler_fixture():
+    """GT_R_t_dict.pkl -> plain npz: (roll, yaw, pitch) from the file-name labels under the sign
+    rules of m1_result_analysis.py:186-194,:236-238, with the stored np_R_GT / np_t_GT_est."""
+    import math
+    import joblib
+    d = joblib.load(os.path.join(REF, "ground_truth_R_t", "GT_R_t_dict.pkl"))
+    names, rpy, Rs, ts, dist = [], [], [], [], []
+    for name, v in d.items():
+        s = name.split('_')
+        # pkl keys are the data file names without their leading token:
+        # <left|right>_<roll>_<distance cm>_pitch_<u|d>_<pitch>_yaw_<yaw>_image
+        raw_roll, raw_pitch, raw_yaw = float(s[1]), float(s[5]), float(s[7])
+        roll = (math.fmod(raw_roll + 180.0, 360.0) - 180.0) * -1.0
+        pitch = raw_pitch * (-1.0 if s[4] == 'd' else 1.0)
+        yaw = raw_yaw * (-1.0 if s[0] == 'left' else 1.0)
+        names.append(name)
+        rpy.append((roll, yaw, pitch))
+        Rs.append(v["np_R_GT"])
+        ts.append(v["np_t_GT_est"].reshape(3))
+        dist.append(float(s[2]))
+    np.savez_compressed(os.path.join(OUT, "euler_fixture.npz"), roll_yaw_pitch_deg=np.array(rpy),
+                        R=np.array(Rs), t=np.array(ts), distance_cm=np.array(dist))
+    return len(names)
+
+
+def solve_pnp_case(PNPS, TTBX, tag, B, seed):
+    """solve_pnp() itself with two patterns (arg-min res_norm, PNP_SOLVER_LIB.py:166-199)."""
+    from pnp_solver_test_b200 import patterns as pt
+    K = pt.default_camera_matrix()
+    pats = [pt.get_golden_pattern("Alexander"), pt.get_golden_pattern("Holly")]
+    solver_gt = quiet(PNPS.PNP_SOLVER, K, pats, [1.0, 1.0], verbose=False)
+    solver = quiet(PNPS.PNP_SOLVER, K, pats, [1.0, 1.0], verbose=False)
+    keys = list(pats[0].keys())
+    rng = np.random.default_rng(seed)
+    uv = np.zeros((B, 15, 2)); R = np.zeros((B, 3, 3)); t = np.zeros((B, 3)); eul = np.zeros((B, 3))
+    res = np.zeros(B); best = np.zeros(B, np.int32); gen = np.zeros(B, np.int32)
+    for b in range(B):
+        roll, pitch, yaw, depth, tt = draw_pose(rng)
+        gen[b] = b % 2
+        solver_gt.set_golden_pattern_id(int(gen[b]))
+        R_gt = solver_gt.get_rotation_matrix_from_Euler(roll, yaw, pitch, is_degree=True)
+        pts = quiet(solver_gt.perspective_projection_golden_landmarks, R_gt, tt, is_quantized=True)
+        uv[b] = np.array([[pts[k][0, 0], pts[k][1, 0]] for k in keys])
+        Rb, tb, t3, r_, y_, p_, rn = quiet(solver.solve_pnp, pts)
+        R[b], t[b], eul[b], res[b] = Rb, np.array(tb).reshape(3), (r_, y_, p_), rn
+        best[b] = solver.current_golden_pattern_id
+    P = np.array([[solver.np_point_3d_pretransfer_dict_list[i][k].reshape(3) for k in keys] for i in range(2)])
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, patterns=P, uv=uv, R=R, t=t, euler=eul,
+                        res_norm=res, best_pattern=best, generating_pattern=gen,
+                        key_index=np.array([keys.index(k) for k in pt.LM_KEY_LIST_6], np.int32))
+    from oracle import oracle as orc
+    idx = [keys.index(k) for k in pt.LM_KEY_LIST_6]
+    o = orc.solve_batch("qeif", uv[:, idx], P[:, idx], K)
+    print("%-28s B=%4d | dR %.2e dt %.2e | best_pattern equal %d/%d"
+          % (tag, B, np.abs(o["R"] - R).max(), np.abs(o["t"] - t).max(), (o["best_pattern"] == best).sum(), B))
+
+def stress_report_case(PNPS, TTBX, tag, B, seed):
+    """The body of random_stress_test.py:226-410 (pose draw, quantised projection, solve_pnp,
+    pass flags, compare_result_and_generate_result_dict) plus the statistics block of
+    TEST_TOOLBOX.data_analysis_and_saving (:1070-1112), all by the unmodified reference."""
+    from pnp_solver_test_b200 import patterns as pt
+    K = pt.default_camera_matrix()
+    pats = [pt.get_golden_pattern("Alexander")]
+    solver_gt = quiet(PNPS.PNP_SOLVER, K, pats, [1.0], verbose=False)
+    solver = quiet(PNPS.PNP_SOLVER, K, pats, [1.0], verbose=False)
+    cls_param = quiet(TTBX.get_classification_parameters, drpy_class_format="drpy_expand")
+    keys = list(pats[0].keys())
+    rng = np.random.default_rng(seed)
+    uv = np.zeros((B, 15, 2)); gt = np.zeros((B, 4))
+    R = np.zeros((B, 3, 3)); t = np.zeros((B, 3)); eul = np.zeros((B, 3)); res = np.zeros(B)
+    rep = np.zeros((B, 16)); flags = np.zeros((B, 4), np.int32); midx = np.zeros((B, 3), np.int32)
+    depth_class = np.zeros(B, np.int32)
+    result_list = []
+    for b in range(B):
+        roll, pitch, yaw, depth, tt = draw_pose(rng)
+        R_gt0 = solver_gt.get_rotation_matrix_from_Euler(roll, yaw, pitch, is_degree=True)
+        solver_gt.set_golden_pattern_id(0)
+        pts = quiet(solver_gt.perspective_projection_golden_landmarks, R_gt0, tt, is_quantized=True,
+                    is_pretrans_points=False, is_returning_homogeneous_vec=True)
+        uv[b] = np.array([[pts[k][0, 0], pts[k][1, 0]] for k in keys])
+        gt[b] = (depth, roll, pitch, yaw)
+        dist_cm = depth * 100.0
+        cd = {c: quiet(TTBX.classify_drpy, cls_param, v, class_name=n_)
+              for c, v, n_ in (("distance", dist_cm, "depth"), ("roll", roll, "roll"), ("pitch", pitch, "pitch"), ("yaw", yaw, "yaw"))}
+        depth_class[b] = cls_param["labels"]["depth"].index(cd["distance"])
+        Rb, tb, t3, r_, y_, p_, rn = quiet(solver.solve_pnp, pts)
+        R[b], t[b], eul[b], res[b] = Rb, np.array(tb).reshape(3), (r_, y_, p_), rn
+        R_gt = solver.get_rotation_matrix_from_Euler(roll, yaw, pitch, is_degree=True)   # :365
+        distance_GT = dist_cm * 0.01
+        t_gt_est = (tb / t3) * distance_GT                                               # :367-368
+        pass_list, pass_count = TTBX.check_if_the_sample_passed((t3 * 100.0, r_, p_, y_), (dist_cm, roll, pitch, yaw),
+                                                                (10.0, 10.0, 10.0, 10.0))
+        flags[b] = [int(bool(x)) for x in pass_list]
+        data_idx = dict(idx=b, file_name="x", distance=dist_cm, roll=roll, pitch=pitch, yaw=yaw, **{"class": cd})
+        rd, _, _ = quiet(TTBX.compare_result_and_generate_result_dict, solver, data_idx, Rb, tb, (r_, p_, y_), R_gt, t_gt_est,
+                         (roll, pitch, yaw), rn, 4 - pass_count, pass_count, pass_list, np_point_image_dict=pts, verbose=False)
+        result_list.append(rd)
+        rep[b] = [rd["depth_err"], rd["roll_err"], rd["pitch_err"], rd["yaw_err"],
+                  rd["LM_GT_error_average_normalize"], rd["LM_GT_error_max_normalize"],
+                  rd["predict_LM_error_average_normalize"], rd["predict_LM_error_max_normalize"],
+                  rd["predict_GT_error_average_normalize"], rd["predict_GT_error_max_normalize"],
+                  rd["t3_est"], rd["distance_GT"], rd["roll_est"], rd["pitch_est"], rd["yaw_est"], 0.0]
+        midx[b] = [keys.index(rd["LM_GT_error_max_key"]) if rd["LM_GT_error_max_key"] else -1,
+                   keys.index(rd["predict_LM_error_max_key"]) if rd["predict_LM_error_max_key"] else -1,
+                   keys.index(rd["predict_GT_error_max_key"]) if rd["predict_GT_error_max_key"] else -1]
+    # statistics, unscaled (unit_scale=1): n, m_ratio, mean, stddev, max_dev, MAE_2_GT, MAE_2_mean
+    def stat(lst, ek, gk):
+        if len(lst) == 0:
+            return [np.nan] * 7
+        d = quiet(TTBX.get_statistic_of_result, lst, data_est_key=ek, data_GT_key=gk, unit="u", unit_scale=1.0, verbose=False)
+        return [d["n_data"], d["m_ratio"], d["mean(u)"], d["stddev(u)"], d["max_dev(u)"], d["MAE_2_GT(u)"], d["MAE_2_mean(u)"]]
+    quant = (("depth", "t3_est", "distance_GT"), ("roll", "roll_est", "roll_GT"), ("pitch", "pitch_est", "pitch_GT"),
+             ("yaw", "yaw_est", "yaw_GT"))
+    labels = cls_param["labels"]["depth"]
+    cdict = quiet(TTBX.get_classified_result, result_list, class_name='distance', approval_func=None)
+    stats_all = np.array([stat(result_list, ek, gk) for _, ek, gk in quant], dtype=np.float64)
+    stats_depth = np.array([[stat(cdict.get(lb, []), ek, gk) for lb in labels] for _, ek, gk in quant], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, pattern=pt.pattern_array(pats[0]), uv=uv, gt=gt, R=R, t=t,
+                        euler=eul, res_norm=res, report=rep, flags=flags, max_idx=midx, depth_class=depth_class,
+                        stats_all=stats_all, stats_by_depth=stats_depth,
+                        key_index=np.array([keys.index(k) for k in pt.LM_KEY_LIST_6], np.int32))
+    from oracle import oracle as orc
+    o = orc.report_batch(pt.pattern_array(pats[0]), uv, K, R, t, eul, gt)
+    print("%-28s B=%4d | report max abs diff %.2e | flags equal %s | max_idx equal %s | pass rate %.3f"
+          % (tag, B, np.abs(o["report"] - rep).max(), (o["flags"] == flags).all(), (o["max_idx"] == midx).all(),
+             flags.all(axis=1).mean()))
+    sa = np.array([orc.stats_of(rep[:, 10 + 0], rep[:, 11])] + [orc.stats_of(rep[:, 12 + i], gt[:, 1 + i]) for i in range(3)])
+    print("%-28s stats_all max rel diff %.2e" % ("", np.abs(sa - stats_all).max()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    PNPS, TTBX = load_reference()
+    from pnp_solver_test_b200 import patterns as pt
+    alex = pt.get_golden_pattern("Alexander")
+    p68, p1024 = pt.synthetic_pattern(68), pt.synthetic_pattern(1024)
+    small = "--small" in sys.argv
+    B = 32 if small else 192
+    cases = []
+    for q, qn in ((True, "q"), (False, "x")):
+        cases += [
+            ("qeif_n6_%s" % qn, "qeif", alex, pt.LM_KEY_LIST_6, B, 42, q),
+            ("qeif_n15_%s" % qn, "qeif", alex, None, B, 43, q),
+            ("qeif_n68_%s" % qn, "qeif", p68, None, B // 2, 44, q),
+            ("lm_n15_%s" % qn, "lm", alex, None, B, 45, q),
+            ("lm_n68_%s" % qn, "lm", p68, None, B, 46, q),
+            ("linear_f2_n15_%s" % qn, "linear_f2", alex, None, B, 47, q),
+            ("linear_f2_n68_%s" % qn, "linear_f2", p68, None, B // 2, 48, q),
+            ("linear_f1_n15_%s" % qn, "linear_f1", alex, None, B, 49, q),
+            ("linear_f1_n68_%s" % qn, "linear_f1", p68, None, B // 2, 50, q),
+        ]
+    cases += [
+        ("qeif_n1024_q", "qeif", p1024, None, 3, 51, True),
+        ("lm_n1024_q", "lm", p1024, None, 12, 52, True),
+        ("linear_f2_n1024_q", "linear_f2", p1024, None, 12, 53, True),
+        ("linear_f1_n1024_q", "linear_f1", p1024, None, 12, 54, True),
+    ]
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
+    for tag, method, pat, keys, b, seed, q in cases:
+        if only and not any(o in tag for o in only):
+            continue
+        g = run_case(PNPS, TTBX, tag, method, pat, keys, b, seed, q)
+        compare_with_oracle(tag, g)
+    if not only or "solve_pnp" in only:
+        solve_pnp_case(PNPS, TTBX, "solve_pnp_two_patterns", 96, 60)
+    if not only or "stress_report" in only:
+        stress_report_case(PNPS, TTBX, "stress_report", 256, 61)
+    if not only or "euler" in only:
+        print("euler fixture:", euler_fixture(), "vectors")
+
+
+if __name__ == "__main__":
+    main()

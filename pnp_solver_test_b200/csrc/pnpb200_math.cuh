@@ -1,0 +1,232 @@
+// pnpb200_math.cuh -- register-resident small linear algebra for the per-problem systems.
+//
+// Everything here is fully unrolled with compile-time indices so that the 6x6 / 12x12
+// normal equations, their factorisations and the 3x3 SVD live in registers (no local
+// memory).  Templated on the scalar type: double = parity mode, float = FP32 mode.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace pnpb200 {
+
+#define PNP_DEV __device__ __forceinline__
+
+// packed upper-triangular storage of a symmetric N x N matrix, row-major: (i,j), i <= j
+template <int N>
+PNP_DEV constexpr int sidx(int i, int j) { return i * N - (i * (i - 1)) / 2 + (j - i); }
+template <int N>
+PNP_DEV constexpr int sym(int i, int j) { return i <= j ? sidx<N>(i, j) : sidx<N>(j, i); }
+
+template <typename T> PNP_DEV T t_sqrt(T x);
+template <> PNP_DEV double t_sqrt<double>(double x) { return sqrt(x); }
+template <> PNP_DEV float t_sqrt<float>(float x) { return sqrtf(x); }
+template <typename T> PNP_DEV T t_abs(T x) { return x < T(0) ? -x : x; }
+template <typename T> PNP_DEV T t_fma(T a, T b, T c);
+template <> PNP_DEV double t_fma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> PNP_DEV float t_fma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+// In-place LDL^T of a packed SPD matrix.  On return A(j,j) holds 1/d_j and A(j,i), i > j,
+// holds L(i,j).  Replaces the SVD-based np.linalg.pinv of the reference for the SPD systems
+// (PNP_SOLVER_LIB.py:2675, :2887, :2924); equivalent to ~1e-13 at the condition numbers seen
+// (SURVEY.md 7.3).
+template <typename T, int N>
+PNP_DEV void ldlt_factor(T (&A)[N * (N + 1) / 2])
+{
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const T inv = T(1) / A[sidx<N>(j, j)];
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            const T lij = A[sidx<N>(j, i)] * inv;
+#pragma unroll
+            for (int r = i; r < N; ++r) A[sidx<N>(i, r)] = t_fma(-lij, A[sidx<N>(j, r)], A[sidx<N>(i, r)]);
+            A[sidx<N>(j, i)] = lij;
+        }
+        A[sidx<N>(j, j)] = inv;
+    }
+}
+
+// Solve (L D L^T) x = b in place, A as left by ldlt_factor.
+template <typename T, int N>
+PNP_DEV void ldlt_solve(const T (&A)[N * (N + 1) / 2], T (&b)[N])
+{
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) b[i] = t_fma(-A[sidx<N>(j, i)], b[j], b[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) b[j] *= A[sidx<N>(j, j)];
+#pragma unroll
+    for (int j = N - 1; j >= 0; --j) {
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) b[j] = t_fma(-A[sidx<N>(j, i)], b[i], b[j]);
+    }
+}
+
+// Explicit inverse of a packed SPD matrix (in place): A <- A^-1 = L^-T D^-1 L^-1.
+template <typename T, int N>
+PNP_DEV void spd_inverse(T (&A)[N * (N + 1) / 2])
+{
+    ldlt_factor<T, N>(A);
+    // X = L^-1 (unit lower).  Stored in the strictly-upper slots: X(i,j), i > j, at (j,i).
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int i = j + 1; i < N; ++i) {
+            // X(i,j) = -( L(i,j) + sum_{k=j+1}^{i-1} L(i,k) X(k,j) ); L(i,k) is still needed for
+            // later columns j' < k, so write X over column j only (slots (j, *)), which are the
+            // L(*, j) entries -- those are consumed for this (i, j) before being overwritten
+            // only if we go in increasing i and read L(i,j) first.
+            T acc = A[sidx<N>(j, i)];
+#pragma unroll
+            for (int k = j + 1; k < i; ++k) acc = t_fma(A[sidx<N>(k, i)], A[sidx<N>(j, k)], acc);
+            A[sidx<N>(j, i)] = -acc;
+        }
+    }
+    // Ainv(i,j) = sum_{k >= j} X(k,i) X(k,j) / d_k  for i <= j, with X(k,k) = 1.
+    T out[N * (N + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+            // k = j term: X(j,i) * 1 / d_j   (X(j,i) = 1 if i == j)
+            T acc = (i == j) ? A[sidx<N>(j, j)] : A[sidx<N>(i, j)] * A[sidx<N>(j, j)];
+#pragma unroll
+            for (int k = j + 1; k < N; ++k)
+                acc = t_fma(A[sidx<N>(i, k)] * A[sidx<N>(j, k)], A[sidx<N>(k, k)], acc);
+            out[sidx<N>(i, j)] = acc;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < N * (N + 1) / 2; ++e) A[e] = out[e];
+}
+
+// y = S x for packed symmetric S
+template <typename T, int N>
+PNP_DEV void sym_matvec(const T (&S)[N * (N + 1) / 2], const T (&x)[N], T (&y)[N])
+{
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc = t_fma(S[sym<N>(i, j)], x[j], acc);
+        y[i] = acc;
+    }
+}
+
+// 3x3 singular value decomposition by one-sided (Hestenes) Jacobi, enough of it to form
+//   Rproj = U diag(1, 1, det(U V^T)) V^T   and   sigma_max
+// as EKF2_reconstruct_R_t_m1 does with np.linalg.svd / det / norm(ord=2)
+// (PNP_SOLVER_LIB.py:3509-3518, :3530).  G row-major.  det(U V^T) = sign(det G) when G is
+// non-singular, and the -1 lands on the smallest singular value's pair.
+template <typename T>
+PNP_DEV void svd3_project(const T (&G)[9], T (&R)[9], T& sigma_max)
+{
+    T W[9], V[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { W[i] = G[i]; V[i] = T(0); }
+    V[0] = V[4] = V[8] = T(1);
+    const T tol = (sizeof(T) == 8) ? T(2e-16) : T(1e-7);
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        bool rotated = false;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+            const int i = (pr == 2) ? 1 : 0;
+            const int j = (pr == 0) ? 1 : 2;
+            T alpha = T(0), beta = T(0), gamma = T(0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                alpha = t_fma(W[k * 3 + i], W[k * 3 + i], alpha);
+                beta = t_fma(W[k * 3 + j], W[k * 3 + j], beta);
+                gamma = t_fma(W[k * 3 + i], W[k * 3 + j], gamma);
+            }
+            if (gamma != T(0) && t_abs(gamma) > tol * t_sqrt(alpha * beta)) {
+                rotated = true;
+                const T zeta = (beta - alpha) / (T(2) * gamma);
+                const T tt = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(T(1) + zeta * zeta));
+                const T c = T(1) / t_sqrt(T(1) + tt * tt), s = c * tt;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const T wi = W[k * 3 + i], wj = W[k * 3 + j];
+                    W[k * 3 + i] = c * wi - s * wj;
+                    W[k * 3 + j] = s * wi + c * wj;
+                    const T vi = V[k * 3 + i], vj = V[k * 3 + j];
+                    V[k * 3 + i] = c * vi - s * vj;
+                    V[k * 3 + j] = s * vi + c * vj;
+                }
+            }
+        }
+        if (!rotated) break;
+    }
+    T sg[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        sg[j] = t_sqrt(W[j] * W[j] + W[3 + j] * W[3 + j] + W[6 + j] * W[6 + j]);
+    const T det = G[0] * (G[4] * G[8] - G[5] * G[7]) - G[1] * (G[3] * G[8] - G[5] * G[6]) +
+                  G[2] * (G[3] * G[7] - G[4] * G[6]);
+    const T D = (det < T(0)) ? T(-1) : T(1);
+    int jmin = 0;
+    if (sg[1] < sg[jmin]) jmin = 1;
+    if (sg[2] < sg[jmin]) jmin = 2;
+    sigma_max = fmax(sg[0], fmax(sg[1], sg[2]));
+#pragma unroll
+    for (int e = 0; e < 9; ++e) R[e] = T(0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const T f = ((j == jmin) ? D : T(1)) / sg[j];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[r * 3 + c] = t_fma(W[r * 3 + j] * f, V[c * 3 + j], R[r * 3 + c]);
+    }
+}
+
+// get_Euler_from_rotation_matrix, PNP_SOLVER_LIB.py:4474-4517; out = (roll, yaw, pitch).
+// Always evaluated in double (the trig is a negligible share; keeps FP32 mode's angles honest).
+PNP_DEV void euler_from_R(const double (&R)[9], bool is_degree, double (&out)[3])
+{
+    const double kPi = 3.14159265358979323846;
+    const double eps = 1e-7;
+    double th1, th2, th3;
+    if (fabs(kPi / 2.0 - asin(fabs(R[7]))) <= eps) {          // gimbal lock (:4482)
+        const double m = -R[7];
+        const double sg = (m > 0.0) ? 1.0 : ((m < 0.0) ? -1.0 : 0.0);
+        th2 = sg * (kPi / 2.0);
+        th3 = 0.0;
+        th1 = atan2(-R[3], R[0]);
+    } else {
+        th1 = atan2(R[1], R[4]);
+        th3 = atan2(R[6], R[8]);
+        const double c1 = cos(th1), c3 = cos(th3);
+        const double c2 = (fabs(c1) > fabs(c3)) ? (R[4] / c1) : (R[8] / c3);
+        th2 = atan2(-R[7], c2);
+    }
+    double roll = th1, pitch = th2, yaw = th3;
+    if (is_degree) {
+        const double k = 180.0 / kPi;
+        roll *= k; yaw *= k; pitch *= k;
+    }
+    out[0] = roll; out[1] = -yaw; out[2] = pitch;
+}
+
+// get_rotation_matrix_from_Euler, PNP_SOLVER_LIB.py:4442-4472 (R = E_roll E_pitch E_yaw, yaw negated)
+PNP_DEV void R_from_euler(double roll, double yaw, double pitch, bool is_degree, double (&R)[9])
+{
+    const double kPi = 3.14159265358979323846;
+    yaw = -yaw;
+    if (is_degree) {
+        const double k = kPi / 180.0;
+        roll *= k; yaw *= k; pitch *= k;
+    }
+    double s1, c1, s2, c2, s3, c3;
+    sincos(roll, &s1, &c1); sincos(yaw, &s2, &c2); sincos(pitch, &s3, &c3);
+    const double e0 = c2, e1 = 0.0, e2 = -s2;
+    const double e3 = s3 * s2, e4 = c3, e5 = s3 * c2;
+    const double e6 = c3 * s2, e7 = -s3, e8 = c3 * c2;
+    R[0] = c1 * e0 + s1 * e3; R[1] = c1 * e1 + s1 * e4; R[2] = c1 * e2 + s1 * e5;
+    R[3] = -s1 * e0 + c1 * e3; R[4] = -s1 * e1 + c1 * e4; R[5] = -s1 * e2 + c1 * e5;
+    R[6] = e6; R[7] = e7; R[8] = e8;
+}
+
+}  // namespace pnpb200

@@ -1,0 +1,537 @@
+// pnpb200_solve.cu -- the hot path: batched PnP solve kernels for sm_100a and their C ABI.
+//
+// Two execution shapes share the solver code in pnpb200_solvers.cuh:
+//
+//  k_solve_thread  one problem per thread.  A CTA is ONE warp that owns 32 consecutive
+//                  problems: their [32, n_total, 2] pixel rows are one contiguous span of HBM,
+//                  read with coalesced 16-byte vector loads, normalised with K^-1 on the way
+//                  (f2_get_B_xy, PNP_SOLVER_LIB.py:3291-3312) and staged in shared memory
+//                  point-major / problem-minor with an odd row stride, so that the 14 solver
+//                  passes read them conflict-free.  The pattern sits in shared memory too and
+//                  is read as a warp-wide broadcast.  All normal equations, factorisations and
+//                  SO(3) work stay in the thread's registers; no shuffles are needed at all.
+//                  Several such one-warp CTAs are resident per SM, so staging of one overlaps
+//                  the FP64 work of the others.
+//  k_solve_warp    one problem per warp for large n (n = 1024): lanes stride over the points
+//                  with coalesced vector loads straight from global memory (L1/L2 resident
+//                  across iterations), partial sums are combined with shuffle butterflies.
+//
+// No tensor cores on purpose: the per-problem systems are 6x6 / 12x12.
+#include <mutex>
+#include <string.h>
+#include <vector>
+
+#include "pnpb200_common.cuh"
+#include "pnpb200_solvers.cuh"
+
+namespace pnpb200 {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* where, cudaError_t e)
+{
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int get_device_props(DeviceProps* out)
+{
+    static std::mutex mu;
+    static std::vector<DeviceProps> cache;
+    int dev = 0;
+    PNP_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    for (const DeviceProps& p : cache)
+        if (p.device == dev) { *out = p; return PNPB200_OK; }
+    DeviceProps p;
+    p.device = dev;
+    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    size_t free_b = 0;
+    PNP_CUDA_OK(cudaMemGetInfo(&free_b, &p.total_mem));
+    cache.push_back(p);
+    *out = p;
+    return PNPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel arguments
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct SolveArgs {
+    const T* uv;            // [B, n_total, 2]
+    const T* pattern;       // [P, n_total, 3]
+    const int32_t* idx;     // [n] device, or nullptr
+    long long B;
+    int n_total, n, n_patterns;
+    double kinv[6];         // first two rows of K^-1
+    SolverPrm<T> prm;
+    T* R; T* t; T* euler; T* res;
+    int32_t* iters; int32_t* best;
+};
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+// normalised correspondences of one problem, staged in shared memory (thread mapping)
+template <typename T>
+struct PtsShared {
+    const T* base;   // &sB[problem slot]
+    int stride;      // row stride (problems per tile + 1)
+    PNP_DEV void get(int i, T& bx, T& by) const
+    {
+        bx = base[(2 * i) * stride];
+        by = base[(2 * i + 1) * stride];
+    }
+};
+
+// raw pixels of one problem in global memory, normalised on the fly (warp mapping)
+template <typename T>
+struct PtsGlobal {
+    const T* row;          // &uv[b, 0, 0]
+    const int32_t* idx;    // shared-memory copy of the selection, or nullptr
+    T k00, k01, k02, k10, k11, k12;
+    PNP_DEV void get(int i, T& bx, T& by) const
+    {
+        const int j = idx ? idx[i] : i;
+        const typename Vec2<T>::type p = __ldg(reinterpret_cast<const typename Vec2<T>::type*>(row) + j);
+        bx = k00 * p.x + k01 * p.y + k02;
+        by = k10 * p.x + k11 * p.y + k12;
+    }
+};
+
+// Pattern constants (PNP_PATC per pattern) by one warp: M0, m0, n and G = (D^T D)^-1.
+// Accumulated in double whatever T is (they are shared by every problem of the launch).
+template <typename T>
+PNP_DEV void pattern_constants(const T* __restrict__ sP, int n, T* __restrict__ sC, int lane)
+{
+    double acc[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) acc[e] = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double th[3] = { (double)sP[3 * i], (double)sP[3 * i + 1], (double)sP[3 * i + 2] };
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) acc[s3(a, b)] = fma(th[a], th[b], acc[s3(a, b)]);
+            acc[6 + a] += th[a];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) acc[e] = group_sum<32, double>(acc[e]);
+    if (lane == 0) {
+        double G[10];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) G[sidx<4>(a, b)] = acc[s3(a, b)];
+            G[sidx<4>(a, 3)] = acc[6 + a];
+        }
+        G[sidx<4>(3, 3)] = (double)n;
+        spd_inverse<double, 4>(G);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) sC[e] = (T)acc[e];
+        sC[9] = (T)n;
+#pragma unroll
+        for (int e = 0; e < 10; ++e) sC[10 + e] = (T)G[e];
+    }
+}
+
+template <typename T, int METHOD, int LPP, typename Pts>
+PNP_DEV void run_method(const Pts& pts, const T* sP, const T* sC, int n, int sub, const SolverPrm<T>& prm,
+                        Result<T>& out)
+{
+    if (METHOD == PNPB200_METHOD_QEIF)           solve_qeif<T, LPP, Pts>(pts, sP, n, sub, prm, out);
+    else if (METHOD == PNPB200_METHOD_LM)        solve_lm<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
+    else if (METHOD == PNPB200_METHOD_LINEAR_F2) solve_linear_f2<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
+    else                                         solve_linear_f1<T, LPP, Pts>(pts, sP, n, sub, prm, out);
+}
+
+// solve_pnp's loop over patterns with the strict-'<' arg-min on res_norm (:166-199)
+template <typename T, int METHOD, int LPP, typename Pts>
+PNP_DEV void solve_all_patterns(const Pts& pts, const T* sP, const T* sC, int n, int n_patterns, int sub,
+                                const SolverPrm<T>& prm, Result<T>& best, int& best_p)
+{
+    run_method<T, METHOD, LPP, Pts>(pts, sP, sC, n, sub, prm, best);
+    best_p = 0;
+    for (int p = 1; p < n_patterns; ++p) {
+        Result<T> cand;
+        run_method<T, METHOD, LPP, Pts>(pts, sP + (size_t)p * n * 3, sC + p * PNP_PATC, n, sub, prm, cand);
+        if (cand.res < best.res) { best = cand; best_p = p; }
+    }
+}
+
+template <typename T>
+PNP_DEV void write_result(const SolveArgs<T>& a, long long b, const Result<T>& r, int best_p)
+{
+    if (a.R) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a.R[b * 9 + e] = r.R[e];
+    }
+    if (a.t) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a.t[b * 3 + e] = r.t[e];
+    }
+    if (a.euler) {
+        double Rd[9], e3[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rd[e] = (double)r.R[e];
+        euler_from_R(Rd, true, e3);                       // degrees, (roll, yaw, pitch) (:2998)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a.euler[b * 3 + e] = (T)e3[e];
+    }
+    if (a.res) a.res[b] = r.res;
+    if (a.iters) a.iters[b] = r.iters;
+    if (a.best) a.best[b] = best_p;
+}
+
+// shared-memory carve-up common to both kernels: [pattern | constants | (index) | tile]
+template <typename T>
+PNP_DEV void load_pattern(const SolveArgs<T>& a, T* sP, T* sC, int32_t* sIdx, int tid, int nthreads)
+{
+    if (a.idx) {
+        for (int i = tid; i < a.n; i += nthreads) sIdx[i] = a.idx[i];
+        __syncthreads();
+    }
+    for (int e = tid; e < a.n_patterns * a.n * 3; e += nthreads) {
+        const int p = e / (a.n * 3), r = e - p * (a.n * 3), i = r / 3, c = r - 3 * i;
+        const int src = a.idx ? sIdx[i] : i;
+        sP[e] = a.pattern[((size_t)p * a.n_total + src) * 3 + c];
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// one problem per thread; CTA = 1 warp = 32 consecutive problems
+// ------------------------------------------------------------------------------------------
+constexpr int kTileProblems = 32;
+constexpr int kTileStride = kTileProblems + 1;
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ SolveArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sP = reinterpret_cast<T*>(smem_raw);
+    T* sC = sP + (size_t)a.n_patterns * a.n * 3;
+    T* sB = sC + a.n_patterns * PNP_PATC;
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sB + (size_t)2 * a.n * kTileStride);
+    const int lane = threadIdx.x;
+
+    load_pattern<T>(a, sP, sC, sIdx, lane, 32);
+    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
+        for (int p = 0; p < a.n_patterns; ++p) pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
+        __syncwarp();
+    }
+    const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
+    const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
+    typedef typename Vec2<T>::type V2;
+
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long b0 = tile * kTileProblems;
+        // ---- stage + normalise the tile: element e = (problem p, point i), coalesced in HBM
+        const int n = a.n;
+        int p = 0, i = lane;
+        while (i >= n) { i -= n; ++p; }
+        for (; p < kTileProblems;) {
+            long long b = b0 + p;
+            if (b >= a.B) b = a.B - 1;                    // ragged last tile: replicate, never written
+            const int src = a.idx ? sIdx[i] : i;
+            const V2 px = __ldg(reinterpret_cast<const V2*>(a.uv) + (size_t)b * a.n_total + src);
+            sB[(2 * i) * kTileStride + p] = k00 * px.x + k01 * px.y + k02;
+            sB[(2 * i + 1) * kTileStride + p] = k10 * px.x + k11 * px.y + k12;
+            i += 32;
+            while (i >= n) { i -= n; ++p; }
+        }
+        __syncwarp();
+        // ---- solve: lane <-> problem
+        PtsShared<T> pts;
+        pts.base = sB + lane;
+        pts.stride = kTileStride;
+        Result<T> best;
+        int best_p;
+        solve_all_patterns<T, METHOD, 1, PtsShared<T> >(pts, sP, sC, n, a.n_patterns, 0, a.prm, best, best_p);
+        const long long b = b0 + lane;
+        if (b < a.B) write_result<T>(a, b, best, best_p);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// one problem per warp (large n)
+// ------------------------------------------------------------------------------------------
+constexpr int kWarpsPerBlock = 8;
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_solve_warp(const __grid_constant__ SolveArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sP = reinterpret_cast<T*>(smem_raw);
+    T* sC = sP + (size_t)a.n_patterns * a.n * 3;
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sC + a.n_patterns * PNP_PATC);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    load_pattern<T>(a, sP, sC, sIdx, threadIdx.x, blockDim.x);
+    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
+        for (int p = warp; p < a.n_patterns; p += kWarpsPerBlock)
+            pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
+        __syncthreads();
+    }
+    PtsGlobal<T> pts;
+    pts.idx = a.idx ? sIdx : nullptr;
+    pts.k00 = (T)a.kinv[0]; pts.k01 = (T)a.kinv[1]; pts.k02 = (T)a.kinv[2];
+    pts.k10 = (T)a.kinv[3]; pts.k11 = (T)a.kinv[4]; pts.k12 = (T)a.kinv[5];
+    for (long long b = (long long)blockIdx.x * kWarpsPerBlock + warp; b < a.B; b += (long long)gridDim.x * kWarpsPerBlock) {
+        pts.row = a.uv + (size_t)b * a.n_total * 2;
+        Result<T> best;
+        int best_p;
+        solve_all_patterns<T, METHOD, 32, PtsGlobal<T> >(pts, sP, sC, a.n, a.n_patterns, lane, a.prm, best, best_p);
+        if (lane == 0) write_result<T>(a, b, best, best_p);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static SolverPrm<T> make_prm(const pnpb200_params& p)
+{
+    SolverPrm<T> s;
+    s.max_it = p.max_it;
+    s.linear_it = p.linear_it;
+    s.lm_lambda = (T)p.lm_lambda;
+    s.exit_tol = (T)p.exit_tol;
+    // eif_Q_diag = sigma^2 / f^2; eif_Q_pinv = 1 / eif_Q_diag (:2844-2852)
+    s.meas_w = (T)(1.0 / ((p.meas_sigma_px * p.meas_sigma_px) / (p.f_weight * p.f_weight)));
+    s.proc_q = (T)p.proc_q;
+    s.proc_d = (T)p.proc_d;
+    s.sigma0 = (T)(1.0 / p.omega0);
+    s.res_old0 = (T)p.res_old0;
+    return s;
+}
+
+static void fill_default_params(pnpb200_params* p)
+{
+    p->max_it = 14; p->linear_it = 3;
+    p->lm_lambda = 1e-5; p->exit_tol = 1e-2;
+    p->f_weight = 225.68; p->meas_sigma_px = 3.0;
+    p->proc_q = 1e-1; p->proc_d = 1e-2; p->omega0 = 1e-5; p->res_old0 = 1e-7;
+    p->mapping = PNPB200_MAP_AUTO; p->reserved = 0;
+}
+
+template <typename T, int METHOD>
+static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
+{
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc != PNPB200_OK) return rc;
+    const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
+    const size_t idx_bytes = a.idx ? (size_t)a.n * sizeof(int32_t) : 0;
+    const size_t thread_smem = pat_bytes + (size_t)2 * a.n * kTileStride * sizeof(T) + idx_bytes;
+    const size_t warp_smem = pat_bytes + idx_bytes;
+    if (mapping == PNPB200_MAP_AUTO)
+        mapping = ((size_t)a.n * sizeof(T) <= 96 * 8 && thread_smem <= (size_t)dp.max_smem_optin / 2) ? PNPB200_MAP_THREAD
+                                                                                                    : PNPB200_MAP_WARP;
+    if (mapping == PNPB200_MAP_THREAD) {
+        if (thread_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_thread<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
+        const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+        const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
+        k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(a);
+    } else if (mapping == PNPB200_MAP_WARP) {
+        if (warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_warp<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+        int per_sm = 1;
+        PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_warp<T, METHOD>, kWarpsPerBlock * 32, warp_smem));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (a.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const long long cap = (long long)dp.sm_count * per_sm;   // persistent: a multiple of the SM count
+        if (grid > cap) grid = cap;
+        k_solve_warp<T, METHOD><<<(unsigned)grid, kWarpsPerBlock * 32, warp_smem, stream>>>(a);
+    } else {
+        return PNPB200_EINVAL;
+    }
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
+template <typename T>
+static int solve_typed(int method, long long B, int n_total, int n, const void* uv, const void* pattern,
+                       int n_patterns, const int32_t* idx_dev, const double* K, const pnpb200_params& prm,
+                       void* R, void* t, void* euler, void* res, int32_t* iters, int32_t* best, cudaStream_t stream)
+{
+    SolveArgs<T> a;
+    a.uv = (const T*)uv; a.pattern = (const T*)pattern; a.idx = idx_dev;
+    a.B = B; a.n_total = n_total; a.n = n; a.n_patterns = n_patterns;
+    double Kinv[9];
+    host_inv3(K, Kinv);
+    for (int e = 0; e < 6; ++e) a.kinv[e] = Kinv[e];
+    a.prm = make_prm<T>(prm);
+    a.R = (T*)R; a.t = (T*)t; a.euler = (T*)euler; a.res = (T*)res; a.iters = iters; a.best = best;
+    switch (method) {
+    case PNPB200_METHOD_QEIF:      return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);
+    case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
+    case PNPB200_METHOD_LINEAR_F2: return launch_solve<T, PNPB200_METHOD_LINEAR_F2>(a, prm.mapping, stream);
+    case PNPB200_METHOD_LINEAR_F1: return launch_solve<T, PNPB200_METHOD_LINEAR_F1>(a, prm.mapping, stream);
+    default: return PNPB200_EINVAL;
+    }
+}
+
+}  // namespace pnpb200
+
+using namespace pnpb200;
+
+extern "C" {
+
+int pnpb200_version(void) { return PNPB200_VERSION; }
+const char* pnpb200_last_error(void) { return g_last_error; }
+
+int pnpb200_default_params(pnpb200_params* p)
+{
+    if (!p) return PNPB200_EINVAL;
+    fill_default_params(p);
+    return PNPB200_OK;
+}
+
+int pnpb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes)
+{
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc != PNPB200_OK) return rc;
+    if (sm_count) *sm_count = dp.sm_count;
+    if (cc_major) *cc_major = dp.cc_major;
+    if (cc_minor) *cc_minor = dp.cc_minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)dp.total_mem;
+    return PNPB200_OK;
+}
+
+int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
+                        int n_patterns, const int32_t* point_index, const double* K, const pnpb200_params* params,
+                        void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters, int32_t* best_pattern,
+                        void* stream)
+{
+    if (B < 0 || n_total < 1 || n < 1 || (!point_index && n != n_total) || !uv || !pattern || !K) return PNPB200_EINVAL;
+    if (n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
+    if (method < 0 || method > 3 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
+    if (B == 0) return PNPB200_OK;
+    pnpb200_params prm;
+    if (params) prm = *params; else fill_default_params(&prm);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* idx_dev = nullptr;
+    if (point_index) {
+        for (int i = 0; i < n; ++i)
+            if (point_index[i] < 0 || point_index[i] >= n_total) return PNPB200_EINVAL;
+        PNP_CUDA_OK(cudaMallocAsync((void**)&idx_dev, sizeof(int32_t) * (size_t)n, st));
+        PNP_CUDA_OK(cudaMemcpyAsync(idx_dev, point_index, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    int rc;
+    if (dtype == PNPB200_DTYPE_F64)
+        rc = solve_typed<double>(method, B, n_total, n, uv, pattern, n_patterns, idx_dev, K, prm, R, t, euler_deg,
+                                 res_norm, iters, best_pattern, st);
+    else
+        rc = solve_typed<float>(method, B, n_total, n, uv, pattern, n_patterns, idx_dev, K, prm, R, t, euler_deg,
+                                res_norm, iters, best_pattern, st);
+    if (idx_dev) cudaFreeAsync(idx_dev, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry point: chunked, multi-stream H2D -> solve -> D2H pipeline
+// ------------------------------------------------------------------------------------------
+struct pnpb200_pipeline {
+    int dtype, n_total, n_patterns, n_streams;
+    int64_t chunk;
+    size_t esz;
+    std::vector<cudaStream_t> streams;
+    std::vector<void*> d_uv, d_R, d_t, d_e, d_res;
+    std::vector<int32_t*> d_it, d_best;
+    void* d_pattern;
+};
+
+int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_problems, int n_total, int n_patterns,
+                            int n_streams)
+{
+    if (!out || chunk_problems < 1 || n_total < 1 || n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
+    if (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32) return PNPB200_EINVAL;
+    if (n_streams < 1) n_streams = 3;
+    pnpb200_pipeline* p = new pnpb200_pipeline();
+    p->dtype = dtype; p->n_total = n_total; p->n_patterns = n_patterns; p->n_streams = n_streams;
+    p->chunk = chunk_problems;
+    p->esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
+    p->d_pattern = nullptr;
+    *out = p;
+    PNP_CUDA_OK(cudaMalloc(&p->d_pattern, p->esz * (size_t)n_patterns * n_total * 3));
+    for (int s = 0; s < n_streams; ++s) {
+        cudaStream_t st;
+        PNP_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        p->streams.push_back(st);
+        void *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr, *e = nullptr, *f = nullptr, *g = nullptr;
+        PNP_CUDA_OK(cudaMalloc(&a, p->esz * (size_t)chunk_problems * n_total * 2)); p->d_uv.push_back(a);
+        PNP_CUDA_OK(cudaMalloc(&b, p->esz * (size_t)chunk_problems * 9)); p->d_R.push_back(b);
+        PNP_CUDA_OK(cudaMalloc(&c, p->esz * (size_t)chunk_problems * 3)); p->d_t.push_back(c);
+        PNP_CUDA_OK(cudaMalloc(&d, p->esz * (size_t)chunk_problems * 3)); p->d_e.push_back(d);
+        PNP_CUDA_OK(cudaMalloc(&e, p->esz * (size_t)chunk_problems)); p->d_res.push_back(e);
+        PNP_CUDA_OK(cudaMalloc(&f, sizeof(int32_t) * (size_t)chunk_problems)); p->d_it.push_back((int32_t*)f);
+        PNP_CUDA_OK(cudaMalloc(&g, sizeof(int32_t) * (size_t)chunk_problems)); p->d_best.push_back((int32_t*)g);
+    }
+    return PNPB200_OK;
+}
+
+int pnpb200_pipeline_destroy(pnpb200_pipeline* p)
+{
+    if (!p) return PNPB200_EINVAL;
+    for (cudaStream_t st : p->streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (void* q : p->d_uv) cudaFree(q);
+    for (void* q : p->d_R) cudaFree(q);
+    for (void* q : p->d_t) cudaFree(q);
+    for (void* q : p->d_e) cudaFree(q);
+    for (void* q : p->d_res) cudaFree(q);
+    for (int32_t* q : p->d_it) cudaFree(q);
+    for (int32_t* q : p->d_best) cudaFree(q);
+    if (p->d_pattern) cudaFree(p->d_pattern);
+    delete p;
+    return PNPB200_OK;
+}
+
+int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, const void* uv_host,
+                             const void* pattern_host, const int32_t* point_index, const double* K,
+                             const pnpb200_params* params, void* R, void* t, void* euler_deg, void* res_norm,
+                             int32_t* iters, int32_t* best_pattern)
+{
+    if (!p || !uv_host || !pattern_host || !K || B < 0) return PNPB200_EINVAL;
+    const size_t esz = p->esz;
+    PNP_CUDA_OK(cudaMemcpyAsync(p->d_pattern, pattern_host, esz * (size_t)p->n_patterns * p->n_total * 3,
+                                cudaMemcpyHostToDevice, p->streams[0]));
+    PNP_CUDA_OK(cudaStreamSynchronize(p->streams[0]));
+    int64_t done = 0;
+    int s = 0;
+    while (done < B) {
+        const int64_t nb = (B - done < p->chunk) ? (B - done) : p->chunk;
+        cudaStream_t st = p->streams[s];
+        const char* src = (const char*)uv_host + esz * (size_t)done * p->n_total * 2;
+        PNP_CUDA_OK(cudaMemcpyAsync(p->d_uv[s], src, esz * (size_t)nb * p->n_total * 2, cudaMemcpyHostToDevice, st));
+        int rc = pnpb200_solve_batch(method, p->dtype, nb, p->n_total, n, p->d_uv[s], p->d_pattern, p->n_patterns,
+                                     point_index, K, params, R ? p->d_R[s] : nullptr, t ? p->d_t[s] : nullptr,
+                                     euler_deg ? p->d_e[s] : nullptr, res_norm ? p->d_res[s] : nullptr,
+                                     iters ? p->d_it[s] : nullptr, best_pattern ? p->d_best[s] : nullptr, st);
+        if (rc != PNPB200_OK) return rc;
+        if (R) PNP_CUDA_OK(cudaMemcpyAsync((char*)R + esz * (size_t)done * 9, p->d_R[s], esz * (size_t)nb * 9, cudaMemcpyDeviceToHost, st));
+        if (t) PNP_CUDA_OK(cudaMemcpyAsync((char*)t + esz * (size_t)done * 3, p->d_t[s], esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
+        if (euler_deg) PNP_CUDA_OK(cudaMemcpyAsync((char*)euler_deg + esz * (size_t)done * 3, p->d_e[s], esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
+        if (res_norm) PNP_CUDA_OK(cudaMemcpyAsync((char*)res_norm + esz * (size_t)done, p->d_res[s], esz * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (iters) PNP_CUDA_OK(cudaMemcpyAsync(iters + done, p->d_it[s], sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (best_pattern) PNP_CUDA_OK(cudaMemcpyAsync(best_pattern + done, p->d_best[s], sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        done += nb;
+        s = (s + 1) % p->n_streams;
+        // a stream's buffers are reused n_streams chunks later; stream order protects them
+    }
+    for (cudaStream_t st : p->streams) PNP_CUDA_OK(cudaStreamSynchronize(st));
+    return PNPB200_OK;
+}
+
+}  // extern "C"

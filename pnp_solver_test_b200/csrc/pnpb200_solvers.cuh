@@ -1,0 +1,572 @@
+// pnpb200_solvers.cuh -- the four per-problem solvers as device functions.
+//
+// Each solver is written once against a "points" accessor (normalised correspondences of ONE
+// problem) and a lanes-per-problem constant LPP:
+//   LPP = 1   one problem per thread (32 problems per warp); sums stay in the thread.
+//   LPP = 32  one problem per warp; every lane accumulates a strided subset of the points and
+//             the partial normal equations are combined with an xor-butterfly of warp shuffles,
+//             which leaves bitwise-identical sums in all lanes, so the small dense solves and the
+//             convergence decision are warp-uniform by construction.
+//
+// Math follows SURVEY.md Appendix A; reference line numbers are cited at each step
+// (scripts/PNP_SOLVER_LIB.py unless noted).  The O(n) work per iteration is restricted to the
+// terms that actually depend on the state: every block of J^T J that is the state-independent
+// moment of the correspondences times a power of gamma is accumulated once per problem.
+#pragma once
+#include "pnpb200_math.cuh"
+
+namespace pnpb200 {
+
+template <typename T>
+struct SolverPrm {
+    int max_it, linear_it;
+    T lm_lambda, exit_tol, meas_w, proc_q, proc_d, sigma0, res_old0;
+};
+
+template <typename T>
+struct Result {
+    T R[9], t[3], res;
+    int iters;
+};
+
+// per-pattern constants kept in shared memory (computed once per CTA)
+//   [0..5] M0 = sum theta theta^T (packed 3x3)   [6..8] m0 = sum theta   [9] n
+//   [10..19] G = (D^T D)^-1, D = [P | 1]  (packed 4x4; f2_get_D_pinv :3283 is G D^T)
+#define PNP_PATC 20
+
+template <int LPP, typename T>
+PNP_DEV T group_sum(T v)
+{
+#pragma unroll
+    for (int m = LPP / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+template <int LPP, typename T, int N>
+PNP_DEV void group_sum_arr(T (&v)[N])
+{
+    if (LPP > 1) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = group_sum<LPP, T>(v[k]);
+    }
+}
+
+PNP_DEV constexpr int s3(int a, int b) { return sym<3>(a, b); }
+
+// -------------------------------------------------------------------------------------------
+// block reconstruction of (R, t) from phi = [phi_1(3), phi_2(3), delta_1, delta_2]
+// reconstruct_R_t_block_reconstruction :4158-4364
+// -------------------------------------------------------------------------------------------
+template <typename T>
+PNP_DEV void block_reconstruct(const T (&phi)[8], T (&R)[9], T (&t)[3], T& t3)
+{
+    const T K00 = phi[0], K01 = phi[1], K10 = phi[3], K11 = phi[4];
+    const T k1 = K00 * K00 + K10 * K10;                   // K^T K (:4205-4211)
+    const T k2 = K00 * K01 + K10 * K11;
+    const T k3 = K01 * K01 + K11 * K11;
+    const T Dd = (k1 - k3) * (k1 - k3) + T(4) * k2 * k2;  // :4215
+    const T gamma2 = T(0.5) * ((k1 + k3) + t_sqrt(Dd));
+    const T gamma = t_sqrt(gamma2);
+    const T e_se = t_sqrt(gamma2 - k1);                   // :4230
+    const T sgn = (k2 > T(0)) ? T(1) : ((k2 < T(0)) ? T(-1) : T(0));   // np.sign
+    const T d_se = -sgn * t_sqrt(gamma2 - k3);            // :4233
+    const T detK = K00 * K11 - K01 * K10;
+    const T ds0 = (K11 * e_se - K10 * d_se) / detK;       // inv(K^T) beta (:4242)
+    const T ds1 = (-K01 * e_se + K00 * d_se) / detK;
+    const T c = detK / gamma;                             // :4247
+    const T a0 = -(c * ds0), a1 = -(c * ds1);             // :4249
+    const T sim = a0 * phi[2] + a1 * phi[5];              // :4261
+    const T se = (sim < T(0)) ? T(-1) : T(1);             // :4266
+    const T ig = T(1) / gamma;
+    R[0] = K00 / gamma; R[1] = K01 / gamma; R[2] = (se * a0) / gamma;
+    R[3] = K10 / gamma; R[4] = K11 / gamma; R[5] = (se * a1) / gamma;
+    R[6] = (se * e_se) / gamma; R[7] = (se * d_se) / gamma; R[8] = c / gamma;   // :4326-4340
+    t3 = ig;                                              // :4357
+    t[0] = phi[6] * t3; t[1] = phi[7] * t3; t[2] = t3;    // :4360
+}
+
+// -------------------------------------------------------------------------------------------
+// QEIF -- solve_pnp_QEIF_single_pattern :2771-3025, QEKF_get_hx_H :3902-3983,
+//         QEKF_reconstruct_R_t_m1 :3542-3609
+// -------------------------------------------------------------------------------------------
+template <typename T>
+PNP_DEV void qekf_phi(const T (&x)[6], T (&p1)[3], T (&p2)[3], T (&p3)[3], T& gamma)
+{
+    const T qr = x[0], qi = x[1], qj = x[2], qk = x[3];
+    const T nq = t_sqrt(qr * qr + qi * qi + qj * qj + qk * qk);
+    gamma = nq * nq;                                      // (np.linalg.norm(q))**2 (:3918)
+    const T qii = qi * qi, qjj = qj * qj, qkk = qk * qk;
+    const T qij = qi * qj, qjk = qj * qk, qik = qi * qk;
+    const T qri = qr * qi, qrj = qr * qj, qrk = qr * qk;
+    p1[0] = gamma - 2 * (qjj + qkk); p1[1] = 2 * (qij - qrk); p1[2] = 2 * (qik + qrj);   // :3934
+    p2[0] = 2 * (qij + qrk); p2[1] = gamma - 2 * (qii + qkk); p2[2] = 2 * (qjk - qri);   // :3935
+    p3[0] = 2 * (qik - qrj); p3[1] = 2 * (qjk + qri); p3[2] = gamma - 2 * (qii + qjj);   // :3936
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, int n, int sub,
+                        const SolverPrm<T>& prm, Result<T>& out)
+{
+    T x[6] = { T(1), T(0), T(0), T(0), T(0), T(0) };      // :2831-2833
+    T Sig[21];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) Sig[e] = T(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Sig[sidx<6>(i, i)] = prm.sigma0;   // pinv(1e-5 I) (:2836-2837)
+    T res_old = prm.res_old0, res = T(1e5);
+    bool done = false;
+    int iters = 0;
+    const T w = prm.meas_w;                               // 1 / (9 / f^2) (:2844-2852)
+    const T nT = T(n);
+
+    for (int it = 0; it < prm.max_it; ++it) {
+        if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
+        else          { if (done) break; }
+        // ---- predict: Omega = pinv(Sigma + R) (:2887), zeta = Omega x (:2889)
+        T Om[21];
+#pragma unroll
+        for (int e = 0; e < 21; ++e) Om[e] = Sig[e];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Om[sidx<6>(i, i)] += (i < 4) ? prm.proc_q : prm.proc_d;
+        spd_inverse<T, 6>(Om);
+        T zeta[6];
+        sym_matvec<T, 6>(Om, x, zeta);
+        // ---- measurement model at x (:3902-3983)
+        T p1[3], p2[3], p3[3], gamma;
+        qekf_phi<T>(x, p1, p2, p3, gamma);
+        const T r2 = 2 * x[0], i2 = 2 * x[1], j2 = 2 * x[2], k2 = 2 * x[3];
+        const T Q1[12] = { r2, i2, -j2, -k2, -k2, j2, i2, -r2, j2, k2, r2, i2 };     // :3945
+        const T Q2[12] = { k2, j2, i2, r2, r2, -i2, j2, -k2, -i2, -r2, k2, j2 };     // :3949
+        const T Q3[12] = { -j2, k2, -r2, i2, i2, r2, k2, j2, r2, -i2, -j2, k2 };     // :3953
+        T qq[10], qd1[4], qd2[4], hv[6], res2 = T(0);
+#pragma unroll
+        for (int e = 0; e < 10; ++e) qq[e] = T(0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { qd1[e] = T(0); qd2[e] = T(0); }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) hv[e] = T(0);
+        for (int i = sub; i < n; i += LPP) {
+            const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+            T bx, by;
+            pts.get(i, bx, by);
+            const T P1 = th0 * p1[0] + th1 * p1[1] + th2 * p1[2];
+            const T P2 = th0 * p2[0] + th1 * p2[1] + th2 * p2[2];
+            const T P3 = th0 * p3[0] + th1 * p3[1] + th2 * p3[2];
+            const T dzx = bx - (P1 - bx * P3 + x[4]);     // z - hx (:3969, :2905)
+            const T dzy = by - (P2 - by * P3 + x[5]);     // :3970
+            T Hx[4], Hy[4];
+            T hxq = x[4], hyq = x[5];                     // (H x) rows: Hq . q + delta
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const T a1 = th0 * Q1[c] + th1 * Q1[4 + c] + th2 * Q1[8 + c];
+                const T a2 = th0 * Q2[c] + th1 * Q2[4 + c] + th2 * Q2[8 + c];
+                const T a3 = th0 * Q3[c] + th1 * Q3[4 + c] + th2 * Q3[8 + c];
+                Hx[c] = a1 - bx * a3;                     // :3979
+                Hy[c] = a2 - by * a3;                     // :3980
+                hxq = t_fma(Hx[c], x[c], hxq);
+                hyq = t_fma(Hy[c], x[c], hyq);
+            }
+            const T vx = dzx + hxq, vy = dzy + hyq;       // z - hx + H x (:2898)
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                for (int b = a; b < 4; ++b)
+                    qq[sidx<4>(a, b)] = t_fma(Hx[a], Hx[b], t_fma(Hy[a], Hy[b], qq[sidx<4>(a, b)]));
+                qd1[a] += Hx[a];
+                qd2[a] += Hy[a];
+                hv[a] = t_fma(Hx[a], vx, t_fma(Hy[a], vy, hv[a]));
+            }
+            hv[4] += vx; hv[5] += vy;
+            res2 = t_fma(dzx, dzx, t_fma(dzy, dzy, res2));
+        }
+        group_sum_arr<LPP>(qq); group_sum_arr<LPP>(qd1); group_sum_arr<LPP>(qd2); group_sum_arr<LPP>(hv);
+        res2 = group_sum<LPP>(res2);
+        // ---- update: Omega += H^T Q^-1 H, zeta += H^T Q^-1 (z - hx + H x) (:2896-2898)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = a; b < 4; ++b) Om[sidx<6>(a, b)] = t_fma(w, qq[sidx<4>(a, b)], Om[sidx<6>(a, b)]);
+            Om[sidx<6>(a, 4)] = t_fma(w, qd1[a], Om[sidx<6>(a, 4)]);
+            Om[sidx<6>(a, 5)] = t_fma(w, qd2[a], Om[sidx<6>(a, 5)]);
+        }
+        Om[sidx<6>(4, 4)] = t_fma(w, nT, Om[sidx<6>(4, 4)]);
+        Om[sidx<6>(5, 5)] = t_fma(w, nT, Om[sidx<6>(5, 5)]);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) zeta[a] = t_fma(w, hv[a], zeta[a]);
+        const T res_new = t_sqrt(res2);                   // :2905-2907
+        // ---- x = pinv(Omega) zeta (:2924-2925)
+        spd_inverse<T, 6>(Om);
+        T xn[6];
+        sym_matvec<T, 6>(Om, zeta, xn);
+        if (!done) {
+#pragma unroll
+            for (int e = 0; e < 21; ++e) Sig[e] = Om[e];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) x[e] = xn[e];
+            res = res_new;
+            ++iters;
+            const T ratio = (res - res_old) / res_old;    // :2945
+            res_old = res;
+            if (t_abs(ratio) < prm.exit_tol) done = true; // :2952
+        }
+    }
+    // ---- QEKF_reconstruct_R_t_m1 :3590-3605
+    T p1[3], p2[3], p3[3], gamma;
+    qekf_phi<T>(x, p1, p2, p3, gamma);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out.R[k] = p1[k] / gamma; out.R[3 + k] = p2[k] / gamma; out.R[6 + k] = p3[k] / gamma; }
+    const T t3 = T(1) / gamma;
+    out.t[0] = x[4] * t3; out.t[1] = x[5] * t3; out.t[2] = t3;
+    out.res = res;
+    out.iters = iters;
+}
+
+// -------------------------------------------------------------------------------------------
+// LM -- solve_pnp_LM_single_pattern :2567-2769, EKF2_get_hx_H :3718-3836,
+//       EKF2_reconstruct_R_t_m1 :3500-3540
+// state x = [u1(3), u2(3), u3(3), delta_1, delta_2, gamma]
+// -------------------------------------------------------------------------------------------
+// A += row row^T for a constraint row whose only non-zeros are va at block ba and vb at block bb
+template <typename T, int BA, int BB>
+PNP_DEV void add_outer2(T (&A)[78], T (&g)[12], const T (&va)[3], const T (&vb)[3], T e)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+            A[sidx<12>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<12>(BA + a, BA + b)]);
+            A[sidx<12>(BB + a, BB + b)] = t_fma(vb[a], vb[b], A[sidx<12>(BB + a, BB + b)]);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            A[sidx<12>(BA + a, BB + b)] = t_fma(va[a], vb[b], A[sidx<12>(BA + a, BB + b)]);
+        g[BA + a] = t_fma(va[a], e, g[BA + a]);
+        g[BB + a] = t_fma(vb[a], e, g[BB + a]);
+    }
+}
+template <typename T, int BA>
+PNP_DEV void add_outer1(T (&A)[78], T (&g)[12], const T (&va)[3], T e)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+            A[sidx<12>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<12>(BA + a, BA + b)]);
+        g[BA + a] = t_fma(va[a], e, g[BA + a]);
+    }
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                      const SolverPrm<T>& prm, Result<T>& out)
+{
+    constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
+    T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2619-2624
+
+    // ---- state-independent moments of this problem's correspondences (once)
+    //      Mx = sum bx th th^T, My = sum by th th^T, Mw = sum (bx^2+by^2) th th^T,
+    //      mx = sum bx th, my = sum by th
+    T Mx[6], My[6], Mw[6], mx[3], my[3];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { Mx[e] = T(0); My[e] = T(0); Mw[e] = T(0); }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { mx[e] = T(0); my[e] = T(0); }
+    for (int i = sub; i < n; i += LPP) {
+        const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
+        T bx, by;
+        pts.get(i, bx, by);
+        const T ww = bx * bx + by * by;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) {
+                const T m = th[a] * th[b];
+                Mx[s3(a, b)] = t_fma(bx, m, Mx[s3(a, b)]);
+                My[s3(a, b)] = t_fma(by, m, My[s3(a, b)]);
+                Mw[s3(a, b)] = t_fma(ww, m, Mw[s3(a, b)]);
+            }
+            mx[a] = t_fma(bx, th[a], mx[a]);
+            my[a] = t_fma(by, th[a], my[a]);
+        }
+    }
+    group_sum_arr<LPP>(Mx); group_sum_arr<LPP>(My); group_sum_arr<LPP>(Mw);
+    group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my);
+
+    T res = T(1e5);
+    for (int it = 0; it < prm.max_it; ++it) {             // :2642, fixed count, no exit test
+        const T gam = x[GG], d1 = x[D1], d2 = x[D2];
+        // ---- state-dependent sums over the correspondences
+        T sg1[3], sg2[3], sg3[3], r1[3], r2[3], r3[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { sg1[e] = sg2[e] = sg3[e] = r1[e] = r2[e] = r3[e] = T(0); }
+        T s1 = T(0), s2 = T(0), sgg = T(0), q1 = T(0), q2 = T(0), qg = T(0), rr = T(0);
+        for (int i = sub; i < n; i += LPP) {
+            const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
+            T bx, by;
+            pts.get(i, bx, by);
+            const T a = th[0] * x[0] + th[1] * x[1] + th[2] * x[2];
+            const T b = th[0] * x[3] + th[1] * x[4] + th[2] * x[5];
+            const T c = th[0] * x[6] + th[1] * x[7] + th[2] * x[8];
+            const T g1 = a - bx * c, g2 = b - by * c;     // hu1_bar, hu2_bar (:3738-3741)
+            const T rx = bx - (gam * g1 + d1);            // z - hx (:3750, :2679)
+            const T ry = by - (gam * g2 + d2);
+            const T w3 = bx * g1 + by * g2, v3 = bx * rx + by * ry;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                sg1[k] = t_fma(th[k], g1, sg1[k]); sg2[k] = t_fma(th[k], g2, sg2[k]); sg3[k] = t_fma(th[k], w3, sg3[k]);
+                r1[k] = t_fma(th[k], rx, r1[k]);   r2[k] = t_fma(th[k], ry, r2[k]);   r3[k] = t_fma(th[k], v3, r3[k]);
+            }
+            s1 += g1; s2 += g2; sgg = t_fma(g1, g1, t_fma(g2, g2, sgg));
+            q1 += rx; q2 += ry; qg = t_fma(g1, rx, t_fma(g2, ry, qg));
+            rr = t_fma(rx, rx, t_fma(ry, ry, rr));
+        }
+        group_sum_arr<LPP>(sg1); group_sum_arr<LPP>(sg2); group_sum_arr<LPP>(sg3);
+        group_sum_arr<LPP>(r1); group_sum_arr<LPP>(r2); group_sum_arr<LPP>(r3);
+        s1 = group_sum<LPP>(s1); s2 = group_sum<LPP>(s2); sgg = group_sum<LPP>(sgg);
+        q1 = group_sum<LPP>(q1); q2 = group_sum<LPP>(q2); qg = group_sum<LPP>(qg); rr = group_sum<LPP>(rr);
+        res = t_sqrt(rr);                                 // res_norm of the state BEFORE the update (:2681)
+
+        // ---- A = J^T J + lambda I (:2666-2667), g = J^T (z - hx) (:2684)
+        T A[78], g[12];
+        const T gg2 = gam * gam;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) {
+                const T m0 = gg2 * sC[s3(a, b)];
+                A[sidx<12>(U1 + a, U1 + b)] = m0;
+                A[sidx<12>(U2 + a, U2 + b)] = m0;
+                A[sidx<12>(U3 + a, U3 + b)] = gg2 * Mw[s3(a, b)];
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                A[sidx<12>(U1 + a, U2 + b)] = T(0);
+                A[sidx<12>(U1 + a, U3 + b)] = -gg2 * Mx[s3(a, b)];
+                A[sidx<12>(U2 + a, U3 + b)] = -gg2 * My[s3(a, b)];
+            }
+            A[sidx<12>(U1 + a, D1)] = gam * sC[6 + a]; A[sidx<12>(U1 + a, D2)] = T(0); A[sidx<12>(U1 + a, GG)] = gam * sg1[a];
+            A[sidx<12>(U2 + a, D1)] = T(0); A[sidx<12>(U2 + a, D2)] = gam * sC[6 + a]; A[sidx<12>(U2 + a, GG)] = gam * sg2[a];
+            A[sidx<12>(U3 + a, D1)] = -gam * mx[a]; A[sidx<12>(U3 + a, D2)] = -gam * my[a]; A[sidx<12>(U3 + a, GG)] = -gam * sg3[a];
+            g[U1 + a] = gam * r1[a]; g[U2 + a] = gam * r2[a]; g[U3 + a] = -gam * r3[a];
+        }
+        A[sidx<12>(D1, D1)] = sC[9]; A[sidx<12>(D1, D2)] = T(0); A[sidx<12>(D1, GG)] = s1;
+        A[sidx<12>(D2, D2)] = sC[9]; A[sidx<12>(D2, GG)] = s2;
+        A[sidx<12>(GG, GG)] = sgg;
+        g[D1] = q1; g[D2] = q2; g[GG] = qg;
+        // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones)
+        {
+            const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
+            const T u11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+            const T u22 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+            const T u33 = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2];
+            const T u13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
+            const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
+            const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+            const T n1 = t_sqrt(u11), n2 = t_sqrt(u22), n3 = t_sqrt(u33);
+            const T nu2[3] = { -u2[0], -u2[1], -u2[2] }, nu3[3] = { -u3[0], -u3[1], -u3[2] };
+            add_outer2<T, U1, U3>(A, g, u3, u1, T(0) - u13);          // u1.u3 = 0
+            add_outer2<T, U2, U3>(A, g, u3, u2, T(0) - u23);          // u2.u3 = 0
+            add_outer2<T, U1, U2>(A, g, u2, u1, T(0) - u12);          // u1.u2 = 0
+            add_outer2<T, U1, U3>(A, g, u1, nu3, T(0) - (u11 - u33)); // rows use u, not 2u (:3808)
+            add_outer2<T, U2, U3>(A, g, u2, nu3, T(0) - (u22 - u33));
+            add_outer2<T, U1, U2>(A, g, u1, nu2, T(0) - (u11 - u22));
+            const T h1 = T(1) / (T(2) * n1), h2 = T(1) / (T(2) * n2), h3 = T(1) / (T(2) * n3);
+            const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
+            const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
+            const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
+            add_outer1<T, U1>(A, g, j1, T(1) - n1);
+            add_outer1<T, U2>(A, g, j2, T(1) - n2);
+            add_outer1<T, U3>(A, g, j3, T(1) - n3);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) A[sidx<12>(i, i)] += prm.lm_lambda;
+        // ---- x += pinv(A) g (:2675, :2702)
+        ldlt_factor<T, 12>(A);
+        ldlt_solve<T, 12>(A, g);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) x[i] += g[i];
+    }
+    // ---- EKF2_reconstruct_R_t_m1 :3500-3540
+    T G[9], smax;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) G[e] = x[e];
+    svd3_project<T>(G, out.R, smax);
+    const T t3 = T(1) / (smax * x[GG]);                   // :3530-3533
+    out.t[0] = x[D1] * t3; out.t[1] = x[D2] * t3; out.t[2] = t3;
+    out.res = res;
+    out.iters = prm.max_it;
+}
+
+// -------------------------------------------------------------------------------------------
+// Linear stage, formulation 2 -- solve_pnp_formulation_2_single_pattern :693-953,
+// helpers :3274-3375.  D^+ B = G (D^T B) with the pattern-constant G = (D^T D)^-1, so the
+// per-problem work is the 20 moments of (bx, by) against [theta theta^T, theta, 1].
+// -------------------------------------------------------------------------------------------
+template <typename T>
+PNP_DEV void g4_apply(const T* __restrict__ G, const T (&v)[4], T (&o)[4])
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = t_fma(G[sym<4>(i, j)], v[j], acc);
+        o[i] = acc;
+    }
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_linear_f2(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                             const SolverPrm<T>& prm, Result<T>& out)
+{
+    T Sx[6], Sy[6], sx[3], sy[3], s0x = T(0), s0y = T(0);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { Sx[e] = T(0); Sy[e] = T(0); }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { sx[e] = T(0); sy[e] = T(0); }
+    for (int i = sub; i < n; i += LPP) {
+        const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
+        T bx, by;
+        pts.get(i, bx, by);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) {
+                const T m = th[a] * th[b];
+                Sx[s3(a, b)] = t_fma(bx, m, Sx[s3(a, b)]);
+                Sy[s3(a, b)] = t_fma(by, m, Sy[s3(a, b)]);
+            }
+            sx[a] = t_fma(bx, th[a], sx[a]);
+            sy[a] = t_fma(by, th[a], sy[a]);
+        }
+        s0x += bx; s0y += by;
+    }
+    group_sum_arr<LPP>(Sx); group_sum_arr<LPP>(Sy); group_sum_arr<LPP>(sx); group_sum_arr<LPP>(sy);
+    s0x = group_sum<LPP>(s0x); s0y = group_sum<LPP>(s0y);
+
+    const T* G = sC + 10;
+    T v0x[4], v0y[4], Mxm[12], Mym[12];                   // :3314-3328
+    {
+        const T bxv[4] = { sx[0], sx[1], sx[2], s0x }, byv[4] = { sy[0], sy[1], sy[2], s0y };
+        g4_apply<T>(G, bxv, v0x);
+        g4_apply<T>(G, byv, v0y);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const T cx[4] = { Sx[s3(0, c)], Sx[s3(1, c)], Sx[s3(2, c)], sx[c] };
+            const T cy[4] = { Sy[s3(0, c)], Sy[s3(1, c)], Sy[s3(2, c)], sy[c] };
+            T ox[4], oy[4];
+            g4_apply<T>(G, cx, ox);
+            g4_apply<T>(G, cy, oy);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { Mxm[k * 3 + c] = ox[k]; Mym[k * 3 + c] = oy[k]; }
+        }
+    }
+    T phi3[3] = { T(0), T(0), T(1) };                     // :758
+    T res = T(30);
+    const int nit = prm.linear_it < 1 ? 1 : prm.linear_it;
+    for (int it = 0; it < nit; ++it) {
+        T phi[8], t3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                     // :3337
+            const T px = v0x[k] + (Mxm[k * 3] * phi3[0] + Mxm[k * 3 + 1] * phi3[1] + Mxm[k * 3 + 2] * phi3[2]);
+            const T py = v0y[k] + (Mym[k * 3] * phi3[0] + Mym[k * 3 + 1] * phi3[1] + Mym[k * 3 + 2] * phi3[2]);
+            if (k < 3) { phi[k] = px; phi[3 + k] = py; } else { phi[6] = px; phi[7] = py; }
+        }
+        block_reconstruct<T>(phi, out.R, out.t, t3);      // :862
+        if (it == nit - 1) {
+            // f2_cal_res_all with the phi rebuilt from (R, t) and the OLD phi_3 (:868-877, :3368)
+            T pxn[4], pyn[4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { pxn[k] = out.R[k] / t3; pyn[k] = out.R[3 + k] / t3; }
+            pxn[3] = out.t[0] / t3; pyn[3] = out.t[1] / t3;
+            T rx2 = T(0), ry2 = T(0);
+            for (int i = sub; i < n; i += LPP) {
+                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+                T bx, by;
+                pts.get(i, bx, by);
+                const T db = T(1) + (th0 * phi3[0] + th1 * phi3[1] + th2 * phi3[2]);
+                const T dx = th0 * pxn[0] + th1 * pxn[1] + th2 * pxn[2] + pxn[3];
+                const T dy = th0 * pyn[0] + th1 * pyn[1] + th2 * pyn[2] + pyn[3];
+                const T ex = bx * db - dx, ey = by * db - dy;
+                rx2 = t_fma(ex, ex, rx2); ry2 = t_fma(ey, ey, ry2);
+            }
+            rx2 = group_sum<LPP>(rx2); ry2 = group_sum<LPP>(ry2);
+            const T nx = t_sqrt(rx2), ny = t_sqrt(ry2);
+            res = t_sqrt(nx * nx + ny * ny);              // :3374
+        }
+        const T it3 = T(1) / t3;                          // update_phi_3_est_m2 :4002-4010
+#pragma unroll
+        for (int k = 0; k < 3; ++k) phi3[k] = it3 * out.R[6 + k];
+    }
+    out.res = res;
+    out.iters = nit;
+}
+
+// -------------------------------------------------------------------------------------------
+// Linear stage, formulation 1 -- solve_pnp_single_pattern :205-430, helpers :3031-3111.
+// A(phi_3) has the x rows acting on (phi_1, delta_1) and the y rows on (phi_2, delta_2) with the
+// SAME 2n/2 x 4 block, so pinv(A) B is two 4x4 normal-equation solves sharing one matrix.
+// -------------------------------------------------------------------------------------------
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_linear_f1(const Pts& pts, const T* __restrict__ sP, int n, int sub,
+                             const SolverPrm<T>& prm, Result<T>& out)
+{
+    T phi3[3] = { T(0), T(0), T(1) };
+    T res = T(30);
+    const int nit = prm.linear_it < 1 ? 1 : prm.linear_it;
+    const T eps = T(1e-7);
+    for (int it = 0; it < nit; ++it) {
+        T N[10], bxv[4], byv[4];
+#pragma unroll
+        for (int e = 0; e < 10; ++e) N[e] = T(0);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { bxv[e] = T(0); byv[e] = T(0); }
+        for (int i = sub; i < n; i += LPP) {
+            const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+            T bx, by;
+            pts.get(i, bx, by);
+            T Delta = th0 * phi3[0] + th1 * phi3[1] + th2 * phi3[2] + T(1);   // get_Delta_i :3031-3046
+            if (t_abs(Delta) <= eps) Delta = (Delta < T(0)) ? -eps : eps;
+            const T a[4] = { th0 / Delta, th1 / Delta, th2 / Delta, T(1) / Delta };     // get_A_i :3048-3062
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+#pragma unroll
+                for (int q = p; q < 4; ++q) N[sidx<4>(p, q)] = t_fma(a[p], a[q], N[sidx<4>(p, q)]);
+                bxv[p] = t_fma(a[p], bx, bxv[p]);
+                byv[p] = t_fma(a[p], by, byv[p]);
+            }
+        }
+        group_sum_arr<LPP>(N); group_sum_arr<LPP>(bxv); group_sum_arr<LPP>(byv);
+        ldlt_factor<T, 4>(N);                             // phi = pinv(A) B (:262)
+        ldlt_solve<T, 4>(N, bxv);
+        ldlt_solve<T, 4>(N, byv);
+        const T phi[8] = { bxv[0], bxv[1], bxv[2], byv[0], byv[1], byv[2], bxv[3], byv[3] };
+        T t3;
+        block_reconstruct<T>(phi, out.R, out.t, t3);      // :365
+        if (it == nit - 1) {                              // res = B - A phi_new (:381-387), A from the old phi_3
+            T pn[8];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { pn[k] = out.R[k] / t3; pn[3 + k] = out.R[3 + k] / t3; }
+            pn[6] = out.t[0] / t3; pn[7] = out.t[1] / t3;
+            T r2 = T(0);
+            for (int i = sub; i < n; i += LPP) {
+                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+                T bx, by;
+                pts.get(i, bx, by);
+                T Delta = th0 * phi3[0] + th1 * phi3[1] + th2 * phi3[2] + T(1);
+                if (t_abs(Delta) <= eps) Delta = (Delta < T(0)) ? -eps : eps;
+                const T a0 = th0 / Delta, a1 = th1 / Delta, a2 = th2 / Delta, a3 = T(1) / Delta;
+                const T ex = bx - (a0 * pn[0] + a1 * pn[1] + a2 * pn[2] + a3 * pn[6]);
+                const T ey = by - (a0 * pn[3] + a1 * pn[4] + a2 * pn[5] + a3 * pn[7]);
+                r2 = t_fma(ex, ex, t_fma(ey, ey, r2));
+            }
+            r2 = group_sum<LPP>(r2);
+            res = t_sqrt(r2);
+        }
+        const T it3 = T(1) / t3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) phi3[k] = it3 * out.R[6 + k];
+    }
+    out.res = res;
+    out.iters = nit;
+}
+
+}  // namespace pnpb200

@@ -1,0 +1,175 @@
+"""Batched workload, error reporting and error statistics around the solve (SURVEY.md 8a rows
+a14-a16, 8e): device-side synthetic inputs, per-problem error report, and the statistics of
+TEST_TOOLBOX.get_statistic_of_result as two reducible passes so that problem shards on
+different GPUs combine with two tiny all-reduces (NCCL over NVLink; gloo in CPU tests).
+
+The solve path itself has no inter-GPU traffic: problems are sharded by global index.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr
+from .solver import _dtype_code, _k_host, _stream_ptr
+
+# TEST_TOOLBOX.get_classification_parameters("drpy_expand") (TEST_TOOLBOX.py:133-162)
+CLASS_BINS = {
+    "depth": [30.0 + 20.0 * i for i in range(11)],     # cm; labels 20, 40, ..., 240
+    "roll": [-35.0, -15.0, 15.0, 35.0],
+    "pitch": [-23.0, -8.0, 8.0, 23.0],
+    "yaw": [-30.0, -10.0, 10.0, 30.0],
+}
+CLASS_LABELS = {
+    "depth": [str(20 * (i + 1)) for i in range(12)],
+    "roll": ["-45", "-25", "0", "25", "45"],
+    "pitch": ["-30", "-15", "0", "15", "30"],
+    "yaw": ["-40", "-20", "0", "20", "40"],
+}
+STAT_KEYS = ("n_data", "m_ratio", "mean", "stddev", "max_dev", "MAE_2_GT", "MAE_2_mean")
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous range of the global problem index owned by `rank`."""
+    base, rem = divmod(int(total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def synth_batch(b0, B, pattern, K, cfg=None, dtype=torch.float64, device=None, want_pose=False):
+    """Problems b0..b0+B-1 of the global counter-based stream (pnpb200_synth_batch).
+
+    pattern: [n,3] array-like in metres.  Returns dict(uv [B,n,2] dtype, gt [B,4] f64 =
+    (distance m, roll, pitch, yaw deg)[, R_gt [B,3,3], t_gt [B,3]])."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    pat = torch.as_tensor(np.ascontiguousarray(np.asarray(pattern, dtype=np.float64)), device=device)
+    n = int(pat.shape[0])
+    uv = torch.empty((B, n, 2), dtype=dtype, device=device)
+    gt = torch.empty((B, 4), dtype=torch.float64, device=device)
+    Rg = torch.empty((B, 3, 3), dtype=torch.float64, device=device) if want_pose else None
+    tg = torch.empty((B, 3), dtype=torch.float64, device=device) if want_pose else None
+    Kh, Kp = _k_host(K)
+    with torch.cuda.device(device):
+        check(lib.pnpb200_synth_batch(C.c_int(_dtype_code(dtype)), C.c_int64(int(b0)), C.c_int64(int(B)), C.c_int(n),
+                                      ptr(pat), Kp, C.byref(cfg) if cfg is not None else None, ptr(uv),
+                                      C.cast(ptr(gt), C.POINTER(C.c_double)),
+                                      C.cast(ptr(Rg), C.POINTER(C.c_double)) if want_pose else None,
+                                      C.cast(ptr(tg), C.POINTER(C.c_double)) if want_pose else None,
+                                      _stream_ptr(device)), "pnpb200_synth_batch")
+    out = dict(uv=uv, gt=gt)
+    if want_pose:
+        out["R_gt"], out["t_gt"] = Rg, tg
+    return out
+
+
+def report_batch(pattern, uv, K, R, t, euler, gt, bounds=(10.0, 10.0, 10.0, 10.0)):
+    """Per-problem error report (pnpb200_report_batch): dict(report [B,16] f64, flags [B,4] int32,
+    max_idx [B,3] int32).  Column meaning: include/pnpb200.h.  pattern [n,3], uv [B,n,2]: every
+    landmark of the pattern, as in compare_result_and_generate_result_dict (TEST_TOOLBOX.py:291)."""
+    dev = uv.device
+    pattern = torch.as_tensor(pattern, device=dev).to(uv.dtype).contiguous()
+    B, n = int(uv.shape[0]), int(uv.shape[1])
+    rep = torch.empty((B, _lib.REPORT_WIDTH), dtype=torch.float64, device=dev)
+    flags = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    midx = torch.empty((B, 3), dtype=torch.int32, device=dev)
+    Kh, Kp = _k_host(K)
+    bd = (C.c_double * 4)(*[float(b) for b in bounds])
+    gt = gt.to(torch.float64).contiguous()
+    with torch.cuda.device(dev):
+        check(lib.pnpb200_report_batch(C.c_int(_dtype_code(uv.dtype)), C.c_int64(B), C.c_int(n), ptr(pattern), ptr(uv.contiguous()),
+                                       Kp, ptr(R.contiguous()), ptr(t.contiguous()), ptr(euler.contiguous()),
+                                       C.cast(ptr(gt), C.POINTER(C.c_double)), bd,
+                                       C.cast(ptr(rep), C.POINTER(C.c_double)),
+                                       C.cast(ptr(flags), C.POINTER(C.c_int32)), C.cast(ptr(midx), C.POINTER(C.c_int32)),
+                                       _stream_ptr(dev)), "pnpb200_report_batch")
+    return dict(report=rep, flags=flags, max_idx=midx)
+
+
+def classify(values, bins, scale=1.0):
+    """np.digitize(values*scale, bins) on the device (TEST_TOOLBOX.classify_drpy, :239-247).
+    values: 1-D (possibly strided) FP64 CUDA tensor view."""
+    assert values.dtype == torch.float64 and values.dim() == 1
+    B = int(values.shape[0])
+    cls = torch.empty((B,), dtype=torch.int32, device=values.device)
+    bn = (C.c_double * len(bins))(*[float(b) for b in bins])
+    with torch.cuda.device(values.device):
+        check(lib.pnpb200_classify(C.c_int64(B), C.cast(ptr(values), C.POINTER(C.c_double)), C.c_int64(values.stride(0) if B else 1),
+                                   C.c_double(scale), bn, C.c_int(len(bins)), C.cast(ptr(cls), C.POINTER(C.c_int32)),
+                                   _stream_ptr(values.device)), "pnpb200_classify")
+    return cls
+
+
+def _all_reduce(t, op, group):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=op, group=group)
+
+
+def reduce_phase1(s1, group=None):
+    """all_reduce(SUM) of the pass-1 sums [n_class,4] = (n, sum est/gt, sum e, 0); returns the
+    global per-class error mean.  Works on any backend (NCCL on GPUs, gloo in CPU tests)."""
+    import torch.distributed as dist
+    _all_reduce(s1, dist.ReduceOp.SUM, group)
+    return (s1[:, 2] / s1[:, 0]).contiguous()
+
+
+def reduce_phase2(s2, group=None):
+    """pass-2 sums [n_class,4] = (sum (e-m)^2, sum |e|, sum |e-m|, max |e-m|): SUM the first
+    three columns, MAX the last."""
+    import torch.distributed as dist
+    sm = s2[:, :3].contiguous()
+    mx = s2[:, 3].contiguous()
+    _all_reduce(sm, dist.ReduceOp.SUM, group)
+    _all_reduce(mx, dist.ReduceOp.MAX, group)
+    return torch.cat([sm, mx[:, None]], dim=1)
+
+
+def finalize_stats(s1, s2):
+    """(n, m_ratio, mean, stddev [population], max_dev, MAE_2_GT, MAE_2_mean) per class
+    (TEST_TOOLBOX.py:907-915, :928-935)."""
+    n = s1[:, 0]
+    return torch.stack([n, s1[:, 1] / n, s1[:, 2] / n, torch.sqrt(s2[:, 0] / n), s2[:, 3], s2[:, 1] / n, s2[:, 2] / n], dim=1)
+
+
+def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=True):
+    """get_statistic_of_result (TEST_TOOLBOX.py:892-937) per class, over ALL ranks' shards.
+
+    est, gt: 1-D FP64 CUDA views (strided allowed) of this rank's shard; class_id int32 or None.
+    Two phases: all_reduce(SUM) of [n, sum est/gt, sum e] -> global means;
+    all_reduce(SUM) of [sum (e-m)^2, sum |e|, sum |e-m|] and all_reduce(MAX) of max |e-m|.
+    Returns a float64 CPU tensor [n_class, 7] in STAT_KEYS order (NaN rows for empty classes)."""
+    dev = est.device
+    B = int(est.shape[0])
+    dp = lambda x: None if x is None else C.cast(ptr(x), C.POINTER(C.c_double))
+    s1 = torch.empty((n_class, 4), dtype=torch.float64, device=dev)
+    cid = None if class_id is None else C.cast(ptr(class_id), C.POINTER(C.c_int32))
+    es = est.stride(0) if B else 1
+    gs = (gt.stride(0) if B else 1) if gt is not None else 0
+    with torch.cuda.device(dev):
+        check(lib.pnpb200_stats_pass1(C.c_int64(B), dp(est), C.c_int64(es), dp(gt), C.c_int64(gs), cid, C.c_int(n_class),
+                                      dp(s1), _stream_ptr(dev)), "pnpb200_stats_pass1")
+    mean = reduce_phase1(s1, group) if distributed else (s1[:, 2] / s1[:, 0]).contiguous()
+    mean = torch.nan_to_num(mean).contiguous()
+    s2 = torch.empty((n_class, 4), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.pnpb200_stats_pass2(C.c_int64(B), dp(est), C.c_int64(es), dp(gt), C.c_int64(gs), cid, C.c_int(n_class),
+                                      dp(mean), dp(s2), _stream_ptr(dev)), "pnpb200_stats_pass2")
+    if distributed:
+        s2 = reduce_phase2(s2, group)
+    return finalize_stats(s1, s2).cpu()
+
+
+def error_statistics(report, gt, group=None, distributed=True):
+    """The statistics block of TEST_TOOLBOX.data_analysis_and_saving (:1070-1346) for the four
+    reported quantities, for class 'all' and per GT-depth class.  report: [B,16] from
+    report_batch; gt [B,4].  Returns {quantity: {'all': stats[7], 'by_depth': stats[12,7]}}."""
+    out = {}
+    cls = classify(gt[:, 0], CLASS_BINS["depth"], scale=100.0)
+    # (estimate column, GT source): depth compares t3_est with distance_GT (:1118), angles est vs GT
+    cols = {"depth": (report[:, 10], report[:, 11]), "roll": (report[:, 12], gt[:, 1]),
+            "pitch": (report[:, 13], gt[:, 2]), "yaw": (report[:, 14], gt[:, 3])}
+    for name, (e, g) in cols.items():
+        out[name] = dict(all=statistics(e, g, None, 1, group, distributed)[0],
+                         by_depth=statistics(e, g, cls, len(CLASS_LABELS["depth"]), group, distributed))
+    return out

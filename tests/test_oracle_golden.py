@@ -1,0 +1,79 @@
+"""Pin the CPU oracle (oracle/pnp_oracle.c) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by oracle/make_golden.py in the build container) and against the
+reference's only own fixture (GT_R_t_dict.pkl -> euler_fixture.npz)."""
+import numpy as np
+import pytest
+
+from conftest import SOLVER_GOLDENS, compare_solutions, load_golden
+from oracle import oracle as orc
+
+
+@pytest.mark.parametrize("name", SOLVER_GOLDENS)
+def test_oracle_matches_reference_solver(name):
+    g = load_golden(name)
+    o = orc.solve_batch(str(g["method"]), g["uv"], g["pattern"], g["K"])
+    stats = compare_solutions(o, g, mask=g["stable"], iters_mask=g["iters_stable"])
+    # LM is chaotic on part of its inputs; the stable fraction must be what the
+    # survey measured, otherwise the tag (and the contract) is meaningless.
+    assert g["stable"].mean() > (0.7 if str(g["method"]) == "lm" else 0.999), stats
+
+
+def test_oracle_solve_pnp_two_patterns():
+    g = load_golden("solve_pnp_two_patterns")
+    idx = g["key_index"]
+    o = orc.solve_batch("qeif", g["uv"][:, idx], g["patterns"][:, idx], g["K"])
+    assert (o["best_pattern"] == g["best_pattern"]).all()
+    assert np.abs(o["R"] - g["R"]).max() < 1e-9 and np.abs(o["t"] - g["t"]).max() < 1e-9
+    assert np.abs(o["res_norm"] - g["res_norm"]).max() < 1e-12
+
+
+def test_oracle_euler_fixture():
+    """The reference's own fixture: 1434 (file-name Euler labels -> np_R_GT) vectors."""
+    g = load_golden("euler_fixture")
+    rpy, R = g["roll_yaw_pitch_deg"], g["R"]
+    for i in range(len(R)):
+        assert np.abs(orc.R_from_euler(*rpy[i], is_degree=True) - R[i]).max() < 1e-12
+        back = np.array(orc.euler_from_R(R[i], is_degree=True))
+        assert np.abs(back - rpy[i]).max() < 1e-9
+    assert np.abs(g["t"][:, 2] - g["distance_cm"] / 100.0).max() < 1e-12
+
+
+def test_oracle_report_and_statistics():
+    g = load_golden("stress_report")
+    o = orc.report_batch(g["pattern"], g["uv"], g["K"], g["R"], g["t"], g["euler"], g["gt"])
+    assert np.abs(o["report"] - g["report"]).max() < 1e-10
+    assert (o["flags"] == g["flags"]).all() and (o["max_idx"] == g["max_idx"]).all()
+    rep, gt = g["report"], g["gt"]
+    cols = [(rep[:, 10], rep[:, 11])] + [(rep[:, 12 + i], gt[:, 1 + i]) for i in range(3)]
+    for q, (e, t) in enumerate(cols):
+        np.testing.assert_allclose(np.array(orc.stats_of(e, t)), g["stats_all"][q], rtol=1e-12, atol=1e-14)
+        for c in range(12):
+            sel = g["depth_class"] == c
+            ref = g["stats_by_depth"][q, c]
+            if sel.sum() == 0:
+                assert np.isnan(ref).all()
+            else:
+                np.testing.assert_allclose(np.array(orc.stats_of(e[sel], t[sel])), ref, rtol=1e-12, atol=1e-14)
+
+
+def test_oracle_synth_is_shard_invariant_and_sane():
+    from pnp_solver_test_b200 import patterns as pt
+    P, K = pt.pattern_array(pt.synthetic_pattern(68)), pt.default_camera_matrix()
+    full = orc.synth(0, 300, P, K)
+    a, b = orc.synth(0, 100, P, K), orc.synth(100, 200, P, K)
+    assert np.array_equal(full["uv"], np.concatenate([a["uv"], b["uv"]]))
+    assert np.array_equal(full["gt"], np.concatenate([a["gt"], b["gt"]]))
+    gt = full["gt"]
+    assert (gt[:, 0] >= 0.2).all() and (gt[:, 0] <= 2.25).all() and (np.abs(gt[:, 1:]) <= 45).all()
+    assert np.array_equal(full["uv"], np.rint(full["uv"]))          # quantised to integer pixels
+    noisy = orc.synth(0, 2000, P, K, orc.default_synth(is_quantized=False, noise_sigma_px=2.0))
+    clean = orc.synth(0, 2000, P, K, orc.default_synth(is_quantized=False))
+    d = (noisy["uv"] - clean["uv"]).ravel()
+    assert abs(d.mean()) < 0.02 and abs(d.std() - 2.0) < 0.02
+    # QEIF on the synthetic stress workload passes the reference's own 10 cm / 10 deg criterion
+    P15 = pt.pattern_array(pt.get_golden_pattern())
+    w = orc.synth(0, 400, P15, K)
+    idx = [list(pt.get_golden_pattern()).index(k) for k in pt.LM_KEY_LIST_6]
+    s = orc.solve_batch("qeif", w["uv"][:, idx], P15[idx], K)
+    r = orc.report_batch(P15, w["uv"], K, s["R"], s["t"], s["euler"], w["gt"])
+    assert r["flags"].all(axis=1).mean() > 0.95
