@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: PnP solves/sec (device-timed) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- 1,048,576 problems x 68-point face
+pattern, LM refinement, FP64, per GPU (weak scaling: rank r owns problems [r*B, (r+1)*B) of one
+global counter-based synthetic stream, so a sharded run is the slice of the unsharded one).
+A "step" is one pass of the hot path over the rank's batch: the fused solve kernel (packing and
+K^-1 normalisation, 14 LM iterations, SO(3) projection, Euler), the error-report kernel, and the
+error statistics with their two all-reduces (NCCL over NVLink; the only inter-GPU traffic).
+Inputs are resident in HBM for `value`; `e2e` runs the same solve through the host-buffer entry
+point (pinned host memory -> H2D -> solve -> D2H of all results) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+B_PER_GPU = 1 << 20
+N_POINTS = 68
+METHOD = "lm"
+METRIC = "pnp_solves_per_sec"
+UNIT = "solves/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per solve of the LM kernel as implemented (DESIGN.md "Kernels"); FMA = 2 flops
+# ------------------------------------------------------------------------------------------------
+def lm_flops_per_solve(n, max_it=14):
+    per_point_once = 56          # 24 moment FMAs + theta theta^T products + bx^2+by^2
+    per_point_iter = 83          # 3 dots, g, r, 18 theta-weighted FMAs, 7 scalar sums
+    per_iter = 1300              # build A (78), 9 constraint rows, LDL^T 12x12, two triangular solves
+    final = 600                  # 3x3 Jacobi SVD projection, t, Euler
+    return n * (per_point_once + max_it * per_point_iter) + max_it * per_iter + final
+
+
+def lm_flops_survey(n, max_it=14):
+    return max_it * (212 * n + 1100) + 1000        # naive structure
+
+
+def bytes_per_solve(n, s=8):
+    return s * (2 * n + 16) + 8
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.rows)}
+        sm, reasons = [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_rate(sample, n_threads=0, method=METHOD, n=N_POINTS, seed=42):
+    from oracle import oracle as orc
+    from pnp_solver_test_b200 import patterns as pt
+    P = pt.pattern_array(pt.synthetic_pattern(n))
+    K = pt.default_camera_matrix()
+    w = orc.synth(0, sample, P, K, orc.default_synth(seed=seed))
+    t0 = time.perf_counter()
+    orc.solve_batch(method, w["uv"], P, K, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def cpu_baseline_block(target_seconds=12.0):
+    from oracle import oracle as orc
+    cores = orc.num_threads()
+    r0, _ = cpu_rate(max(256, 64 * cores))                      # calibration
+    sample = int(max(256, min(B_PER_GPU, r0 * target_seconds)))
+    rate, dt = cpu_rate(sample)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of the %d problems of the workload (first %d of the seeded stream), %.1f s on %d threads; "
+                      "oracle/pnp_oracle.c = C port of the reference's NumPy algorithm incl. SVD-based pinv"
+                      % (sample, B_PER_GPU, sample, dt, cores)}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    cores = orc.num_threads()
+    r0, _ = cpu_rate(max(256, 64 * cores))
+    sample = int(max(256, min(B_PER_GPU, r0 * 8.0)))            # ~8 s per step
+    for _ in range(args.warmup):
+        cpu_rate(max(64, sample // 8))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_rate(sample)
+    dt = time.perf_counter() - t0
+    rate = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "68-point LM PnP solves, FP64, random_stress_test pose distribution, quantised pixels",
+                   "method": METHOD, "n_points": N_POINTS, "problems_per_step": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d problems per step x %d steps on %d host threads (oracle/pnp_oracle.c; the reference "
+                                   "is pure Python and is not on this box)" % (sample, args.steps, cores)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pnp_solver_test_b200 as pnp
+    from pnp_solver_test_b200 import _lib, workload as wl, patterns as pt
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, n = args.problems, N_POINTS
+    K = pt.default_camera_matrix()
+    P = pt.pattern_array(pt.synthetic_pattern(n))
+    pat = torch.from_numpy(P).to(dev)[None].contiguous()
+    params = pnp.default_params()
+
+    # inputs resident in HBM: this rank's slice of the global stream
+    w = wl.synth_batch(rank * B, B, P, K, cfg=pnp.default_synth(seed=42), device=dev)
+    uv, gt = w["uv"], w["gt"]
+    torch.cuda.synchronize()
+
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    last = {}
+
+    def step(i=None):
+        if i is not None:
+            ev_a[i].record()
+        out = pnp.solve_batch(METHOD, uv, pat, K, params=params)
+        if i is not None:
+            ev_b[i].record()
+        rep = wl.report_batch(P, uv, K, out["R"], out["t"], out["euler"], gt)
+        last["stats"] = wl.error_statistics(rep["report"], gt)          # two all-reduce phases per quantity
+        last["pass"] = rep["flags"]
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = _lib.LAUNCHES[0]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(i)
+    t_end.record()
+    barrier()
+    launches = _lib.LAUNCHES[0] - l0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_a, ev_b)]))
+    tt = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ms_kernel_max = float(tt[0]), float(tt[1])
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, copies timed)
+    e2e = None
+    if not args.no_e2e:
+        host_uv = torch.empty((B, n, 2), dtype=torch.float64).pin_memory()
+        host_uv.copy_(uv)
+        host_pat = torch.from_numpy(P)[None].contiguous()
+        outs = {"R": torch.empty((B, 3, 3), dtype=torch.float64).pin_memory(), "t": torch.empty((B, 3), dtype=torch.float64).pin_memory(),
+                "euler": torch.empty((B, 3), dtype=torch.float64).pin_memory(), "res_norm": torch.empty((B,), dtype=torch.float64).pin_memory(),
+                "iters": torch.empty((B,), dtype=torch.int32).pin_memory(), "best_pattern": torch.empty((B,), dtype=torch.int32).pin_memory()}
+        pipe = pnp.HostPipeline(torch.float64, chunk_problems=args.chunk, n_total=n, n_patterns=1, n_streams=3, device=dev)
+        for _ in range(2):
+            pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)
+        barrier()
+        t0 = time.perf_counter()
+        e_steps = max(1, min(args.steps, 5))
+        for _ in range(e_steps):
+            pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)   # blocks until results are on the host
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = host_uv.numel() * 8
+        d2h = sum(v.numel() * v.element_size() for v in outs.values())
+        e2e = {"value": world * B * e_steps / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e_steps, "api": "pnpb200_solve_batch_host via HostPipeline.solve (pinned host buffers, %d-problem chunks, 3 streams)" % args.chunk}
+        assert torch.equal(outs["iters"], torch.full((B,), 14, dtype=torch.int32))
+        pipe.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_solve_thread<double, LM>): FP64 FMA pipe
+    import ctypes as C
+    peak = C.c_double(0.0)
+    _lib.check(_lib.lib.pnpb200_fma_peak(0, 200000, C.byref(peak)), "pnpb200_fma_peak")
+    fl = lm_flops_per_solve(n)
+    achieved_tf = fl * B / (ms_kernel_max * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_achieved = bytes_per_solve(n) * B / (ms_kernel_max * 1e-3) / 1e9
+    roofline = {"bound": "fp64_pipe", "kernel": "k_solve_thread<double, LM>", "achieved": achieved_tf, "peak": peak.value / 1e12,
+                "unit": "TFLOP/s", "frac": achieved_tf / (peak.value / 1e12), "traffic": None,
+                "peak_source": "measured in this run by pnpb200_fma_peak (FP64 FMA microbenchmark; MEASURED_PEAKS.json has no FP64 figure)",
+                "flops_per_solve": fl, "flops_per_solve_survey_formula": lm_flops_survey(n), "kernel_ms": ms_kernel_max,
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                        "bytes_per_solve": bytes_per_solve(n),
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}}
+    cpu = cpu_baseline_block() if (world == 1 and not args.no_cpu) else None
+    st = last["stats"]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: %d problems x %d-point face pattern per GPU, LM refinement (14 it), FP64, "
+                               "random_stress_test pose distribution, integer-quantised pixels" % (B, n),
+                   "method": METHOD, "n_points": n, "problems_per_gpu": B, "global_problems": world * B,
+                   "step": "solve kernel + error-report kernel + error statistics (two all-reduce phases)",
+                   "l2": "inputs are %.2f GB per step, larger than the 126 MB L2" % (uv.numel() * 8 / 1e9),
+                   "parallelism": "problems sharded by global index, no solve-path traffic"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "quality": {"pass_rate_10cm_10deg": float(last["pass"].all(dim=1).double().mean()),
+                    "depth_MAE_m": float(st["depth"]["all"][5]), "yaw_MAE_deg": float(st["yaw"]["all"][5]),
+                    "n_stat": float(st["depth"]["all"][0])},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--problems", type=int, default=B_PER_GPU, help="problems per GPU (default: the BASELINE config)")
+    ap.add_argument("--chunk", type=int, default=1 << 17, help="e2e pipeline chunk (problems)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

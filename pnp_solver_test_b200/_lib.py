@@ -85,3 +85,11 @@ def default_synth(**kw):
 def ptr(t):
     """device/host pointer of a torch tensor (or None)"""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# number of kernels of THIS library launched by the Python wrappers (bench.py reports it)
+LAUNCHES = [0]
+
+
+def count_launch(n=1):
+    LAUNCHES[0] += int(n)

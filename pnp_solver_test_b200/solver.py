@@ -79,6 +79,7 @@ def solve_batch(method, uv, patterns, K, point_index=None, params=None, want=("R
             ptr(o.get("R")), ptr(o.get("t")), ptr(o.get("euler")), ptr(o.get("res_norm")),
             ptr(o.get("iters")), ptr(o.get("best_pattern")), _stream_ptr(dev))
     check(rc, "pnpb200_solve_batch")
+    _lib.count_launch(1 if B > 0 else 0)
     return o
 
 
@@ -89,6 +90,7 @@ class HostPipeline(object):
     def __init__(self, dtype, chunk_problems, n_total, n_patterns=1, n_streams=3, device=None):
         self.dt = _dtype_code(dtype)
         self.n_total, self.n_patterns = int(n_total), int(n_patterns)
+        self.chunk = int(chunk_problems)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -125,6 +127,7 @@ class HostPipeline(object):
                 ptr(out.get("R")), ptr(out.get("t")), ptr(out.get("euler")), ptr(out.get("res_norm")),
                 ptr(out.get("iters")), ptr(out.get("best_pattern")))
         check(rc, "pnpb200_solve_batch_host")
+        _lib.count_launch((B + self.chunk - 1) // self.chunk)
         return out
 
 
@@ -136,6 +139,7 @@ def R_from_euler_batch(euler, is_degree=False):
     with torch.cuda.device(euler.device):
         check(lib.pnpb200_R_from_euler(C.c_int(_dtype_code(euler.dtype)), C.c_int64(B), ptr(euler), C.c_int(int(is_degree)),
                                        ptr(R), _stream_ptr(euler.device)), "pnpb200_R_from_euler")
+    _lib.count_launch()
     return R
 
 
@@ -147,6 +151,7 @@ def euler_from_R_batch(R, is_degree=False):
     with torch.cuda.device(R.device):
         check(lib.pnpb200_euler_from_R(C.c_int(_dtype_code(R.dtype)), C.c_int64(B), ptr(R), C.c_int(int(is_degree)),
                                        ptr(e), _stream_ptr(R.device)), "pnpb200_euler_from_R")
+    _lib.count_launch()
     return e
 
 
@@ -160,6 +165,7 @@ def project_batch(pattern, K, R, t, is_quantized=False, quantize_q=1.0):
         check(lib.pnpb200_project(C.c_int(_dtype_code(R.dtype)), C.c_int64(B), C.c_int(n), ptr(pattern), Kp, ptr(R), ptr(t),
                                   C.c_int(int(is_quantized)), C.c_double(float(quantize_q)), ptr(out),
                                   _stream_ptr(R.device)), "pnpb200_project")
+    _lib.count_launch()
     return out
 
 

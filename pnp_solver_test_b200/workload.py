@@ -57,6 +57,7 @@ def synth_batch(b0, B, pattern, K, cfg=None, dtype=torch.float64, device=None, w
                                       C.cast(ptr(Rg), C.POINTER(C.c_double)) if want_pose else None,
                                       C.cast(ptr(tg), C.POINTER(C.c_double)) if want_pose else None,
                                       _stream_ptr(device)), "pnpb200_synth_batch")
+    _lib.count_launch()
     out = dict(uv=uv, gt=gt)
     if want_pose:
         out["R_gt"], out["t_gt"] = Rg, tg
@@ -83,6 +84,7 @@ def report_batch(pattern, uv, K, R, t, euler, gt, bounds=(10.0, 10.0, 10.0, 10.0
                                        C.cast(ptr(rep), C.POINTER(C.c_double)),
                                        C.cast(ptr(flags), C.POINTER(C.c_int32)), C.cast(ptr(midx), C.POINTER(C.c_int32)),
                                        _stream_ptr(dev)), "pnpb200_report_batch")
+    _lib.count_launch()
     return dict(report=rep, flags=flags, max_idx=midx)
 
 
@@ -97,6 +99,7 @@ def classify(values, bins, scale=1.0):
         check(lib.pnpb200_classify(C.c_int64(B), C.cast(ptr(values), C.POINTER(C.c_double)), C.c_int64(values.stride(0) if B else 1),
                                    C.c_double(scale), bn, C.c_int(len(bins)), C.cast(ptr(cls), C.POINTER(C.c_int32)),
                                    _stream_ptr(values.device)), "pnpb200_classify")
+    _lib.count_launch()
     return cls
 
 
@@ -149,12 +152,14 @@ def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=T
     with torch.cuda.device(dev):
         check(lib.pnpb200_stats_pass1(C.c_int64(B), dp(est), C.c_int64(es), dp(gt), C.c_int64(gs), cid, C.c_int(n_class),
                                       dp(s1), _stream_ptr(dev)), "pnpb200_stats_pass1")
+    _lib.count_launch()
     mean = reduce_phase1(s1, group) if distributed else (s1[:, 2] / s1[:, 0]).contiguous()
     mean = torch.nan_to_num(mean).contiguous()
     s2 = torch.empty((n_class, 4), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         check(lib.pnpb200_stats_pass2(C.c_int64(B), dp(est), C.c_int64(es), dp(gt), C.c_int64(gs), cid, C.c_int(n_class),
                                       dp(mean), dp(s2), _stream_ptr(dev)), "pnpb200_stats_pass2")
+    _lib.count_launch()
     if distributed:
         s2 = reduce_phase2(s2, group)
     return finalize_stats(s1, s2).cpu()

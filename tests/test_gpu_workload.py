@@ -1,0 +1,107 @@
+"""Parity of the kernels either side of the solve: Euler <-> R, projection, the synthetic
+workload generator, error reporting, classification and the two-pass statistics."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import dev, to_np
+from oracle import oracle as orc
+from pnp_solver_test_b200 import patterns as pt
+
+pytestmark = pytest.mark.gpu
+
+
+def test_euler_kernels_match_reference_fixture_and_oracle():
+    import pnp_solver_test_b200 as pnp
+    g = load_golden("euler_fixture")
+    R = pnp.R_from_euler_batch(dev(g["roll_yaw_pitch_deg"]), is_degree=True).cpu().numpy()
+    assert np.abs(R - g["R"]).max() < 1e-12                         # the reference's own fixture
+    e = pnp.euler_from_R_batch(dev(g["R"]), is_degree=True).cpu().numpy()
+    assert np.abs(e - g["roll_yaw_pitch_deg"]).max() < 1e-9
+    rng = np.random.default_rng(0)
+    ang = rng.uniform(-3.0, 3.0, (5000, 3))
+    R = pnp.R_from_euler_batch(dev(ang), is_degree=False).cpu().numpy()
+    Ro = np.array([orc.R_from_euler(*a, is_degree=False) for a in ang])
+    assert np.abs(R - Ro).max() < 1e-14
+    e = pnp.euler_from_R_batch(dev(Ro), is_degree=False).cpu().numpy()
+    eo = np.array([orc.euler_from_R(r, False) for r in Ro])
+    assert np.abs(e - eo).max() < 1e-12
+    # gimbal-lock branch (PNP_SOLVER_LIB.py:4482)
+    Rg = np.array([orc.R_from_euler(0.3, 0.0, np.pi / 2, False), orc.R_from_euler(-1.0, 0.0, -np.pi / 2, False)])
+    eg = pnp.euler_from_R_batch(dev(Rg), False).cpu().numpy()
+    assert np.abs(eg - np.array([orc.euler_from_R(r, False) for r in Rg])).max() < 1e-12
+    f32 = pnp.euler_from_R_batch(dev(Ro, torch.float32), False).cpu().numpy()
+    assert np.median(np.abs(f32 - eo)) < 1e-5
+
+
+def test_projection_matches_oracle_including_rounding():
+    import pnp_solver_test_b200 as pnp
+    P = pt.pattern_array(pt.synthetic_pattern(68))
+    K = pt.default_camera_matrix()
+    w = orc.synth(0, 512, P, K)
+    for quant, q in ((False, 1.0), (True, 1.0), (True, 30.0 / 112.0)):
+        got = pnp.project_batch(dev(P), K, dev(w["R_gt"]), dev(w["t_gt"]), quant, q).cpu().numpy()
+        ref = np.array([orc.project(P, K, w["R_gt"][b], w["t_gt"][b], quant, q) for b in range(512)])
+        if quant:
+            assert (np.abs(got - ref) > 1e-9).mean() < 1e-4         # a tie may round the other way
+        else:
+            assert np.abs(got - ref).max() < 1e-10
+    # behind the camera: divide by |z| (PNP_SOLVER_LIB.py:4548) -> homogeneous coordinate -1
+    t_neg = w["t_gt"].copy(); t_neg[:, 2] *= -1
+    got = pnp.project_batch(dev(P), K, dev(w["R_gt"]), dev(t_neg), False, 1.0).cpu().numpy()
+    assert np.allclose(got[..., 2], -1.0)
+
+
+def test_synthetic_workload_matches_oracle_and_is_shard_invariant():
+    import pnp_solver_test_b200 as pnp
+    from pnp_solver_test_b200 import workload as wl
+    P = pt.pattern_array(pt.synthetic_pattern(68))
+    K = pt.default_camera_matrix()
+    for cfg_kw in (dict(is_quantized=0), dict(is_quantized=1), dict(is_quantized=0, noise_sigma_px=1.5),
+                   dict(is_quantized=1, quantize_q=30.0 / 112.0, noise_sigma_px=0.5)):
+        ref = orc.synth(5, 4000, P, K, orc.default_synth(seed=9, **{k: v for k, v in cfg_kw.items()}))
+        got = wl.synth_batch(5, 4000, P, K, cfg=pnp.default_synth(seed=9, **cfg_kw), want_pose=True)
+        assert np.abs(got["gt"].cpu().numpy() - ref["gt"]).max() < 1e-12
+        assert np.abs(got["R_gt"].cpu().numpy() - ref["R_gt"]).max() < 1e-14
+        d = np.abs(got["uv"].cpu().numpy() - ref["uv"])
+        assert (d > 1e-8).mean() < 1e-4, (cfg_kw, d.max())
+    full = wl.synth_batch(0, 3000, P, K)["uv"]
+    parts = torch.cat([wl.synth_batch(0, 1000, P, K)["uv"], wl.synth_batch(1000, 2000, P, K)["uv"]])
+    assert torch.equal(full, parts)
+    f32 = wl.synth_batch(0, 3000, P, K, dtype=torch.float32)["uv"]
+    assert torch.equal(f32.double(), full)                          # integer pixels are exact in FP32
+
+
+def test_report_classification_and_statistics_match_reference():
+    from pnp_solver_test_b200 import workload as wl
+    g = load_golden("stress_report")
+    rep = wl.report_batch(g["pattern"], dev(g["uv"]), g["K"], dev(g["R"]), dev(g["t"]), dev(g["euler"]), dev(g["gt"]))
+    assert np.abs(rep["report"].cpu().numpy() - g["report"]).max() < 1e-10
+    assert np.array_equal(rep["flags"].cpu().numpy(), g["flags"])
+    assert np.array_equal(rep["max_idx"].cpu().numpy(), g["max_idx"])
+    cls = wl.classify(dev(g["gt"])[:, 0], wl.CLASS_BINS["depth"], scale=100.0)
+    assert np.array_equal(cls.cpu().numpy(), g["depth_class"])
+    st = wl.error_statistics(rep["report"], dev(g["gt"]), distributed=False)
+    for q, name in enumerate(("depth", "roll", "pitch", "yaw")):
+        np.testing.assert_allclose(st[name]["all"].numpy(), g["stats_all"][q], rtol=1e-11, atol=1e-13)
+        ref = g["stats_by_depth"][q]
+        has = ~np.isnan(ref[:, 0])
+        np.testing.assert_allclose(st[name]["by_depth"].numpy()[has], ref[has], rtol=1e-11, atol=1e-13)
+
+
+def test_report_on_cuda_solution_matches_oracle_report():
+    import pnp_solver_test_b200 as pnp
+    from pnp_solver_test_b200 import workload as wl
+    pat15 = pt.get_golden_pattern()
+    P, K = pt.pattern_array(pat15), pt.default_camera_matrix()
+    w = orc.synth(0, 5000, P, K)
+    idx = [list(pat15).index(k) for k in pt.LM_KEY_LIST_6]
+    out = pnp.solve_batch("qeif", dev(w["uv"]), dev(P)[None], K, point_index=idx)
+    rep = wl.report_batch(P, dev(w["uv"]), K, out["R"], out["t"], out["euler"], dev(w["gt"]))
+    o = to_np(out)
+    ref = orc.report_batch(P, w["uv"], K, o["R"], o["t"], o["euler"], w["gt"])
+    assert np.abs(rep["report"].cpu().numpy() - ref["report"]).max() < 1e-9
+    assert np.array_equal(rep["flags"].cpu().numpy(), ref["flags"])
+    assert (rep["max_idx"].cpu().numpy() == ref["max_idx"]).mean() > 0.999
+    assert ref["flags"].all(axis=1).mean() > 0.95
