@@ -54,41 +54,60 @@ def bytes_per_solve(n, s=8):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  Started
+    before the warm-up (nvidia-smi takes a while to come up); rows are time-stamped on arrival and
+    only those inside [mark_begin, mark_end] count (all rows under load if the region is too short)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "50", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
+
+    def wait_first(self, timeout=10.0):
+        t = time.perf_counter()
+        while not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.05)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.rows)}
+        inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or 1e300)]
+        scope = "timed region"
+        if len(inside) < 3:
+            inside, scope = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than 3 samples)"
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(inside), "scope": scope}
         sm, reasons = [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 out["sm_max_mhz"] = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 continue
         if sm:
             out["sm_mhz"] = float(np.median(sm))
+            out["sm_mhz_max_seen"] = float(np.max(sm))
         out["reasons"] = sorted(reasons)
         return out
 
@@ -205,11 +224,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 0)):
-        step()
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first()
+    for _ in range(max(args.warmup, 0)):
+        step()
     barrier()
+    sampler.mark_begin()
     l0 = _lib.LAUNCHES[0]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -217,6 +238,7 @@ def run_ours(args):
         step(i)
     t_end.record()
     barrier()
+    sampler.mark_end()
     launches = _lib.LAUNCHES[0] - l0
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
@@ -307,8 +329,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=B_PER_GPU, help="problems per GPU (default: the BASELINE config)")
     ap.add_argument("--chunk", type=int, default=1 << 17, help="e2e pipeline chunk (problems)")

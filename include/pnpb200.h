@@ -175,20 +175,24 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
                          double* report, int32_t* flags, int32_t* max_idx, void* stream);
 
 /*
- * Error statistics, two passes so that shards can be combined with two small all-reduces
- * (TEST_TOOLBOX.get_statistic_of_result, TEST_TOOLBOX.py:892-937).
- *   est, gt: [B] strided views (element stride in doubles) of FP64 device data; gt may be NULL
- *   class_id: [B] int32 device or NULL (all in class 0); n_class classes
- *   pass 1 -> sums1 [n_class,4]  = n, sum(est/gt), sum(e), 0            (SUM-reducible)
- *   pass 2 (given mean[n_class]) -> sums2 [n_class,4] = sum((e-m)^2), sum|e|, sum|e-m|, max|e-m|
- *                                  (first three SUM-reducible, last MAX-reducible)
+ * Error statistics, two passes so that shards can be combined with two small all-reduce phases
+ * (TEST_TOOLBOX.get_statistic_of_result, TEST_TOOLBOX.py:892-937), for nq <= 4 quantities at once
+ * (depth, roll, pitch, yaw in TEST_TOOLBOX.data_analysis_and_saving, :1070-1112), per class and,
+ * in the extra LAST row, over all problems.
+ *   est[q], gt[q]: FP64 device vectors with element strides est_stride[q], gt_stride[q]
+ *                  (gt or gt[q] may be NULL: statistics of the value itself);  arrays of nq [host]
+ *   class_id: [B] int32 device or NULL (every problem in class 0); n_class <= 64 classes
+ *   pass 1 -> sums1 [nq, n_class+1, 4] = n, sum(est/gt), sum(e), 0                  (SUM-reducible)
+ *   pass 2 (given mean [nq, n_class+1] device) -> sums2 [nq, n_class+1, 4]
+ *            = sum((e-m)^2), sum|e|, sum|e-m|, max|e-m|     (first three SUM-, last MAX-reducible)
  */
-int pnpb200_stats_pass1(int64_t B, const double* est, int64_t est_stride, const double* gt,
-                        int64_t gt_stride, const int32_t* class_id, int n_class,
-                        double* sums1, void* stream);
-int pnpb200_stats_pass2(int64_t B, const double* est, int64_t est_stride, const double* gt,
-                        int64_t gt_stride, const int32_t* class_id, int n_class,
-                        const double* mean, double* sums2, void* stream);
+int pnpb200_stats_pass1(int64_t B, int nq, const double* const* est, const int64_t* est_stride,
+                        const double* const* gt, const int64_t* gt_stride,
+                        const int32_t* class_id, int n_class, double* sums1, void* stream);
+int pnpb200_stats_pass2(int64_t B, int nq, const double* const* est, const int64_t* est_stride,
+                        const double* const* gt, const int64_t* gt_stride,
+                        const int32_t* class_id, int n_class, const double* mean, double* sums2,
+                        void* stream);
 
 /*
  * Ground-truth classification, np.digitize(value, bins) (TEST_TOOLBOX.classify_drpy,

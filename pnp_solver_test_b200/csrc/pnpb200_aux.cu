@@ -67,6 +67,20 @@ PNP_DEV void project_point(const double* K, const double (&R)[9], const double (
     }
 }
 
+// Same projection for the error report (never quantised): one reciprocal instead of three
+// divisions; the homogeneous coordinate z/|z| is exactly +-1.
+PNP_DEV void project_point_fast(const double* K, const double (&R)[9], const double (&t)[3], double x, double y, double z,
+                                double (&o)[3])
+{
+    double X[3], ray[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) X[r] = R[r * 3] * x + R[r * 3 + 1] * y + R[r * 3 + 2] * z + t[r];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) ray[r] = K[r * 3] * X[0] + K[r * 3 + 1] * X[1] + K[r * 3 + 2] * X[2];
+    const double inv = 1.0 / fabs(ray[2]);
+    o[0] = ray[0] * inv; o[1] = ray[1] * inv; o[2] = copysign(1.0, ray[2]);
+}
+
 struct KMat { double k[9]; };
 
 template <typename T>
@@ -207,8 +221,8 @@ __global__ void k_report(long long B, int n, const void* pattern, const void* uv
     for (int i = lane; i < n; i += 32) {
         const double x = ld<T>(pattern, 3 * i), y = ld<T>(pattern, 3 * i + 1), z = ld<T>(pattern, 3 * i + 2);
         double pe[3], pg[3];
-        project_point(K.k, Re, te, x, y, z, false, 1.0, pe);   // TEST_TOOLBOX.py:312
-        project_point(K.k, Rg, tg, x, y, z, false, 1.0, pg);   // :314
+        project_point_fast(K.k, Re, te, x, y, z, pe);          // TEST_TOOLBOX.py:312
+        project_point_fast(K.k, Rg, tg, x, y, z, pg);          // :314
         const double mu = ld<T>(uv, ((size_t)b * n + i) * 2), mv = ld<T>(uv, ((size_t)b * n + i) * 2 + 1), mw = 1.0;
         double d0, d1, d2, e;
         d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];     // LM vs GT (:321)
@@ -237,43 +251,134 @@ __global__ void k_report(long long B, int n, const void* pattern, const void* uv
 }
 
 // ------------------------------------------------------------------------------------------
-// statistics (get_statistic_of_result, TEST_TOOLBOX.py:892-937), two SUM/MAX-reducible passes
+// statistics (get_statistic_of_result, TEST_TOOLBOX.py:892-937), two SUM/MAX-reducible passes,
+// for up to 4 quantities at once, per class and (last row) over all problems.
+//   pass 1 row = (n, sum est/gt, sum e, 0);  pass 2 row = (sum (e-m)^2, sum |e|, sum |e-m|, max |e-m|)
+// No floating-point atomics on shared memory: lanes of a warp that share a class take turns
+// (rank among equal-class lanes via __match_any_sync), each turn is conflict-free; the "all"
+// row is accumulated in registers.  One RED per (block, row, column) to global memory at the end.
 // ------------------------------------------------------------------------------------------
 constexpr int kStatBlock = 256;
+constexpr int kStatWarps = kStatBlock / 32;
 constexpr int kStatMaxClass = 64;
+constexpr int kStatMaxQ = 4;
 
-PNP_DEV void atomic_max_double(double* addr, double v)   // v >= 0
+struct StatIn {
+    const double* est[kStatMaxQ];
+    const double* gt[kStatMaxQ];
+    long long es[kStatMaxQ], gs[kStatMaxQ];
+    int nq;
+};
+
+PNP_DEV void atomic_max_double(double* addr, double v)   // v >= 0: the bit pattern is monotone
 {
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
 template <int PASS>
-__global__ void k_stats(long long B, const double* __restrict__ est, long long es, const double* __restrict__ gt,
-                        long long gs, const int32_t* __restrict__ cls, int n_class, const double* __restrict__ mean,
-                        double* out)
+__global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
+                                                     const double* __restrict__ mean, double* out)
 {
-    __shared__ double sh[kStatMaxClass * 4];
-    for (int e = threadIdx.x; e < n_class * 4; e += blockDim.x) sh[e] = 0.0;
+    extern __shared__ double sh[];                        // [warp][n_class][nq][4]
+    const int nq = in.nq, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = n_class + 1;                         // + the "all" row
+    const int per_warp = n_class * nq * 4;
+    for (int e = threadIdx.x; e < kStatWarps * per_warp; e += blockDim.x) sh[e] = 0.0;
     __syncthreads();
-    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        const int c = cls ? cls[b] : 0;
-        if (c < 0 || c >= n_class) continue;
-        const double ev = est[b * es];
-        double ratio, err;
-        if (gt) { const double g = gt[b * gs]; ratio = ev / g; err = ev - g; }
-        else    { ratio = ev; err = ev; }
-        if (PASS == 1) {
-            atomicAdd(&sh[c * 4], 1.0); atomicAdd(&sh[c * 4 + 1], ratio); atomicAdd(&sh[c * 4 + 2], err);
-        } else {
-            const double d = err - mean[c];
-            atomicAdd(&sh[c * 4], d * d); atomicAdd(&sh[c * 4 + 1], fabs(err)); atomicAdd(&sh[c * 4 + 2], fabs(d));
-            atomic_max_double(&sh[c * 4 + 3], fabs(d));
+    double* mine = sh + warp * per_warp;
+    double all[kStatMaxQ][4];
+#pragma unroll
+    for (int q = 0; q < kStatMaxQ; ++q) all[q][0] = all[q][1] = all[q][2] = all[q][3] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long b_start = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // all lanes of a warp iterate together (the match below needs the full warp)
+    for (long long base = b_start - lane; base < B; base += stride) {
+        const long long b = base + lane;
+        const bool ok = b < B;
+        int c = -1;
+        double v[kStatMaxQ][4];
+#pragma unroll
+        for (int q = 0; q < kStatMaxQ; ++q) v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+        if (ok) {
+            c = cls ? cls[b] : 0;
+            if (c < 0 || c >= n_class) c = -1;
+#pragma unroll
+            for (int q = 0; q < kStatMaxQ; ++q) {
+                if (q < nq) {
+                    const double ev = in.est[q][b * in.es[q]];
+                    double ratio, err;
+                    if (in.gt[q]) { const double g = in.gt[q][b * in.gs[q]]; ratio = ev / g; err = ev - g; }
+                    else          { ratio = ev; err = ev; }
+                    if (PASS == 1) { v[q][0] = 1.0; v[q][1] = ratio; v[q][2] = err; }
+                    else {
+                        if (c >= 0) { const double d = err - mean[q * rows + c]; v[q][0] = d * d; v[q][1] = fabs(err); v[q][2] = fabs(d); v[q][3] = fabs(d); }
+                    }
+                    // the "all" row (its own mean in pass 2)
+                    if (PASS == 1) { all[q][0] += 1.0; all[q][1] += ratio; all[q][2] += err; }
+                    else {
+                        const double d = err - mean[q * rows + n_class];
+                        all[q][0] += d * d; all[q][1] += fabs(err); all[q][2] += fabs(d); all[q][3] = fmax(all[q][3], fabs(d));
+                    }
+                }
+            }
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, c);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        const unsigned any_valid = __ballot_sync(0xffffffffu, c >= 0);
+        int max_rank = 0;
+        {
+            int r = (c >= 0) ? rank : 0;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) r = max(r, __shfl_xor_sync(0xffffffffu, r, off));
+            max_rank = r;
+        }
+        if (any_valid) {
+            for (int turn = 0; turn <= max_rank; ++turn) {
+                if (c >= 0 && rank == turn) {
+                    double* row = mine + (size_t)c * nq * 4;
+#pragma unroll
+                    for (int q = 0; q < kStatMaxQ; ++q) {
+                        if (q < nq) {
+                            row[q * 4 + 0] += v[q][0]; row[q * 4 + 1] += v[q][1]; row[q * 4 + 2] += v[q][2];
+                            if (PASS == 2) row[q * 4 + 3] = fmax(row[q * 4 + 3], v[q][3]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n_class * 4; e += blockDim.x) {
-        if (PASS == 2 && (e & 3) == 3) atomic_max_double(&out[e], sh[e]);
-        else if (sh[e] != 0.0) atomicAdd(&out[e], sh[e]);
+    // classes: sum over the block's warps, one RED per value
+    for (int e = threadIdx.x; e < per_warp; e += blockDim.x) {
+        double acc = 0.0;
+        const bool is_max = (PASS == 2) && ((e & 3) == 3);
+        for (int w = 0; w < kStatWarps; ++w) acc = is_max ? fmax(acc, sh[w * per_warp + e]) : acc + sh[w * per_warp + e];
+        const int c = e / (nq * 4), r = e - c * nq * 4, q = r >> 2, k = r & 3;
+        double* dst = out + ((size_t)q * rows + c) * 4 + k;
+        if (is_max) atomic_max_double(dst, acc);
+        else if (acc != 0.0) atomicAdd(dst, acc);
+    }
+    // "all" row: warp shuffle reduction, then one RED per warp
+#pragma unroll
+    for (int q = 0; q < kStatMaxQ; ++q) {
+        if (q < nq) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double a = all[q][k];
+                const bool is_max = (PASS == 2) && (k == 3);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double o = __shfl_xor_sync(0xffffffffu, a, off);
+                    a = is_max ? fmax(a, o) : a + o;
+                }
+                if (lane == 0) {
+                    double* dst = out + ((size_t)q * rows + n_class) * 4 + k;
+                    if (is_max) atomic_max_double(dst, a);
+                    else if (a != 0.0) atomicAdd(dst, a);
+                }
+            }
+        }
     }
 }
 
@@ -397,6 +502,8 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
     return PNPB200_OK;
 }
 
+}  // extern "C"
+
 static int stats_grid(int64_t B)
 {
     DeviceProps dp;
@@ -406,28 +513,44 @@ static int stats_grid(int64_t B)
     return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
-int pnpb200_stats_pass1(int64_t B, const double* est, int64_t est_stride, const double* gt, int64_t gt_stride,
-                        const int32_t* class_id, int n_class, double* sums1, void* stream)
+template <int PASS>
+static int stats_launch(int64_t B, int nq, const double* const* est, const int64_t* es, const double* const* gt,
+                        const int64_t* gs, const int32_t* class_id, int n_class, const double* mean, double* sums,
+                        cudaStream_t st)
 {
-    if (B < 0 || !est || !sums1 || n_class < 1 || n_class > kStatMaxClass) return PNPB200_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
-    PNP_CUDA_OK(cudaMemsetAsync(sums1, 0, sizeof(double) * 4 * (size_t)n_class, st));
+    if (B < 0 || nq < 1 || nq > kStatMaxQ || !est || !es || !sums || n_class < 1 || n_class > kStatMaxClass) return PNPB200_EINVAL;
+    if (PASS == 2 && !mean) return PNPB200_EINVAL;
+    StatIn in;
+    in.nq = nq;
+    for (int q = 0; q < kStatMaxQ; ++q) {
+        in.est[q] = (q < nq) ? est[q] : nullptr;
+        in.gt[q] = (q < nq && gt) ? gt[q] : nullptr;
+        in.es[q] = (q < nq) ? es[q] : 0;
+        in.gs[q] = (q < nq && gs) ? gs[q] : 0;
+        if (q < nq && !in.est[q]) return PNPB200_EINVAL;
+    }
+    PNP_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * (size_t)nq * (n_class + 1), st));
     if (B == 0) return PNPB200_OK;
-    k_stats<1><<<stats_grid(B), kStatBlock, 0, st>>>(B, est, est_stride, gt, gt_stride, class_id, n_class, nullptr, sums1);
+    const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
+    if (smem > 48 * 1024) PNP_CUDA_OK(cudaFuncSetAttribute(k_stats<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, mean, sums);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
 
-int pnpb200_stats_pass2(int64_t B, const double* est, int64_t est_stride, const double* gt, int64_t gt_stride,
-                        const int32_t* class_id, int n_class, const double* mean, double* sums2, void* stream)
+extern "C" {
+
+int pnpb200_stats_pass1(int64_t B, int nq, const double* const* est, const int64_t* est_stride, const double* const* gt,
+                        const int64_t* gt_stride, const int32_t* class_id, int n_class, double* sums1, void* stream)
 {
-    if (B < 0 || !est || !sums2 || !mean || n_class < 1 || n_class > kStatMaxClass) return PNPB200_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
-    PNP_CUDA_OK(cudaMemsetAsync(sums2, 0, sizeof(double) * 4 * (size_t)n_class, st));
-    if (B == 0) return PNPB200_OK;
-    k_stats<2><<<stats_grid(B), kStatBlock, 0, st>>>(B, est, est_stride, gt, gt_stride, class_id, n_class, mean, sums2);
-    PNP_CUDA_OK(cudaGetLastError());
-    return PNPB200_OK;
+    return stats_launch<1>(B, nq, est, est_stride, gt, gt_stride, class_id, n_class, nullptr, sums1, (cudaStream_t)stream);
+}
+
+int pnpb200_stats_pass2(int64_t B, int nq, const double* const* est, const int64_t* est_stride, const double* const* gt,
+                        const int64_t* gt_stride, const int32_t* class_id, int n_class, const double* mean, double* sums2,
+                        void* stream)
+{
+    return stats_launch<2>(B, nq, est, est_stride, gt, gt_stride, class_id, n_class, mean, sums2, (cudaStream_t)stream);
 }
 
 int pnpb200_classify(int64_t B, const double* values, int64_t stride, double scale, const double* bins, int n_bins,

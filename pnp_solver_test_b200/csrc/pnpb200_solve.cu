@@ -3,15 +3,15 @@
 // Two execution shapes share the solver code in pnpb200_solvers.cuh:
 //
 //  k_solve_thread  one problem per thread.  A CTA is ONE warp that owns 32 consecutive
-//                  problems: their [32, n_total, 2] pixel rows are one contiguous span of HBM,
-//                  read with coalesced 16-byte vector loads, normalised with K^-1 on the way
-//                  (f2_get_B_xy, PNP_SOLVER_LIB.py:3291-3312) and staged in shared memory
-//                  point-major / problem-minor with an odd row stride, so that the 14 solver
-//                  passes read them conflict-free.  The pattern sits in shared memory too and
-//                  is read as a warp-wide broadcast.  All normal equations, factorisations and
-//                  SO(3) work stay in the thread's registers; no shuffles are needed at all.
-//                  Several such one-warp CTAs are resident per SM, so staging of one overlaps
-//                  the FP64 work of the others.
+//                  problems.  Each lane issues one TMA bulk copy (cp.async.bulk, completion on
+//                  an mbarrier) of its problem's [n_total, 2] pixel row from HBM into a padded
+//                  shared-memory row (row pitch = odd multiple of 16 B, so the per-lane 16-byte
+//                  reads of the 14 solver passes are bank-conflict free), then normalises its
+//                  row in place with K^-1 (f2_get_B_xy, PNP_SOLVER_LIB.py:3291-3312).  The
+//                  pattern sits in shared memory too and is read as a warp-wide broadcast.
+//                  All normal equations, factorisations and SO(3) work stay in the thread's
+//                  registers; no shuffles are needed at all.  Several such one-warp CTAs are
+//                  resident per SM, so the copy of one overlaps the FP64 work of the others.
 //  k_solve_warp    one problem per warp for large n (n = 1024): lanes stride over the points
 //                  with coalesced vector loads straight from global memory (L1/L2 resident
 //                  across iterations), partial sums are combined with shuffle butterflies.
@@ -68,6 +68,8 @@ struct SolveArgs {
     const int32_t* idx;     // [n] device, or nullptr
     long long B;
     int n_total, n, n_patterns;
+    int row_pitch;          // thread mapping: shared-memory row pitch in elements of T
+    int use_tma;            // rows are 16-byte aligned multiples of 16 bytes -> cp.async.bulk
     double kinv[6];         // first two rows of K^-1
     SolverPrm<T> prm;
     T* R; T* t; T* euler; T* res;
@@ -78,17 +80,50 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };
 template <> struct Vec2<float> { typedef float2 type; };
 
-// normalised correspondences of one problem, staged in shared memory (thread mapping)
+// normalised correspondences of one problem: that problem's row in shared memory (thread mapping)
 template <typename T>
-struct PtsShared {
-    const T* base;   // &sB[problem slot]
-    int stride;      // row stride (problems per tile + 1)
+struct PtsRow {
+    const T* row;          // [n_total][2], already multiplied by K^-1
+    const int32_t* idx;    // shared-memory copy of the landmark selection, or nullptr
     PNP_DEV void get(int i, T& bx, T& by) const
     {
-        bx = base[(2 * i) * stride];
-        by = base[(2 * i + 1) * stride];
+        const int j = idx ? idx[i] : i;
+        const typename Vec2<T>::type p = reinterpret_cast<const typename Vec2<T>::type*>(row)[j];
+        bx = p.x;
+        by = p.y;
     }
 };
+
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+PNP_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PNP_DEV void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PNP_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PNP_DEV void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+PNP_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+PNP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // raw pixels of one problem in global memory, normalised on the fly (warp mapping)
 template <typename T>
@@ -210,17 +245,48 @@ PNP_DEV void load_pattern(const SolveArgs<T>& a, T* sP, T* sC, int32_t* sIdx, in
 // one problem per thread; CTA = 1 warp = 32 consecutive problems
 // ------------------------------------------------------------------------------------------
 constexpr int kTileProblems = 32;
-constexpr int kTileStride = kTileProblems + 1;
 
 template <typename T, int METHOD>
 __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ SolveArgs<T> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sP = reinterpret_cast<T*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [tile rows | pattern | constants | index | mbarrier]
+    T* sRows = reinterpret_cast<T*>(smem_raw);
+    T* sP = sRows + (size_t)kTileProblems * a.row_pitch;
     T* sC = sP + (size_t)a.n_patterns * a.n * 3;
-    T* sB = sC + a.n_patterns * PNP_PATC;
-    int32_t* sIdx = reinterpret_cast<int32_t*>(sB + (size_t)2 * a.n * kTileStride);
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sC + a.n_patterns * PNP_PATC);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((unsigned char*)(sIdx + (a.idx ? a.n : 0)) - smem_raw) + 7) & ~(size_t)7));
     const int lane = threadIdx.x;
+    typedef typename Vec2<T>::type V2;
+
+    if (a.use_tma) {
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+    }
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    const uint32_t row_bytes = (uint32_t)a.n_total * 2u * (uint32_t)sizeof(T);
+    uint32_t phase = 0;
+    // kick off the first tile's copies before touching the pattern so the two overlap
+    long long tile = blockIdx.x;
+    auto issue_tile = [&](long long tl) {
+        const long long b0 = tl * kTileProblems;
+        const int valid = (int)((a.B - b0 < kTileProblems) ? (a.B - b0) : kTileProblems);
+        if (a.use_tma) {
+            if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)valid);
+            __syncwarp();
+            if (lane < valid)
+                bulk_copy_g2s(sRows + (size_t)lane * a.row_pitch, a.uv + (size_t)(b0 + lane) * a.n_total * 2, row_bytes, bar);
+        } else {
+            // rows not 16-byte granular (FP32 with odd n_total): coalesced element loads instead
+            const int per_row = a.n_total * 2;
+            for (int e = lane; e < valid * per_row; e += 32) {
+                const int p = e / per_row, c = e - p * per_row;
+                sRows[(size_t)p * a.row_pitch + c] = __ldg(a.uv + (size_t)b0 * per_row + e);
+            }
+        }
+        return valid;
+    };
+    int valid = (tile < n_tiles) ? issue_tile(tile) : 0;
 
     load_pattern<T>(a, sP, sC, sIdx, lane, 32);
     if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
@@ -229,36 +295,39 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
     }
     const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
     const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
-    typedef typename Vec2<T>::type V2;
 
-    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (; tile < n_tiles;) {
         const long long b0 = tile * kTileProblems;
-        // ---- stage + normalise the tile: element e = (problem p, point i), coalesced in HBM
-        const int n = a.n;
-        int p = 0, i = lane;
-        while (i >= n) { i -= n; ++p; }
-        for (; p < kTileProblems;) {
-            long long b = b0 + p;
-            if (b >= a.B) b = a.B - 1;                    // ragged last tile: replicate, never written
-            const int src = a.idx ? sIdx[i] : i;
-            const V2 px = __ldg(reinterpret_cast<const V2*>(a.uv) + (size_t)b * a.n_total + src);
-            sB[(2 * i) * kTileStride + p] = k00 * px.x + k01 * px.y + k02;
-            sB[(2 * i + 1) * kTileStride + p] = k10 * px.x + k11 * px.y + k12;
-            i += 32;
-            while (i >= n) { i -= n; ++p; }
+        if (a.use_tma) { mbar_wait(bar, phase); phase ^= 1u; }
+        else           { __syncwarp(); }
+        // ---- lane <-> problem; a ragged tile's spare lanes shadow its last valid problem
+        const int my = (lane < valid) ? lane : (valid - 1);
+        T* row = sRows + (size_t)my * a.row_pitch;
+        if (lane < valid) {                               // nu = K^-1 [u, v, 1]^T in place (:3305)
+            V2* r2 = reinterpret_cast<V2*>(row);
+            for (int i = 0; i < a.n_total; ++i) {
+                const V2 px = r2[i];
+                V2 o;
+                o.x = k00 * px.x + k01 * px.y + k02;
+                o.y = k10 * px.x + k11 * px.y + k12;
+                r2[i] = o;
+            }
         }
         __syncwarp();
-        // ---- solve: lane <-> problem
-        PtsShared<T> pts;
-        pts.base = sB + lane;
-        pts.stride = kTileStride;
+        PtsRow<T> pts;
+        pts.row = row;
+        pts.idx = a.idx ? sIdx : nullptr;
         Result<T> best;
         int best_p;
-        solve_all_patterns<T, METHOD, 1, PtsShared<T> >(pts, sP, sC, n, a.n_patterns, 0, a.prm, best, best_p);
+        solve_all_patterns<T, METHOD, 1, PtsRow<T> >(pts, sP, sC, a.n, a.n_patterns, 0, a.prm, best, best_p);
         const long long b = b0 + lane;
         if (b < a.B) write_result<T>(a, b, best, best_p);
-        __syncwarp();
+        tile += gridDim.x;
+        if (tile < n_tiles) {
+            __syncwarp();
+            fence_proxy_async();                          // generic-proxy writes above before the next async-proxy fill
+            valid = issue_tile(tile);
+        }
     }
 }
 
@@ -332,17 +401,26 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     if (rc != PNPB200_OK) return rc;
     const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
     const size_t idx_bytes = a.idx ? (size_t)a.n * sizeof(int32_t) : 0;
-    const size_t thread_smem = pat_bytes + (size_t)2 * a.n * kTileStride * sizeof(T) + idx_bytes;
+    // thread mapping: row pitch = odd multiple of 16 bytes (conflict-free 16-byte reads, TMA-aligned)
+    const size_t row_bytes = (size_t)a.n_total * 2 * sizeof(T);
+    size_t units = (row_bytes + 15) / 16;
+    if ((units & 1) == 0) ++units;
+    const int row_pitch = (int)(units * 16 / sizeof(T));
+    const int use_tma = (row_bytes % 16 == 0) ? 1 : 0;
+    const size_t thread_smem = (size_t)kTileProblems * row_pitch * sizeof(T) + pat_bytes + idx_bytes + 16;
     const size_t warp_smem = pat_bytes + idx_bytes;
     if (mapping == PNPB200_MAP_AUTO)
-        mapping = ((size_t)a.n * sizeof(T) <= 96 * 8 && thread_smem <= (size_t)dp.max_smem_optin / 2) ? PNPB200_MAP_THREAD
-                                                                                                    : PNPB200_MAP_WARP;
+        mapping = ((size_t)a.n_total * sizeof(T) <= 96 * 8 && thread_smem <= (size_t)dp.max_smem_optin / 2) ? PNPB200_MAP_THREAD
+                                                                                                          : PNPB200_MAP_WARP;
     if (mapping == PNPB200_MAP_THREAD) {
         if (thread_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
         PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_thread<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
+        SolveArgs<T> at = a;
+        at.row_pitch = row_pitch;
+        at.use_tma = use_tma;
         const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
         const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
-        k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(a);
+        k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(at);
     } else if (mapping == PNPB200_MAP_WARP) {
         if (warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
         PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_warp<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
@@ -368,6 +446,7 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     SolveArgs<T> a;
     a.uv = (const T*)uv; a.pattern = (const T*)pattern; a.idx = idx_dev;
     a.B = B; a.n_total = n_total; a.n = n; a.n_patterns = n_patterns;
+    a.row_pitch = 0; a.use_tma = 0;
     double Kinv[9];
     host_inv3(K, Kinv);
     for (int e = 0; e < 6; ++e) a.kinv[e] = Kinv[e];

@@ -294,11 +294,13 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
     T res = T(1e5);
     for (int it = 0; it < prm.max_it; ++it) {             // :2642, fixed count, no exit test
         const T gam = x[GG], d1 = x[D1], d2 = x[D2];
-        // ---- state-dependent sums over the correspondences
-        T sg1[3], sg2[3], sg3[3], r1[3], r2[3], r3[3];
+        // ---- state-dependent sums over the correspondences: only what involves the residual
+        //      (z - hx) is accumulated point by point; the gamma column of J^T J is a bilinear
+        //      form of the moments (no cancellation: its terms have the size of the result)
+        T r1[3], r2[3], r3[3];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) { sg1[e] = sg2[e] = sg3[e] = r1[e] = r2[e] = r3[e] = T(0); }
-        T s1 = T(0), s2 = T(0), sgg = T(0), q1 = T(0), q2 = T(0), qg = T(0), rr = T(0);
+        for (int e = 0; e < 3; ++e) { r1[e] = r2[e] = r3[e] = T(0); }
+        T q1 = T(0), q2 = T(0), qg = T(0), rr = T(0);
         for (int i = sub; i < n; i += LPP) {
             const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
             T bx, by;
@@ -309,20 +311,34 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
             const T g1 = a - bx * c, g2 = b - by * c;     // hu1_bar, hu2_bar (:3738-3741)
             const T rx = bx - (gam * g1 + d1);            // z - hx (:3750, :2679)
             const T ry = by - (gam * g2 + d2);
-            const T w3 = bx * g1 + by * g2, v3 = bx * rx + by * ry;
+            const T v3 = bx * rx + by * ry;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                sg1[k] = t_fma(th[k], g1, sg1[k]); sg2[k] = t_fma(th[k], g2, sg2[k]); sg3[k] = t_fma(th[k], w3, sg3[k]);
-                r1[k] = t_fma(th[k], rx, r1[k]);   r2[k] = t_fma(th[k], ry, r2[k]);   r3[k] = t_fma(th[k], v3, r3[k]);
+                r1[k] = t_fma(th[k], rx, r1[k]); r2[k] = t_fma(th[k], ry, r2[k]); r3[k] = t_fma(th[k], v3, r3[k]);
             }
-            s1 += g1; s2 += g2; sgg = t_fma(g1, g1, t_fma(g2, g2, sgg));
             q1 += rx; q2 += ry; qg = t_fma(g1, rx, t_fma(g2, ry, qg));
             rr = t_fma(rx, rx, t_fma(ry, ry, rr));
         }
-        group_sum_arr<LPP>(sg1); group_sum_arr<LPP>(sg2); group_sum_arr<LPP>(sg3);
         group_sum_arr<LPP>(r1); group_sum_arr<LPP>(r2); group_sum_arr<LPP>(r3);
-        s1 = group_sum<LPP>(s1); s2 = group_sum<LPP>(s2); sgg = group_sum<LPP>(sgg);
         q1 = group_sum<LPP>(q1); q2 = group_sum<LPP>(q2); qg = group_sum<LPP>(qg); rr = group_sum<LPP>(rr);
+        // sg1 = sum th g1 = M0 u1 - Mx u3;  sg2 = M0 u2 - My u3;  sg3 = sum th (bx g1 + by g2) = Mx u1 + My u2 - Mw u3
+        // s1 = sum g1 = m0.u1 - mx.u3;  s2 = m0.u2 - my.u3;  sgg = sum g1^2 + g2^2 = u1.sg1 + u2.sg2 - u3.sg3
+        T sg1[3], sg2[3], sg3[3], s1 = T(0), s2 = T(0), sgg = T(0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            T e1 = T(0), e2 = T(0), e3 = T(0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                e1 = t_fma(sC[s3(k, j)], x[j], t_fma(-Mx[s3(k, j)], x[6 + j], e1));
+                e2 = t_fma(sC[s3(k, j)], x[3 + j], t_fma(-My[s3(k, j)], x[6 + j], e2));
+                e3 = t_fma(Mx[s3(k, j)], x[j], t_fma(My[s3(k, j)], x[3 + j], t_fma(-Mw[s3(k, j)], x[6 + j], e3)));
+            }
+            sg1[k] = e1; sg2[k] = e2; sg3[k] = e3;
+            s1 = t_fma(sC[6 + k], x[k], t_fma(-mx[k], x[6 + k], s1));
+            s2 = t_fma(sC[6 + k], x[3 + k], t_fma(-my[k], x[6 + k], s2));
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sgg = t_fma(x[k], sg1[k], t_fma(x[3 + k], sg2[k], t_fma(-x[6 + k], sg3[k], sgg)));
         res = t_sqrt(rr);                                 // res_norm of the state BEFORE the update (:2681)
 
         // ---- A = J^T J + lambda I (:2666-2667), g = J^T (z - hx) (:2684)

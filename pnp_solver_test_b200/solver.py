@@ -72,6 +72,8 @@ def solve_batch(method, uv, patterns, K, point_index=None, params=None, want=("R
     if "iters" in want: o["iters"] = torch.empty((B,), dtype=torch.int32, device=dev)
     if "best_pattern" in want: o["best_pattern"] = torch.empty((B,), dtype=torch.int32, device=dev)
     Kh, Kp = _k_host(K)
+    if B == 0:
+        return o
     with torch.cuda.device(dev):
         rc = lib.pnpb200_solve_batch(
             C.c_int(m), C.c_int(dt), C.c_int64(B), C.c_int(n_total), C.c_int(n), ptr(uv), ptr(patterns),

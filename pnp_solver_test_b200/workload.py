@@ -110,54 +110,65 @@ def _all_reduce(t, op, group):
 
 
 def reduce_phase1(s1, group=None):
-    """all_reduce(SUM) of the pass-1 sums [n_class,4] = (n, sum est/gt, sum e, 0); returns the
-    global per-class error mean.  Works on any backend (NCCL on GPUs, gloo in CPU tests)."""
+    """all_reduce(SUM) of the pass-1 sums [..., 4] = (n, sum est/gt, sum e, 0); returns the global
+    per-row error mean.  Works on any backend (NCCL on GPUs, gloo in CPU tests)."""
     import torch.distributed as dist
     _all_reduce(s1, dist.ReduceOp.SUM, group)
-    return (s1[:, 2] / s1[:, 0]).contiguous()
+    return (s1[..., 2] / s1[..., 0]).contiguous()
 
 
 def reduce_phase2(s2, group=None):
-    """pass-2 sums [n_class,4] = (sum (e-m)^2, sum |e|, sum |e-m|, max |e-m|): SUM the first
-    three columns, MAX the last."""
+    """pass-2 sums [..., 4] = (sum (e-m)^2, sum |e|, sum |e-m|, max |e-m|): SUM the first three
+    columns, MAX the last."""
     import torch.distributed as dist
-    sm = s2[:, :3].contiguous()
-    mx = s2[:, 3].contiguous()
+    sm = s2[..., :3].contiguous()
+    mx = s2[..., 3].contiguous()
     _all_reduce(sm, dist.ReduceOp.SUM, group)
     _all_reduce(mx, dist.ReduceOp.MAX, group)
-    return torch.cat([sm, mx[:, None]], dim=1)
+    return torch.cat([sm, mx[..., None]], dim=-1)
 
 
 def finalize_stats(s1, s2):
-    """(n, m_ratio, mean, stddev [population], max_dev, MAE_2_GT, MAE_2_mean) per class
+    """(n, m_ratio, mean, stddev [population], max_dev, MAE_2_GT, MAE_2_mean) per row
     (TEST_TOOLBOX.py:907-915, :928-935)."""
-    n = s1[:, 0]
-    return torch.stack([n, s1[:, 1] / n, s1[:, 2] / n, torch.sqrt(s2[:, 0] / n), s2[:, 3], s2[:, 1] / n, s2[:, 2] / n], dim=1)
+    n = s1[..., 0]
+    return torch.stack([n, s1[..., 1] / n, s1[..., 2] / n, torch.sqrt(s2[..., 0] / n), s2[..., 3], s2[..., 1] / n, s2[..., 2] / n], dim=-1)
 
 
 def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=True):
-    """get_statistic_of_result (TEST_TOOLBOX.py:892-937) per class, over ALL ranks' shards.
+    """get_statistic_of_result (TEST_TOOLBOX.py:892-937) for up to 4 quantities at once, per class
+    and over all problems, over ALL ranks' shards.
 
-    est, gt: 1-D FP64 CUDA views (strided allowed) of this rank's shard; class_id int32 or None.
-    Two phases (SURVEY.md 8e): all_reduce(SUM) of [n, sum est/gt, sum e] -> global means;
-    all_reduce(SUM) of [sum (e-m)^2, sum |e|, sum |e-m|] and all_reduce(MAX) of max |e-m|.
-    Returns a float64 CPU tensor [n_class, 7] in STAT_KEYS order (NaN rows for empty classes)."""
-    dev = est.device
-    B = int(est.shape[0])
-    dp = lambda x: None if x is None else C.cast(ptr(x), C.POINTER(C.c_double))
-    s1 = torch.empty((n_class, 4), dtype=torch.float64, device=dev)
+    est, gt: lists of 1-D FP64 CUDA views (strided allowed) of this rank's shard (gt entries or gt
+    itself may be None); class_id int32 [B] or None.  Two phases: all_reduce(SUM) of
+    [n, sum est/gt, sum e] -> global means; all_reduce(SUM) of [sum (e-m)^2, sum |e|, sum |e-m|] and
+    all_reduce(MAX) of max |e-m|.  Returns a float64 CPU tensor [nq, n_class+1, 7] in STAT_KEYS
+    order; the last row of each quantity is the class 'all'; empty classes have n = 0."""
+    if torch.is_tensor(est):
+        est, gt = [est], [gt]
+    nq = len(est)
+    gt = list(gt) if gt is not None else [None] * nq
+    dev = est[0].device
+    B = int(est[0].shape[0])
+    PD = C.POINTER(C.c_double)
+    dp = lambda x: None if x is None else C.cast(ptr(x), PD)
+    est_a = (PD * nq)(*[dp(e) for e in est])
+    gt_a = (PD * nq)(*[dp(g) for g in gt])
+    es_a = (C.c_int64 * nq)(*[int(e.stride(0)) if B else 1 for e in est])
+    gs_a = (C.c_int64 * nq)(*[(int(g.stride(0)) if B else 1) if g is not None else 0 for g in gt])
+    for e in est:
+        assert e.dtype == torch.float64 and e.dim() == 1 and int(e.shape[0]) == B
     cid = None if class_id is None else C.cast(ptr(class_id), C.POINTER(C.c_int32))
-    es = est.stride(0) if B else 1
-    gs = (gt.stride(0) if B else 1) if gt is not None else 0
+    s1 = torch.empty((nq, n_class + 1, 4), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        check(lib.pnpb200_stats_pass1(C.c_int64(B), dp(est), C.c_int64(es), dp(gt), C.c_int64(gs), cid, C.c_int(n_class),
+        check(lib.pnpb200_stats_pass1(C.c_int64(B), C.c_int(nq), est_a, es_a, gt_a, gs_a, cid, C.c_int(n_class),
                                       dp(s1), _stream_ptr(dev)), "pnpb200_stats_pass1")
     _lib.count_launch()
-    mean = reduce_phase1(s1, group) if distributed else (s1[:, 2] / s1[:, 0]).contiguous()
+    mean = reduce_phase1(s1, group) if distributed else (s1[..., 2] / s1[..., 0]).contiguous()
     mean = torch.nan_to_num(mean).contiguous()
-    s2 = torch.empty((n_class, 4), dtype=torch.float64, device=dev)
+    s2 = torch.empty((nq, n_class + 1, 4), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        check(lib.pnpb200_stats_pass2(C.c_int64(B), dp(est), C.c_int64(es), dp(gt), C.c_int64(gs), cid, C.c_int(n_class),
+        check(lib.pnpb200_stats_pass2(C.c_int64(B), C.c_int(nq), est_a, es_a, gt_a, gs_a, cid, C.c_int(n_class),
                                       dp(mean), dp(s2), _stream_ptr(dev)), "pnpb200_stats_pass2")
     _lib.count_launch()
     if distributed:
@@ -166,15 +177,13 @@ def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=T
 
 
 def error_statistics(report, gt, group=None, distributed=True):
-    """The statistics block of TEST_TOOLBOX.data_analysis_and_saving (:1070-1346) for the four
-    reported quantities, for class 'all' and per GT-depth class.  report: [B,16] from
-    report_batch; gt [B,4].  Returns {quantity: {'all': stats[7], 'by_depth': stats[12,7]}}."""
-    out = {}
+    """The statistics block of TEST_TOOLBOX.data_analysis_and_saving (:1070-1112) for the four
+    reported quantities, for class 'all' and per GT-depth class, in two kernels and two all-reduce
+    phases.  report: [B,16] from report_batch; gt [B,4].
+    Returns {quantity: {'all': stats[7], 'by_depth': stats[12,7]}} (CPU tensors, STAT_KEYS order)."""
     cls = classify(gt[:, 0], CLASS_BINS["depth"], scale=100.0)
-    # (estimate column, GT source): depth compares t3_est with distance_GT (:1118), angles est vs GT
-    cols = {"depth": (report[:, 10], report[:, 11]), "roll": (report[:, 12], gt[:, 1]),
-            "pitch": (report[:, 13], gt[:, 2]), "yaw": (report[:, 14], gt[:, 3])}
-    for name, (e, g) in cols.items():
-        out[name] = dict(all=statistics(e, g, None, 1, group, distributed)[0],
-                         by_depth=statistics(e, g, cls, len(CLASS_LABELS["depth"]), group, distributed))
-    return out
+    # (estimate, GT): depth compares t3_est with distance_GT (:1073), the angles est vs GT
+    est = [report[:, 10], report[:, 12], report[:, 13], report[:, 14]]
+    ref = [report[:, 11], gt[:, 1], gt[:, 2], gt[:, 3]]
+    st = statistics(est, ref, cls, len(CLASS_LABELS["depth"]), group, distributed)
+    return {name: dict(all=st[q, -1], by_depth=st[q, :-1]) for q, name in enumerate(("depth", "roll", "pitch", "yaw"))}

@@ -61,7 +61,7 @@ def _stats_worker(rank, world_size, port, q):
         m = c == k
         s1[k] = [m.sum(), (e[m] / t[m]).sum(), (e[m] - t[m]).sum(), 0.0]
     s1 = torch.from_numpy(s1)
-    mean = torch.nan_to_num(wl.reduce_phase1(s1)).numpy()
+    mean = torch.nan_to_num(wl.reduce_phase1(s1)).numpy()          # [n_class]
     s2 = np.zeros((n_class, 4))
     for k in range(n_class):
         m = c == k
