@@ -42,6 +42,8 @@ extern "C" {
 /* execution shape (0 = let the library choose from n) */
 #define PNPB200_MAP_AUTO    0
 #define PNPB200_MAP_THREAD  1   /* one problem per thread, correspondences staged in shared memory */
+#define PNPB200_MAP_MOMENT  2   /* LM / linear F2, one pattern: moments -> O(1) iterations ->      */
+                                /* point-wise residual, as three streaming kernels (default there) */
 #define PNPB200_MAP_WARP    32  /* one problem per warp, shuffle-reduced normal equations          */
 
 #define PNPB200_OK          0

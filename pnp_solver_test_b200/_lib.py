@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libpnpb200.so")
 METHOD_QEIF, METHOD_LM, METHOD_LINEAR_F2, METHOD_LINEAR_F1 = 0, 1, 2, 3
 METHODS = {"qeif": 0, "lm": 1, "linear_f2": 2, "linear_f1": 3}
 DTYPE_F64, DTYPE_F32 = 0, 1
-MAP_AUTO, MAP_THREAD, MAP_WARP = 0, 1, 32
+MAP_AUTO, MAP_THREAD, MAP_MOMENT, MAP_WARP = 0, 1, 2, 32
 REPORT_WIDTH = 16
 MAX_PATTERNS = 8
 

@@ -225,27 +225,110 @@ PNP_DEV void write_result(const SolveArgs<T>& a, long long b, const Result<T>& r
     if (a.best) a.best[b] = best_p;
 }
 
-// shared-memory carve-up common to both kernels: [pattern | constants | (index) | tile]
+// pattern (restricted to the selected landmarks, in selection order) and the selection -> shared memory
 template <typename T>
-PNP_DEV void load_pattern(const SolveArgs<T>& a, T* sP, T* sC, int32_t* sIdx, int tid, int nthreads)
+PNP_DEV void load_pattern(const T* __restrict__ pattern, const int32_t* __restrict__ idx, int n_total, int n, int n_patterns,
+                          T* sP, int32_t* sIdx, int tid, int nthreads)
 {
-    if (a.idx) {
-        for (int i = tid; i < a.n; i += nthreads) sIdx[i] = a.idx[i];
+    if (idx) {
+        for (int i = tid; i < n; i += nthreads) sIdx[i] = idx[i];
         __syncthreads();
     }
-    for (int e = tid; e < a.n_patterns * a.n * 3; e += nthreads) {
-        const int p = e / (a.n * 3), r = e - p * (a.n * 3), i = r / 3, c = r - 3 * i;
-        const int src = a.idx ? sIdx[i] : i;
-        sP[e] = a.pattern[((size_t)p * a.n_total + src) * 3 + c];
+    for (int e = tid; e < n_patterns * n * 3; e += nthreads) {
+        const int p = e / (n * 3), r = e - p * (n * 3), i = r / 3, c = r - 3 * i;
+        const int src = idx ? sIdx[i] : i;
+        sP[e] = pattern[((size_t)p * n_total + src) * 3 + c];
     }
     __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
-// one problem per thread; CTA = 1 warp = 32 consecutive problems
+// Row tile: 32 consecutive problems' pixel rows staged in shared memory by one warp.
+// Lane l issues one TMA bulk copy of row l (completion on an mbarrier), waits, and multiplies its
+// row by K^-1 in place (f2_get_B_xy :3291-3312).  Row pitch = odd multiple of 16 B.
 // ------------------------------------------------------------------------------------------
 constexpr int kTileProblems = 32;
 
+template <typename T>
+struct RowTile {
+    T* rows;
+    uint64_t* bar;
+    const T* uv;
+    long long B;
+    int n_total, row_pitch, use_tma;
+    uint32_t phase, row_bytes;
+    T k00, k01, k02, k10, k11, k12;
+
+    PNP_DEV void init(T* rows_, uint64_t* bar_, const T* uv_, long long B_, int n_total_, int row_pitch_, int use_tma_,
+                      const double* kinv, int lane)
+    {
+        rows = rows_; bar = bar_; uv = uv_; B = B_; n_total = n_total_; row_pitch = row_pitch_; use_tma = use_tma_;
+        phase = 0; row_bytes = (uint32_t)n_total * 2u * (uint32_t)sizeof(T);
+        k00 = (T)kinv[0]; k01 = (T)kinv[1]; k02 = (T)kinv[2]; k10 = (T)kinv[3]; k11 = (T)kinv[4]; k12 = (T)kinv[5];
+        if (use_tma) {
+            if (lane == 0) mbar_init(bar, 1);
+            __syncwarp();
+        }
+    }
+    // start filling the tile; returns the number of valid problems in it
+    PNP_DEV int issue(long long tile, int lane)
+    {
+        const long long b0 = tile * kTileProblems;
+        const int valid = (int)((B - b0 < kTileProblems) ? (B - b0) : kTileProblems);
+        if (use_tma) {
+            if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)valid);
+            __syncwarp();
+            if (lane < valid) bulk_copy_g2s(rows + (size_t)lane * row_pitch, uv + (size_t)(b0 + lane) * n_total * 2, row_bytes, bar);
+        } else {
+            // rows not 16-byte granular (FP32 with odd n_total): coalesced element loads instead
+            const int per_row = n_total * 2;
+            for (int e = lane; e < valid * per_row; e += 32) {
+                const int p = e / per_row, c = e - p * per_row;
+                rows[(size_t)p * row_pitch + c] = __ldg(uv + (size_t)b0 * per_row + e);
+            }
+        }
+        return valid;
+    }
+    // wait for the fill, normalise, return this lane's row (spare lanes of a ragged tile shadow
+    // the last valid problem so that the whole warp stays converged)
+    PNP_DEV const T* acquire(int lane, int valid)
+    {
+        typedef typename Vec2<T>::type V2;
+        if (use_tma) { mbar_wait(bar, phase); phase ^= 1u; }
+        else         { __syncwarp(); }
+        const int my = (lane < valid) ? lane : (valid - 1);
+        T* row = rows + (size_t)my * row_pitch;
+        if (lane < valid) {                               // nu = K^-1 [u, v, 1]^T (:3305)
+            V2* r2 = reinterpret_cast<V2*>(row);
+#pragma unroll 4
+            for (int i = 0; i < n_total; ++i) {
+                const V2 px = r2[i];
+                V2 o;
+                o.x = k00 * px.x + k01 * px.y + k02;
+                o.y = k10 * px.x + k11 * px.y + k12;
+                r2[i] = o;
+            }
+        }
+        __syncwarp();
+        return row;
+    }
+    // generic-proxy accesses to the tile are done; the next async-proxy fill may start
+    PNP_DEV void release()
+    {
+        __syncwarp();
+        fence_proxy_async();
+    }
+};
+
+template <typename T>
+PNP_DEV uint64_t* carve_bar(unsigned char* smem_raw, const void* after)
+{
+    return reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((const unsigned char*)after - smem_raw) + 7) & ~(size_t)7));
+}
+
+// ------------------------------------------------------------------------------------------
+// direct mapping, one problem per thread; CTA = 1 warp = 32 consecutive problems
+// ------------------------------------------------------------------------------------------
 template <typename T, int METHOD>
 __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ SolveArgs<T> a)
 {
@@ -255,67 +338,23 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
     T* sP = sRows + (size_t)kTileProblems * a.row_pitch;
     T* sC = sP + (size_t)a.n_patterns * a.n * 3;
     int32_t* sIdx = reinterpret_cast<int32_t*>(sC + a.n_patterns * PNP_PATC);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((unsigned char*)(sIdx + (a.idx ? a.n : 0)) - smem_raw) + 7) & ~(size_t)7));
     const int lane = threadIdx.x;
-    typedef typename Vec2<T>::type V2;
+    RowTile<T> tile_buf;
+    tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (a.idx ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
 
-    if (a.use_tma) {
-        if (lane == 0) mbar_init(bar, 1);
-        __syncwarp();
-    }
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
-    const uint32_t row_bytes = (uint32_t)a.n_total * 2u * (uint32_t)sizeof(T);
-    uint32_t phase = 0;
-    // kick off the first tile's copies before touching the pattern so the two overlap
     long long tile = blockIdx.x;
-    auto issue_tile = [&](long long tl) {
-        const long long b0 = tl * kTileProblems;
-        const int valid = (int)((a.B - b0 < kTileProblems) ? (a.B - b0) : kTileProblems);
-        if (a.use_tma) {
-            if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)valid);
-            __syncwarp();
-            if (lane < valid)
-                bulk_copy_g2s(sRows + (size_t)lane * a.row_pitch, a.uv + (size_t)(b0 + lane) * a.n_total * 2, row_bytes, bar);
-        } else {
-            // rows not 16-byte granular (FP32 with odd n_total): coalesced element loads instead
-            const int per_row = a.n_total * 2;
-            for (int e = lane; e < valid * per_row; e += 32) {
-                const int p = e / per_row, c = e - p * per_row;
-                sRows[(size_t)p * a.row_pitch + c] = __ldg(a.uv + (size_t)b0 * per_row + e);
-            }
-        }
-        return valid;
-    };
-    int valid = (tile < n_tiles) ? issue_tile(tile) : 0;
-
-    load_pattern<T>(a, sP, sC, sIdx, lane, 32);
+    // kick off the first tile's copies before touching the pattern so the two overlap
+    int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
+    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, a.n_patterns, sP, sIdx, lane, 32);
     if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
         for (int p = 0; p < a.n_patterns; ++p) pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncwarp();
     }
-    const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
-    const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
-
-    for (; tile < n_tiles;) {
+    while (tile < n_tiles) {
         const long long b0 = tile * kTileProblems;
-        if (a.use_tma) { mbar_wait(bar, phase); phase ^= 1u; }
-        else           { __syncwarp(); }
-        // ---- lane <-> problem; a ragged tile's spare lanes shadow its last valid problem
-        const int my = (lane < valid) ? lane : (valid - 1);
-        T* row = sRows + (size_t)my * a.row_pitch;
-        if (lane < valid) {                               // nu = K^-1 [u, v, 1]^T in place (:3305)
-            V2* r2 = reinterpret_cast<V2*>(row);
-            for (int i = 0; i < a.n_total; ++i) {
-                const V2 px = r2[i];
-                V2 o;
-                o.x = k00 * px.x + k01 * px.y + k02;
-                o.y = k10 * px.x + k11 * px.y + k12;
-                r2[i] = o;
-            }
-        }
-        __syncwarp();
         PtsRow<T> pts;
-        pts.row = row;
+        pts.row = tile_buf.acquire(lane, valid);
         pts.idx = a.idx ? sIdx : nullptr;
         Result<T> best;
         int best_p;
@@ -324,11 +363,223 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
         if (b < a.B) write_result<T>(a, b, best, best_p);
         tile += gridDim.x;
         if (tile < n_tiles) {
-            __syncwarp();
-            fence_proxy_async();                          // generic-proxy writes above before the next async-proxy fill
-            valid = issue_tile(tile);
+            tile_buf.release();
+            valid = tile_buf.issue(tile, lane);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// moment mapping (LM and linear F2, one pattern): three streaming kernels
+//   k_moments_*   uv -> 29 moments per problem            (HBM-bound: reads every pixel once)
+//   k_iterate     moments -> pose, one problem per thread (FP64 pipe; no shared-memory residency,
+//                 so occupancy is bounded by registers only)
+//   k_residual_*  uv + state before the last update -> res_norm, point by point (HBM-bound)
+// Workspace (stream-ordered allocation): mom [PNP_NMOM][B], tail [PNP_NTAIL][B], patc [PNP_PATC].
+// ------------------------------------------------------------------------------------------
+#define PNP_NTAIL 12
+
+template <typename T>
+struct MomArgs {
+    const T* uv; const T* pattern; const int32_t* idx;
+    long long B;
+    int n_total, n, row_pitch, use_tma;
+    double kinv[6];
+    SolverPrm<T> prm;
+    T* mom; T* tail; T* patc;
+    T* R; T* t; T* euler; T* res;
+    int32_t* iters; int32_t* best;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_pattern_constants(const T* __restrict__ pattern, const int32_t* __restrict__ idx, int n, T* patc)
+{
+    // one warp; reads the (selected) pattern straight from global memory
+    const int lane = threadIdx.x;
+    double acc[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) acc[e] = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const int j = idx ? idx[i] : i;
+        const double th[3] = { (double)pattern[3 * j], (double)pattern[3 * j + 1], (double)pattern[3 * j + 2] };
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) acc[s3(a, b)] = fma(th[a], th[b], acc[s3(a, b)]);
+            acc[6 + a] += th[a];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) acc[e] = group_sum<32, double>(acc[e]);
+    if (lane == 0) {
+        double G[10];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) G[sidx<4>(a, b)] = acc[s3(a, b)];
+            G[sidx<4>(a, 3)] = acc[6 + a];
+        }
+        G[sidx<4>(3, 3)] = (double)n;
+        spd_inverse<double, 4>(G);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) patc[e] = (T)acc[e];
+        patc[9] = (T)n;
+#pragma unroll
+        for (int e = 0; e < 10; ++e) patc[10 + e] = (T)G[e];
+    }
+}
+
+// PASS 0: moments.  PASS 1: residual at the stored state (LM: x before the last update; F2: tail).
+template <typename T, int METHOD, int PASS>
+__global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ MomArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* sRows = reinterpret_cast<T*>(smem_raw);
+    T* sP = sRows + (size_t)kTileProblems * a.row_pitch;
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sP + (size_t)a.n * 3);
+    const int lane = threadIdx.x;
+    RowTile<T> tile_buf;
+    tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (a.idx ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    long long tile = blockIdx.x;
+    int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
+    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, 1, sP, sIdx, lane, 32);
+    while (tile < n_tiles) {
+        const long long b0 = tile * kTileProblems;
+        long long b = b0 + lane;
+        const bool ok = b < a.B;
+        if (!ok) b = a.B - 1;
+        T st[PNP_NTAIL];
+        if (PASS == 1) {                                  // issue the state loads before waiting on the tile
+#pragma unroll
+            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.B + b];
+        }
+        PtsRow<T> pts;
+        pts.row = tile_buf.acquire(lane, valid);
+        pts.idx = a.idx ? sIdx : nullptr;
+        if (PASS == 0) {
+            Moments<T> mom;
+            accumulate_moments<T, 1, PtsRow<T> >(pts, sP, a.n, 0, mom);
+            if (ok) {
+#pragma unroll
+                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.B + b] = mom.at(k);
+            }
+        } else {
+            T res;
+            if (METHOD == PNPB200_METHOD_LM) {
+                T x[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) x[k] = st[k];
+                res = lm_residual_direct<T, 1, PtsRow<T> >(pts, sP, a.n, 0, x);
+            } else {
+                F2Tail<T> f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) f.phi3[k] = st[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { f.pxn[k] = st[3 + k]; f.pyn[k] = st[7 + k]; }
+                res = f2_residual_direct<T, 1, PtsRow<T> >(pts, sP, a.n, 0, f);
+            }
+            if (ok && a.res) a.res[b] = res;
+        }
+        tile += gridDim.x;
+        if (tile < n_tiles) {
+            tile_buf.release();
+            valid = tile_buf.issue(tile, lane);
+        }
+    }
+}
+
+template <typename T, int METHOD, int PASS>
+__global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ MomArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* sP = reinterpret_cast<T*>(smem_raw);
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sP + (size_t)a.n * 3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, 1, sP, sIdx, threadIdx.x, blockDim.x);
+    PtsGlobal<T> pts;
+    pts.idx = a.idx ? sIdx : nullptr;
+    pts.k00 = (T)a.kinv[0]; pts.k01 = (T)a.kinv[1]; pts.k02 = (T)a.kinv[2];
+    pts.k10 = (T)a.kinv[3]; pts.k11 = (T)a.kinv[4]; pts.k12 = (T)a.kinv[5];
+    for (long long b = (long long)blockIdx.x * nwarps + warp; b < a.B; b += (long long)gridDim.x * nwarps) {
+        pts.row = a.uv + (size_t)b * a.n_total * 2;
+        if (PASS == 0) {
+            Moments<T> mom;
+            accumulate_moments<T, 32, PtsGlobal<T> >(pts, sP, a.n, lane, mom);
+            // after the butterfly every lane holds every sum: lane k writes moment k
+            T mine = T(0);
+#pragma unroll
+            for (int k = 0; k < PNP_NMOM; ++k) if (lane == k) mine = mom.at(k);
+            if (lane < PNP_NMOM) a.mom[(size_t)lane * a.B + b] = mine;
+        } else {
+            T res;
+            if (METHOD == PNPB200_METHOD_LM) {
+                T x[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) x[k] = a.tail[(size_t)k * a.B + b];
+                res = lm_residual_direct<T, 32, PtsGlobal<T> >(pts, sP, a.n, lane, x);
+            } else {
+                F2Tail<T> f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) f.phi3[k] = a.tail[(size_t)k * a.B + b];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { f.pxn[k] = a.tail[(size_t)(3 + k) * a.B + b]; f.pyn[k] = a.tail[(size_t)(7 + k) * a.B + b]; }
+                res = f2_residual_direct<T, 32, PtsGlobal<T> >(pts, sP, a.n, lane, f);
+            }
+            if (lane == 0 && a.res) a.res[b] = res;
+        }
+    }
+}
+
+constexpr int kIterBlock = 128;
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(kIterBlock) k_iterate(const __grid_constant__ MomArgs<T> a)
+{
+    __shared__ T sC[PNP_PATC];
+    if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
+    __syncthreads();
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    Moments<T> mom;
+#pragma unroll
+    for (int k = 0; k < PNP_NMOM; ++k) mom.at(k) = a.mom[(size_t)k * a.B + b];
+    Result<T> out;
+    T st[PNP_NTAIL];
+    if (METHOD == PNPB200_METHOD_LM) {
+        T xp[12];
+        solve_lm_from_moments<T>(mom, sC, a.prm, xp, out);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st[k] = xp[k];
+    } else {
+        F2Tail<T> f;
+        solve_f2_from_moments<T>(mom, sC, a.prm, f, out);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st[k] = f.phi3[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { st[3 + k] = f.pxn[k]; st[7 + k] = f.pyn[k]; }
+        st[11] = T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.B + b] = st[k];
+    if (a.R) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) a.R[b * 9 + e] = out.R[e];
+    }
+    if (a.t) {
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a.t[b * 3 + e] = out.t[e];
+    }
+    if (a.euler) {
+        double Rd[9], e3[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rd[e] = (double)out.R[e];
+        euler_from_R(Rd, true, e3);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) a.euler[b * 3 + e] = (T)e3[e];
+    }
+    if (a.iters) a.iters[b] = out.iters;
+    if (a.best) a.best[b] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -339,13 +590,13 @@ constexpr int kWarpsPerBlock = 8;
 template <typename T, int METHOD>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_solve_warp(const __grid_constant__ SolveArgs<T> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* sP = reinterpret_cast<T*>(smem_raw);
     T* sC = sP + (size_t)a.n_patterns * a.n * 3;
     int32_t* sIdx = reinterpret_cast<int32_t*>(sC + a.n_patterns * PNP_PATC);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    load_pattern<T>(a, sP, sC, sIdx, threadIdx.x, blockDim.x);
+    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, a.n_patterns, sP, sIdx, threadIdx.x, blockDim.x);
     if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
         for (int p = warp; p < a.n_patterns; p += kWarpsPerBlock)
             pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
@@ -393,31 +644,102 @@ static void fill_default_params(pnpb200_params* p)
     p->mapping = PNPB200_MAP_AUTO; p->reserved = 0;
 }
 
+struct RowGeom { int row_pitch, use_tma; size_t tile_bytes; };
+
+template <typename T>
+static RowGeom row_geometry(int n_total)
+{
+    // row pitch = odd multiple of 16 bytes (conflict-free 16-byte per-lane reads, TMA-aligned)
+    RowGeom g;
+    const size_t row_bytes = (size_t)n_total * 2 * sizeof(T);
+    size_t units = (row_bytes + 15) / 16;
+    if ((units & 1) == 0) ++units;
+    g.row_pitch = (int)(units * 16 / sizeof(T));
+    g.use_tma = (row_bytes % 16 == 0) ? 1 : 0;
+    g.tile_bytes = (size_t)kTileProblems * g.row_pitch * sizeof(T);
+    return g;
+}
+
+static long long persistent_grid(long long work_items, int sm_count, int per_sm)
+{
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)sm_count * per_sm;      // a multiple of the SM count
+    return work_items < cap ? (work_items < 1 ? 1 : work_items) : cap;
+}
+
+// LM / linear F2 with one pattern: moments -> iterate -> residual (see the kernels' header)
+template <typename T, int METHOD>
+static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStream_t stream)
+{
+    const RowGeom g = row_geometry<T>(a.n_total);
+    const size_t idx_bytes = a.idx ? (size_t)a.n * sizeof(int32_t) : 0;
+    const size_t pat_bytes = (size_t)a.n * 3 * sizeof(T);
+    const size_t thread_smem = g.tile_bytes + pat_bytes + idx_bytes + 16;
+    const size_t warp_smem = pat_bytes + idx_bytes;
+    const bool by_thread = g.tile_bytes <= 48 * 1024 && thread_smem <= (size_t)dp.max_smem_optin;
+    if (!by_thread && warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
+
+    T* ws = nullptr;
+    const size_t ws_elems = (size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)a.B + PNP_PATC;
+    PNP_CUDA_OK(cudaMallocAsync((void**)&ws, ws_elems * sizeof(T), stream));
+    MomArgs<T> m;
+    m.uv = a.uv; m.pattern = a.pattern; m.idx = a.idx; m.B = a.B; m.n_total = a.n_total; m.n = a.n;
+    m.row_pitch = g.row_pitch; m.use_tma = g.use_tma;
+    for (int e = 0; e < 6; ++e) m.kinv[e] = a.kinv[e];
+    m.prm = a.prm;
+    m.mom = ws; m.tail = ws + (size_t)PNP_NMOM * a.B; m.patc = m.tail + (size_t)PNP_NTAIL * a.B;
+    m.R = a.R; m.t = a.t; m.euler = a.euler; m.res = a.res; m.iters = a.iters; m.best = a.best;
+
+    k_pattern_constants<T><<<1, 32, 0, stream>>>(a.pattern, a.idx, a.n, m.patc);
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    if (by_thread) {
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
+        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
+        k_stream_thread<T, METHOD, 0><<<grid, 32, thread_smem, stream>>>(m);
+        k_iterate<T, METHOD><<<(unsigned)((a.B + kIterBlock - 1) / kIterBlock), kIterBlock, 0, stream>>>(m);
+        if (a.res) k_stream_thread<T, METHOD, 1><<<grid, 32, thread_smem, stream>>>(m);
+    } else {
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+        int per_sm = 1;
+        PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp<T, METHOD, 0>, 256, warp_smem));
+        const unsigned grid = (unsigned)persistent_grid((a.B + 7) / 8, dp.sm_count, per_sm);
+        k_stream_warp<T, METHOD, 0><<<grid, 256, warp_smem, stream>>>(m);
+        k_iterate<T, METHOD><<<(unsigned)((a.B + kIterBlock - 1) / kIterBlock), kIterBlock, 0, stream>>>(m);
+        if (a.res) k_stream_warp<T, METHOD, 1><<<grid, 256, warp_smem, stream>>>(m);
+    }
+    PNP_CUDA_OK(cudaGetLastError());
+    PNP_CUDA_OK(cudaFreeAsync(ws, stream));
+    return PNPB200_OK;
+}
+
 template <typename T, int METHOD>
 static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
 {
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc != PNPB200_OK) return rc;
+    constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2);
+    const RowGeom g = row_geometry<T>(a.n_total);
     const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
     const size_t idx_bytes = a.idx ? (size_t)a.n * sizeof(int32_t) : 0;
-    // thread mapping: row pitch = odd multiple of 16 bytes (conflict-free 16-byte reads, TMA-aligned)
-    const size_t row_bytes = (size_t)a.n_total * 2 * sizeof(T);
-    size_t units = (row_bytes + 15) / 16;
-    if ((units & 1) == 0) ++units;
-    const int row_pitch = (int)(units * 16 / sizeof(T));
-    const int use_tma = (row_bytes % 16 == 0) ? 1 : 0;
-    const size_t thread_smem = (size_t)kTileProblems * row_pitch * sizeof(T) + pat_bytes + idx_bytes + 16;
+    const size_t thread_smem = g.tile_bytes + pat_bytes + idx_bytes + 16;
     const size_t warp_smem = pat_bytes + idx_bytes;
-    if (mapping == PNPB200_MAP_AUTO)
-        mapping = ((size_t)a.n_total * sizeof(T) <= 96 * 8 && thread_smem <= (size_t)dp.max_smem_optin / 2) ? PNPB200_MAP_THREAD
-                                                                                                          : PNPB200_MAP_WARP;
+    if (mapping == PNPB200_MAP_AUTO) {
+        if (has_moment_form && a.n_patterns == 1) mapping = PNPB200_MAP_MOMENT;
+        else mapping = (g.tile_bytes <= 48 * 1024 && thread_smem <= (size_t)dp.max_smem_optin) ? PNPB200_MAP_THREAD : PNPB200_MAP_WARP;
+    }
+    if (mapping == PNPB200_MAP_MOMENT) {
+        if (!has_moment_form || a.n_patterns != 1) return PNPB200_EINVAL;
+        if (has_moment_form) return launch_moment<T, has_moment_form ? METHOD : PNPB200_METHOD_LM>(a, dp, stream);
+    }
     if (mapping == PNPB200_MAP_THREAD) {
         if (thread_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
         PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_thread<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
         SolveArgs<T> at = a;
-        at.row_pitch = row_pitch;
-        at.use_tma = use_tma;
+        at.row_pitch = g.row_pitch;
+        at.use_tma = g.use_tma;
         const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
         const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
         k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(at);
@@ -426,10 +748,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
         PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_warp<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
         int per_sm = 1;
         PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_warp<T, METHOD>, kWarpsPerBlock * 32, warp_smem));
-        if (per_sm < 1) per_sm = 1;
-        long long grid = (a.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        const long long cap = (long long)dp.sm_count * per_sm;   // persistent: a multiple of the SM count
-        if (grid > cap) grid = cap;
+        const long long grid = persistent_grid((a.B + kWarpsPerBlock - 1) / kWarpsPerBlock, dp.sm_count, per_sm);
         k_solve_warp<T, METHOD><<<(unsigned)grid, kWarpsPerBlock * 32, warp_smem, stream>>>(a);
     } else {
         return PNPB200_EINVAL;

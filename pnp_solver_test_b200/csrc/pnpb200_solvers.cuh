@@ -255,25 +255,25 @@ PNP_DEV void add_outer1(T (&A)[78], T (&g)[12], const T (&va)[3], T e)
     }
 }
 
-template <typename T, int LPP, typename Pts>
-PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
-                      const SolverPrm<T>& prm, Result<T>& out)
-{
-    constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
-    T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2619-2624
-
-    // ---- state-independent moments of this problem's correspondences (once)
-    //      Mx = sum bx th th^T, My = sum by th th^T, Mw = sum (bx^2+by^2) th th^T,
-    //      mx = sum bx th, my = sum by th
-    T Mx[6], My[6], Mw[6], mx[3], my[3];
+// State-independent moments of one problem's correspondences against the pattern:
+//   Mx = sum bx th th^T, My = sum by th th^T, Mw = sum (bx^2+by^2) th th^T   (packed 3x3 each)
+//   mx = sum bx th, my = sum by th, mw = sum (bx^2+by^2) th, sx0 = sum bx, sy0 = sum by
+// Every block of J^T J of the LM problem is one of these (or the pattern constants M0, m0, n)
+// times a power of gamma, and so are the sums of the linear stage F2 (its D^T B and D^T (B o P)).
+#define PNP_NMOM 29
+template <typename T>
+struct Moments {
+    T Mx[6], My[6], Mw[6], mx[3], my[3], mw[3], sx0, sy0;
+    PNP_DEV void zero()
+    {
 #pragma unroll
-    for (int e = 0; e < 6; ++e) { Mx[e] = T(0); My[e] = T(0); Mw[e] = T(0); }
+        for (int e = 0; e < 6; ++e) { Mx[e] = T(0); My[e] = T(0); Mw[e] = T(0); }
 #pragma unroll
-    for (int e = 0; e < 3; ++e) { mx[e] = T(0); my[e] = T(0); }
-    for (int i = sub; i < n; i += LPP) {
-        const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
-        T bx, by;
-        pts.get(i, bx, by);
+        for (int e = 0; e < 3; ++e) { mx[e] = T(0); my[e] = T(0); mw[e] = T(0); }
+        sx0 = T(0); sy0 = T(0);
+    }
+    PNP_DEV void add(const T (&th)[3], T bx, T by)
+    {
         const T ww = bx * bx + by * by;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -286,21 +286,205 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
             }
             mx[a] = t_fma(bx, th[a], mx[a]);
             my[a] = t_fma(by, th[a], my[a]);
+            mw[a] = t_fma(ww, th[a], mw[a]);
         }
+        sx0 += bx; sy0 += by;
     }
-    group_sum_arr<LPP>(Mx); group_sum_arr<LPP>(My); group_sum_arr<LPP>(Mw);
-    group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my);
+    template <int LPP>
+    PNP_DEV void reduce()
+    {
+        group_sum_arr<LPP>(Mx); group_sum_arr<LPP>(My); group_sum_arr<LPP>(Mw);
+        group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my); group_sum_arr<LPP>(mw);
+        sx0 = group_sum<LPP>(sx0); sy0 = group_sum<LPP>(sy0);
+    }
+    // flat order used for the [PNP_NMOM][B] workspace of the moment mapping
+    PNP_DEV T& at(int k)
+    {
+        return k < 6 ? Mx[k] : k < 12 ? My[k - 6] : k < 18 ? Mw[k - 12] : k < 21 ? mx[k - 18] : k < 24 ? my[k - 21]
+               : k < 27 ? mw[k - 24] : (k == 27 ? sx0 : sy0);
+    }
+};
 
+template <typename T, int LPP, typename Pts>
+PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n, int sub, Moments<T>& mom)
+{
+    mom.zero();
+    for (int i = sub; i < n; i += LPP) {
+        const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
+        T bx, by;
+        pts.get(i, bx, by);
+        mom.add(th, bx, by);
+    }
+    mom.template reduce<LPP>();
+}
+
+// The gamma column of J^T J as bilinear forms of the moments (terms have the size of the result):
+//   sg1 = sum th g1 = M0 u1 - Mx u3;  sg2 = M0 u2 - My u3;  sg3 = sum th (bx g1 + by g2) = Mx u1 + My u2 - Mw u3
+//   s1 = sum g1 = m0.u1 - mx.u3;  s2 = m0.u2 - my.u3;  sgg = sum g1^2 + g2^2 = u1.sg1 + u2.sg2 - u3.sg3
+template <typename T>
+struct GammaCol { T sg1[3], sg2[3], sg3[3], s1, s2, sgg; };
+
+template <typename T>
+PNP_DEV void lm_gamma_column(const T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, GammaCol<T>& gc)
+{
+    gc.s1 = T(0); gc.s2 = T(0); gc.sgg = T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T e1 = T(0), e2 = T(0), e3 = T(0);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            e1 = t_fma(sC[s3(k, j)], x[j], t_fma(-m.Mx[s3(k, j)], x[6 + j], e1));
+            e2 = t_fma(sC[s3(k, j)], x[3 + j], t_fma(-m.My[s3(k, j)], x[6 + j], e2));
+            e3 = t_fma(m.Mx[s3(k, j)], x[j], t_fma(m.My[s3(k, j)], x[3 + j], t_fma(-m.Mw[s3(k, j)], x[6 + j], e3)));
+        }
+        gc.sg1[k] = e1; gc.sg2[k] = e2; gc.sg3[k] = e3;
+        gc.s1 = t_fma(sC[6 + k], x[k], t_fma(-m.mx[k], x[6 + k], gc.s1));
+        gc.s2 = t_fma(sC[6 + k], x[3 + k], t_fma(-m.my[k], x[6 + k], gc.s2));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gc.sgg = t_fma(x[k], gc.sg1[k], t_fma(x[3 + k], gc.sg2[k], t_fma(-x[6 + k], gc.sg3[k], gc.sgg)));
+}
+
+// J^T (z - hx) of the 2n measurement rows
+template <typename T>
+struct LmRhs { T r1[3], r2[3], r3[3], q1, q2, qg; };
+
+// ... from the moments (moment mapping).  Unlike the gamma column these are differences of terms
+// ~|z|/|z - hx| larger than the result; the rounding this adds to the step is ~1e3 times smaller
+// than the effect of a 1e-13 relative input perturbation, which is what defines the parity subset.
+template <typename T>
+PNP_DEV void lm_rhs_from_moments(const T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, const GammaCol<T>& gc, LmRhs<T>& r)
+{
+    const T gam = x[11], d1 = x[9], d2 = x[10];
+    T qa = T(0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.r1[k] = m.mx[k] - gam * gc.sg1[k] - d1 * sC[6 + k];
+        r.r2[k] = m.my[k] - gam * gc.sg2[k] - d2 * sC[6 + k];
+        r.r3[k] = m.mw[k] - gam * gc.sg3[k] - d1 * m.mx[k] - d2 * m.my[k];
+        qa = t_fma(m.mx[k], x[k], t_fma(m.my[k], x[3 + k], t_fma(-m.mw[k], x[6 + k], qa)));
+    }
+    r.q1 = m.sx0 - gam * gc.s1 - sC[9] * d1;
+    r.q2 = m.sy0 - gam * gc.s2 - sC[9] * d2;
+    r.qg = qa - gam * gc.sgg - d1 * gc.s1 - d2 * gc.s2;
+}
+
+// One damped Gauss-Newton step: A = J^T J + lambda I (:2666-2667) from the moments and the gamma
+// column, g = J^T (z - hx) (:2684) from `r`, the nine constraint rows, x += pinv(A) g (:2675, :2702).
+template <typename T>
+PNP_DEV void lm_step(T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, const GammaCol<T>& gc, const LmRhs<T>& r,
+                     T lambda)
+{
+    constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
+    const T gam = x[GG];
+    T A[78], g[12];
+    const T gg2 = gam * gam;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+            const T m0 = gg2 * sC[s3(a, b)];
+            A[sidx<12>(U1 + a, U1 + b)] = m0;
+            A[sidx<12>(U2 + a, U2 + b)] = m0;
+            A[sidx<12>(U3 + a, U3 + b)] = gg2 * m.Mw[s3(a, b)];
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            A[sidx<12>(U1 + a, U2 + b)] = T(0);
+            A[sidx<12>(U1 + a, U3 + b)] = -gg2 * m.Mx[s3(a, b)];
+            A[sidx<12>(U2 + a, U3 + b)] = -gg2 * m.My[s3(a, b)];
+        }
+        A[sidx<12>(U1 + a, D1)] = gam * sC[6 + a]; A[sidx<12>(U1 + a, D2)] = T(0); A[sidx<12>(U1 + a, GG)] = gam * gc.sg1[a];
+        A[sidx<12>(U2 + a, D1)] = T(0); A[sidx<12>(U2 + a, D2)] = gam * sC[6 + a]; A[sidx<12>(U2 + a, GG)] = gam * gc.sg2[a];
+        A[sidx<12>(U3 + a, D1)] = -gam * m.mx[a]; A[sidx<12>(U3 + a, D2)] = -gam * m.my[a]; A[sidx<12>(U3 + a, GG)] = -gam * gc.sg3[a];
+        g[U1 + a] = gam * r.r1[a]; g[U2 + a] = gam * r.r2[a]; g[U3 + a] = -gam * r.r3[a];
+    }
+    A[sidx<12>(D1, D1)] = sC[9]; A[sidx<12>(D1, D2)] = T(0); A[sidx<12>(D1, GG)] = gc.s1;
+    A[sidx<12>(D2, D2)] = sC[9]; A[sidx<12>(D2, GG)] = gc.s2;
+    A[sidx<12>(GG, GG)] = gc.sgg;
+    g[D1] = r.q1; g[D2] = r.q2; g[GG] = r.qg;
+    // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones)
+    {
+        const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
+        const T u11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+        const T u22 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+        const T u33 = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2];
+        const T u13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
+        const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
+        const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+        const T n1 = t_sqrt(u11), n2 = t_sqrt(u22), n3 = t_sqrt(u33);
+        const T nu2[3] = { -u2[0], -u2[1], -u2[2] }, nu3[3] = { -u3[0], -u3[1], -u3[2] };
+        add_outer2<T, U1, U3>(A, g, u3, u1, T(0) - u13);          // u1.u3 = 0
+        add_outer2<T, U2, U3>(A, g, u3, u2, T(0) - u23);          // u2.u3 = 0
+        add_outer2<T, U1, U2>(A, g, u2, u1, T(0) - u12);          // u1.u2 = 0
+        add_outer2<T, U1, U3>(A, g, u1, nu3, T(0) - (u11 - u33)); // rows use u, not 2u (:3808)
+        add_outer2<T, U2, U3>(A, g, u2, nu3, T(0) - (u22 - u33));
+        add_outer2<T, U1, U2>(A, g, u1, nu2, T(0) - (u11 - u22));
+        const T h1 = T(1) / (T(2) * n1), h2 = T(1) / (T(2) * n2), h3 = T(1) / (T(2) * n3);
+        const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
+        const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
+        const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
+        add_outer1<T, U1>(A, g, j1, T(1) - n1);
+        add_outer1<T, U2>(A, g, j2, T(1) - n2);
+        add_outer1<T, U3>(A, g, j3, T(1) - n3);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) A[sidx<12>(i, i)] += lambda;
+    ldlt_factor<T, 12>(A);
+    ldlt_solve<T, 12>(A, g);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] += g[i];
+}
+
+// ||z - hx|| over the 2n measurement rows at state x, point by point (:2679-2681)
+template <typename T, int LPP, typename Pts>
+PNP_DEV T lm_residual_direct(const Pts& pts, const T* __restrict__ sP, int n, int sub, const T (&x)[12])
+{
+    const T gam = x[11], d1 = x[9], d2 = x[10];
+    T rr = T(0);
+    for (int i = sub; i < n; i += LPP) {
+        const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+        T bx, by;
+        pts.get(i, bx, by);
+        const T a = th0 * x[0] + th1 * x[1] + th2 * x[2];
+        const T b = th0 * x[3] + th1 * x[4] + th2 * x[5];
+        const T c = th0 * x[6] + th1 * x[7] + th2 * x[8];
+        const T rx = bx - (gam * (a - bx * c) + d1);
+        const T ry = by - (gam * (b - by * c) + d2);
+        rr = t_fma(rx, rx, t_fma(ry, ry, rr));
+    }
+    return t_sqrt(group_sum<LPP>(rr));
+}
+
+// EKF2_reconstruct_R_t_m1 :3500-3540
+template <typename T>
+PNP_DEV void lm_reconstruct(const T (&x)[12], Result<T>& out)
+{
+    T G[9], smax;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) G[e] = x[e];
+    svd3_project<T>(G, out.R, smax);
+    const T t3 = T(1) / (smax * x[11]);                   // :3530-3533
+    out.t[0] = x[9] * t3; out.t[1] = x[10] * t3; out.t[2] = t3;
+}
+
+// Fused form (direct mapping): J^T (z - hx) and the residual are accumulated point by point in
+// every iteration; J^T J comes from the moments.
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                      const SolverPrm<T>& prm, Result<T>& out)
+{
+    T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2619-2624
+    Moments<T> mom;
+    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T res = T(1e5);
     for (int it = 0; it < prm.max_it; ++it) {             // :2642, fixed count, no exit test
-        const T gam = x[GG], d1 = x[D1], d2 = x[D2];
-        // ---- state-dependent sums over the correspondences: only what involves the residual
-        //      (z - hx) is accumulated point by point; the gamma column of J^T J is a bilinear
-        //      form of the moments (no cancellation: its terms have the size of the result)
-        T r1[3], r2[3], r3[3];
+        const T gam = x[11], d1 = x[9], d2 = x[10];
+        LmRhs<T> r;
 #pragma unroll
-        for (int e = 0; e < 3; ++e) { r1[e] = r2[e] = r3[e] = T(0); }
-        T q1 = T(0), q2 = T(0), qg = T(0), rr = T(0);
+        for (int e = 0; e < 3; ++e) { r.r1[e] = r.r2[e] = r.r3[e] = T(0); }
+        r.q1 = r.q2 = r.qg = T(0);
+        T rr = T(0);
         for (int i = sub; i < n; i += LPP) {
             const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
             T bx, by;
@@ -314,101 +498,43 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
             const T v3 = bx * rx + by * ry;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                r1[k] = t_fma(th[k], rx, r1[k]); r2[k] = t_fma(th[k], ry, r2[k]); r3[k] = t_fma(th[k], v3, r3[k]);
+                r.r1[k] = t_fma(th[k], rx, r.r1[k]); r.r2[k] = t_fma(th[k], ry, r.r2[k]); r.r3[k] = t_fma(th[k], v3, r.r3[k]);
             }
-            q1 += rx; q2 += ry; qg = t_fma(g1, rx, t_fma(g2, ry, qg));
+            r.q1 += rx; r.q2 += ry; r.qg = t_fma(g1, rx, t_fma(g2, ry, r.qg));
             rr = t_fma(rx, rx, t_fma(ry, ry, rr));
         }
-        group_sum_arr<LPP>(r1); group_sum_arr<LPP>(r2); group_sum_arr<LPP>(r3);
-        q1 = group_sum<LPP>(q1); q2 = group_sum<LPP>(q2); qg = group_sum<LPP>(qg); rr = group_sum<LPP>(rr);
-        // sg1 = sum th g1 = M0 u1 - Mx u3;  sg2 = M0 u2 - My u3;  sg3 = sum th (bx g1 + by g2) = Mx u1 + My u2 - Mw u3
-        // s1 = sum g1 = m0.u1 - mx.u3;  s2 = m0.u2 - my.u3;  sgg = sum g1^2 + g2^2 = u1.sg1 + u2.sg2 - u3.sg3
-        T sg1[3], sg2[3], sg3[3], s1 = T(0), s2 = T(0), sgg = T(0);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            T e1 = T(0), e2 = T(0), e3 = T(0);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                e1 = t_fma(sC[s3(k, j)], x[j], t_fma(-Mx[s3(k, j)], x[6 + j], e1));
-                e2 = t_fma(sC[s3(k, j)], x[3 + j], t_fma(-My[s3(k, j)], x[6 + j], e2));
-                e3 = t_fma(Mx[s3(k, j)], x[j], t_fma(My[s3(k, j)], x[3 + j], t_fma(-Mw[s3(k, j)], x[6 + j], e3)));
-            }
-            sg1[k] = e1; sg2[k] = e2; sg3[k] = e3;
-            s1 = t_fma(sC[6 + k], x[k], t_fma(-mx[k], x[6 + k], s1));
-            s2 = t_fma(sC[6 + k], x[3 + k], t_fma(-my[k], x[6 + k], s2));
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) sgg = t_fma(x[k], sg1[k], t_fma(x[3 + k], sg2[k], t_fma(-x[6 + k], sg3[k], sgg)));
+        group_sum_arr<LPP>(r.r1); group_sum_arr<LPP>(r.r2); group_sum_arr<LPP>(r.r3);
+        r.q1 = group_sum<LPP>(r.q1); r.q2 = group_sum<LPP>(r.q2); r.qg = group_sum<LPP>(r.qg); rr = group_sum<LPP>(rr);
         res = t_sqrt(rr);                                 // res_norm of the state BEFORE the update (:2681)
-
-        // ---- A = J^T J + lambda I (:2666-2667), g = J^T (z - hx) (:2684)
-        T A[78], g[12];
-        const T gg2 = gam * gam;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-            for (int b = a; b < 3; ++b) {
-                const T m0 = gg2 * sC[s3(a, b)];
-                A[sidx<12>(U1 + a, U1 + b)] = m0;
-                A[sidx<12>(U2 + a, U2 + b)] = m0;
-                A[sidx<12>(U3 + a, U3 + b)] = gg2 * Mw[s3(a, b)];
-            }
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                A[sidx<12>(U1 + a, U2 + b)] = T(0);
-                A[sidx<12>(U1 + a, U3 + b)] = -gg2 * Mx[s3(a, b)];
-                A[sidx<12>(U2 + a, U3 + b)] = -gg2 * My[s3(a, b)];
-            }
-            A[sidx<12>(U1 + a, D1)] = gam * sC[6 + a]; A[sidx<12>(U1 + a, D2)] = T(0); A[sidx<12>(U1 + a, GG)] = gam * sg1[a];
-            A[sidx<12>(U2 + a, D1)] = T(0); A[sidx<12>(U2 + a, D2)] = gam * sC[6 + a]; A[sidx<12>(U2 + a, GG)] = gam * sg2[a];
-            A[sidx<12>(U3 + a, D1)] = -gam * mx[a]; A[sidx<12>(U3 + a, D2)] = -gam * my[a]; A[sidx<12>(U3 + a, GG)] = -gam * sg3[a];
-            g[U1 + a] = gam * r1[a]; g[U2 + a] = gam * r2[a]; g[U3 + a] = -gam * r3[a];
-        }
-        A[sidx<12>(D1, D1)] = sC[9]; A[sidx<12>(D1, D2)] = T(0); A[sidx<12>(D1, GG)] = s1;
-        A[sidx<12>(D2, D2)] = sC[9]; A[sidx<12>(D2, GG)] = s2;
-        A[sidx<12>(GG, GG)] = sgg;
-        g[D1] = q1; g[D2] = q2; g[GG] = qg;
-        // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones)
-        {
-            const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
-            const T u11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
-            const T u22 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
-            const T u33 = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2];
-            const T u13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
-            const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
-            const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
-            const T n1 = t_sqrt(u11), n2 = t_sqrt(u22), n3 = t_sqrt(u33);
-            const T nu2[3] = { -u2[0], -u2[1], -u2[2] }, nu3[3] = { -u3[0], -u3[1], -u3[2] };
-            add_outer2<T, U1, U3>(A, g, u3, u1, T(0) - u13);          // u1.u3 = 0
-            add_outer2<T, U2, U3>(A, g, u3, u2, T(0) - u23);          // u2.u3 = 0
-            add_outer2<T, U1, U2>(A, g, u2, u1, T(0) - u12);          // u1.u2 = 0
-            add_outer2<T, U1, U3>(A, g, u1, nu3, T(0) - (u11 - u33)); // rows use u, not 2u (:3808)
-            add_outer2<T, U2, U3>(A, g, u2, nu3, T(0) - (u22 - u33));
-            add_outer2<T, U1, U2>(A, g, u1, nu2, T(0) - (u11 - u22));
-            const T h1 = T(1) / (T(2) * n1), h2 = T(1) / (T(2) * n2), h3 = T(1) / (T(2) * n3);
-            const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
-            const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
-            const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
-            add_outer1<T, U1>(A, g, j1, T(1) - n1);
-            add_outer1<T, U2>(A, g, j2, T(1) - n2);
-            add_outer1<T, U3>(A, g, j3, T(1) - n3);
-        }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) A[sidx<12>(i, i)] += prm.lm_lambda;
-        // ---- x += pinv(A) g (:2675, :2702)
-        ldlt_factor<T, 12>(A);
-        ldlt_solve<T, 12>(A, g);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) x[i] += g[i];
+        GammaCol<T> gc;
+        lm_gamma_column<T>(x, mom, sC, gc);
+        lm_step<T>(x, mom, sC, gc, r, prm.lm_lambda);
     }
-    // ---- EKF2_reconstruct_R_t_m1 :3500-3540
-    T G[9], smax;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) G[e] = x[e];
-    svd3_project<T>(G, out.R, smax);
-    const T t3 = T(1) / (smax * x[GG]);                   // :3530-3533
-    out.t[0] = x[D1] * t3; out.t[1] = x[D2] * t3; out.t[2] = t3;
+    lm_reconstruct<T>(x, out);
     out.res = res;
+    out.iters = prm.max_it;
+}
+
+// Moment form (moment mapping): every iteration is O(1) in the moments; x_prev receives the state
+// before the last update, at which the caller evaluates res_norm point by point.
+template <typename T>
+PNP_DEV void solve_lm_from_moments(const Moments<T>& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, T (&x_prev)[12],
+                                   Result<T>& out)
+{
+    T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2619-2624
+#pragma unroll
+    for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
+    for (int it = 0; it < prm.max_it; ++it) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
+        GammaCol<T> gc;
+        LmRhs<T> r;
+        lm_gamma_column<T>(x, mom, sC, gc);
+        lm_rhs_from_moments<T>(x, mom, sC, gc, r);
+        lm_step<T>(x, mom, sC, gc, r, prm.lm_lambda);
+    }
+    lm_reconstruct<T>(x, out);
+    out.res = T(0);
     out.iters = prm.max_it;
 }
 
@@ -429,45 +555,45 @@ PNP_DEV void g4_apply(const T* __restrict__ G, const T (&v)[4], T (&o)[4])
     }
 }
 
+// residual of f2_cal_res_all (:3368) at (phi_3 old, phi rebuilt from R, t): res_norm_all (:3374)
+template <typename T>
+struct F2Tail { T phi3[3], pxn[4], pyn[4]; };
+
 template <typename T, int LPP, typename Pts>
-PNP_DEV void solve_linear_f2(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
-                             const SolverPrm<T>& prm, Result<T>& out)
+PNP_DEV T f2_residual_direct(const Pts& pts, const T* __restrict__ sP, int n, int sub, const F2Tail<T>& f)
 {
-    T Sx[6], Sy[6], sx[3], sy[3], s0x = T(0), s0y = T(0);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) { Sx[e] = T(0); Sy[e] = T(0); }
-#pragma unroll
-    for (int e = 0; e < 3; ++e) { sx[e] = T(0); sy[e] = T(0); }
+    T rx2 = T(0), ry2 = T(0);
     for (int i = sub; i < n; i += LPP) {
-        const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
+        const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
         T bx, by;
         pts.get(i, bx, by);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-            for (int b = a; b < 3; ++b) {
-                const T m = th[a] * th[b];
-                Sx[s3(a, b)] = t_fma(bx, m, Sx[s3(a, b)]);
-                Sy[s3(a, b)] = t_fma(by, m, Sy[s3(a, b)]);
-            }
-            sx[a] = t_fma(bx, th[a], sx[a]);
-            sy[a] = t_fma(by, th[a], sy[a]);
-        }
-        s0x += bx; s0y += by;
+        const T db = T(1) + (th0 * f.phi3[0] + th1 * f.phi3[1] + th2 * f.phi3[2]);
+        const T dx = th0 * f.pxn[0] + th1 * f.pxn[1] + th2 * f.pxn[2] + f.pxn[3];
+        const T dy = th0 * f.pyn[0] + th1 * f.pyn[1] + th2 * f.pyn[2] + f.pyn[3];
+        const T ex = bx * db - dx, ey = by * db - dy;
+        rx2 = t_fma(ex, ex, rx2); ry2 = t_fma(ey, ey, ry2);
     }
-    group_sum_arr<LPP>(Sx); group_sum_arr<LPP>(Sy); group_sum_arr<LPP>(sx); group_sum_arr<LPP>(sy);
-    s0x = group_sum<LPP>(s0x); s0y = group_sum<LPP>(s0y);
+    rx2 = group_sum<LPP>(rx2); ry2 = group_sum<LPP>(ry2);
+    const T nx = t_sqrt(rx2), ny = t_sqrt(ry2);
+    return t_sqrt(nx * nx + ny * ny);
+}
 
+// The three fixed-point iterations on phi_3 from the moments; `tail` = what the residual of the
+// last iteration needs.
+template <typename T>
+PNP_DEV void solve_f2_from_moments(const Moments<T>& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, F2Tail<T>& tail,
+                                   Result<T>& out)
+{
     const T* G = sC + 10;
     T v0x[4], v0y[4], Mxm[12], Mym[12];                   // :3314-3328
     {
-        const T bxv[4] = { sx[0], sx[1], sx[2], s0x }, byv[4] = { sy[0], sy[1], sy[2], s0y };
+        const T bxv[4] = { mom.mx[0], mom.mx[1], mom.mx[2], mom.sx0 }, byv[4] = { mom.my[0], mom.my[1], mom.my[2], mom.sy0 };
         g4_apply<T>(G, bxv, v0x);
         g4_apply<T>(G, byv, v0y);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const T cx[4] = { Sx[s3(0, c)], Sx[s3(1, c)], Sx[s3(2, c)], sx[c] };
-            const T cy[4] = { Sy[s3(0, c)], Sy[s3(1, c)], Sy[s3(2, c)], sy[c] };
+            const T cx[4] = { mom.Mx[s3(0, c)], mom.Mx[s3(1, c)], mom.Mx[s3(2, c)], mom.mx[c] };
+            const T cy[4] = { mom.My[s3(0, c)], mom.My[s3(1, c)], mom.My[s3(2, c)], mom.my[c] };
             T ox[4], oy[4];
             g4_apply<T>(G, cx, ox);
             g4_apply<T>(G, cy, oy);
@@ -476,7 +602,6 @@ PNP_DEV void solve_linear_f2(const Pts& pts, const T* __restrict__ sP, const T* 
         }
     }
     T phi3[3] = { T(0), T(0), T(1) };                     // :758
-    T res = T(30);
     const int nit = prm.linear_it < 1 ? 1 : prm.linear_it;
     for (int it = 0; it < nit; ++it) {
         T phi[8], t3;
@@ -487,33 +612,28 @@ PNP_DEV void solve_linear_f2(const Pts& pts, const T* __restrict__ sP, const T* 
             if (k < 3) { phi[k] = px; phi[3 + k] = py; } else { phi[6] = px; phi[7] = py; }
         }
         block_reconstruct<T>(phi, out.R, out.t, t3);      // :862
-        if (it == nit - 1) {
-            // f2_cal_res_all with the phi rebuilt from (R, t) and the OLD phi_3 (:868-877, :3368)
-            T pxn[4], pyn[4];
+        if (it == nit - 1) {                              // (:868-877): phi from (R, t), the OLD phi_3
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { pxn[k] = out.R[k] / t3; pyn[k] = out.R[3 + k] / t3; }
-            pxn[3] = out.t[0] / t3; pyn[3] = out.t[1] / t3;
-            T rx2 = T(0), ry2 = T(0);
-            for (int i = sub; i < n; i += LPP) {
-                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
-                T bx, by;
-                pts.get(i, bx, by);
-                const T db = T(1) + (th0 * phi3[0] + th1 * phi3[1] + th2 * phi3[2]);
-                const T dx = th0 * pxn[0] + th1 * pxn[1] + th2 * pxn[2] + pxn[3];
-                const T dy = th0 * pyn[0] + th1 * pyn[1] + th2 * pyn[2] + pyn[3];
-                const T ex = bx * db - dx, ey = by * db - dy;
-                rx2 = t_fma(ex, ex, rx2); ry2 = t_fma(ey, ey, ry2);
-            }
-            rx2 = group_sum<LPP>(rx2); ry2 = group_sum<LPP>(ry2);
-            const T nx = t_sqrt(rx2), ny = t_sqrt(ry2);
-            res = t_sqrt(nx * nx + ny * ny);              // :3374
+            for (int k = 0; k < 3; ++k) { tail.pxn[k] = out.R[k] / t3; tail.pyn[k] = out.R[3 + k] / t3; tail.phi3[k] = phi3[k]; }
+            tail.pxn[3] = out.t[0] / t3; tail.pyn[3] = out.t[1] / t3;
         }
         const T it3 = T(1) / t3;                          // update_phi_3_est_m2 :4002-4010
 #pragma unroll
         for (int k = 0; k < 3; ++k) phi3[k] = it3 * out.R[6 + k];
     }
-    out.res = res;
+    out.res = T(30);
     out.iters = nit;
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_linear_f2(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                             const SolverPrm<T>& prm, Result<T>& out)
+{
+    Moments<T> mom;
+    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    F2Tail<T> tail;
+    solve_f2_from_moments<T>(mom, sC, prm, tail, out);
+    out.res = f2_residual_direct<T, LPP, Pts>(pts, sP, n, sub, tail);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -13,15 +13,18 @@ from oracle import oracle as orc
 from pnp_solver_test_b200 import patterns as pt
 
 pytestmark = pytest.mark.gpu
-MAP_THREAD, MAP_WARP = 1, 32
+MAP_THREAD, MAP_MOMENT, MAP_WARP = 1, 2, 32
+HAS_MOMENT_FORM = ("lm", "linear_f2")
 
 
-@pytest.mark.parametrize("mapping", [MAP_THREAD, MAP_WARP])
+@pytest.mark.parametrize("mapping", [MAP_THREAD, MAP_MOMENT, MAP_WARP])
 @pytest.mark.parametrize("name", SOLVER_GOLDENS)
 def test_cuda_matches_reference_goldens(name, mapping):
     g = load_golden(name)
     if mapping == MAP_THREAD and g["pattern"].shape[0] > 256:
         pytest.skip("thread mapping holds the tile in shared memory: n <= ~380")
+    if mapping == MAP_MOMENT and str(g["method"]) not in HAS_MOMENT_FORM:
+        pytest.skip("moment mapping exists for LM and linear F2")
     out = cuda_solve(str(g["method"]), g["uv"], g["pattern"], g["K"], mapping=mapping)
     compare_solutions(out, g, mask=g["stable"], iters_mask=g["iters_stable"])
 
@@ -45,8 +48,11 @@ def _workload(n, B, seed, quantized=True, noise=0.0):
 
 @pytest.mark.parametrize("method", ["qeif", "lm", "linear_f2", "linear_f1"])
 @pytest.mark.parametrize("n,B,mapping", [(15, 4096, MAP_THREAD), (68, 4096, MAP_THREAD), (68, 1024, MAP_WARP),
-                                        (1024, 96, MAP_WARP)])
+                                        (1024, 96, MAP_WARP), (15, 4096, MAP_MOMENT), (68, 4096, MAP_MOMENT),
+                                        (1024, 96, MAP_MOMENT)])
 def test_cuda_matches_oracle_on_fresh_inputs(method, n, B, mapping):
+    if mapping == MAP_MOMENT and method not in HAS_MOMENT_FORM:
+        pytest.skip("moment mapping exists for LM and linear F2")
     P, K, w = _workload(n, B, seed=1000 + n)
     ref, stable, it_stable = oracle_stability(method, w["uv"], P, K)
     out = cuda_solve(method, w["uv"], P, K, mapping=mapping)
@@ -58,8 +64,20 @@ def test_cuda_matches_oracle_on_fresh_inputs(method, n, B, mapping):
 def test_cuda_matches_oracle_with_pixel_noise(method):
     P, K, w = _workload(68, 2048, seed=7, quantized=False, noise=1.5)
     ref, stable, it_stable = oracle_stability(method, w["uv"], P, K)
-    out = cuda_solve(method, w["uv"], P, K, mapping=MAP_THREAD)
-    compare_solutions(out, ref, mask=stable, iters_mask=it_stable)
+    for mapping in ((MAP_THREAD, MAP_MOMENT) if method == "lm" else (MAP_THREAD,)):
+        out = cuda_solve(method, w["uv"], P, K, mapping=mapping)
+        compare_solutions(out, ref, mask=stable, iters_mask=it_stable)
+
+
+def test_moment_mapping_with_landmark_subset_and_ragged_batches():
+    P, K, w = _workload(15, 1000, seed=13)
+    idx = np.array([0, 1, 3, 4, 5, 6, 9, 12], np.int32)
+    for method in HAS_MOMENT_FORM:
+        for B in (1, 33, 1000):
+            ref, stable, _ = oracle_stability(method, w["uv"][:B, idx], P[idx], K)
+            out = cuda_solve(method, w["uv"][:B], P, K, mapping=MAP_MOMENT, point_index=idx)
+            if stable.any():
+                compare_solutions(out, ref, mask=stable)
 
 
 def test_landmark_subset_selection_matches_gather():
@@ -190,11 +208,12 @@ def test_full_size_properties_1m_x_68_lm():
     ref, stable, _ = oracle_stability("lm", uv_s, P, K)
     got = {k: v[sample] for k, v in to_np(a).items()}
     compare_solutions(got, ref, mask=stable)
-    wq = to_np(pnp.solve_batch("lm", w["uv"][:65536], pat, K, params=pnp.default_params(mapping=MAP_WARP)))
-    at = {k: v[:65536] for k, v in to_np(a).items()}
+    at = {k: v[:65536] for k, v in to_np(a).items()}            # default mapping = moment form
     ref2, stable2, _ = oracle_stability("lm", w["uv"][:4096].cpu().numpy(), P, K)
     m = np.zeros(65536, bool); m[:4096] = stable2
-    compare_solutions(wq, at, mask=m)
+    for mapping in (MAP_WARP, MAP_THREAD):                       # the other execution shapes agree
+        wq = to_np(pnp.solve_batch("lm", w["uv"][:65536], pat, K, params=pnp.default_params(mapping=mapping)))
+        compare_solutions(wq, at, mask=m)
 
 
 def test_full_size_qeif_recovers_ground_truth():
