@@ -35,18 +35,23 @@ UNIT = "solves/s"
 
 
 # ------------------------------------------------------------------------------------------------
-# algorithmic work per solve of the LM kernel as implemented (DESIGN.md "Kernels"); FMA = 2 flops
+# Algorithmic work per solve of the LM path as implemented (DESIGN.md "Kernels"); FMA = 2 flops.
+# Moment mapping = three kernels:
+#   k_stream_thread<.,LM,0>  moments: per point 6 theta*theta^T products, bx^2+by^2, 27 FMAs, 2 adds   65 flop/pt   (HBM-bound)
+#   k_iterate<.,LM>          14 x [gamma column 84 FMA, rhs 82, build A 60, nine constraint rows 440,
+#                            LDL^T 12x12 + two triangular solves 926, update 12] + 3x3 SVD, t, Euler   (FP64 pipe)
+#   k_stream_thread<.,LM,1>  residual at the state before the last update: 34 flop/pt                  (HBM-bound)
 # ------------------------------------------------------------------------------------------------
+def lm_flops_iterate(max_it=14):
+    return max_it * (168 + 82 + 60 + 440 + 926 + 12) + 1000
+
+
 def lm_flops_per_solve(n, max_it=14):
-    per_point_once = 56          # 24 moment FMAs + theta theta^T products + bx^2+by^2
-    per_point_iter = 83          # 3 dots, g, r, 18 theta-weighted FMAs, 7 scalar sums
-    per_iter = 1300              # build A (78), 9 constraint rows, LDL^T 12x12, two triangular solves
-    final = 600                  # 3x3 Jacobi SVD projection, t, Euler
-    return n * (per_point_once + max_it * per_point_iter) + max_it * per_iter + final
+    return n * (65 + 34) + lm_flops_iterate(max_it)
 
 
 def lm_flops_survey(n, max_it=14):
-    return max_it * (212 * n + 1100) + 1000        # naive structure
+    return max_it * (212 * n + 1100) + 1000        # per-iteration Jacobians, naive structure
 
 
 def bytes_per_solve(n, s=8):
@@ -197,7 +202,7 @@ def run_ours(args):
     K = pt.default_camera_matrix()
     P = pt.pattern_array(pt.synthetic_pattern(n))
     pat = torch.from_numpy(P).to(dev)[None].contiguous()
-    params = pnp.default_params()
+    params = pnp.default_params(flags=_lib.FLAG_PROFILE)      # CUDA events around each kernel of the solve
 
     # inputs resident in HBM: this rank's slice of the global stream
     w = wl.synth_batch(rank * B, B, P, K, cfg=pnp.default_synth(seed=42), device=dev)
@@ -232,6 +237,7 @@ def run_ours(args):
     barrier()
     sampler.mark_begin()
     l0 = _lib.LAUNCHES[0]
+    _lib.check(_lib.lib.pnpb200_profile_reset(), "pnpb200_profile_reset")
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
@@ -283,26 +289,38 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_solve_thread<double, LM>): FP64 FMA pipe
+    # ---- roofline of the dominant kernel (k_iterate<double, LM>): FP64 FMA pipe
     import ctypes as C
+    kms = (C.c_float * 3)()
+    ncall = C.c_int(0)
+    _lib.check(_lib.lib.pnpb200_profile_read(kms, C.byref(ncall)), "pnpb200_profile_read")
+    ms_mom, ms_it, ms_res = float(kms[0]), float(kms[1]), float(kms[2])
     peak = C.c_double(0.0)
     _lib.check(_lib.lib.pnpb200_fma_peak(0, 200000, C.byref(peak)), "pnpb200_fma_peak")
-    fl = lm_flops_per_solve(n)
-    achieved_tf = fl * B / (ms_kernel_max * 1e-3) / 1e12
+    fl = lm_flops_iterate()
+    achieved_tf = fl * B / (ms_it * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_achieved = bytes_per_solve(n) * B / (ms_kernel_max * 1e-3) / 1e9
-    roofline = {"bound": "fp64_pipe", "kernel": "k_solve_thread<double, LM>", "achieved": achieved_tf, "peak": peak.value / 1e12,
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    mom_bytes = (2 * n * 8 + 29 * 8) * B          # read every pixel once, write 29 moments
+    res_bytes = (2 * n * 8 + 12 * 8 + 8) * B      # read every pixel and the 12-double state, write res_norm
+    roofline = {"bound": "fp64_pipe", "kernel": "k_iterate<double, LM>", "achieved": achieved_tf, "peak": peak.value / 1e12,
                 "unit": "TFLOP/s", "frac": achieved_tf / (peak.value / 1e12), "traffic": None,
                 "peak_source": "measured in this run by pnpb200_fma_peak (FP64 FMA microbenchmark; MEASURED_PEAKS.json has no FP64 figure)",
-                "flops_per_solve": fl, "flops_per_solve_survey_formula": lm_flops_survey(n), "kernel_ms": ms_kernel_max,
-                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                        "bytes_per_solve": bytes_per_solve(n),
-                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}}
+                "flops_per_solve": fl, "kernel_ms": ms_it, "timed_calls": int(ncall.value),
+                "solve_ms": ms_kernel_max, "flops_per_solve_whole_path": lm_flops_per_solve(n),
+                "flops_per_solve_survey_formula": lm_flops_survey(n),
+                "other_kernels": [
+                    {"kernel": "k_stream_thread<double, LM, 0> (moments)", "bound": "hbm", "kernel_ms": ms_mom,
+                     "achieved": mom_bytes / (ms_mom * 1e-3) / 1e9 if ms_mom > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (mom_bytes / (ms_mom * 1e-3) / 1e9 / hbm_peak) if ms_mom > 0 else None, "peak_source": hbm_src},
+                    {"kernel": "k_stream_thread<double, LM, 1> (residual)", "bound": "hbm", "kernel_ms": ms_res,
+                     "achieved": res_bytes / (ms_res * 1e-3) / 1e9 if ms_res > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (res_bytes / (ms_res * 1e-3) / 1e9 / hbm_peak) if ms_res > 0 else None, "peak_source": hbm_src}]}
     cpu = cpu_baseline_block() if (world == 1 and not args.no_cpu) else None
     st = last["stats"]
     line = {
@@ -312,7 +330,7 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: %d problems x %d-point face pattern per GPU, LM refinement (14 it), FP64, "
                                "random_stress_test pose distribution, integer-quantised pixels" % (B, n),
                    "method": METHOD, "n_points": n, "problems_per_gpu": B, "global_problems": world * B,
-                   "step": "solve kernel + error-report kernel + error statistics (two all-reduce phases)",
+                   "step": "solve (moments, iterate, residual kernels) + error-report kernel + error statistics (two all-reduce phases)",
                    "l2": "inputs are %.2f GB per step, larger than the 126 MB L2" % (uv.numel() * 8 / 1e9),
                    "parallelism": "problems sharded by global index, no solve-path traffic"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

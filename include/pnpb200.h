@@ -52,6 +52,8 @@ extern "C" {
 #define PNPB200_ENODEVICE  -3   /* no usable CUDA device                                           */
 #define PNPB200_ETOOLARGE  -4   /* n exceeds what the selected mapping can hold                    */
 
+#define PNPB200_FLAG_PROFILE 1  /* record CUDA events around each kernel of the call (pnpb200_profile_read) */
+
 #define PNPB200_MAX_PATTERNS 8
 #define PNPB200_REPORT_WIDTH 16
 
@@ -68,7 +70,9 @@ typedef struct pnpb200_params {
     double  omega0;        /* 1e-5    :2836  initial information                                   */
     double  res_old0;      /* 1e-7    :2863                                                        */
     int32_t mapping;       /* PNPB200_MAP_*                                                        */
-    int32_t reserved;
+    int32_t flags;         /* PNPB200_FLAG_*                                                       */
+    void*   workspace;     /* [device] optional scratch of workspace_bytes (pnpb200_workspace_bytes);  */
+    int64_t workspace_bytes; /* NULL/0: the call takes it from the stream-ordered CUDA memory pool   */
 } pnpb200_params;
 
 /* Synthetic workload description (random_stress_test.py:246-258, LM_noise_test.py:141-189). */
@@ -89,6 +93,8 @@ const char* pnpb200_last_error(void);          /* text of the last CUDA error se
 int pnpb200_default_params(pnpb200_params* p);
 int pnpb200_default_synth(pnpb200_synth* s);
 int pnpb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+/* scratch bytes pnpb200_solve_batch needs for this call shape (0 for the direct mappings) */
+int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping);
 
 /*
  * The hot path.  Replaces the per-problem loop around PNP_SOLVER.solve_pnp
@@ -115,6 +121,15 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n,
                         const pnpb200_params* params,
                         void* R, void* t, void* euler_deg, void* res_norm,
                         int32_t* iters, int32_t* best_pattern, void* stream);
+
+/*
+ * Per-kernel device times of the pnpb200_solve_batch calls made by this thread with
+ * PNPB200_FLAG_PROFILE since the last reset, measured with CUDA events on the call's stream.
+ * ms[3] = average duration of (moments | direct solve kernel, iterate, residual); kernels a
+ * mapping does not launch report 0.  pnpb200_profile_read synchronises with the recorded events.
+ */
+int pnpb200_profile_reset(void);
+int pnpb200_profile_read(float* ms, int* n_calls);
 
 /*
  * Same, from HOST buffers (pageable or pinned), chunked and double-buffered through a

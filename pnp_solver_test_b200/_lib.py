@@ -14,14 +14,15 @@ METHODS = {"qeif": 0, "lm": 1, "linear_f2": 2, "linear_f1": 3}
 DTYPE_F64, DTYPE_F32 = 0, 1
 MAP_AUTO, MAP_THREAD, MAP_MOMENT, MAP_WARP = 0, 1, 2, 32
 REPORT_WIDTH = 16
+FLAG_PROFILE = 1
 MAX_PATTERNS = 8
 
 EXPORTS = [
     "pnpb200_version", "pnpb200_last_error", "pnpb200_default_params", "pnpb200_default_synth",
-    "pnpb200_device_info", "pnpb200_solve_batch", "pnpb200_pipeline_create", "pnpb200_pipeline_destroy",
+    "pnpb200_device_info", "pnpb200_workspace_bytes", "pnpb200_solve_batch", "pnpb200_pipeline_create", "pnpb200_pipeline_destroy",
     "pnpb200_solve_batch_host", "pnpb200_R_from_euler", "pnpb200_euler_from_R", "pnpb200_project",
     "pnpb200_synth_batch", "pnpb200_report_batch", "pnpb200_stats_pass1", "pnpb200_stats_pass2",
-    "pnpb200_fma_peak", "pnpb200_classify",
+    "pnpb200_fma_peak", "pnpb200_classify", "pnpb200_profile_reset", "pnpb200_profile_read",
 ]
 
 
@@ -30,7 +31,8 @@ class Params(C.Structure):
     _fields_ = [("max_it", C.c_int32), ("linear_it", C.c_int32), ("lm_lambda", C.c_double),
                 ("exit_tol", C.c_double), ("f_weight", C.c_double), ("meas_sigma_px", C.c_double),
                 ("proc_q", C.c_double), ("proc_d", C.c_double), ("omega0", C.c_double),
-                ("res_old0", C.c_double), ("mapping", C.c_int32), ("reserved", C.c_int32)]
+                ("res_old0", C.c_double), ("mapping", C.c_int32), ("flags", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 class Synth(C.Structure):
@@ -55,6 +57,7 @@ lib.pnpb200_last_error.restype = C.c_char_p
 for _name in EXPORTS:
     if _name not in ("pnpb200_last_error",):
         getattr(lib, _name).restype = C.c_int
+lib.pnpb200_workspace_bytes.restype = C.c_int64
 
 _ERR = {-1: "EINVAL (bad argument)", -2: "ECUDA (CUDA runtime error)", -3: "ENODEVICE (no usable CUDA device)",
         -4: "ETOOLARGE (n too large for the selected mapping)"}

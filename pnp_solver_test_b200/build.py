@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libpnpb200.so")
 SOURCES = ["pnpb200_solve.cu", "pnpb200_aux.cu"]
-HEADERS = ["pnpb200_common.cuh", "pnpb200_math.cuh", "pnpb200_solvers.cuh", os.path.join("..", "..", "include", "pnpb200.h")]
+HEADERS = ["pnpb200_common.cuh", "pnpb200_math.cuh", "pnpb200_solvers.cuh", "pnpb200_tile.cuh", os.path.join("..", "..", "include", "pnpb200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

@@ -6,6 +6,7 @@
 // coalesced loads, grids sized from the problem count.
 #include "pnpb200_common.cuh"
 #include "pnpb200_math.cuh"
+#include "pnpb200_tile.cuh"
 
 namespace pnpb200 {
 
@@ -247,6 +248,114 @@ __global__ void k_report(long long B, int n, const void* pattern, const void* uv
             flags[b * 4 + 3] = fabs(yaw_e - yaw_g) < bounds.b[3];
         }
         if (max_idx) { max_idx[b * 3] = i0; max_idx[b * 3 + 1] = i1; max_idx[b * 3 + 2] = i2; }
+    }
+}
+
+// Same report, one problem per thread: the 32 pixel rows of a warp's problems are staged by TMA
+// bulk copies (pnpb200_tile.cuh), K is folded into the two poses once per problem (M = K R,
+// m = K t), and the Euler -> R trigonometry is done once per problem instead of once per lane.
+template <typename T>
+struct ReportArgs {
+    const T* pattern; const T* uv; const T* R; const T* t; const T* euler;
+    const double* gt;
+    long long B;
+    int n, row_pitch, use_tma;
+    double K[9], bounds[4];
+    double* report; int32_t* flags; int32_t* max_idx;
+};
+
+PNP_DEV void fold_camera(const double* K, const double (&R)[9], const double (&t)[3], double (&M)[9], double (&m)[3])
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) M[r * 3 + c] = K[r * 3] * R[c] + K[r * 3 + 1] * R[3 + c] + K[r * 3 + 2] * R[6 + c];
+        m[r] = K[r * 3] * t[0] + K[r * 3 + 1] * t[1] + K[r * 3 + 2] * t[2];
+    }
+}
+
+PNP_DEV void project_folded(const double (&M)[9], const double (&m)[3], double x, double y, double z, double (&o)[3])
+{
+    const double r0 = fma(M[0], x, fma(M[1], y, fma(M[2], z, m[0])));
+    const double r1 = fma(M[3], x, fma(M[4], y, fma(M[5], z, m[1])));
+    const double r2 = fma(M[6], x, fma(M[7], y, fma(M[8], z, m[2])));
+    const double inv = 1.0 / fabs(r2);                    // :4548 divides by |z|
+    o[0] = r0 * inv; o[1] = r1 * inv; o[2] = copysign(1.0, r2);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ ReportArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* sRows = reinterpret_cast<T*>(smem_raw);
+    T* sP = sRows + (size_t)kTileProblems * a.row_pitch;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sP + (size_t)a.n * 3) - smem_raw)) + 7) & ~(size_t)7));
+    const int lane = threadIdx.x;
+    typedef typename Vec2<T>::type V2;
+    RowTile<T> tile_buf;
+    const double kdummy[6] = { 1, 0, 0, 0, 1, 0 };
+    tile_buf.init(sRows, bar, a.uv, a.B, a.n, a.row_pitch, a.use_tma, kdummy, lane, /*normalise=*/false);
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    long long tile = blockIdx.x;
+    int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
+    for (int e = lane; e < a.n * 3; e += 32) sP[e] = a.pattern[e];
+    __syncwarp();
+    while (tile < n_tiles) {
+        long long b = tile * kTileProblems + lane;
+        const bool ok = b < a.B;
+        if (!ok) b = a.B - 1;
+        double Re[9], te[3], Rg[9], tg[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Re[k] = (double)a.R[b * 9 + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) te[k] = (double)a.t[b * 3 + k];
+        const double roll_e = (double)a.euler[b * 3], yaw_e = (double)a.euler[b * 3 + 1], pitch_e = (double)a.euler[b * 3 + 2];
+        const double dist = a.gt[b * 4], roll_g = a.gt[b * 4 + 1], pitch_g = a.gt[b * 4 + 2], yaw_g = a.gt[b * 4 + 3];
+        const double t3 = te[2];
+        R_from_euler(roll_g, yaw_g, pitch_g, true, Rg);   // random_stress_test.py:365
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tg[k] = (te[k] / t3) * dist;   // :367-368
+        double Me[9], me[3], Mg[9], mg[3];
+        fold_camera(a.K, Re, te, Me, me);
+        fold_camera(a.K, Rg, tg, Mg, mg);
+        const V2* row = reinterpret_cast<const V2*>(tile_buf.acquire(lane, valid));
+        double s0 = 0, s1 = 0, s2 = 0, m0 = 0, m1 = 0, m2 = 0;
+        int i0 = -1, i1 = -1, i2 = -1;
+        for (int i = 0; i < a.n; ++i) {
+            const double x = (double)sP[3 * i], y = (double)sP[3 * i + 1], z = (double)sP[3 * i + 2];
+            double pe[3], pg[3];
+            project_folded(Me, me, x, y, z, pe);          // TEST_TOOLBOX.py:312
+            project_folded(Mg, mg, x, y, z, pg);          // :314
+            const V2 px = row[i];
+            const double mu = (double)px.x, mv = (double)px.y, mw = 1.0;
+            double d0, d1, d2, e;
+            d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];             // LM vs GT (:321)
+            e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
+            d0 = pe[0] - mu; d1 = pe[1] - mv; d2 = pe[2] - mw;             // prediction vs LM (:326)
+            e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
+            d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1]; d2 = pe[2] - pg[2];    // prediction vs GT (:331)
+            e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
+        }
+        if (ok) {
+            double* rp = a.report + b * PNPB200_REPORT_WIDTH;
+            rp[0] = t3 - dist; rp[1] = roll_e - roll_g; rp[2] = pitch_e - pitch_g; rp[3] = yaw_e - yaw_g;
+            rp[4] = (s0 / a.n) * dist; rp[5] = m0 * dist;
+            rp[6] = (s1 / a.n) * dist; rp[7] = m1 * dist;
+            rp[8] = (s2 / a.n) * dist; rp[9] = m2 * dist;
+            rp[10] = t3; rp[11] = dist; rp[12] = roll_e; rp[13] = pitch_e; rp[14] = yaw_e; rp[15] = 0.0;
+            if (a.flags) {
+                a.flags[b * 4] = fabs(t3 * 100.0 - dist * 100.0) < a.bounds[0];
+                a.flags[b * 4 + 1] = fabs(roll_e - roll_g) < a.bounds[1];
+                a.flags[b * 4 + 2] = fabs(pitch_e - pitch_g) < a.bounds[2];
+                a.flags[b * 4 + 3] = fabs(yaw_e - yaw_g) < a.bounds[3];
+            }
+            if (a.max_idx) { a.max_idx[b * 3] = i0; a.max_idx[b * 3 + 1] = i1; a.max_idx[b * 3 + 2] = i2; }
+        }
+        tile += gridDim.x;
+        if (tile < n_tiles) {
+            tile_buf.release();
+            valid = tile_buf.issue(tile, lane);
+        }
     }
 }
 
@@ -494,10 +603,31 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
     Bounds bd;
     for (int e = 0; e < 4; ++e) bd.b[e] = bounds ? bounds[e] : 10.0;
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = grid_for(B * 32, 256);
-    DISPATCH_DTYPE(dtype,
-                   (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)),
-                   (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)));
+    const size_t esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
+    const RowGeom g = (dtype == PNPB200_DTYPE_F64) ? row_geometry<double>(n) : row_geometry<float>(n);
+    const size_t smem = g.tile_bytes + (size_t)n * 3 * esz + 16;
+    if (g.tile_bytes <= 48 * 1024) {
+        const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
+        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
+#define LAUNCH_REPORT_THREAD(TT)                                                                                        \
+        {                                                                                                               \
+            ReportArgs<TT> a;                                                                                           \
+            a.pattern = (const TT*)pattern; a.uv = (const TT*)uv; a.R = (const TT*)R; a.t = (const TT*)t;              \
+            a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = g.row_pitch; a.use_tma = g.use_tma; \
+            for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
+            for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
+            a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
+            PNP_CUDA_OK(cudaFuncSetAttribute(k_report_thread<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_report_thread<TT><<<grid, 32, smem, st>>>(a);                                                             \
+        }
+        DISPATCH_DTYPE(dtype, LAUNCH_REPORT_THREAD(double), LAUNCH_REPORT_THREAD(float));
+#undef LAUNCH_REPORT_THREAD
+    } else {
+        const unsigned grid = grid_for(B * 32, 256);
+        DISPATCH_DTYPE(dtype,
+                       (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)),
+                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)));
+    }
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

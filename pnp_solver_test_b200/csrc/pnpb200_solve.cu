@@ -23,6 +23,7 @@
 
 #include "pnpb200_common.cuh"
 #include "pnpb200_solvers.cuh"
+#include "pnpb200_tile.cuh"
 
 namespace pnpb200 {
 
@@ -53,10 +54,50 @@ int get_device_props(DeviceProps* out)
     PNP_CUDA_OK(cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     size_t free_b = 0;
     PNP_CUDA_OK(cudaMemGetInfo(&free_b, &p.total_mem));
+    {   // keep stream-ordered scratch cached in the device's default pool instead of returning it
+        // to the driver at every synchronisation (a moment-mapping call would re-map it each time)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     cache.push_back(p);
     *out = p;
     return PNPB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// optional per-kernel timing (PNPB200_FLAG_PROFILE): a ring of event quadruples per host thread
+// ------------------------------------------------------------------------------------------
+struct ProfileRing {
+    static constexpr int kSlots = 64;
+    cudaEvent_t ev[kSlots][4];
+    int used[kSlots];     // number of events recorded in the slot (0 = empty)
+    bool created = false;
+    int next = 0, count = 0;
+    int begin()
+    {
+        if (!created) {
+            for (int s = 0; s < kSlots; ++s) {
+                for (int e = 0; e < 4; ++e) cudaEventCreate(&ev[s][e]);
+                used[s] = 0;
+            }
+            created = true;
+        }
+        const int s = next;
+        next = (next + 1) % kSlots;
+        if (count < kSlots) ++count;
+        used[s] = 0;
+        return s;
+    }
+    void mark(int slot, cudaStream_t st)
+    {
+        if (slot >= 0 && used[slot] < 4) cudaEventRecord(ev[slot][used[slot]++], st);
+    }
+};
+static thread_local ProfileRing g_prof;
 
 // ------------------------------------------------------------------------------------------
 // kernel arguments
@@ -74,56 +115,9 @@ struct SolveArgs {
     SolverPrm<T> prm;
     T* R; T* t; T* euler; T* res;
     int32_t* iters; int32_t* best;
+    void* ws; size_t ws_bytes;   // optional caller scratch (moment mapping)
+    int profile;
 };
-
-template <typename T> struct Vec2;
-template <> struct Vec2<double> { typedef double2 type; };
-template <> struct Vec2<float> { typedef float2 type; };
-
-// normalised correspondences of one problem: that problem's row in shared memory (thread mapping)
-template <typename T>
-struct PtsRow {
-    const T* row;          // [n_total][2], already multiplied by K^-1
-    const int32_t* idx;    // shared-memory copy of the landmark selection, or nullptr
-    PNP_DEV void get(int i, T& bx, T& by) const
-    {
-        const int j = idx ? idx[i] : i;
-        const typename Vec2<T>::type p = reinterpret_cast<const typename Vec2<T>::type*>(row)[j];
-        bx = p.x;
-        by = p.y;
-    }
-};
-
-// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
-PNP_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-PNP_DEV void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-PNP_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-PNP_DEV void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-PNP_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-PNP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // raw pixels of one problem in global memory, normalised on the fly (warp mapping)
 template <typename T>
@@ -240,90 +234,6 @@ PNP_DEV void load_pattern(const T* __restrict__ pattern, const int32_t* __restri
         sP[e] = pattern[((size_t)p * n_total + src) * 3 + c];
     }
     __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------
-// Row tile: 32 consecutive problems' pixel rows staged in shared memory by one warp.
-// Lane l issues one TMA bulk copy of row l (completion on an mbarrier), waits, and multiplies its
-// row by K^-1 in place (f2_get_B_xy :3291-3312).  Row pitch = odd multiple of 16 B.
-// ------------------------------------------------------------------------------------------
-constexpr int kTileProblems = 32;
-
-template <typename T>
-struct RowTile {
-    T* rows;
-    uint64_t* bar;
-    const T* uv;
-    long long B;
-    int n_total, row_pitch, use_tma;
-    uint32_t phase, row_bytes;
-    T k00, k01, k02, k10, k11, k12;
-
-    PNP_DEV void init(T* rows_, uint64_t* bar_, const T* uv_, long long B_, int n_total_, int row_pitch_, int use_tma_,
-                      const double* kinv, int lane)
-    {
-        rows = rows_; bar = bar_; uv = uv_; B = B_; n_total = n_total_; row_pitch = row_pitch_; use_tma = use_tma_;
-        phase = 0; row_bytes = (uint32_t)n_total * 2u * (uint32_t)sizeof(T);
-        k00 = (T)kinv[0]; k01 = (T)kinv[1]; k02 = (T)kinv[2]; k10 = (T)kinv[3]; k11 = (T)kinv[4]; k12 = (T)kinv[5];
-        if (use_tma) {
-            if (lane == 0) mbar_init(bar, 1);
-            __syncwarp();
-        }
-    }
-    // start filling the tile; returns the number of valid problems in it
-    PNP_DEV int issue(long long tile, int lane)
-    {
-        const long long b0 = tile * kTileProblems;
-        const int valid = (int)((B - b0 < kTileProblems) ? (B - b0) : kTileProblems);
-        if (use_tma) {
-            if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)valid);
-            __syncwarp();
-            if (lane < valid) bulk_copy_g2s(rows + (size_t)lane * row_pitch, uv + (size_t)(b0 + lane) * n_total * 2, row_bytes, bar);
-        } else {
-            // rows not 16-byte granular (FP32 with odd n_total): coalesced element loads instead
-            const int per_row = n_total * 2;
-            for (int e = lane; e < valid * per_row; e += 32) {
-                const int p = e / per_row, c = e - p * per_row;
-                rows[(size_t)p * row_pitch + c] = __ldg(uv + (size_t)b0 * per_row + e);
-            }
-        }
-        return valid;
-    }
-    // wait for the fill, normalise, return this lane's row (spare lanes of a ragged tile shadow
-    // the last valid problem so that the whole warp stays converged)
-    PNP_DEV const T* acquire(int lane, int valid)
-    {
-        typedef typename Vec2<T>::type V2;
-        if (use_tma) { mbar_wait(bar, phase); phase ^= 1u; }
-        else         { __syncwarp(); }
-        const int my = (lane < valid) ? lane : (valid - 1);
-        T* row = rows + (size_t)my * row_pitch;
-        if (lane < valid) {                               // nu = K^-1 [u, v, 1]^T (:3305)
-            V2* r2 = reinterpret_cast<V2*>(row);
-#pragma unroll 4
-            for (int i = 0; i < n_total; ++i) {
-                const V2 px = r2[i];
-                V2 o;
-                o.x = k00 * px.x + k01 * px.y + k02;
-                o.y = k10 * px.x + k11 * px.y + k12;
-                r2[i] = o;
-            }
-        }
-        __syncwarp();
-        return row;
-    }
-    // generic-proxy accesses to the tile are done; the next async-proxy fill may start
-    PNP_DEV void release()
-    {
-        __syncwarp();
-        fence_proxy_async();
-    }
-};
-
-template <typename T>
-PNP_DEV uint64_t* carve_bar(unsigned char* smem_raw, const void* after)
-{
-    return reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((const unsigned char*)after - smem_raw) + 7) & ~(size_t)7));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -641,23 +551,8 @@ static void fill_default_params(pnpb200_params* p)
     p->lm_lambda = 1e-5; p->exit_tol = 1e-2;
     p->f_weight = 225.68; p->meas_sigma_px = 3.0;
     p->proc_q = 1e-1; p->proc_d = 1e-2; p->omega0 = 1e-5; p->res_old0 = 1e-7;
-    p->mapping = PNPB200_MAP_AUTO; p->reserved = 0;
-}
-
-struct RowGeom { int row_pitch, use_tma; size_t tile_bytes; };
-
-template <typename T>
-static RowGeom row_geometry(int n_total)
-{
-    // row pitch = odd multiple of 16 bytes (conflict-free 16-byte per-lane reads, TMA-aligned)
-    RowGeom g;
-    const size_t row_bytes = (size_t)n_total * 2 * sizeof(T);
-    size_t units = (row_bytes + 15) / 16;
-    if ((units & 1) == 0) ++units;
-    g.row_pitch = (int)(units * 16 / sizeof(T));
-    g.use_tma = (row_bytes % 16 == 0) ? 1 : 0;
-    g.tile_bytes = (size_t)kTileProblems * g.row_pitch * sizeof(T);
-    return g;
+    p->mapping = PNPB200_MAP_AUTO; p->flags = 0;
+    p->workspace = nullptr; p->workspace_bytes = 0;
 }
 
 static long long persistent_grid(long long work_items, int sm_count, int per_sm)
@@ -681,7 +576,9 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
 
     T* ws = nullptr;
     const size_t ws_elems = (size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)a.B + PNP_PATC;
-    PNP_CUDA_OK(cudaMallocAsync((void**)&ws, ws_elems * sizeof(T), stream));
+    const bool own_ws = !(a.ws && a.ws_bytes >= ws_elems * sizeof(T));
+    if (own_ws) PNP_CUDA_OK(cudaMallocAsync((void**)&ws, ws_elems * sizeof(T), stream));
+    else ws = (T*)a.ws;
     MomArgs<T> m;
     m.uv = a.uv; m.pattern = a.pattern; m.idx = a.idx; m.B = a.B; m.n_total = a.n_total; m.n = a.n;
     m.row_pitch = g.row_pitch; m.use_tma = g.use_tma;
@@ -692,13 +589,18 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
 
     k_pattern_constants<T><<<1, 32, 0, stream>>>(a.pattern, a.idx, a.n, m.patc);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    const int slot = a.profile ? g_prof.begin() : -1;
+    g_prof.mark(slot, stream);
     if (by_thread) {
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
         const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
         k_stream_thread<T, METHOD, 0><<<grid, 32, thread_smem, stream>>>(m);
+        g_prof.mark(slot, stream);
         k_iterate<T, METHOD><<<(unsigned)((a.B + kIterBlock - 1) / kIterBlock), kIterBlock, 0, stream>>>(m);
+        g_prof.mark(slot, stream);
         if (a.res) k_stream_thread<T, METHOD, 1><<<grid, 32, thread_smem, stream>>>(m);
+        g_prof.mark(slot, stream);
     } else {
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
@@ -706,11 +608,14 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
         PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp<T, METHOD, 0>, 256, warp_smem));
         const unsigned grid = (unsigned)persistent_grid((a.B + 7) / 8, dp.sm_count, per_sm);
         k_stream_warp<T, METHOD, 0><<<grid, 256, warp_smem, stream>>>(m);
+        g_prof.mark(slot, stream);
         k_iterate<T, METHOD><<<(unsigned)((a.B + kIterBlock - 1) / kIterBlock), kIterBlock, 0, stream>>>(m);
+        g_prof.mark(slot, stream);
         if (a.res) k_stream_warp<T, METHOD, 1><<<grid, 256, warp_smem, stream>>>(m);
+        g_prof.mark(slot, stream);
     }
     PNP_CUDA_OK(cudaGetLastError());
-    PNP_CUDA_OK(cudaFreeAsync(ws, stream));
+    if (own_ws) PNP_CUDA_OK(cudaFreeAsync(ws, stream));
     return PNPB200_OK;
 }
 
@@ -742,14 +647,20 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
         at.use_tma = g.use_tma;
         const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
         const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
+        const int slot = a.profile ? g_prof.begin() : -1;
+        g_prof.mark(slot, stream);
         k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(at);
+        g_prof.mark(slot, stream);
     } else if (mapping == PNPB200_MAP_WARP) {
         if (warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
         PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_warp<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
         int per_sm = 1;
         PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_warp<T, METHOD>, kWarpsPerBlock * 32, warp_smem));
         const long long grid = persistent_grid((a.B + kWarpsPerBlock - 1) / kWarpsPerBlock, dp.sm_count, per_sm);
+        const int slot = a.profile ? g_prof.begin() : -1;
+        g_prof.mark(slot, stream);
         k_solve_warp<T, METHOD><<<(unsigned)grid, kWarpsPerBlock * 32, warp_smem, stream>>>(a);
+        g_prof.mark(slot, stream);
     } else {
         return PNPB200_EINVAL;
     }
@@ -771,6 +682,8 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     for (int e = 0; e < 6; ++e) a.kinv[e] = Kinv[e];
     a.prm = make_prm<T>(prm);
     a.R = (T*)R; a.t = (T*)t; a.euler = (T*)euler; a.res = (T*)res; a.iters = iters; a.best = best;
+    a.profile = (prm.flags & PNPB200_FLAG_PROFILE) ? 1 : 0;
+    a.ws = prm.workspace; a.ws_bytes = (prm.workspace && prm.workspace_bytes > 0) ? (size_t)prm.workspace_bytes : 0;
     switch (method) {
     case PNPB200_METHOD_QEIF:      return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);
     case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
@@ -806,6 +719,43 @@ int pnpb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hb
     if (cc_minor) *cc_minor = dp.cc_minor;
     if (hbm_bytes) *hbm_bytes = (int64_t)dp.total_mem;
     return PNPB200_OK;
+}
+
+int pnpb200_profile_reset(void)
+{
+    g_prof.next = 0; g_prof.count = 0;
+    if (g_prof.created)
+        for (int s = 0; s < ProfileRing::kSlots; ++s) g_prof.used[s] = 0;
+    return PNPB200_OK;
+}
+
+int pnpb200_profile_read(float* ms, int* n_calls)
+{
+    if (!ms) return PNPB200_EINVAL;
+    double acc[3] = { 0, 0, 0 };
+    int calls = 0;
+    for (int s = 0; s < g_prof.count && g_prof.created; ++s) {
+        const int u = g_prof.used[s];
+        if (u < 2) continue;
+        PNP_CUDA_OK(cudaEventSynchronize(g_prof.ev[s][u - 1]));
+        for (int k = 0; k + 1 < u; ++k) {
+            float t = 0.f;
+            PNP_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[s][k], g_prof.ev[s][k + 1]));
+            acc[k] += t;
+        }
+        ++calls;
+    }
+    for (int k = 0; k < 3; ++k) ms[k] = calls ? (float)(acc[k] / calls) : 0.f;
+    if (n_calls) *n_calls = calls;
+    return PNPB200_OK;
+}
+
+int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping)
+{
+    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2) && n_patterns == 1;
+    if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
+    const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
+    return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
 }
 
 int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
@@ -848,6 +798,8 @@ struct pnpb200_pipeline {
     std::vector<cudaStream_t> streams;
     std::vector<void*> d_uv, d_R, d_t, d_e, d_res;
     std::vector<int32_t*> d_it, d_best;
+    std::vector<void*> d_ws;
+    size_t ws_bytes;
     void* d_pattern;
 };
 
@@ -862,6 +814,7 @@ int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_pro
     p->chunk = chunk_problems;
     p->esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
     p->d_pattern = nullptr;
+    p->ws_bytes = ((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)chunk_problems + PNP_PATC) * p->esz;
     *out = p;
     PNP_CUDA_OK(cudaMalloc(&p->d_pattern, p->esz * (size_t)n_patterns * n_total * 3));
     for (int s = 0; s < n_streams; ++s) {
@@ -876,6 +829,8 @@ int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_pro
         PNP_CUDA_OK(cudaMalloc(&e, p->esz * (size_t)chunk_problems)); p->d_res.push_back(e);
         PNP_CUDA_OK(cudaMalloc(&f, sizeof(int32_t) * (size_t)chunk_problems)); p->d_it.push_back((int32_t*)f);
         PNP_CUDA_OK(cudaMalloc(&g, sizeof(int32_t) * (size_t)chunk_problems)); p->d_best.push_back((int32_t*)g);
+        void* w = nullptr;
+        PNP_CUDA_OK(cudaMalloc(&w, p->ws_bytes)); p->d_ws.push_back(w);
     }
     return PNPB200_OK;
 }
@@ -891,6 +846,7 @@ int pnpb200_pipeline_destroy(pnpb200_pipeline* p)
     for (void* q : p->d_res) cudaFree(q);
     for (int32_t* q : p->d_it) cudaFree(q);
     for (int32_t* q : p->d_best) cudaFree(q);
+    for (void* q : p->d_ws) cudaFree(q);
     if (p->d_pattern) cudaFree(p->d_pattern);
     delete p;
     return PNPB200_OK;
@@ -913,8 +869,11 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
         cudaStream_t st = p->streams[s];
         const char* src = (const char*)uv_host + esz * (size_t)done * p->n_total * 2;
         PNP_CUDA_OK(cudaMemcpyAsync(p->d_uv[s], src, esz * (size_t)nb * p->n_total * 2, cudaMemcpyHostToDevice, st));
+        pnpb200_params prm;
+        if (params) prm = *params; else fill_default_params(&prm);
+        if (!prm.workspace) { prm.workspace = p->d_ws[s]; prm.workspace_bytes = (int64_t)p->ws_bytes; }
         int rc = pnpb200_solve_batch(method, p->dtype, nb, p->n_total, n, p->d_uv[s], p->d_pattern, p->n_patterns,
-                                     point_index, K, params, R ? p->d_R[s] : nullptr, t ? p->d_t[s] : nullptr,
+                                     point_index, K, &prm, R ? p->d_R[s] : nullptr, t ? p->d_t[s] : nullptr,
                                      euler_deg ? p->d_e[s] : nullptr, res_norm ? p->d_res[s] : nullptr,
                                      iters ? p->d_it[s] : nullptr, best_pattern ? p->d_best[s] : nullptr, st);
         if (rc != PNPB200_OK) return rc;

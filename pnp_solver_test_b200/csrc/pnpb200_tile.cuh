@@ -1,0 +1,166 @@
+// pnpb200_tile.cuh -- shared-memory row tiles filled by TMA bulk copies (cp.async.bulk + mbarrier).
+//
+// Used by every one-problem-per-thread kernel: a CTA is ONE warp that owns 32 consecutive
+// problems; lane l copies problem l's [n_total, 2] pixel row from HBM into a padded shared-memory
+// row with a single bulk copy.  The row pitch is an odd multiple of 16 bytes, so the per-lane
+// 16-byte reads that follow are bank-conflict free.
+#pragma once
+#include <stdint.h>
+#include "pnpb200_math.cuh"
+
+namespace pnpb200 {
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { typedef double2 type; };
+template <> struct Vec2<float> { typedef float2 type; };
+
+// normalised correspondences of one problem: that problem's row in shared memory (thread mapping)
+template <typename T>
+struct PtsRow {
+    const T* row;          // [n_total][2], already multiplied by K^-1
+    const int32_t* idx;    // shared-memory copy of the landmark selection, or nullptr
+    PNP_DEV void get(int i, T& bx, T& by) const
+    {
+        const int j = idx ? idx[i] : i;
+        const typename Vec2<T>::type p = reinterpret_cast<const typename Vec2<T>::type*>(row)[j];
+        bx = p.x;
+        by = p.y;
+    }
+};
+
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+PNP_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+PNP_DEV void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PNP_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PNP_DEV void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+PNP_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+PNP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// Row tile: 32 consecutive problems' pixel rows staged in shared memory by one warp.
+// Lane l issues one TMA bulk copy of row l (completion on an mbarrier), waits, and multiplies its
+// row by K^-1 in place (f2_get_B_xy :3291-3312).  Row pitch = odd multiple of 16 B.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileProblems = 32;
+
+template <typename T>
+struct RowTile {
+    T* rows;
+    uint64_t* bar;
+    const T* uv;
+    long long B;
+    int n_total, row_pitch, use_tma;
+    uint32_t phase, row_bytes;
+    T k00, k01, k02, k10, k11, k12;
+
+    bool normalise;
+
+    PNP_DEV void init(T* rows_, uint64_t* bar_, const T* uv_, long long B_, int n_total_, int row_pitch_, int use_tma_,
+                      const double* kinv, int lane, bool normalise_ = true)
+    {
+        rows = rows_; bar = bar_; uv = uv_; B = B_; n_total = n_total_; row_pitch = row_pitch_; use_tma = use_tma_;
+        normalise = normalise_;
+        phase = 0; row_bytes = (uint32_t)n_total * 2u * (uint32_t)sizeof(T);
+        k00 = (T)kinv[0]; k01 = (T)kinv[1]; k02 = (T)kinv[2]; k10 = (T)kinv[3]; k11 = (T)kinv[4]; k12 = (T)kinv[5];
+        if (use_tma) {
+            if (lane == 0) mbar_init(bar, 1);
+            __syncwarp();
+        }
+    }
+    // start filling the tile; returns the number of valid problems in it
+    PNP_DEV int issue(long long tile, int lane)
+    {
+        const long long b0 = tile * kTileProblems;
+        const int valid = (int)((B - b0 < kTileProblems) ? (B - b0) : kTileProblems);
+        if (use_tma) {
+            if (lane == 0) mbar_expect_tx(bar, row_bytes * (uint32_t)valid);
+            __syncwarp();
+            if (lane < valid) bulk_copy_g2s(rows + (size_t)lane * row_pitch, uv + (size_t)(b0 + lane) * n_total * 2, row_bytes, bar);
+        } else {
+            // rows not 16-byte granular (FP32 with odd n_total): coalesced element loads instead
+            const int per_row = n_total * 2;
+            for (int e = lane; e < valid * per_row; e += 32) {
+                const int p = e / per_row, c = e - p * per_row;
+                rows[(size_t)p * row_pitch + c] = __ldg(uv + (size_t)b0 * per_row + e);
+            }
+        }
+        return valid;
+    }
+    // wait for the fill, normalise, return this lane's row (spare lanes of a ragged tile shadow
+    // the last valid problem so that the whole warp stays converged)
+    PNP_DEV const T* acquire(int lane, int valid)
+    {
+        typedef typename Vec2<T>::type V2;
+        if (use_tma) { mbar_wait(bar, phase); phase ^= 1u; }
+        else         { __syncwarp(); }
+        const int my = (lane < valid) ? lane : (valid - 1);
+        T* row = rows + (size_t)my * row_pitch;
+        if (normalise && lane < valid) {                  // nu = K^-1 [u, v, 1]^T (:3305)
+            V2* r2 = reinterpret_cast<V2*>(row);
+#pragma unroll 4
+            for (int i = 0; i < n_total; ++i) {
+                const V2 px = r2[i];
+                V2 o;
+                o.x = k00 * px.x + k01 * px.y + k02;
+                o.y = k10 * px.x + k11 * px.y + k12;
+                r2[i] = o;
+            }
+        }
+        __syncwarp();
+        return row;
+    }
+    // generic-proxy accesses to the tile are done; the next async-proxy fill may start
+    PNP_DEV void release()
+    {
+        __syncwarp();
+        fence_proxy_async();
+    }
+};
+
+template <typename T>
+PNP_DEV uint64_t* carve_bar(unsigned char* smem_raw, const void* after)
+{
+    return reinterpret_cast<uint64_t*>(smem_raw + (((size_t)((const unsigned char*)after - smem_raw) + 7) & ~(size_t)7));
+}
+
+
+struct RowGeom { int row_pitch, use_tma; size_t tile_bytes; };
+
+template <typename T>
+inline RowGeom row_geometry(int n_total)
+{
+    // row pitch = odd multiple of 16 bytes (conflict-free 16-byte per-lane reads, TMA-aligned)
+    RowGeom g;
+    const size_t row_bytes = (size_t)n_total * 2 * sizeof(T);
+    size_t units = (row_bytes + 15) / 16;
+    if ((units & 1) == 0) ++units;
+    g.row_pitch = (int)(units * 16 / sizeof(T));
+    g.use_tma = (row_bytes % 16 == 0) ? 1 : 0;
+    g.tile_bytes = (size_t)kTileProblems * g.row_pitch * sizeof(T);
+    return g;
+}
+
+}  // namespace pnpb200

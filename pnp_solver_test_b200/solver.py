@@ -39,6 +39,12 @@ def _k_host(K):
     return K, K.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def _copy_params(p):
+    q = _lib.Params()
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(_lib.Params))
+    return q
+
+
 def solve_batch(method, uv, patterns, K, point_index=None, params=None, want=("R", "t", "euler", "res_norm", "iters", "best_pattern")):
     """pnpb200_solve_batch on device tensors.
 
@@ -74,6 +80,16 @@ def solve_batch(method, uv, patterns, K, point_index=None, params=None, want=("R
     Kh, Kp = _k_host(K)
     if B == 0:
         return o
+    # scratch for the moment mapping from torch's caching allocator (stream-ordered, no driver call)
+    prm = _lib.default_params() if params is None else params
+    ws_bytes = int(lib.pnpb200_workspace_bytes(C.c_int(m), C.c_int(dt), C.c_int64(B), C.c_int(int(patterns.shape[0])),
+                                               C.c_int(int(prm.mapping))))
+    ws = None
+    if ws_bytes > 0 and not prm.workspace:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        prm = _copy_params(prm)
+        prm.workspace, prm.workspace_bytes = ws.data_ptr(), ws_bytes
+    params = prm
     with torch.cuda.device(dev):
         rc = lib.pnpb200_solve_batch(
             C.c_int(m), C.c_int(dt), C.c_int64(B), C.c_int(n_total), C.c_int(n), ptr(uv), ptr(patterns),

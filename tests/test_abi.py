@@ -26,11 +26,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from pnp_solver_test_b200 import _lib
-    assert C.sizeof(_lib.Params) == 2 * 4 + 8 * 8 + 2 * 4
+    assert C.sizeof(_lib.Params) == 2 * 4 + 8 * 8 + 2 * 4 + 8 + 8
     assert C.sizeof(_lib.Synth) == 8 + 4 * 8 + 2 * 4 + 2 * 8
     p = _lib.default_params()
     assert (p.max_it, p.linear_it, p.lm_lambda, p.exit_tol, p.f_weight) == (14, 3, 1e-5, 1e-2, 225.68)
     assert (p.meas_sigma_px, p.proc_q, p.proc_d, p.omega0, p.res_old0, p.mapping) == (3.0, 0.1, 0.01, 1e-5, 1e-7, 0)
+    assert (p.flags, p.workspace, p.workspace_bytes) == (0, None, 0)
     s = _lib.default_synth()
     assert (s.seed, s.angle_range_deg, s.depth_min_m, s.depth_max_m, s.fov_max_deg) == (42, 45.0, 0.2, 2.25, 45.0)
     assert (s.is_quantized, s.quantize_q, s.noise_sigma_px) == (1, 1.0, 0.0)

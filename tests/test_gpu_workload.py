@@ -105,3 +105,16 @@ def test_report_on_cuda_solution_matches_oracle_report():
     assert np.array_equal(rep["flags"].cpu().numpy(), ref["flags"])
     assert (rep["max_idx"].cpu().numpy() == ref["max_idx"]).mean() > 0.999
     assert ref["flags"].all(axis=1).mean() > 0.95
+
+
+def test_report_warp_kernel_for_large_patterns():
+    """n = 1024: the 32-row tile no longer fits, the one-warp-per-problem report kernel runs."""
+    from pnp_solver_test_b200 import workload as wl
+    P, K = pt.pattern_array(pt.synthetic_pattern(1024)), pt.default_camera_matrix()
+    w = orc.synth(0, 200, P, K)
+    s = orc.solve_batch("linear_f2", w["uv"], P, K)
+    ref = orc.report_batch(P, w["uv"], K, s["R"], s["t"], s["euler"], w["gt"])
+    rep = wl.report_batch(P, dev(w["uv"]), K, dev(s["R"]), dev(s["t"]), dev(s["euler"]), dev(w["gt"]))
+    assert np.abs(rep["report"].cpu().numpy() - ref["report"]).max() < 1e-9
+    assert np.array_equal(rep["flags"].cpu().numpy(), ref["flags"])
+    assert (rep["max_idx"].cpu().numpy() == ref["max_idx"]).mean() > 0.99
