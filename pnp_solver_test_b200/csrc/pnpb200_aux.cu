@@ -359,6 +359,87 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
     }
 }
 
+// Streaming variant of k_report_thread: the rows go through two small chunk buffers (RowStream).
+template <typename T>
+__global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ ReportArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename Vec2<T>::type V2;
+    T* sBuf = reinterpret_cast<T*>(smem_raw);
+    T* sP = sBuf + (size_t)2 * kTileProblems * a.row_pitch;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sP + (size_t)a.n * 3) - smem_raw)) + 7) & ~(size_t)7));
+    const int lane = threadIdx.x;
+    RowStream<T> rs;
+    rs.init(sBuf, bars, a.uv, a.B, a.n, a.use_tma /* chunk */, a.row_pitch, lane);
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    long long tile = blockIdx.x;
+    if (tile < n_tiles) rs.begin_tile(tile, lane);
+    for (int e = lane; e < a.n * 3; e += 32) sP[e] = a.pattern[e];
+    __syncwarp();
+    while (tile < n_tiles) {
+        long long b = tile * kTileProblems + lane;
+        const bool ok = b < a.B;
+        if (!ok) b = a.B - 1;
+        double Re[9], te[3], Rg[9], tg[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Re[k] = (double)a.R[b * 9 + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) te[k] = (double)a.t[b * 3 + k];
+        const double roll_e = (double)a.euler[b * 3], yaw_e = (double)a.euler[b * 3 + 1], pitch_e = (double)a.euler[b * 3 + 2];
+        const double dist = a.gt[b * 4], roll_g = a.gt[b * 4 + 1], pitch_g = a.gt[b * 4 + 2], yaw_g = a.gt[b * 4 + 3];
+        const double t3 = te[2];
+        R_from_euler(roll_g, yaw_g, pitch_g, true, Rg);   // random_stress_test.py:365
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tg[k] = (te[k] / t3) * dist;   // :367-368
+        double Me[9], me[3], Mg[9], mg[3];
+        fold_camera(a.K, Re, te, Me, me);
+        fold_camera(a.K, Rg, tg, Mg, mg);
+        double s0 = 0, s1 = 0, s2 = 0, m0 = 0, m1 = 0, m2 = 0;
+        int i0 = -1, i1 = -1, i2 = -1;
+        for (int c = 0; c < rs.n_chunks; ++c) {
+            const V2* row = rs.wait(c, lane);
+            const int cnt = rs.count(c), base = c * rs.chunk;
+            for (int k = 0; k < cnt; ++k) {
+                const int i = base + k;
+                const double x = (double)sP[3 * i], y = (double)sP[3 * i + 1], z = (double)sP[3 * i + 2];
+                double pe[3], pg[3];
+                project_folded(Me, me, x, y, z, pe);      // TEST_TOOLBOX.py:312
+                project_folded(Mg, mg, x, y, z, pg);      // :314
+                const V2 px = row[k];
+                const double mu = (double)px.x, mv = (double)px.y, mw = 1.0;
+                double d0, d1, d2, e;
+                d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];             // LM vs GT (:321)
+                e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
+                d0 = pe[0] - mu; d1 = pe[1] - mv; d2 = pe[2] - mw;             // prediction vs LM (:326)
+                e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
+                d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1]; d2 = pe[2] - pg[2];    // prediction vs GT (:331)
+                e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
+            }
+            rs.done(c, lane);
+        }
+        if (ok) {
+            double* rp = a.report + b * PNPB200_REPORT_WIDTH;
+            rp[0] = t3 - dist; rp[1] = roll_e - roll_g; rp[2] = pitch_e - pitch_g; rp[3] = yaw_e - yaw_g;
+            rp[4] = (s0 / a.n) * dist; rp[5] = m0 * dist;
+            rp[6] = (s1 / a.n) * dist; rp[7] = m1 * dist;
+            rp[8] = (s2 / a.n) * dist; rp[9] = m2 * dist;
+            rp[10] = t3; rp[11] = dist; rp[12] = roll_e; rp[13] = pitch_e; rp[14] = yaw_e; rp[15] = 0.0;
+            if (a.flags) {
+                a.flags[b * 4] = fabs(t3 * 100.0 - dist * 100.0) < a.bounds[0];
+                a.flags[b * 4 + 1] = fabs(roll_e - roll_g) < a.bounds[1];
+                a.flags[b * 4 + 2] = fabs(pitch_e - pitch_g) < a.bounds[2];
+                a.flags[b * 4 + 3] = fabs(yaw_e - yaw_g) < a.bounds[3];
+            }
+            if (a.max_idx) { a.max_idx[b * 3] = i0; a.max_idx[b * 3 + 1] = i1; a.max_idx[b * 3 + 2] = i2; }
+        }
+        tile += gridDim.x;
+        if (tile < n_tiles) {
+            fence_proxy_async();
+            rs.begin_tile(tile, lane);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // statistics (get_statistic_of_result, TEST_TOOLBOX.py:892-937), two SUM/MAX-reducible passes,
 // for up to 4 quantities at once, per class and (last row) over all problems.
@@ -606,7 +687,25 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
     const size_t esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
     const RowGeom g = (dtype == PNPB200_DTYPE_F64) ? row_geometry<double>(n) : row_geometry<float>(n);
     const size_t smem = g.tile_bytes + (size_t)n * 3 * esz + 16;
-    if (g.tile_bytes <= 48 * 1024) {
+    const StreamGeom sg = (dtype == PNPB200_DTYPE_F64) ? stream_geometry<double>(n) : stream_geometry<float>(n);
+    if (g.tile_bytes <= 48 * 1024 && sg.use_stream) {
+        const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
+        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
+        const size_t csmem = 2 * sg.buf_bytes + (size_t)n * 3 * esz + 32;
+#define LAUNCH_REPORT_CHUNK(TT)                                                                                         \
+        {                                                                                                               \
+            ReportArgs<TT> a;                                                                                           \
+            a.pattern = (const TT*)pattern; a.uv = (const TT*)uv; a.R = (const TT*)R; a.t = (const TT*)t;              \
+            a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = sg.pitch; a.use_tma = sg.chunk;  \
+            for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
+            for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
+            a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
+            PNP_CUDA_OK(cudaFuncSetAttribute(k_report_chunk<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+            k_report_chunk<TT><<<grid, 32, csmem, st>>>(a);                                                             \
+        }
+        DISPATCH_DTYPE(dtype, LAUNCH_REPORT_CHUNK(double), LAUNCH_REPORT_CHUNK(float));
+#undef LAUNCH_REPORT_CHUNK
+    } else if (g.tile_bytes <= 48 * 1024) {
         const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
         const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
 #define LAUNCH_REPORT_THREAD(TT)                                                                                        \

@@ -20,6 +20,10 @@ PNP_DEV constexpr int sym(int i, int j) { return i <= j ? sidx<N>(i, j) : sidx<N
 template <typename T> PNP_DEV T t_sqrt(T x);
 template <> PNP_DEV double t_sqrt<double>(double x) { return sqrt(x); }
 template <> PNP_DEV float t_sqrt<float>(float x) { return sqrtf(x); }
+// correctly rounded reciprocal without the slow-path branches of operator/ (MUFU.RCP64H + Newton)
+template <typename T> PNP_DEV T t_rcp(T x);
+template <> PNP_DEV double t_rcp<double>(double x) { return __drcp_rn(x); }
+template <> PNP_DEV float t_rcp<float>(float x) { return __frcp_rn(x); }
 template <typename T> PNP_DEV T t_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> PNP_DEV T t_fma(T a, T b, T c);
 template <> PNP_DEV double t_fma<double>(double a, double b, double c) { return fma(a, b, c); }
@@ -34,7 +38,7 @@ PNP_DEV void ldlt_factor(T (&A)[N * (N + 1) / 2])
 {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        const T inv = T(1) / A[sidx<N>(j, j)];
+        const T inv = t_rcp<T>(A[sidx<N>(j, j)]);
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             const T lij = A[sidx<N>(j, i)] * inv;

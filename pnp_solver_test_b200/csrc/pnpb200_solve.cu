@@ -116,7 +116,7 @@ struct SolveArgs {
     T* R; T* t; T* euler; T* res;
     int32_t* iters; int32_t* best;
     void* ws; size_t ws_bytes;   // optional caller scratch (moment mapping)
-    int profile;
+    int profile, tune;
 };
 
 // raw pixels of one problem in global memory, normalised on the fly (warp mapping)
@@ -399,6 +399,93 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
     }
 }
 
+// Streaming variant of k_stream_thread (all landmarks, rows a multiple of 16 bytes): chunks of the
+// rows go through two small buffers (RowStream), K^-1 is applied on the fly.
+template <typename T, int METHOD, int PASS>
+__global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ MomArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename Vec2<T>::type V2;
+    T* sBuf = reinterpret_cast<T*>(smem_raw);
+    T* sP = sBuf + (size_t)2 * kTileProblems * a.row_pitch;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sP + (size_t)a.n * 3) - smem_raw)) + 7) & ~(size_t)7));
+    const int lane = threadIdx.x;
+    RowStream<T> rs;
+    rs.init(sBuf, bars, a.uv, a.B, a.n_total, a.use_tma /* chunk */, a.row_pitch, lane);
+    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
+    long long tile = blockIdx.x;
+    if (tile < n_tiles) rs.begin_tile(tile, lane);
+    for (int e = lane; e < a.n * 3; e += 32) sP[e] = a.pattern[e];
+    __syncwarp();
+    const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
+    const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
+    while (tile < n_tiles) {
+        long long b = tile * kTileProblems + lane;
+        const bool ok = b < a.B;
+        if (!ok) b = a.B - 1;
+        Moments<T> mom;
+        T x[12];
+        F2Tail<T> f;
+        T acc0 = T(0), acc1 = T(0);
+        if (PASS == 0) mom.zero();
+        else {
+            T st[PNP_NTAIL];
+#pragma unroll
+            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.B + b];
+            if (METHOD == PNPB200_METHOD_LM) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) x[k] = st[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) f.phi3[k] = st[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { f.pxn[k] = st[3 + k]; f.pyn[k] = st[7 + k]; }
+            }
+        }
+        for (int c = 0; c < rs.n_chunks; ++c) {
+            const V2* row = rs.wait(c, lane);
+            const int cnt = rs.count(c), i0 = c * rs.chunk;
+            for (int k = 0; k < cnt; ++k) {
+                const V2 px = row[k];
+                const T bx = k00 * px.x + k01 * px.y + k02;   // nu = K^-1 [u, v, 1]^T (:3305)
+                const T by = k10 * px.x + k11 * px.y + k12;
+                const T th[3] = { sP[3 * (i0 + k)], sP[3 * (i0 + k) + 1], sP[3 * (i0 + k) + 2] };
+                if (PASS == 0) {
+                    mom.add(th, bx, by);
+                } else if (METHOD == PNPB200_METHOD_LM) {
+                    const T aa = th[0] * x[0] + th[1] * x[1] + th[2] * x[2];
+                    const T bb = th[0] * x[3] + th[1] * x[4] + th[2] * x[5];
+                    const T cc = th[0] * x[6] + th[1] * x[7] + th[2] * x[8];
+                    const T rx = bx - (x[11] * (aa - bx * cc) + x[9]);    // z - hx (:3750, :2679)
+                    const T ry = by - (x[11] * (bb - by * cc) + x[10]);
+                    acc0 = t_fma(rx, rx, t_fma(ry, ry, acc0));
+                } else {
+                    const T db = T(1) + (th[0] * f.phi3[0] + th[1] * f.phi3[1] + th[2] * f.phi3[2]);
+                    const T dx = th[0] * f.pxn[0] + th[1] * f.pxn[1] + th[2] * f.pxn[2] + f.pxn[3];
+                    const T dy = th[0] * f.pyn[0] + th[1] * f.pyn[1] + th[2] * f.pyn[2] + f.pyn[3];
+                    const T ex = bx * db - dx, ey = by * db - dy;
+                    acc0 = t_fma(ex, ex, acc0); acc1 = t_fma(ey, ey, acc1);
+                }
+            }
+            rs.done(c, lane);
+        }
+        if (ok) {
+            if (PASS == 0) {
+#pragma unroll
+                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.B + b] = mom.at(k);
+            } else if (a.res) {
+                if (METHOD == PNPB200_METHOD_LM) a.res[b] = t_sqrt(acc0);                 // :2681
+                else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
+            }
+        }
+        tile += gridDim.x;
+        if (tile < n_tiles) {
+            fence_proxy_async();
+            rs.begin_tile(tile, lane);
+        }
+    }
+}
+
 template <typename T, int METHOD, int PASS>
 __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ MomArgs<T> a)
 {
@@ -443,33 +530,42 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
 
 constexpr int kIterBlock = 128;
 
-template <typename T, int METHOD>
-__global__ void __launch_bounds__(kIterBlock) k_iterate(const __grid_constant__ MomArgs<T> a)
+// MINB = resident blocks per SM the register allocation is bounded for (2: 255 regs, 3: 168, 4: 128)
+template <typename T, int METHOD, int MINB>
+__global__ void __launch_bounds__(kIterBlock, MINB) k_iterate(const __grid_constant__ MomArgs<T> a)
 {
     __shared__ T sC[PNP_PATC];
+    __shared__ T sMom[PNP_NMOM * kIterBlock];             // [moment][thread]: conflict-free columns
     if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
-    __syncthreads();
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
-    Moments<T> mom;
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = b < a.B;
+    if (!ok) b = a.B - 1;
 #pragma unroll
-    for (int k = 0; k < PNP_NMOM; ++k) mom.at(k) = a.mom[(size_t)k * a.B + b];
+    for (int k = 0; k < PNP_NMOM; ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.B + b];
+    __syncthreads();
+    MomentsRef<T> mom;
+    mom.base = sMom + threadIdx.x;
+    mom.stride = kIterBlock;
     Result<T> out;
     T st[PNP_NTAIL];
     if (METHOD == PNPB200_METHOD_LM) {
         T xp[12];
-        solve_lm_from_moments<T>(mom, sC, a.prm, xp, out);
+        solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, a.prm, xp, out);
 #pragma unroll
         for (int k = 0; k < 12; ++k) st[k] = xp[k];
     } else {
+        Moments<T> mr;
+#pragma unroll
+        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMom[k * kIterBlock + threadIdx.x];
         F2Tail<T> f;
-        solve_f2_from_moments<T>(mom, sC, a.prm, f, out);
+        solve_f2_from_moments<T>(mr, sC, a.prm, f, out);
 #pragma unroll
         for (int k = 0; k < 3; ++k) st[k] = f.phi3[k];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { st[3 + k] = f.pxn[k]; st[7 + k] = f.pyn[k]; }
         st[11] = T(0);
     }
+    if (!ok) return;
 #pragma unroll
     for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.B + b] = st[k];
     if (a.R) {
@@ -490,6 +586,15 @@ __global__ void __launch_bounds__(kIterBlock) k_iterate(const __grid_constant__ 
     }
     if (a.iters) a.iters[b] = out.iters;
     if (a.best) a.best[b] = 0;
+}
+
+template <typename T, int METHOD>
+static void launch_iterate(const MomArgs<T>& m, int tune, cudaStream_t stream)
+{
+    const unsigned grid = (unsigned)((m.B + kIterBlock - 1) / kIterBlock);
+    if (tune == 2)      k_iterate<T, METHOD, 2><<<grid, kIterBlock, 0, stream>>>(m);
+    else if (tune == 4) k_iterate<T, METHOD, 4><<<grid, kIterBlock, 0, stream>>>(m);
+    else                k_iterate<T, METHOD, 3><<<grid, kIterBlock, 0, stream>>>(m);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -590,16 +695,30 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     k_pattern_constants<T><<<1, 32, 0, stream>>>(a.pattern, a.idx, a.n, m.patc);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     const int slot = a.profile ? g_prof.begin() : -1;
+    const StreamGeom sg = stream_geometry<T>(a.n_total);
+    const size_t chunk_smem = 2 * sg.buf_bytes + pat_bytes + 32;
+    const unsigned tile_grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
     g_prof.mark(slot, stream);
-    if (by_thread) {
+    if (by_thread && !a.idx && sg.use_stream && a.tune != 9) {
+        MomArgs<T> mc = m;
+        mc.row_pitch = sg.pitch;
+        mc.use_tma = sg.chunk;                                // RowStream: points per chunk
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
+        k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, chunk_smem, stream>>>(mc);
+        g_prof.mark(slot, stream);
+        launch_iterate<T, METHOD>(m, a.tune, stream);
+        g_prof.mark(slot, stream);
+        if (a.res) k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, chunk_smem, stream>>>(mc);
+        g_prof.mark(slot, stream);
+    } else if (by_thread) {
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
-        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
-        k_stream_thread<T, METHOD, 0><<<grid, 32, thread_smem, stream>>>(m);
+        k_stream_thread<T, METHOD, 0><<<tile_grid, 32, thread_smem, stream>>>(m);
         g_prof.mark(slot, stream);
-        k_iterate<T, METHOD><<<(unsigned)((a.B + kIterBlock - 1) / kIterBlock), kIterBlock, 0, stream>>>(m);
+        launch_iterate<T, METHOD>(m, a.tune, stream);
         g_prof.mark(slot, stream);
-        if (a.res) k_stream_thread<T, METHOD, 1><<<grid, 32, thread_smem, stream>>>(m);
+        if (a.res) k_stream_thread<T, METHOD, 1><<<tile_grid, 32, thread_smem, stream>>>(m);
         g_prof.mark(slot, stream);
     } else {
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
@@ -609,7 +728,7 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
         const unsigned grid = (unsigned)persistent_grid((a.B + 7) / 8, dp.sm_count, per_sm);
         k_stream_warp<T, METHOD, 0><<<grid, 256, warp_smem, stream>>>(m);
         g_prof.mark(slot, stream);
-        k_iterate<T, METHOD><<<(unsigned)((a.B + kIterBlock - 1) / kIterBlock), kIterBlock, 0, stream>>>(m);
+        launch_iterate<T, METHOD>(m, a.tune, stream);
         g_prof.mark(slot, stream);
         if (a.res) k_stream_warp<T, METHOD, 1><<<grid, 256, warp_smem, stream>>>(m);
         g_prof.mark(slot, stream);
@@ -683,6 +802,7 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     a.prm = make_prm<T>(prm);
     a.R = (T*)R; a.t = (T*)t; a.euler = (T*)euler; a.res = (T*)res; a.iters = iters; a.best = best;
     a.profile = (prm.flags & PNPB200_FLAG_PROFILE) ? 1 : 0;
+    a.tune = (prm.flags >> 8) & 0xff;                     // undocumented tuning knob (register budget of k_iterate)
     a.ws = prm.workspace; a.ws_bytes = (prm.workspace && prm.workspace_bytes > 0) ? (size_t)prm.workspace_bytes : 0;
     switch (method) {
     case PNPB200_METHOD_QEIF:      return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);

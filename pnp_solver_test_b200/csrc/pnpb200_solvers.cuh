@@ -225,36 +225,6 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, int n, int sub
 //       EKF2_reconstruct_R_t_m1 :3500-3540
 // state x = [u1(3), u2(3), u3(3), delta_1, delta_2, gamma]
 // -------------------------------------------------------------------------------------------
-// A += row row^T for a constraint row whose only non-zeros are va at block ba and vb at block bb
-template <typename T, int BA, int BB>
-PNP_DEV void add_outer2(T (&A)[78], T (&g)[12], const T (&va)[3], const T (&vb)[3], T e)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = a; b < 3; ++b) {
-            A[sidx<12>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<12>(BA + a, BA + b)]);
-            A[sidx<12>(BB + a, BB + b)] = t_fma(vb[a], vb[b], A[sidx<12>(BB + a, BB + b)]);
-        }
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-            A[sidx<12>(BA + a, BB + b)] = t_fma(va[a], vb[b], A[sidx<12>(BA + a, BB + b)]);
-        g[BA + a] = t_fma(va[a], e, g[BA + a]);
-        g[BB + a] = t_fma(vb[a], e, g[BB + a]);
-    }
-}
-template <typename T, int BA>
-PNP_DEV void add_outer1(T (&A)[78], T (&g)[12], const T (&va)[3], T e)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = a; b < 3; ++b)
-            A[sidx<12>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<12>(BA + a, BA + b)]);
-        g[BA + a] = t_fma(va[a], e, g[BA + a]);
-    }
-}
-
 // State-independent moments of one problem's correspondences against the pattern:
 //   Mx = sum bx th th^T, My = sum by th th^T, Mw = sum (bx^2+by^2) th th^T   (packed 3x3 each)
 //   mx = sum bx th, my = sum by th, mw = sum (bx^2+by^2) th, sx0 = sum bx, sy0 = sum by
@@ -297,12 +267,36 @@ struct Moments {
         group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my); group_sum_arr<LPP>(mw);
         sx0 = group_sum<LPP>(sx0); sy0 = group_sum<LPP>(sy0);
     }
+    PNP_DEV T gMx(int k) const { return Mx[k]; }
+    PNP_DEV T gMy(int k) const { return My[k]; }
+    PNP_DEV T gMw(int k) const { return Mw[k]; }
+    PNP_DEV T gmx(int k) const { return mx[k]; }
+    PNP_DEV T gmy(int k) const { return my[k]; }
+    PNP_DEV T gmw(int k) const { return mw[k]; }
+    PNP_DEV T gsx0() const { return sx0; }
+    PNP_DEV T gsy0() const { return sy0; }
     // flat order used for the [PNP_NMOM][B] workspace of the moment mapping
     PNP_DEV T& at(int k)
     {
         return k < 6 ? Mx[k] : k < 12 ? My[k - 6] : k < 18 ? Mw[k - 12] : k < 21 ? mx[k - 18] : k < 24 ? my[k - 21]
                : k < 27 ? mw[k - 24] : (k == 27 ? sx0 : sy0);
     }
+};
+
+// The same 29 moments parked in shared memory, one column per thread ([PNP_NMOM][stride], flat
+// order of Moments::at): k_iterate keeps them there so that the registers go to the 10x10 system.
+template <typename T>
+struct MomentsRef {
+    const T* base;
+    int stride;
+    PNP_DEV T gMx(int k) const { return base[k * stride]; }
+    PNP_DEV T gMy(int k) const { return base[(6 + k) * stride]; }
+    PNP_DEV T gMw(int k) const { return base[(12 + k) * stride]; }
+    PNP_DEV T gmx(int k) const { return base[(18 + k) * stride]; }
+    PNP_DEV T gmy(int k) const { return base[(21 + k) * stride]; }
+    PNP_DEV T gmw(int k) const { return base[(24 + k) * stride]; }
+    PNP_DEV T gsx0() const { return base[27 * stride]; }
+    PNP_DEV T gsy0() const { return base[28 * stride]; }
 };
 
 template <typename T, int LPP, typename Pts>
@@ -324,8 +318,8 @@ PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n,
 template <typename T>
 struct GammaCol { T sg1[3], sg2[3], sg3[3], s1, s2, sgg; };
 
-template <typename T>
-PNP_DEV void lm_gamma_column(const T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, GammaCol<T>& gc)
+template <typename T, typename M>
+PNP_DEV void lm_gamma_column(const T (&x)[12], const M& m, const T* __restrict__ sC, GammaCol<T>& gc)
 {
     gc.s1 = T(0); gc.s2 = T(0); gc.sgg = T(0);
 #pragma unroll
@@ -333,13 +327,14 @@ PNP_DEV void lm_gamma_column(const T (&x)[12], const Moments<T>& m, const T* __r
         T e1 = T(0), e2 = T(0), e3 = T(0);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            e1 = t_fma(sC[s3(k, j)], x[j], t_fma(-m.Mx[s3(k, j)], x[6 + j], e1));
-            e2 = t_fma(sC[s3(k, j)], x[3 + j], t_fma(-m.My[s3(k, j)], x[6 + j], e2));
-            e3 = t_fma(m.Mx[s3(k, j)], x[j], t_fma(m.My[s3(k, j)], x[3 + j], t_fma(-m.Mw[s3(k, j)], x[6 + j], e3)));
+            const T mxkj = m.gMx(s3(k, j)), mykj = m.gMy(s3(k, j));
+            e1 = t_fma(sC[s3(k, j)], x[j], t_fma(-mxkj, x[6 + j], e1));
+            e2 = t_fma(sC[s3(k, j)], x[3 + j], t_fma(-mykj, x[6 + j], e2));
+            e3 = t_fma(mxkj, x[j], t_fma(mykj, x[3 + j], t_fma(-m.gMw(s3(k, j)), x[6 + j], e3)));
         }
         gc.sg1[k] = e1; gc.sg2[k] = e2; gc.sg3[k] = e3;
-        gc.s1 = t_fma(sC[6 + k], x[k], t_fma(-m.mx[k], x[6 + k], gc.s1));
-        gc.s2 = t_fma(sC[6 + k], x[3 + k], t_fma(-m.my[k], x[6 + k], gc.s2));
+        gc.s1 = t_fma(sC[6 + k], x[k], t_fma(-m.gmx(k), x[6 + k], gc.s1));
+        gc.s2 = t_fma(sC[6 + k], x[3 + k], t_fma(-m.gmy(k), x[6 + k], gc.s2));
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) gc.sgg = t_fma(x[k], gc.sg1[k], t_fma(x[3 + k], gc.sg2[k], t_fma(-x[6 + k], gc.sg3[k], gc.sgg)));
@@ -352,57 +347,114 @@ struct LmRhs { T r1[3], r2[3], r3[3], q1, q2, qg; };
 // ... from the moments (moment mapping).  Unlike the gamma column these are differences of terms
 // ~|z|/|z - hx| larger than the result; the rounding this adds to the step is ~1e3 times smaller
 // than the effect of a 1e-13 relative input perturbation, which is what defines the parity subset.
-template <typename T>
-PNP_DEV void lm_rhs_from_moments(const T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, const GammaCol<T>& gc, LmRhs<T>& r)
+template <typename T, typename M>
+PNP_DEV void lm_rhs_from_moments(const T (&x)[12], const M& m, const T* __restrict__ sC, const GammaCol<T>& gc, LmRhs<T>& r)
 {
     const T gam = x[11], d1 = x[9], d2 = x[10];
     T qa = T(0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        r.r1[k] = m.mx[k] - gam * gc.sg1[k] - d1 * sC[6 + k];
-        r.r2[k] = m.my[k] - gam * gc.sg2[k] - d2 * sC[6 + k];
-        r.r3[k] = m.mw[k] - gam * gc.sg3[k] - d1 * m.mx[k] - d2 * m.my[k];
-        qa = t_fma(m.mx[k], x[k], t_fma(m.my[k], x[3 + k], t_fma(-m.mw[k], x[6 + k], qa)));
+        const T mxk = m.gmx(k), myk = m.gmy(k), mwk = m.gmw(k);
+        r.r1[k] = mxk - gam * gc.sg1[k] - d1 * sC[6 + k];
+        r.r2[k] = myk - gam * gc.sg2[k] - d2 * sC[6 + k];
+        r.r3[k] = mwk - gam * gc.sg3[k] - d1 * mxk - d2 * myk;
+        qa = t_fma(mxk, x[k], t_fma(myk, x[3 + k], t_fma(-mwk, x[6 + k], qa)));
     }
-    r.q1 = m.sx0 - gam * gc.s1 - sC[9] * d1;
-    r.q2 = m.sy0 - gam * gc.s2 - sC[9] * d2;
+    r.q1 = m.gsx0() - gam * gc.s1 - sC[9] * d1;
+    r.q2 = m.gsy0() - gam * gc.s2 - sC[9] * d2;
     r.qg = qa - gam * gc.sgg - d1 * gc.s1 - d2 * gc.s2;
+}
+
+// A += row row^T for a constraint row whose only non-zeros are va at block BA and vb at block BB
+template <typename T, int BA, int BB>
+PNP_DEV void add_outer2(T (&A)[55], T (&g)[10], const T (&va)[3], const T (&vb)[3], T e)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+            A[sidx<10>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<10>(BA + a, BA + b)]);
+            A[sidx<10>(BB + a, BB + b)] = t_fma(vb[a], vb[b], A[sidx<10>(BB + a, BB + b)]);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            A[sidx<10>(BA + a, BB + b)] = t_fma(va[a], vb[b], A[sidx<10>(BA + a, BB + b)]);
+        g[BA + a] = t_fma(va[a], e, g[BA + a]);
+        g[BB + a] = t_fma(vb[a], e, g[BB + a]);
+    }
+}
+template <typename T, int BA>
+PNP_DEV void add_outer1(T (&A)[55], T (&g)[10], const T (&va)[3], T e)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+            A[sidx<10>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<10>(BA + a, BA + b)]);
+        g[BA + a] = t_fma(va[a], e, g[BA + a]);
+    }
 }
 
 // One damped Gauss-Newton step: A = J^T J + lambda I (:2666-2667) from the moments and the gamma
 // column, g = J^T (z - hx) (:2684) from `r`, the nine constraint rows, x += pinv(A) g (:2675, :2702).
-template <typename T>
-PNP_DEV void lm_step(T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, const GammaCol<T>& gc, const LmRhs<T>& r,
+// delta_1 and delta_2 are eliminated first: their pivots are the constant n + lambda, they do not
+// couple to each other, and each couples to seven of the other unknowns only.  What is factorised
+// is the 10 x 10 Schur complement on (u1, u2, u3, gamma) -- the LDL^T of the 12 x 12 matrix with
+// the two delta columns ordered first, written out.
+template <typename T, typename M>
+PNP_DEV void lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaCol<T>& gc, const LmRhs<T>& r,
                      T lambda)
 {
-    constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
-    const T gam = x[GG];
-    T A[78], g[12];
+    constexpr int U1 = 0, U2 = 3, U3 = 6, GG = 9;       // order inside the reduced system
+    const T gam = x[11];
+    T A[55], g[10];
     const T gg2 = gam * gam;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
         for (int b = a; b < 3; ++b) {
             const T m0 = gg2 * sC[s3(a, b)];
-            A[sidx<12>(U1 + a, U1 + b)] = m0;
-            A[sidx<12>(U2 + a, U2 + b)] = m0;
-            A[sidx<12>(U3 + a, U3 + b)] = gg2 * m.Mw[s3(a, b)];
+            A[sidx<10>(U1 + a, U1 + b)] = m0;
+            A[sidx<10>(U2 + a, U2 + b)] = m0;
+            A[sidx<10>(U3 + a, U3 + b)] = gg2 * m.gMw(s3(a, b));
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            A[sidx<12>(U1 + a, U2 + b)] = T(0);
-            A[sidx<12>(U1 + a, U3 + b)] = -gg2 * m.Mx[s3(a, b)];
-            A[sidx<12>(U2 + a, U3 + b)] = -gg2 * m.My[s3(a, b)];
+            A[sidx<10>(U1 + a, U2 + b)] = T(0);
+            A[sidx<10>(U1 + a, U3 + b)] = -gg2 * m.gMx(s3(a, b));
+            A[sidx<10>(U2 + a, U3 + b)] = -gg2 * m.gMy(s3(a, b));
         }
-        A[sidx<12>(U1 + a, D1)] = gam * sC[6 + a]; A[sidx<12>(U1 + a, D2)] = T(0); A[sidx<12>(U1 + a, GG)] = gam * gc.sg1[a];
-        A[sidx<12>(U2 + a, D1)] = T(0); A[sidx<12>(U2 + a, D2)] = gam * sC[6 + a]; A[sidx<12>(U2 + a, GG)] = gam * gc.sg2[a];
-        A[sidx<12>(U3 + a, D1)] = -gam * m.mx[a]; A[sidx<12>(U3 + a, D2)] = -gam * m.my[a]; A[sidx<12>(U3 + a, GG)] = -gam * gc.sg3[a];
+        A[sidx<10>(U1 + a, GG)] = gam * gc.sg1[a];
+        A[sidx<10>(U2 + a, GG)] = gam * gc.sg2[a];
+        A[sidx<10>(U3 + a, GG)] = -gam * gc.sg3[a];
         g[U1 + a] = gam * r.r1[a]; g[U2 + a] = gam * r.r2[a]; g[U3 + a] = -gam * r.r3[a];
     }
-    A[sidx<12>(D1, D1)] = sC[9]; A[sidx<12>(D1, D2)] = T(0); A[sidx<12>(D1, GG)] = gc.s1;
-    A[sidx<12>(D2, D2)] = sC[9]; A[sidx<12>(D2, GG)] = gc.s2;
-    A[sidx<12>(GG, GG)] = gc.sgg;
-    g[D1] = r.q1; g[D2] = r.q2; g[GG] = r.qg;
+    A[sidx<10>(GG, GG)] = gc.sgg;
+    g[GG] = r.qg;
+    // ---- eliminate delta_1 (column [gam m0; 0; -gam mx; s1]) and delta_2 ([0; gam m0; -gam my; s2])
+    const T ip = t_rcp<T>(sC[9] + lambda);
+    T c1[7], c2[7];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        c1[a] = gam * sC[6 + a]; c1[3 + a] = -gam * m.gmx(a);
+        c2[a] = c1[a];           c2[3 + a] = -gam * m.gmy(a);
+    }
+    c1[6] = gc.s1; c2[6] = gc.s2;
+    {
+        constexpr int i1[7] = { 0, 1, 2, 6, 7, 8, 9 }, i2[7] = { 3, 4, 5, 6, 7, 8, 9 };
+        const T f1 = r.q1 * ip, f2 = r.q2 * ip;
+#pragma unroll
+        for (int p = 0; p < 7; ++p) {
+            const T b1 = c1[p] * ip, b2 = c2[p] * ip;
+#pragma unroll
+            for (int q = p; q < 7; ++q) {
+                A[sidx<10>(i1[p], i1[q])] = t_fma(-b1, c1[q], A[sidx<10>(i1[p], i1[q])]);
+                A[sidx<10>(i2[p], i2[q])] = t_fma(-b2, c2[q], A[sidx<10>(i2[p], i2[q])]);
+            }
+            g[i1[p]] = t_fma(-c1[p], f1, g[i1[p]]);
+            g[i2[p]] = t_fma(-c2[p], f2, g[i2[p]]);
+        }
+    }
     // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones)
     {
         const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
@@ -420,7 +472,7 @@ PNP_DEV void lm_step(T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, 
         add_outer2<T, U1, U3>(A, g, u1, nu3, T(0) - (u11 - u33)); // rows use u, not 2u (:3808)
         add_outer2<T, U2, U3>(A, g, u2, nu3, T(0) - (u22 - u33));
         add_outer2<T, U1, U2>(A, g, u1, nu2, T(0) - (u11 - u22));
-        const T h1 = T(1) / (T(2) * n1), h2 = T(1) / (T(2) * n2), h3 = T(1) / (T(2) * n3);
+        const T h1 = t_rcp<T>(T(2) * n1), h2 = t_rcp<T>(T(2) * n2), h3 = t_rcp<T>(T(2) * n3);
         const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
         const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
         const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
@@ -429,11 +481,19 @@ PNP_DEV void lm_step(T (&x)[12], const Moments<T>& m, const T* __restrict__ sC, 
         add_outer1<T, U3>(A, g, j3, T(1) - n3);
     }
 #pragma unroll
-    for (int i = 0; i < 12; ++i) A[sidx<12>(i, i)] += lambda;
-    ldlt_factor<T, 12>(A);
-    ldlt_solve<T, 12>(A, g);
+    for (int i = 0; i < 10; ++i) A[sidx<10>(i, i)] += lambda;
+    ldlt_factor<T, 10>(A);
+    ldlt_solve<T, 10>(A, g);
+    // ---- back-substitute the two deltas: d_k = (rhs_k - column_k . dx) / (n + lambda)
+    T e1 = r.q1, e2 = r.q2;
+    {
+        constexpr int i1[7] = { 0, 1, 2, 6, 7, 8, 9 }, i2[7] = { 3, 4, 5, 6, 7, 8, 9 };
 #pragma unroll
-    for (int i = 0; i < 12; ++i) x[i] += g[i];
+        for (int p = 0; p < 7; ++p) { e1 = t_fma(-c1[p], g[i1[p]], e1); e2 = t_fma(-c2[p], g[i2[p]], e2); }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] += g[i];
+    x[9] += e1 * ip; x[10] += e2 * ip; x[11] += g[GG];
 }
 
 // ||z - hx|| over the 2n measurement rows at state x, point by point (:2679-2681)
@@ -507,8 +567,8 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
         r.q1 = group_sum<LPP>(r.q1); r.q2 = group_sum<LPP>(r.q2); r.qg = group_sum<LPP>(r.qg); rr = group_sum<LPP>(rr);
         res = t_sqrt(rr);                                 // res_norm of the state BEFORE the update (:2681)
         GammaCol<T> gc;
-        lm_gamma_column<T>(x, mom, sC, gc);
-        lm_step<T>(x, mom, sC, gc, r, prm.lm_lambda);
+        lm_gamma_column<T, Moments<T> >(x, mom, sC, gc);
+        lm_step<T, Moments<T> >(x, mom, sC, gc, r, prm.lm_lambda);
     }
     lm_reconstruct<T>(x, out);
     out.res = res;
@@ -517,8 +577,8 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
 
 // Moment form (moment mapping): every iteration is O(1) in the moments; x_prev receives the state
 // before the last update, at which the caller evaluates res_norm point by point.
-template <typename T>
-PNP_DEV void solve_lm_from_moments(const Moments<T>& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, T (&x_prev)[12],
+template <typename T, typename M>
+PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, T (&x_prev)[12],
                                    Result<T>& out)
 {
     T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2619-2624
@@ -529,9 +589,9 @@ PNP_DEV void solve_lm_from_moments(const Moments<T>& mom, const T* __restrict__ 
         for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
         GammaCol<T> gc;
         LmRhs<T> r;
-        lm_gamma_column<T>(x, mom, sC, gc);
-        lm_rhs_from_moments<T>(x, mom, sC, gc, r);
-        lm_step<T>(x, mom, sC, gc, r, prm.lm_lambda);
+        lm_gamma_column<T, M>(x, mom, sC, gc);
+        lm_rhs_from_moments<T, M>(x, mom, sC, gc, r);
+        lm_step<T, M>(x, mom, sC, gc, r, prm.lm_lambda);
     }
     lm_reconstruct<T>(x, out);
     out.res = T(0);
@@ -541,7 +601,7 @@ PNP_DEV void solve_lm_from_moments(const Moments<T>& mom, const T* __restrict__ 
 // -------------------------------------------------------------------------------------------
 // Linear stage, formulation 2 -- solve_pnp_formulation_2_single_pattern :693-953,
 // helpers :3274-3375.  D^+ B = G (D^T B) with the pattern-constant G = (D^T D)^-1, so the
-// per-problem work is the 20 moments of (bx, by) against [theta theta^T, theta, 1].
+// per-problem work is the moments of (bx, by) against [theta theta^T, theta, 1].
 // -------------------------------------------------------------------------------------------
 template <typename T>
 PNP_DEV void g4_apply(const T* __restrict__ G, const T (&v)[4], T (&o)[4])

@@ -163,4 +163,87 @@ inline RowGeom row_geometry(int n_total)
     return g;
 }
 
+// ------------------------------------------------------------------------------------------
+// Row stream: the same 32 problems per warp, but for kernels that read every pixel ONCE
+// (moments, residual, error report).  Rows are streamed in chunks of `chunk` points through two
+// small shared-memory buffers (lane l bulk-copies its own row chunk; one mbarrier per buffer),
+// so a warp holds ~17 KB instead of a whole 35 KB tile and twice as many warps fit per SM, and
+// the copy of chunk c+1 overlaps the arithmetic on chunk c.
+// ------------------------------------------------------------------------------------------
+struct StreamGeom { int chunk, pitch, use_stream; size_t buf_bytes; };
+
+template <typename T>
+inline StreamGeom stream_geometry(int n_total)
+{
+    StreamGeom g;
+    const int per16 = 16 / (2 * (int)sizeof(T));             // points per 16 bytes: 1 (double), 2 (float)
+    g.use_stream = (n_total % per16 == 0) ? 1 : 0;
+    int c = 17 * per16;                                       // 272-byte chunks
+    if (c > n_total) c = n_total;
+    g.chunk = c;
+    size_t units = ((size_t)c * 2 * sizeof(T) + 15) / 16;
+    if ((units & 1) == 0) ++units;                            // odd multiple of 16 B: conflict-free lanes
+    g.pitch = (int)(units * 16 / sizeof(T));
+    g.buf_bytes = (size_t)kTileProblems * g.pitch * sizeof(T);
+    return g;
+}
+
+template <typename T>
+struct RowStream {
+    typedef typename Vec2<T>::type V2;
+    T* buf0;            // two buffers of kTileProblems * pitch elements
+    uint64_t* bar;      // two mbarriers
+    const T* uv;
+    long long B, b0;
+    int n_total, chunk, pitch, n_chunks, valid;
+    uint32_t phase;     // bit s = parity to wait for on buffer s
+
+    PNP_DEV T* buf(int s) const { return buf0 + (size_t)s * kTileProblems * pitch; }
+
+    PNP_DEV void init(T* smem, uint64_t* bars, const T* uv_, long long B_, int n_total_, int chunk_, int pitch_, int lane)
+    {
+        buf0 = smem;
+        bar = bars; uv = uv_; B = B_; n_total = n_total_; chunk = chunk_; pitch = pitch_;
+        n_chunks = (n_total + chunk - 1) / chunk;
+        phase = 0;
+        if (lane == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+        __syncwarp();
+    }
+    PNP_DEV int count(int c) const { const int rem = n_total - c * chunk; return rem < chunk ? rem : chunk; }
+    PNP_DEV void issue(int c, int lane)
+    {
+        const int s = c & 1;
+        const uint32_t bytes = (uint32_t)count(c) * 2u * (uint32_t)sizeof(T);
+        if (lane == 0) mbar_expect_tx(bar + s, bytes * (uint32_t)valid);
+        __syncwarp();
+        if (lane < valid)
+            bulk_copy_g2s(buf(s) + (size_t)lane * pitch, uv + ((size_t)(b0 + lane) * n_total + (size_t)c * chunk) * 2, bytes, bar + s);
+    }
+    PNP_DEV void begin_tile(long long tile, int lane)
+    {
+        b0 = tile * kTileProblems;
+        valid = (int)((B - b0 < kTileProblems) ? (B - b0) : kTileProblems);
+        issue(0, lane);
+        if (n_chunks > 1) issue(1, lane);
+    }
+    // this lane's row chunk c (spare lanes of a ragged tile shadow the last valid problem)
+    PNP_DEV const V2* wait(int c, int lane)
+    {
+        const int s = c & 1;
+        mbar_wait(bar + s, (phase >> s) & 1u);
+        phase ^= (1u << s);
+        const int my = (lane < valid) ? lane : (valid - 1);
+        return reinterpret_cast<const V2*>(buf(s) + (size_t)my * pitch);
+    }
+    // chunk c has been consumed by every lane: its buffer may be refilled with chunk c + 2
+    PNP_DEV void done(int c, int lane)
+    {
+        __syncwarp();
+        if (c + 2 < n_chunks) {
+            fence_proxy_async();
+            issue(c + 2, lane);
+        }
+    }
+};
+
 }  // namespace pnpb200
