@@ -102,11 +102,15 @@ static thread_local ProfileRing g_prof;
 // ------------------------------------------------------------------------------------------
 // kernel arguments
 // ------------------------------------------------------------------------------------------
+#define PNP_MAX_INLINE_IDX 96
+
 template <typename T>
 struct SolveArgs {
     const T* uv;            // [B, n_total, 2]
     const T* pattern;       // [P, n_total, 3]
-    const int32_t* idx;     // [n] device, or nullptr
+    const int32_t* idx;     // [n] device (large selections), or nullptr
+    int idx_mode;           // 0: all landmarks, 1: idx_inline, 2: idx (device)
+    int32_t idx_inline[PNP_MAX_INLINE_IDX];
     long long B;
     int n_total, n, n_patterns;
     int row_pitch;          // thread mapping: shared-memory row pitch in elements of T
@@ -219,6 +223,13 @@ PNP_DEV void write_result(const SolveArgs<T>& a, long long b, const Result<T>& r
     if (a.best) a.best[b] = best_p;
 }
 
+// the landmark selection: small ones travel inside the kernel arguments (no allocation, no copy)
+template <typename A>
+PNP_DEV const int32_t* selection_of(const A& a)
+{
+    return a.idx_mode == 1 ? a.idx_inline : (a.idx_mode == 2 ? a.idx : nullptr);
+}
+
 // pattern (restricted to the selected landmarks, in selection order) and the selection -> shared memory
 template <typename T>
 PNP_DEV void load_pattern(const T* __restrict__ pattern, const int32_t* __restrict__ idx, int n_total, int n, int n_patterns,
@@ -249,14 +260,15 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
     T* sC = sP + (size_t)a.n_patterns * a.n * 3;
     int32_t* sIdx = reinterpret_cast<int32_t*>(sC + a.n_patterns * PNP_PATC);
     const int lane = threadIdx.x;
+    const int32_t* sel = selection_of(a);
     RowTile<T> tile_buf;
-    tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (a.idx ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
+    tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (sel ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
 
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     long long tile = blockIdx.x;
     // kick off the first tile's copies before touching the pattern so the two overlap
     int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
-    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, a.n_patterns, sP, sIdx, lane, 32);
+    load_pattern<T>(a.pattern, sel, a.n_total, a.n, a.n_patterns, sP, sIdx, lane, 32);
     if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
         for (int p = 0; p < a.n_patterns; ++p) pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncwarp();
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
         const long long b0 = tile * kTileProblems;
         PtsRow<T> pts;
         pts.row = tile_buf.acquire(lane, valid);
-        pts.idx = a.idx ? sIdx : nullptr;
+        pts.idx = sel ? sIdx : nullptr;
         Result<T> best;
         int best_p;
         solve_all_patterns<T, METHOD, 1, PtsRow<T> >(pts, sP, sC, a.n, a.n_patterns, 0, a.prm, best, best_p);
@@ -292,6 +304,8 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
 template <typename T>
 struct MomArgs {
     const T* uv; const T* pattern; const int32_t* idx;
+    int idx_mode;
+    int32_t idx_inline[PNP_MAX_INLINE_IDX];
     long long B;
     int n_total, n, row_pitch, use_tma;
     double kinv[6];
@@ -302,10 +316,14 @@ struct MomArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(32) k_pattern_constants(const T* __restrict__ pattern, const int32_t* __restrict__ idx, int n, T* patc)
+__global__ void __launch_bounds__(32) k_pattern_constants(const __grid_constant__ MomArgs<T> a)
 {
     // one warp; reads the (selected) pattern straight from global memory
     const int lane = threadIdx.x;
+    const T* __restrict__ pattern = a.pattern;
+    const int32_t* idx = selection_of(a);
+    const int n = a.n;
+    T* patc = a.patc;
     double acc[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) acc[e] = 0.0;
@@ -348,12 +366,13 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
     T* sP = sRows + (size_t)kTileProblems * a.row_pitch;
     int32_t* sIdx = reinterpret_cast<int32_t*>(sP + (size_t)a.n * 3);
     const int lane = threadIdx.x;
+    const int32_t* sel = selection_of(a);
     RowTile<T> tile_buf;
-    tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (a.idx ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
+    tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (sel ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     long long tile = blockIdx.x;
     int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
-    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, 1, sP, sIdx, lane, 32);
+    load_pattern<T>(a.pattern, sel, a.n_total, a.n, 1, sP, sIdx, lane, 32);
     while (tile < n_tiles) {
         const long long b0 = tile * kTileProblems;
         long long b = b0 + lane;
@@ -366,7 +385,7 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
         }
         PtsRow<T> pts;
         pts.row = tile_buf.acquire(lane, valid);
-        pts.idx = a.idx ? sIdx : nullptr;
+        pts.idx = sel ? sIdx : nullptr;
         if (PASS == 0) {
             Moments<T> mom;
             accumulate_moments<T, 1, PtsRow<T> >(pts, sP, a.n, 0, mom);
@@ -493,9 +512,10 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
     T* sP = reinterpret_cast<T*>(smem_raw);
     int32_t* sIdx = reinterpret_cast<int32_t*>(sP + (size_t)a.n * 3);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, 1, sP, sIdx, threadIdx.x, blockDim.x);
+    const int32_t* sel = selection_of(a);
+    load_pattern<T>(a.pattern, sel, a.n_total, a.n, 1, sP, sIdx, threadIdx.x, blockDim.x);
     PtsGlobal<T> pts;
-    pts.idx = a.idx ? sIdx : nullptr;
+    pts.idx = sel ? sIdx : nullptr;
     pts.k00 = (T)a.kinv[0]; pts.k01 = (T)a.kinv[1]; pts.k02 = (T)a.kinv[2];
     pts.k10 = (T)a.kinv[3]; pts.k11 = (T)a.kinv[4]; pts.k12 = (T)a.kinv[5];
     for (long long b = (long long)blockIdx.x * nwarps + warp; b < a.B; b += (long long)gridDim.x * nwarps) {
@@ -611,14 +631,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_solve_warp(const __grid
     int32_t* sIdx = reinterpret_cast<int32_t*>(sC + a.n_patterns * PNP_PATC);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    load_pattern<T>(a.pattern, a.idx, a.n_total, a.n, a.n_patterns, sP, sIdx, threadIdx.x, blockDim.x);
+    const int32_t* sel = selection_of(a);
+    load_pattern<T>(a.pattern, sel, a.n_total, a.n, a.n_patterns, sP, sIdx, threadIdx.x, blockDim.x);
     if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
         for (int p = warp; p < a.n_patterns; p += kWarpsPerBlock)
             pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncthreads();
     }
     PtsGlobal<T> pts;
-    pts.idx = a.idx ? sIdx : nullptr;
+    pts.idx = sel ? sIdx : nullptr;
     pts.k00 = (T)a.kinv[0]; pts.k01 = (T)a.kinv[1]; pts.k02 = (T)a.kinv[2];
     pts.k10 = (T)a.kinv[3]; pts.k11 = (T)a.kinv[4]; pts.k12 = (T)a.kinv[5];
     for (long long b = (long long)blockIdx.x * kWarpsPerBlock + warp; b < a.B; b += (long long)gridDim.x * kWarpsPerBlock) {
@@ -672,7 +693,7 @@ template <typename T, int METHOD>
 static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStream_t stream)
 {
     const RowGeom g = row_geometry<T>(a.n_total);
-    const size_t idx_bytes = a.idx ? (size_t)a.n * sizeof(int32_t) : 0;
+    const size_t idx_bytes = a.idx_mode ? (size_t)a.n * sizeof(int32_t) : 0;
     const size_t pat_bytes = (size_t)a.n * 3 * sizeof(T);
     const size_t thread_smem = g.tile_bytes + pat_bytes + idx_bytes + 16;
     const size_t warp_smem = pat_bytes + idx_bytes;
@@ -685,21 +706,23 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     if (own_ws) PNP_CUDA_OK(cudaMallocAsync((void**)&ws, ws_elems * sizeof(T), stream));
     else ws = (T*)a.ws;
     MomArgs<T> m;
-    m.uv = a.uv; m.pattern = a.pattern; m.idx = a.idx; m.B = a.B; m.n_total = a.n_total; m.n = a.n;
+    m.uv = a.uv; m.pattern = a.pattern; m.idx = a.idx; m.idx_mode = a.idx_mode;
+    for (int e = 0; e < PNP_MAX_INLINE_IDX; ++e) m.idx_inline[e] = a.idx_inline[e];
+    m.B = a.B; m.n_total = a.n_total; m.n = a.n;
     m.row_pitch = g.row_pitch; m.use_tma = g.use_tma;
     for (int e = 0; e < 6; ++e) m.kinv[e] = a.kinv[e];
     m.prm = a.prm;
     m.mom = ws; m.tail = ws + (size_t)PNP_NMOM * a.B; m.patc = m.tail + (size_t)PNP_NTAIL * a.B;
     m.R = a.R; m.t = a.t; m.euler = a.euler; m.res = a.res; m.iters = a.iters; m.best = a.best;
 
-    k_pattern_constants<T><<<1, 32, 0, stream>>>(a.pattern, a.idx, a.n, m.patc);
+    k_pattern_constants<T><<<1, 32, 0, stream>>>(m);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     const int slot = a.profile ? g_prof.begin() : -1;
     const StreamGeom sg = stream_geometry<T>(a.n_total);
     const size_t chunk_smem = 2 * sg.buf_bytes + pat_bytes + 32;
     const unsigned tile_grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
     g_prof.mark(slot, stream);
-    if (by_thread && !a.idx && sg.use_stream && a.tune != 9) {
+    if (by_thread && !a.idx_mode && sg.use_stream && a.tune != 9) {
         MomArgs<T> mc = m;
         mc.row_pitch = sg.pitch;
         mc.use_tma = sg.chunk;                                // RowStream: points per chunk
@@ -747,7 +770,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2);
     const RowGeom g = row_geometry<T>(a.n_total);
     const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
-    const size_t idx_bytes = a.idx ? (size_t)a.n * sizeof(int32_t) : 0;
+    const size_t idx_bytes = a.idx_mode ? (size_t)a.n * sizeof(int32_t) : 0;
     const size_t thread_smem = g.tile_bytes + pat_bytes + idx_bytes + 16;
     const size_t warp_smem = pat_bytes + idx_bytes;
     if (mapping == PNPB200_MAP_AUTO) {
@@ -789,11 +812,13 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
 
 template <typename T>
 static int solve_typed(int method, long long B, int n_total, int n, const void* uv, const void* pattern,
-                       int n_patterns, const int32_t* idx_dev, const double* K, const pnpb200_params& prm,
+                       int n_patterns, const int32_t* idx_host, const int32_t* idx_dev, const double* K, const pnpb200_params& prm,
                        void* R, void* t, void* euler, void* res, int32_t* iters, int32_t* best, cudaStream_t stream)
 {
     SolveArgs<T> a;
     a.uv = (const T*)uv; a.pattern = (const T*)pattern; a.idx = idx_dev;
+    a.idx_mode = idx_host ? (idx_dev ? 2 : 1) : 0;
+    for (int e = 0; e < PNP_MAX_INLINE_IDX; ++e) a.idx_inline[e] = (idx_host && !idx_dev && e < n) ? idx_host[e] : 0;
     a.B = B; a.n_total = n_total; a.n = n; a.n_patterns = n_patterns;
     a.row_pitch = 0; a.use_tma = 0;
     double Kinv[9];
@@ -894,15 +919,17 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, co
     if (point_index) {
         for (int i = 0; i < n; ++i)
             if (point_index[i] < 0 || point_index[i] >= n_total) return PNPB200_EINVAL;
-        PNP_CUDA_OK(cudaMallocAsync((void**)&idx_dev, sizeof(int32_t) * (size_t)n, st));
-        PNP_CUDA_OK(cudaMemcpyAsync(idx_dev, point_index, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (n > PNP_MAX_INLINE_IDX) {   // large selections go through device memory; small ones ride in the kernel arguments
+            PNP_CUDA_OK(cudaMallocAsync((void**)&idx_dev, sizeof(int32_t) * (size_t)n, st));
+            PNP_CUDA_OK(cudaMemcpyAsync(idx_dev, point_index, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
     }
     int rc;
     if (dtype == PNPB200_DTYPE_F64)
-        rc = solve_typed<double>(method, B, n_total, n, uv, pattern, n_patterns, idx_dev, K, prm, R, t, euler_deg,
+        rc = solve_typed<double>(method, B, n_total, n, uv, pattern, n_patterns, point_index, idx_dev, K, prm, R, t, euler_deg,
                                  res_norm, iters, best_pattern, st);
     else
-        rc = solve_typed<float>(method, B, n_total, n, uv, pattern, n_patterns, idx_dev, K, prm, R, t, euler_deg,
+        rc = solve_typed<float>(method, B, n_total, n, uv, pattern, n_patterns, point_index, idx_dev, K, prm, R, t, euler_deg,
                                 res_norm, iters, best_pattern, st);
     if (idx_dev) cudaFreeAsync(idx_dev, st);
     return rc;

@@ -287,7 +287,7 @@ struct Moments {
 // order of Moments::at): k_iterate keeps them there so that the registers go to the 10x10 system.
 template <typename T>
 struct MomentsRef {
-    const T* base;
+    const volatile T* base;   // volatile: re-read per use instead of being hoisted into (spilled) registers
     int stride;
     PNP_DEV T gMx(int k) const { return base[k * stride]; }
     PNP_DEV T gMy(int k) const { return base[(6 + k) * stride]; }
@@ -303,6 +303,7 @@ template <typename T, int LPP, typename Pts>
 PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n, int sub, Moments<T>& mom)
 {
     mom.zero();
+#pragma unroll 4
     for (int i = sub; i < n; i += LPP) {
         const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
         T bx, by;
@@ -502,6 +503,7 @@ PNP_DEV T lm_residual_direct(const Pts& pts, const T* __restrict__ sP, int n, in
 {
     const T gam = x[11], d1 = x[9], d2 = x[10];
     T rr = T(0);
+#pragma unroll 4
     for (int i = sub; i < n; i += LPP) {
         const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
         T bx, by;
@@ -623,6 +625,7 @@ template <typename T, int LPP, typename Pts>
 PNP_DEV T f2_residual_direct(const Pts& pts, const T* __restrict__ sP, int n, int sub, const F2Tail<T>& f)
 {
     T rx2 = T(0), ry2 = T(0);
+#pragma unroll 4
     for (int i = sub; i < n; i += LPP) {
         const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
         T bx, by;

@@ -93,6 +93,17 @@ def test_landmark_subset_selection_matches_gather():
         compare_solutions(a, ref)
 
 
+def test_large_selection_goes_through_device_memory():
+    """More than 96 selected landmarks: the selection no longer rides in the kernel arguments."""
+    P, K, w = _workload(1024, 64, seed=17)
+    idx = np.arange(5, 1024, 7, dtype=np.int32)[:130]
+    for method, mappings in (("qeif", (MAP_WARP,)), ("linear_f2", (MAP_WARP, MAP_MOMENT)), ("linear_f1", (MAP_WARP,))):
+        ref = orc.solve_batch(method, w["uv"][:, idx], P[idx], K)
+        for mapping in mappings:
+            out = cuda_solve(method, w["uv"], P, K, mapping=mapping, point_index=idx)
+            compare_solutions(out, ref)
+
+
 @pytest.mark.parametrize("B", [1, 31, 32, 33, 1000])
 def test_ragged_batch_sizes(B):
     P, K, w = _workload(15, 1000, seed=11)
