@@ -200,16 +200,17 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
  *                  (gt or gt[q] may be NULL: statistics of the value itself);  arrays of nq [host]
  *   class_id: [B] int32 device or NULL (every problem in class 0); n_class <= 64 classes
  *   pass 1 -> sums1 [nq, n_class+1, 4] = n, sum(est/gt), sum(e), 0                  (SUM-reducible)
- *   pass 2 (given mean [nq, n_class+1] device) -> sums2 [nq, n_class+1, 4]
- *            = sum((e-m)^2), sum|e|, sum|e-m|, max|e-m|     (first three SUM-, last MAX-reducible)
+ *   pass 2, given the (all-reduced) sums1 from which it derives the means itself
+ *          -> sums2 [nq, n_class+1, 4] = sum((e-m)^2), sum|e|, sum|e-m|, 0           (SUM-reducible)
+ *             max2  [nq, n_class+1]    = max|e-m|                                    (MAX-reducible)
  */
 int pnpb200_stats_pass1(int64_t B, int nq, const double* const* est, const int64_t* est_stride,
                         const double* const* gt, const int64_t* gt_stride,
                         const int32_t* class_id, int n_class, double* sums1, void* stream);
 int pnpb200_stats_pass2(int64_t B, int nq, const double* const* est, const int64_t* est_stride,
                         const double* const* gt, const int64_t* gt_stride,
-                        const int32_t* class_id, int n_class, const double* mean, double* sums2,
-                        void* stream);
+                        const int32_t* class_id, int n_class, const double* sums1, double* sums2,
+                        double* max2, void* stream);
 
 /*
  * Ground-truth classification, np.digitize(value, bins) (TEST_TOOLBOX.classify_drpy,

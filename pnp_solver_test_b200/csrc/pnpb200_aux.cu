@@ -467,14 +467,22 @@ PNP_DEV void atomic_max_double(double* addr, double v)   // v >= 0: the bit patt
 
 template <int PASS>
 __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
-                                                     const double* __restrict__ mean, double* out)
+                                                     const double* __restrict__ sums1, double* out, double* out_max)
 {
     extern __shared__ double sh[];                        // [warp][n_class][nq][4]
     const int nq = in.nq, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rows = n_class + 1;                         // + the "all" row
     const int per_warp = n_class * nq * 4;
+    __shared__ double sMean[kStatMaxQ * (kStatMaxClass + 1)];
     for (int e = threadIdx.x; e < kStatWarps * per_warp; e += blockDim.x) sh[e] = 0.0;
+    if (PASS == 2) {                                      // mean = sum e / n from the (all-reduced) pass-1 sums
+        for (int e = threadIdx.x; e < nq * rows; e += blockDim.x) {
+            const double cnt = sums1[e * 4];
+            sMean[e] = cnt > 0.0 ? sums1[e * 4 + 2] / cnt : 0.0;
+        }
+    }
     __syncthreads();
+    const double* mean = sMean;
     double* mine = sh + warp * per_warp;
     double all[kStatMaxQ][4];
 #pragma unroll
@@ -545,9 +553,8 @@ __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, co
         const bool is_max = (PASS == 2) && ((e & 3) == 3);
         for (int w = 0; w < kStatWarps; ++w) acc = is_max ? fmax(acc, sh[w * per_warp + e]) : acc + sh[w * per_warp + e];
         const int c = e / (nq * 4), r = e - c * nq * 4, q = r >> 2, k = r & 3;
-        double* dst = out + ((size_t)q * rows + c) * 4 + k;
-        if (is_max) atomic_max_double(dst, acc);
-        else if (acc != 0.0) atomicAdd(dst, acc);
+        if (is_max) atomic_max_double(out_max + (size_t)q * rows + c, acc);
+        else if (acc != 0.0) atomicAdd(out + ((size_t)q * rows + c) * 4 + k, acc);
     }
     // "all" row: warp shuffle reduction, then one RED per warp
 #pragma unroll
@@ -563,9 +570,8 @@ __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, co
                     a = is_max ? fmax(a, o) : a + o;
                 }
                 if (lane == 0) {
-                    double* dst = out + ((size_t)q * rows + n_class) * 4 + k;
-                    if (is_max) atomic_max_double(dst, a);
-                    else if (a != 0.0) atomicAdd(dst, a);
+                    if (is_max) atomic_max_double(out_max + (size_t)q * rows + n_class, a);
+                    else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + n_class) * 4 + k, a);
                 }
             }
         }
@@ -744,11 +750,11 @@ static int stats_grid(int64_t B)
 
 template <int PASS>
 static int stats_launch(int64_t B, int nq, const double* const* est, const int64_t* es, const double* const* gt,
-                        const int64_t* gs, const int32_t* class_id, int n_class, const double* mean, double* sums,
-                        cudaStream_t st)
+                        const int64_t* gs, const int32_t* class_id, int n_class, const double* sums1, double* sums,
+                        double* sums_max, cudaStream_t st)
 {
     if (B < 0 || nq < 1 || nq > kStatMaxQ || !est || !es || !sums || n_class < 1 || n_class > kStatMaxClass) return PNPB200_EINVAL;
-    if (PASS == 2 && !mean) return PNPB200_EINVAL;
+    if (PASS == 2 && (!sums1 || !sums_max)) return PNPB200_EINVAL;
     StatIn in;
     in.nq = nq;
     for (int q = 0; q < kStatMaxQ; ++q) {
@@ -759,10 +765,11 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
         if (q < nq && !in.est[q]) return PNPB200_EINVAL;
     }
     PNP_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * (size_t)nq * (n_class + 1), st));
+    if (PASS == 2) PNP_CUDA_OK(cudaMemsetAsync(sums_max, 0, sizeof(double) * (size_t)nq * (n_class + 1), st));
     if (B == 0) return PNPB200_OK;
     const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
     if (smem > 48 * 1024) PNP_CUDA_OK(cudaFuncSetAttribute(k_stats<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, mean, sums);
+    k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -772,14 +779,14 @@ extern "C" {
 int pnpb200_stats_pass1(int64_t B, int nq, const double* const* est, const int64_t* est_stride, const double* const* gt,
                         const int64_t* gt_stride, const int32_t* class_id, int n_class, double* sums1, void* stream)
 {
-    return stats_launch<1>(B, nq, est, est_stride, gt, gt_stride, class_id, n_class, nullptr, sums1, (cudaStream_t)stream);
+    return stats_launch<1>(B, nq, est, est_stride, gt, gt_stride, class_id, n_class, nullptr, sums1, nullptr, (cudaStream_t)stream);
 }
 
 int pnpb200_stats_pass2(int64_t B, int nq, const double* const* est, const int64_t* est_stride, const double* const* gt,
-                        const int64_t* gt_stride, const int32_t* class_id, int n_class, const double* mean, double* sums2,
-                        void* stream)
+                        const int64_t* gt_stride, const int32_t* class_id, int n_class, const double* sums1, double* sums2,
+                        double* max2, void* stream)
 {
-    return stats_launch<2>(B, nq, est, est_stride, gt, gt_stride, class_id, n_class, mean, sums2, (cudaStream_t)stream);
+    return stats_launch<2>(B, nq, est, est_stride, gt, gt_stride, class_id, n_class, sums1, sums2, max2, (cudaStream_t)stream);
 }
 
 int pnpb200_classify(int64_t B, const double* values, int64_t stride, double scale, const double* bins, int n_bins,

@@ -110,40 +110,69 @@ def _all_reduce(t, op, group):
 
 
 def reduce_phase1(s1, group=None):
-    """all_reduce(SUM) of the pass-1 sums [..., 4] = (n, sum est/gt, sum e, 0); returns the global
-    per-row error mean.  Works on any backend (NCCL on GPUs, gloo in CPU tests)."""
+    """Phase 1: all_reduce(SUM) of the pass-1 sums [..., 4] = (n, sum est/gt, sum e, 0), in place.
+    Works on any backend (NCCL on GPUs, gloo in CPU tests)."""
     import torch.distributed as dist
     _all_reduce(s1, dist.ReduceOp.SUM, group)
-    return (s1[..., 2] / s1[..., 0]).contiguous()
+    return s1
 
 
-def reduce_phase2(s2, group=None):
-    """pass-2 sums [..., 4] = (sum (e-m)^2, sum |e|, sum |e-m|, max |e-m|): SUM the first three
-    columns, MAX the last."""
+def reduce_phase2(s2, mx, group=None):
+    """Phase 2: all_reduce(SUM) of [..., 4] = (sum (e-m)^2, sum |e|, sum |e-m|, 0) and
+    all_reduce(MAX) of max |e-m|, in place."""
     import torch.distributed as dist
-    sm = s2[..., :3].contiguous()
-    mx = s2[..., 3].contiguous()
-    _all_reduce(sm, dist.ReduceOp.SUM, group)
+    _all_reduce(s2, dist.ReduceOp.SUM, group)
     _all_reduce(mx, dist.ReduceOp.MAX, group)
-    return torch.cat([sm, mx[..., None]], dim=-1)
+    return s2, mx
 
 
-def finalize_stats(s1, s2):
+def finalize_stats(s1, s2, mx):
     """(n, m_ratio, mean, stddev [population], max_dev, MAE_2_GT, MAE_2_mean) per row
-    (TEST_TOOLBOX.py:907-915, :928-935)."""
-    n = s1[..., 0]
-    return torch.stack([n, s1[..., 1] / n, s1[..., 2] / n, torch.sqrt(s2[..., 0] / n), s2[..., 3], s2[..., 1] / n, s2[..., 2] / n], dim=-1)
+    (TEST_TOOLBOX.py:907-915, :928-935), on the host from the three small reduced arrays."""
+    s1, s2, mx = (np.asarray(a.detach().cpu().numpy() if torch.is_tensor(a) else a, dtype=np.float64) for a in (s1, s2, mx))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        n = s1[..., 0]
+        out = np.stack([n, s1[..., 1] / n, s1[..., 2] / n, np.sqrt(s2[..., 0] / n), mx, s2[..., 1] / n, s2[..., 2] / n], axis=-1)
+    return torch.from_numpy(out)
 
 
-def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=True):
+class PendingStats(object):
+    """Statistics whose reduced sums are still on their way to the host (asynchronous D2H into a
+    pinned buffer); `.result()` waits for the copy and finalises.  Lets a caller queue many batches
+    without a host synchronisation per batch."""
+    _pinned = {}
+
+    def __init__(self, flat, nq, rows):
+        self.nq, self.rows = nq, rows
+        n = int(flat.numel())
+        free = PendingStats._pinned.setdefault(n, [])
+        self._host = free.pop() if free else torch.empty((n,), dtype=torch.float64).pin_memory()
+        self._host.copy_(flat, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(flat.device))
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            self._event.synchronize()
+            nq, rows, h = self.nq, self.rows, self._host
+            self._out = finalize_stats(h[:nq * rows * 4].view(nq, rows, 4).clone(), h[nq * rows * 4:nq * rows * 8].view(nq, rows, 4).clone(),
+                                       h[nq * rows * 8:].view(nq, rows).clone())
+            PendingStats._pinned[int(h.numel())].append(h)
+            self._host = None
+        return self._out
+
+
+def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=True, lazy=False):
     """get_statistic_of_result (TEST_TOOLBOX.py:892-937) for up to 4 quantities at once, per class
     and over all problems, over ALL ranks' shards.
 
     est, gt: lists of 1-D FP64 CUDA views (strided allowed) of this rank's shard (gt entries or gt
-    itself may be None); class_id int32 [B] or None.  Two phases: all_reduce(SUM) of
-    [n, sum est/gt, sum e] -> global means; all_reduce(SUM) of [sum (e-m)^2, sum |e|, sum |e-m|] and
-    all_reduce(MAX) of max |e-m|.  Returns a float64 CPU tensor [nq, n_class+1, 7] in STAT_KEYS
-    order; the last row of each quantity is the class 'all'; empty classes have n = 0."""
+    itself may be None); class_id int32 [B] or None.  Two kernels and two reduction phases
+    (SURVEY.md 8e): all_reduce(SUM) of [n, sum est/gt, sum e]; the second kernel derives the global
+    means from them; all_reduce(SUM) of [sum (e-m)^2, sum |e|, sum |e-m|] and all_reduce(MAX) of
+    max |e-m|.  Returns a float64 CPU tensor [nq, n_class+1, 7] in STAT_KEYS order; the last row of
+    each quantity is the class 'all'; empty classes have n = 0."""
     if torch.is_tensor(est):
         est, gt = [est], [gt]
     nq = len(est)
@@ -159,31 +188,47 @@ def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=T
     for e in est:
         assert e.dtype == torch.float64 and e.dim() == 1 and int(e.shape[0]) == B
     cid = None if class_id is None else C.cast(ptr(class_id), C.POINTER(C.c_int32))
-    s1 = torch.empty((nq, n_class + 1, 4), dtype=torch.float64, device=dev)
+    rows = n_class + 1
+    flat = torch.empty((nq * rows * 9,), dtype=torch.float64, device=dev)      # s1 | s2 | max in one allocation
+    s1 = flat[:nq * rows * 4].view(nq, rows, 4)
+    s2 = flat[nq * rows * 4:nq * rows * 8].view(nq, rows, 4)
+    mx = flat[nq * rows * 8:].view(nq, rows)
     with torch.cuda.device(dev):
         check(lib.pnpb200_stats_pass1(C.c_int64(B), C.c_int(nq), est_a, es_a, gt_a, gs_a, cid, C.c_int(n_class),
                                       dp(s1), _stream_ptr(dev)), "pnpb200_stats_pass1")
     _lib.count_launch()
-    mean = reduce_phase1(s1, group) if distributed else (s1[..., 2] / s1[..., 0]).contiguous()
-    mean = torch.nan_to_num(mean).contiguous()
-    s2 = torch.empty((nq, n_class + 1, 4), dtype=torch.float64, device=dev)
+    if distributed:
+        reduce_phase1(s1, group)
     with torch.cuda.device(dev):
         check(lib.pnpb200_stats_pass2(C.c_int64(B), C.c_int(nq), est_a, es_a, gt_a, gs_a, cid, C.c_int(n_class),
-                                      dp(mean), dp(s2), _stream_ptr(dev)), "pnpb200_stats_pass2")
+                                      dp(s1), dp(s2), dp(mx), _stream_ptr(dev)), "pnpb200_stats_pass2")
     _lib.count_launch()
     if distributed:
-        s2 = reduce_phase2(s2, group)
-    return finalize_stats(s1, s2).cpu()
+        reduce_phase2(s2, mx, group)
+    pending = PendingStats(flat, nq, rows)
+    return pending if lazy else pending.result()                                # .result() is the only synchronisation
 
 
-def error_statistics(report, gt, group=None, distributed=True):
+def error_statistics(report, gt, group=None, distributed=True, lazy=False):
     """The statistics block of TEST_TOOLBOX.data_analysis_and_saving (:1070-1112) for the four
     reported quantities, for class 'all' and per GT-depth class, in two kernels and two all-reduce
     phases.  report: [B,16] from report_batch; gt [B,4].
-    Returns {quantity: {'all': stats[7], 'by_depth': stats[12,7]}} (CPU tensors, STAT_KEYS order)."""
+    Returns {quantity: {'all': stats[7], 'by_depth': stats[12,7]}} (CPU tensors, STAT_KEYS order);
+    lazy=True returns an object whose .result() gives that dict (no host sync in this call)."""
     cls = classify(gt[:, 0], CLASS_BINS["depth"], scale=100.0)
     # (estimate, GT): depth compares t3_est with distance_GT (:1073), the angles est vs GT
     est = [report[:, 10], report[:, 12], report[:, 13], report[:, 14]]
     ref = [report[:, 11], gt[:, 1], gt[:, 2], gt[:, 3]]
-    st = statistics(est, ref, cls, len(CLASS_LABELS["depth"]), group, distributed)
-    return {name: dict(all=st[q, -1], by_depth=st[q, :-1]) for q, name in enumerate(("depth", "roll", "pitch", "yaw"))}
+    st = statistics(est, ref, cls, len(CLASS_LABELS["depth"]), group, distributed, lazy=lazy)
+    unpack = lambda x: {name: dict(all=x[q, -1], by_depth=x[q, :-1]) for q, name in enumerate(("depth", "roll", "pitch", "yaw"))}
+    if lazy:
+        return _LazyDict(st, unpack)
+    return unpack(st)
+
+
+class _LazyDict(object):
+    def __init__(self, pending, unpack):
+        self._pending, self._unpack = pending, unpack
+
+    def result(self):
+        return self._unpack(self._pending.result())

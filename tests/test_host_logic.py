@@ -60,15 +60,18 @@ def _stats_worker(rank, world_size, port, q):
     for k in range(n_class):
         m = c == k
         s1[k] = [m.sum(), (e[m] / t[m]).sum(), (e[m] - t[m]).sum(), 0.0]
-    s1 = torch.from_numpy(s1)
-    mean = torch.nan_to_num(wl.reduce_phase1(s1)).numpy()          # [n_class]
+    s1 = wl.reduce_phase1(torch.from_numpy(s1)).numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean = np.nan_to_num(s1[:, 2] / s1[:, 0])                  # what k_stats<2> derives from the reduced sums
     s2 = np.zeros((n_class, 4))
+    mx = np.zeros(n_class)
     for k in range(n_class):
         m = c == k
         d = (e[m] - t[m]) - mean[k]
-        s2[k] = [(d * d).sum(), np.abs(e[m] - t[m]).sum(), np.abs(d).sum(), np.abs(d).max() if m.any() else 0.0]
-    s2 = wl.reduce_phase2(torch.from_numpy(s2))
-    out = wl.finalize_stats(s1, s2).numpy()
+        s2[k] = [(d * d).sum(), np.abs(e[m] - t[m]).sum(), np.abs(d).sum(), 0.0]
+        mx[k] = np.abs(d).max() if m.any() else 0.0
+    s2, mx = wl.reduce_phase2(torch.from_numpy(s2), torch.from_numpy(mx))
+    out = wl.finalize_stats(torch.from_numpy(s1), s2, mx).numpy()
     if rank == 0:
         q.put(out)
     dist.barrier()
