@@ -86,6 +86,9 @@ typedef struct pnpb200_synth {
     int32_t  reserved;
     double   quantize_q;      /* 1.0                                                               */
     double   noise_sigma_px;  /* 0 = none; Gaussian pixel noise added after quantisation           */
+    double   roll_center_deg; /* 0    angles are centre + U(-angle_range, angle_range); a fixed    */
+    double   pitch_center_deg;/* 0    pose (LM_noise_test.py:180-182, :262) is range 0 + centres   */
+    double   yaw_center_deg;  /* 0                                                                 */
 } pnpb200_synth;
 
 int pnpb200_version(void);

@@ -33,7 +33,8 @@ class Synth(C.Structure):
     """Mirror of oracle_synth_t (defaults = random_stress_test.py:246-258)."""
     _fields_ = [("seed", C.c_uint64), ("angle_range_deg", C.c_double), ("depth_min_m", C.c_double),
                 ("depth_max_m", C.c_double), ("fov_max_deg", C.c_double), ("is_quantized", C.c_int32),
-                ("quantize_q", C.c_double), ("noise_sigma_px", C.c_double)]
+                ("quantize_q", C.c_double), ("noise_sigma_px", C.c_double), ("roll_center_deg", C.c_double),
+                ("pitch_center_deg", C.c_double), ("yaw_center_deg", C.c_double)]
 
 
 def build(force=False):
@@ -78,7 +79,7 @@ def default_params(**kw):
 
 
 def default_synth(seed=42, is_quantized=True, quantize_q=1.0, noise_sigma_px=0.0, **kw):
-    s = Synth(seed, 45.0, 0.20, 2.25, 45.0, int(is_quantized), quantize_q, noise_sigma_px)
+    s = Synth(seed, 45.0, 0.20, 2.25, 45.0, int(is_quantized), quantize_q, noise_sigma_px, 0.0, 0.0, 0.0)
     for k, v in kw.items():
         setattr(s, k, v)
     return s

@@ -899,6 +899,7 @@ typedef struct {
     int32_t is_quantized;     /* :50 */
     double quantize_q;        /* 1.0 */
     double noise_sigma_px;    /* 0 = none */
+    double roll_center_deg, pitch_center_deg, yaw_center_deg;   /* angle = centre + U(-range, range) */
 } oracle_synth_t;
 
 typedef struct {
@@ -921,9 +922,9 @@ static void synth_range(int64_t lo, int64_t hi, void *vctx)
         philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, 0u, k0, k1, r);
         philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 1u, 0u, k0, k1, r + 4);
         philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 2u, 0u, k0, k1, r + 8);
-        roll  = -cfg->angle_range_deg + 2.0 * cfg->angle_range_deg * u01(r[0], r[1]);
-        pitch = -cfg->angle_range_deg + 2.0 * cfg->angle_range_deg * u01(r[2], r[3]);
-        yaw   = -cfg->angle_range_deg + 2.0 * cfg->angle_range_deg * u01(r[4], r[5]);
+        roll  = cfg->roll_center_deg + (-cfg->angle_range_deg + 2.0 * cfg->angle_range_deg * u01(r[0], r[1]));
+        pitch = cfg->pitch_center_deg + (-cfg->angle_range_deg + 2.0 * cfg->angle_range_deg * u01(r[2], r[3]));
+        yaw   = cfg->yaw_center_deg + (-cfg->angle_range_deg + 2.0 * cfg->angle_range_deg * u01(r[4], r[5]));
         depth = cfg->depth_min_m + (cfg->depth_max_m - cfg->depth_min_m) * u01(r[6], r[7]);
         fx    = -cfg->fov_max_deg + 2.0 * cfg->fov_max_deg * u01(r[8], r[9]);
         fy    = -cfg->fov_max_deg + 2.0 * cfg->fov_max_deg * u01(r[10], r[11]);

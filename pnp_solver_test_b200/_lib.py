@@ -39,7 +39,8 @@ class Synth(C.Structure):
     """struct pnpb200_synth"""
     _fields_ = [("seed", C.c_uint64), ("angle_range_deg", C.c_double), ("depth_min_m", C.c_double),
                 ("depth_max_m", C.c_double), ("fov_max_deg", C.c_double), ("is_quantized", C.c_int32),
-                ("reserved", C.c_int32), ("quantize_q", C.c_double), ("noise_sigma_px", C.c_double)]
+                ("reserved", C.c_int32), ("quantize_q", C.c_double), ("noise_sigma_px", C.c_double),
+                ("roll_center_deg", C.c_double), ("pitch_center_deg", C.c_double), ("yaw_center_deg", C.c_double)]
 
 
 class PnpB200Error(RuntimeError):

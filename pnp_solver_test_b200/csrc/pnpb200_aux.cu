@@ -143,9 +143,9 @@ __global__ void k_synth(long long b0, long long B, int n, const double* __restri
     philox4x32_10(g0, g1, 2u, 0u, k0, k1, r2);
     const double kD2R = 3.14159265358979323846 / 180.0;
     const double a = cfg.angle_range_deg, f = cfg.fov_max_deg;
-    const double roll = -a + 2.0 * a * u01(r0[0], r0[1]);
-    const double pitch = -a + 2.0 * a * u01(r0[2], r0[3]);
-    const double yaw = -a + 2.0 * a * u01(r1[0], r1[1]);
+    const double roll = cfg.roll_center_deg + (-a + 2.0 * a * u01(r0[0], r0[1]));
+    const double pitch = cfg.pitch_center_deg + (-a + 2.0 * a * u01(r0[2], r0[3]));
+    const double yaw = cfg.yaw_center_deg + (-a + 2.0 * a * u01(r1[0], r1[1]));
     const double depth = cfg.depth_min_m + (cfg.depth_max_m - cfg.depth_min_m) * u01(r1[2], r1[3]);
     const double fx = -f + 2.0 * f * u01(r2[0], r2[1]);
     const double fy = -f + 2.0 * f * u01(r2[2], r2[3]);
@@ -621,6 +621,7 @@ int pnpb200_default_synth(pnpb200_synth* s)
     if (!s) return PNPB200_EINVAL;
     s->seed = 42; s->angle_range_deg = 45.0; s->depth_min_m = 0.20; s->depth_max_m = 2.25; s->fov_max_deg = 45.0;
     s->is_quantized = 1; s->reserved = 0; s->quantize_q = 1.0; s->noise_sigma_px = 0.0;
+    s->roll_center_deg = 0.0; s->pitch_center_deg = 0.0; s->yaw_center_deg = 0.0;
     return PNPB200_OK;
 }
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from pnp_solver_test_b200 import _lib
     assert C.sizeof(_lib.Params) == 2 * 4 + 8 * 8 + 2 * 4 + 8 + 8
-    assert C.sizeof(_lib.Synth) == 8 + 4 * 8 + 2 * 4 + 2 * 8
+    assert C.sizeof(_lib.Synth) == 8 + 4 * 8 + 2 * 4 + 2 * 8 + 3 * 8
     p = _lib.default_params()
     assert (p.max_it, p.linear_it, p.lm_lambda, p.exit_tol, p.f_weight) == (14, 3, 1e-5, 1e-2, 225.68)
     assert (p.meas_sigma_px, p.proc_q, p.proc_d, p.omega0, p.res_old0, p.mapping) == (3.0, 0.1, 0.01, 1e-5, 1e-7, 0)

@@ -59,7 +59,9 @@ def test_synthetic_workload_matches_oracle_and_is_shard_invariant():
     P = pt.pattern_array(pt.synthetic_pattern(68))
     K = pt.default_camera_matrix()
     for cfg_kw in (dict(is_quantized=0), dict(is_quantized=1), dict(is_quantized=0, noise_sigma_px=1.5),
-                   dict(is_quantized=1, quantize_q=30.0 / 112.0, noise_sigma_px=0.5)):
+                   dict(is_quantized=1, quantize_q=30.0 / 112.0, noise_sigma_px=0.5),
+                   dict(is_quantized=1, quantize_q=30.0 / 112.0, noise_sigma_px=0.4, angle_range_deg=0.0, yaw_center_deg=38.5,
+                        depth_min_m=1.0, depth_max_m=1.0, fov_max_deg=0.0)):      # LM_noise_test.py's fixed pose
         ref = orc.synth(5, 4000, P, K, orc.default_synth(seed=9, **{k: v for k, v in cfg_kw.items()}))
         got = wl.synth_batch(5, 4000, P, K, cfg=pnp.default_synth(seed=9, **cfg_kw), want_pose=True)
         assert np.abs(got["gt"].cpu().numpy() - ref["gt"]).max() < 1e-12
