@@ -35,6 +35,9 @@ extern "C" {
 #define PNPB200_METHOD_LM         1  /* solve_pnp_LM_single_pattern,            PNP_SOLVER_LIB.py:2567-2769 */
 #define PNPB200_METHOD_LINEAR_F2  2  /* solve_pnp_formulation_2_single_pattern, PNP_SOLVER_LIB.py:693-953   */
 #define PNPB200_METHOD_LINEAR_F1  3  /* solve_pnp_single_pattern,               PNP_SOLVER_LIB.py:205-430   */
+#define PNPB200_METHOD_LM_PLUS    4  /* NOT in the reference (non-parity extra): linear F2 initial pose, then LM's 12-state
+                                        damped Gauss-Newton with the true constraint gradients and a convergence test
+                                        (max |dx| <= 1e-10); res_norm at the returned state; one pattern, moment mapping */
 
 #define PNPB200_DTYPE_F64 0
 #define PNPB200_DTYPE_F32 1

@@ -382,8 +382,10 @@ ORACLE_API int pnp_oracle_qeif(int n, const double *P, const double *uv, const d
 /* LM: solve_pnp_LM_single_pattern :2567-2769, EKF2_get_hx_H :3718-3836 (defaults          */
 /*     is_hc0_4_6_linear=False, is_hc1_linear=True), EKF2_reconstruct_R_t_m1 :3500-3540    */
 /* ------------------------------------------------------------------------------------ */
-static void ekf2_hx_H(int n, const double *x, const double *bx, const double *by, const double *P,
-                      double *hx, double *J)
+/* true_jac = 0: the reference's Jacobians (rows 4-6 use u, rows 7-9 use u/(2|u|)).
+ * true_jac = 1: the actual gradients (2u and u/|u|) -- only used by the non-parity LM+ mode. */
+static void ekf2_hx_H_ex(int n, const double *x, const double *bx, const double *by, const double *P,
+                         double *hx, double *J, int true_jac)
 {
     const double *u1 = x, *u2 = x + 3, *u3 = x + 6;
     double d1 = x[9], d2 = x[10], g = x[11];
@@ -425,14 +427,23 @@ static void ekf2_hx_H(int n, const double *x, const double *bx, const double *by
             r[0 * 12 + k] = u3[k];  r[0 * 12 + 6 + k] = u1[k];                    /* :3787-3788 */
             r[1 * 12 + 3 + k] = u3[k]; r[1 * 12 + 6 + k] = u2[k];                 /* :3790-3791 */
             r[2 * 12 + k] = u2[k];  r[2 * 12 + 3 + k] = u1[k];                    /* :3793-3794 */
-            r[3 * 12 + k] = u1[k];  r[3 * 12 + 6 + k] = -u3[k];                   /* :3808-3809 (u, not 2u) */
-            r[4 * 12 + 3 + k] = u2[k]; r[4 * 12 + 6 + k] = -u3[k];                /* :3811-3812 */
-            r[5 * 12 + k] = u1[k];  r[5 * 12 + 3 + k] = -u2[k];                   /* :3814-3815 */
-            r[6 * 12 + k] = u1[k] / (2.0 * n1);                                   /* :3819 halved gradient */
-            r[7 * 12 + 3 + k] = u2[k] / (2.0 * n2);                               /* :3821 */
-            r[8 * 12 + 6 + k] = u3[k] / (2.0 * n3);                               /* :3823 */
+            {
+                const double kq = true_jac ? 2.0 : 1.0, kn = true_jac ? 1.0 : 2.0;
+                r[3 * 12 + k] = kq * u1[k];  r[3 * 12 + 6 + k] = -kq * u3[k];         /* :3808-3809 (u, not 2u) */
+                r[4 * 12 + 3 + k] = kq * u2[k]; r[4 * 12 + 6 + k] = -kq * u3[k];      /* :3811-3812 */
+                r[5 * 12 + k] = kq * u1[k];  r[5 * 12 + 3 + k] = -kq * u2[k];         /* :3814-3815 */
+                r[6 * 12 + k] = u1[k] / (kn * n1);                                    /* :3819 halved gradient */
+                r[7 * 12 + 3 + k] = u2[k] / (kn * n2);                                /* :3821 */
+                r[8 * 12 + 6 + k] = u3[k] / (kn * n3);                                /* :3823 */
+            }
         }
     }
+}
+
+static void ekf2_hx_H(int n, const double *x, const double *bx, const double *by, const double *P,
+                      double *hx, double *J)
+{
+    ekf2_hx_H_ex(n, x, bx, by, P, hx, J, 0);
 }
 
 /* EKF2_reconstruct_R_t_m1 :3500-3540 */
@@ -507,6 +518,73 @@ ORACLE_API int pnp_oracle_lm(int n, const double *P, const double *uv, const dou
     ekf2_reconstruct(x, R, t);
     pnp_oracle_euler_from_R(R, 1, euler);
     *res_norm_out = res;
+    free(bx);
+    return it;
+}
+
+ORACLE_API int pnp_oracle_linear_f2(int n, const double *P, const double *uv, const double *K,
+                                    const oracle_params_t *prm, double *R, double *t, double *euler,
+                                    double *res_norm_out, double *trace);
+
+/* ------------------------------------------------------------------------------------ */
+/* LM+ -- NOT a reference method: the pipeline BASELINE.json's north star   */
+/* describes.  Linear stage F2 (3 iterations) for the initial pose, then the same 12-state      */
+/* damped Gauss-Newton as solve_pnp_LM_single_pattern but with the TRUE constraint gradients     */
+/* and a convergence test: stop when max |dx| <= 1e-10, at most max_it iterations.               */
+/* res_norm = ||z - hx|| over the 2n measurement rows at the RETURNED state.                      */
+/* ------------------------------------------------------------------------------------ */
+ORACLE_API int pnp_oracle_lm_plus(int n, const double *P, const double *uv, const double *K,
+                                  const oracle_params_t *prm, double *R, double *t, double *euler,
+                                  double *res_norm_out, double *trace)
+{
+    int Z = 2 * n + 9, i, j, r, it = 0;
+    double Kinv[9];
+    double *bx = (double *)malloc(sizeof(double) * ((size_t)n * 2 + (size_t)Z * 14));
+    double *by = bx + n, *hx = by + n, *J = hx + Z, *dz = J + (size_t)Z * 12;
+    double x[12], A[144], Ainv[144], g[12], work[144 + 12 + 144];
+    double R0[9], t0[3], e0[3], r0, res2 = 0.0;
+    (void)trace;
+    pnp_oracle_linear_f2(n, P, uv, K, prm, R0, t0, e0, &r0, NULL);
+    for (i = 0; i < 9; ++i) x[i] = R0[i];
+    x[9] = t0[0] / t0[2]; x[10] = t0[1] / t0[2]; x[11] = 1.0 / t0[2];
+    inv3(K, Kinv);
+    normalise(n, uv, Kinv, bx, by);
+    while (it < prm->max_it) {
+        double step = 0.0;
+        ++it;
+        ekf2_hx_H_ex(n, x, bx, by, P, hx, J, 1);
+        for (i = 0; i < 12; ++i)
+            for (j = 0; j < 12; ++j) {
+                double a = 0.0;
+                for (r = 0; r < Z; ++r) a += J[r * 12 + i] * J[r * 12 + j];
+                A[i * 12 + j] = a + ((i == j) ? prm->lm_lambda : 0.0);
+            }
+        pinv_svd(12, 12, A, Ainv, work);
+        for (r = 0; r < Z; ++r) {
+            double z = (r < n) ? bx[r] : (r < 2 * n) ? by[r - n] : (r < 2 * n + 6) ? 0.0 : 1.0;
+            dz[r] = z - hx[r];
+        }
+        for (i = 0; i < 12; ++i) {
+            double a = 0.0;
+            for (r = 0; r < Z; ++r) a += J[r * 12 + i] * dz[r];
+            g[i] = a;
+        }
+        for (i = 0; i < 12; ++i) {
+            double a = 0.0;
+            for (j = 0; j < 12; ++j) a += Ainv[i * 12 + j] * g[j];
+            x[i] += a;
+            if (fabs(a) > step) step = fabs(a);
+        }
+        if (step <= 1e-10) break;
+    }
+    ekf2_hx_H_ex(n, x, bx, by, P, hx, J, 1);
+    for (r = 0; r < 2 * n; ++r) {
+        double z = (r < n) ? bx[r] : by[r - n];
+        res2 += (z - hx[r]) * (z - hx[r]);
+    }
+    ekf2_reconstruct(x, R, t);
+    pnp_oracle_euler_from_R(R, 1, euler);
+    *res_norm_out = sqrt(res2);
     free(bx);
     return it;
 }
@@ -765,6 +843,7 @@ ORACLE_API int pnp_oracle_solve_batch(int method, int64_t B, int n, const double
     case 1: c.fn = pnp_oracle_lm; break;
     case 2: c.fn = pnp_oracle_linear_f2; break;
     case 3: c.fn = pnp_oracle_linear_f1; break;
+    case 4: c.fn = pnp_oracle_lm_plus; break;
     default: return -1;
     }
     c.n = n; c.n_patterns = n_patterns; c.uv = uv; c.patterns = patterns; c.K = K; c.prm = prm;

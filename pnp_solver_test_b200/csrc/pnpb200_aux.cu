@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
         for (int c = 0; c < rs.n_chunks; ++c) {
             const V2* row = rs.wait(c, lane);
             const int cnt = rs.count(c), base = c * rs.chunk;
+#pragma unroll 2
             for (int k = 0; k < cnt; ++k) {
                 const int i = base + k;
                 const double x = (double)sP[3 * i], y = (double)sP[3 * i + 1], z = (double)sP[3 * i + 2];

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
             }
         } else {
             T res;
-            if (METHOD == PNPB200_METHOD_LM) {
+            if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
                 T x[12];
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = st[k];
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
             T st[PNP_NTAIL];
 #pragma unroll
             for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.B + b];
-            if (METHOD == PNPB200_METHOD_LM) {
+            if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = st[k];
             } else {
@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
         for (int c = 0; c < rs.n_chunks; ++c) {
             const V2* row = rs.wait(c, lane);
             const int cnt = rs.count(c), i0 = c * rs.chunk;
+#pragma unroll 2
             for (int k = 0; k < cnt; ++k) {
                 const V2 px = row[k];
                 const T bx = k00 * px.x + k01 * px.y + k02;   // nu = K^-1 [u, v, 1]^T (:3305)
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
                 const T th[3] = { sP[3 * (i0 + k)], sP[3 * (i0 + k) + 1], sP[3 * (i0 + k) + 2] };
                 if (PASS == 0) {
                     mom.add(th, bx, by);
-                } else if (METHOD == PNPB200_METHOD_LM) {
+                } else if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
                     const T aa = th[0] * x[0] + th[1] * x[1] + th[2] * x[2];
                     const T bb = th[0] * x[3] + th[1] * x[4] + th[2] * x[5];
                     const T cc = th[0] * x[6] + th[1] * x[7] + th[2] * x[8];
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
 #pragma unroll
                 for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.B + b] = mom.at(k);
             } else if (a.res) {
-                if (METHOD == PNPB200_METHOD_LM) a.res[b] = t_sqrt(acc0);                 // :2681
+                if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) a.res[b] = t_sqrt(acc0);   // :2681
                 else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
             }
         }
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
             if (lane < PNP_NMOM) a.mom[(size_t)lane * a.B + b] = mine;
         } else {
             T res;
-            if (METHOD == PNPB200_METHOD_LM) {
+            if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
                 T x[12];
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = a.tail[(size_t)k * a.B + b];
@@ -573,6 +574,14 @@ __global__ void __launch_bounds__(kIterBlock, MINB) k_iterate(const __grid_const
         solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, a.prm, xp, out);
 #pragma unroll
         for (int k = 0; k < 12; ++k) st[k] = xp[k];
+    } else if (METHOD == PNPB200_METHOD_LM_PLUS) {
+        Moments<T> mr;
+#pragma unroll
+        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMom[k * kIterBlock + threadIdx.x];
+        T xf[12];
+        solve_lm_plus_from_moments<T, MomentsRef<T> >(mom, mr, sC, a.prm, xf, out);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st[k] = xf[k];
     } else {
         Moments<T> mr;
 #pragma unroll
@@ -767,7 +776,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc != PNPB200_OK) return rc;
-    constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2);
+    constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNPB200_METHOD_LM_PLUS);
     const RowGeom g = row_geometry<T>(a.n_total);
     const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
     const size_t idx_bytes = a.idx_mode ? (size_t)a.n * sizeof(int32_t) : 0;
@@ -834,6 +843,14 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
     case PNPB200_METHOD_LINEAR_F2: return launch_solve<T, PNPB200_METHOD_LINEAR_F2>(a, prm.mapping, stream);
     case PNPB200_METHOD_LINEAR_F1: return launch_solve<T, PNPB200_METHOD_LINEAR_F1>(a, prm.mapping, stream);
+    case PNPB200_METHOD_LM_PLUS: {
+        // non-parity extra: exists in the moment mapping only, one pattern
+        if (n_patterns != 1 || (prm.mapping != PNPB200_MAP_AUTO && prm.mapping != PNPB200_MAP_MOMENT)) return PNPB200_EINVAL;
+        DeviceProps dp;
+        int rc = get_device_props(&dp);
+        if (rc != PNPB200_OK) return rc;
+        return launch_moment<T, PNPB200_METHOD_LM_PLUS>(a, dp, stream);
+    }
     default: return PNPB200_EINVAL;
     }
 }
@@ -897,7 +914,7 @@ int pnpb200_profile_read(float* ms, int* n_calls)
 
 int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping)
 {
-    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2) && n_patterns == 1;
+    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS) && n_patterns == 1;
     if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
     const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
     return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
@@ -910,7 +927,7 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, co
 {
     if (B < 0 || n_total < 1 || n < 1 || (!point_index && n != n_total) || !uv || !pattern || !K) return PNPB200_EINVAL;
     if (n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
-    if (method < 0 || method > 3 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
+    if (method < 0 || method > 4 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
     if (B == 0) return PNPB200_OK;
     pnpb200_params prm;
     if (params) prm = *params; else fill_default_params(&prm);

@@ -402,9 +402,12 @@ PNP_DEV void add_outer1(T (&A)[55], T (&g)[10], const T (&va)[3], T e)
 // couple to each other, and each couples to seven of the other unknowns only.  What is factorised
 // is the 10 x 10 Schur complement on (u1, u2, u3, gamma) -- the LDL^T of the 12 x 12 matrix with
 // the two delta columns ordered first, written out.
-template <typename T, typename M>
-PNP_DEV void lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaCol<T>& gc, const LmRhs<T>& r,
-                     T lambda)
+// TRUE_JAC = false reproduces the reference's constraint Jacobians (rows 4-6 use u, rows 7-9 use
+// u/(2|u|)); true uses the actual gradients (2u, u/|u|) and is only used by the non-parity LM+.
+// Returns max |dx|.
+template <typename T, typename M, bool TRUE_JAC = false>
+PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaCol<T>& gc, const LmRhs<T>& r,
+                  T lambda)
 {
     constexpr int U1 = 0, U2 = 3, U3 = 6, GG = 9;       // order inside the reduced system
     const T gam = x[11];
@@ -466,14 +469,16 @@ PNP_DEV void lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const Gam
         const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
         const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
         const T n1 = t_sqrt(u11), n2 = t_sqrt(u22), n3 = t_sqrt(u33);
-        const T nu2[3] = { -u2[0], -u2[1], -u2[2] }, nu3[3] = { -u3[0], -u3[1], -u3[2] };
+        constexpr T kq = TRUE_JAC ? T(2) : T(1), kn = TRUE_JAC ? T(1) : T(2);
+        const T pu1[3] = { kq * u1[0], kq * u1[1], kq * u1[2] }, pu2[3] = { kq * u2[0], kq * u2[1], kq * u2[2] };
+        const T nu2[3] = { -kq * u2[0], -kq * u2[1], -kq * u2[2] }, nu3[3] = { -kq * u3[0], -kq * u3[1], -kq * u3[2] };
         add_outer2<T, U1, U3>(A, g, u3, u1, T(0) - u13);          // u1.u3 = 0
         add_outer2<T, U2, U3>(A, g, u3, u2, T(0) - u23);          // u2.u3 = 0
         add_outer2<T, U1, U2>(A, g, u2, u1, T(0) - u12);          // u1.u2 = 0
-        add_outer2<T, U1, U3>(A, g, u1, nu3, T(0) - (u11 - u33)); // rows use u, not 2u (:3808)
-        add_outer2<T, U2, U3>(A, g, u2, nu3, T(0) - (u22 - u33));
-        add_outer2<T, U1, U2>(A, g, u1, nu2, T(0) - (u11 - u22));
-        const T h1 = t_rcp<T>(T(2) * n1), h2 = t_rcp<T>(T(2) * n2), h3 = t_rcp<T>(T(2) * n3);
+        add_outer2<T, U1, U3>(A, g, pu1, nu3, T(0) - (u11 - u33)); // reference rows use u, not 2u (:3808)
+        add_outer2<T, U2, U3>(A, g, pu2, nu3, T(0) - (u22 - u33));
+        add_outer2<T, U1, U2>(A, g, pu1, nu2, T(0) - (u11 - u22));
+        const T h1 = t_rcp<T>(kn * n1), h2 = t_rcp<T>(kn * n2), h3 = t_rcp<T>(kn * n3);
         const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
         const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
         const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
@@ -492,9 +497,14 @@ PNP_DEV void lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const Gam
 #pragma unroll
         for (int p = 0; p < 7; ++p) { e1 = t_fma(-c1[p], g[i1[p]], e1); e2 = t_fma(-c2[p], g[i2[p]], e2); }
     }
+    T step = T(0);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) step = fmax(step, t_abs(g[i]));
+    step = fmax(step, fmax(t_abs(e1 * ip), t_abs(e2 * ip)));
 #pragma unroll
     for (int i = 0; i < 9; ++i) x[i] += g[i];
     x[9] += e1 * ip; x[10] += e2 * ip; x[11] += g[GG];
+    return step;
 }
 
 // ||z - hx|| over the 2n measurement rows at state x, point by point (:2679-2681)
@@ -686,6 +696,47 @@ PNP_DEV void solve_f2_from_moments(const Moments<T>& mom, const T* __restrict__ 
     }
     out.res = T(30);
     out.iters = nit;
+}
+
+// LM+ (NOT a reference method; SURVEY.md 8f item 3, the pipeline of BASELINE.json's north star):
+// linear stage F2 for the initial pose, then the 12-state damped Gauss-Newton of LM with the true
+// constraint gradients and a convergence test (max |dx| <= 1e-10, at most max_it iterations).
+// One problem per thread: a warp leaves the loop when all of its lanes have converged.
+// x_out = the returned state, at which the caller evaluates res_norm point by point.
+template <typename T, typename M>
+PNP_DEV void solve_lm_plus_from_moments(const M& mom, const Moments<T>& mom_regs, const T* __restrict__ sC,
+                                        const SolverPrm<T>& prm, T (&x_out)[12], Result<T>& out)
+{
+    F2Tail<T> tail;
+    solve_f2_from_moments<T>(mom_regs, sC, prm, tail, out);
+    T x[12];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) x[e] = out.R[e];
+    x[9] = out.t[0] / out.t[2]; x[10] = out.t[1] / out.t[2]; x[11] = T(1) / out.t[2];
+    bool done = false;
+    int iters = 0;
+    for (int it = 0; it < prm.max_it; ++it) {
+        if (__all_sync(0xffffffffu, done)) break;
+        T xn[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) xn[e] = x[e];
+        GammaCol<T> gc;
+        LmRhs<T> r;
+        lm_gamma_column<T, M>(xn, mom, sC, gc);
+        lm_rhs_from_moments<T, M>(xn, mom, sC, gc, r);
+        const T step = lm_step<T, M, true>(xn, mom, sC, gc, r, prm.lm_lambda);
+        if (!done) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) x[e] = xn[e];
+            ++iters;
+            if (step <= T(sizeof(T) == 8 ? 1e-10 : 1e-5)) done = true;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) x_out[e] = x[e];
+    lm_reconstruct<T>(x, out);
+    out.res = T(0);
+    out.iters = iters;
 }
 
 template <typename T, int LPP, typename Pts>
