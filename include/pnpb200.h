@@ -56,6 +56,7 @@ extern "C" {
 #define PNPB200_ETOOLARGE  -4   /* n exceeds what the selected mapping can hold                    */
 
 #define PNPB200_FLAG_PROFILE 1  /* record CUDA events around each kernel of the call (pnpb200_profile_read) */
+#define PNPB200_FLAG_QEIF_DIRECT 2 /* QEIF: accumulate H^T H point by point even for n >= 12 (default there: from the moments) */
 
 #define PNPB200_MAX_PATTERNS 8
 #define PNPB200_REPORT_WIDTH 16

@@ -16,6 +16,7 @@ DTYPE_F64, DTYPE_F32 = 0, 1
 MAP_AUTO, MAP_THREAD, MAP_MOMENT, MAP_WARP = 0, 1, 2, 32
 REPORT_WIDTH = 16
 FLAG_PROFILE = 1
+FLAG_QEIF_DIRECT = 2
 MAX_PATTERNS = 8
 
 EXPORTS = [

@@ -103,6 +103,9 @@ static thread_local ProfileRing g_prof;
 // kernel arguments
 // ------------------------------------------------------------------------------------------
 #define PNP_MAX_INLINE_IDX 96
+// internal kernel variant: QEIF with H^T H / H^T v from the moments (chosen for n >= 12 landmarks)
+#define PNP_METHOD_QEIF_HYBRID 5
+#define PNP_QEIF_HYBRID_MIN_N 12
 
 template <typename T>
 struct SolveArgs {
@@ -179,7 +182,8 @@ template <typename T, int METHOD, int LPP, typename Pts>
 PNP_DEV void run_method(const Pts& pts, const T* sP, const T* sC, int n, int sub, const SolverPrm<T>& prm,
                         Result<T>& out)
 {
-    if (METHOD == PNPB200_METHOD_QEIF)           solve_qeif<T, LPP, Pts>(pts, sP, n, sub, prm, out);
+    if (METHOD == PNPB200_METHOD_QEIF)           solve_qeif<T, LPP, Pts, false>(pts, sP, sC, n, sub, prm, out);
+    else if (METHOD == PNP_METHOD_QEIF_HYBRID)   solve_qeif<T, LPP, Pts, true>(pts, sP, sC, n, sub, prm, out);
     else if (METHOD == PNPB200_METHOD_LM)        solve_lm<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
     else if (METHOD == PNPB200_METHOD_LINEAR_F2) solve_linear_f2<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
     else                                         solve_linear_f1<T, LPP, Pts>(pts, sP, n, sub, prm, out);
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
     // kick off the first tile's copies before touching the pattern so the two overlap
     int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
     load_pattern<T>(a.pattern, sel, a.n_total, a.n, a.n_patterns, sP, sIdx, lane, 32);
-    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
+    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNP_METHOD_QEIF_HYBRID) {
         for (int p = 0; p < a.n_patterns; ++p) pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncwarp();
     }
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_solve_warp(const __grid
 
     const int32_t* sel = selection_of(a);
     load_pattern<T>(a.pattern, sel, a.n_total, a.n, a.n_patterns, sP, sIdx, threadIdx.x, blockDim.x);
-    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2) {
+    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNP_METHOD_QEIF_HYBRID) {
         for (int p = warp; p < a.n_patterns; p += kWarpsPerBlock)
             pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncthreads();
@@ -839,7 +843,9 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     a.tune = (prm.flags >> 8) & 0xff;                     // undocumented tuning knob (register budget of k_iterate)
     a.ws = prm.workspace; a.ws_bytes = (prm.workspace && prm.workspace_bytes > 0) ? (size_t)prm.workspace_bytes : 0;
     switch (method) {
-    case PNPB200_METHOD_QEIF:      return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);
+    case PNPB200_METHOD_QEIF:
+        if (n >= PNP_QEIF_HYBRID_MIN_N && !(prm.flags & PNPB200_FLAG_QEIF_DIRECT)) return launch_solve<T, PNP_METHOD_QEIF_HYBRID>(a, prm.mapping, stream);
+        return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);
     case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
     case PNPB200_METHOD_LINEAR_F2: return launch_solve<T, PNPB200_METHOD_LINEAR_F2>(a, prm.mapping, stream);
     case PNPB200_METHOD_LINEAR_F1: return launch_solve<T, PNPB200_METHOD_LINEAR_F1>(a, prm.mapping, stream);

@@ -84,147 +84,6 @@ PNP_DEV void block_reconstruct(const T (&phi)[8], T (&R)[9], T (&t)[3], T& t3)
     t[0] = phi[6] * t3; t[1] = phi[7] * t3; t[2] = t3;    // :4360
 }
 
-// -------------------------------------------------------------------------------------------
-// QEIF -- solve_pnp_QEIF_single_pattern :2771-3025, QEKF_get_hx_H :3902-3983,
-//         QEKF_reconstruct_R_t_m1 :3542-3609
-// -------------------------------------------------------------------------------------------
-template <typename T>
-PNP_DEV void qekf_phi(const T (&x)[6], T (&p1)[3], T (&p2)[3], T (&p3)[3], T& gamma)
-{
-    const T qr = x[0], qi = x[1], qj = x[2], qk = x[3];
-    const T nq = t_sqrt(qr * qr + qi * qi + qj * qj + qk * qk);
-    gamma = nq * nq;                                      // (np.linalg.norm(q))**2 (:3918)
-    const T qii = qi * qi, qjj = qj * qj, qkk = qk * qk;
-    const T qij = qi * qj, qjk = qj * qk, qik = qi * qk;
-    const T qri = qr * qi, qrj = qr * qj, qrk = qr * qk;
-    p1[0] = gamma - 2 * (qjj + qkk); p1[1] = 2 * (qij - qrk); p1[2] = 2 * (qik + qrj);   // :3934
-    p2[0] = 2 * (qij + qrk); p2[1] = gamma - 2 * (qii + qkk); p2[2] = 2 * (qjk - qri);   // :3935
-    p3[0] = 2 * (qik - qrj); p3[1] = 2 * (qjk + qri); p3[2] = gamma - 2 * (qii + qjj);   // :3936
-}
-
-template <typename T, int LPP, typename Pts>
-PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, int n, int sub,
-                        const SolverPrm<T>& prm, Result<T>& out)
-{
-    T x[6] = { T(1), T(0), T(0), T(0), T(0), T(0) };      // :2831-2833
-    T Sig[21];
-#pragma unroll
-    for (int e = 0; e < 21; ++e) Sig[e] = T(0);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) Sig[sidx<6>(i, i)] = prm.sigma0;   // pinv(1e-5 I) (:2836-2837)
-    T res_old = prm.res_old0, res = T(1e5);
-    bool done = false;
-    int iters = 0;
-    const T w = prm.meas_w;                               // 1 / (9 / f^2) (:2844-2852)
-    const T nT = T(n);
-
-    for (int it = 0; it < prm.max_it; ++it) {
-        if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
-        else          { if (done) break; }
-        // ---- predict: Omega = pinv(Sigma + R) (:2887), zeta = Omega x (:2889)
-        T Om[21];
-#pragma unroll
-        for (int e = 0; e < 21; ++e) Om[e] = Sig[e];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Om[sidx<6>(i, i)] += (i < 4) ? prm.proc_q : prm.proc_d;
-        spd_inverse<T, 6>(Om);
-        T zeta[6];
-        sym_matvec<T, 6>(Om, x, zeta);
-        // ---- measurement model at x (:3902-3983)
-        T p1[3], p2[3], p3[3], gamma;
-        qekf_phi<T>(x, p1, p2, p3, gamma);
-        const T r2 = 2 * x[0], i2 = 2 * x[1], j2 = 2 * x[2], k2 = 2 * x[3];
-        const T Q1[12] = { r2, i2, -j2, -k2, -k2, j2, i2, -r2, j2, k2, r2, i2 };     // :3945
-        const T Q2[12] = { k2, j2, i2, r2, r2, -i2, j2, -k2, -i2, -r2, k2, j2 };     // :3949
-        const T Q3[12] = { -j2, k2, -r2, i2, i2, r2, k2, j2, r2, -i2, -j2, k2 };     // :3953
-        T qq[10], qd1[4], qd2[4], hv[6], res2 = T(0);
-#pragma unroll
-        for (int e = 0; e < 10; ++e) qq[e] = T(0);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { qd1[e] = T(0); qd2[e] = T(0); }
-#pragma unroll
-        for (int e = 0; e < 6; ++e) hv[e] = T(0);
-        for (int i = sub; i < n; i += LPP) {
-            const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
-            T bx, by;
-            pts.get(i, bx, by);
-            const T P1 = th0 * p1[0] + th1 * p1[1] + th2 * p1[2];
-            const T P2 = th0 * p2[0] + th1 * p2[1] + th2 * p2[2];
-            const T P3 = th0 * p3[0] + th1 * p3[1] + th2 * p3[2];
-            const T dzx = bx - (P1 - bx * P3 + x[4]);     // z - hx (:3969, :2905)
-            const T dzy = by - (P2 - by * P3 + x[5]);     // :3970
-            T Hx[4], Hy[4];
-            T hxq = x[4], hyq = x[5];                     // (H x) rows: Hq . q + delta
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const T a1 = th0 * Q1[c] + th1 * Q1[4 + c] + th2 * Q1[8 + c];
-                const T a2 = th0 * Q2[c] + th1 * Q2[4 + c] + th2 * Q2[8 + c];
-                const T a3 = th0 * Q3[c] + th1 * Q3[4 + c] + th2 * Q3[8 + c];
-                Hx[c] = a1 - bx * a3;                     // :3979
-                Hy[c] = a2 - by * a3;                     // :3980
-                hxq = t_fma(Hx[c], x[c], hxq);
-                hyq = t_fma(Hy[c], x[c], hyq);
-            }
-            const T vx = dzx + hxq, vy = dzy + hyq;       // z - hx + H x (:2898)
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-#pragma unroll
-                for (int b = a; b < 4; ++b)
-                    qq[sidx<4>(a, b)] = t_fma(Hx[a], Hx[b], t_fma(Hy[a], Hy[b], qq[sidx<4>(a, b)]));
-                qd1[a] += Hx[a];
-                qd2[a] += Hy[a];
-                hv[a] = t_fma(Hx[a], vx, t_fma(Hy[a], vy, hv[a]));
-            }
-            hv[4] += vx; hv[5] += vy;
-            res2 = t_fma(dzx, dzx, t_fma(dzy, dzy, res2));
-        }
-        group_sum_arr<LPP>(qq); group_sum_arr<LPP>(qd1); group_sum_arr<LPP>(qd2); group_sum_arr<LPP>(hv);
-        res2 = group_sum<LPP>(res2);
-        // ---- update: Omega += H^T Q^-1 H, zeta += H^T Q^-1 (z - hx + H x) (:2896-2898)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-#pragma unroll
-            for (int b = a; b < 4; ++b) Om[sidx<6>(a, b)] = t_fma(w, qq[sidx<4>(a, b)], Om[sidx<6>(a, b)]);
-            Om[sidx<6>(a, 4)] = t_fma(w, qd1[a], Om[sidx<6>(a, 4)]);
-            Om[sidx<6>(a, 5)] = t_fma(w, qd2[a], Om[sidx<6>(a, 5)]);
-        }
-        Om[sidx<6>(4, 4)] = t_fma(w, nT, Om[sidx<6>(4, 4)]);
-        Om[sidx<6>(5, 5)] = t_fma(w, nT, Om[sidx<6>(5, 5)]);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) zeta[a] = t_fma(w, hv[a], zeta[a]);
-        const T res_new = t_sqrt(res2);                   // :2905-2907
-        // ---- x = pinv(Omega) zeta (:2924-2925)
-        spd_inverse<T, 6>(Om);
-        T xn[6];
-        sym_matvec<T, 6>(Om, zeta, xn);
-        if (!done) {
-#pragma unroll
-            for (int e = 0; e < 21; ++e) Sig[e] = Om[e];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) x[e] = xn[e];
-            res = res_new;
-            ++iters;
-            const T ratio = (res - res_old) / res_old;    // :2945
-            res_old = res;
-            if (t_abs(ratio) < prm.exit_tol) done = true; // :2952
-        }
-    }
-    // ---- QEKF_reconstruct_R_t_m1 :3590-3605
-    T p1[3], p2[3], p3[3], gamma;
-    qekf_phi<T>(x, p1, p2, p3, gamma);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { out.R[k] = p1[k] / gamma; out.R[3 + k] = p2[k] / gamma; out.R[6 + k] = p3[k] / gamma; }
-    const T t3 = T(1) / gamma;
-    out.t[0] = x[4] * t3; out.t[1] = x[5] * t3; out.t[2] = t3;
-    out.res = res;
-    out.iters = iters;
-}
-
-// -------------------------------------------------------------------------------------------
-// LM -- solve_pnp_LM_single_pattern :2567-2769, EKF2_get_hx_H :3718-3836,
-//       EKF2_reconstruct_R_t_m1 :3500-3540
-// state x = [u1(3), u2(3), u3(3), delta_1, delta_2, gamma]
-// -------------------------------------------------------------------------------------------
 // State-independent moments of one problem's correspondences against the pattern:
 //   Mx = sum bx th th^T, My = sum by th th^T, Mw = sum (bx^2+by^2) th th^T   (packed 3x3 each)
 //   mx = sum bx th, my = sum by th, mw = sum (bx^2+by^2) th, sx0 = sum bx, sy0 = sum by
@@ -313,6 +172,213 @@ PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n,
     mom.template reduce<LPP>();
 }
 
+template <typename T>
+PNP_DEV void sym3_mv(const T (&M)[6], const T (&v)[3], T (&o)[3])
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) o[a] = M[s3(a, 0)] * v[0] + M[s3(a, 1)] * v[1] + M[s3(a, 2)] * v[2];
+}
+template <typename T>
+PNP_DEV T dot3(const T (&a)[3], const T (&b)[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// -------------------------------------------------------------------------------------------
+// QEIF -- solve_pnp_QEIF_single_pattern :2771-3025, QEKF_get_hx_H :3902-3983,
+//         QEKF_reconstruct_R_t_m1 :3542-3609
+// -------------------------------------------------------------------------------------------
+template <typename T>
+PNP_DEV void qekf_phi(const T (&x)[6], T (&p1)[3], T (&p2)[3], T (&p3)[3], T& gamma)
+{
+    const T qr = x[0], qi = x[1], qj = x[2], qk = x[3];
+    const T nq = t_sqrt(qr * qr + qi * qi + qj * qj + qk * qk);
+    gamma = nq * nq;                                      // (np.linalg.norm(q))**2 (:3918)
+    const T qii = qi * qi, qjj = qj * qj, qkk = qk * qk;
+    const T qij = qi * qj, qjk = qj * qk, qik = qi * qk;
+    const T qri = qr * qi, qrj = qr * qj, qrk = qr * qk;
+    p1[0] = gamma - 2 * (qjj + qkk); p1[1] = 2 * (qij - qrk); p1[2] = 2 * (qik + qrj);   // :3934
+    p2[0] = 2 * (qij + qrk); p2[1] = gamma - 2 * (qii + qkk); p2[2] = 2 * (qjk - qri);   // :3935
+    p3[0] = 2 * (qik - qrj); p3[1] = 2 * (qjk + qri); p3[2] = gamma - 2 * (qii + qjj);   // :3936
+}
+
+// HYBRID = false: H^T Q^-1 H and H^T Q^-1 (z - hx + H x) are accumulated point by point each
+// iteration (best for the 6-landmark subset).  HYBRID = true: they are bilinear forms of the 29
+// moments (Q_j q = 2 phi_j, so z - hx + H x = b + (P phi_1 - b o P phi_3): no cancellation), and only
+// the residual ||z - hx|| that drives the early-exit test is still evaluated point by point.
+template <typename T, int LPP, typename Pts, bool HYBRID>
+PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                        const SolverPrm<T>& prm, Result<T>& out)
+{
+    Moments<T> mom;
+    if (HYBRID) accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    T x[6] = { T(1), T(0), T(0), T(0), T(0), T(0) };      // :2831-2833
+    T Sig[21];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) Sig[e] = T(0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Sig[sidx<6>(i, i)] = prm.sigma0;   // pinv(1e-5 I) (:2836-2837)
+    T res_old = prm.res_old0, res = T(1e5);
+    bool done = false;
+    int iters = 0;
+    const T w = prm.meas_w;                               // 1 / (9 / f^2) (:2844-2852)
+    const T nT = T(n);
+
+    for (int it = 0; it < prm.max_it; ++it) {
+        if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
+        else          { if (done) break; }
+        // ---- predict: Omega = pinv(Sigma + R) (:2887), zeta = Omega x (:2889)
+        T Om[21];
+#pragma unroll
+        for (int e = 0; e < 21; ++e) Om[e] = Sig[e];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Om[sidx<6>(i, i)] += (i < 4) ? prm.proc_q : prm.proc_d;
+        spd_inverse<T, 6>(Om);
+        T zeta[6];
+        sym_matvec<T, 6>(Om, x, zeta);
+        // ---- measurement model at x (:3902-3983)
+        T p1[3], p2[3], p3[3], gamma;
+        qekf_phi<T>(x, p1, p2, p3, gamma);
+        const T r2 = 2 * x[0], i2 = 2 * x[1], j2 = 2 * x[2], k2 = 2 * x[3];
+        const T Q1[12] = { r2, i2, -j2, -k2, -k2, j2, i2, -r2, j2, k2, r2, i2 };     // :3945
+        const T Q2[12] = { k2, j2, i2, r2, r2, -i2, j2, -k2, -i2, -r2, k2, j2 };     // :3949
+        const T Q3[12] = { -j2, k2, -r2, i2, i2, r2, k2, j2, r2, -i2, -j2, k2 };     // :3953
+        T qq[10], qd1[4], qd2[4], hv[6], res2 = T(0);
+        if (!HYBRID) {
+#pragma unroll
+            for (int e = 0; e < 10; ++e) qq[e] = T(0);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { qd1[e] = T(0); qd2[e] = T(0); }
+#pragma unroll
+            for (int e = 0; e < 6; ++e) hv[e] = T(0);
+            for (int i = sub; i < n; i += LPP) {
+                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+                T bx, by;
+                pts.get(i, bx, by);
+                const T P1 = th0 * p1[0] + th1 * p1[1] + th2 * p1[2];
+                const T P2 = th0 * p2[0] + th1 * p2[1] + th2 * p2[2];
+                const T P3 = th0 * p3[0] + th1 * p3[1] + th2 * p3[2];
+                const T dzx = bx - (P1 - bx * P3 + x[4]);     // z - hx (:3969, :2905)
+                const T dzy = by - (P2 - by * P3 + x[5]);     // :3970
+                T Hx[4], Hy[4];
+                T hxq = x[4], hyq = x[5];                     // (H x) rows: Hq . q + delta
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const T a1 = th0 * Q1[c] + th1 * Q1[4 + c] + th2 * Q1[8 + c];
+                    const T a2 = th0 * Q2[c] + th1 * Q2[4 + c] + th2 * Q2[8 + c];
+                    const T a3 = th0 * Q3[c] + th1 * Q3[4 + c] + th2 * Q3[8 + c];
+                    Hx[c] = a1 - bx * a3;                     // :3979
+                    Hy[c] = a2 - by * a3;                     // :3980
+                    hxq = t_fma(Hx[c], x[c], hxq);
+                    hyq = t_fma(Hy[c], x[c], hyq);
+                }
+                const T vx = dzx + hxq, vy = dzy + hyq;       // z - hx + H x (:2898)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                    for (int b = a; b < 4; ++b)
+                        qq[sidx<4>(a, b)] = t_fma(Hx[a], Hx[b], t_fma(Hy[a], Hy[b], qq[sidx<4>(a, b)]));
+                    qd1[a] += Hx[a];
+                    qd2[a] += Hy[a];
+                    hv[a] = t_fma(Hx[a], vx, t_fma(Hy[a], vy, hv[a]));
+                }
+                hv[4] += vx; hv[5] += vy;
+                res2 = t_fma(dzx, dzx, t_fma(dzy, dzy, res2));
+            }
+            group_sum_arr<LPP>(qq); group_sum_arr<LPP>(qd1); group_sum_arr<LPP>(qd2); group_sum_arr<LPP>(hv);
+            res2 = group_sum<LPP>(res2);
+        } else {
+            // ---- residual, point by point (:2905-2907)
+#pragma unroll 4
+            for (int i = sub; i < n; i += LPP) {
+                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+                T bx, by;
+                pts.get(i, bx, by);
+                const T P1 = th0 * p1[0] + th1 * p1[1] + th2 * p1[2];
+                const T P2 = th0 * p2[0] + th1 * p2[1] + th2 * p2[2];
+                const T P3 = th0 * p3[0] + th1 * p3[1] + th2 * p3[2];
+                const T dzx = bx - (P1 - bx * P3 + x[4]);
+                const T dzy = by - (P2 - by * P3 + x[5]);
+                res2 = t_fma(dzx, dzx, t_fma(dzy, dzy, res2));
+            }
+            res2 = group_sum<LPP>(res2);
+            // ---- H^T H and H^T (z - hx + H x) from the moments
+            const T M0[6] = { sC[0], sC[1], sC[2], sC[3], sC[4], sC[5] };
+            const T m0[3] = { sC[6], sC[7], sC[8] };
+            T q1[4][3], q2[4][3], q3[4][3], a1[4][3], a2[4][3], bxv[4][3], byv[4][3], cw[4][3];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { q1[c][k] = Q1[4 * k + c]; q2[c][k] = Q2[4 * k + c]; q3[c][k] = Q3[4 * k + c]; }
+                sym3_mv<T>(M0, q1[c], a1[c]); sym3_mv<T>(M0, q2[c], a2[c]);
+                sym3_mv<T>(mom.Mx, q3[c], bxv[c]); sym3_mv<T>(mom.My, q3[c], byv[c]); sym3_mv<T>(mom.Mw, q3[c], cw[c]);
+                qd1[c] = dot3<T>(q1[c], m0) - dot3<T>(q3[c], mom.mx);
+                qd2[c] = dot3<T>(q2[c], m0) - dot3<T>(q3[c], mom.my);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int d = c; d < 4; ++d)
+                    qq[sidx<4>(c, d)] = dot3<T>(q1[c], a1[d]) + dot3<T>(q2[c], a2[d]) - (dot3<T>(q1[c], bxv[d]) + dot3<T>(q1[d], bxv[c]))
+                                        - (dot3<T>(q2[c], byv[d]) + dot3<T>(q2[d], byv[c])) + dot3<T>(q3[c], cw[d]);
+            }
+            T e1[3], e2[3], e3[3], t1[3], t2[3], t3v[3], t4[3], t5[3], t6[3], t7[3];
+            sym3_mv<T>(M0, p1, t1); sym3_mv<T>(mom.Mx, p3, t2);            // M0 phi1, Mx phi3
+            sym3_mv<T>(M0, p2, t3v); sym3_mv<T>(mom.My, p3, t4);           // M0 phi2, My phi3
+            sym3_mv<T>(mom.Mx, p1, t5); sym3_mv<T>(mom.My, p2, t6); sym3_mv<T>(mom.Mw, p3, t7);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                e1[k] = mom.mx[k] + t1[k] - t2[k];
+                e2[k] = mom.my[k] + t3v[k] - t4[k];
+                e3[k] = mom.mw[k] + t5[k] + t6[k] - t7[k];
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hv[c] = dot3<T>(q1[c], e1) + dot3<T>(q2[c], e2) - dot3<T>(q3[c], e3);
+            hv[4] = mom.sx0 + dot3<T>(m0, p1) - dot3<T>(mom.mx, p3);
+            hv[5] = mom.sy0 + dot3<T>(m0, p2) - dot3<T>(mom.my, p3);
+        }
+        // ---- update: Omega += H^T Q^-1 H, zeta += H^T Q^-1 (z - hx + H x) (:2896-2898)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = a; b < 4; ++b) Om[sidx<6>(a, b)] = t_fma(w, qq[sidx<4>(a, b)], Om[sidx<6>(a, b)]);
+            Om[sidx<6>(a, 4)] = t_fma(w, qd1[a], Om[sidx<6>(a, 4)]);
+            Om[sidx<6>(a, 5)] = t_fma(w, qd2[a], Om[sidx<6>(a, 5)]);
+        }
+        Om[sidx<6>(4, 4)] = t_fma(w, nT, Om[sidx<6>(4, 4)]);
+        Om[sidx<6>(5, 5)] = t_fma(w, nT, Om[sidx<6>(5, 5)]);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) zeta[a] = t_fma(w, hv[a], zeta[a]);
+        const T res_new = t_sqrt(res2);                   // :2905-2907
+        // ---- x = pinv(Omega) zeta (:2924-2925)
+        spd_inverse<T, 6>(Om);
+        T xn[6];
+        sym_matvec<T, 6>(Om, zeta, xn);
+        if (!done) {
+#pragma unroll
+            for (int e = 0; e < 21; ++e) Sig[e] = Om[e];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) x[e] = xn[e];
+            res = res_new;
+            ++iters;
+            const T ratio = (res - res_old) / res_old;    // :2945
+            res_old = res;
+            if (t_abs(ratio) < prm.exit_tol) done = true; // :2952
+        }
+    }
+    // ---- QEKF_reconstruct_R_t_m1 :3590-3605
+    T p1[3], p2[3], p3[3], gamma;
+    qekf_phi<T>(x, p1, p2, p3, gamma);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out.R[k] = p1[k] / gamma; out.R[3 + k] = p2[k] / gamma; out.R[6 + k] = p3[k] / gamma; }
+    const T t3 = T(1) / gamma;
+    out.t[0] = x[4] * t3; out.t[1] = x[5] * t3; out.t[2] = t3;
+    out.res = res;
+    out.iters = iters;
+}
+
+// -------------------------------------------------------------------------------------------
+// LM -- solve_pnp_LM_single_pattern :2567-2769, EKF2_get_hx_H :3718-3836,
+//       EKF2_reconstruct_R_t_m1 :3500-3540
+// state x = [u1(3), u2(3), u3(3), delta_1, delta_2, gamma]
+// -------------------------------------------------------------------------------------------
 // The gamma column of J^T J as bilinear forms of the moments (terms have the size of the result):
 //   sg1 = sum th g1 = M0 u1 - Mx u3;  sg2 = M0 u2 - My u3;  sg3 = sum th (bx g1 + by g2) = Mx u1 + My u2 - Mw u3
 //   s1 = sum g1 = m0.u1 - mx.u3;  s2 = m0.u2 - my.u3;  sgg = sum g1^2 + g2^2 = u1.sg1 + u2.sg2 - u3.sg3
