@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
         pts.idx = sel ? sIdx : nullptr;
         if (PASS == 0) {
             Moments<T> mom;
-            accumulate_moments<T, 1, PtsRow<T> >(pts, sP, a.n, 0, mom);
+            accumulate_moments<T, 1, PtsRow<T>, METHOD != PNPB200_METHOD_LINEAR_F2>(pts, sP, a.n, 0, mom);
             if (ok) {
 #pragma unroll
                 for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.B + b] = mom.at(k);
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
                 const T by = k10 * px.x + k11 * px.y + k12;
                 const T th[3] = { sP[3 * (i0 + k)], sP[3 * (i0 + k) + 1], sP[3 * (i0 + k) + 2] };
                 if (PASS == 0) {
-                    mom.add(th, bx, by);
+                    mom.template add<METHOD != PNPB200_METHOD_LINEAR_F2>(th, bx, by);
                 } else if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
                     const T aa = th[0] * x[0] + th[1] * x[1] + th[2] * x[2];
                     const T bb = th[0] * x[3] + th[1] * x[4] + th[2] * x[5];
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
         pts.row = a.uv + (size_t)b * a.n_total * 2;
         if (PASS == 0) {
             Moments<T> mom;
-            accumulate_moments<T, 32, PtsGlobal<T> >(pts, sP, a.n, lane, mom);
+            accumulate_moments<T, 32, PtsGlobal<T>, METHOD != PNPB200_METHOD_LINEAR_F2>(pts, sP, a.n, lane, mom);
             // after the butterfly every lane holds every sum: lane k writes moment k
             T mine = T(0);
 #pragma unroll

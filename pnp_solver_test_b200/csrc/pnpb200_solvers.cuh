@@ -101,9 +101,11 @@ struct Moments {
         for (int e = 0; e < 3; ++e) { mx[e] = T(0); my[e] = T(0); mw[e] = T(0); }
         sx0 = T(0); sy0 = T(0);
     }
+    // WITH_W = false skips the (bx^2 + by^2)-weighted moments, which the linear stage F2 never reads
+    template <bool WITH_W = true>
     PNP_DEV void add(const T (&th)[3], T bx, T by)
     {
-        const T ww = bx * bx + by * by;
+        const T ww = WITH_W ? (bx * bx + by * by) : T(0);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -111,19 +113,20 @@ struct Moments {
                 const T m = th[a] * th[b];
                 Mx[s3(a, b)] = t_fma(bx, m, Mx[s3(a, b)]);
                 My[s3(a, b)] = t_fma(by, m, My[s3(a, b)]);
-                Mw[s3(a, b)] = t_fma(ww, m, Mw[s3(a, b)]);
+                if (WITH_W) Mw[s3(a, b)] = t_fma(ww, m, Mw[s3(a, b)]);
             }
             mx[a] = t_fma(bx, th[a], mx[a]);
             my[a] = t_fma(by, th[a], my[a]);
-            mw[a] = t_fma(ww, th[a], mw[a]);
+            if (WITH_W) mw[a] = t_fma(ww, th[a], mw[a]);
         }
         sx0 += bx; sy0 += by;
     }
-    template <int LPP>
+    template <int LPP, bool WITH_W = true>
     PNP_DEV void reduce()
     {
-        group_sum_arr<LPP>(Mx); group_sum_arr<LPP>(My); group_sum_arr<LPP>(Mw);
-        group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my); group_sum_arr<LPP>(mw);
+        group_sum_arr<LPP>(Mx); group_sum_arr<LPP>(My);
+        group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my);
+        if (WITH_W) { group_sum_arr<LPP>(Mw); group_sum_arr<LPP>(mw); }
         sx0 = group_sum<LPP>(sx0); sy0 = group_sum<LPP>(sy0);
     }
     PNP_DEV T gMx(int k) const { return Mx[k]; }
@@ -158,7 +161,7 @@ struct MomentsRef {
     PNP_DEV T gsy0() const { return base[28 * stride]; }
 };
 
-template <typename T, int LPP, typename Pts>
+template <typename T, int LPP, typename Pts, bool WITH_W = true>
 PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n, int sub, Moments<T>& mom)
 {
     mom.zero();
@@ -167,9 +170,9 @@ PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n,
         const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
         T bx, by;
         pts.get(i, bx, by);
-        mom.add(th, bx, by);
+        mom.template add<WITH_W>(th, bx, by);
     }
-    mom.template reduce<LPP>();
+    mom.template reduce<LPP, WITH_W>();
 }
 
 template <typename T>
@@ -810,7 +813,7 @@ PNP_DEV void solve_linear_f2(const Pts& pts, const T* __restrict__ sP, const T* 
                              const SolverPrm<T>& prm, Result<T>& out)
 {
     Moments<T> mom;
-    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    accumulate_moments<T, LPP, Pts, false>(pts, sP, n, sub, mom);
     F2Tail<T> tail;
     solve_f2_from_moments<T>(mom, sC, prm, tail, out);
     out.res = f2_residual_direct<T, LPP, Pts>(pts, sP, n, sub, tail);

@@ -48,7 +48,7 @@ rows = list(csv.reader(io.StringIO(src)))
 if len(rows) > 3:
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) >= len(hdr)]
+    data = [r for r in rows[2:] if len(r) >= len(hdr) and r[ix["# Samples"]] != "# Samples"]
     byop, ex = collections.Counter(), collections.Counter()
     for r in data:
         s = r[ix["Source"]].strip()
