@@ -234,6 +234,13 @@ int pnpb200_classify(int64_t B, const double* values, int64_t stride, double sca
  */
 int pnpb200_fma_peak(int dtype, int iters, double* flops_per_s);
 
+/*
+ * Test hook: the branch-free FP64 reciprocal, reciprocal square root and square root that the
+ * solvers use for pivots and norms (csrc/pnpb200_math.cuh), element-wise on n device doubles
+ * (positive, normal).  No reference counterpart; tests/test_gpu_parity.py bounds their error.
+ */
+int pnpb200_selftest_math(int64_t n, const double* in, double* rcp, double* rsqrt, double* sqrt_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,7 +279,7 @@ PNP_DEV void project_folded(const double (&M)[9], const double (&m)[3], double x
     const double r0 = fma(M[0], x, fma(M[1], y, fma(M[2], z, m[0])));
     const double r1 = fma(M[3], x, fma(M[4], y, fma(M[5], z, m[1])));
     const double r2 = fma(M[6], x, fma(M[7], y, fma(M[8], z, m[2])));
-    const double inv = 1.0 / fabs(r2);                    // :4548 divides by |z|
+    const double inv = t_rcp<double>(fabs(r2));           // :4548 divides by |z|; branch-free, <= 0.5003 ulp
     o[0] = r0 * inv; o[1] = r1 * inv; o[2] = copysign(1.0, r2);
 }
 
@@ -330,11 +330,11 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
             const double mu = (double)px.x, mv = (double)px.y, mw = 1.0;
             double d0, d1, d2, e;
             d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];             // LM vs GT (:321)
-            e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
+            e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
             d0 = pe[0] - mu; d1 = pe[1] - mv; d2 = pe[2] - mw;             // prediction vs LM (:326)
-            e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
+            e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
             d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1]; d2 = pe[2] - pg[2];    // prediction vs GT (:331)
-            e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
+            e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
         }
         if (ok) {
             double* rp = a.report + b * PNPB200_REPORT_WIDTH;
@@ -410,11 +410,11 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
                 const double mu = (double)px.x, mv = (double)px.y, mw = 1.0;
                 double d0, d1, d2, e;
                 d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];             // LM vs GT (:321)
-                e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
+                e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
                 d0 = pe[0] - mu; d1 = pe[1] - mv; d2 = pe[2] - mw;             // prediction vs LM (:326)
-                e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
+                e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
                 d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1]; d2 = pe[2] - pg[2];    // prediction vs GT (:331)
-                e = sqrt(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
+                e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
             }
             rs.done(c, lane);
         }
@@ -604,6 +604,17 @@ __global__ void k_fma_peak(int iters, T seed, T* out)
     }
     const T s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (s == T(-12345)) out[0] = s;   // never true; keeps the chain alive
+}
+
+// the branch-free reciprocal / reciprocal square root of pnpb200_math.cuh, exposed for the tests
+__global__ void k_selftest_math(long long n_signed, const double* __restrict__ in, double* rcp, double* rsq, double* sq)
+{
+    const long long n = n_signed;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = in[i];
+    const double y = t_rsqrt<double>(a);
+    rcp[i] = t_rcp<double>(a); rsq[i] = y; sq[i] = t_sqrt_fast<double>(a, y);
 }
 
 }  // namespace pnpb200
@@ -800,6 +811,15 @@ int pnpb200_classify(int64_t B, const double* values, int64_t stride, double sca
     bn.n = n_bins;
     for (int i = 0; i < 32; ++i) bn.b[i] = (i < n_bins) ? bins[i] : 0.0;
     k_classify<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, values, stride, scale, bn, class_id);
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
+int pnpb200_selftest_math(int64_t n, const double* in, double* rcp, double* rsqrt, double* sqrt_out, void* stream)
+{
+    if (n < 0 || !in || !rcp || !rsqrt || !sqrt_out) return PNPB200_EINVAL;
+    if (n == 0) return PNPB200_OK;
+    k_selftest_math<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, in, rcp, rsqrt, sqrt_out);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

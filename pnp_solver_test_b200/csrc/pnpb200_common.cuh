@@ -5,9 +5,17 @@
 #include <stdio.h>
 #include "../../include/pnpb200.h"
 
+// workspace layout of the moment mapping: [PNP_NMOM][B] moments, [PNP_NTAIL][B] state before the last
+// update (or the F2 tail), PNP_PATC pattern constants (see pnpb200_solvers.cuh)
+#define PNP_NMOM 29
+#define PNP_NTAIL 12
+#define PNP_PATC 20
+// landmark selections up to this size travel inside the kernel arguments; larger ones through device memory
+#define PNP_MAX_INLINE_IDX 96
+
 namespace pnpb200 {
 
-void set_last_error(const char* where, cudaError_t e);   // defined in pnpb200_solve.cu
+void set_last_error(const char* where, cudaError_t e);   // defined in pnpb200_api.cu
 
 #define PNP_CUDA_OK(call)                                                   \
     do {                                                                    \
@@ -34,6 +42,54 @@ struct DeviceProps {
     int device, sm_count, cc_major, cc_minor, max_smem_optin;
     size_t total_mem;
 };
-int get_device_props(DeviceProps* out);   // cached per device; defined in pnpb200_solve.cu
+int get_device_props(DeviceProps* out);   // cached per device; defined in pnpb200_api.cu
+
+// ------------------------------------------------------------------------------------------
+// optional per-kernel timing (PNPB200_FLAG_PROFILE): a ring of event quadruples per host thread
+// ------------------------------------------------------------------------------------------
+struct ProfileRing {
+    static constexpr int kSlots = 64;
+    cudaEvent_t ev[kSlots][4];
+    int used[kSlots];     // number of events recorded in the slot (0 = empty)
+    bool created = false;
+    int next = 0, count = 0;
+    int begin()
+    {
+        if (!created) {
+            for (int s = 0; s < kSlots; ++s) {
+                for (int e = 0; e < 4; ++e) cudaEventCreate(&ev[s][e]);
+                used[s] = 0;
+            }
+            created = true;
+        }
+        const int s = next;
+        next = (next + 1) % kSlots;
+        if (count < kSlots) ++count;
+        used[s] = 0;
+        return s;
+    }
+    void mark(int slot, cudaStream_t st)
+    {
+        if (slot >= 0 && used[slot] < 4) cudaEventRecord(ev[slot][used[slot]++], st);
+    }
+};
+extern thread_local ProfileRing g_prof;            // defined in pnpb200_api.cu
+
+// ------------------------------------------------------------------------------------------
+// The templated solve path (pnpb200_kernels.cu) is compiled once per (scalar type, method group)
+// so that the objects build in parallel; pnpb200_api.cu dispatches to these entry points.
+//   group 0: QEIF, linear F1      group 1: LM, LM+      group 2: linear F2
+// ------------------------------------------------------------------------------------------
+#define PNP_SOLVE_PART_ARGS                                                                                          \
+    int method, long long B, int n_total, int n, const void *uv, const void *pattern, int n_patterns,                 \
+        const int32_t *idx_host, const int32_t *idx_dev, const double *K, const pnpb200_params &prm, void *R, void *t, \
+        void *euler, void *res, int32_t *iters, int32_t *best, cudaStream_t stream
+int solve_part_f64_g0(PNP_SOLVE_PART_ARGS);
+int solve_part_f64_g1(PNP_SOLVE_PART_ARGS);
+int solve_part_f64_g2(PNP_SOLVE_PART_ARGS);
+int solve_part_f32_g0(PNP_SOLVE_PART_ARGS);
+int solve_part_f32_g1(PNP_SOLVE_PART_ARGS);
+int solve_part_f32_g2(PNP_SOLVE_PART_ARGS);
+void fill_default_params(pnpb200_params* p);          // defined in pnpb200_api.cu
 
 }  // namespace pnpb200

@@ -1,4 +1,5 @@
-// pnpb200_solve.cu -- the hot path: batched PnP solve kernels for sm_100a and their C ABI.
+// pnpb200_kernels.cu -- the hot path: batched PnP solve kernels for sm_100a and their launchers.
+// Compiled once per (PNP_F64 = 0|1, PNP_GROUP = 0|1|2); the C ABI lives in pnpb200_api.cu.
 //
 // Two execution shapes share the solver code in pnpb200_solvers.cuh:
 //
@@ -17,92 +18,24 @@
 //                  across iterations), partial sums are combined with shuffle butterflies.
 //
 // No tensor cores on purpose: the per-problem systems are 6x6 / 12x12.
-#include <mutex>
 #include <string.h>
-#include <vector>
 
 #include "pnpb200_common.cuh"
 #include "pnpb200_solvers.cuh"
 #include "pnpb200_tile.cuh"
 
+#ifndef PNP_TUNE_VARIANTS
+#define PNP_TUNE_VARIANTS 0   // 1: also build the experimental k_iterate occupancy variants (tools/time_solve.py --tune)
+#endif
+#ifndef PNP_F64
+#error "compile with -DPNP_F64=0|1 -DPNP_GROUP=0|1|2"
+#endif
+
 namespace pnpb200 {
-
-// ------------------------------------------------------------------------------------------
-// error plumbing
-// ------------------------------------------------------------------------------------------
-static thread_local char g_last_error[512] = "";
-
-void set_last_error(const char* where, cudaError_t e)
-{
-    snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
-}
-
-int get_device_props(DeviceProps* out)
-{
-    static std::mutex mu;
-    static std::vector<DeviceProps> cache;
-    int dev = 0;
-    PNP_CUDA_OK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(mu);
-    for (const DeviceProps& p : cache)
-        if (p.device == dev) { *out = p; return PNPB200_OK; }
-    DeviceProps p;
-    p.device = dev;
-    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
-    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
-    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
-    PNP_CUDA_OK(cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    size_t free_b = 0;
-    PNP_CUDA_OK(cudaMemGetInfo(&free_b, &p.total_mem));
-    {   // keep stream-ordered scratch cached in the device's default pool instead of returning it
-        // to the driver at every synchronisation (a moment-mapping call would re-map it each time)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        cudaGetLastError();
-    }
-    cache.push_back(p);
-    *out = p;
-    return PNPB200_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// optional per-kernel timing (PNPB200_FLAG_PROFILE): a ring of event quadruples per host thread
-// ------------------------------------------------------------------------------------------
-struct ProfileRing {
-    static constexpr int kSlots = 64;
-    cudaEvent_t ev[kSlots][4];
-    int used[kSlots];     // number of events recorded in the slot (0 = empty)
-    bool created = false;
-    int next = 0, count = 0;
-    int begin()
-    {
-        if (!created) {
-            for (int s = 0; s < kSlots; ++s) {
-                for (int e = 0; e < 4; ++e) cudaEventCreate(&ev[s][e]);
-                used[s] = 0;
-            }
-            created = true;
-        }
-        const int s = next;
-        next = (next + 1) % kSlots;
-        if (count < kSlots) ++count;
-        used[s] = 0;
-        return s;
-    }
-    void mark(int slot, cudaStream_t st)
-    {
-        if (slot >= 0 && used[slot] < 4) cudaEventRecord(ev[slot][used[slot]++], st);
-    }
-};
-static thread_local ProfileRing g_prof;
 
 // ------------------------------------------------------------------------------------------
 // kernel arguments
 // ------------------------------------------------------------------------------------------
-#define PNP_MAX_INLINE_IDX 96
 // internal kernel variant: QEIF with H^T H / H^T v from the moments (chosen for n >= 12 landmarks)
 #define PNP_METHOD_QEIF_HYBRID 5
 #define PNP_QEIF_HYBRID_MIN_N 12
@@ -303,14 +236,14 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
 //   k_residual_*  uv + state before the last update -> res_norm, point by point (HBM-bound)
 // Workspace (stream-ordered allocation): mom [PNP_NMOM][B], tail [PNP_NTAIL][B], patc [PNP_PATC].
 // ------------------------------------------------------------------------------------------
-#define PNP_NTAIL 12
 
 template <typename T>
 struct MomArgs {
     const T* uv; const T* pattern; const int32_t* idx;
     int idx_mode;
     int32_t idx_inline[PNP_MAX_INLINE_IDX];
-    long long B;
+    long long B;            // problems of this launch (a slice of the call's batch)
+    long long ld;           // leading dimension of the SoA workspace arrays mom / tail (problems of the whole call)
     int n_total, n, row_pitch, use_tma;
     double kinv[6];
     SolverPrm<T> prm;
@@ -385,7 +318,7 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
         T st[PNP_NTAIL];
         if (PASS == 1) {                                  // issue the state loads before waiting on the tile
 #pragma unroll
-            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.B + b];
+            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.ld + b];
         }
         PtsRow<T> pts;
         pts.row = tile_buf.acquire(lane, valid);
@@ -395,7 +328,7 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
             accumulate_moments<T, 1, PtsRow<T>, METHOD != PNPB200_METHOD_LINEAR_F2>(pts, sP, a.n, 0, mom);
             if (ok) {
 #pragma unroll
-                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.B + b] = mom.at(k);
+                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.ld + b] = mom.at(k);
             }
         } else {
             T res;
@@ -454,7 +387,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
         else {
             T st[PNP_NTAIL];
 #pragma unroll
-            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.B + b];
+            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.ld + b];
             if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = st[k];
@@ -496,7 +429,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
         if (ok) {
             if (PASS == 0) {
 #pragma unroll
-                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.B + b] = mom.at(k);
+                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.ld + b] = mom.at(k);
             } else if (a.res) {
                 if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) a.res[b] = t_sqrt(acc0);   // :2681
                 else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
@@ -532,20 +465,20 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
             T mine = T(0);
 #pragma unroll
             for (int k = 0; k < PNP_NMOM; ++k) if (lane == k) mine = mom.at(k);
-            if (lane < PNP_NMOM) a.mom[(size_t)lane * a.B + b] = mine;
+            if (lane < PNP_NMOM) a.mom[(size_t)lane * a.ld + b] = mine;
         } else {
             T res;
             if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
                 T x[12];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) x[k] = a.tail[(size_t)k * a.B + b];
+                for (int k = 0; k < 12; ++k) x[k] = a.tail[(size_t)k * a.ld + b];
                 res = lm_residual_direct<T, 32, PtsGlobal<T> >(pts, sP, a.n, lane, x);
             } else {
                 F2Tail<T> f;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) f.phi3[k] = a.tail[(size_t)k * a.B + b];
+                for (int k = 0; k < 3; ++k) f.phi3[k] = a.tail[(size_t)k * a.ld + b];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { f.pxn[k] = a.tail[(size_t)(3 + k) * a.B + b]; f.pyn[k] = a.tail[(size_t)(7 + k) * a.B + b]; }
+                for (int k = 0; k < 4; ++k) { f.pxn[k] = a.tail[(size_t)(3 + k) * a.ld + b]; f.pyn[k] = a.tail[(size_t)(7 + k) * a.ld + b]; }
                 res = f2_residual_direct<T, 32, PtsGlobal<T> >(pts, sP, a.n, lane, f);
             }
             if (lane == 0 && a.res) a.res[b] = res;
@@ -553,12 +486,11 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
     }
 }
 
-constexpr int kIterBlock = 128;
 
-// MINB = resident blocks per SM the register allocation is bounded for (2: 255 regs, 3: 168, 4: 128)
-template <typename T, int METHOD, int MINB>
-__global__ void __launch_bounds__(kIterBlock, MINB) k_iterate(const __grid_constant__ MomArgs<T> a)
+template <typename T, int METHOD, int BLOCK>
+__device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
 {
+    constexpr int kIterBlock = BLOCK;
     __shared__ T sC[PNP_PATC];
     __shared__ T sMom[PNP_NMOM * kIterBlock];             // [moment][thread]: conflict-free columns
     if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
@@ -566,7 +498,7 @@ __global__ void __launch_bounds__(kIterBlock, MINB) k_iterate(const __grid_const
     const bool ok = b < a.B;
     if (!ok) b = a.B - 1;
 #pragma unroll
-    for (int k = 0; k < PNP_NMOM; ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.B + b];
+    for (int k = 0; k < PNP_NMOM; ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.ld + b];
     __syncthreads();
     MomentsRef<T> mom;
     mom.base = sMom + threadIdx.x;
@@ -600,7 +532,7 @@ __global__ void __launch_bounds__(kIterBlock, MINB) k_iterate(const __grid_const
     }
     if (!ok) return;
 #pragma unroll
-    for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.B + b] = st[k];
+    for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.ld + b] = st[k];
     if (a.R) {
 #pragma unroll
         for (int e = 0; e < 9; ++e) a.R[b * 9 + e] = out.R[e];
@@ -621,13 +553,34 @@ __global__ void __launch_bounds__(kIterBlock, MINB) k_iterate(const __grid_const
     if (a.best) a.best[b] = 0;
 }
 
+// Register budget per thread given directly: the 64 Ki registers of an SM hold 10 warps at 200 registers
+// (no spills for FP64 LM, which needs ~198), 12 warps at 168 (spills ~40 doubles), 8 warps at 255.
+// Measured for 1 Mi x 68 LM FP64 on B200: 1.02 ms at 200, 1.04 at 184 / 224 / 255, 1.09 at 168.
+template <typename T, int METHOD, int BLOCK, int MAXREG>
+__global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG) k_iterate(const __grid_constant__ MomArgs<T> a)
+{
+    iterate_body<T, METHOD, BLOCK>(a);
+}
+
+template <typename T, int METHOD, int BLOCK, int MAXREG>
+static void launch_iterate_as(const MomArgs<T>& m, cudaStream_t stream)
+{
+    k_iterate<T, METHOD, BLOCK, MAXREG><<<(unsigned)((m.B + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(m);
+}
+
 template <typename T, int METHOD>
 static void launch_iterate(const MomArgs<T>& m, int tune, cudaStream_t stream)
 {
-    const unsigned grid = (unsigned)((m.B + kIterBlock - 1) / kIterBlock);
-    if (tune == 2)      k_iterate<T, METHOD, 2><<<grid, kIterBlock, 0, stream>>>(m);
-    else if (tune == 4) k_iterate<T, METHOD, 4><<<grid, kIterBlock, 0, stream>>>(m);
-    else                k_iterate<T, METHOD, 3><<<grid, kIterBlock, 0, stream>>>(m);
+    switch (tune) {
+#if PNP_TUNE_VARIANTS
+    case 2:  launch_iterate_as<T, METHOD, 128, 255>(m, stream); break;   //  8 warps / SM
+    case 3:  launch_iterate_as<T, METHOD, 128, 168>(m, stream); break;   // 12 warps / SM
+    case 4:  launch_iterate_as<T, METHOD, 128, 128>(m, stream); break;   // 16 warps / SM
+    case 29: launch_iterate_as<T, METHOD, 32, 224>(m, stream); break;    //  9 warps / SM
+    case 31: launch_iterate_as<T, METHOD, 32, 184>(m, stream); break;    // 11 warps / SM
+#endif
+    default: launch_iterate_as<T, METHOD, 64, 200>(m, stream); break;    // 10 warps / SM
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -684,16 +637,6 @@ static SolverPrm<T> make_prm(const pnpb200_params& p)
     return s;
 }
 
-static void fill_default_params(pnpb200_params* p)
-{
-    p->max_it = 14; p->linear_it = 3;
-    p->lm_lambda = 1e-5; p->exit_tol = 1e-2;
-    p->f_weight = 225.68; p->meas_sigma_px = 3.0;
-    p->proc_q = 1e-1; p->proc_d = 1e-2; p->omega0 = 1e-5; p->res_old0 = 1e-7;
-    p->mapping = PNPB200_MAP_AUTO; p->flags = 0;
-    p->workspace = nullptr; p->workspace_bytes = 0;
-}
-
 static long long persistent_grid(long long work_items, int sm_count, int per_sm)
 {
     if (per_sm < 1) per_sm = 1;
@@ -701,7 +644,44 @@ static long long persistent_grid(long long work_items, int sm_count, int per_sm)
     return work_items < cap ? (work_items < 1 ? 1 : work_items) : cap;
 }
 
-// LM / linear F2 with one pattern: moments -> iterate -> residual (see the kernels' header)
+// one of the three passes over the problems [b0, b0 + nb) of the batch
+template <typename T, int METHOD>
+static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, long long nb, int shape, const StreamGeom& sg,
+                              size_t smem, int per_sm, const DeviceProps& dp, int tune, cudaStream_t stream)
+{
+    MomArgs<T> m = full;
+    m.B = nb;
+    m.uv = full.uv + (size_t)b0 * full.n_total * 2;
+    m.mom = full.mom + b0; m.tail = full.tail + b0;
+    if (full.R) m.R = full.R + b0 * 9;
+    if (full.t) m.t = full.t + b0 * 3;
+    if (full.euler) m.euler = full.euler + b0 * 3;
+    if (full.res) m.res = full.res + b0;
+    if (full.iters) m.iters = full.iters + b0;
+    if (full.best) m.best = full.best + b0;
+    if (pass == 1) { launch_iterate<T, METHOD>(m, tune, stream); return PNPB200_OK; }
+    const long long n_tiles = (nb + kTileProblems - 1) / kTileProblems;
+    const unsigned tile_grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
+    if (shape == 0) {                                         // chunked row streaming
+        m.row_pitch = sg.pitch;
+        m.use_tma = sg.chunk;                                 // RowStream: points per chunk
+        if (pass == 0) k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
+        else           k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
+    } else if (shape == 1) {                                  // whole-row tiles
+        if (pass == 0) k_stream_thread<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
+        else           k_stream_thread<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
+    } else {                                                  // one problem per warp
+        const unsigned grid = (unsigned)persistent_grid((nb + 7) / 8, dp.sm_count, per_sm);
+        if (pass == 0) k_stream_warp<T, METHOD, 0><<<grid, 256, smem, stream>>>(m);
+        else           k_stream_warp<T, METHOD, 1><<<grid, 256, smem, stream>>>(m);
+    }
+    return PNPB200_OK;
+}
+
+// LM / linear F2 with one pattern: moments -> iterate -> residual (see the kernels' header).
+// (Measured and rejected: cutting the batch into slices that flow through the three passes on
+// different streams.  The kernels do overlap, but k_iterate fills the register file, so the
+// streaming blocks displace iterate blocks instead of adding warps: same total time.)
 template <typename T, int METHOD>
 static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStream_t stream)
 {
@@ -721,54 +701,41 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     MomArgs<T> m;
     m.uv = a.uv; m.pattern = a.pattern; m.idx = a.idx; m.idx_mode = a.idx_mode;
     for (int e = 0; e < PNP_MAX_INLINE_IDX; ++e) m.idx_inline[e] = a.idx_inline[e];
-    m.B = a.B; m.n_total = a.n_total; m.n = a.n;
+    m.B = a.B; m.ld = a.B; m.n_total = a.n_total; m.n = a.n;
     m.row_pitch = g.row_pitch; m.use_tma = g.use_tma;
     for (int e = 0; e < 6; ++e) m.kinv[e] = a.kinv[e];
     m.prm = a.prm;
     m.mom = ws; m.tail = ws + (size_t)PNP_NMOM * a.B; m.patc = m.tail + (size_t)PNP_NTAIL * a.B;
     m.R = a.R; m.t = a.t; m.euler = a.euler; m.res = a.res; m.iters = a.iters; m.best = a.best;
 
-    k_pattern_constants<T><<<1, 32, 0, stream>>>(m);
-    const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
-    const int slot = a.profile ? g_prof.begin() : -1;
+    // kernel shape of the two streaming passes
     const StreamGeom sg = stream_geometry<T>(a.n_total);
-    const size_t chunk_smem = 2 * sg.buf_bytes + pat_bytes + 32;
-    const unsigned tile_grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
-    g_prof.mark(slot, stream);
+    int shape, per_sm = 1;
+    size_t smem;
     if (by_thread && !a.idx_mode && sg.use_stream && a.tune != 9) {
-        MomArgs<T> mc = m;
-        mc.row_pitch = sg.pitch;
-        mc.use_tma = sg.chunk;                                // RowStream: points per chunk
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chunk_smem));
-        k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, chunk_smem, stream>>>(mc);
-        g_prof.mark(slot, stream);
-        launch_iterate<T, METHOD>(m, a.tune, stream);
-        g_prof.mark(slot, stream);
-        if (a.res) k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, chunk_smem, stream>>>(mc);
-        g_prof.mark(slot, stream);
+        shape = 0; smem = 2 * sg.buf_bytes + pat_bytes + 32;
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else if (by_thread) {
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
-        k_stream_thread<T, METHOD, 0><<<tile_grid, 32, thread_smem, stream>>>(m);
-        g_prof.mark(slot, stream);
-        launch_iterate<T, METHOD>(m, a.tune, stream);
-        g_prof.mark(slot, stream);
-        if (a.res) k_stream_thread<T, METHOD, 1><<<tile_grid, 32, thread_smem, stream>>>(m);
-        g_prof.mark(slot, stream);
+        shape = 1; smem = thread_smem;
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
-        int per_sm = 1;
-        PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp<T, METHOD, 0>, 256, warp_smem));
-        const unsigned grid = (unsigned)persistent_grid((a.B + 7) / 8, dp.sm_count, per_sm);
-        k_stream_warp<T, METHOD, 0><<<grid, 256, warp_smem, stream>>>(m);
-        g_prof.mark(slot, stream);
-        launch_iterate<T, METHOD>(m, a.tune, stream);
-        g_prof.mark(slot, stream);
-        if (a.res) k_stream_warp<T, METHOD, 1><<<grid, 256, warp_smem, stream>>>(m);
-        g_prof.mark(slot, stream);
+        shape = 2; smem = warp_smem;
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp<T, METHOD, 0>, 256, smem));
     }
+
+    k_pattern_constants<T><<<1, 32, 0, stream>>>(m);
+    const int slot = a.profile ? g_prof.begin() : -1;
+    g_prof.mark(slot, stream);
+    launch_moment_pass<T, METHOD>(0, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    g_prof.mark(slot, stream);
+    launch_moment_pass<T, METHOD>(1, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    g_prof.mark(slot, stream);
+    if (a.res) launch_moment_pass<T, METHOD>(2, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    g_prof.mark(slot, stream);
     PNP_CUDA_OK(cudaGetLastError());
     if (own_ws) PNP_CUDA_OK(cudaFreeAsync(ws, stream));
     return PNPB200_OK;
@@ -840,15 +807,16 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     a.prm = make_prm<T>(prm);
     a.R = (T*)R; a.t = (T*)t; a.euler = (T*)euler; a.res = (T*)res; a.iters = iters; a.best = best;
     a.profile = (prm.flags & PNPB200_FLAG_PROFILE) ? 1 : 0;
-    a.tune = (prm.flags >> 8) & 0xff;                     // undocumented tuning knob (register budget of k_iterate)
+    a.tune = (prm.flags >> 8) & 0xff;                     // undocumented tuning knob (register budget of k_iterate, slice size)
     a.ws = prm.workspace; a.ws_bytes = (prm.workspace && prm.workspace_bytes > 0) ? (size_t)prm.workspace_bytes : 0;
     switch (method) {
+#if PNP_GROUP == 0
     case PNPB200_METHOD_QEIF:
         if (n >= PNP_QEIF_HYBRID_MIN_N && !(prm.flags & PNPB200_FLAG_QEIF_DIRECT)) return launch_solve<T, PNP_METHOD_QEIF_HYBRID>(a, prm.mapping, stream);
         return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);
-    case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
-    case PNPB200_METHOD_LINEAR_F2: return launch_solve<T, PNPB200_METHOD_LINEAR_F2>(a, prm.mapping, stream);
     case PNPB200_METHOD_LINEAR_F1: return launch_solve<T, PNPB200_METHOD_LINEAR_F1>(a, prm.mapping, stream);
+#elif PNP_GROUP == 1
+    case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
     case PNPB200_METHOD_LM_PLUS: {
         // non-parity extra: exists in the moment mapping only, one pattern
         if (n_patterns != 1 || (prm.mapping != PNPB200_MAP_AUTO && prm.mapping != PNPB200_MAP_MOMENT)) return PNPB200_EINVAL;
@@ -857,208 +825,27 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
         if (rc != PNPB200_OK) return rc;
         return launch_moment<T, PNPB200_METHOD_LM_PLUS>(a, dp, stream);
     }
+#else
+    case PNPB200_METHOD_LINEAR_F2: return launch_solve<T, PNPB200_METHOD_LINEAR_F2>(a, prm.mapping, stream);
+#endif
     default: return PNPB200_EINVAL;
     }
 }
 
+#define PNP_CAT3_(a, b, c) a##b##c
+#define PNP_CAT3(a, b, c) PNP_CAT3_(a, b, c)
+#if PNP_F64
+#define PNP_PART_NAME PNP_CAT3(solve_part_f64_g, PNP_GROUP, )
+typedef double part_scalar;
+#else
+#define PNP_PART_NAME PNP_CAT3(solve_part_f32_g, PNP_GROUP, )
+typedef float part_scalar;
+#endif
+
+int PNP_PART_NAME(PNP_SOLVE_PART_ARGS)
+{
+    return solve_typed<part_scalar>(method, B, n_total, n, uv, pattern, n_patterns, idx_host, idx_dev, K, prm, R, t, euler, res,
+                                    iters, best, stream);
+}
+
 }  // namespace pnpb200
-
-using namespace pnpb200;
-
-extern "C" {
-
-int pnpb200_version(void) { return PNPB200_VERSION; }
-const char* pnpb200_last_error(void) { return g_last_error; }
-
-int pnpb200_default_params(pnpb200_params* p)
-{
-    if (!p) return PNPB200_EINVAL;
-    fill_default_params(p);
-    return PNPB200_OK;
-}
-
-int pnpb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes)
-{
-    DeviceProps dp;
-    int rc = get_device_props(&dp);
-    if (rc != PNPB200_OK) return rc;
-    if (sm_count) *sm_count = dp.sm_count;
-    if (cc_major) *cc_major = dp.cc_major;
-    if (cc_minor) *cc_minor = dp.cc_minor;
-    if (hbm_bytes) *hbm_bytes = (int64_t)dp.total_mem;
-    return PNPB200_OK;
-}
-
-int pnpb200_profile_reset(void)
-{
-    g_prof.next = 0; g_prof.count = 0;
-    if (g_prof.created)
-        for (int s = 0; s < ProfileRing::kSlots; ++s) g_prof.used[s] = 0;
-    return PNPB200_OK;
-}
-
-int pnpb200_profile_read(float* ms, int* n_calls)
-{
-    if (!ms) return PNPB200_EINVAL;
-    double acc[3] = { 0, 0, 0 };
-    int calls = 0;
-    for (int s = 0; s < g_prof.count && g_prof.created; ++s) {
-        const int u = g_prof.used[s];
-        if (u < 2) continue;
-        PNP_CUDA_OK(cudaEventSynchronize(g_prof.ev[s][u - 1]));
-        for (int k = 0; k + 1 < u; ++k) {
-            float t = 0.f;
-            PNP_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[s][k], g_prof.ev[s][k + 1]));
-            acc[k] += t;
-        }
-        ++calls;
-    }
-    for (int k = 0; k < 3; ++k) ms[k] = calls ? (float)(acc[k] / calls) : 0.f;
-    if (n_calls) *n_calls = calls;
-    return PNPB200_OK;
-}
-
-int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping)
-{
-    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS) && n_patterns == 1;
-    if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
-    const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
-    return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
-}
-
-int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
-                        int n_patterns, const int32_t* point_index, const double* K, const pnpb200_params* params,
-                        void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters, int32_t* best_pattern,
-                        void* stream)
-{
-    if (B < 0 || n_total < 1 || n < 1 || (!point_index && n != n_total) || !uv || !pattern || !K) return PNPB200_EINVAL;
-    if (n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
-    if (method < 0 || method > 4 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
-    if (B == 0) return PNPB200_OK;
-    pnpb200_params prm;
-    if (params) prm = *params; else fill_default_params(&prm);
-    cudaStream_t st = (cudaStream_t)stream;
-    int32_t* idx_dev = nullptr;
-    if (point_index) {
-        for (int i = 0; i < n; ++i)
-            if (point_index[i] < 0 || point_index[i] >= n_total) return PNPB200_EINVAL;
-        if (n > PNP_MAX_INLINE_IDX) {   // large selections go through device memory; small ones ride in the kernel arguments
-            PNP_CUDA_OK(cudaMallocAsync((void**)&idx_dev, sizeof(int32_t) * (size_t)n, st));
-            PNP_CUDA_OK(cudaMemcpyAsync(idx_dev, point_index, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-        }
-    }
-    int rc;
-    if (dtype == PNPB200_DTYPE_F64)
-        rc = solve_typed<double>(method, B, n_total, n, uv, pattern, n_patterns, point_index, idx_dev, K, prm, R, t, euler_deg,
-                                 res_norm, iters, best_pattern, st);
-    else
-        rc = solve_typed<float>(method, B, n_total, n, uv, pattern, n_patterns, point_index, idx_dev, K, prm, R, t, euler_deg,
-                                res_norm, iters, best_pattern, st);
-    if (idx_dev) cudaFreeAsync(idx_dev, st);
-    return rc;
-}
-
-// ------------------------------------------------------------------------------------------
-// host-buffer entry point: chunked, multi-stream H2D -> solve -> D2H pipeline
-// ------------------------------------------------------------------------------------------
-struct pnpb200_pipeline {
-    int dtype, n_total, n_patterns, n_streams;
-    int64_t chunk;
-    size_t esz;
-    std::vector<cudaStream_t> streams;
-    std::vector<void*> d_uv, d_R, d_t, d_e, d_res;
-    std::vector<int32_t*> d_it, d_best;
-    std::vector<void*> d_ws;
-    size_t ws_bytes;
-    void* d_pattern;
-};
-
-int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_problems, int n_total, int n_patterns,
-                            int n_streams)
-{
-    if (!out || chunk_problems < 1 || n_total < 1 || n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
-    if (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32) return PNPB200_EINVAL;
-    if (n_streams < 1) n_streams = 3;
-    pnpb200_pipeline* p = new pnpb200_pipeline();
-    p->dtype = dtype; p->n_total = n_total; p->n_patterns = n_patterns; p->n_streams = n_streams;
-    p->chunk = chunk_problems;
-    p->esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
-    p->d_pattern = nullptr;
-    p->ws_bytes = ((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)chunk_problems + PNP_PATC) * p->esz;
-    *out = p;
-    PNP_CUDA_OK(cudaMalloc(&p->d_pattern, p->esz * (size_t)n_patterns * n_total * 3));
-    for (int s = 0; s < n_streams; ++s) {
-        cudaStream_t st;
-        PNP_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        p->streams.push_back(st);
-        void *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr, *e = nullptr, *f = nullptr, *g = nullptr;
-        PNP_CUDA_OK(cudaMalloc(&a, p->esz * (size_t)chunk_problems * n_total * 2)); p->d_uv.push_back(a);
-        PNP_CUDA_OK(cudaMalloc(&b, p->esz * (size_t)chunk_problems * 9)); p->d_R.push_back(b);
-        PNP_CUDA_OK(cudaMalloc(&c, p->esz * (size_t)chunk_problems * 3)); p->d_t.push_back(c);
-        PNP_CUDA_OK(cudaMalloc(&d, p->esz * (size_t)chunk_problems * 3)); p->d_e.push_back(d);
-        PNP_CUDA_OK(cudaMalloc(&e, p->esz * (size_t)chunk_problems)); p->d_res.push_back(e);
-        PNP_CUDA_OK(cudaMalloc(&f, sizeof(int32_t) * (size_t)chunk_problems)); p->d_it.push_back((int32_t*)f);
-        PNP_CUDA_OK(cudaMalloc(&g, sizeof(int32_t) * (size_t)chunk_problems)); p->d_best.push_back((int32_t*)g);
-        void* w = nullptr;
-        PNP_CUDA_OK(cudaMalloc(&w, p->ws_bytes)); p->d_ws.push_back(w);
-    }
-    return PNPB200_OK;
-}
-
-int pnpb200_pipeline_destroy(pnpb200_pipeline* p)
-{
-    if (!p) return PNPB200_EINVAL;
-    for (cudaStream_t st : p->streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-    for (void* q : p->d_uv) cudaFree(q);
-    for (void* q : p->d_R) cudaFree(q);
-    for (void* q : p->d_t) cudaFree(q);
-    for (void* q : p->d_e) cudaFree(q);
-    for (void* q : p->d_res) cudaFree(q);
-    for (int32_t* q : p->d_it) cudaFree(q);
-    for (int32_t* q : p->d_best) cudaFree(q);
-    for (void* q : p->d_ws) cudaFree(q);
-    if (p->d_pattern) cudaFree(p->d_pattern);
-    delete p;
-    return PNPB200_OK;
-}
-
-int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, const void* uv_host,
-                             const void* pattern_host, const int32_t* point_index, const double* K,
-                             const pnpb200_params* params, void* R, void* t, void* euler_deg, void* res_norm,
-                             int32_t* iters, int32_t* best_pattern)
-{
-    if (!p || !uv_host || !pattern_host || !K || B < 0) return PNPB200_EINVAL;
-    const size_t esz = p->esz;
-    PNP_CUDA_OK(cudaMemcpyAsync(p->d_pattern, pattern_host, esz * (size_t)p->n_patterns * p->n_total * 3,
-                                cudaMemcpyHostToDevice, p->streams[0]));
-    PNP_CUDA_OK(cudaStreamSynchronize(p->streams[0]));
-    int64_t done = 0;
-    int s = 0;
-    while (done < B) {
-        const int64_t nb = (B - done < p->chunk) ? (B - done) : p->chunk;
-        cudaStream_t st = p->streams[s];
-        const char* src = (const char*)uv_host + esz * (size_t)done * p->n_total * 2;
-        PNP_CUDA_OK(cudaMemcpyAsync(p->d_uv[s], src, esz * (size_t)nb * p->n_total * 2, cudaMemcpyHostToDevice, st));
-        pnpb200_params prm;
-        if (params) prm = *params; else fill_default_params(&prm);
-        if (!prm.workspace) { prm.workspace = p->d_ws[s]; prm.workspace_bytes = (int64_t)p->ws_bytes; }
-        int rc = pnpb200_solve_batch(method, p->dtype, nb, p->n_total, n, p->d_uv[s], p->d_pattern, p->n_patterns,
-                                     point_index, K, &prm, R ? p->d_R[s] : nullptr, t ? p->d_t[s] : nullptr,
-                                     euler_deg ? p->d_e[s] : nullptr, res_norm ? p->d_res[s] : nullptr,
-                                     iters ? p->d_it[s] : nullptr, best_pattern ? p->d_best[s] : nullptr, st);
-        if (rc != PNPB200_OK) return rc;
-        if (R) PNP_CUDA_OK(cudaMemcpyAsync((char*)R + esz * (size_t)done * 9, p->d_R[s], esz * (size_t)nb * 9, cudaMemcpyDeviceToHost, st));
-        if (t) PNP_CUDA_OK(cudaMemcpyAsync((char*)t + esz * (size_t)done * 3, p->d_t[s], esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
-        if (euler_deg) PNP_CUDA_OK(cudaMemcpyAsync((char*)euler_deg + esz * (size_t)done * 3, p->d_e[s], esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
-        if (res_norm) PNP_CUDA_OK(cudaMemcpyAsync((char*)res_norm + esz * (size_t)done, p->d_res[s], esz * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (iters) PNP_CUDA_OK(cudaMemcpyAsync(iters + done, p->d_it[s], sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (best_pattern) PNP_CUDA_OK(cudaMemcpyAsync(best_pattern + done, p->d_best[s], sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        done += nb;
-        s = (s + 1) % p->n_streams;
-        // a stream's buffers are reused n_streams chunks later; stream order protects them
-    }
-    for (cudaStream_t st : p->streams) PNP_CUDA_OK(cudaStreamSynchronize(st));
-    return PNPB200_OK;
-}
-
-}  // extern "C"

@@ -20,10 +20,50 @@ PNP_DEV constexpr int sym(int i, int j) { return i <= j ? sidx<N>(i, j) : sidx<N
 template <typename T> PNP_DEV T t_sqrt(T x);
 template <> PNP_DEV double t_sqrt<double>(double x) { return sqrt(x); }
 template <> PNP_DEV float t_sqrt<float>(float x) { return sqrtf(x); }
-// correctly rounded reciprocal without the slow-path branches of operator/ (MUFU.RCP64H + Newton)
+// Branch-free reciprocal and reciprocal square root for normal, finite, non-zero arguments (pivots
+// of SPD systems, squared norms).  The CUDA library versions (1.0 / x, __drcp_rn, sqrt) carry a
+// slow-path branch for denormals and the exponent extremes; inside the fully unrolled 10 x 10
+// factorisation every such branch ends a basic block and stops ptxas from scheduling the seed and
+// its Newton steps in the shadow of the independent trailing updates.  Seed: MUFU.RCP64H /
+// MUFU.RSQ64H (about 2^-20 relative); one third-order step brings it to ~2^-60 before rounding
+// (faithfully rounded, not correctly rounded; verified on the device by
+// tests/test_gpu_parity.py::test_fast_reciprocals).
 template <typename T> PNP_DEV T t_rcp(T x);
-template <> PNP_DEV double t_rcp<double>(double x) { return __drcp_rn(x); }
+template <> PNP_DEV double t_rcp<double>(double a)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    e = fma(e, e, e);                                     // e + e^2
+    return fma(x, e, x);                                  // x (1 + e + e^2): error e^3 ~ 2^-60, <= 0.5003 ulp measured
+}
 template <> PNP_DEV float t_rcp<float>(float x) { return __frcp_rn(x); }
+// 1 / sqrt(a)
+template <typename T> PNP_DEV T t_rsqrt(T x);
+template <> PNP_DEV double t_rsqrt<double>(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double ha = 0.5 * a;
+    double e = fma(-ha * y, y, 0.5);                      // (1 - a y^2) / 2
+    return fma(y, fma(1.5 * e, e, e), y);                 // y (1 + e' / 2 + 3 e'^2 / 8), e' = 2 e: third order
+}
+template <> PNP_DEV float t_rsqrt<float>(float x) { return rsqrtf(x); }
+// sqrt(a) = a / sqrt(a) with one correction step (a > 0, normal)
+template <typename T> PNP_DEV T t_sqrt_fast(T a, T rs);   // rs = t_rsqrt(a)
+template <> PNP_DEV double t_sqrt_fast<double>(double a, double rs)
+{
+    const double s = a * rs;
+    return fma(fma(-s, s, a), 0.5 * rs, s);
+}
+template <> PNP_DEV float t_sqrt_fast<float>(float a, float rs) { return sqrtf(a); }
+// branch-free sqrt for a >= 0 including exact zeros (distances): the seed sees max(a, 2^-1000), so
+// a = 0 gives 0 * finite = 0
+PNP_DEV double sqrt_nonneg(double a)
+{
+    const double rs = t_rsqrt<double>(fmax(a, 9.3326361850321888e-302));
+    return t_sqrt_fast<double>(a, rs);
+}
 template <typename T> PNP_DEV T t_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> PNP_DEV T t_fma(T a, T b, T c);
 template <> PNP_DEV double t_fma<double>(double a, double b, double c) { return fma(a, b, c); }
@@ -39,11 +79,18 @@ PNP_DEV void ldlt_factor(T (&A)[N * (N + 1) / 2])
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const T inv = t_rcp<T>(A[sidx<N>(j, j)]);
+        // The next pivot is the serial chain of the factorisation (rcp -> scale -> update -> rcp ...):
+        // its update uses a^2 / d, whose square does not wait for the reciprocal.
+        if (j + 1 < N) {
+            const T a = A[sidx<N>(j, j + 1)];
+            A[sidx<N>(j + 1, j + 1)] = t_fma(-(a * a), inv, A[sidx<N>(j + 1, j + 1)]);
+        }
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             const T lij = A[sidx<N>(j, i)] * inv;
 #pragma unroll
-            for (int r = i; r < N; ++r) A[sidx<N>(i, r)] = t_fma(-lij, A[sidx<N>(j, r)], A[sidx<N>(i, r)]);
+            for (int r = i; r < N; ++r)
+                if (!(i == j + 1 && r == j + 1)) A[sidx<N>(i, r)] = t_fma(-lij, A[sidx<N>(j, r)], A[sidx<N>(i, r)]);
             A[sidx<N>(j, i)] = lij;
         }
         A[sidx<N>(j, j)] = inv;
@@ -63,8 +110,10 @@ PNP_DEV void ldlt_solve(const T (&A)[N * (N + 1) / 2], T (&b)[N])
     for (int j = 0; j < N; ++j) b[j] *= A[sidx<N>(j, j)];
 #pragma unroll
     for (int j = N - 1; j >= 0; --j) {
+        // oldest unknowns first: the one computed last (b[j+1]) enters last, so the dependent chain
+        // through the back substitution is N FMAs long instead of N (N - 1) / 2
 #pragma unroll
-        for (int i = j + 1; i < N; ++i) b[j] = t_fma(-A[sidx<N>(j, i)], b[i], b[j]);
+        for (int i = N - 1; i > j; --i) b[j] = t_fma(-A[sidx<N>(j, i)], b[i], b[j]);
     }
 }
 

@@ -13,6 +13,7 @@
 // terms that actually depend on the state: every block of J^T J that is the state-independent
 // moment of the correspondences times a power of gamma is accumulated once per problem.
 #pragma once
+#include "pnpb200_common.cuh"
 #include "pnpb200_math.cuh"
 
 namespace pnpb200 {
@@ -32,7 +33,7 @@ struct Result {
 // per-pattern constants kept in shared memory (computed once per CTA)
 //   [0..5] M0 = sum theta theta^T (packed 3x3)   [6..8] m0 = sum theta   [9] n
 //   [10..19] G = (D^T D)^-1, D = [P | 1]  (packed 4x4; f2_get_D_pinv :3283 is G D^T)
-#define PNP_PATC 20
+// PNP_PATC (= 20) is defined in pnpb200_common.cuh
 
 template <int LPP, typename T>
 PNP_DEV T group_sum(T v)
@@ -89,7 +90,7 @@ PNP_DEV void block_reconstruct(const T (&phi)[8], T (&R)[9], T (&t)[3], T& t3)
 //   mx = sum bx th, my = sum by th, mw = sum (bx^2+by^2) th, sx0 = sum bx, sy0 = sum by
 // Every block of J^T J of the LM problem is one of these (or the pattern constants M0, m0, n)
 // times a power of gamma, and so are the sums of the linear stage F2 (its D^T B and D^T (B o P)).
-#define PNP_NMOM 29
+// PNP_NMOM (= 29) is defined in pnpb200_common.cuh
 template <typename T>
 struct Moments {
     T Mx[6], My[6], Mw[6], mx[3], my[3], mw[3], sx0, sy0;
@@ -486,10 +487,11 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
         for (int b = a; b < 3; ++b) {
-            const T m0 = gg2 * sC[s3(a, b)];
+            const T lam = (a == b) ? lambda : T(0);        // + lambda I (:2667)
+            const T m0 = t_fma(gg2, sC[s3(a, b)], lam);
             A[sidx<10>(U1 + a, U1 + b)] = m0;
             A[sidx<10>(U2 + a, U2 + b)] = m0;
-            A[sidx<10>(U3 + a, U3 + b)] = gg2 * m.gMw(s3(a, b));
+            A[sidx<10>(U3 + a, U3 + b)] = t_fma(gg2, m.gMw(s3(a, b)), lam);
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
@@ -502,7 +504,7 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         A[sidx<10>(U3 + a, GG)] = -gam * gc.sg3[a];
         g[U1 + a] = gam * r.r1[a]; g[U2 + a] = gam * r.r2[a]; g[U3 + a] = -gam * r.r3[a];
     }
-    A[sidx<10>(GG, GG)] = gc.sgg;
+    A[sidx<10>(GG, GG)] = gc.sgg + lambda;
     g[GG] = r.qg;
     // ---- eliminate delta_1 (column [gam m0; 0; -gam mx; s1]) and delta_2 ([0; gam m0; -gam my; s2])
     const T ip = t_rcp<T>(sC[9] + lambda);
@@ -537,7 +539,9 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         const T u13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
         const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
         const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
-        const T n1 = t_sqrt(u11), n2 = t_sqrt(u22), n3 = t_sqrt(u33);
+        // |u| and 1 / (kn |u|) from one reciprocal square root each
+        const T y1 = t_rsqrt<T>(u11), y2 = t_rsqrt<T>(u22), y3 = t_rsqrt<T>(u33);
+        const T n1 = t_sqrt_fast<T>(u11, y1), n2 = t_sqrt_fast<T>(u22, y2), n3 = t_sqrt_fast<T>(u33, y3);
         constexpr T kq = TRUE_JAC ? T(2) : T(1), kn = TRUE_JAC ? T(1) : T(2);
         const T pu1[3] = { kq * u1[0], kq * u1[1], kq * u1[2] }, pu2[3] = { kq * u2[0], kq * u2[1], kq * u2[2] };
         const T nu2[3] = { -kq * u2[0], -kq * u2[1], -kq * u2[2] }, nu3[3] = { -kq * u3[0], -kq * u3[1], -kq * u3[2] };
@@ -547,7 +551,7 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         add_outer2<T, U1, U3>(A, g, pu1, nu3, T(0) - (u11 - u33)); // reference rows use u, not 2u (:3808)
         add_outer2<T, U2, U3>(A, g, pu2, nu3, T(0) - (u22 - u33));
         add_outer2<T, U1, U2>(A, g, pu1, nu2, T(0) - (u11 - u22));
-        const T h1 = t_rcp<T>(kn * n1), h2 = t_rcp<T>(kn * n2), h3 = t_rcp<T>(kn * n3);
+        const T h1 = y1 * (T(1) / kn), h2 = y2 * (T(1) / kn), h3 = y3 * (T(1) / kn);
         const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
         const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
         const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
@@ -555,16 +559,15 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         add_outer1<T, U2>(A, g, j2, T(1) - n2);
         add_outer1<T, U3>(A, g, j3, T(1) - n3);
     }
-#pragma unroll
-    for (int i = 0; i < 10; ++i) A[sidx<10>(i, i)] += lambda;
     ldlt_factor<T, 10>(A);
     ldlt_solve<T, 10>(A, g);
     // ---- back-substitute the two deltas: d_k = (rhs_k - column_k . dx) / (n + lambda)
     T e1 = r.q1, e2 = r.q2;
     {
         constexpr int i1[7] = { 0, 1, 2, 6, 7, 8, 9 }, i2[7] = { 3, 4, 5, 6, 7, 8, 9 };
+        // the back substitution delivers g[9] first and g[0] last: consume them in that order
 #pragma unroll
-        for (int p = 0; p < 7; ++p) { e1 = t_fma(-c1[p], g[i1[p]], e1); e2 = t_fma(-c2[p], g[i2[p]], e2); }
+        for (int p = 6; p >= 0; --p) { e1 = t_fma(-c1[p], g[i1[p]], e1); e2 = t_fma(-c2[p], g[i2[p]], e2); }
     }
     T step = T(0);
 #pragma unroll

@@ -276,3 +276,24 @@ def test_lm_plus_nonparity_mode_converges_and_matches_its_oracle():
     assert float(ok.double().mean()) > 0.95 and float(err[ok].median()) < 1e-9
     with pytest.raises(pnp.PnpB200Error):                      # moment mapping only
         pnp.solve_batch("lm_plus", w["uv"][:64], dev(P)[None], K, params=pnp.default_params(mapping=MAP_THREAD))
+
+
+def test_fast_reciprocals():
+    """The branch-free rcp / rsqrt / sqrt of csrc/pnpb200_math.cuh (pivots, norms) are within 1 ulp."""
+    import ctypes as C
+    from pnp_solver_test_b200 import _lib
+    rng = np.random.default_rng(5)
+    a = np.concatenate([rng.uniform(0.5, 2.0, 100000), 10.0 ** rng.uniform(-250, 250, 100000),
+                        np.array([1.0, 2.0, 4.0, 0.25, 3.0, 1e-300, 1e300])])
+    x = dev(a)
+    o = [torch.empty_like(x) for _ in range(3)]
+    _lib.check(_lib.lib.pnpb200_selftest_math(C.c_int64(a.size), C.c_void_p(x.data_ptr()), C.c_void_p(o[0].data_ptr()),
+                                              C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr()), None),
+               "pnpb200_selftest_math")
+    torch.cuda.synchronize()
+    rcp, rsq, sq = (t.cpu().numpy() for t in o)
+    ulp = 2.0 ** -52
+    al = a.astype(np.longdouble)
+    assert np.abs(rcp * al - 1).max() <= 1.01 * ulp
+    assert np.abs(rsq.astype(np.longdouble) ** 2 * al - 1).max() <= 2.5 * ulp
+    assert np.abs(sq.astype(np.longdouble) / np.sqrt(al) - 1).max() <= 1.01 * ulp

@@ -25,6 +25,7 @@ ap.add_argument("--tune", default="0")
 ap.add_argument("--dtype", default="f64")
 ap.add_argument("--subset6", action="store_true")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--noprof", action="store_true", help="no per-kernel events (the sliced pipeline only runs without them)")
 args = ap.parse_args()
 
 dt = torch.float64 if args.dtype == "f64" else torch.float32
@@ -35,8 +36,9 @@ w = wl.synth_batch(0, args.B, P, K, dtype=dt)
 patd = torch.from_numpy(P).cuda().to(dt)[None]
 idx = [list(pat).index(k) for k in pt.LM_KEY_LIST_6] if args.subset6 else None
 for mapping in [int(x) for x in args.mapping.split(",")]:
+  for sl in [0]:
     for tune in [int(x) for x in args.tune.split(",")]:
-        prm = pnp.default_params(mapping=mapping, flags=_lib.FLAG_PROFILE | (tune << 8))
+        prm = pnp.default_params(mapping=mapping, flags=(0 if args.noprof else _lib.FLAG_PROFILE) | (tune << 8))
         for _ in range(3):
             pnp.solve_batch(args.method, w["uv"], patd, K, point_index=idx, params=prm)
         torch.cuda.synchronize()
@@ -51,6 +53,6 @@ for mapping in [int(x) for x in args.mapping.split(",")]:
         nc = C.c_int()
         _lib.lib.pnpb200_profile_read(ms, C.byref(nc))
         tot = e0.elapsed_time(e1) / args.reps
-        print("method=%s n=%d B=%d dtype=%s mapping=%d tune=%d: total %.3f ms (%.3e solves/s) kernels [%.3f %.3f %.3f] ms  mean iters %.2f"
-              % (args.method, args.n, args.B, args.dtype, mapping, tune, tot, args.B / tot * 1e3, ms[0], ms[1], ms[2],
+        print("method=%s n=%d B=%d dtype=%s mapping=%d tune=%d slice=%d: total %.3f ms (%.3e solves/s) kernels [%.3f %.3f %.3f] ms  mean iters %.2f"
+              % (args.method, args.n, args.B, args.dtype, mapping, tune, sl, tot, args.B / tot * 1e3, ms[0], ms[1], ms[2],
                  float(out["iters"].double().mean())), flush=True)
