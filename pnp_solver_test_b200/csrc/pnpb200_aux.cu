@@ -274,13 +274,30 @@ PNP_DEV void fold_camera(const double* K, const double (&R)[9], const double (&t
     }
 }
 
-PNP_DEV void project_folded(const double (&M)[9], const double (&m)[3], double x, double y, double z, double (&o)[3])
+// o = (u, v); behind = the homogeneous coordinate z / |z| is -1 (the point is behind the camera)
+PNP_DEV void project_folded(const double (&M)[9], const double (&m)[3], double x, double y, double z, double (&o)[2], bool& behind)
 {
     const double r0 = fma(M[0], x, fma(M[1], y, fma(M[2], z, m[0])));
     const double r1 = fma(M[3], x, fma(M[4], y, fma(M[5], z, m[1])));
     const double r2 = fma(M[6], x, fma(M[7], y, fma(M[8], z, m[2])));
     const double inv = t_rcp<double>(fabs(r2));           // :4548 divides by |z|; branch-free, <= 0.5003 ulp
-    o[0] = r0 * inv; o[1] = r1 * inv; o[2] = copysign(1.0, r2);
+    o[0] = r0 * inv; o[1] = r1 * inv;
+    behind = __double2hiint(r2) < 0;
+}
+
+// The three error distances of one landmark (cal_LM_error_distances, TEST_TOOLBOX.py:252-286).  The
+// third component of every difference is a difference of homogeneous coordinates that are exactly +-1
+// (the measured one is +1), so its square is 0 or 4.
+PNP_DEV void landmark_errors(const double (&pe)[2], bool be, const double (&pg)[2], bool bg, double mu, double mv,
+                             double& e0, double& e1, double& e2)
+{
+    double d0, d1;
+    d0 = mu - pg[0]; d1 = mv - pg[1];                          // LM vs GT (:321)
+    e0 = sqrt_nonneg(fma(d0, d0, fma(d1, d1, bg ? 4.0 : 0.0)));
+    d0 = pe[0] - mu; d1 = pe[1] - mv;                          // prediction vs LM (:326)
+    e1 = sqrt_nonneg(fma(d0, d0, fma(d1, d1, be ? 4.0 : 0.0)));
+    d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1];                    // prediction vs GT (:331)
+    e2 = sqrt_nonneg(fma(d0, d0, fma(d1, d1, (be != bg) ? 4.0 : 0.0)));
 }
 
 template <typename T>
@@ -323,18 +340,15 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
         int i0 = -1, i1 = -1, i2 = -1;
         for (int i = 0; i < a.n; ++i) {
             const double x = (double)sP[3 * i], y = (double)sP[3 * i + 1], z = (double)sP[3 * i + 2];
-            double pe[3], pg[3];
-            project_folded(Me, me, x, y, z, pe);          // TEST_TOOLBOX.py:312
-            project_folded(Mg, mg, x, y, z, pg);          // :314
+            double pe[2], pg[2], e0, e1, e2;
+            bool be, bg;
+            project_folded(Me, me, x, y, z, pe, be);      // TEST_TOOLBOX.py:312
+            project_folded(Mg, mg, x, y, z, pg, bg);      // :314
             const V2 px = row[i];
-            const double mu = (double)px.x, mv = (double)px.y, mw = 1.0;
-            double d0, d1, d2, e;
-            d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];             // LM vs GT (:321)
-            e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
-            d0 = pe[0] - mu; d1 = pe[1] - mv; d2 = pe[2] - mw;             // prediction vs LM (:326)
-            e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
-            d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1]; d2 = pe[2] - pg[2];    // prediction vs GT (:331)
-            e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
+            landmark_errors(pe, be, pg, bg, (double)px.x, (double)px.y, e0, e1, e2);
+            s0 += e0; if (e0 > m0) { m0 = e0; i0 = i; }
+            s1 += e1; if (e1 > m1) { m1 = e1; i1 = i; }
+            s2 += e2; if (e2 > m2) { m2 = e2; i2 = i; }
         }
         if (ok) {
             double* rp = a.report + b * PNPB200_REPORT_WIDTH;
@@ -403,18 +417,15 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
             for (int k = 0; k < cnt; ++k) {
                 const int i = base + k;
                 const double x = (double)sP[3 * i], y = (double)sP[3 * i + 1], z = (double)sP[3 * i + 2];
-                double pe[3], pg[3];
-                project_folded(Me, me, x, y, z, pe);      // TEST_TOOLBOX.py:312
-                project_folded(Mg, mg, x, y, z, pg);      // :314
+                double pe[2], pg[2], e0, e1, e2;
+                bool be, bg;
+                project_folded(Me, me, x, y, z, pe, be);  // TEST_TOOLBOX.py:312
+                project_folded(Mg, mg, x, y, z, pg, bg);  // :314
                 const V2 px = row[k];
-                const double mu = (double)px.x, mv = (double)px.y, mw = 1.0;
-                double d0, d1, d2, e;
-                d0 = mu - pg[0]; d1 = mv - pg[1]; d2 = mw - pg[2];             // LM vs GT (:321)
-                e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s0 += e; if (e > m0) { m0 = e; i0 = i; }
-                d0 = pe[0] - mu; d1 = pe[1] - mv; d2 = pe[2] - mw;             // prediction vs LM (:326)
-                e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s1 += e; if (e > m1) { m1 = e; i1 = i; }
-                d0 = pe[0] - pg[0]; d1 = pe[1] - pg[1]; d2 = pe[2] - pg[2];    // prediction vs GT (:331)
-                e = sqrt_nonneg(fma(d0, d0, fma(d1, d1, d2 * d2))); s2 += e; if (e > m2) { m2 = e; i2 = i; }
+                landmark_errors(pe, be, pg, bg, (double)px.x, (double)px.y, e0, e1, e2);
+                s0 += e0; if (e0 > m0) { m0 = e0; i0 = i; }
+                s1 += e1; if (e1 > m1) { m1 = e1; i1 = i; }
+                s2 += e2; if (e2 > m2) { m2 = e2; i2 = i; }
             }
             rs.done(c, lane);
         }
@@ -579,6 +590,127 @@ __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, co
     }
 }
 
+// Fast path of the same two passes when the per-class tables fit in shared memory with one private
+// column per LANE ([warp][class][quantity][value][32 lanes]: every lane adds to its own 8-byte word,
+// so there is no conflict, no matching and no turn-taking whatever the class pattern is).  Four
+// warps per block (one block per SM); each thread first issues the loads of kStatUnroll problems,
+// then accumulates them, so that enough bytes are in flight at this low occupancy.
+constexpr int kStatLaneBlock = 128;
+constexpr int kStatLaneWarps = kStatLaneBlock / 32;
+constexpr int kStatUnroll = 4;
+
+template <int PASS>
+__global__ void __launch_bounds__(kStatLaneBlock) k_stats_lane(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
+                                                             const double* __restrict__ sums1, double* out, double* out_max)
+{
+    extern __shared__ double sh[];                        // [warp][n_class][nq][NV][32]
+    constexpr int NV = (PASS == 1) ? 3 : 4;
+    const int nq = in.nq, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = n_class + 1;
+    const int entries = n_class * nq * NV;                // per warp, times 32 lanes
+    __shared__ double sMean[kStatMaxQ * (kStatMaxClass + 1)];
+    for (int e = threadIdx.x; e < kStatLaneWarps * entries * 32; e += blockDim.x) sh[e] = 0.0;
+    if (PASS == 2) {
+        for (int e = threadIdx.x; e < nq * rows; e += blockDim.x) {
+            const double cnt = sums1[e * 4];
+            sMean[e] = cnt > 0.0 ? sums1[e * 4 + 2] / cnt : 0.0;
+        }
+    }
+    __syncthreads();
+    double* mine = sh + (size_t)warp * entries * 32 + lane;
+    double all[kStatMaxQ][4];
+#pragma unroll
+    for (int q = 0; q < kStatMaxQ; ++q) all[q][0] = all[q][1] = all[q][2] = all[q][3] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long b0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; b0 < B; b0 += stride * kStatUnroll) {
+        int c[kStatUnroll];
+        double ev[kStatUnroll][kStatMaxQ], gv[kStatUnroll][kStatMaxQ];
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) {           // all loads first
+            const long long b = b0 + u * stride;
+            c[u] = -2;                                    // -2: no problem; -1: problem outside the classes
+            if (b < B) {
+                c[u] = cls ? cls[b] : 0;
+                if (c[u] < 0 || c[u] >= n_class) c[u] = -1;
+#pragma unroll
+                for (int q = 0; q < kStatMaxQ; ++q) {
+                    if (q < nq) {
+                        ev[u][q] = in.est[q][b * in.es[q]];
+                        gv[u][q] = in.gt[q] ? in.gt[q][b * in.gs[q]] : 0.0;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) {
+            if (c[u] == -2) continue;
+#pragma unroll
+            for (int q = 0; q < kStatMaxQ; ++q) {
+                if (q < nq) {
+                    double ratio, err;
+                    if (in.gt[q]) { ratio = ev[u][q] / gv[u][q]; err = ev[u][q] - gv[u][q]; }
+                    else          { ratio = ev[u][q]; err = ev[u][q]; }
+                    if (PASS == 1) {
+                        all[q][0] += 1.0; all[q][1] += ratio; all[q][2] += err;
+                        if (c[u] >= 0) {
+                            double* p = mine + (size_t)((c[u] * nq + q) * NV) * 32;
+                            p[0] += 1.0; p[32] += ratio; p[64] += err;
+                        }
+                    } else {
+                        const double da = err - sMean[q * rows + n_class];
+                        all[q][0] += da * da; all[q][1] += fabs(err); all[q][2] += fabs(da); all[q][3] = fmax(all[q][3], fabs(da));
+                        if (c[u] >= 0) {
+                            const double d = err - sMean[q * rows + c[u]];
+                            double* p = mine + (size_t)((c[u] * nq + q) * NV) * 32;
+                            p[0] += d * d; p[32] += fabs(err); p[64] += fabs(d); p[96] = fmax(p[96], fabs(d));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // classes: entry e = (class, quantity, value); sum the block's warps per lane, then across lanes
+    for (int e = warp; e < entries; e += kStatLaneWarps) {
+        const int k = e % NV, cq = e / NV, q = cq % nq, c = cq / nq;
+        const bool is_max = (PASS == 2) && (k == 3);
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < kStatLaneWarps; ++w) {
+            const double v = sh[((size_t)w * entries + e) * 32 + lane];
+            a = is_max ? fmax(a, v) : a + v;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double o = __shfl_xor_sync(0xffffffffu, a, off);
+            a = is_max ? fmax(a, o) : a + o;
+        }
+        if (lane == 0) {
+            if (is_max) atomic_max_double(out_max + (size_t)q * rows + c, a);
+            else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + c) * 4 + k, a);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kStatMaxQ; ++q) {                 // the "all" row
+        if (q < nq) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double a = all[q][k];
+                const bool is_max = (PASS == 2) && (k == 3);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double o = __shfl_xor_sync(0xffffffffu, a, off);
+                    a = is_max ? fmax(a, o) : a + o;
+                }
+                if (lane == 0) {
+                    if (is_max) atomic_max_double(out_max + (size_t)q * rows + n_class, a);
+                    else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + n_class) * 4 + k, a);
+                }
+            }
+        }
+    }
+}
+
 struct Bins { double b[32]; int n; };
 __global__ void k_classify(long long B, const double* __restrict__ v, long long stride, double scale, Bins bins, int32_t* cls)
 {
@@ -614,7 +746,8 @@ __global__ void k_selftest_math(long long n_signed, const double* __restrict__ i
     if (i >= n) return;
     const double a = in[i];
     const double y = t_rsqrt<double>(a);
-    rcp[i] = t_rcp<double>(a); rsq[i] = y; sq[i] = t_sqrt_fast<double>(a, y);
+    rcp[i] = t_rcp<double>(a); rsq[i] = y;
+    sq[i] = (i & 1) ? sqrt_nonneg(a) : t_sqrt_fast<double>(a, y);   // both square roots in use (report / LM constraint rows)
 }
 
 }  // namespace pnpb200
@@ -780,9 +913,20 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
     PNP_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 4 * (size_t)nq * (n_class + 1), st));
     if (PASS == 2) PNP_CUDA_OK(cudaMemsetAsync(sums_max, 0, sizeof(double) * (size_t)nq * (n_class + 1), st));
     if (B == 0) return PNPB200_OK;
-    const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
-    if (smem > 48 * 1024) PNP_CUDA_OK(cudaFuncSetAttribute(k_stats<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
+    DeviceProps dp;
+    int rc = get_device_props(&dp);
+    if (rc != PNPB200_OK) return rc;
+    const size_t lane_smem = sizeof(double) * (size_t)kStatLaneWarps * n_class * nq * (PASS == 1 ? 3 : 4) * 32;
+    if (lane_smem + 4096 <= (size_t)dp.max_smem_optin) {  // lane-private tables fit: one block per SM
+        PNP_CUDA_OK(cudaFuncSetAttribute(k_stats_lane<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+        long long g = (B + kStatLaneBlock - 1) / kStatLaneBlock;
+        if (g > dp.sm_count) g = dp.sm_count;
+        k_stats_lane<PASS><<<(unsigned)g, kStatLaneBlock, lane_smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
+    } else {
+        const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
+        if (smem > 48 * 1024) PNP_CUDA_OK(cudaFuncSetAttribute(k_stats<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
+    }
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

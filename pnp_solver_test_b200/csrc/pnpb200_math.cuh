@@ -37,7 +37,12 @@ template <> PNP_DEV double t_rcp<double>(double a)
     e = fma(e, e, e);                                     // e + e^2
     return fma(x, e, x);                                  // x (1 + e + e^2): error e^3 ~ 2^-60, <= 0.5003 ulp measured
 }
-template <> PNP_DEV float t_rcp<float>(float x) { return __frcp_rn(x); }
+template <> PNP_DEV float t_rcp<float>(float a)
+{
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));   // MUFU.RCP, ~1 ulp
+    return fmaf(x, fmaf(-a, x, 1.0f), x);
+}
 // 1 / sqrt(a)
 template <typename T> PNP_DEV T t_rsqrt(T x);
 template <> PNP_DEV double t_rsqrt<double>(double a)
@@ -48,7 +53,12 @@ template <> PNP_DEV double t_rsqrt<double>(double a)
     double e = fma(-ha * y, y, 0.5);                      // (1 - a y^2) / 2
     return fma(y, fma(1.5 * e, e, e), y);                 // y (1 + e' / 2 + 3 e'^2 / 8), e' = 2 e: third order
 }
-template <> PNP_DEV float t_rsqrt<float>(float x) { return rsqrtf(x); }
+template <> PNP_DEV float t_rsqrt<float>(float a)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));  // MUFU.RSQ, ~2 ulp
+    return fmaf(y, fmaf(-0.5f * a * y, y, 0.5f), y);
+}
 // sqrt(a) = a / sqrt(a) with one correction step (a > 0, normal)
 template <typename T> PNP_DEV T t_sqrt_fast(T a, T rs);   // rs = t_rsqrt(a)
 template <> PNP_DEV double t_sqrt_fast<double>(double a, double rs)
@@ -56,13 +66,22 @@ template <> PNP_DEV double t_sqrt_fast<double>(double a, double rs)
     const double s = a * rs;
     return fma(fma(-s, s, a), 0.5 * rs, s);
 }
-template <> PNP_DEV float t_sqrt_fast<float>(float a, float rs) { return sqrtf(a); }
+template <> PNP_DEV float t_sqrt_fast<float>(float a, float rs)
+{
+    const float s = a * rs;
+    return fmaf(fmaf(-s, s, a), 0.5f * rs, s);
+}
 // branch-free sqrt for a >= 0 including exact zeros (distances): the seed sees max(a, 2^-1000), so
-// a = 0 gives 0 * finite = 0
+// a = 0 gives 0 * finite = 0.  s0 = a y0 carries the seed's 2^-20 error e' = 1 - a y0^2; one third-order
+// step s0 (1 + e'/2 + 3 e'^2 / 8) leaves ~e'^3: five FP64 instructions after the MUFU, ~1 ulp.
 PNP_DEV double sqrt_nonneg(double a)
 {
-    const double rs = t_rsqrt<double>(fmax(a, 9.3326361850321888e-302));
-    return t_sqrt_fast<double>(a, rs);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(fmax(a, 9.3326361850321888e-302)));
+    const double s0 = a * y;
+    const double e = fma(-s0, y, 1.0);
+    const double p = fma(0.375, e, 0.5) * e;
+    return fma(s0, p, s0);
 }
 template <typename T> PNP_DEV T t_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> PNP_DEV T t_fma(T a, T b, T c);

@@ -296,4 +296,4 @@ def test_fast_reciprocals():
     al = a.astype(np.longdouble)
     assert np.abs(rcp * al - 1).max() <= 1.01 * ulp
     assert np.abs(rsq.astype(np.longdouble) ** 2 * al - 1).max() <= 2.5 * ulp
-    assert np.abs(sq.astype(np.longdouble) / np.sqrt(al) - 1).max() <= 1.01 * ulp
+    assert np.abs(sq.astype(np.longdouble) / np.sqrt(al) - 1).max() <= 1.6 * ulp     # even: t_sqrt_fast, odd: sqrt_nonneg

@@ -120,3 +120,30 @@ def test_report_warp_kernel_for_large_patterns():
     assert np.abs(rep["report"].cpu().numpy() - ref["report"]).max() < 1e-9
     assert np.array_equal(rep["flags"].cpu().numpy(), ref["flags"])
     assert (rep["max_idx"].cpu().numpy() == ref["max_idx"]).mean() > 0.99
+
+
+@pytest.mark.parametrize("n_class,nq", [(1, 1), (13, 4), (64, 4), (40, 2)])
+def test_statistics_kernels_both_paths_match_numpy(n_class, nq):
+    """Lane-private tables (few classes) and the turn-taking kernel (tables too large for shared
+    memory) against the NumPy restatement of get_statistic_of_result, ragged B, empty classes."""
+    from pnp_solver_test_b200 import workload as wl
+    rng = np.random.default_rng(n_class * 10 + nq)
+    B = 70001
+    est = rng.normal(1.0, 0.3, (B, nq)) + 3.0
+    gt = rng.normal(1.0, 0.1, (B, nq)) + 3.0
+    cls = rng.integers(0, n_class + 2, B).astype(np.int32) - 1          # -1 and n_class: outside every class
+    cls[cls == 2] = 3 if n_class > 3 else cls[cls == 2]                 # leave class 2 empty when there is room
+    d_est, d_gt = dev(est), dev(gt)
+    st = wl.statistics([d_est[:, q] for q in range(nq)], [d_gt[:, q] for q in range(nq)],
+                       torch.from_numpy(cls).cuda(), n_class, distributed=False).numpy()
+    assert st.shape == (nq, n_class + 1, 7)
+    for q in range(nq):
+        for c in list(range(n_class)) + [-1]:
+            sel = np.ones(B, bool) if c == -1 else (cls == c)
+            row = st[q, c]
+            if sel.sum() == 0:
+                assert row[0] == 0
+                continue
+            ref = np.array(orc.stats_of(est[sel, q], gt[sel, q]), dtype=np.float64)
+            assert row[0] == ref[0]
+            assert np.abs(row[1:] - ref[1:]).max() < 1e-11 * max(1.0, np.abs(ref[1:]).max()), (q, c, row, ref)
