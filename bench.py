@@ -7,9 +7,10 @@
 Workload (config.workload): BASELINE.json configs[1] -- 1,048,576 problems x 68-point face
 pattern, LM refinement, FP64, per GPU (weak scaling: rank r owns problems [r*B, (r+1)*B) of one
 global counter-based synthetic stream, so a sharded run is the slice of the unsharded one).
-A "step" is one pass of the hot path over the rank's batch: the fused solve kernel (packing and
-K^-1 normalisation, 14 LM iterations, SO(3) projection, Euler), the error-report kernel, and the
-error statistics with their two all-reduces (NCCL over NVLink; the only inter-GPU traffic).
+A "step" is one pass of the hot path over the rank's batch: the solve (three kernels: packing, K^-1
+normalisation and moments; 14 LM iterations, SO(3) projection, Euler; point-wise residual), the
+error-report kernel, and the error statistics with their two all-reduces (NCCL over NVLink; the only
+inter-GPU traffic).
 Inputs are resident in HBM for `value`; `e2e` runs the same solve through the host-buffer entry
 point (pinned host memory -> H2D -> solve -> D2H of all results) inside the timed region.
 """
@@ -37,17 +38,27 @@ UNIT = "solves/s"
 # ------------------------------------------------------------------------------------------------
 # Algorithmic work per solve of the LM path as implemented (DESIGN.md "Kernels"); FMA = 2 flops.
 # Moment mapping = three kernels:
-#   k_stream_thread<.,LM,0>  moments: per point 6 theta*theta^T products, bx^2+by^2, 27 FMAs, 2 adds   65 flop/pt   (HBM-bound)
-#   k_iterate<.,LM>          14 x [gamma column 84 FMA, rhs 82, build A 60, nine constraint rows 440,
-#                            LDL^T 12x12 + two triangular solves 926, update 12] + 3x3 SVD, t, Euler   (FP64 pipe)
-#   k_stream_thread<.,LM,1>  residual at the state before the last update: 34 flop/pt                  (HBM-bound)
+#   k_stream_chunk<.,LM,0>  moments: per point 6 theta*theta^T products, bx^2+by^2, 27 FMAs, 2 adds    65 flop/pt   (HBM-bound)
+#   k_iterate<.,LM>         14 x [gamma column 84 FMA = 168, rhs 37 FMA = 74, A and g set-up 62, eliminate
+#                           delta_1/delta_2 70 FMA + 28 MUL = 168, nine constraint rows (dots, 3 rsqrt/sqrt, 189
+#                           FMA of outer products) 477, LDL^T 10x10 (165 FMA, 55 MUL, 10 reciprocals) 455,
+#                           two triangular solves 190, delta back-substitution and update 42] = 14 x 1636
+#                           + 3x3 SVD, t, Euler ~1000                                               (FP64 pipe)
+#                           (cross-check: the SASS of one iteration is 721 DFMA + 159 DMUL + 36 DADD = 1637)
+#   k_stream_chunk<.,LM,1>  residual at the state before the last update: 34 flop/pt                   (HBM-bound)
 # ------------------------------------------------------------------------------------------------
 def lm_flops_iterate(max_it=14):
-    return max_it * (168 + 82 + 60 + 440 + 926 + 12) + 1000
+    return max_it * (168 + 74 + 62 + 168 + 477 + 455 + 190 + 42) + 1000
 
 
 def lm_flops_per_solve(n, max_it=14):
     return n * (65 + 34) + lm_flops_iterate(max_it)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_iterate<double, LM> launch over 1,048,576 problems, from the
+# committed `ncu --set full` capture (bench.py cannot run ncu on itself); algorithmic bytes are 456 per problem
+# (29 moments in; state before the last update, R, t, Euler, iters, best out) = 478 MB.
+NCU_TRAFFIC = {"bytes": 243.71e6 + 190.85e6, "problems": 1 << 20, "source": "profiles/r01f_k_iterate_lm68_ncu.md"}
 
 
 def lm_flops_survey(n, max_it=14):
@@ -284,8 +295,22 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         h2d = host_uv.numel() * 8
         d2h = sum(v.numel() * v.element_size() for v in outs.values())
+        # what bounds it: the same pixels copied host -> device alone (pinned, one cudaMemcpyAsync per step)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        uv.copy_(host_uv, non_blocking=True)
+        barrier()
+        c0.record()
+        for _ in range(3):
+            uv.copy_(host_uv, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        copy_ms = c0.elapsed_time(c1) / 3
+        e2e_ms = 1e3 * float(tt[0]) / e_steps
         e2e = {"value": world * B * e_steps / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e_steps, "api": "pnpb200_solve_batch_host via HostPipeline.solve (pinned host buffers, %d-problem chunks, 3 streams)" % args.chunk}
+               "steps": e_steps, "ms_per_step": e2e_ms,
+               "api": "pnpb200_solve_batch_host via HostPipeline.solve (pinned host buffers, %d-problem chunks, 3 streams)" % args.chunk,
+               "bound": {"what": "PCIe host->device copy of the pixels", "h2d_copy_alone_ms": copy_ms,
+                         "h2d_copy_alone_gbs": h2d / (copy_ms * 1e-3) / 1e9, "e2e_over_copy": e2e_ms / copy_ms}}
         assert torch.equal(outs["iters"], torch.full((B,), 14, dtype=torch.int32))
         pipe.close()
 
@@ -310,16 +335,18 @@ def run_ours(args):
     mom_bytes = (2 * n * 8 + 29 * 8) * B          # read every pixel once, write 29 moments
     res_bytes = (2 * n * 8 + 12 * 8 + 8) * B      # read every pixel and the 12-double state, write res_norm
     roofline = {"bound": "fp64_pipe", "kernel": "k_iterate<double, LM>", "achieved": achieved_tf, "peak": peak.value / 1e12,
-                "unit": "TFLOP/s", "frac": achieved_tf / (peak.value / 1e12), "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tf / (peak.value / 1e12),
+                "traffic": NCU_TRAFFIC["bytes"] * B / NCU_TRAFFIC["problems"], "traffic_unit": "bytes per launch (ncu dram read + write, %s)" % NCU_TRAFFIC["source"],
+                "algorithmic_bytes": 456 * B,
                 "peak_source": "measured in this run by pnpb200_fma_peak (FP64 FMA microbenchmark; MEASURED_PEAKS.json has no FP64 figure)",
                 "flops_per_solve": fl, "kernel_ms": ms_it, "timed_calls": int(ncall.value),
                 "solve_ms": ms_kernel_max, "flops_per_solve_whole_path": lm_flops_per_solve(n),
                 "flops_per_solve_survey_formula": lm_flops_survey(n),
                 "other_kernels": [
-                    {"kernel": "k_stream_thread<double, LM, 0> (moments)", "bound": "hbm", "kernel_ms": ms_mom,
+                    {"kernel": "k_stream_chunk<double, LM, 0> (moments)", "bound": "hbm", "kernel_ms": ms_mom,
                      "achieved": mom_bytes / (ms_mom * 1e-3) / 1e9 if ms_mom > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (mom_bytes / (ms_mom * 1e-3) / 1e9 / hbm_peak) if ms_mom > 0 else None, "peak_source": hbm_src},
-                    {"kernel": "k_stream_thread<double, LM, 1> (residual)", "bound": "hbm", "kernel_ms": ms_res,
+                    {"kernel": "k_stream_chunk<double, LM, 1> (residual)", "bound": "hbm", "kernel_ms": ms_res,
                      "achieved": res_bytes / (ms_res * 1e-3) / 1e9 if ms_res > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (res_bytes / (ms_res * 1e-3) / 1e9 / hbm_peak) if ms_res > 0 else None, "peak_source": hbm_src}]}
     cpu = cpu_baseline_block() if (world == 1 and not args.no_cpu) else None
@@ -348,7 +375,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=B_PER_GPU, help="problems per GPU (default: the BASELINE config)")

@@ -730,6 +730,7 @@ __global__ void k_fma_peak(int iters, T seed, T* out)
 {
     T a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const T m = T(0.999999), c = T(1e-6);
+#pragma unroll 16
     for (int i = 0; i < iters; ++i) {
         a0 = t_fma(a0, m, c); a1 = t_fma(a1, m, c); a2 = t_fma(a2, m, c); a3 = t_fma(a3, m, c);
         a4 = t_fma(a4, m, c); a5 = t_fma(a5, m, c); a6 = t_fma(a6, m, c); a7 = t_fma(a7, m, c);

@@ -847,7 +847,8 @@ PNP_DEV void solve_linear_f1(const Pts& pts, const T* __restrict__ sP, int n, in
             pts.get(i, bx, by);
             T Delta = th0 * phi3[0] + th1 * phi3[1] + th2 * phi3[2] + T(1);   // get_Delta_i :3031-3046
             if (t_abs(Delta) <= eps) Delta = (Delta < T(0)) ? -eps : eps;
-            const T a[4] = { th0 / Delta, th1 / Delta, th2 / Delta, T(1) / Delta };     // get_A_i :3048-3062
+            const T iD = t_rcp<T>(Delta);                 // |Delta| >= 1e-7 after the clamp: normal range
+            const T a[4] = { th0 * iD, th1 * iD, th2 * iD, iD };                          // get_A_i :3048-3062
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
 #pragma unroll
@@ -875,7 +876,7 @@ PNP_DEV void solve_linear_f1(const Pts& pts, const T* __restrict__ sP, int n, in
                 pts.get(i, bx, by);
                 T Delta = th0 * phi3[0] + th1 * phi3[1] + th2 * phi3[2] + T(1);
                 if (t_abs(Delta) <= eps) Delta = (Delta < T(0)) ? -eps : eps;
-                const T a0 = th0 / Delta, a1 = th1 / Delta, a2 = th2 / Delta, a3 = T(1) / Delta;
+                const T a3 = t_rcp<T>(Delta), a0 = th0 * a3, a1 = th1 * a3, a2 = th2 * a3;
                 const T ex = bx - (a0 * pn[0] + a1 * pn[1] + a2 * pn[2] + a3 * pn[6]);
                 const T ey = by - (a0 * pn[3] + a1 * pn[4] + a2 * pn[5] + a3 * pn[7]);
                 r2 = t_fma(ex, ex, t_fma(ey, ey, r2));
