@@ -64,7 +64,7 @@ def dict_from_uv(keys, uv):
 def call_method(solver, method, pts, pattern_np, key_list):
     """Returns (R, t, t3, roll, yaw, pitch, res_norm, iters)."""
     counter = {"n": 0}
-    name = {"qeif": "QEKF_get_hx_H", "lm": "EKF2_get_hx_H"}.get(method)
+    name = {"qeif": "QEKF_get_hx_H", "lm": "EKF2_get_hx_H", "eif2": "EKF2_get_hx_H"}.get(method)
     if name:
         orig = getattr(solver, name)
 
@@ -81,6 +81,8 @@ def call_method(solver, method, pts, pattern_np, key_list):
             r = solver.solve_pnp_formulation_2_single_pattern(pts, pattern_np)
         elif method == "linear_f1":
             r = solver.solve_pnp_single_pattern(pts, pattern_np)
+        elif method == "eif2":
+            r = solver.solve_pnp_EIF2_single_pattern(pts, pattern_np)
         else:
             raise ValueError(method)
     finally:
@@ -310,12 +312,15 @@ def main():
             ("linear_f2_n68_%s" % qn, "linear_f2", p68, None, B // 2, 48, q),
             ("linear_f1_n15_%s" % qn, "linear_f1", alex, None, B, 49, q),
             ("linear_f1_n68_%s" % qn, "linear_f1", p68, None, B // 2, 50, q),
+            ("eif2_n15_%s" % qn, "eif2", alex, None, B, 55, q),
+            ("eif2_n68_%s" % qn, "eif2", p68, None, B // 2, 56, q),
         ]
     cases += [
         ("qeif_n1024_q", "qeif", p1024, None, 3, 51, True),
         ("lm_n1024_q", "lm", p1024, None, 12, 52, True),
         ("linear_f2_n1024_q", "linear_f2", p1024, None, 12, 53, True),
         ("linear_f1_n1024_q", "linear_f1", p1024, None, 12, 54, True),
+        ("eif2_n1024_q", "eif2", p1024, None, 6, 57, True),
     ]
     only = [a for a in sys.argv[1:] if not a.startswith("--")]
     for tag, method, pat, keys, b, seed, q in cases:

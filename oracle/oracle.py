@@ -17,8 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libpnp_oracle.so")
 
 METHOD_QEIF, METHOD_LM, METHOD_LINEAR_F2, METHOD_LINEAR_F1 = 0, 1, 2, 3
-METHODS = {"qeif": 0, "lm": 1, "linear_f2": 2, "linear_f1": 3, "lm_plus": 4}
-TRACE_DIM = {0: 6, 1: 12, 2: 11, 3: 11, 4: 12}
+METHODS = {"qeif": 0, "lm": 1, "linear_f2": 2, "linear_f1": 3, "lm_plus": 4, "eif2": 5}
+TRACE_DIM = {0: 6, 1: 12, 2: 11, 3: 11, 4: 12, 5: 12}
 
 
 class Params(C.Structure):
@@ -100,7 +100,7 @@ def solve_one(method, P, uv, K, params=None, want_trace=False):
     nit = max(params.max_it, params.linear_it)
     trace = np.full((nit, TRACE_DIM[m]), np.nan) if want_trace else None
     fn = [lib().pnp_oracle_qeif, lib().pnp_oracle_lm, lib().pnp_oracle_linear_f2,
-          lib().pnp_oracle_linear_f1, lib().pnp_oracle_lm_plus][m]
+          lib().pnp_oracle_linear_f1, lib().pnp_oracle_lm_plus, lib().pnp_oracle_eif2][m]
     fn.restype = C.c_int
     it = fn(C.c_int(n), _p(P), _p(uv), _p(K), C.byref(params), _p(R), _p(t), _p(e), C.byref(res),
             _p(trace) if want_trace else None)

@@ -527,6 +527,111 @@ ORACLE_API int pnp_oracle_linear_f2(int n, const double *P, const double *uv, co
                                     double *res_norm_out, double *trace);
 
 /* ------------------------------------------------------------------------------------ */
+/* EIF2: solve_pnp_EIF2_single_pattern :2001-2276 -- the iterated information filter on the  */
+/* 12-state model of EKF2_get_hx_H (:3718-3836, same defaults as LM) with the state-dependent */
+/* process covariance of EKF2_get_process_covariance_R (:3668-3716) and QEIF's early exit.     */
+/* ------------------------------------------------------------------------------------ */
+/* EKF2_get_process_covariance_R :3668-3716.  Rk is 12 x 12 row-major. */
+static void ekf2_process_cov(const double *x, double *Rk)
+{
+    const double sig_th = 60.0 * (3.14159265358979323846 / 180.0);   /* np.deg2rad(60.0) :3686 */
+    const double sig_t12 = 0.05, sig_t3 = 2.0;                       /* :3687, :3689 */
+    double C[27];                                                     /* vstack(-so3(u1), -so3(u2), -so3(u3)) :3694 */
+    int b, i, j, k;
+    memset(Rk, 0, sizeof(double) * 144);
+    for (b = 0; b < 3; ++b) {
+        const double *u = x + 3 * b;
+        double *c = C + 9 * b;                                        /* get_so3_matrix_from_vec3 :3661-3666, negated */
+        c[0] = -0.0;   c[1] = u[2];   c[2] = -u[1];
+        c[3] = -u[2];  c[4] = -0.0;   c[5] = u[0];
+        c[6] = u[1];   c[7] = -u[0];  c[8] = -0.0;
+    }
+    for (i = 0; i < 9; ++i)                                           /* Ck @ (sigma^2 I) @ Ck.T :3695-3696 */
+        for (j = 0; j < 9; ++j) {
+            double a = 0.0;
+            for (k = 0; k < 3; ++k) a += (C[i * 3 + k] * (sig_th * sig_th)) * C[j * 3 + k];
+            Rk[i * 12 + j] = a;
+        }
+    Rk[9 * 12 + 9] = Rk[10 * 12 + 10] = fabs(x[11]) * (sig_t12 * sig_t12);   /* :3700 */
+    Rk[11 * 12 + 11] = (x[11] * x[11]) * (sig_t3 * sig_t3);                  /* :3701 */
+}
+
+ORACLE_API int pnp_oracle_eif2(int n, const double *P, const double *uv, const double *K,
+                               const oracle_params_t *prm, double *R, double *t, double *euler,
+                               double *res_norm_out, double *trace)
+{
+    int Z = 2 * n + 9, i, j, r, it = 0;
+    double Kinv[9];
+    double *bx = (double *)malloc(sizeof(double) * ((size_t)n * 2 + (size_t)Z * 15));
+    double *by = bx + n, *hx = by + n, *J = hx + Z, *qinv = J + (size_t)Z * 12, *z = qinv + Z;
+    double x[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1 };   /* :2058-2063 */
+    double Omega[144], Sigma[144], Rk[144], tmp[144], zeta[12], work[144 + 12 + 144];
+    double res = 1e5, res_old = 1e-7;                         /* :2101-2102 */
+
+    inv3(K, Kinv);
+    normalise(n, uv, Kinv, bx, by);
+    for (r = 0; r < Z; ++r) {
+        /* eif_z :2049-2055 and eif_Q_diag :2080-2091, eif_Q_pinv = pinv(diag) = 1 / diag */
+        double q;
+        if (r < n) z[r] = bx[r];
+        else if (r < 2 * n) z[r] = by[r - n];
+        else if (r < 2 * n + 6) z[r] = 0.0;
+        else z[r] = 1.0;
+        if (r < 2 * n) q = (prm->meas_sigma_px * prm->meas_sigma_px) / (prm->f_weight * prm->f_weight);
+        else if (r < 2 * n + 3) q = 1e-2 * 16.0;
+        else if (r < 2 * n + 6) q = (2.0 * 2.0) * 1e-2 * 16.0;
+        else q = 1.0;
+        qinv[r] = 1.0 / q;
+    }
+    for (i = 0; i < 144; ++i) Omega[i] = 0.0;
+    for (i = 0; i < 12; ++i) Omega[i * 12 + i] = 1e-5;        /* :2067 */
+    pinv_svd(12, 12, Omega, Sigma, work);                     /* eif_Omega_pinv :2068 */
+
+    while (it < prm->max_it) {                                /* :2107 */
+        double ratio, res2 = 0.0;
+        ++it;
+        /* predict :2146-2152: Omega = pinv(G Omega_pinv G^T + R_k), G = I; zeta = Omega x */
+        ekf2_process_cov(x, Rk);
+        for (i = 0; i < 144; ++i) tmp[i] = Sigma[i] + Rk[i];
+        pinv_svd(12, 12, tmp, Omega, work);
+        for (i = 0; i < 12; ++i) {
+            zeta[i] = 0.0;
+            for (j = 0; j < 12; ++j) zeta[i] += Omega[i * 12 + j] * x[j];
+        }
+        /* update :2157-2164 */
+        ekf2_hx_H(n, x, bx, by, P, hx, J);
+        for (r = 0; r < Z; ++r) {
+            double dz = z[r] - hx[r], Hx = 0.0, v;
+            for (j = 0; j < 12; ++j) Hx += J[r * 12 + j] * x[j];
+            v = dz + Hx;                                      /* z - hx + H x */
+            for (i = 0; i < 12; ++i) {
+                double hw = J[r * 12 + i] * qinv[r];          /* (H^T Q^-1)[i, r] */
+                if (hw == 0.0) continue;
+                zeta[i] += hw * v;
+                for (j = 0; j < 12; ++j) Omega[i * 12 + j] += hw * J[r * 12 + j];
+            }
+            if (r < 2 * n) res2 += dz * dz;
+        }
+        res = sqrt(res2);                                     /* res_norm over the 2n measurement rows :2178 */
+        pinv_svd(12, 12, Omega, Sigma, work);                 /* :2184 */
+        for (i = 0; i < 12; ++i) {                            /* :2185 */
+            double a = 0.0;
+            for (j = 0; j < 12; ++j) a += Sigma[i * 12 + j] * zeta[j];
+            x[i] = a;
+        }
+        if (trace) for (i = 0; i < 12; ++i) trace[(it - 1) * 12 + i] = x[i];
+        ratio = (res - res_old) / res_old;                    /* :2196 */
+        res_old = res;
+        if (fabs(ratio) < prm->exit_tol) break;               /* :2202 */
+    }
+    ekf2_reconstruct(x, R, t);
+    pnp_oracle_euler_from_R(R, 1, euler);
+    *res_norm_out = res;
+    free(bx);
+    return it;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* LM+ -- NOT a reference method: the pipeline BASELINE.json's north star   */
 /* describes.  Linear stage F2 (3 iterations) for the initial pose, then the same 12-state      */
 /* damped Gauss-Newton as solve_pnp_LM_single_pattern but with the TRUE constraint gradients     */
@@ -844,6 +949,7 @@ ORACLE_API int pnp_oracle_solve_batch(int method, int64_t B, int n, const double
     case 2: c.fn = pnp_oracle_linear_f2; break;
     case 3: c.fn = pnp_oracle_linear_f1; break;
     case 4: c.fn = pnp_oracle_lm_plus; break;
+    case 5: c.fn = pnp_oracle_eif2; break;
     default: return -1;
     }
     c.n = n; c.n_patterns = n_patterns; c.uv = uv; c.patterns = patterns; c.K = K; c.prm = prm;
