@@ -38,6 +38,8 @@ extern "C" {
 #define PNPB200_METHOD_LM_PLUS    4  /* NOT in the reference (non-parity extra): linear F2 initial pose, then LM's 12-state
                                         damped Gauss-Newton with the true constraint gradients and a convergence test
                                         (max |dx| <= 1e-10); res_norm at the returned state; one pattern, moment mapping */
+#define PNPB200_METHOD_EIF2       5  /* solve_pnp_EIF2_single_pattern,          PNP_SOLVER_LIB.py:2001-2276: iterated information filter
+                                        on LM's 12-state model with EKF2_get_process_covariance_R (:3668-3716) and QEIF's early exit */
 
 #define PNPB200_DTYPE_F64 0
 #define PNPB200_DTYPE_F32 1

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libpnpb200.so")
 
 METHOD_QEIF, METHOD_LM, METHOD_LINEAR_F2, METHOD_LINEAR_F1 = 0, 1, 2, 3
 METHOD_LM_PLUS = 4
-METHODS = {"qeif": 0, "lm": 1, "linear_f2": 2, "linear_f1": 3, "lm_plus": 4}
+METHOD_EIF2 = 5
+METHODS = {"qeif": 0, "lm": 1, "linear_f2": 2, "linear_f1": 3, "lm_plus": 4, "eif2": 5}
 DTYPE_F64, DTYPE_F32 = 0, 1
 MAP_AUTO, MAP_THREAD, MAP_MOMENT, MAP_WARP = 0, 1, 2, 32
 REPORT_WIDTH = 16

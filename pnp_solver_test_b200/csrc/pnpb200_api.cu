@@ -136,7 +136,7 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, co
 {
     if (B < 0 || n_total < 1 || n < 1 || (!point_index && n != n_total) || !uv || !pattern || !K) return PNPB200_EINVAL;
     if (n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
-    if (method < 0 || method > 4 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
+    if (method < 0 || method > 5 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
     if (B == 0) return PNPB200_OK;
     pnpb200_params prm;
     if (params) prm = *params; else fill_default_params(&prm);
@@ -151,10 +151,10 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, co
         }
     }
     const int group = (method == PNPB200_METHOD_QEIF || method == PNPB200_METHOD_LINEAR_F1) ? 0
-                      : (method == PNPB200_METHOD_LINEAR_F2 ? 2 : 1);
+                      : (method == PNPB200_METHOD_LINEAR_F2 ? 2 : (method == PNPB200_METHOD_EIF2 ? 3 : 1));
     typedef int (*part_fn)(PNP_SOLVE_PART_ARGS);
-    static const part_fn parts[2][3] = { { solve_part_f64_g0, solve_part_f64_g1, solve_part_f64_g2 },
-                                         { solve_part_f32_g0, solve_part_f32_g1, solve_part_f32_g2 } };
+    static const part_fn parts[2][4] = { { solve_part_f64_g0, solve_part_f64_g1, solve_part_f64_g2, solve_part_f64_g3 },
+                                         { solve_part_f32_g0, solve_part_f32_g1, solve_part_f32_g2, solve_part_f32_g3 } };
     const int rc = parts[dtype == PNPB200_DTYPE_F64 ? 0 : 1][group](method, B, n_total, n, uv, pattern, n_patterns, point_index,
                                                                    idx_dev, K, prm, R, t, euler_deg, res_norm, iters,
                                                                    best_pattern, st);

@@ -78,7 +78,7 @@ extern thread_local ProfileRing g_prof;            // defined in pnpb200_api.cu
 // ------------------------------------------------------------------------------------------
 // The templated solve path (pnpb200_kernels.cu) is compiled once per (scalar type, method group)
 // so that the objects build in parallel; pnpb200_api.cu dispatches to these entry points.
-//   group 0: QEIF, linear F1      group 1: LM, LM+      group 2: linear F2
+//   group 0: QEIF, linear F1      group 1: LM, LM+      group 2: linear F2      group 3: EIF2
 // ------------------------------------------------------------------------------------------
 #define PNP_SOLVE_PART_ARGS                                                                                          \
     int method, long long B, int n_total, int n, const void *uv, const void *pattern, int n_patterns,                 \
@@ -87,9 +87,11 @@ extern thread_local ProfileRing g_prof;            // defined in pnpb200_api.cu
 int solve_part_f64_g0(PNP_SOLVE_PART_ARGS);
 int solve_part_f64_g1(PNP_SOLVE_PART_ARGS);
 int solve_part_f64_g2(PNP_SOLVE_PART_ARGS);
+int solve_part_f64_g3(PNP_SOLVE_PART_ARGS);
 int solve_part_f32_g0(PNP_SOLVE_PART_ARGS);
 int solve_part_f32_g1(PNP_SOLVE_PART_ARGS);
 int solve_part_f32_g2(PNP_SOLVE_PART_ARGS);
+int solve_part_f32_g3(PNP_SOLVE_PART_ARGS);
 void fill_default_params(pnpb200_params* p);          // defined in pnpb200_api.cu
 
 }  // namespace pnpb200

@@ -1,5 +1,5 @@
 // pnpb200_kernels.cu -- the hot path: batched PnP solve kernels for sm_100a and their launchers.
-// Compiled once per (PNP_F64 = 0|1, PNP_GROUP = 0|1|2); the C ABI lives in pnpb200_api.cu.
+// Compiled once per (PNP_F64 = 0|1, PNP_GROUP = 0|1|2|3); the C ABI lives in pnpb200_api.cu.
 //
 // Two execution shapes share the solver code in pnpb200_solvers.cuh:
 //
@@ -28,7 +28,7 @@
 #define PNP_TUNE_VARIANTS 0   // 1: also build the experimental k_iterate occupancy variants (tools/time_solve.py --tune)
 #endif
 #ifndef PNP_F64
-#error "compile with -DPNP_F64=0|1 -DPNP_GROUP=0|1|2"
+#error "compile with -DPNP_F64=0|1 -DPNP_GROUP=0|1|2|3"
 #endif
 
 namespace pnpb200 {
@@ -37,7 +37,7 @@ namespace pnpb200 {
 // kernel arguments
 // ------------------------------------------------------------------------------------------
 // internal kernel variant: QEIF with H^T H / H^T v from the moments (chosen for n >= 12 landmarks)
-#define PNP_METHOD_QEIF_HYBRID 5
+#define PNP_METHOD_QEIF_HYBRID 100
 #define PNP_QEIF_HYBRID_MIN_N 12
 
 template <typename T>
@@ -119,6 +119,7 @@ PNP_DEV void run_method(const Pts& pts, const T* sP, const T* sC, int n, int sub
     else if (METHOD == PNP_METHOD_QEIF_HYBRID)   solve_qeif<T, LPP, Pts, true>(pts, sP, sC, n, sub, prm, out);
     else if (METHOD == PNPB200_METHOD_LM)        solve_lm<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
     else if (METHOD == PNPB200_METHOD_LINEAR_F2) solve_linear_f2<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
+    else if (METHOD == PNPB200_METHOD_EIF2)      solve_eif2<T, LPP, Pts>(pts, sP, sC, n, sub, prm, out);
     else                                         solve_linear_f1<T, LPP, Pts>(pts, sP, n, sub, prm, out);
 }
 
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(32) k_solve_thread(const __grid_constant__ Sol
     // kick off the first tile's copies before touching the pattern so the two overlap
     int valid = (tile < n_tiles) ? tile_buf.issue(tile, lane) : 0;
     load_pattern<T>(a.pattern, sel, a.n_total, a.n, a.n_patterns, sP, sIdx, lane, 32);
-    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNP_METHOD_QEIF_HYBRID) {
+    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNP_METHOD_QEIF_HYBRID || METHOD == PNPB200_METHOD_EIF2) {
         for (int p = 0; p < a.n_patterns; ++p) pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncwarp();
     }
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_solve_warp(const __grid
 
     const int32_t* sel = selection_of(a);
     load_pattern<T>(a.pattern, sel, a.n_total, a.n, a.n_patterns, sP, sIdx, threadIdx.x, blockDim.x);
-    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNP_METHOD_QEIF_HYBRID) {
+    if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNP_METHOD_QEIF_HYBRID || METHOD == PNPB200_METHOD_EIF2) {
         for (int p = warp; p < a.n_patterns; p += kWarpsPerBlock)
             pattern_constants<T>(sP + (size_t)p * a.n * 3, a.n, sC + p * PNP_PATC, lane);
         __syncthreads();
@@ -825,8 +826,10 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
         if (rc != PNPB200_OK) return rc;
         return launch_moment<T, PNPB200_METHOD_LM_PLUS>(a, dp, stream);
     }
-#else
+#elif PNP_GROUP == 2
     case PNPB200_METHOD_LINEAR_F2: return launch_solve<T, PNPB200_METHOD_LINEAR_F2>(a, prm.mapping, stream);
+#else
+    case PNPB200_METHOD_EIF2:      return launch_solve<T, PNPB200_METHOD_EIF2>(a, prm.mapping, stream);
 #endif
     default: return PNPB200_EINVAL;
     }

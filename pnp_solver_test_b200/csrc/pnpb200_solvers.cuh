@@ -683,6 +683,196 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
 }
 
 // -------------------------------------------------------------------------------------------
+// EIF2 -- solve_pnp_EIF2_single_pattern :2001-2276: the iterated information filter on LM's
+// 12-state model (EKF2_get_hx_H :3718-3836) with the state-dependent process covariance of
+// EKF2_get_process_covariance_R (:3668-3716) and QEIF's early exit on the residual.
+// H^T Q^-1 H and H^T Q^-1 (z - hx + H x) of the 2n measurement rows are bilinear forms of the 29
+// moments (z - hx + H x = b + gamma (P phi_1 - b o P phi_3): no cancellation); the nine constraint
+// rows are added one by one with their own weights; ||z - hx|| that drives the exit test is evaluated
+// point by point.  State order as in the reference: [u1, u2, u3, delta_1, delta_2, gamma].
+// -------------------------------------------------------------------------------------------
+// Omega += w c c^T, zeta += w c (z - h + c.x) for a row with non-zeros va at block BA, vb at block BB
+template <typename T, int BA, int BB>
+PNP_DEV void eif2_row2(T (&Om)[78], T (&zeta)[12], const T (&va)[3], const T (&vb)[3], T v, T w)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const T wa = w * va[a], wb = w * vb[a];
+#pragma unroll
+        for (int b = a; b < 3; ++b) {
+            Om[sidx<12>(BA + a, BA + b)] = t_fma(wa, va[b], Om[sidx<12>(BA + a, BA + b)]);
+            Om[sidx<12>(BB + a, BB + b)] = t_fma(wb, vb[b], Om[sidx<12>(BB + a, BB + b)]);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Om[sidx<12>(BA + a, BB + b)] = t_fma(wa, vb[b], Om[sidx<12>(BA + a, BB + b)]);
+        zeta[BA + a] = t_fma(wa, v, zeta[BA + a]);
+        zeta[BB + a] = t_fma(wb, v, zeta[BB + a]);
+    }
+}
+template <typename T, int BA>
+PNP_DEV void eif2_row1(T (&Om)[78], T (&zeta)[12], const T (&va)[3], T v, T w)
+{
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const T wa = w * va[a];
+#pragma unroll
+        for (int b = a; b < 3; ++b) Om[sidx<12>(BA + a, BA + b)] = t_fma(wa, va[b], Om[sidx<12>(BA + a, BA + b)]);
+        zeta[BA + a] = t_fma(wa, v, zeta[BA + a]);
+    }
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                        const SolverPrm<T>& prm, Result<T>& out)
+{
+    constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
+    Moments<T> mom;
+    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2058-2063
+    T Sig[78];
+#pragma unroll
+    for (int e = 0; e < 78; ++e) Sig[e] = T(0);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Sig[sidx<12>(i, i)] = T(1e5);        // pinv(1e-5 I) (:2067-2068)
+    T res_old = T(1e-7), res = T(1e5);                               // :2101-2102
+    bool done = false;
+    int iters = 0;
+    const T w = prm.meas_w;                                          // 1 / (9 / f^2) (:2080-2083)
+    const T wc1 = T(1.0 / (1e-2 * 16.0)), wc2 = T(1.0 / (4.0 * 1e-2 * 16.0)), wc3 = T(1);   // :2085-2091
+    const T sth = T(60.0 * (3.14159265358979323846 / 180.0));
+    const T sth2 = sth * sth, st12 = T(0.05 * 0.05), st3 = T(4.0);   // :3686-3689
+
+    for (int it = 0; it < prm.max_it; ++it) {
+        if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
+        else          { if (done) break; }
+        const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
+        const T gam = x[GG], d1 = x[D1], d2 = x[D2];
+        const T u11 = dot3<T>(u1, u1), u22 = dot3<T>(u2, u2), u33 = dot3<T>(u3, u3);
+        const T u13 = dot3<T>(u1, u3), u23 = dot3<T>(u2, u3), u12 = dot3<T>(u1, u2);
+        // ---- predict: Omega = pinv(Sigma + R_k) (:2146-2150), zeta = Omega x (:2152)
+        // R_k's u blocks: so3(u_i) sigma^2 so3(u_j)^T = sigma^2 ((u_i . u_j) I - u_j u_i^T)   (:3690-3696)
+        T Om[78];
+#pragma unroll
+        for (int e = 0; e < 78; ++e) Om[e] = Sig[e];
+        {
+            const T* uu[3] = { u1, u2, u3 };
+            const T dd[3][3] = { { u11, u12, u13 }, { u12, u22, u23 }, { u13, u23, u33 } };
+#pragma unroll
+            for (int bi = 0; bi < 3; ++bi)
+#pragma unroll
+                for (int bj = bi; bj < 3; ++bj)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) {
+                            if (bi == bj && b < a) continue;
+                            const T v = ((a == b) ? dd[bi][bj] : T(0)) - uu[bj][a] * uu[bi][b];
+                            Om[sidx<12>(3 * bi + a, 3 * bj + b)] = t_fma(sth2, v, Om[sidx<12>(3 * bi + a, 3 * bj + b)]);
+                        }
+        }
+        Om[sidx<12>(D1, D1)] += t_abs(gam) * st12;                   // :3700
+        Om[sidx<12>(D2, D2)] += t_abs(gam) * st12;
+        Om[sidx<12>(GG, GG)] += (gam * gam) * st3;                   // :3701
+        spd_inverse<T, 12>(Om);
+        T zeta[12];
+        sym_matvec<T, 12>(Om, x, zeta);
+        // ---- residual over the 2n measurement rows, point by point (:2176-2178)
+        T res2 = T(0);
+#pragma unroll 4
+        for (int i = sub; i < n; i += LPP) {
+            const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+            T bx, by;
+            pts.get(i, bx, by);
+            const T a = th0 * u1[0] + th1 * u1[1] + th2 * u1[2];
+            const T b = th0 * u2[0] + th1 * u2[1] + th2 * u2[2];
+            const T c = th0 * u3[0] + th1 * u3[1] + th2 * u3[2];
+            const T rx = bx - (gam * (a - bx * c) + d1);
+            const T ry = by - (gam * (b - by * c) + d2);
+            res2 = t_fma(rx, rx, t_fma(ry, ry, res2));
+        }
+        res2 = group_sum<LPP>(res2);
+        // ---- update, measurement rows from the moments (:2157-2164)
+        {
+            GammaCol<T> gc;
+            lm_gamma_column<T, Moments<T> >(x, mom, sC, gc);
+            const T wg = w * gam, wgg = wg * gam;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    Om[sidx<12>(U1 + a, U1 + b)] = t_fma(wgg, sC[s3(a, b)], Om[sidx<12>(U1 + a, U1 + b)]);
+                    Om[sidx<12>(U2 + a, U2 + b)] = t_fma(wgg, sC[s3(a, b)], Om[sidx<12>(U2 + a, U2 + b)]);
+                    Om[sidx<12>(U3 + a, U3 + b)] = t_fma(wgg, mom.Mw[s3(a, b)], Om[sidx<12>(U3 + a, U3 + b)]);
+                }
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    Om[sidx<12>(U1 + a, U3 + b)] = t_fma(-wgg, mom.Mx[s3(a, b)], Om[sidx<12>(U1 + a, U3 + b)]);
+                    Om[sidx<12>(U2 + a, U3 + b)] = t_fma(-wgg, mom.My[s3(a, b)], Om[sidx<12>(U2 + a, U3 + b)]);
+                }
+                Om[sidx<12>(U1 + a, D1)] = t_fma(wg, sC[6 + a], Om[sidx<12>(U1 + a, D1)]);
+                Om[sidx<12>(U2 + a, D2)] = t_fma(wg, sC[6 + a], Om[sidx<12>(U2 + a, D2)]);
+                Om[sidx<12>(U3 + a, D1)] = t_fma(-wg, mom.mx[a], Om[sidx<12>(U3 + a, D1)]);
+                Om[sidx<12>(U3 + a, D2)] = t_fma(-wg, mom.my[a], Om[sidx<12>(U3 + a, D2)]);
+                Om[sidx<12>(U1 + a, GG)] = t_fma(wg, gc.sg1[a], Om[sidx<12>(U1 + a, GG)]);
+                Om[sidx<12>(U2 + a, GG)] = t_fma(wg, gc.sg2[a], Om[sidx<12>(U2 + a, GG)]);
+                Om[sidx<12>(U3 + a, GG)] = t_fma(-wg, gc.sg3[a], Om[sidx<12>(U3 + a, GG)]);
+                // H^T Q^-1 (z - hx + H x), z - hx + H x = (bx + gamma g1, by + gamma g2)
+                zeta[U1 + a] = t_fma(wg, mom.mx[a] + gam * gc.sg1[a], zeta[U1 + a]);
+                zeta[U2 + a] = t_fma(wg, mom.my[a] + gam * gc.sg2[a], zeta[U2 + a]);
+                zeta[U3 + a] = t_fma(-wg, mom.mw[a] + gam * gc.sg3[a], zeta[U3 + a]);
+            }
+            Om[sidx<12>(D1, D1)] = t_fma(w, sC[9], Om[sidx<12>(D1, D1)]);
+            Om[sidx<12>(D2, D2)] = t_fma(w, sC[9], Om[sidx<12>(D2, D2)]);
+            Om[sidx<12>(D1, GG)] = t_fma(w, gc.s1, Om[sidx<12>(D1, GG)]);
+            Om[sidx<12>(D2, GG)] = t_fma(w, gc.s2, Om[sidx<12>(D2, GG)]);
+            Om[sidx<12>(GG, GG)] = t_fma(w, gc.sgg, Om[sidx<12>(GG, GG)]);
+            const T qa = dot3<T>(mom.mx, u1) + dot3<T>(mom.my, u2) - dot3<T>(mom.mw, u3);
+            zeta[D1] = t_fma(w, mom.sx0 + gam * gc.s1, zeta[D1]);
+            zeta[D2] = t_fma(w, mom.sy0 + gam * gc.s2, zeta[D2]);
+            zeta[GG] = t_fma(w, qa + gam * gc.sgg, zeta[GG]);
+        }
+        // ---- update, the nine constraint rows (:3753-3772, Jacobians :3787-3823); v = z - h + c.x
+        {
+            const T nu2[3] = { -u2[0], -u2[1], -u2[2] }, nu3[3] = { -u3[0], -u3[1], -u3[2] };
+            eif2_row2<T, U1, U3>(Om, zeta, u3, u1, T(0) - u13 + (u13 + u13), wc1);
+            eif2_row2<T, U2, U3>(Om, zeta, u3, u2, T(0) - u23 + (u23 + u23), wc1);
+            eif2_row2<T, U1, U2>(Om, zeta, u2, u1, T(0) - u12 + (u12 + u12), wc1);
+            eif2_row2<T, U1, U3>(Om, zeta, u1, nu3, T(0) - (u11 - u33) + (u11 - u33), wc2);
+            eif2_row2<T, U2, U3>(Om, zeta, u2, nu3, T(0) - (u22 - u33) + (u22 - u33), wc2);
+            eif2_row2<T, U1, U2>(Om, zeta, u1, nu2, T(0) - (u11 - u22) + (u11 - u22), wc2);
+            const T y1 = t_rsqrt<T>(u11), y2 = t_rsqrt<T>(u22), y3 = t_rsqrt<T>(u33);
+            const T n1 = t_sqrt_fast<T>(u11, y1), n2 = t_sqrt_fast<T>(u22, y2), n3 = t_sqrt_fast<T>(u33, y3);
+            const T h1 = T(0.5) * y1, h2 = T(0.5) * y2, h3 = T(0.5) * y3;
+            const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
+            const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
+            const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
+            eif2_row1<T, U1>(Om, zeta, j1, T(1) - n1 + dot3<T>(j1, u1), wc3);
+            eif2_row1<T, U2>(Om, zeta, j2, T(1) - n2 + dot3<T>(j2, u2), wc3);
+            eif2_row1<T, U3>(Om, zeta, j3, T(1) - n3 + dot3<T>(j3, u3), wc3);
+        }
+        const T res_new = t_sqrt(res2);
+        // ---- x = pinv(Omega) zeta (:2184-2185)
+        spd_inverse<T, 12>(Om);
+        T xn[12];
+        sym_matvec<T, 12>(Om, zeta, xn);
+        if (!done) {
+#pragma unroll
+            for (int e = 0; e < 78; ++e) Sig[e] = Om[e];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) x[e] = xn[e];
+            res = res_new;
+            ++iters;
+            const T ratio = (res - res_old) / res_old;               // :2196
+            res_old = res;
+            if (t_abs(ratio) < prm.exit_tol) done = true;            // :2202
+        }
+    }
+    lm_reconstruct<T>(x, out);
+    out.res = res;
+    out.iters = iters;
+}
+
+// -------------------------------------------------------------------------------------------
 // Linear stage, formulation 2 -- solve_pnp_formulation_2_single_pattern :693-953,
 // helpers :3274-3375.  D^+ B = G (D^T B) with the pattern-constant G = (D^T D)^-1, so the
 // per-problem work is the moments of (bx, by) against [theta theta^T, theta, 1].

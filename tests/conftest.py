@@ -47,7 +47,7 @@ def load_golden(name):
     return {k: d[k] for k in d.files}
 
 
-SOLVER_GOLDENS = [n for n in golden_names() if n.split("_n")[0] in ("qeif", "lm", "linear_f1", "linear_f2")]
+SOLVER_GOLDENS = [n for n in golden_names() if n.split("_n")[0] in ("qeif", "lm", "linear_f1", "linear_f2", "eif2")]
 
 
 RES_NOISE_FLOOR = 1e-10

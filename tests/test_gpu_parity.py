@@ -46,7 +46,7 @@ def _workload(n, B, seed, quantized=True, noise=0.0):
     return P, K, w
 
 
-@pytest.mark.parametrize("method", ["qeif", "lm", "linear_f2", "linear_f1"])
+@pytest.mark.parametrize("method", ["qeif", "lm", "linear_f2", "linear_f1", "eif2"])
 @pytest.mark.parametrize("n,B,mapping", [(15, 4096, MAP_THREAD), (68, 4096, MAP_THREAD), (68, 1024, MAP_WARP),
                                         (1024, 96, MAP_WARP), (15, 4096, MAP_MOMENT), (68, 4096, MAP_MOMENT),
                                         (1024, 96, MAP_MOMENT)])
@@ -57,7 +57,8 @@ def test_cuda_matches_oracle_on_fresh_inputs(method, n, B, mapping):
     ref, stable, it_stable = oracle_stability(method, w["uv"], P, K)
     out = cuda_solve(method, w["uv"], P, K, mapping=mapping)
     compare_solutions(out, ref, mask=stable, iters_mask=it_stable)
-    assert stable.mean() > (0.7 if method == "lm" else 0.999)
+    # EIF2 with n = 1024 is sensitive at the 1e-10 cut (amplification ~1e3: 78 % of these inputs pass the cut; golden eif2_n1024: 5 of 6)
+    assert stable.mean() > {"lm": 0.7, "eif2": 0.99 if n < 1024 else 0.7}.get(method, 0.999)
 
 
 @pytest.mark.parametrize("method", ["qeif", "lm"])

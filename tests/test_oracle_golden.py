@@ -15,7 +15,9 @@ def test_oracle_matches_reference_solver(name):
     stats = compare_solutions(o, g, mask=g["stable"], iters_mask=g["iters_stable"])
     # LM is chaotic on part of its inputs; the stable fraction must be what the
     # survey measured, otherwise the tag (and the contract) is meaningless.
-    assert g["stable"].mean() > (0.7 if str(g["method"]) == "lm" else 0.999), stats
+    # (eif2_n1024 holds 6 problems, one of them sensitive at the 1e-10 cut)
+    floor = {"lm": 0.7, "eif2": 0.8}.get(str(g["method"]), 0.999)
+    assert g["stable"].mean() > floor, stats
 
 
 def test_oracle_solve_pnp_two_patterns():
