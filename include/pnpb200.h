@@ -186,6 +186,18 @@ int pnpb200_synth_batch(int dtype, int64_t b0, int64_t B, int n, const void* pat
                         void* uv, double* gt, double* R_gt, double* t_gt, void* stream);
 
 /*
+ * The workload of face_variation_test.py (:296-356): the same pose stream, but the pixels are the
+ * projection of a PERTURBED pattern -- a random direction of the 3 (n - 1) coordinates of all
+ * landmarks but `fixed_index` ("eye_c_51", :318; -1 = none fixed), scaled to perturb_radius_m
+ * (0.02, :319) -- while the solver keeps the golden pattern.  perturb [B,n,3] (f64, may be NULL)
+ * receives np_pattern_perturbation_dict of each problem, the input of pnpb200_fragility_accumulate.
+ */
+int pnpb200_synth_face_variation(int dtype, int64_t b0, int64_t B, int n, const void* pattern_f64,
+                                 const double* K, const pnpb200_synth* cfg, double perturb_radius_m,
+                                 int fixed_index, void* uv, double* gt, double* R_gt, double* t_gt,
+                                 double* perturb, void* stream);
+
+/*
  * Error reporting per problem.  Replaces check_if_the_sample_passed (TEST_TOOLBOX.py:55-62),
  * cal_LM_error_distances (:252-286), the error fields of compare_result_and_generate_result_dict
  * (:396-463) and the glue at random_stress_test.py:353-377.  Always FP64 outputs.
@@ -228,6 +240,38 @@ int pnpb200_stats_pass2(int64_t B, int nq, const double* const* est, const int64
  */
 int pnpb200_classify(int64_t B, const double* values, int64_t stride, double scale,
                      const double* bins, int n_bins, int32_t* class_id, void* stream);
+
+/*
+ * The analysis stage of face_variation_test.py (:631-759) for up to 4 error quantities at once.
+ *
+ * Selection of the top k problems by |value| -- what the script does by popping k items off heaps of
+ * (-|err|, idx) tuples (:631-653), so ties go to the SMALLER index -- as an exact radix select on the
+ * 96-bit key (bits of |value|, then ~global index), 12 digits of 8 bits, most significant first.
+ * pnpb200_topk_histogram counts, per quantity, the problems whose key starts with the
+ * n_digits_decided digits of (prefix_hi, prefix_lo), by their next digit: hist [nq, 256] (device,
+ * uint64).  The caller (workload.fragility_analysis) walks the histogram from 255 down to pick the
+ * next digit; across GPUs the histograms are summed, nothing else is exchanged.  idx0 = global index
+ * of this shard's first problem.  values[q]: device doubles with element stride[q].
+ */
+int pnpb200_topk_histogram(int64_t B, int64_t idx0, int nq, const double* const* values, const int64_t* stride,
+                           const uint64_t* prefix_hi, const uint32_t* prefix_lo, int n_digits_decided,
+                           uint64_t* hist, void* stream);
+
+/*
+ * get_most_fragile_point_and_perturbation_direction (face_variation_test.py:658-728) over the
+ * problems whose key is >= (threshold_hi, threshold_lo): per quantity, n_selected, the sum and the
+ * maximum of |value| (top_value_mean, value_max), count [nq, n] = how often each landmark carried
+ * the largest perturbation norm (strict >, first landmark wins), and gram [nq, 3n, 3n] = sum of
+ * v v^T over the selected perturbation vectors (upper 16 x 16 tiles only; mirror it), whose
+ * eigen-decomposition is the script's SVD of the m x 3n perturbation matrix (singular values =
+ * sqrt of the eigenvalues, right singular vectors = eigenvectors).  perturb [B, n, 3] from
+ * pnpb200_synth_face_variation; list [nq, list_capacity] receives the selected local indices.
+ * All outputs are device memory and are zeroed by the call.
+ */
+int pnpb200_fragility_accumulate(int64_t B, int64_t idx0, int nq, const double* const* values, const int64_t* stride,
+                                 const uint64_t* threshold_hi, const uint32_t* threshold_lo, const double* perturb,
+                                 int n, int64_t list_capacity, int64_t* list, uint64_t* n_selected, uint64_t* count,
+                                 double* value_sum, double* value_max, double* gram, void* stream);
 
 /*
  * FMA-pipe microbenchmark used by bench.py for the roofline denominator (MEASURED_PEAKS.json

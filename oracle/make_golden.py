@@ -292,6 +292,59 @@ def stress_report_case(PNPS, TTBX, tag, B, seed):
     print("%-28s stats_all max rel diff %.2e" % ("", np.abs(sa - stats_all).max()))
 
 
+def fragility_case(tag, B, seed):
+    """The analysis block of face_variation_test.py (:631-759).  The script executes on import, so its
+    function get_most_fragile_point_and_perturbation_direction is taken from the file's text at run
+    time (lines from its `def` to the next top-level `def`) and exec'd unmodified; the heaps are built
+    and popped exactly as :631-653 do.  Inputs: the oracle's perturbed-pattern workload and the
+    errors of the (pinned) oracle QEIF solve with the golden pattern."""
+    import heapq
+    from oracle import oracle as orc
+    from pnp_solver_test_b200 import patterns as pt
+    src = open(os.path.join(REF, "face_variation_test.py")).read().split("\n")
+    i0 = next(i for i, l in enumerate(src) if l.startswith("def get_most_fragile_point_and_perturbation_direction"))
+    i1 = next(i for i in range(i0 + 1, len(src)) if src[i].startswith("def "))
+    ns = {"np": np}
+    exec("\n".join(src[i0:i1]), ns)
+    ref_fn = ns["get_most_fragile_point_and_perturbation_direction"]
+    pat = pt.get_golden_pattern("Alexander")
+    keys = list(pat.keys())
+    P, K = pt.pattern_array(pat), pt.default_camera_matrix()
+    fixed = keys.index("eye_c_51")
+    w = orc.synth_face_variation(0, B, P, K, fixed, 0.02, orc.default_synth(seed=seed))
+    idx = [keys.index(k) for k in pt.LM_KEY_LIST_6]
+    o = orc.solve_batch("qeif", w["uv"][:, idx], P[idx], K)
+    err = np.stack([o["t"][:, 2] - w["gt"][:, 0], o["euler"][:, 0] - w["gt"][:, 1], o["euler"][:, 2] - w["gt"][:, 2],
+                    o["euler"][:, 1] - w["gt"][:, 3]], axis=1)      # depth, roll, pitch, yaw
+    result_list = [dict(np_pattern_perturbation_dict={k: w["perturb"][b, j].reshape(3, 1) for j, k in enumerate(keys)})
+                   for b in range(B)]
+    out = {}
+    k = int(B * 0.1)
+    for q, name in enumerate(("depth", "roll", "pitch", "yaw")):
+        heap = []
+        for b in range(B):
+            heapq.heappush(heap, (-abs(err[b, q]), b))              # :555-560 of the script
+        top = []
+        for _ in range(k):
+            e = list(heapq.heappop(heap)); e[0] *= -1; top.append(e)   # :641-653
+        r = quiet(ref_fn, pat, result_list, top)
+        out[name + "_count"] = np.array([r["fragile_point_count_dict"][kk] for kk in keys])
+        out[name + "_sorted_keys"] = np.array([kk for _, kk in r["fragile_point_sorted_list"]])
+        out[name + "_similarity"] = np.array(r["top_similarity_list"])
+        out[name + "_directions"] = np.array([[d[kk].reshape(3) for kk in keys] for d in r["top_perturbation_list"]])
+        out[name + "_value_max"], out[name + "_value_mean"] = r["value_max"], r["top_value_mean"]
+        mine = orc.fragility_of(np.abs(err[:, q]), w["perturb"], keys)
+        dsim = np.abs(mine["top_similarity"] - out[name + "_similarity"]).max()
+        ddir = max(min(np.abs(mine["top_perturbation"][i] - out[name + "_directions"][i]).max(),
+                       np.abs(mine["top_perturbation"][i] + out[name + "_directions"][i]).max()) for i in range(5))
+        print("%-28s %-5s counts equal %s | sorted equal %s | d similarity %.2e | d direction %.2e | d mean %.2e"
+              % (tag, name, (np.array([mine["fragile_point_count_dict"][kk] for kk in keys]) == out[name + "_count"]).all(),
+                 [kk for _, kk in mine["fragile_point_sorted_list"]] == list(out[name + "_sorted_keys"]), dsim, ddir,
+                 abs(mine["top_value_mean"] - out[name + "_value_mean"])))
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, pattern=P, keys=np.array(keys), fixed_index=fixed, seed=seed,
+                        uv=w["uv"], gt=w["gt"], perturb=w["perturb"], err=err, **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     PNPS, TTBX = load_reference()
@@ -332,6 +385,8 @@ def main():
         solve_pnp_case(PNPS, TTBX, "solve_pnp_two_patterns", 96, 60)
     if not only or "stress_report" in only:
         stress_report_case(PNPS, TTBX, "stress_report", 256, 61)
+    if not only or "fragility" in only:
+        fragility_case("fragility", 600, 62)
     if not only or "euler" in only:
         print("euler fixture:", euler_fixture(), "vectors")
 

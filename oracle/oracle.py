@@ -198,3 +198,45 @@ def stats_of(est, gt=None):
     mae_mean = np.linalg.norm(err - mean, ord=1) / n
     max_dev = np.linalg.norm(err - mean, ord=np.inf)
     return (n, ratio_mean, mean, std, max_dev, mae_gt, mae_mean)
+
+
+def synth_face_variation(b0, B, P, K, fixed_index, radius_m=0.02, cfg=None, n_threads=0):
+    """face_variation_test.py:296-356 workload: pixels of a randomly perturbed pattern."""
+    P, K = _f64(P), _f64(K)
+    n = P.shape[0]
+    cfg = cfg or default_synth()
+    uv, gt, pert = np.zeros((B, n, 2)), np.zeros((B, 4)), np.zeros((B, n, 3))
+    lib().pnp_oracle_synth_face_variation(C.c_int64(b0), C.c_int64(B), C.c_int(n), _p(P), _p(K), C.byref(cfg),
+                                          C.c_double(radius_m), C.c_int(fixed_index), _p(uv), _p(gt), None, None,
+                                          _p(pert), C.c_int(n_threads))
+    return dict(uv=uv, gt=gt, perturb=pert)
+
+
+def fragility_of(abs_err, perturb, keys, ratio=0.1, k_top_direction=5):
+    """NumPy restatement of the analysis block of face_variation_test.py for ONE error quantity:
+    the heap selection (:631-653: pop int(len * ratio) items off a heap of (-|err|, idx), i.e. largest
+    |err| first, smaller idx on ties) and get_most_fragile_point_and_perturbation_direction (:658-728).
+    abs_err [B]; perturb [B,n,3] in key order.  Returns the script's result_dict with arrays."""
+    abs_err = np.asarray(abs_err, np.float64)
+    perturb = np.asarray(perturb, np.float64)
+    B, n = perturb.shape[0], perturb.shape[1]
+    k = int(B * ratio)                                               # :632
+    order = sorted(range(B), key=lambda i: (-abs_err[i], i))[:k]     # heappop order (:641-646)
+    count = {key: 0 for key in keys}                                 # :661-664
+    rows, vsum = [], 0.0
+    for i in order:
+        vsum += abs_err[i]
+        norms = np.linalg.norm(perturb[i], axis=1)                   # :672
+        nmax, kmax = -1.0, None
+        for j, key in enumerate(keys):                               # strict '>', first wins (:674-676)
+            if norms[j] > nmax:
+                nmax, kmax = norms[j], key
+        count[kmax] += 1
+        rows.append(perturb[i].reshape(-1))                          # vstack of the (3,1) blocks (:681)
+    M = np.array(rows)                                               # m x 3n (:684)
+    sorted_list = sorted([(count[key], key) for key in keys], reverse=True)    # :694-695
+    u, s, vh = np.linalg.svd(M)                                      # :699
+    return dict(fragile_point_count_dict=count, fragile_point_sorted_list=sorted_list,
+                top_perturbation=vh[:k_top_direction].reshape(k_top_direction, n, 3),
+                top_similarity=s[:k_top_direction], value_max=abs_err[order[0]],
+                top_value_mean=vsum / float(len(order)), selected=np.array(order))

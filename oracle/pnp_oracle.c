@@ -1089,7 +1089,20 @@ typedef struct {
 
 typedef struct {
     int64_t b0; int n; const double *P, *K; const oracle_synth_t *cfg; double *uv, *gt, *R_gt, *t_gt;
+    double perturb_radius; int fixed_idx; double *perturb;   /* face_variation_test.py:317-345 */
 } synth_ctx_t;
+
+/* three N(0,1) draws for point i of problem gidx (the pattern perturbation) */
+static void perturb_normals(uint64_t gidx, int i, uint32_t k0, uint32_t k1, double *z)
+{
+    uint32_t a[4], b[4];
+    double r1, r2;
+    philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 16u + (uint32_t)i, 2u, k0, k1, a);
+    philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), 16u + (uint32_t)i, 3u, k0, k1, b);
+    r1 = sqrt(-2.0 * log(1.0 - u01(a[0], a[1]))); r2 = sqrt(-2.0 * log(1.0 - u01(b[0], b[1])));
+    z[0] = r1 * cos(2.0 * M_PI * u01(a[2], a[3])); z[1] = r1 * sin(2.0 * M_PI * u01(a[2], a[3]));
+    z[2] = r2 * cos(2.0 * M_PI * u01(b[2], b[3]));
+}
 
 static void synth_range(int64_t lo, int64_t hi, void *vctx)
 {
@@ -1098,7 +1111,8 @@ static void synth_range(int64_t lo, int64_t hi, void *vctx)
     int n = c->n;
     int64_t bb;
     uint32_t k0 = (uint32_t)cfg->seed, k1 = (uint32_t)(cfg->seed >> 32);
-    double *uvw = (double *)malloc(sizeof(double) * (size_t)n * 3);
+    double *uvw = (double *)malloc(sizeof(double) * (size_t)n * 6);
+    double *Pp = uvw + (size_t)n * 3;                 /* the (perturbed) pattern the pixels come from */
     for (bb = lo; bb < hi; ++bb) {
         uint64_t gidx = (uint64_t)(c->b0 + bb);
         uint32_t r[12];
@@ -1115,7 +1129,28 @@ static void synth_range(int64_t lo, int64_t hi, void *vctx)
         fy    = -cfg->fov_max_deg + 2.0 * cfg->fov_max_deg * u01(r[10], r[11]);
         t[0] = depth * tan(fx * DEG2RAD); t[1] = depth * tan(fy * DEG2RAD); t[2] = depth;
         pnp_oracle_R_from_euler(roll, yaw, pitch, 1, R);
-        pnp_oracle_project(n, c->P, c->K, R, t, 0, 1.0, uvw);
+        memcpy(Pp, c->P, sizeof(double) * (size_t)n * 3);
+        if (c->perturb_radius > 0.0) {
+            /* unit_vec of a 3 (n - 1) standard normal vector times the radius, one landmark fixed
+             * (face_variation_test.py:321-345; the i.i.d. draws make the reshape order immaterial) */
+            double ss = 0.0, sc, z[3];
+            for (i = 0; i < n; ++i) {
+                if (i == c->fixed_idx) continue;
+                perturb_normals(gidx, i, k0, k1, z);
+                ss += z[0] * z[0] + z[1] * z[1] + z[2] * z[2];
+            }
+            sc = c->perturb_radius / sqrt(ss);
+            for (i = 0; i < n; ++i) {
+                int k;
+                z[0] = z[1] = z[2] = 0.0;
+                if (i != c->fixed_idx) perturb_normals(gidx, i, k0, k1, z);
+                for (k = 0; k < 3; ++k) {
+                    Pp[3 * i + k] += sc * z[k];
+                    if (c->perturb) c->perturb[((size_t)bb * n + i) * 3 + k] = sc * z[k];
+                }
+            }
+        }
+        pnp_oracle_project(n, Pp, c->K, R, t, 0, 1.0, uvw);
         for (i = 0; i < n; ++i) {
             double u = uvw[3 * i], v = uvw[3 * i + 1];
             /* quantise first (random_stress_test.py:290), then add noise (LM_noise_test.py:272-286) */
@@ -1145,5 +1180,18 @@ ORACLE_API void pnp_oracle_synth(int64_t b0, int64_t B, int n, const double *P, 
 {
     synth_ctx_t c;
     c.b0 = b0; c.n = n; c.P = P; c.K = K; c.cfg = cfg; c.uv = uv; c.gt = gt; c.R_gt = R_gt; c.t_gt = t_gt;
+    c.perturb_radius = 0.0; c.fixed_idx = -1; c.perturb = NULL;
+    parallel_for(B, n_threads, 256, synth_range, &c);
+}
+
+/* the face_variation_test.py workload: pixels of a perturbed pattern; perturb [B,n,3] */
+ORACLE_API void pnp_oracle_synth_face_variation(int64_t b0, int64_t B, int n, const double *P, const double *K,
+                                                const oracle_synth_t *cfg, double radius_m, int fixed_index,
+                                                double *uv, double *gt, double *R_gt, double *t_gt,
+                                                double *perturb, int n_threads)
+{
+    synth_ctx_t c;
+    c.b0 = b0; c.n = n; c.P = P; c.K = K; c.cfg = cfg; c.uv = uv; c.gt = gt; c.R_gt = R_gt; c.t_gt = t_gt;
+    c.perturb_radius = radius_m; c.fixed_idx = fixed_index; c.perturb = perturb;
     parallel_for(B, n_threads, 256, synth_range, &c);
 }

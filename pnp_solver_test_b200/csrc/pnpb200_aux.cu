@@ -126,9 +126,22 @@ PNP_DEV double u01(uint32_t hi, uint32_t lo)
     return (double)v * (1.0 / 9007199254740992.0);
 }
 
+// three N(0,1) draws for point i of problem gidx (pattern perturbation, face_variation_test.py:324)
+PNP_DEV void perturb_normals(uint32_t g0, uint32_t g1, int i, uint32_t k0, uint32_t k1, double (&z)[3])
+{
+    uint32_t a[4], b[4];
+    philox4x32_10(g0, g1, 16u + (uint32_t)i, 2u, k0, k1, a);
+    philox4x32_10(g0, g1, 16u + (uint32_t)i, 3u, k0, k1, b);
+    const double r1 = sqrt(-2.0 * log(1.0 - u01(a[0], a[1]))), r2 = sqrt(-2.0 * log(1.0 - u01(b[0], b[1])));
+    double sn, cs;
+    sincos(2.0 * 3.14159265358979323846 * u01(a[2], a[3]), &sn, &cs);
+    z[0] = r1 * cs; z[1] = r1 * sn;
+    z[2] = r2 * cos(2.0 * 3.14159265358979323846 * u01(b[2], b[3]));
+}
+
 template <typename T>
 __global__ void k_synth(long long b0, long long B, int n, const double* __restrict__ pattern, KMat K, pnpb200_synth cfg,
-                        void* uv, double* gt, double* R_gt, double* t_gt)
+                        void* uv, double* gt, double* R_gt, double* t_gt, double perturb_radius, int fixed_idx, double* perturb)
 {
     // one warp per problem: lane 0's pose is broadcast, lanes stride over the points
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -152,9 +165,32 @@ __global__ void k_synth(long long b0, long long B, int n, const double* __restri
     double Rm[9], tv[3];
     tv[0] = depth * tan(fx * kD2R); tv[1] = depth * tan(fy * kD2R); tv[2] = depth;
     R_from_euler(roll, yaw, pitch, true, Rm);
+    // face_variation_test.py:317-345: a random direction of the 3 (n - 1) pattern coordinates (one
+    // landmark stays fixed), scaled to perturb_radius, moves the pattern the pixels are generated from
+    double pscale = 0.0;
+    if (perturb_radius > 0.0) {
+        double ss = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            if (i == fixed_idx) continue;
+            double z[3];
+            perturb_normals(g0, g1, i, k0, k1, z);
+            ss += z[0] * z[0] + z[1] * z[1] + z[2] * z[2];
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+        pscale = perturb_radius / sqrt(ss);
+    }
     for (int i = lane; i < n; i += 32) {
         double o[3];
-        project_point(K.k, Rm, tv, pattern[3 * i], pattern[3 * i + 1], pattern[3 * i + 2], false, 1.0, o);
+        double px = pattern[3 * i], py = pattern[3 * i + 1], pz = pattern[3 * i + 2];
+        if (perturb_radius > 0.0) {
+            double z[3] = { 0.0, 0.0, 0.0 };
+            if (i != fixed_idx) perturb_normals(g0, g1, i, k0, k1, z);
+            const double d0 = pscale * z[0], d1 = pscale * z[1], d2 = pscale * z[2];
+            px += d0; py += d1; pz += d2;
+            if (perturb) { perturb[((size_t)w * n + i) * 3] = d0; perturb[((size_t)w * n + i) * 3 + 1] = d1; perturb[((size_t)w * n + i) * 3 + 2] = d2; }
+        }
+        project_point(K.k, Rm, tv, px, py, pz, false, 1.0, o);
         double u = o[0], v = o[1];
         if (cfg.is_quantized) { u = rint(u / cfg.quantize_q) * cfg.quantize_q; v = rint(v / cfg.quantize_q) * cfg.quantize_q; }
         if (cfg.noise_sigma_px > 0.0) {
@@ -808,10 +844,11 @@ int pnpb200_project(int dtype, int64_t B, int n, const void* pattern, const doub
     return PNPB200_OK;
 }
 
-int pnpb200_synth_batch(int dtype, int64_t b0, int64_t B, int n, const void* pattern_f64, const double* K,
-                        const pnpb200_synth* cfg, void* uv, double* gt, double* R_gt, double* t_gt, void* stream)
+static int synth_launch(int dtype, int64_t b0, int64_t B, int n, const void* pattern_f64, const double* K,
+                        const pnpb200_synth* cfg, void* uv, double* gt, double* R_gt, double* t_gt, double radius, int fixed_idx,
+                        double* perturb, void* stream)
 {
-    if (B < 0 || n < 1 || !pattern_f64 || !K || !uv) return PNPB200_EINVAL;
+    if (B < 0 || n < 1 || !pattern_f64 || !K || !uv || radius < 0.0) return PNPB200_EINVAL;
     if (B == 0) return PNPB200_OK;
     pnpb200_synth c;
     if (cfg) c = *cfg; else pnpb200_default_synth(&c);
@@ -820,10 +857,24 @@ int pnpb200_synth_batch(int dtype, int64_t b0, int64_t B, int n, const void* pat
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = grid_for(B * 32, 256);
     DISPATCH_DTYPE(dtype,
-                   (k_synth<double><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt)),
-                   (k_synth<float><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt)));
+                   (k_synth<double><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt, radius, fixed_idx, perturb)),
+                   (k_synth<float><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt, radius, fixed_idx, perturb)));
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
+}
+
+int pnpb200_synth_batch(int dtype, int64_t b0, int64_t B, int n, const void* pattern_f64, const double* K,
+                        const pnpb200_synth* cfg, void* uv, double* gt, double* R_gt, double* t_gt, void* stream)
+{
+    return synth_launch(dtype, b0, B, n, pattern_f64, K, cfg, uv, gt, R_gt, t_gt, 0.0, -1, nullptr, stream);
+}
+
+int pnpb200_synth_face_variation(int dtype, int64_t b0, int64_t B, int n, const void* pattern_f64, const double* K,
+                                 const pnpb200_synth* cfg, double perturb_radius_m, int fixed_index, void* uv, double* gt,
+                                 double* R_gt, double* t_gt, double* perturb, void* stream)
+{
+    if (!(perturb_radius_m > 0.0) || fixed_index >= n || (fixed_index < 0 ? n < 1 : n < 2)) return PNPB200_EINVAL;
+    return synth_launch(dtype, b0, B, n, pattern_f64, K, cfg, uv, gt, R_gt, t_gt, perturb_radius_m, fixed_index, perturb, stream);
 }
 
 int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const void* uv, const double* K,

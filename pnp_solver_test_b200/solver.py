@@ -324,6 +324,10 @@ class PNP_SOLVER(object):
         """PNP_SOLVER_LIB.py:2567-2769 (LM_key_list is ignored there too: all points, :2576, :2597)"""
         return self._solve_single("lm", np_point_image_dict, np_point_3d_pretransfer_dict, list(np_point_3d_pretransfer_dict.keys()))
 
+    def solve_pnp_EIF2_single_pattern(self, np_point_image_dict, np_point_3d_pretransfer_dict, LM_key_list=None):
+        """PNP_SOLVER_LIB.py:2001-2276 (all points, like LM: f2_get_P / f2_get_B_xy without a key list, :2012, :2045)"""
+        return self._solve_single("eif2", np_point_image_dict, np_point_3d_pretransfer_dict, list(np_point_3d_pretransfer_dict.keys()))
+
     def solve_pnp_formulation_2_single_pattern(self, np_point_image_dict, np_point_3d_pretransfer_dict, LM_key_list=None):
         """PNP_SOLVER_LIB.py:693-953"""
         return self._solve_single("linear_f2", np_point_image_dict, np_point_3d_pretransfer_dict, list(np_point_3d_pretransfer_dict.keys()))

@@ -232,3 +232,131 @@ class _LazyDict(object):
 
     def result(self):
         return self._unpack(self._pending.result())
+
+
+# ------------------------------------------------------------------------------------------------
+# face_variation_test.py: perturbed-pattern workload and the "most fragile point" analysis
+# ------------------------------------------------------------------------------------------------
+def synth_face_variation(b0, B, pattern, K, fixed_index, perturb_radius_m=0.02, cfg=None, dtype=torch.float64, device=None):
+    """face_variation_test.py:296-356 for problems b0..b0+B-1 of the global stream: pixels of a
+    randomly perturbed pattern (unit direction of the 3(n-1) coordinates of every landmark but
+    `fixed_index`, times perturb_radius_m).  Returns dict(uv, gt, perturb [B,n,3] f64)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    pat = torch.as_tensor(np.ascontiguousarray(np.asarray(pattern, dtype=np.float64)), device=device)
+    n = int(pat.shape[0])
+    uv = torch.empty((B, n, 2), dtype=dtype, device=device)
+    gt = torch.empty((B, 4), dtype=torch.float64, device=device)
+    pert = torch.empty((B, n, 3), dtype=torch.float64, device=device)
+    Kh, Kp = _k_host(K)
+    PD = C.POINTER(C.c_double)
+    with torch.cuda.device(device):
+        check(lib.pnpb200_synth_face_variation(C.c_int(_dtype_code(dtype)), C.c_int64(int(b0)), C.c_int64(int(B)), C.c_int(n),
+                                               ptr(pat), Kp, C.byref(cfg) if cfg is not None else None,
+                                               C.c_double(float(perturb_radius_m)), C.c_int(int(fixed_index)), ptr(uv),
+                                               C.cast(ptr(gt), PD), None, None, C.cast(ptr(pert), PD), _stream_ptr(device)),
+              "pnpb200_synth_face_variation")
+    _lib.count_launch()
+    return dict(uv=uv, gt=gt, perturb=pert)
+
+
+def topk_thresholds(values, k, idx0=0, group=None):
+    """Exact k-th largest key (|value| bits, then smaller global index first) of each quantity over
+    ALL ranks' shards: 12 histogram kernels; the 256-bin histograms are the only thing all-reduced.
+    values: list of 1-D FP64 CUDA views of this rank's shard.  Returns (hi [nq] uint64, lo [nq] uint32)
+    as Python ints -- every key >= (hi, lo) is in the top k."""
+    import torch.distributed as dist
+    nq = len(values)
+    dev = values[0].device
+    B = int(values[0].shape[0])
+    PD = C.POINTER(C.c_double)
+    val_a = (PD * nq)(*[C.cast(ptr(v), PD) for v in values])
+    str_a = (C.c_int64 * nq)(*[int(v.stride(0)) if B else 1 for v in values])
+    hi, lo, rem = [0] * nq, [0] * nq, [int(k)] * nq
+    hist = torch.zeros((nq, 256), dtype=torch.int64, device=dev)
+    for d in range(12):
+        hi_a = (C.c_uint64 * nq)(*hi)
+        lo_a = (C.c_uint32 * nq)(*lo)
+        with torch.cuda.device(dev):
+            check(lib.pnpb200_topk_histogram(C.c_int64(B), C.c_int64(int(idx0)), C.c_int(nq), val_a, str_a, hi_a, lo_a, C.c_int(d),
+                                             C.cast(ptr(hist), C.POINTER(C.c_uint64)), _stream_ptr(dev)), "pnpb200_topk_histogram")
+        _lib.count_launch()
+        _all_reduce(hist, dist.ReduceOp.SUM if dist.is_available() else None, group)
+        h = hist.cpu().numpy()
+        for q in range(nq):
+            digit = 0
+            for dg in range(255, -1, -1):                 # from the largest digit down
+                if h[q, dg] >= rem[q]:
+                    digit = dg
+                    break
+                rem[q] -= int(h[q, dg])
+            if d < 8:
+                hi[q] |= digit << (56 - 8 * d)
+            else:
+                lo[q] |= digit << (24 - 8 * (d - 8))
+    return hi, lo
+
+
+def fragility_analysis(abs_err, perturb, idx0=0, ratio=0.1, k_top_direction=5, total=None, group=None, keys=None):
+    """The analysis block of face_variation_test.py (:631-759) on the device, over ALL ranks' shards.
+
+    abs_err: list of up to four 1-D FP64 CUDA views (|depth err|, |roll err|, ...) of this rank's
+    shard; perturb [B,n,3] from synth_face_variation; idx0 = global index of the shard's first
+    problem; total = number of problems over all ranks (default: this shard).  The top
+    int(total * ratio) problems of each quantity are selected exactly as the script's heaps do.
+    Returns one dict per quantity with the script's result_dict fields as arrays:
+    fragile_point_count [n], fragile_point_order (landmark indices, most fragile first),
+    top_perturbation [k_top_direction, n, 3], top_similarity [k_top_direction], value_max,
+    top_value_mean, n_selected; with keys (landmark names in pattern order) also
+    fragile_point_count_dict and fragile_point_sorted_list = [(count, key)] sorted like the script
+    (reverse tuple order, :694-695)."""
+    import torch.distributed as dist
+    nq = len(abs_err)
+    dev = perturb.device
+    B, n = int(perturb.shape[0]), int(perturb.shape[1])
+    total = B if total is None else int(total)
+    k = int(total * ratio)                                                       # :632
+    if k < 1:
+        raise ValueError("fragility_analysis: nothing to select (total * ratio < 1)")
+    hi, lo = topk_thresholds(abs_err, k, idx0, group)
+    PD = C.POINTER(C.c_double)
+    val_a = (PD * nq)(*[C.cast(ptr(v), PD) for v in abs_err])
+    str_a = (C.c_int64 * nq)(*[int(v.stride(0)) if B else 1 for v in abs_err])
+    D = 3 * n
+    cap = max(1, min(B, k))
+    lst = torch.empty((nq, cap), dtype=torch.int64, device=dev)
+    nsel = torch.zeros((nq,), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((nq, n), dtype=torch.int64, device=dev)
+    vsum = torch.zeros((nq,), dtype=torch.float64, device=dev)
+    vmax = torch.zeros((nq,), dtype=torch.float64, device=dev)
+    gram = torch.zeros((nq, D, D), dtype=torch.float64, device=dev)
+    pert = perturb.contiguous()
+    PU = C.POINTER(C.c_uint64)
+    with torch.cuda.device(dev):
+        check(lib.pnpb200_fragility_accumulate(C.c_int64(B), C.c_int64(int(idx0)), C.c_int(nq), val_a, str_a,
+                                               (C.c_uint64 * nq)(*hi), (C.c_uint32 * nq)(*lo), C.cast(ptr(pert), PD), C.c_int(n),
+                                               C.c_int64(cap), C.cast(ptr(lst), C.POINTER(C.c_int64)), C.cast(ptr(nsel), PU),
+                                               C.cast(ptr(cnt), PU), C.cast(ptr(vsum), PD), C.cast(ptr(vmax), PD),
+                                               C.cast(ptr(gram), PD), _stream_ptr(dev)), "pnpb200_fragility_accumulate")
+    _lib.count_launch(2)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t_ in (nsel, cnt, vsum, gram):
+            dist.all_reduce(t_, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(vmax, op=dist.ReduceOp.MAX, group=group)
+    out = []
+    G = gram.cpu().numpy()
+    for q in range(nq):
+        g = np.triu(G[q]) + np.triu(G[q], 1).T                                  # the kernel fills the upper tiles
+        w, v = np.linalg.eigh(g)
+        order = np.argsort(w)[::-1][:k_top_direction]
+        m = int(nsel[q].item())
+        c = cnt[q].cpu().numpy()
+        out.append(dict(
+            n_selected=m, fragile_point_count=c,
+            fragile_point_order=np.array(sorted(range(n), key=lambda i: (-int(c[i]), i))),
+            top_similarity=np.sqrt(np.maximum(w[order], 0.0)),                    # singular values of the m x 3n matrix
+            top_perturbation=v[:, order].T.reshape(-1, n, 3),                     # right singular vectors (sign is arbitrary)
+            value_max=float(vmax[q].item()), top_value_mean=float(vsum[q].item()) / max(m, 1)))
+        if keys is not None:
+            out[-1]["fragile_point_count_dict"] = {key: int(c[i]) for i, key in enumerate(keys)}
+            out[-1]["fragile_point_sorted_list"] = sorted([(int(c[i]), key) for i, key in enumerate(keys)], reverse=True)
+    return out

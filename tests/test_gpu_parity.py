@@ -178,7 +178,7 @@ def test_pnp_solver_class_is_a_drop_in():
     R, t, t3, roll, yaw, pitch, res = one.solve_pnp_LM_single_pattern(pts, one.np_point_3d_pretransfer_dict_list[0])
     assert np.abs(R - gl["R"][b]).max() < 1e-9 and abs(res - gl["res_norm"][b]) < 1e-9 and one.last_iters == 14
     for meth, name in (("solve_pnp_formulation_2_single_pattern", "linear_f2_n15_q"), ("solve_pnp_single_pattern", "linear_f1_n15_q"),
-                       ("solve_pnp_QEIF_single_pattern", "qeif_n15_q")):
+                       ("solve_pnp_QEIF_single_pattern", "qeif_n15_q"), ("solve_pnp_EIF2_single_pattern", "eif2_n15_q")):
         gg = load_golden(name)
         pts = {k: np.array([[gg["uv"][0, i, 0]], [gg["uv"][0, i, 1]], [1.0]]) for i, k in enumerate(keys)}
         r = getattr(one, meth)(pts, one.np_point_3d_pretransfer_dict_list[0])

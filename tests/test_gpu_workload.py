@@ -147,3 +147,43 @@ def test_statistics_kernels_both_paths_match_numpy(n_class, nq):
             ref = np.array(orc.stats_of(est[sel, q], gt[sel, q]), dtype=np.float64)
             assert row[0] == ref[0]
             assert np.abs(row[1:] - ref[1:]).max() < 1e-11 * max(1.0, np.abs(ref[1:]).max()), (q, c, row, ref)
+
+
+def test_face_variation_workload_and_fragility_analysis_match_reference():
+    """face_variation_test.py: perturbed-pattern generator vs the oracle; device top-10 % selection,
+    fragile-point counts and perturbation directions vs the script's own function (golden) and, on a
+    larger batch with ties, vs its NumPy restatement."""
+    from pnp_solver_test_b200 import workload as wl
+    import pnp_solver_test_b200 as pnp
+    g = load_golden("fragility")
+    keys = [str(k) for k in g["keys"]]
+    fixed = int(g["fixed_index"])
+    w = wl.synth_face_variation(0, 600, g["pattern"], g["K"], fixed, 0.02, cfg=pnp.default_synth(seed=int(g["seed"])))
+    assert np.abs(w["perturb"].cpu().numpy() - g["perturb"]).max() < 1e-15
+    assert (np.abs(w["uv"].cpu().numpy() - g["uv"]) > 1e-8).mean() < 1e-3
+    assert np.abs(w["gt"].cpu().numpy() - g["gt"]).max() < 1e-12
+    err = dev(np.abs(g["err"]))
+    res = wl.fragility_analysis([err[:, q] for q in range(4)], dev(g["perturb"]), keys=keys)
+    for q, name in enumerate(("depth", "roll", "pitch", "yaw")):
+        r = res[q]
+        assert r["n_selected"] == 60
+        assert np.array_equal(r["fragile_point_count"], g[name + "_count"])
+        assert [k for _, k in r["fragile_point_sorted_list"]] == [str(k) for k in g[name + "_sorted_keys"]]
+        assert np.abs(r["top_similarity"] - g[name + "_similarity"]).max() < 1e-12
+        for i in range(5):
+            d, ref = r["top_perturbation"][i], g[name + "_directions"][i]
+            assert min(np.abs(d - ref).max(), np.abs(d + ref).max()) < 1e-8
+        assert r["value_max"] == g[name + "_value_max"] and abs(r["top_value_mean"] - g[name + "_value_mean"]) < 1e-14
+    # larger batch, 68 landmarks, quantised errors (many exact ties at the selection threshold), shard offset
+    rng = np.random.default_rng(3)
+    B, n = 50000, 68
+    e = np.round(rng.gamma(2.0, 1.0, (B, 2)), 1)                    # ties by construction
+    pert = rng.normal(size=(B, n, 3)) * rng.uniform(0.1, 1.0, (B, n, 1))
+    res = wl.fragility_analysis([dev(e)[:, 0], dev(e)[:, 1]], dev(pert), idx0=0)
+    kk = ["k%03d" % i for i in range(n)]
+    for q in range(2):
+        ref = orc.fragility_of(e[:, q], pert, kk)
+        assert res[q]["n_selected"] == 5000
+        assert np.array_equal(res[q]["fragile_point_count"], np.array([ref["fragile_point_count_dict"][k] for k in kk]))
+        assert np.abs(res[q]["top_similarity"] / ref["top_similarity"] - 1).max() < 1e-10
+        assert res[q]["value_max"] == ref["value_max"] and abs(res[q]["top_value_mean"] - ref["top_value_mean"]) < 1e-12

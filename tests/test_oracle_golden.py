@@ -79,3 +79,36 @@ def test_oracle_synth_is_shard_invariant_and_sane():
     s = orc.solve_batch("qeif", w["uv"][:, idx], P15[idx], K)
     r = orc.report_batch(P15, w["uv"], K, s["R"], s["t"], s["euler"], w["gt"])
     assert r["flags"].all(axis=1).mean() > 0.95
+
+
+def test_oracle_fragility_analysis_matches_reference():
+    """face_variation_test.py's heap selection + get_most_fragile_point_and_perturbation_direction
+    (the script's own function, exec'd unmodified by oracle/make_golden.py) on 600 problems."""
+    g = load_golden("fragility")
+    keys = [str(k) for k in g["keys"]]
+    for q, name in enumerate(("depth", "roll", "pitch", "yaw")):
+        r = orc.fragility_of(np.abs(g["err"][:, q]), g["perturb"], keys)
+        assert np.array_equal(np.array([r["fragile_point_count_dict"][k] for k in keys]), g[name + "_count"])
+        assert [k for _, k in r["fragile_point_sorted_list"]] == [str(k) for k in g[name + "_sorted_keys"]]
+        assert np.abs(r["top_similarity"] - g[name + "_similarity"]).max() < 1e-12
+        for i in range(5):
+            d, ref = r["top_perturbation"][i], g[name + "_directions"][i]
+            assert min(np.abs(d - ref).max(), np.abs(d + ref).max()) < 1e-9
+        assert r["value_max"] == g[name + "_value_max"] and abs(r["top_value_mean"] - g[name + "_value_mean"]) < 1e-15
+
+
+def test_oracle_face_variation_workload():
+    from pnp_solver_test_b200 import patterns as pt
+    pat = pt.get_golden_pattern()
+    keys = list(pat.keys())
+    P, K = pt.pattern_array(pat), pt.default_camera_matrix()
+    fixed = keys.index("eye_c_51")
+    w = orc.synth_face_variation(3, 500, P, K, fixed, 0.02)
+    assert np.abs(np.linalg.norm(w["perturb"].reshape(500, -1), axis=1) - 0.02).max() < 1e-15   # unit_vec * radius (:326-331)
+    assert (w["perturb"][:, fixed] == 0).all() and (np.abs(w["perturb"]).sum(axis=2) > 0)[:, np.arange(15) != fixed].all()
+    plain = orc.synth(3, 500, P, K)
+    assert np.array_equal(plain["gt"], w["gt"])                     # same pose stream
+    assert 0.2 < np.abs(plain["uv"] - w["uv"]).max() < 60.0          # a 2 cm pattern change moves pixels, not poses
+    g = load_golden("fragility")
+    again = orc.synth_face_variation(0, 600, g["pattern"], g["K"], int(g["fixed_index"]), 0.02, orc.default_synth(seed=int(g["seed"])))
+    assert np.array_equal(again["perturb"], g["perturb"]) and np.array_equal(again["uv"], g["uv"])
