@@ -11,6 +11,9 @@ shapes, timed here for the record (profiles/).  Device-timed with CUDA events, i
     fixed pose t=(0,0,1), grid 30/112 px, QEIF-6, FP64 vs FP32: yaw-error mean/std/MAE per cell
  3  large n: 1024-point pattern, 100k problems: linear stage (F2) alone, and LM
  4  64M x 68-point LM, sharded by problem index over the visible ranks (torchrun) or one GPU
+ 5   face_variation_test.py: perturbed-pattern workload, QEIF-6 solve, error report,
+    statistics, top-10 % selection + fragile-point / perturbation-direction analysis, sharded like 4
+ 6   EIF2 beside LM and QEIF on the stress workload, 15 and 68 landmarks: pass rate and rate
 """
 import argparse
 import json
@@ -136,6 +139,58 @@ def config4(scale):
             "yaw_MAE_deg": float(st["yaw"]["all"][5]), "hbm_gb_inputs_per_gpu": B * 68 * 16 / 1e9}
 
 
+def config5(scale):
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    total = int((1 << 20) * world * scale)
+    lo, hi = wl.shard_range(total, rank, world)
+    B = hi - lo
+    K = pt.default_camera_matrix()
+    pat = pt.get_golden_pattern("Alexander")
+    keys = list(pat.keys())
+    P = pt.pattern_array(pat)
+    solver = pnp.PNP_SOLVER(K, [pat], [1.0])
+    fixed = keys.index("eye_c_51")                                  # face_variation_test.py:318
+
+    def full():
+        w = wl.synth_face_variation(lo, B, P, K, fixed, 0.02)
+        o = solver.solve_pnp_batch(w["uv"])
+        rep = wl.report_batch(P, w["uv"], K, o["R"], o["t"], o["euler"], w["gt"])
+        st = wl.error_statistics(rep["report"], w["gt"], lazy=True)
+        ae = rep["report"][:, :4].abs()
+        fr = wl.fragility_analysis([ae[:, q] for q in range(4)], w["perturb"], idx0=lo, total=total, keys=keys)
+        return st, fr, rep
+    ms, (st, fr, rep) = timed(full, reps=5, warm=3)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    st = st.result()
+    return {"config": 5, "workload": "face_variation_test: %d problems over %d GPU(s), Alexander 15 pts perturbed by a 2 cm random direction, "
+                                     "QEIF-6 with the golden pattern, report, statistics, top-10 %% fragility analysis" % (total, world),
+            "ms_generate_solve_report_stats_analysis": float(t[0]), "samples_per_s": total / float(t[0]) * 1e3,
+            "depth_MAE_cm": 100 * float(st["depth"]["all"][5]), "yaw_MAE_deg": float(st["yaw"]["all"][5]),
+            "n_selected": [f["n_selected"] for f in fr],
+            "most_fragile_depth": fr[0]["fragile_point_sorted_list"][:3], "most_fragile_yaw": fr[3]["fragile_point_sorted_list"][:3],
+            "top_similarity_depth": [float(x) for x in fr[0]["top_similarity"]], "value_max_depth_m": fr[0]["value_max"],
+            "top_value_mean_depth_m": fr[0]["top_value_mean"]}
+
+
+def config6(scale):
+    B = int((1 << 18) * scale)
+    K = pt.default_camera_matrix()
+    res = {"config": 6, "workload": "stress workload, %d problems, FP64: EIF2 beside LM and QEIF (all landmarks)" % B}
+    for n, pat in ((15, pt.get_golden_pattern("Alexander")), (68, pt.synthetic_pattern(68))):
+        P = pt.pattern_array(pat)
+        w = wl.synth_batch(0, B, P, K)
+        patd = torch.from_numpy(P).cuda()[None]
+        for method in ("eif2", "lm", "qeif"):
+            ms, o = timed(lambda: pnp.solve_batch(method, w["uv"], patd, K))
+            rep = wl.report_batch(P, w["uv"], K, o["R"], o["t"], o["euler"], w["gt"])
+            res["%s_n%d" % (method, n)] = {"ms": ms, "solves_per_s": B / ms * 1e3, "mean_iters": float(o["iters"].double().mean()),
+                                          "pass_rate_10cm_10deg": float(rep["flags"].all(dim=1).double().mean())}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="0,2,3")
@@ -146,9 +201,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
-    fns = {0: config0, 2: config2, 3: config3, 4: config4}
+    fns = {0: config0, 2: config2, 3: config3, 4: config4, 5: config5, 6: config6}
     for c in [int(x) for x in args.configs.split(",")]:
-        if world > 1 and c != 4:
+        if world > 1 and c not in (4, 5):
             continue
         r = fns[c](args.scale)
         if rank == 0:
