@@ -274,6 +274,25 @@ int pnpb200_fragility_accumulate(int64_t B, int64_t idx0, int nq, const double* 
                                  double* value_sum, double* value_max, double* gram, void* stream);
 
 /*
+ * Host-side result table (no GPU): the CSV that TEST_TOOLBOX.write_result_to_csv (TEST_TOOLBOX.py:693-708)
+ * writes from the list of result dicts of compare_result_and_generate_result_dict (:396-463), straight
+ * from the arrays pnpb200_report_batch returns, copied to the host (pinned or not).  Same column names
+ * and order for every scalar / string / tuple / dict field (the six ndarray fields are left out), same
+ * csv dialect (QUOTE_MINIMAL, "\r\n"), floats as Python's repr(float), bools as True / False.
+ *   report [B,16], flags [B,4], max_idx [B,3], res_norm [B], gt [B,4]        (host)
+ *   key_names [n_keys]: landmark names in pattern order (the *_error_max_key columns)
+ *   bins[q] / n_bins[q] / labels[q], q = depth (cm), roll, pitch, yaw: classify_drpy (:239-247),
+ *   n_bins[q] + 1 labels each; they give the `class` and `file_name` columns (random_stress_test.py:300-306)
+ *   append = 0: truncate and write the header; 1: append rows (shards / chunks in order); idx0 = first idx
+ * pnpb200_format_repr exposes the float formatter for the tests (out_size >= 32).
+ */
+int pnpb200_write_result_csv(const char* path, int append, int64_t B, int64_t idx0, const double* report,
+                             const int32_t* flags, const int32_t* max_idx, const double* res_norm, const double* gt,
+                             const char* const* key_names, int n_keys, const double* const* bins, const int32_t* n_bins,
+                             const char* const* const* labels, int n_threads);
+int pnpb200_format_repr(double v, char* out, int out_size);
+
+/*
  * FMA-pipe microbenchmark used by bench.py for the roofline denominator (MEASURED_PEAKS.json
  * has no FP64/FP32 FMA figure).  Runs `iters` dependent-chain-free FMAs per thread on a full
  * grid and returns the device-timed rate in FLOP/s (2 per FMA).  Synchronous.

@@ -255,7 +255,8 @@ def stress_report_case(PNPS, TTBX, tag, B, seed):
         pass_list, pass_count = TTBX.check_if_the_sample_passed((t3 * 100.0, r_, p_, y_), (dist_cm, roll, pitch, yaw),
                                                                 (10.0, 10.0, 10.0, 10.0))
         flags[b] = [int(bool(x)) for x in pass_list]
-        data_idx = dict(idx=b, file_name="x", distance=dist_cm, roll=roll, pitch=pitch, yaw=yaw, **{"class": cd})
+        data_idx = dict(idx=b, file_name="random_drpy_%s_%s_%s_%s" % (cd["distance"], cd["roll"], cd["pitch"], cd["yaw"]),   # random_stress_test.py:301
+                        distance=dist_cm, roll=roll, pitch=pitch, yaw=yaw, **{"class": cd})
         rd, _, _ = quiet(TTBX.compare_result_and_generate_result_dict, solver, data_idx, Rb, tb, (r_, p_, y_), R_gt, t_gt_est,
                          (roll, pitch, yaw), rn, 4 - pass_count, pass_count, pass_list, np_point_image_dict=pts, verbose=False)
         result_list.append(rd)
@@ -279,9 +280,39 @@ def stress_report_case(PNPS, TTBX, tag, B, seed):
     cdict = quiet(TTBX.get_classified_result, result_list, class_name='distance', approval_func=None)
     stats_all = np.array([stat(result_list, ek, gk) for _, ek, gk in quant], dtype=np.float64)
     stats_depth = np.array([[stat(cdict.get(lb, []), ek, gk) for lb in labels] for _, ek, gk in quant], dtype=np.float64)
+    # the writers (TEST_TOOLBOX.py:693-820), unmodified, on the same result_list.  The six ndarray fields are
+    # dropped from the dicts first (NumPy's multi-line str() of a matrix in a CSV cell is not reproduced), and the
+    # NumPy scalars of this generator are turned into the Python floats the script's own draws would be under NumPy 1.x
+    # (NumPy 2 prints np.float64(...) inside the `drpy` tuple).
+    import tempfile
+    drop = ("np_R_GT", "np_R_est", "np_R_err", "np_t_GT_est", "np_t_est", "np_t_err")
+    plain = []
+    for rd in result_list:
+        d = {k: v for k, v in rd.items() if k not in drop}
+        d["drpy"] = tuple(float(x) for x in d["drpy"])
+        for k, v in list(d.items()):
+            if isinstance(v, (np.floating,)):
+                d[k] = float(v)
+            elif isinstance(v, (np.bool_,)):
+                d[k] = bool(v)
+        plain.append(d)
+    tmpd = tempfile.mkdtemp()
+    quiet(TTBX.write_result_to_csv, plain, os.path.join(tmpd, "r.csv"))
+    result_csv = open(os.path.join(tmpd, "r.csv"), newline="").read()
+    stat_txt, stat_csv = {}, {}
+    for name, ek, gk, unit, sc in (("depth", "t3_est", "distance_GT", "cm", 100.0), ("roll", "roll_est", "roll_GT", "deg.", 1.0),
+                                   ("pitch", "pitch_est", "pitch_GT", "deg.", 1.0), ("yaw", "yaw_est", "yaw_GT", "deg.", 1.0)):
+        csd = {lb: quiet(TTBX.get_statistic_of_result, lst, class_name="distance", class_label=lb, data_est_key=ek, data_GT_key=gk,
+                         unit=unit, unit_scale=sc, verbose=False) for lb, lst in cdict.items()}
+        quiet(TTBX.write_statistic_to_txt, csd, os.path.join(tmpd, "s.txt"), class_name="distance", statistic_data_name=name)
+        quiet(TTBX.write_statistic_to_csv, csd, os.path.join(tmpd, "s.csv"), class_name="distance", statistic_data_name=name, is_horizontal=True)
+        stat_txt[name] = open(os.path.join(tmpd, "s.txt"), newline="").read()
+        stat_csv[name] = open(os.path.join(tmpd, "s.csv"), newline="").read()
     np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, pattern=pt.pattern_array(pats[0]), uv=uv, gt=gt, R=R, t=t,
                         euler=eul, res_norm=res, report=rep, flags=flags, max_idx=midx, depth_class=depth_class,
-                        stats_all=stats_all, stats_by_depth=stats_depth,
+                        stats_all=stats_all, stats_by_depth=stats_depth, keys=np.array(keys), result_csv=np.array(result_csv),
+                        **{"stat_txt_" + k: np.array(v) for k, v in stat_txt.items()},
+                        **{"stat_csv_" + k: np.array(v) for k, v in stat_csv.items()},
                         key_index=np.array([keys.index(k) for k in pt.LM_KEY_LIST_6], np.int32))
     from oracle import oracle as orc
     o = orc.report_batch(pt.pattern_array(pats[0]), uv, K, R, t, eul, gt)

@@ -360,3 +360,105 @@ def fragility_analysis(abs_err, perturb, idx0=0, ratio=0.1, k_top_direction=5, t
             out[-1]["fragile_point_count_dict"] = {key: int(c[i]) for i, key in enumerate(keys)}
             out[-1]["fragile_point_sorted_list"] = sorted([(int(c[i]), key) for i, key in enumerate(keys)], reverse=True)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# result writers (TEST_TOOLBOX.py:693-887, :1070-1346)
+# ------------------------------------------------------------------------------------------------
+def write_result_csv(path, report, flags, max_idx, res_norm, gt, key_names, idx0=0, append=False, n_threads=0):
+    """TEST_TOOLBOX.write_result_to_csv (:693-708) for a whole batch: the native writer formats the
+    rows from the report arrays (CUDA tensors are copied to the host first; NumPy arrays and CPU
+    tensors are used as they are).  key_names: landmark names in pattern order."""
+    def host(x, dt):
+        if torch.is_tensor(x):
+            x = x.detach().to("cpu")
+            return np.ascontiguousarray(x.numpy().astype(dt, copy=False))
+        return np.ascontiguousarray(np.asarray(x, dtype=dt))
+    rep, fl, mi = host(report, np.float64), host(flags, np.int32), host(max_idx, np.int32)
+    rn, g = host(res_norm, np.float64).reshape(-1), host(gt, np.float64)
+    B = rep.shape[0]
+    assert rep.shape == (B, 16) and fl.shape == (B, 4) and mi.shape == (B, 3) and rn.shape == (B,) and g.shape == (B, 4)
+    names = [k.encode() for k in key_names]
+    name_a = (C.c_char_p * len(names))(*names)
+    order = ("depth", "roll", "pitch", "yaw")
+    bins_np = [np.asarray(CLASS_BINS[q], np.float64) for q in order]
+    PD = C.POINTER(C.c_double)
+    bins_a = (PD * 4)(*[b.ctypes.data_as(PD) for b in bins_np])
+    nb_a = (C.c_int32 * 4)(*[len(b) for b in bins_np])
+    lab_keep = [(C.c_char_p * len(CLASS_LABELS[q]))(*[s.encode() for s in CLASS_LABELS[q]]) for q in order]
+    lab_a = (C.POINTER(C.c_char_p) * 4)(*[C.cast(a, C.POINTER(C.c_char_p)) for a in lab_keep])
+    check(lib.pnpb200_write_result_csv(str(path).encode(), C.c_int(1 if append else 0), C.c_int64(B), C.c_int64(int(idx0)),
+                                       rep.ctypes.data_as(PD), fl.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       mi.ctypes.data_as(C.POINTER(C.c_int32)), rn.ctypes.data_as(PD), g.ctypes.data_as(PD),
+                                       name_a, C.c_int(len(names)), bins_a, nb_a, lab_a, C.c_int(int(n_threads))),
+          "pnpb200_write_result_csv")
+    return path
+
+
+def statistic_dicts(stats, labels, unit, unit_scale):
+    """One quantity's statistics (error_statistics()[name]) as the {class label: statis_dict} the
+    reference builds with get_statistic_of_result per class (TEST_TOOLBOX.py:928-936, :1090-1101):
+    keys n_data, m_ratio, mean(u), stddev(u), max_dev(u), MAE_2_GT(u), MAE_2_mean(u); classes without
+    data are absent, 'all' is included."""
+    out = {}
+    rows = [(lb, stats["by_depth"][i]) for i, lb in enumerate(labels)] + [("all", stats["all"])]
+    for lb, r in rows:
+        r = [float(x) for x in r]
+        if not r[0] > 0:
+            continue
+        out[lb] = {"n_data": int(r[0]), "m_ratio": r[1], "mean(%s)" % unit: r[2] * unit_scale, "stddev(%s)" % unit: r[3] * unit_scale,
+                   "max_dev(%s)" % unit: r[4] * unit_scale, "MAE_2_GT(%s)" % unit: r[5] * unit_scale,
+                   "MAE_2_mean(%s)" % unit: r[6] * unit_scale}
+    return out
+
+
+def _class_order(e):
+    return float("-inf") if e == "all" else float(e)                 # TEST_TOOLBOX._class_order_func :710-716
+
+
+def write_statistic_txt(class_statistic_dict, path, class_name="distance", statistic_data_name="depth"):
+    """TEST_TOOLBOX.write_statistic_to_txt (:718-752), same text."""
+    s = "\nStatistic of [%s] for each [%s] class:\n" % (statistic_data_name, class_name)
+    for lb in sorted(class_statistic_dict, key=_class_order):
+        s += "[%s]: " % lb + " | ".join("%s=%f" % (k, v) for k, v in class_statistic_dict[lb].items()) + "\n"
+    with open(path, "w") as f:
+        f.write(s)
+    return s
+
+
+def write_statistic_csv(class_statistic_dict, path, is_horizontal=True):
+    """TEST_TOOLBOX.write_statistic_to_csv (:754-820), same rows through the same csv.DictWriter."""
+    import csv
+    labels = sorted(class_statistic_dict, key=_class_order)
+    metrics = list(class_statistic_dict[labels[0]].keys())
+    if is_horizontal:
+        fields = ["_"] + labels
+        rows = [dict([("_", m)] + [(lb, class_statistic_dict[lb][m]) for lb in labels]) for m in metrics]
+    else:
+        fields = ["_"] + metrics
+        rows = [dict([("_", lb)] + [(m, class_statistic_dict[lb][m]) for m in metrics]) for lb in labels]
+    with open(path, mode="w") as f:
+        w = csv.DictWriter(f, fieldnames=fields, extrasaction="ignore")
+        w.writeheader()
+        w.writerows(rows)
+    return rows
+
+
+def data_analysis_and_saving(rep, res_norm, gt, key_names, result_csv_dir_str, result_csv_file_prefix_str,
+                             result_statistic_txt_file_prefix_str, data_file_str, is_statistic_csv_horizontal=True,
+                             idx0=0, group=None, distributed=True):
+    """TEST_TOOLBOX.data_analysis_and_saving (:1070-1130) for a batch: the result CSV and, for depth,
+    roll, pitch and yaw per distance class, the statistic TXT and CSV files, with the reference's file
+    names.  rep = report_batch(...) dict.  Returns the four {label: statis_dict} dicts."""
+    stem = data_file_str[:-4]
+    write_result_csv(result_csv_dir_str + result_csv_file_prefix_str + stem + ".csv", rep["report"], rep["flags"], rep["max_idx"],
+                     res_norm, gt, key_names, idx0=idx0)
+    st = error_statistics(rep["report"], gt, group=group, distributed=distributed)
+    out = {}
+    for name, unit, scale in (("depth", "cm", 100.0), ("roll", "deg.", 1.0), ("pitch", "deg.", 1.0), ("yaw", "deg.", 1.0)):
+        d = statistic_dicts(st[name], CLASS_LABELS["depth"], unit, scale)
+        base = result_csv_dir_str + result_statistic_txt_file_prefix_str + stem + "_distance_to_%s" % name
+        write_statistic_txt(d, base + ".txt", class_name="distance", statistic_data_name=name)
+        write_statistic_csv(d, base + ".csv", is_horizontal=is_statistic_csv_horizontal)
+        out[name] = d
+    return out

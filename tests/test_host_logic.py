@@ -102,3 +102,55 @@ def test_class_bins_match_reference_classification():
     cls = np.digitize(g["gt"][:, 0] * 100.0, wl.CLASS_BINS["depth"])
     np.testing.assert_array_equal(cls, g["depth_class"])
     assert wl.CLASS_LABELS["depth"][0] == "20" and wl.CLASS_LABELS["depth"][-1] == "240"
+
+
+def test_float_repr_formatter_matches_python():
+    """The native CSV writer's float formatter against repr(float) (what csv.DictWriter writes)."""
+    import ctypes as C
+    from pnp_solver_test_b200 import _lib
+    rng = np.random.default_rng(0)
+    vals = [0.0, -0.0, 1.0, -3.0, 100000.0, 1e-5, 0.0001234, 9.999e-5, 1.5e16, 9999999999999998.0, 123456789012345678.0, 0.1 + 0.2,
+            1e22, 5e-324, 1.7976931348623157e308, float("inf"), float("-inf"), float("nan"), 2.5e-7, 123.456, 1e15, 1e16, 0.5, 1 / 3]
+    vals += list(rng.normal(size=300) * 10.0 ** rng.integers(-20, 20, 300)) + list(rng.uniform(-200, 200, 300))
+    buf = C.create_string_buffer(64)
+    for v in vals:
+        _lib.check(_lib.lib.pnpb200_format_repr(C.c_double(float(v)), buf, 64), "pnpb200_format_repr")
+        assert buf.value.decode() == repr(float(v)), (v, buf.value)
+
+
+def test_result_and_statistic_writers_match_reference(tmp_path):
+    """write_result_csv / write_statistic_txt / write_statistic_csv against the files the unmodified
+    TEST_TOOLBOX writers produced from the reference's own result dicts (tests/golden/stress_report.npz)."""
+    import csv
+    import io
+    from pnp_solver_test_b200 import workload as wl
+    g = load_golden("stress_report")
+    keys = [str(k) for k in g["keys"]]
+    # the reference's distance_GT is (depth * 100) * 0.01; put it where report_batch's column 11 is
+    p = wl.write_result_csv(tmp_path / "r.csv", g["report"], g["flags"], g["max_idx"], g["res_norm"], g["gt"], keys, n_threads=3)
+    mine = list(csv.reader(io.StringIO(open(p, newline="").read())))
+    ref = list(csv.reader(io.StringIO(str(g["result_csv"]))))
+    assert open(p, newline="").read().count("\r\n") == len(ref)            # csv's default line terminator
+    assert mine[0] == ref[0] and len(mine) == len(ref) == 257
+    num = [i for i, h in enumerate(ref[0]) if h not in ("idx", "file_name", "drpy", "class", "fail_count", "pass_count")
+           and not h.startswith("is_") and not h.endswith("_key")]
+    for a, b in zip(mine[1:], ref[1:]):
+        for i, h in enumerate(ref[0]):
+            if i in num:
+                assert abs(float(a[i]) - float(b[i])) <= 1e-9 * max(1.0, abs(float(b[i]))), (h, a[i], b[i])
+            elif h == "drpy":
+                x, y = eval(a[i]), eval(b[i])
+                assert len(x) == 4 and max(abs(u - v) for u, v in zip(x, y)) < 1e-12
+            else:
+                assert a[i] == b[i], (h, a[i], b[i])
+    # byte-identical wherever the numbers are: rows whose floats all agree exactly
+    same = sum(1 for a, b in zip(mine[1:], ref[1:]) if a == b)
+    assert same >= 0                                                     # informational; numerics differ in the last digits
+    # statistics files: text produced from the golden statistics rows
+    for q, (name, unit, scale) in enumerate((("depth", "cm", 100.0), ("roll", "deg.", 1.0), ("pitch", "deg.", 1.0), ("yaw", "deg.", 1.0))):
+        st = {"all": g["stats_all"][q], "by_depth": np.nan_to_num(g["stats_by_depth"][q])}
+        d = wl.statistic_dicts(st, wl.CLASS_LABELS["depth"], unit, scale)
+        txt = wl.write_statistic_txt(d, tmp_path / "s.txt", class_name="distance", statistic_data_name=name)
+        assert txt == str(g["stat_txt_" + name]) and open(tmp_path / "s.txt").read() == txt
+        wl.write_statistic_csv(d, tmp_path / "s.csv", is_horizontal=True)
+        assert open(tmp_path / "s.csv", newline="").read() == str(g["stat_csv_" + name])
