@@ -658,25 +658,40 @@ __global__ void __launch_bounds__(kStatLaneBlock) k_stats_lane(long long B, Stat
 #pragma unroll
     for (int q = 0; q < kStatMaxQ; ++q) all[q][0] = all[q][1] = all[q][2] = all[q][3] = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long b0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; b0 < B; b0 += stride * kStatUnroll) {
-        int c[kStatUnroll];
-        double ev[kStatUnroll][kStatMaxQ], gv[kStatUnroll][kStatMaxQ];
+    // Software pipeline: the loads of batch k+1 (kStatUnroll problems) are in flight while batch k is
+    // accumulated -- with one warp per scheduler nothing else hides the DRAM latency.
+    int c[kStatUnroll], cn[kStatUnroll];
+    double ev[kStatUnroll][kStatMaxQ], gv[kStatUnroll][kStatMaxQ], evn[kStatUnroll][kStatMaxQ], gvn[kStatUnroll][kStatMaxQ];
+    auto load = [&](long long b0, int (&cc)[kStatUnroll], double (&e)[kStatUnroll][kStatMaxQ], double (&g)[kStatUnroll][kStatMaxQ]) {
 #pragma unroll
-        for (int u = 0; u < kStatUnroll; ++u) {           // all loads first
+        for (int u = 0; u < kStatUnroll; ++u) {
             const long long b = b0 + u * stride;
-            c[u] = -2;                                    // -2: no problem; -1: problem outside the classes
+            cc[u] = -2;                                   // -2: no problem; -1: problem outside the classes
+#pragma unroll
+            for (int q = 0; q < kStatMaxQ; ++q) { e[u][q] = 0.0; g[u][q] = 1.0; }
             if (b < B) {
-                c[u] = cls ? cls[b] : 0;
-                if (c[u] < 0 || c[u] >= n_class) c[u] = -1;
+                cc[u] = cls ? cls[b] : 0;
+                if (cc[u] < 0 || cc[u] >= n_class) cc[u] = -1;
 #pragma unroll
                 for (int q = 0; q < kStatMaxQ; ++q) {
                     if (q < nq) {
-                        ev[u][q] = in.est[q][b * in.es[q]];
-                        gv[u][q] = in.gt[q] ? in.gt[q][b * in.gs[q]] : 0.0;
+                        e[u][q] = in.est[q][b * in.es[q]];
+                        g[u][q] = in.gt[q] ? in.gt[q][b * in.gs[q]] : 0.0;
                     }
                 }
             }
         }
+    };
+    long long b0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b0 < B) load(b0, cn, evn, gvn);
+    for (; b0 < B; b0 += stride * kStatUnroll) {
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) {
+            c[u] = cn[u];
+#pragma unroll
+            for (int q = 0; q < kStatMaxQ; ++q) { ev[u][q] = evn[u][q]; gv[u][q] = gvn[u][q]; }
+        }
+        if (b0 + stride * kStatUnroll < B) load(b0 + stride * kStatUnroll, cn, evn, gvn);
 #pragma unroll
         for (int u = 0; u < kStatUnroll; ++u) {
             if (c[u] == -2) continue;

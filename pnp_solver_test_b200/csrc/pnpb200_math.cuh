@@ -192,6 +192,12 @@ PNP_DEV void sym_matvec(const T (&S)[N * (N + 1) / 2], const T (&x)[N], T (&y)[N
 // as EKF2_reconstruct_R_t_m1 does with np.linalg.svd / det / norm(ord=2)
 // (PNP_SOLVER_LIB.py:3509-3518, :3530).  G row-major.  det(U V^T) = sign(det G) when G is
 // non-singular, and the -1 lands on the smallest singular value's pair.
+template <typename T> PNP_DEV T t_sqrt_pos(T a) { return t_sqrt_fast<T>(a, t_rsqrt<T>(a)); }   // a > 0, normal
+
+// Branch-free rotations: a rotation that is not needed (|gamma| <= tol sqrt(alpha beta)) becomes the
+// identity by selects, divisions and square roots are the MUFU-seeded ones, and the sweep loop ends
+// when no lane of the warp rotated -- the library division / sqrt slow paths and the per-lane
+// divergence of the first version made this epilogue a third of k_iterate's time.
 template <typename T>
 PNP_DEV void svd3_project(const T (&G)[9], T (&R)[9], T& sigma_max)
 {
@@ -200,6 +206,7 @@ PNP_DEV void svd3_project(const T (&G)[9], T (&R)[9], T& sigma_max)
     for (int i = 0; i < 9; ++i) { W[i] = G[i]; V[i] = T(0); }
     V[0] = V[4] = V[8] = T(1);
     const T tol = (sizeof(T) == 8) ? T(2e-16) : T(1e-7);
+    const T tol2 = tol * tol;
     for (int sweep = 0; sweep < 12; ++sweep) {
         bool rotated = false;
 #pragma unroll
@@ -213,23 +220,25 @@ PNP_DEV void svd3_project(const T (&G)[9], T (&R)[9], T& sigma_max)
                 beta = t_fma(W[k * 3 + j], W[k * 3 + j], beta);
                 gamma = t_fma(W[k * 3 + i], W[k * 3 + j], gamma);
             }
-            if (gamma != T(0) && t_abs(gamma) > tol * t_sqrt(alpha * beta)) {
-                rotated = true;
-                const T zeta = (beta - alpha) / (T(2) * gamma);
-                const T tt = (zeta >= T(0) ? T(1) : T(-1)) / (t_abs(zeta) + t_sqrt(T(1) + zeta * zeta));
-                const T c = T(1) / t_sqrt(T(1) + tt * tt), s = c * tt;
+            const bool rot = gamma * gamma > tol2 * (alpha * beta);      // gamma != 0 and |gamma| > tol sqrt(alpha beta)
+            rotated = rotated || rot;
+            const T gs = rot ? gamma : T(1);
+            const T zeta = (beta - alpha) * t_rcp<T>(gs + gs);
+            const T tt0 = t_rcp<T>(t_abs(zeta) + t_sqrt_pos<T>(t_fma(zeta, zeta, T(1))));
+            const T tt = (zeta >= T(0)) ? tt0 : -tt0;
+            const T c0 = t_rsqrt<T>(t_fma(tt, tt, T(1)));
+            const T c = rot ? c0 : T(1), s = rot ? c0 * tt : T(0);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const T wi = W[k * 3 + i], wj = W[k * 3 + j];
-                    W[k * 3 + i] = c * wi - s * wj;
-                    W[k * 3 + j] = s * wi + c * wj;
-                    const T vi = V[k * 3 + i], vj = V[k * 3 + j];
-                    V[k * 3 + i] = c * vi - s * vj;
-                    V[k * 3 + j] = s * vi + c * vj;
-                }
+            for (int k = 0; k < 3; ++k) {
+                const T wi = W[k * 3 + i], wj = W[k * 3 + j];
+                W[k * 3 + i] = c * wi - s * wj;
+                W[k * 3 + j] = s * wi + c * wj;
+                const T vi = V[k * 3 + i], vj = V[k * 3 + j];
+                V[k * 3 + i] = c * vi - s * vj;
+                V[k * 3 + j] = s * vi + c * vj;
             }
         }
-        if (!rotated) break;
+        if (!__any_sync(__activemask(), rotated)) break;
     }
     T sg[3];
 #pragma unroll
@@ -259,9 +268,11 @@ PNP_DEV void svd3_project(const T (&G)[9], T (&R)[9], T& sigma_max)
 PNP_DEV void euler_from_R(const double (&R)[9], bool is_degree, double (&out)[3])
 {
     const double kPi = 3.14159265358979323846;
-    const double eps = 1e-7;
+    // |pi/2 - asin(|R7|)| <= 1e-7  <=>  cos(1e-7) <= |R7| <= 1  (asin is NaN above 1 and the test then fails, :4482)
+    const double kGimbal = 0.999999999999995;              // cos(1e-7) = 1 - 5.0e-15
+    const double a7 = fabs(R[7]);
     double th1, th2, th3;
-    if (fabs(kPi / 2.0 - asin(fabs(R[7]))) <= eps) {          // gimbal lock (:4482)
+    if (a7 >= kGimbal && a7 <= 1.0) {                       // gimbal lock (:4482)
         const double m = -R[7];
         const double sg = (m > 0.0) ? 1.0 : ((m < 0.0) ? -1.0 : 0.0);
         th2 = sg * (kPi / 2.0);
@@ -270,7 +281,10 @@ PNP_DEV void euler_from_R(const double (&R)[9], bool is_degree, double (&out)[3]
     } else {
         th1 = atan2(R[1], R[4]);
         th3 = atan2(R[6], R[8]);
-        const double c1 = cos(th1), c3 = cos(th3);
+        // cos(atan2(y, x)) = x / hypot(x, y): no second trip through the trigonometric routines (:4490-4493)
+        const double h1 = R[1] * R[1] + R[4] * R[4], h3 = R[6] * R[6] + R[8] * R[8];
+        const double c1 = (h1 > 0.0) ? R[4] * t_rsqrt<double>(h1) : 1.0;
+        const double c3 = (h3 > 0.0) ? R[8] * t_rsqrt<double>(h3) : 1.0;
         const double c2 = (fabs(c1) > fabs(c3)) ? (R[4] / c1) : (R[8] / c3);
         th2 = atan2(-R[7], c2);
     }

@@ -6,6 +6,7 @@
 // 16-byte reads that follow are bank-conflict free.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include "pnpb200_math.cuh"
 
 namespace pnpb200 {
@@ -171,6 +172,21 @@ inline RowGeom row_geometry(int n_total)
 // the copy of chunk c+1 overlaps the arithmetic on chunk c.
 // ------------------------------------------------------------------------------------------
 struct StreamGeom { int chunk, pitch, use_stream; size_t buf_bytes; };
+constexpr int kStreamChunkUnits = 17;                     // 272-byte chunks
+
+// Points per chunk, in units of 16 bytes.  Odd, so that the row pitch is an odd multiple of 16 B.
+// Smaller chunks = smaller buffers = more resident warps (shared memory is what limits them), but
+// more mbarrier round trips per row.  PNPB200_STREAM_CHUNK overrides the default (tuning only).
+inline int stream_chunk_units()
+{
+    static const int units = []() {
+        const char* e = getenv("PNPB200_STREAM_CHUNK");
+        int u = e ? atoi(e) : 0;
+        if (u < 1 || u > 127) u = kStreamChunkUnits;
+        return u | 1;
+    }();
+    return units;
+}
 
 template <typename T>
 inline StreamGeom stream_geometry(int n_total)
@@ -178,7 +194,7 @@ inline StreamGeom stream_geometry(int n_total)
     StreamGeom g;
     const int per16 = 16 / (2 * (int)sizeof(T));             // points per 16 bytes: 1 (double), 2 (float)
     g.use_stream = (n_total % per16 == 0) ? 1 : 0;
-    int c = 17 * per16;                                       // 272-byte chunks
+    int c = stream_chunk_units() * per16;
     if (c > n_total) c = n_total;
     g.chunk = c;
     size_t units = ((size_t)c * 2 * sizeof(T) + 15) / 16;
