@@ -298,3 +298,30 @@ def test_fast_reciprocals():
     assert np.abs(rcp * al - 1).max() <= 1.01 * ulp
     assert np.abs(rsq.astype(np.longdouble) ** 2 * al - 1).max() <= 2.5 * ulp
     assert np.abs(sq.astype(np.longdouble) / np.sqrt(al) - 1).max() <= 1.6 * ulp     # even: t_sqrt_fast, odd: sqrt_nonneg
+
+
+@pytest.mark.parametrize("method,subset", [("lm", False), ("qeif", True), ("eif2", False)])
+def test_host_buffer_pipeline_equals_device_call(method, subset):
+    """pnpb200_solve_batch_host (the end-to-end entry point: chunked H2D / solve / D2H on three
+    streams, pinned or pageable host buffers) returns exactly what one device-resident call does,
+    for a ragged batch that is not a multiple of the chunk."""
+    import pnp_solver_test_b200 as pnp
+    pat = pt.get_golden_pattern()
+    P, K = pt.pattern_array(pat), pt.default_camera_matrix()
+    B = 5 * 1000 + 37
+    w = orc.synth(0, B, P, K)
+    idx = [list(pat).index(k) for k in pt.LM_KEY_LIST_6] if subset else None
+    ref = to_np(pnp.solve_batch(method, dev(w["uv"]), dev(P)[None], K, point_index=idx))
+    for pinned in (True, False):
+        host_uv = torch.from_numpy(w["uv"])
+        host_uv = host_uv.pin_memory() if pinned else host_uv
+        outs = {"R": torch.empty((B, 3, 3), dtype=torch.float64), "t": torch.empty((B, 3), dtype=torch.float64),
+                "euler": torch.empty((B, 3), dtype=torch.float64), "res_norm": torch.empty((B,), dtype=torch.float64),
+                "iters": torch.empty((B,), dtype=torch.int32), "best_pattern": torch.empty((B,), dtype=torch.int32)}
+        if pinned:
+            outs = {k: v.pin_memory() for k, v in outs.items()}
+        pipe = pnp.HostPipeline(torch.float64, chunk_problems=1000, n_total=15, n_patterns=1, n_streams=3)
+        pipe.solve(method, host_uv, torch.from_numpy(P)[None].contiguous(), K, outs, point_index=idx)
+        pipe.close()
+        for k in outs:
+            assert np.array_equal(outs[k].numpy().reshape(ref[k].shape), ref[k], equal_nan=True), (k, pinned)
