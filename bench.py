@@ -39,16 +39,16 @@ UNIT = "solves/s"
 # Algorithmic work per solve of the LM path as implemented (DESIGN.md "Kernels"); FMA = 2 flops.
 # Moment mapping = three kernels:
 #   k_stream_chunk<.,LM,0>  moments: per point 6 theta*theta^T products, bx^2+by^2, 27 FMAs, 2 adds    65 flop/pt   (HBM-bound)
-#   k_iterate<.,LM>         14 x [gamma column 84 FMA = 168, rhs 37 FMA = 74, A and g set-up 62, eliminate
-#                           delta_1/delta_2 70 FMA + 28 MUL = 168, nine constraint rows (dots, 3 rsqrt/sqrt, 189
-#                           FMA of outer products) 477, LDL^T 10x10 (165 FMA, 55 MUL, 10 reciprocals) 455,
-#                           two triangular solves 190, delta back-substitution and update 42] = 14 x 1636
+#   k_iterate<.,LM>         14 x [gamma column 84 FMA = 168, rhs 37 FMA = 74, scaled set-up with the delta_1/delta_2
+#                           elimination folded into the constant 9x9 core 150, nine constraint rows (dots, 3 rsqrt/sqrt,
+#                           189 FMA of outer products) 486, LDL^T 10x10 (165 FMA, 55 MUL, 10 reciprocals) 455, two
+#                           triangular solves 190, delta back-substitution and update 46] = 14 x 1569
 #                           + 3x3 SVD, t, Euler ~1000                                               (FP64 pipe)
-#                           (cross-check: the SASS of one iteration is 721 DFMA + 159 DMUL + 36 DADD = 1637)
+#                           (cross-check: the SASS of one iteration is 717 DFMA + 117 DMUL + 18 DADD = 1569)
 #   k_stream_chunk<.,LM,1>  residual at the state before the last update: 34 flop/pt                   (HBM-bound)
 # ------------------------------------------------------------------------------------------------
 def lm_flops_iterate(max_it=14):
-    return max_it * (168 + 74 + 62 + 168 + 477 + 455 + 190 + 42) + 1000
+    return max_it * (168 + 74 + 150 + 486 + 455 + 190 + 46) + 1000
 
 
 def lm_flops_per_solve(n, max_it=14):

@@ -468,69 +468,60 @@ PNP_DEV void add_outer1(T (&A)[55], T (&g)[10], const T (&va)[3], T e)
 
 // One damped Gauss-Newton step: A = J^T J + lambda I (:2666-2667) from the moments and the gamma
 // column, g = J^T (z - hx) (:2684) from `r`, the nine constraint rows, x += pinv(A) g (:2675, :2702).
-// delta_1 and delta_2 are eliminated first: their pivots are the constant n + lambda, they do not
-// couple to each other, and each couples to seven of the other unknowns only.  What is factorised
-// is the 10 x 10 Schur complement on (u1, u2, u3, gamma) -- the LDL^T of the 12 x 12 matrix with
-// the two delta columns ordered first, written out.
+//
+// Solved in the variables y = (gamma du1, gamma du2, gamma du3, d gamma) -- a diagonal scaling of the
+// same linear system.  Every measurement row then has constant coefficients in (y_u, d delta), so
+// after delta_1 and delta_2 are eliminated (their pivots are the constant n + lambda, they do not
+// couple to each other) the 9 x 9 core of the matrix is a per-problem constant of the moments:
+//   S11 = S22 = M0 - m0 m0^T / p,  S12 = 0,  S13 = -Mx + m0 mx^T / p,  S23 = -My + m0 my^T / p,
+//   S33 = Mw - (mx mx^T + my my^T) / p,                                        p = n + lambda
+// and per iteration only lambda / gamma^2 on its diagonal, the gamma column / row, the right-hand
+// side and the nine constraint rows (scaled by 1 / gamma) change.  What is factorised is the
+// 10 x 10 Schur complement on (y_u1, y_u2, y_u3, d gamma) -- the LDL^T of the 12 x 12 matrix with the
+// two delta columns ordered first, written out.
 // TRUE_JAC = false reproduces the reference's constraint Jacobians (rows 4-6 use u, rows 7-9 use
 // u/(2|u|)); true uses the actual gradients (2u, u/|u|) and is only used by the non-parity LM+.
 // Returns max |dx|.
 template <typename T, typename M, bool TRUE_JAC = false>
 PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaCol<T>& gc, const LmRhs<T>& r,
-                  T lambda)
+                  T lambda, T ip /* 1 / (n + lambda), loop-invariant */)
 {
     constexpr int U1 = 0, U2 = 3, U3 = 6, GG = 9;       // order inside the reduced system
     const T gam = x[11];
+    const T ig = t_rcp<T>(gam);
+    const T lg = lambda * (ig * ig);                    // lambda I in the scaled variables
+    const T m0[3] = { sC[6], sC[7], sC[8] };
+    const T m0p[3] = { m0[0] * ip, m0[1] * ip, m0[2] * ip };
+    const T mx[3] = { m.gmx(0), m.gmx(1), m.gmx(2) }, my[3] = { m.gmy(0), m.gmy(1), m.gmy(2) };
+    const T mxp[3] = { mx[0] * ip, mx[1] * ip, mx[2] * ip }, myp[3] = { my[0] * ip, my[1] * ip, my[2] * ip };
+    const T f1 = r.q1 * ip, f2 = r.q2 * ip, s1p = gc.s1 * ip, s2p = gc.s2 * ip;
     T A[55], g[10];
-    const T gg2 = gam * gam;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
         for (int b = a; b < 3; ++b) {
-            const T lam = (a == b) ? lambda : T(0);        // + lambda I (:2667)
-            const T m0 = t_fma(gg2, sC[s3(a, b)], lam);
-            A[sidx<10>(U1 + a, U1 + b)] = m0;
-            A[sidx<10>(U2 + a, U2 + b)] = m0;
-            A[sidx<10>(U3 + a, U3 + b)] = t_fma(gg2, m.gMw(s3(a, b)), lam);
+            const T lam = (a == b) ? lg : T(0);
+            const T s11 = t_fma(-m0p[a], m0[b], sC[s3(a, b)]) + lam;
+            A[sidx<10>(U1 + a, U1 + b)] = s11;
+            A[sidx<10>(U2 + a, U2 + b)] = s11;
+            A[sidx<10>(U3 + a, U3 + b)] = t_fma(-mxp[a], mx[b], t_fma(-myp[a], my[b], m.gMw(s3(a, b)))) + lam;
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             A[sidx<10>(U1 + a, U2 + b)] = T(0);
-            A[sidx<10>(U1 + a, U3 + b)] = -gg2 * m.gMx(s3(a, b));
-            A[sidx<10>(U2 + a, U3 + b)] = -gg2 * m.gMy(s3(a, b));
+            A[sidx<10>(U1 + a, U3 + b)] = t_fma(m0p[a], mx[b], -m.gMx(s3(a, b)));
+            A[sidx<10>(U2 + a, U3 + b)] = t_fma(m0p[a], my[b], -m.gMy(s3(a, b)));
         }
-        A[sidx<10>(U1 + a, GG)] = gam * gc.sg1[a];
-        A[sidx<10>(U2 + a, GG)] = gam * gc.sg2[a];
-        A[sidx<10>(U3 + a, GG)] = -gam * gc.sg3[a];
-        g[U1 + a] = gam * r.r1[a]; g[U2 + a] = gam * r.r2[a]; g[U3 + a] = -gam * r.r3[a];
+        A[sidx<10>(U1 + a, GG)] = t_fma(-m0[a], s1p, gc.sg1[a]);
+        A[sidx<10>(U2 + a, GG)] = t_fma(-m0[a], s2p, gc.sg2[a]);
+        A[sidx<10>(U3 + a, GG)] = t_fma(mx[a], s1p, t_fma(my[a], s2p, -gc.sg3[a]));
+        g[U1 + a] = t_fma(-m0[a], f1, r.r1[a]);
+        g[U2 + a] = t_fma(-m0[a], f2, r.r2[a]);
+        g[U3 + a] = t_fma(mx[a], f1, t_fma(my[a], f2, -r.r3[a]));
     }
-    A[sidx<10>(GG, GG)] = gc.sgg + lambda;
-    g[GG] = r.qg;
-    // ---- eliminate delta_1 (column [gam m0; 0; -gam mx; s1]) and delta_2 ([0; gam m0; -gam my; s2])
-    const T ip = t_rcp<T>(sC[9] + lambda);
-    T c1[7], c2[7];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        c1[a] = gam * sC[6 + a]; c1[3 + a] = -gam * m.gmx(a);
-        c2[a] = c1[a];           c2[3 + a] = -gam * m.gmy(a);
-    }
-    c1[6] = gc.s1; c2[6] = gc.s2;
-    {
-        constexpr int i1[7] = { 0, 1, 2, 6, 7, 8, 9 }, i2[7] = { 3, 4, 5, 6, 7, 8, 9 };
-        const T f1 = r.q1 * ip, f2 = r.q2 * ip;
-#pragma unroll
-        for (int p = 0; p < 7; ++p) {
-            const T b1 = c1[p] * ip, b2 = c2[p] * ip;
-#pragma unroll
-            for (int q = p; q < 7; ++q) {
-                A[sidx<10>(i1[p], i1[q])] = t_fma(-b1, c1[q], A[sidx<10>(i1[p], i1[q])]);
-                A[sidx<10>(i2[p], i2[q])] = t_fma(-b2, c2[q], A[sidx<10>(i2[p], i2[q])]);
-            }
-            g[i1[p]] = t_fma(-c1[p], f1, g[i1[p]]);
-            g[i2[p]] = t_fma(-c2[p], f2, g[i2[p]]);
-        }
-    }
-    // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones)
+    A[sidx<10>(GG, GG)] = t_fma(-gc.s1, s1p, t_fma(-gc.s2, s2p, gc.sgg + lambda));
+    g[GG] = t_fma(-gc.s1, f1, t_fma(-gc.s2, f2, r.qg));
+    // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones), times 1 / gamma
     {
         const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
         const T u11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
@@ -543,38 +534,40 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         const T y1 = t_rsqrt<T>(u11), y2 = t_rsqrt<T>(u22), y3 = t_rsqrt<T>(u33);
         const T n1 = t_sqrt_fast<T>(u11, y1), n2 = t_sqrt_fast<T>(u22, y2), n3 = t_sqrt_fast<T>(u33, y3);
         constexpr T kq = TRUE_JAC ? T(2) : T(1), kn = TRUE_JAC ? T(1) : T(2);
-        const T pu1[3] = { kq * u1[0], kq * u1[1], kq * u1[2] }, pu2[3] = { kq * u2[0], kq * u2[1], kq * u2[2] };
-        const T nu2[3] = { -kq * u2[0], -kq * u2[1], -kq * u2[2] }, nu3[3] = { -kq * u3[0], -kq * u3[1], -kq * u3[2] };
-        add_outer2<T, U1, U3>(A, g, u3, u1, T(0) - u13);          // u1.u3 = 0
-        add_outer2<T, U2, U3>(A, g, u3, u2, T(0) - u23);          // u2.u3 = 0
-        add_outer2<T, U1, U2>(A, g, u2, u1, T(0) - u12);          // u1.u2 = 0
-        add_outer2<T, U1, U3>(A, g, pu1, nu3, T(0) - (u11 - u33)); // reference rows use u, not 2u (:3808)
-        add_outer2<T, U2, U3>(A, g, pu2, nu3, T(0) - (u22 - u33));
-        add_outer2<T, U1, U2>(A, g, pu1, nu2, T(0) - (u11 - u22));
+        const T w1[3] = { u1[0] * ig, u1[1] * ig, u1[2] * ig };          // u / gamma
+        const T w2[3] = { u2[0] * ig, u2[1] * ig, u2[2] * ig };
+        const T w3[3] = { u3[0] * ig, u3[1] * ig, u3[2] * ig };
+        const T pw1[3] = { kq * w1[0], kq * w1[1], kq * w1[2] }, pw2[3] = { kq * w2[0], kq * w2[1], kq * w2[2] };
+        const T nw2[3] = { -kq * w2[0], -kq * w2[1], -kq * w2[2] }, nw3[3] = { -kq * w3[0], -kq * w3[1], -kq * w3[2] };
+        add_outer2<T, U1, U3>(A, g, w3, w1, T(0) - u13);          // u1.u3 = 0
+        add_outer2<T, U2, U3>(A, g, w3, w2, T(0) - u23);          // u2.u3 = 0
+        add_outer2<T, U1, U2>(A, g, w2, w1, T(0) - u12);          // u1.u2 = 0
+        add_outer2<T, U1, U3>(A, g, pw1, nw3, T(0) - (u11 - u33)); // reference rows use u, not 2u (:3808)
+        add_outer2<T, U2, U3>(A, g, pw2, nw3, T(0) - (u22 - u33));
+        add_outer2<T, U1, U2>(A, g, pw1, nw2, T(0) - (u11 - u22));
         const T h1 = y1 * (T(1) / kn), h2 = y2 * (T(1) / kn), h3 = y3 * (T(1) / kn);
-        const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
-        const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
-        const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
+        const T j1[3] = { w1[0] * h1, w1[1] * h1, w1[2] * h1 };   // u^T / (2 |u|) (:3819), over gamma
+        const T j2[3] = { w2[0] * h2, w2[1] * h2, w2[2] * h2 };
+        const T j3[3] = { w3[0] * h3, w3[1] * h3, w3[2] * h3 };
         add_outer1<T, U1>(A, g, j1, T(1) - n1);
         add_outer1<T, U2>(A, g, j2, T(1) - n2);
         add_outer1<T, U3>(A, g, j3, T(1) - n3);
     }
     ldlt_factor<T, 10>(A);
     ldlt_solve<T, 10>(A, g);
-    // ---- back-substitute the two deltas: d_k = (rhs_k - column_k . dx) / (n + lambda)
-    T e1 = r.q1, e2 = r.q2;
-    {
-        constexpr int i1[7] = { 0, 1, 2, 6, 7, 8, 9 }, i2[7] = { 3, 4, 5, 6, 7, 8, 9 };
-        // the back substitution delivers g[9] first and g[0] last: consume them in that order
+    // ---- back-substitute the two deltas: d_k = (rhs_k - column_k . y) / p; the back substitution
+    // delivers g[9] first and g[0] last: consume them in that order
+    T e1 = t_fma(-gc.s1, g[GG], r.q1), e2 = t_fma(-gc.s2, g[GG], r.q2);
 #pragma unroll
-        for (int p = 6; p >= 0; --p) { e1 = t_fma(-c1[p], g[i1[p]], e1); e2 = t_fma(-c2[p], g[i2[p]], e2); }
-    }
-    T step = T(0);
+    for (int a = 2; a >= 0; --a) { e1 = t_fma(mx[a], g[U3 + a], e1); e2 = t_fma(my[a], g[U3 + a], e2); }
 #pragma unroll
-    for (int i = 0; i < 10; ++i) step = fmax(step, t_abs(g[i]));
+    for (int a = 2; a >= 0; --a) { e1 = t_fma(-m0[a], g[U1 + a], e1); e2 = t_fma(-m0[a], g[U2 + a], e2); }
+    T step = t_abs(g[GG]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) step = fmax(step, t_abs(g[i] * ig));
     step = fmax(step, fmax(t_abs(e1 * ip), t_abs(e2 * ip)));
 #pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] += g[i];
+    for (int i = 0; i < 9; ++i) x[i] = t_fma(g[i], ig, x[i]);
     x[9] += e1 * ip; x[10] += e2 * ip; x[11] += g[GG];
     return step;
 }
@@ -622,6 +615,7 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
     Moments<T> mom;
     accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T res = T(1e5);
+    const T ip = t_rcp<T>(sC[9] + prm.lm_lambda);
     for (int it = 0; it < prm.max_it; ++it) {             // :2642, fixed count, no exit test
         const T gam = x[11], d1 = x[9], d2 = x[10];
         LmRhs<T> r;
@@ -652,7 +646,7 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
         res = t_sqrt(rr);                                 // res_norm of the state BEFORE the update (:2681)
         GammaCol<T> gc;
         lm_gamma_column<T, Moments<T> >(x, mom, sC, gc);
-        lm_step<T, Moments<T> >(x, mom, sC, gc, r, prm.lm_lambda);
+        lm_step<T, Moments<T> >(x, mom, sC, gc, r, prm.lm_lambda, ip);
     }
     lm_reconstruct<T>(x, out);
     out.res = res;
@@ -668,6 +662,7 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
     T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2619-2624
 #pragma unroll
     for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
+    const T ip = t_rcp<T>(sC[9] + prm.lm_lambda);
     for (int it = 0; it < prm.max_it; ++it) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
@@ -675,7 +670,7 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
         LmRhs<T> r;
         lm_gamma_column<T, M>(x, mom, sC, gc);
         lm_rhs_from_moments<T, M>(x, mom, sC, gc, r);
-        lm_step<T, M>(x, mom, sC, gc, r, prm.lm_lambda);
+        lm_step<T, M>(x, mom, sC, gc, r, prm.lm_lambda, ip);
     }
     lm_reconstruct<T>(x, out);
     out.res = T(0);
@@ -977,6 +972,7 @@ PNP_DEV void solve_lm_plus_from_moments(const M& mom, const Moments<T>& mom_regs
     x[9] = out.t[0] / out.t[2]; x[10] = out.t[1] / out.t[2]; x[11] = T(1) / out.t[2];
     bool done = false;
     int iters = 0;
+    const T ip = t_rcp<T>(sC[9] + prm.lm_lambda);
     for (int it = 0; it < prm.max_it; ++it) {
         if (__all_sync(0xffffffffu, done)) break;
         T xn[12];
@@ -986,7 +982,7 @@ PNP_DEV void solve_lm_plus_from_moments(const M& mom, const Moments<T>& mom_regs
         LmRhs<T> r;
         lm_gamma_column<T, M>(xn, mom, sC, gc);
         lm_rhs_from_moments<T, M>(xn, mom, sC, gc, r);
-        const T step = lm_step<T, M, true>(xn, mom, sC, gc, r, prm.lm_lambda);
+        const T step = lm_step<T, M, true>(xn, mom, sC, gc, r, prm.lm_lambda, ip);
         if (!done) {
 #pragma unroll
             for (int e = 0; e < 12; ++e) x[e] = xn[e];
