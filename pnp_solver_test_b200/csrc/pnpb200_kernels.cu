@@ -554,9 +554,9 @@ __device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
     if (a.best) a.best[b] = 0;
 }
 
-// Register budget per thread given directly: the 64 Ki registers of an SM hold 10 warps at 200 registers
-// (no spills for FP64 LM, which needs ~198), 12 warps at 168 (spills ~40 doubles), 8 warps at 255.
-// Measured for 1 Mi x 68 LM FP64 on B200: 1.02 ms at 200, 1.04 at 184 / 224 / 255, 1.09 at 168.
+// Register budget per thread given directly: the 64 Ki registers of an SM hold 9 warps at 224 registers
+// (no spills for FP64 LM, which wants ~222), 10 at 200, 12 at 168 (spills ~40 doubles), 8 at 255.
+// Measured for 1 Mi x 68 LM FP64 on B200 (scaled step): 0.946 ms at 224 / 255, 0.963 at 200, 0.992 at 184, 1.010 at 168.
 template <typename T, int METHOD, int BLOCK, int MAXREG>
 __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG) k_iterate(const __grid_constant__ MomArgs<T> a)
 {
@@ -577,10 +577,10 @@ static void launch_iterate(const MomArgs<T>& m, int tune, cudaStream_t stream)
     case 2:  launch_iterate_as<T, METHOD, 128, 255>(m, stream); break;   //  8 warps / SM
     case 3:  launch_iterate_as<T, METHOD, 128, 168>(m, stream); break;   // 12 warps / SM
     case 4:  launch_iterate_as<T, METHOD, 128, 128>(m, stream); break;   // 16 warps / SM
-    case 29: launch_iterate_as<T, METHOD, 32, 224>(m, stream); break;    //  9 warps / SM
+    case 30: launch_iterate_as<T, METHOD, 64, 200>(m, stream); break;    // 10 warps / SM
     case 31: launch_iterate_as<T, METHOD, 32, 184>(m, stream); break;    // 11 warps / SM
 #endif
-    default: launch_iterate_as<T, METHOD, 64, 200>(m, stream); break;    // 10 warps / SM
+    default: launch_iterate_as<T, METHOD, 32, 224>(m, stream); break;    //  9 warps / SM, no spills
     }
 }
 
