@@ -627,25 +627,26 @@ __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, co
 }
 
 // Fast path of the same two passes when the per-class tables fit in shared memory with one private
-// column per LANE ([warp][class][quantity][value][32 lanes]: every lane adds to its own 8-byte word,
-// so there is no conflict, no matching and no turn-taking whatever the class pattern is).  Four
-// warps per block (one block per SM); each thread first issues the loads of kStatUnroll problems,
-// then accumulates them, so that enough bytes are in flight at this low occupancy.
-constexpr int kStatLaneBlock = 128;
-constexpr int kStatLaneWarps = kStatLaneBlock / 32;
+// column per LANE ([warp][class][value][32 lanes]: every lane adds to its own 8-byte word, so there
+// is no conflict, no matching and no turn-taking whatever the class pattern is).  Each WARP works on
+// ONE quantity (warp % nq), so its table is a quarter of the all-quantities one and up to 16 warps
+// fit per SM (one block per SM): the first version had 4 warps per SM doing all four quantities and
+// sat on exposed load / shared-memory latency (issue slots 18 % busy, 82 us for 36 MB).
+constexpr int kStatLaneMaxWarps = 16;
 constexpr int kStatUnroll = 4;
 
 template <int PASS>
-__global__ void __launch_bounds__(kStatLaneBlock) k_stats_lane(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
-                                                             const double* __restrict__ sums1, double* out, double* out_max)
+__global__ void __launch_bounds__(kStatLaneMaxWarps * 32) k_stats_lane(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
+                                                                   const double* __restrict__ sums1, double* out, double* out_max)
 {
-    extern __shared__ double sh[];                        // [warp][n_class][nq][NV][32]
+    extern __shared__ double sh[];                        // [warp][n_class][NV][32]
     constexpr int NV = (PASS == 1) ? 3 : 4;
-    const int nq = in.nq, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nq = in.nq, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int q = warp % nq, group = warp / nq, n_groups = n_warps / nq;     // blockDim.x is a multiple of 32 nq
     const int rows = n_class + 1;
-    const int entries = n_class * nq * NV;                // per warp, times 32 lanes
+    const int entries = n_class * NV;                     // per warp, times 32 lanes
     __shared__ double sMean[kStatMaxQ * (kStatMaxClass + 1)];
-    for (int e = threadIdx.x; e < kStatLaneWarps * entries * 32; e += blockDim.x) sh[e] = 0.0;
+    for (int e = threadIdx.x; e < n_warps * entries * 32; e += blockDim.x) sh[e] = 0.0;
     if (PASS == 2) {
         for (int e = threadIdx.x; e < nq * rows; e += blockDim.x) {
             const double cnt = sums1[e * 4];
@@ -654,81 +655,60 @@ __global__ void __launch_bounds__(kStatLaneBlock) k_stats_lane(long long B, Stat
     }
     __syncthreads();
     double* mine = sh + (size_t)warp * entries * 32 + lane;
-    double all[kStatMaxQ][4];
+    const double* __restrict__ est = in.est[0];
+    const double* __restrict__ gtp = in.gt[0];
+    long long es = in.es[0], gs = in.gs[0];
 #pragma unroll
-    for (int q = 0; q < kStatMaxQ; ++q) all[q][0] = all[q][1] = all[q][2] = all[q][3] = 0.0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    // Software pipeline: the loads of batch k+1 (kStatUnroll problems) are in flight while batch k is
-    // accumulated -- with one warp per scheduler nothing else hides the DRAM latency.
-    int c[kStatUnroll], cn[kStatUnroll];
-    double ev[kStatUnroll][kStatMaxQ], gv[kStatUnroll][kStatMaxQ], evn[kStatUnroll][kStatMaxQ], gvn[kStatUnroll][kStatMaxQ];
-    auto load = [&](long long b0, int (&cc)[kStatUnroll], double (&e)[kStatUnroll][kStatMaxQ], double (&g)[kStatUnroll][kStatMaxQ]) {
+    for (int k = 1; k < kStatMaxQ; ++k)
+        if (k == q) { est = in.est[k]; gtp = in.gt[k]; es = in.es[k]; gs = in.gs[k]; }
+    const double mean_all = (PASS == 2) ? sMean[q * rows + n_class] : 0.0;
+    double all0 = 0.0, all1 = 0.0, all2 = 0.0, all3 = 0.0;
+    const long long stride = (long long)gridDim.x * n_groups * 32;
+    for (long long b0 = ((long long)blockIdx.x * n_groups + group) * 32 + lane; b0 < B; b0 += stride * kStatUnroll) {
+        int c[kStatUnroll];
+        double ev[kStatUnroll], gv[kStatUnroll];
 #pragma unroll
-        for (int u = 0; u < kStatUnroll; ++u) {
+        for (int u = 0; u < kStatUnroll; ++u) {           // all loads first
             const long long b = b0 + u * stride;
-            cc[u] = -2;                                   // -2: no problem; -1: problem outside the classes
-#pragma unroll
-            for (int q = 0; q < kStatMaxQ; ++q) { e[u][q] = 0.0; g[u][q] = 1.0; }
+            c[u] = -2;                                    // -2: no problem; -1: problem outside the classes
+            ev[u] = 0.0; gv[u] = 1.0;
             if (b < B) {
-                cc[u] = cls ? cls[b] : 0;
-                if (cc[u] < 0 || cc[u] >= n_class) cc[u] = -1;
-#pragma unroll
-                for (int q = 0; q < kStatMaxQ; ++q) {
-                    if (q < nq) {
-                        e[u][q] = in.est[q][b * in.es[q]];
-                        g[u][q] = in.gt[q] ? in.gt[q][b * in.gs[q]] : 0.0;
-                    }
-                }
+                c[u] = cls ? cls[b] : 0;
+                ev[u] = est[b * es];
+                if (gtp) gv[u] = gtp[b * gs];
             }
         }
-    };
-    long long b0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b0 < B) load(b0, cn, evn, gvn);
-    for (; b0 < B; b0 += stride * kStatUnroll) {
-#pragma unroll
-        for (int u = 0; u < kStatUnroll; ++u) {
-            c[u] = cn[u];
-#pragma unroll
-            for (int q = 0; q < kStatMaxQ; ++q) { ev[u][q] = evn[u][q]; gv[u][q] = gvn[u][q]; }
-        }
-        if (b0 + stride * kStatUnroll < B) load(b0 + stride * kStatUnroll, cn, evn, gvn);
 #pragma unroll
         for (int u = 0; u < kStatUnroll; ++u) {
             if (c[u] == -2) continue;
-#pragma unroll
-            for (int q = 0; q < kStatMaxQ; ++q) {
-                if (q < nq) {
-                    double ratio, err;
-                    if (in.gt[q]) { ratio = ev[u][q] / gv[u][q]; err = ev[u][q] - gv[u][q]; }
-                    else          { ratio = ev[u][q]; err = ev[u][q]; }
-                    if (PASS == 1) {
-                        all[q][0] += 1.0; all[q][1] += ratio; all[q][2] += err;
-                        if (c[u] >= 0) {
-                            double* p = mine + (size_t)((c[u] * nq + q) * NV) * 32;
-                            p[0] += 1.0; p[32] += ratio; p[64] += err;
-                        }
-                    } else {
-                        const double da = err - sMean[q * rows + n_class];
-                        all[q][0] += da * da; all[q][1] += fabs(err); all[q][2] += fabs(da); all[q][3] = fmax(all[q][3], fabs(da));
-                        if (c[u] >= 0) {
-                            const double d = err - sMean[q * rows + c[u]];
-                            double* p = mine + (size_t)((c[u] * nq + q) * NV) * 32;
-                            p[0] += d * d; p[32] += fabs(err); p[64] += fabs(d); p[96] = fmax(p[96], fabs(d));
-                        }
-                    }
+            const int cc = (c[u] < 0 || c[u] >= n_class) ? -1 : c[u];
+            const double ratio = gtp ? ev[u] / gv[u] : ev[u];
+            const double err = gtp ? ev[u] - gv[u] : ev[u];
+            if (PASS == 1) {
+                all0 += 1.0; all1 += ratio; all2 += err;
+                if (cc >= 0) {
+                    double* p = mine + (size_t)(cc * NV) * 32;
+                    p[0] += 1.0; p[32] += ratio; p[64] += err;
+                }
+            } else {
+                const double da = err - mean_all;
+                all0 += da * da; all1 += fabs(err); all2 += fabs(da); all3 = fmax(all3, fabs(da));
+                if (cc >= 0) {
+                    const double d = err - sMean[q * rows + cc];
+                    double* p = mine + (size_t)(cc * NV) * 32;
+                    p[0] += d * d; p[32] += fabs(err); p[64] += fabs(d); p[96] = fmax(p[96], fabs(d));
                 }
             }
         }
     }
     __syncthreads();
-    // classes: entry e = (class, quantity, value); sum the block's warps per lane, then across lanes
-    for (int e = warp; e < entries; e += kStatLaneWarps) {
-        const int k = e % NV, cq = e / NV, q = cq % nq, c = cq / nq;
+    // classes: entry e = (quantity, class, value): add the warps that worked on that quantity per lane, then across lanes
+    for (int e = warp; e < nq * entries; e += n_warps) {
+        const int qq = e / entries, r = e - qq * entries, cidx = r / NV, k = r - cidx * NV;
         const bool is_max = (PASS == 2) && (k == 3);
         double a = 0.0;
-#pragma unroll
-        for (int w = 0; w < kStatLaneWarps; ++w) {
-            const double v = sh[((size_t)w * entries + e) * 32 + lane];
+        for (int g = 0; g < n_groups; ++g) {
+            const double v = sh[((size_t)(g * nq + qq) * entries + r) * 32 + lane];
             a = is_max ? fmax(a, v) : a + v;
         }
 #pragma unroll
@@ -737,26 +717,24 @@ __global__ void __launch_bounds__(kStatLaneBlock) k_stats_lane(long long B, Stat
             a = is_max ? fmax(a, o) : a + o;
         }
         if (lane == 0) {
-            if (is_max) atomic_max_double(out_max + (size_t)q * rows + c, a);
-            else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + c) * 4 + k, a);
+            if (is_max) atomic_max_double(out_max + (size_t)qq * rows + cidx, a);
+            else if (a != 0.0) atomicAdd(out + ((size_t)qq * rows + cidx) * 4 + k, a);
         }
     }
+    {                                                     // the "all" row of this warp's quantity
+        double av[4] = { all0, all1, all2, all3 };
 #pragma unroll
-    for (int q = 0; q < kStatMaxQ; ++q) {                 // the "all" row
-        if (q < nq) {
+        for (int k = 0; k < 4; ++k) {
+            double a = av[k];
+            const bool is_max = (PASS == 2) && (k == 3);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double a = all[q][k];
-                const bool is_max = (PASS == 2) && (k == 3);
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const double o = __shfl_xor_sync(0xffffffffu, a, off);
-                    a = is_max ? fmax(a, o) : a + o;
-                }
-                if (lane == 0) {
-                    if (is_max) atomic_max_double(out_max + (size_t)q * rows + n_class, a);
-                    else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + n_class) * 4 + k, a);
-                }
+            for (int off = 16; off >= 1; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, a, off);
+                a = is_max ? fmax(a, o) : a + o;
+            }
+            if (lane == 0) {
+                if (is_max) atomic_max_double(out_max + (size_t)q * rows + n_class, a);
+                else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + n_class) * 4 + k, a);
             }
         }
     }
@@ -983,12 +961,17 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc != PNPB200_OK) return rc;
-    const size_t lane_smem = sizeof(double) * (size_t)kStatLaneWarps * n_class * nq * (PASS == 1 ? 3 : 4) * 32;
-    if (lane_smem + 4096 <= (size_t)dp.max_smem_optin) {  // lane-private tables fit: one block per SM
+    const size_t per_warp = sizeof(double) * (size_t)n_class * (PASS == 1 ? 3 : 4) * 32;
+    int warps = (int)(((size_t)dp.max_smem_optin - 4096) / per_warp);
+    if (warps > kStatLaneMaxWarps) warps = kStatLaneMaxWarps;
+    warps -= warps % nq;                                  // every quantity gets the same number of warps
+    if (warps >= nq) {                                    // lane-private tables fit: one block per SM
+        const size_t lane_smem = per_warp * warps;
         PNP_CUDA_OK(cudaFuncSetAttribute(k_stats_lane<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
-        long long g = (B + kStatLaneBlock - 1) / kStatLaneBlock;
+        const int per_block = (warps / nq) * 32;          // problems a block covers per sweep
+        long long g = (B + per_block - 1) / per_block;
         if (g > dp.sm_count) g = dp.sm_count;
-        k_stats_lane<PASS><<<(unsigned)g, kStatLaneBlock, lane_smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
+        k_stats_lane<PASS><<<(unsigned)g, warps * 32, lane_smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
     } else {
         const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
         if (smem > 48 * 1024) PNP_CUDA_OK(cudaFuncSetAttribute(k_stats<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
