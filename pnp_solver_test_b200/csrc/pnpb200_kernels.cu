@@ -488,52 +488,46 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
 }
 
 
-template <typename T, int METHOD, int BLOCK>
-__device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
+// The O(1)-per-iteration part of the moment mapping for one problem per thread: moments parked in shared
+// memory ([PNP_NMOM][stride] columns, this thread's column at sMomCol) -> pose `out` and the 12 numbers the
+// residual pass needs (LM: the state before the last update; F2: its tail).
+template <typename T, int METHOD>
+__device__ __forceinline__ void iterate_core(const T* sMomCol, int stride, const T* sC, const SolverPrm<T>& prm,
+                                             T (&st)[PNP_NTAIL], Result<T>& out)
 {
-    constexpr int kIterBlock = BLOCK;
-    __shared__ T sC[PNP_PATC];
-    __shared__ T sMom[PNP_NMOM * kIterBlock];             // [moment][thread]: conflict-free columns
-    if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
-    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = b < a.B;
-    if (!ok) b = a.B - 1;
-#pragma unroll
-    for (int k = 0; k < PNP_NMOM; ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.ld + b];
-    __syncthreads();
     MomentsRef<T> mom;
-    mom.base = sMom + threadIdx.x;
-    mom.stride = kIterBlock;
-    Result<T> out;
-    T st[PNP_NTAIL];
+    mom.base = sMomCol;
+    mom.stride = stride;
     if (METHOD == PNPB200_METHOD_LM) {
         T xp[12];
-        solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, a.prm, xp, out);
+        solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, prm, xp, out);
 #pragma unroll
         for (int k = 0; k < 12; ++k) st[k] = xp[k];
     } else if (METHOD == PNPB200_METHOD_LM_PLUS) {
         Moments<T> mr;
 #pragma unroll
-        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMom[k * kIterBlock + threadIdx.x];
+        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMomCol[k * stride];
         T xf[12];
-        solve_lm_plus_from_moments<T, MomentsRef<T> >(mom, mr, sC, a.prm, xf, out);
+        solve_lm_plus_from_moments<T, MomentsRef<T> >(mom, mr, sC, prm, xf, out);
 #pragma unroll
         for (int k = 0; k < 12; ++k) st[k] = xf[k];
     } else {
         Moments<T> mr;
 #pragma unroll
-        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMom[k * kIterBlock + threadIdx.x];
+        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMomCol[k * stride];
         F2Tail<T> f;
-        solve_f2_from_moments<T>(mr, sC, a.prm, f, out);
+        solve_f2_from_moments<T>(mr, sC, prm, f, out);
 #pragma unroll
         for (int k = 0; k < 3; ++k) st[k] = f.phi3[k];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { st[3 + k] = f.pxn[k]; st[7 + k] = f.pyn[k]; }
         st[11] = T(0);
     }
-    if (!ok) return;
-#pragma unroll
-    for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.ld + b] = st[k];
+}
+
+template <typename T>
+__device__ __forceinline__ void write_pose(const MomArgs<T>& a, long long b, const Result<T>& out)
+{
     if (a.R) {
 #pragma unroll
         for (int e = 0; e < 9; ++e) a.R[b * 9 + e] = out.R[e];
@@ -552,6 +546,28 @@ __device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
     }
     if (a.iters) a.iters[b] = out.iters;
     if (a.best) a.best[b] = 0;
+}
+
+template <typename T, int METHOD, int BLOCK>
+__device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
+{
+    constexpr int kIterBlock = BLOCK;
+    __shared__ T sC[PNP_PATC];
+    __shared__ T sMom[PNP_NMOM * kIterBlock];             // [moment][thread]: conflict-free columns
+    if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = b < a.B;
+    if (!ok) b = a.B - 1;
+#pragma unroll
+    for (int k = 0; k < PNP_NMOM; ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.ld + b];
+    __syncthreads();
+    Result<T> out;
+    T st[PNP_NTAIL];
+    iterate_core<T, METHOD>(sMom + threadIdx.x, kIterBlock, sC, a.prm, st, out);
+    if (!ok) return;
+#pragma unroll
+    for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.ld + b] = st[k];
+    write_pose<T>(a, b, out);
 }
 
 // Register budget per thread given directly: the 64 Ki registers of an SM hold 9 warps at 224 registers
@@ -680,9 +696,13 @@ static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, lo
 }
 
 // LM / linear F2 with one pattern: moments -> iterate -> residual (see the kernels' header).
-// (Measured and rejected: cutting the batch into slices that flow through the three passes on
-// different streams.  The kernels do overlap, but k_iterate fills the register file, so the
-// streaming blocks displace iterate blocks instead of adding warps: same total time.)
+// (Measured and rejected: (1) cutting the batch into slices that flow through the three passes on
+// different streams -- the kernels do overlap, but k_iterate fills the register file, so the
+// streaming blocks displace iterate blocks instead of adding warps: same total time; (2) the three
+// passes in one kernel per 32-problem tile, second stream issued before the iterations: 1.479 ms
+// against 1.460 ms -- with 8 warps per SM the warps that stream are simply missing from the FP64
+// pipe; (3) warp-specialised producer / consumer CTAs do not fit: setmaxnreg works per 128-thread
+// warpgroup, and 4 compute warps at 224 registers + 4 streaming warps already fill half an SM.)
 template <typename T, int METHOD>
 static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStream_t stream)
 {
