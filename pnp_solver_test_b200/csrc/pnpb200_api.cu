@@ -1,6 +1,7 @@
 // pnpb200_api.cu -- the C ABI of the solve path (include/pnpb200.h): argument checks, dispatch to the
 // per-(dtype, method group) objects of pnpb200_kernels.cu, per-kernel profiling, and the
 // host-buffer pipeline.
+#include <map>
 #include <mutex>
 #include <string.h>
 #include <vector>
@@ -52,6 +53,51 @@ int get_device_props(DeviceProps* out)
 
 
 thread_local ProfileRing g_prof;
+
+namespace {
+struct KernelKey {
+    int dev; const void* fn; int block; size_t smem;
+    bool operator<(const KernelKey& o) const
+    {
+        if (dev != o.dev) return dev < o.dev;
+        if (fn != o.fn) return fn < o.fn;
+        if (block != o.block) return block < o.block;
+        return smem < o.smem;
+    }
+};
+}  // namespace
+
+cudaError_t set_dynamic_smem(const void* kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<KernelKey, size_t> done;               // largest size set so far
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = done[KernelKey{ dev, kernel, 0, 0 }];
+    if (cur >= bytes && cur != 0) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
+
+cudaError_t blocks_per_sm(int* out, const void* kernel, int block_threads, size_t smem_bytes)
+{
+    static std::mutex mu;
+    static std::map<KernelKey, int> cache;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    const KernelKey key{ dev, kernel, block_threads, smem_bytes };
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return cudaSuccess; }
+    int n = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, block_threads, smem_bytes);
+    if (e == cudaSuccess) { cache[key] = n; *out = n; }
+    return e;
+}
 
 void fill_default_params(pnpb200_params* p)
 {

@@ -897,7 +897,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
             a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
-            PNP_CUDA_OK(cudaFuncSetAttribute(k_report_chunk<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+            PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT>, csmem)); \
             k_report_chunk<TT><<<grid, 32, csmem, st>>>(a);                                                             \
         }
         DISPATCH_DTYPE(dtype, LAUNCH_REPORT_CHUNK(double), LAUNCH_REPORT_CHUNK(float));
@@ -913,7 +913,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
             a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
-            PNP_CUDA_OK(cudaFuncSetAttribute(k_report_thread<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_thread<TT>, smem)); \
             k_report_thread<TT><<<grid, 32, smem, st>>>(a);                                                             \
         }
         DISPATCH_DTYPE(dtype, LAUNCH_REPORT_THREAD(double), LAUNCH_REPORT_THREAD(float));
@@ -967,14 +967,14 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
     warps -= warps % nq;                                  // every quantity gets the same number of warps
     if (warps >= nq) {                                    // lane-private tables fit: one block per SM
         const size_t lane_smem = per_warp * warps;
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stats_lane<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stats_lane<PASS>, lane_smem));
         const int per_block = (warps / nq) * 32;          // problems a block covers per sweep
         long long g = (B + per_block - 1) / per_block;
         if (g > dp.sm_count) g = dp.sm_count;
         k_stats_lane<PASS><<<(unsigned)g, warps * 32, lane_smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
     } else {
         const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
-        if (smem > 48 * 1024) PNP_CUDA_OK(cudaFuncSetAttribute(k_stats<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 48 * 1024) PNP_CUDA_OK(set_dynamic_smem((const void*)k_stats<PASS>, smem));
         k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
     }
     PNP_CUDA_OK(cudaGetLastError());

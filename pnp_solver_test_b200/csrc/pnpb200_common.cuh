@@ -44,6 +44,11 @@ struct DeviceProps {
 };
 int get_device_props(DeviceProps* out);   // cached per device; defined in pnpb200_api.cu
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy query, remembered per (device, kernel): both cost
+// tens of microseconds on the host, which is visible when a call is only a few hundred microseconds of kernels
+cudaError_t set_dynamic_smem(const void* kernel, size_t bytes);                                   // defined in pnpb200_api.cu
+cudaError_t blocks_per_sm(int* out, const void* kernel, int block_threads, size_t smem_bytes);   // defined in pnpb200_api.cu
+
 // ------------------------------------------------------------------------------------------
 // optional per-kernel timing (PNPB200_FLAG_PROFILE): a ring of event quadruples per host thread
 // ------------------------------------------------------------------------------------------

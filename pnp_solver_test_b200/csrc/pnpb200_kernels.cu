@@ -488,6 +488,118 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
 }
 
 
+// ------------------------------------------------------------------------------------------
+// One problem per warp for large n, rows staged by TMA bulk copies: each warp streams its problems'
+// rows through a ring of kRingSlots shared-memory slots of kRingPoints points (one cp.async.bulk per
+// slot, issued by lane 0, completion on the slot's mbarrier), kRingSlots - 1 copies ahead of the
+// arithmetic and straight across problem boundaries, so that the bytes in flight per SM do not
+// depend on registers or on the unroll depth of a load loop (the __ldg version reached 50-60 % of
+// the HBM peak on 100 k x 1024 points).  Lanes read consecutive 16-byte pixels: conflict-free.  The
+// pattern (24 KB for 1024 points) is read through L1 instead of taking shared memory from the ring.
+// Requires all landmarks (no selection) and rows that are a multiple of 16 bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int kRingSlots = 3;
+constexpr int kRingPoints = 256;          // 4 KB per slot in FP64: 8 points per lane between two barrier waits
+constexpr int kRingWarps = 8;
+
+template <typename T, int METHOD, int PASS>
+__global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __grid_constant__ MomArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typedef typename Vec2<T>::type V2;
+    T* sRing = reinterpret_cast<T*>(smem_raw);                                 // [warp][slot][kRingPoints][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kRingWarps * kRingSlots * kRingPoints * 2 * sizeof(T));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const T* __restrict__ gP = a.pattern;
+    T* ring = sRing + (size_t)warp * kRingSlots * kRingPoints * 2;
+    uint64_t* bar = bars + warp * kRingSlots;
+    if (lane == 0)
+        for (int k = 0; k < kRingSlots; ++k) mbar_init(bar + k, 1);
+    __syncwarp();
+    const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
+    const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
+    const int n = a.n, cpp = (n + kRingPoints - 1) / kRingPoints;            // chunks per problem
+    const long long w0 = (long long)blockIdx.x * kRingWarps + warp, wstride = (long long)gridDim.x * kRingWarps;
+    const long long my_problems = (w0 < a.B) ? (a.B - w0 + wstride - 1) / wstride : 0;
+    const long long total = my_problems * cpp;                                // chunks this warp will consume
+    // chunk g of this warp = chunk (g % cpp) of problem w0 + (g / cpp) * wstride
+    auto issue = [&](long long g) {
+        if (lane == 0) {
+            const long long b = w0 + (g / cpp) * wstride;
+            const int c = (int)(g % cpp);
+            const int cnt = (n - c * kRingPoints < kRingPoints) ? (n - c * kRingPoints) : kRingPoints;
+            const uint32_t bytes = (uint32_t)cnt * 2u * (uint32_t)sizeof(T);
+            const int slot = (int)(g % kRingSlots);
+            mbar_expect_tx(bar + slot, bytes);
+            bulk_copy_g2s(ring + (size_t)slot * kRingPoints * 2, a.uv + ((size_t)b * n + (size_t)c * kRingPoints) * 2, bytes, bar + slot);
+        }
+    };
+    for (long long g = 0; g < kRingSlots - 1 && g < total; ++g) issue(g);
+    uint32_t phase = 0;                                                      // bit s = parity to wait for on slot s
+    long long g = 0;
+    for (long long p = 0; p < my_problems; ++p) {
+        const long long b = w0 + p * wstride;
+        Moments<T> mom;
+        T st[PNP_NTAIL];
+        T acc0 = T(0), acc1 = T(0);
+        if (PASS == 0) mom.zero();
+        else {
+#pragma unroll
+            for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.ld + b];
+        }
+        for (int c = 0; c < cpp; ++c, ++g) {
+            const int slot = (int)(g % kRingSlots);
+            // refill the slot that was consumed one step ago, then wait for this one
+            if (g + kRingSlots - 1 < total) {
+                __syncwarp();
+                fence_proxy_async();
+                issue(g + kRingSlots - 1);
+            }
+            mbar_wait(bar + slot, (phase >> slot) & 1u);
+            phase ^= (1u << slot);
+            const V2* row = reinterpret_cast<const V2*>(ring + (size_t)slot * kRingPoints * 2);
+            const int cnt = (n - c * kRingPoints < kRingPoints) ? (n - c * kRingPoints) : kRingPoints;
+#pragma unroll 4
+            for (int k = lane; k < cnt; k += 32) {
+                const V2 px = row[k];
+                const int i = c * kRingPoints + k;
+                const T bx = k00 * px.x + k01 * px.y + k02;                   // nu = K^-1 [u, v, 1]^T (:3305)
+                const T by = k10 * px.x + k11 * px.y + k12;
+                const T th[3] = { __ldg(gP + 3 * i), __ldg(gP + 3 * i + 1), __ldg(gP + 3 * i + 2) };
+                if (PASS == 0) {
+                    mom.template add<METHOD != PNPB200_METHOD_LINEAR_F2>(th, bx, by);
+                } else if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
+                    const T aa = th[0] * st[0] + th[1] * st[1] + th[2] * st[2];
+                    const T bb = th[0] * st[3] + th[1] * st[4] + th[2] * st[5];
+                    const T cc = th[0] * st[6] + th[1] * st[7] + th[2] * st[8];
+                    const T rx = bx - (st[11] * (aa - bx * cc) + st[9]);      // z - hx (:3750, :2679)
+                    const T ry = by - (st[11] * (bb - by * cc) + st[10]);
+                    acc0 = t_fma(rx, rx, t_fma(ry, ry, acc0));
+                } else {
+                    const T db = T(1) + (th[0] * st[0] + th[1] * st[1] + th[2] * st[2]);
+                    const T dx = th[0] * st[3] + th[1] * st[4] + th[2] * st[5] + st[6];
+                    const T dy = th[0] * st[7] + th[1] * st[8] + th[2] * st[9] + st[10];
+                    const T ex = bx * db - dx, ey = by * db - dy;
+                    acc0 = t_fma(ex, ex, acc0); acc1 = t_fma(ey, ey, acc1);
+                }
+            }
+        }
+        if (PASS == 0) {
+            mom.template reduce<32, METHOD != PNPB200_METHOD_LINEAR_F2>();
+            T mine = T(0);                                                    // after the butterfly every lane holds every sum
+#pragma unroll
+            for (int k = 0; k < PNP_NMOM; ++k) if (lane == k) mine = mom.at(k);
+            if (lane < PNP_NMOM) a.mom[(size_t)lane * a.ld + b] = mine;
+        } else {
+            acc0 = group_sum<32>(acc0); acc1 = group_sum<32>(acc1);
+            if (lane == 0 && a.res) {
+                if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) a.res[b] = t_sqrt(acc0);   // :2681
+                else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
+            }
+        }
+    }
+}
+
 // The O(1)-per-iteration part of the moment mapping for one problem per thread: moments parked in shared
 // memory ([PNP_NMOM][stride] columns, this thread's column at sMomCol) -> pose `out` and the 12 numbers the
 // residual pass needs (LM: the state before the last update; F2: its tail).
@@ -687,7 +799,11 @@ static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, lo
     } else if (shape == 1) {                                  // whole-row tiles
         if (pass == 0) k_stream_thread<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
         else           k_stream_thread<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
-    } else {                                                  // one problem per warp
+    } else if (shape == 3) {                                  // one problem per warp, rows through a TMA ring
+        const unsigned grid = (unsigned)persistent_grid((nb + kRingWarps - 1) / kRingWarps, dp.sm_count, per_sm);
+        if (pass == 0) k_stream_warp_tma<T, METHOD, 0><<<grid, kRingWarps * 32, smem, stream>>>(m);
+        else           k_stream_warp_tma<T, METHOD, 1><<<grid, kRingWarps * 32, smem, stream>>>(m);
+    } else {                                                  // one problem per warp, coalesced loads
         const unsigned grid = (unsigned)persistent_grid((nb + 7) / 8, dp.sm_count, per_sm);
         if (pass == 0) k_stream_warp<T, METHOD, 0><<<grid, 256, smem, stream>>>(m);
         else           k_stream_warp<T, METHOD, 1><<<grid, 256, smem, stream>>>(m);
@@ -735,17 +851,24 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     size_t smem;
     if (by_thread && !a.idx_mode && sg.use_stream && a.tune != 9) {
         shape = 0; smem = 2 * sg.buf_bytes + pat_bytes + 32;
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_chunk<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 0>, smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 1>, smem));
     } else if (by_thread) {
         shape = 1; smem = thread_smem;
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_thread<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_thread<T, METHOD, 0>, smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_thread<T, METHOD, 1>, smem));
+    } else if (!a.idx_mode && ((size_t)a.n_total * 2 * sizeof(T)) % 16 == 0 && a.tune != 9 &&
+               a.n_total >= kRingPoints) {
+        shape = 3;
+        smem = (size_t)kRingWarps * kRingSlots * (kRingPoints * 2 * sizeof(T) + 8);
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_warp_tma<T, METHOD, 0>, smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_warp_tma<T, METHOD, 1>, smem));
+        PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_stream_warp_tma<T, METHOD, 0>, kRingWarps * 32, smem));
     } else {
         shape = 2; smem = warp_smem;
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_stream_warp<T, METHOD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stream_warp<T, METHOD, 0>, 256, smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_warp<T, METHOD, 0>, smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_warp<T, METHOD, 1>, smem));
+        PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_stream_warp<T, METHOD, 0>, 256, smem));
     }
 
     k_pattern_constants<T><<<1, 32, 0, stream>>>(m);
@@ -784,7 +907,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     }
     if (mapping == PNPB200_MAP_THREAD) {
         if (thread_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_thread<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thread_smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_solve_thread<T, METHOD>, thread_smem));
         SolveArgs<T> at = a;
         at.row_pitch = g.row_pitch;
         at.use_tma = g.use_tma;
@@ -796,9 +919,9 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
         g_prof.mark(slot, stream);
     } else if (mapping == PNPB200_MAP_WARP) {
         if (warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
-        PNP_CUDA_OK(cudaFuncSetAttribute(k_solve_warp<T, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_solve_warp<T, METHOD>, warp_smem));
         int per_sm = 1;
-        PNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_warp<T, METHOD>, kWarpsPerBlock * 32, warp_smem));
+        PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_solve_warp<T, METHOD>, kWarpsPerBlock * 32, warp_smem));
         const long long grid = persistent_grid((a.B + kWarpsPerBlock - 1) / kWarpsPerBlock, dp.sm_count, per_sm);
         const int slot = a.profile ? g_prof.begin() : -1;
         g_prof.mark(slot, stream);

@@ -166,7 +166,7 @@ template <typename T, int LPP, typename Pts, bool WITH_W = true>
 PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n, int sub, Moments<T>& mom)
 {
     mom.zero();
-#pragma unroll 4
+#pragma unroll (LPP == 32 ? 8 : 4)
     for (int i = sub; i < n; i += LPP) {
         const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
         T bx, by;
