@@ -128,6 +128,31 @@ class ClockSampler(threading.Thread):
         return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads (and with them the first-touch placement of the pinned host buffers it is
+    about to allocate) to the NUMA node its GPU hangs off -- what `numactl --cpunodebind --membind` does
+    in a launcher script.  Matters for the end-to-end arm at N > 1: eight ranks streaming 1 GB per step
+    from host memory otherwise cross the socket interconnect.  Returns a description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"gpu": bdf, "node": node, "bound": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu": bdf, "node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:                                # no sysfs, no permission: run unbound
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,6 +232,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the CUDA path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if not args.no_numa else {"bound": False, "why": "--no-numa"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, n = args.problems, N_POINTS
@@ -307,7 +333,7 @@ def run_ours(args):
         copy_ms = c0.elapsed_time(c1) / 3
         e2e_ms = 1e3 * float(tt[0]) / e_steps
         e2e = {"value": world * B * e_steps / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e_steps, "ms_per_step": e2e_ms,
+               "steps": e_steps, "ms_per_step": e2e_ms, "numa": numa,
                "api": "pnpb200_solve_batch_host via HostPipeline.solve (pinned host buffers, %d-problem chunks, 3 streams)" % args.chunk,
                "bound": {"what": "PCIe host->device copy of the pixels", "h2d_copy_alone_ms": copy_ms,
                          "h2d_copy_alone_gbs": h2d / (copy_ms * 1e-3) / 1e9, "e2e_over_copy": e2e_ms / copy_ms}}
@@ -382,6 +408,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 17, help="e2e pipeline chunk (problems)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
