@@ -84,6 +84,10 @@ PNP_DEV double sqrt_nonneg(double a)
     const double p = fma(0.375, e, 0.5) * e;
     return fma(s0, p, s0);
 }
+// sqrt of a non-negative number, zero included, without the slow-path branch of sqrt()
+template <typename T> PNP_DEV T t_sqrt_nn(T a);
+template <> PNP_DEV double t_sqrt_nn<double>(double a) { return sqrt_nonneg(a); }
+template <> PNP_DEV float t_sqrt_nn<float>(float a) { return sqrtf(a); }
 template <typename T> PNP_DEV T t_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> PNP_DEV T t_fma(T a, T b, T c);
 template <> PNP_DEV double t_fma<double>(double a, double b, double c) { return fma(a, b, c); }

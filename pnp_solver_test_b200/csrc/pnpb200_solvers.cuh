@@ -350,7 +350,7 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
         Om[sidx<6>(5, 5)] = t_fma(w, nT, Om[sidx<6>(5, 5)]);
 #pragma unroll
         for (int a = 0; a < 6; ++a) zeta[a] = t_fma(w, hv[a], zeta[a]);
-        const T res_new = t_sqrt(res2);                   // :2905-2907
+        const T res_new = t_sqrt_nn<T>(res2);                   // :2905-2907
         // ---- x = pinv(Omega) zeta (:2924-2925)
         spd_inverse<T, 6>(Om);
         T xn[6];
@@ -362,7 +362,7 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
             for (int e = 0; e < 6; ++e) x[e] = xn[e];
             res = res_new;
             ++iters;
-            const T ratio = (res - res_old) / res_old;    // :2945
+            const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference    // :2945
             res_old = res;
             if (t_abs(ratio) < prm.exit_tol) done = true; // :2952
         }
@@ -845,7 +845,7 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
             eif2_row1<T, U2>(Om, zeta, j2, T(1) - n2 + dot3<T>(j2, u2), wc3);
             eif2_row1<T, U3>(Om, zeta, j3, T(1) - n3 + dot3<T>(j3, u3), wc3);
         }
-        const T res_new = t_sqrt(res2);
+        const T res_new = t_sqrt_nn<T>(res2);
         // ---- x = pinv(Omega) zeta (:2184-2185)
         spd_inverse<T, 12>(Om);
         T xn[12];
@@ -857,7 +857,7 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
             for (int e = 0; e < 12; ++e) x[e] = xn[e];
             res = res_new;
             ++iters;
-            const T ratio = (res - res_old) / res_old;               // :2196
+            const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference               // :2196
             res_old = res;
             if (t_abs(ratio) < prm.exit_tol) done = true;            // :2202
         }
