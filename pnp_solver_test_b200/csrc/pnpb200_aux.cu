@@ -875,6 +875,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
                          double* report, int32_t* flags, int32_t* max_idx, void* stream)
 {
     if (B < 0 || n < 1 || !pattern || !uv || !K || !R || !t || !euler_deg || !gt || !report) return PNPB200_EINVAL;
+    if (((uintptr_t)uv & 15u) != 0) return PNPB200_EINVAL;   // rows are staged with 16-byte bulk copies
     if (B == 0) return PNPB200_OK;
     KMat km;
     for (int e = 0; e < 9; ++e) km.k[e] = K[e];

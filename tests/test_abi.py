@@ -43,6 +43,10 @@ def test_argument_validation_needs_no_gpu():
     rc = _lib.lib.pnpb200_solve_batch(0, 0, C.c_int64(4), 6, 6, None, None, 1, None, None, None,
                                       None, None, None, None, None, None, None)
     assert rc == -1                                   # PNPB200_EINVAL: null uv
+    K = (C.c_double * 9)(225.7, 0, 160, 0, 225.7, 120, 0, 0, 1)
+    rc = _lib.lib.pnpb200_solve_batch(0, 0, C.c_int64(4), 6, 6, C.c_void_p(0x1008), C.c_void_p(0x2000), 1, None, K, None,
+                                      None, None, None, None, None, None, None)
+    assert rc == -1                                   # uv not 16-byte aligned
     assert _lib.lib.pnpb200_default_params(None) == -1
     with pytest.raises(_lib.PnpB200Error):
         _lib.check(-1, "x")
