@@ -214,11 +214,13 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
     Moments<T> mom;
     if (HYBRID) accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T x[6] = { T(1), T(0), T(0), T(0), T(0), T(0) };      // :2831-2833
-    T Sig[21];
+    // One 6 x 6 array carries Sigma from one iteration to the next and Omega inside it.  Lanes that have
+    // left the loop (done) keep their x, res and iters; what their matrix becomes no longer matters.
+    T Om[21];
 #pragma unroll
-    for (int e = 0; e < 21; ++e) Sig[e] = T(0);
+    for (int e = 0; e < 21; ++e) Om[e] = T(0);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) Sig[sidx<6>(i, i)] = prm.sigma0;   // pinv(1e-5 I) (:2836-2837)
+    for (int i = 0; i < 6; ++i) Om[sidx<6>(i, i)] = prm.sigma0;   // pinv(1e-5 I) (:2836-2837)
     T res_old = prm.res_old0, res = T(1e5);
     bool done = false;
     int iters = 0;
@@ -229,9 +231,6 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
         if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
         else          { if (done) break; }
         // ---- predict: Omega = pinv(Sigma + R) (:2887), zeta = Omega x (:2889)
-        T Om[21];
-#pragma unroll
-        for (int e = 0; e < 21; ++e) Om[e] = Sig[e];
 #pragma unroll
         for (int i = 0; i < 6; ++i) Om[sidx<6>(i, i)] += (i < 4) ? prm.proc_q : prm.proc_d;
         spd_inverse<T, 6>(Om);
@@ -356,8 +355,6 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
         T xn[6];
         sym_matvec<T, 6>(Om, zeta, xn);
         if (!done) {
-#pragma unroll
-            for (int e = 0; e < 21; ++e) Sig[e] = Om[e];
 #pragma unroll
             for (int e = 0; e < 6; ++e) x[e] = xn[e];
             res = res_new;
@@ -724,11 +721,12 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
     Moments<T> mom;
     accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2058-2063
-    T Sig[78];
+    // One 12 x 12 array carries Sigma from one iteration to the next and Omega inside it (see solve_qeif)
+    T Om[78];
 #pragma unroll
-    for (int e = 0; e < 78; ++e) Sig[e] = T(0);
+    for (int e = 0; e < 78; ++e) Om[e] = T(0);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) Sig[sidx<12>(i, i)] = T(1e5);        // pinv(1e-5 I) (:2067-2068)
+    for (int i = 0; i < 12; ++i) Om[sidx<12>(i, i)] = T(1e5);         // pinv(1e-5 I) (:2067-2068)
     T res_old = T(1e-7), res = T(1e5);                               // :2101-2102
     bool done = false;
     int iters = 0;
@@ -746,9 +744,6 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
         const T u13 = dot3<T>(u1, u3), u23 = dot3<T>(u2, u3), u12 = dot3<T>(u1, u2);
         // ---- predict: Omega = pinv(Sigma + R_k) (:2146-2150), zeta = Omega x (:2152)
         // R_k's u blocks: so3(u_i) sigma^2 so3(u_j)^T = sigma^2 ((u_i . u_j) I - u_j u_i^T)   (:3690-3696)
-        T Om[78];
-#pragma unroll
-        for (int e = 0; e < 78; ++e) Om[e] = Sig[e];
         {
             const T* uu[3] = { u1, u2, u3 };
             const T dd[3][3] = { { u11, u12, u13 }, { u12, u22, u23 }, { u13, u23, u33 } };
@@ -851,8 +846,6 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
         T xn[12];
         sym_matvec<T, 12>(Om, zeta, xn);
         if (!done) {
-#pragma unroll
-            for (int e = 0; e < 78; ++e) Sig[e] = Om[e];
 #pragma unroll
             for (int e = 0; e < 12; ++e) x[e] = xn[e];
             res = res_new;
