@@ -259,27 +259,62 @@ def synth_face_variation(b0, B, pattern, K, fixed_index, perturb_radius_m=0.02, 
     return dict(uv=uv, gt=gt, perturb=pert)
 
 
-def topk_thresholds(values, k, idx0=0, group=None):
+def key_of(values, idx0=0):
+    """The selection key of each problem as two NumPy integer arrays (hi uint64 = bits of |value|, NaN as
+    +inf; lo uint32 = ~global index): what pnpb200_topk_histogram / pnpb200_fragility_accumulate compare."""
+    a = np.abs(np.asarray(values, np.float64))
+    hi = np.where(np.isnan(a), np.float64(np.inf), a).view(np.uint64)
+    lo = (~(np.arange(a.shape[0], dtype=np.int64) + int(idx0))).astype(np.uint32)
+    return hi, lo
+
+
+def numpy_histogram(values_list, idx0):
+    """Host stand-in for pnpb200_topk_histogram (tests, and shards that live in host memory):
+    returns hist_fn(prefix_hi, prefix_lo, n_digits) -> int64 [nq, 256]."""
+    keys = [key_of(v, idx0) for v in values_list]
+
+    def digit(hi, lo, d):
+        return ((hi >> np.uint64(56 - 8 * d)) & np.uint64(0xff)).astype(np.int64) if d < 8 else \
+               ((lo >> np.uint32(24 - 8 * (d - 8))) & np.uint32(0xff)).astype(np.int64)
+
+    def fn(pre_hi, pre_lo, nd):
+        out = np.zeros((len(keys), 256), np.int64)
+        for q, (hi, lo) in enumerate(keys):
+            m = np.ones(hi.shape[0], bool)
+            for d in range(nd):
+                want = (pre_hi[q] >> (56 - 8 * d)) & 0xff if d < 8 else (pre_lo[q] >> (24 - 8 * (d - 8))) & 0xff
+                m &= digit(hi, lo, d) == want
+            out[q] = np.bincount(digit(hi, lo, nd)[m], minlength=256)
+        return out
+    return fn
+
+
+def topk_thresholds(values, k, idx0=0, group=None, hist_fn=None):
     """Exact k-th largest key (|value| bits, then smaller global index first) of each quantity over
     ALL ranks' shards: 12 histogram kernels; the 256-bin histograms are the only thing all-reduced.
-    values: list of 1-D FP64 CUDA views of this rank's shard.  Returns (hi [nq] uint64, lo [nq] uint32)
-    as Python ints -- every key >= (hi, lo) is in the top k."""
+    values: list of 1-D FP64 CUDA views of this rank's shard (or, with hist_fn = numpy_histogram(...),
+    anything).  Returns (hi [nq] uint64, lo [nq] uint32) as Python ints -- every key >= (hi, lo) is in
+    the top k."""
     import torch.distributed as dist
     nq = len(values)
-    dev = values[0].device
-    B = int(values[0].shape[0])
-    PD = C.POINTER(C.c_double)
-    val_a = (PD * nq)(*[C.cast(ptr(v), PD) for v in values])
-    str_a = (C.c_int64 * nq)(*[int(v.stride(0)) if B else 1 for v in values])
     hi, lo, rem = [0] * nq, [0] * nq, [int(k)] * nq
-    hist = torch.zeros((nq, 256), dtype=torch.int64, device=dev)
+    if hist_fn is None:
+        dev = values[0].device
+        B = int(values[0].shape[0])
+        PD = C.POINTER(C.c_double)
+        val_a = (PD * nq)(*[C.cast(ptr(v), PD) for v in values])
+        str_a = (C.c_int64 * nq)(*[int(v.stride(0)) if B else 1 for v in values])
+        hist = torch.zeros((nq, 256), dtype=torch.int64, device=dev)
     for d in range(12):
-        hi_a = (C.c_uint64 * nq)(*hi)
-        lo_a = (C.c_uint32 * nq)(*lo)
-        with torch.cuda.device(dev):
-            check(lib.pnpb200_topk_histogram(C.c_int64(B), C.c_int64(int(idx0)), C.c_int(nq), val_a, str_a, hi_a, lo_a, C.c_int(d),
-                                             C.cast(ptr(hist), C.POINTER(C.c_uint64)), _stream_ptr(dev)), "pnpb200_topk_histogram")
-        _lib.count_launch()
+        if hist_fn is None:
+            hi_a = (C.c_uint64 * nq)(*hi)
+            lo_a = (C.c_uint32 * nq)(*lo)
+            with torch.cuda.device(dev):
+                check(lib.pnpb200_topk_histogram(C.c_int64(B), C.c_int64(int(idx0)), C.c_int(nq), val_a, str_a, hi_a, lo_a, C.c_int(d),
+                                                 C.cast(ptr(hist), C.POINTER(C.c_uint64)), _stream_ptr(dev)), "pnpb200_topk_histogram")
+            _lib.count_launch()
+        else:
+            hist = torch.from_numpy(hist_fn(hi, lo, d))
         _all_reduce(hist, dist.ReduceOp.SUM if dist.is_available() else None, group)
         h = hist.cpu().numpy()
         for q in range(nq):

@@ -154,3 +154,48 @@ def test_result_and_statistic_writers_match_reference(tmp_path):
         assert txt == str(g["stat_txt_" + name]) and open(tmp_path / "s.txt").read() == txt
         wl.write_statistic_csv(d, tmp_path / "s.csv", is_horizontal=True)
         assert open(tmp_path / "s.csv", newline="").read() == str(g["stat_csv_" + name])
+
+
+def _topk_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from pnp_solver_test_b200 import workload as wl
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_golden("fragility")
+    err = np.abs(g["err"])
+    err[::7, 1] = 3.25                                              # exact ties across both shards
+    lo, hi = wl.shard_range(err.shape[0], rank, world)
+    vals = [err[lo:hi, qq] for qq in range(4)]
+    thr = wl.topk_thresholds(vals, 60, idx0=lo, hist_fn=wl.numpy_histogram(vals, lo))
+    sel = []
+    for qq in range(4):
+        khi, klo = wl.key_of(vals[qq], lo)
+        m = (khi > np.uint64(thr[0][qq])) | ((khi == np.uint64(thr[0][qq])) & (klo >= np.uint32(thr[1][qq])))
+        sel.append((np.flatnonzero(m) + lo).tolist())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sel)
+    if rank == 0:
+        q.put((gathered, err))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_topk_selection_over_gloo_world_size_2():
+    """The radix select of workload.fragility_analysis across two shards (histograms all-reduced over
+    gloo, NumPy standing in for the histogram kernel): the union of the per-shard selections is exactly
+    the top-k of the whole batch in the order the script's heaps pop (largest |err|, then smaller idx)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_topk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, err = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for qq in range(4):
+        got = sorted(gathered[0][qq] + gathered[1][qq])
+        want = sorted(sorted(range(err.shape[0]), key=lambda i: (-err[i, qq], i))[:60])
+        assert got == want, qq
