@@ -98,6 +98,7 @@ typedef struct pnpb200_synth {
 } pnpb200_synth;
 
 int pnpb200_version(void);
+int64_t pnpb200_launch_count(void);             /* kernels launched by this library since it was loaded (all threads) */
 const char* pnpb200_last_error(void);          /* text of the last CUDA error seen by this thread */
 int pnpb200_default_params(pnpb200_params* p);
 int pnpb200_default_synth(pnpb200_synth* s);

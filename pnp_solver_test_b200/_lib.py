@@ -21,7 +21,7 @@ FLAG_QEIF_DIRECT = 2
 MAX_PATTERNS = 8
 
 EXPORTS = [
-    "pnpb200_version", "pnpb200_last_error", "pnpb200_default_params", "pnpb200_default_synth",
+    "pnpb200_version", "pnpb200_launch_count", "pnpb200_last_error", "pnpb200_default_params", "pnpb200_default_synth",
     "pnpb200_device_info", "pnpb200_workspace_bytes", "pnpb200_solve_batch", "pnpb200_pipeline_create", "pnpb200_pipeline_destroy",
     "pnpb200_solve_batch_host", "pnpb200_R_from_euler", "pnpb200_euler_from_R", "pnpb200_project",
     "pnpb200_synth_batch", "pnpb200_report_batch", "pnpb200_stats_pass1", "pnpb200_stats_pass2",
@@ -63,6 +63,7 @@ for _name in EXPORTS:
     if _name not in ("pnpb200_last_error",):
         getattr(lib, _name).restype = C.c_int
 lib.pnpb200_workspace_bytes.restype = C.c_int64
+lib.pnpb200_launch_count.restype = C.c_int64
 
 _ERR = {-1: "EINVAL (bad argument)", -2: "ECUDA (CUDA runtime error)", -3: "ENODEVICE (no usable CUDA device)",
         -4: "ETOOLARGE (n too large for the selected mapping)"}

@@ -181,7 +181,7 @@ int pnpb200_topk_histogram(int64_t B, int64_t idx0, int nq, const double* const*
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc != PNPB200_OK) return rc;
-    k_topk_hist<<<grid_cap(B, 256, dp.sm_count * 8), 256, 0, st>>>(B, idx0, in, n_digits_decided, (unsigned long long*)hist);
+    k_topk_hist<<<grid_cap(B, 256, dp.sm_count * 8), 256, 0, st>>>(B, idx0, in, n_digits_decided, (unsigned long long*)hist); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -216,13 +216,13 @@ int pnpb200_fragility_accumulate(int64_t B, int64_t idx0, int nq, const double* 
     if (rc != PNPB200_OK) return rc;
     k_select<<<grid_cap(B, 256, dp.sm_count * 8), 256, 0, st>>>(B, idx0, in, perturb, n, list_capacity, (long long*)list,
                                                                (unsigned long long*)n_selected, (unsigned long long*)count,
-                                                               value_sum, value_max);
+                                                               value_sum, value_max); count_kernel_launches(1);
     const int tiles = (D + kGramTile - 1) / kGramTile;
     int slices = (dp.sm_count * 4) / (tiles * (tiles + 1) / 2 * nq);
     if (slices < 1) slices = 1;
     if (slices > 256) slices = 256;
     k_gram<<<dim3(tiles, tiles, nq * slices), kGramTile * kGramTile, 0, st>>>(perturb, D, list_capacity, (const long long*)list,
-                                                                              (const unsigned long long*)n_selected, slices, gram);
+                                                                              (const unsigned long long*)n_selected, slices, gram); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

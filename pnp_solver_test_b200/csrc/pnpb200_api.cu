@@ -1,6 +1,7 @@
 // pnpb200_api.cu -- the C ABI of the solve path (include/pnpb200.h): argument checks, dispatch to the
 // per-(dtype, method group) objects of pnpb200_kernels.cu, per-kernel profiling, and the
 // host-buffer pipeline.
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string.h>
@@ -53,6 +54,9 @@ int get_device_props(DeviceProps* out)
 
 
 thread_local ProfileRing g_prof;
+
+static std::atomic<long long> g_launches{0};
+void count_kernel_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
 struct KernelKey {
@@ -117,6 +121,7 @@ using namespace pnpb200;
 extern "C" {
 
 int pnpb200_version(void) { return PNPB200_VERSION; }
+int64_t pnpb200_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 const char* pnpb200_last_error(void) { return g_last_error; }
 
 int pnpb200_default_params(pnpb200_params* p)

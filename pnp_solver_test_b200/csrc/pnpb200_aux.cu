@@ -806,7 +806,7 @@ int pnpb200_R_from_euler(int dtype, int64_t B, const void* euler, int is_degree,
     if (B == 0) return PNPB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_DTYPE(dtype, (k_R_from_euler<double><<<grid_for(B, 128), 128, 0, st>>>(B, euler, is_degree, R)),
-                   (k_R_from_euler<float><<<grid_for(B, 128), 128, 0, st>>>(B, euler, is_degree, R)));
+                   (k_R_from_euler<float><<<grid_for(B, 128), 128, 0, st>>>(B, euler, is_degree, R))); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -817,7 +817,7 @@ int pnpb200_euler_from_R(int dtype, int64_t B, const void* R, int is_degree, voi
     if (B == 0) return PNPB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_DTYPE(dtype, (k_euler_from_R<double><<<grid_for(B, 128), 128, 0, st>>>(B, R, is_degree, euler)),
-                   (k_euler_from_R<float><<<grid_for(B, 128), 128, 0, st>>>(B, R, is_degree, euler)));
+                   (k_euler_from_R<float><<<grid_for(B, 128), 128, 0, st>>>(B, R, is_degree, euler))); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -832,7 +832,7 @@ int pnpb200_project(int dtype, int64_t B, int n, const void* pattern, const doub
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_DTYPE(dtype,
                    (k_project<double><<<grid_for(B * n, 256), 256, 0, st>>>(B, n, pattern, km, R, t, is_quantized, quantize_q, uvw)),
-                   (k_project<float><<<grid_for(B * n, 256), 256, 0, st>>>(B, n, pattern, km, R, t, is_quantized, quantize_q, uvw)));
+                   (k_project<float><<<grid_for(B * n, 256), 256, 0, st>>>(B, n, pattern, km, R, t, is_quantized, quantize_q, uvw))); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -851,7 +851,7 @@ static int synth_launch(int dtype, int64_t b0, int64_t B, int n, const void* pat
     const unsigned grid = grid_for(B * 32, 256);
     DISPATCH_DTYPE(dtype,
                    (k_synth<double><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt, radius, fixed_idx, perturb)),
-                   (k_synth<float><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt, radius, fixed_idx, perturb)));
+                   (k_synth<float><<<grid, 256, 0, st>>>(b0, B, n, (const double*)pattern_f64, km, c, uv, gt, R_gt, t_gt, radius, fixed_idx, perturb))); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -899,7 +899,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
             a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
             PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT>, csmem)); \
-            k_report_chunk<TT><<<grid, 32, csmem, st>>>(a);                                                             \
+            k_report_chunk<TT><<<grid, 32, csmem, st>>>(a); count_kernel_launches(1);                                                             \
         }
         DISPATCH_DTYPE(dtype, LAUNCH_REPORT_CHUNK(double), LAUNCH_REPORT_CHUNK(float));
 #undef LAUNCH_REPORT_CHUNK
@@ -915,7 +915,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
             a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
             PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_thread<TT>, smem)); \
-            k_report_thread<TT><<<grid, 32, smem, st>>>(a);                                                             \
+            k_report_thread<TT><<<grid, 32, smem, st>>>(a); count_kernel_launches(1);                                                             \
         }
         DISPATCH_DTYPE(dtype, LAUNCH_REPORT_THREAD(double), LAUNCH_REPORT_THREAD(float));
 #undef LAUNCH_REPORT_THREAD
@@ -923,7 +923,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
         const unsigned grid = grid_for(B * 32, 256);
         DISPATCH_DTYPE(dtype,
                        (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)),
-                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)));
+                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx))); count_kernel_launches(1);
     }
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
@@ -972,11 +972,11 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
         const int per_block = (warps / nq) * 32;          // problems a block covers per sweep
         long long g = (B + per_block - 1) / per_block;
         if (g > dp.sm_count) g = dp.sm_count;
-        k_stats_lane<PASS><<<(unsigned)g, warps * 32, lane_smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
+        k_stats_lane<PASS><<<(unsigned)g, warps * 32, lane_smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max); count_kernel_launches(1);
     } else {
         const size_t smem = sizeof(double) * (size_t)kStatWarps * n_class * nq * 4;
         if (smem > 48 * 1024) PNP_CUDA_OK(set_dynamic_smem((const void*)k_stats<PASS>, smem));
-        k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max);
+        k_stats<PASS><<<stats_grid(B), kStatBlock, smem, st>>>(B, in, class_id, n_class, sums1, sums, sums_max); count_kernel_launches(1);
     }
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
@@ -1005,7 +1005,7 @@ int pnpb200_classify(int64_t B, const double* values, int64_t stride, double sca
     Bins bn;
     bn.n = n_bins;
     for (int i = 0; i < 32; ++i) bn.b[i] = (i < n_bins) ? bins[i] : 0.0;
-    k_classify<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, values, stride, scale, bn, class_id);
+    k_classify<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, values, stride, scale, bn, class_id); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -1014,7 +1014,7 @@ int pnpb200_selftest_math(int64_t n, const double* in, double* rcp, double* rsqr
 {
     if (n < 0 || !in || !rcp || !rsqrt || !sqrt_out) return PNPB200_EINVAL;
     if (n == 0) return PNPB200_OK;
-    k_selftest_math<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, in, rcp, rsqrt, sqrt_out);
+    k_selftest_math<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, in, rcp, rsqrt, sqrt_out); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }
@@ -1036,6 +1036,7 @@ int pnpb200_fma_peak(int dtype, int iters, double* flops_per_s)
         PNP_CUDA_OK(cudaEventRecord(e0, 0));
         if (dtype == PNPB200_DTYPE_F64) k_fma_peak<double><<<grid, block>>>(iters, 1.0, (double*)out);
         else                            k_fma_peak<float><<<grid, block>>>(iters, 1.0f, (float*)out);
+        count_kernel_launches(1);
         PNP_CUDA_OK(cudaEventRecord(e1, 0));
         PNP_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0.f;

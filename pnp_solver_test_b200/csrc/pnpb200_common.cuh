@@ -46,6 +46,7 @@ int get_device_props(DeviceProps* out);   // cached per device; defined in pnpb2
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy query, remembered per (device, kernel): both cost
 // tens of microseconds on the host, which is visible when a call is only a few hundred microseconds of kernels
+void count_kernel_launches(int n);   // kernels this library has launched (pnpb200_launch_count); defined in pnpb200_api.cu
 cudaError_t set_dynamic_smem(const void* kernel, size_t bytes);                                   // defined in pnpb200_api.cu
 cudaError_t blocks_per_sm(int* out, const void* kernel, int block_threads, size_t smem_bytes);   // defined in pnpb200_api.cu
 

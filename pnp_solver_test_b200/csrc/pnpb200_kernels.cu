@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG) k_iterate(const __g
 template <typename T, int METHOD, int BLOCK, int MAXREG>
 static void launch_iterate_as(const MomArgs<T>& m, cudaStream_t stream)
 {
-    k_iterate<T, METHOD, BLOCK, MAXREG><<<(unsigned)((m.B + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(m);
+    k_iterate<T, METHOD, BLOCK, MAXREG><<<(unsigned)((m.B + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(m); count_kernel_launches(1);
 }
 
 template <typename T, int METHOD>
@@ -796,17 +796,21 @@ static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, lo
         m.use_tma = sg.chunk;                                 // RowStream: points per chunk
         if (pass == 0) k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
         else           k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
+        count_kernel_launches(1);
     } else if (shape == 1) {                                  // whole-row tiles
         if (pass == 0) k_stream_thread<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
         else           k_stream_thread<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
+        count_kernel_launches(1);
     } else if (shape == 3) {                                  // one problem per warp, rows through a TMA ring
         const unsigned grid = (unsigned)persistent_grid((nb + kRingWarps - 1) / kRingWarps, dp.sm_count, per_sm);
         if (pass == 0) k_stream_warp_tma<T, METHOD, 0><<<grid, kRingWarps * 32, smem, stream>>>(m);
         else           k_stream_warp_tma<T, METHOD, 1><<<grid, kRingWarps * 32, smem, stream>>>(m);
+        count_kernel_launches(1);
     } else {                                                  // one problem per warp, coalesced loads
         const unsigned grid = (unsigned)persistent_grid((nb + 7) / 8, dp.sm_count, per_sm);
         if (pass == 0) k_stream_warp<T, METHOD, 0><<<grid, 256, smem, stream>>>(m);
         else           k_stream_warp<T, METHOD, 1><<<grid, 256, smem, stream>>>(m);
+        count_kernel_launches(1);
     }
     return PNPB200_OK;
 }
@@ -871,7 +875,7 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
         PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_stream_warp<T, METHOD, 0>, 256, smem));
     }
 
-    k_pattern_constants<T><<<1, 32, 0, stream>>>(m);
+    k_pattern_constants<T><<<1, 32, 0, stream>>>(m); count_kernel_launches(1);
     const int slot = a.profile ? g_prof.begin() : -1;
     g_prof.mark(slot, stream);
     launch_moment_pass<T, METHOD>(0, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
@@ -915,7 +919,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
         const long long grid = n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL;
         const int slot = a.profile ? g_prof.begin() : -1;
         g_prof.mark(slot, stream);
-        k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(at);
+        k_solve_thread<T, METHOD><<<(unsigned)grid, 32, thread_smem, stream>>>(at); count_kernel_launches(1);
         g_prof.mark(slot, stream);
     } else if (mapping == PNPB200_MAP_WARP) {
         if (warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
@@ -925,7 +929,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
         const long long grid = persistent_grid((a.B + kWarpsPerBlock - 1) / kWarpsPerBlock, dp.sm_count, per_sm);
         const int slot = a.profile ? g_prof.begin() : -1;
         g_prof.mark(slot, stream);
-        k_solve_warp<T, METHOD><<<(unsigned)grid, kWarpsPerBlock * 32, warp_smem, stream>>>(a);
+        k_solve_warp<T, METHOD><<<(unsigned)grid, kWarpsPerBlock * 32, warp_smem, stream>>>(a); count_kernel_launches(1);
         g_prof.mark(slot, stream);
     } else {
         return PNPB200_EINVAL;
