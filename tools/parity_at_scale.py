@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Developer tool (GPU box): CUDA vs oracle on a larger fresh sample than the test suite uses; prints the largest
+deviation on the well-posed subset per method (the 1e-9 contract of DESIGN.md section 4)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import torch
+from gpu_util import cuda_solve, oracle_stability
+from oracle import oracle as orc
+from pnp_solver_test_b200 import patterns as pt
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+K = pt.default_camera_matrix()
+for n in (15, 68):
+    pat = pt.get_golden_pattern() if n == 15 else pt.synthetic_pattern(n)
+    P = pt.pattern_array(pat)
+    for quant in (True, False):
+        w = orc.synth(0, B, P, K, orc.default_synth(seed=777 + n, is_quantized=quant))
+        for method in ("qeif", "lm", "linear_f2", "linear_f1", "eif2"):
+            ref, stable, it_stable = oracle_stability(method, w["uv"], P, K)
+            out = cuda_solve(method, w["uv"], P, K)
+            dR = np.abs(out["R"] - ref["R"]).reshape(B, -1).max(axis=1)
+            dt = np.abs(out["t"] - ref["t"]).max(axis=1) / np.abs(ref["t"][:, 2])
+            ok_it = it_stable & (np.abs(ref["res_norm"]) > 1e-10)
+            print("n=%-3d %-9s %-9s stable %.3f | max dR %.2e  max dt/t3 %.2e | iters equal %d / %d"
+                  % (n, "quantised" if quant else "exact", method, stable.mean(), dR[stable].max(), dt[stable].max(),
+                     (out["iters"][ok_it] == ref["iters"][ok_it]).sum(), ok_it.sum()), flush=True)
