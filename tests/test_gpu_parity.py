@@ -327,3 +327,44 @@ def test_host_buffer_pipeline_equals_device_call(method, subset):
         pipe.close()
         for k in outs:
             assert np.array_equal(outs[k].numpy().reshape(ref[k].shape), ref[k], equal_nan=True), (k, pinned)
+
+
+@pytest.mark.parametrize("method,n,mapping", [("qeif", 15, 1), ("qeif", 15, 32), ("lm", 68, 2), ("lm", 68, 1), ("linear_f2", 68, 2),
+                                             ("linear_f1", 15, 1), ("eif2", 15, 1), ("lm", 1024, 2), ("linear_f2", 1024, 2),
+                                             ("lm", 15, 32)])
+def test_no_access_outside_the_callers_buffers(method, n, mapping):
+    """Straight through the C ABI with guarded buffers: the pixel array sits between NaN walls (an
+    out-of-bounds read would poison a result) and every output between sentinel walls (an
+    out-of-bounds write would change them), for a ragged batch."""
+    import ctypes as C
+    from pnp_solver_test_b200 import _lib
+    pat = pt.get_golden_pattern() if n == 15 else pt.synthetic_pattern(n)
+    P, K = pt.pattern_array(pat), pt.default_camera_matrix()
+    B = 77 if n < 1024 else 19
+    w = orc.synth(11, B, P, K)
+    ref = cuda_solve(method, w["uv"], P, K, mapping=mapping)
+    wall = 4096                                                            # doubles on either side (multiple of 2: 16-byte alignment)
+    uv_buf = torch.full((wall + B * n * 2 + wall,), float("nan"), dtype=torch.float64, device="cuda")
+    uv_buf[wall:wall + B * n * 2] = dev(w["uv"]).reshape(-1)
+    patd = dev(P)
+    sizes = {"R": 9, "t": 3, "euler": 3, "res_norm": 1}
+    bufs = {k: torch.full((wall + B * s + wall,), -7.5, dtype=torch.float64, device="cuda") for k, s in sizes.items()}
+    ibufs = {k: torch.full((wall + B + wall,), -77, dtype=torch.int32, device="cuda") for k in ("iters", "best_pattern")}
+    prm = _lib.default_params(mapping=mapping)
+    Kh = (C.c_double * 9)(*np.asarray(K, np.float64).reshape(-1))
+    p = lambda t_, off, esz: C.c_void_p(t_.data_ptr() + off * esz)
+    rc = _lib.lib.pnpb200_solve_batch(C.c_int(_lib.METHODS[method]), C.c_int(0), C.c_int64(B), C.c_int(n), C.c_int(n),
+                                      p(uv_buf, wall, 8), C.c_void_p(patd.data_ptr()), C.c_int(1), None, Kh, C.byref(prm),
+                                      p(bufs["R"], wall, 8), p(bufs["t"], wall, 8), p(bufs["euler"], wall, 8), p(bufs["res_norm"], wall, 8),
+                                      C.cast(p(ibufs["iters"], wall, 4), C.POINTER(C.c_int32)),
+                                      C.cast(p(ibufs["best_pattern"], wall, 4), C.POINTER(C.c_int32)), None)
+    _lib.check(rc, "pnpb200_solve_batch")
+    torch.cuda.synchronize()
+    for k, s in sizes.items():
+        b = bufs[k].cpu().numpy()
+        assert (b[:wall] == -7.5).all() and (b[wall + B * s:] == -7.5).all(), k
+        assert np.array_equal(b[wall:wall + B * s].reshape(ref[k].shape), ref[k], equal_nan=True), k
+    for k in ibufs:
+        b = ibufs[k].cpu().numpy()
+        assert (b[:wall] == -77).all() and (b[wall + B:] == -77).all(), k
+        assert np.array_equal(b[wall:wall + B], ref[k]), k
