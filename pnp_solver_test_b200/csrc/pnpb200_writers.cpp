@@ -20,43 +20,51 @@
 
 namespace {
 
-// repr(float) of CPython (float_repr_style = 'short')
+// repr(float) of CPython (float_repr_style = 'short'), appended without temporaries
 void append_repr(std::string& out, double v)
 {
     if (std::isnan(v)) { out += "nan"; return; }
     if (std::isinf(v)) { out += (v < 0 ? "-inf" : "inf"); return; }
     char buf[40];
     auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);   // d[.ddd]e[+-]XX, shortest
-    *r.ptr = 0;
     const char* p = buf;
+    const char* end = r.ptr;
     if (*p == '-') { out += '-'; ++p; }
-    const char* e = std::strchr(p, 'e');
-    std::string digits;
+    const char* e = p;
+    while (*e != 'e') ++e;
+    char digits[24];
+    int nd = 0;
     for (const char* c = p; c < e; ++c)
-        if (*c != '.') digits += *c;
-    const int exp10 = std::atoi(e + 1);
+        if (*c != '.') digits[nd++] = *c;
+    int exp10 = 0;
+    for (const char* c = e + 2; c < end; ++c) exp10 = exp10 * 10 + (*c - '0');
+    if (e[1] == '-') exp10 = -exp10;
+    char o[48];
+    int n = 0;
     if (exp10 >= -4 && exp10 < 16) {                      // fixed notation
         if (exp10 < 0) {
-            out += "0.";
-            out.append((size_t)(-exp10 - 1), '0');
-            out += digits;
-        } else if ((int)digits.size() <= exp10 + 1) {
-            out += digits;
-            out.append((size_t)(exp10 + 1 - (int)digits.size()), '0');
-            out += ".0";
+            o[n++] = '0'; o[n++] = '.';
+            for (int k = 0; k < -exp10 - 1; ++k) o[n++] = '0';
+            for (int k = 0; k < nd; ++k) o[n++] = digits[k];
+        } else if (nd <= exp10 + 1) {
+            for (int k = 0; k < nd; ++k) o[n++] = digits[k];
+            for (int k = nd; k < exp10 + 1; ++k) o[n++] = '0';
+            o[n++] = '.'; o[n++] = '0';
         } else {
-            out.append(digits, 0, (size_t)exp10 + 1);
-            out += '.';
-            out.append(digits, (size_t)exp10 + 1, std::string::npos);
+            for (int k = 0; k <= exp10; ++k) o[n++] = digits[k];
+            o[n++] = '.';
+            for (int k = exp10 + 1; k < nd; ++k) o[n++] = digits[k];
         }
     } else {                                              // d.ddde+XX, at least two exponent digits
-        out += digits[0];
-        if (digits.size() > 1) { out += '.'; out.append(digits, 1, std::string::npos); }
-        out += (e[1] == '-') ? "e-" : "e+";
+        o[n++] = digits[0];
+        if (nd > 1) { o[n++] = '.'; for (int k = 1; k < nd; ++k) o[n++] = digits[k]; }
+        o[n++] = 'e'; o[n++] = (exp10 < 0) ? '-' : '+';
         const int ae = exp10 < 0 ? -exp10 : exp10;
-        if (ae < 10) out += '0';
-        out += std::to_string(ae);
+        if (ae >= 100) o[n++] = (char)('0' + ae / 100);
+        o[n++] = (char)('0' + (ae / 10) % 10);
+        o[n++] = (char)('0' + ae % 10);
     }
+    out.append(o, (size_t)n);
 }
 
 // csv QUOTE_MINIMAL: quote when the field holds the delimiter, the quote char or a line break
@@ -123,15 +131,17 @@ int pnpb200_write_result_csv(const char* path, int append, int64_t B, int64_t id
     const int64_t kChunk = 4096;                          // rows per formatting task
     const int64_t n_chunks = (B + kChunk - 1) / kChunk;
     int rc = PNPB200_OK;
+    std::vector<std::string> text((size_t)n_threads);     // one buffer per slot, reused by every batch
+    for (auto& t : text) t.reserve((size_t)kChunk * 800);
     for (int64_t c0 = 0; c0 < n_chunks && rc == PNPB200_OK; c0 += n_threads) {
         const int batch = (int)((n_chunks - c0 < n_threads) ? (n_chunks - c0) : n_threads);
-        std::vector<std::string> text((size_t)batch);
         std::vector<std::thread> pool;
         for (int w = 0; w < batch; ++w) {
             pool.emplace_back([&, w]() {
                 std::string& out = text[(size_t)w];
-                out.reserve((size_t)kChunk * 640);
+                out.clear();
                 std::string tmp;
+                tmp.reserve(160);
                 const int64_t lo = (c0 + w) * kChunk, hi = (lo + kChunk < B) ? (lo + kChunk) : B;
                 for (int64_t b = lo; b < hi; ++b) {
                     const double* rp = report + b * PNPB200_REPORT_WIDTH;
