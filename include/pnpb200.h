@@ -294,6 +294,16 @@ int pnpb200_write_result_csv(const char* path, int append, int64_t B, int64_t id
 int pnpb200_format_repr(double v, char* out, int out_size);
 
 /*
+ * Combined class of the four ground-truth quantities (TEST_TOOLBOX.get_all_class_seperated_result,
+ * :975-1030): id = ((cd * nr + cr) * np + cp) * ny + cy, each c = np.digitize(gt[:, q] * scale[q], bins[q])
+ * in the order distance, roll, pitch, yaw; gt [B,4] device; bins / n_bins / scale host arrays of 4.
+ * pnpb200_stats_pass1/2 accept the resulting n_class = nd*nr*np*ny (up to 2^20): beyond 64 classes
+ * they add straight into the global table.
+ */
+int pnpb200_classify_drpy(int64_t B, const double* gt, const double* const* bins, const int32_t* n_bins,
+                          const double* scale, int32_t* class_id, void* stream);
+
+/*
  * FMA-pipe microbenchmark used by bench.py for the roofline denominator (MEASURED_PEAKS.json
  * has no FP64/FP32 FMA figure).  Runs `iters` dependent-chain-free FMAs per thread on a full
  * grid and returns the device-timed rate in FLOP/s (2 per FMA).  Synchronous.

@@ -308,7 +308,23 @@ def stress_report_case(PNPS, TTBX, tag, B, seed):
         quiet(TTBX.write_statistic_to_csv, csd, os.path.join(tmpd, "s.csv"), class_name="distance", statistic_data_name=name, is_horizontal=True)
         stat_txt[name] = open(os.path.join(tmpd, "s.txt"), newline="").read()
         stat_csv[name] = open(os.path.join(tmpd, "s.csv"), newline="").read()
+    # the (distance, roll, pitch, yaw) class-combination tables of data_analysis_and_saving (:1215-1346): the unmodified
+    # get_all_class_seperated_result / get_drpy_statistic / write_drpy_2_depth_statistic_CSV on the same result_list
+    dcd, d_l, r_l, p_l, y_l = quiet(TTBX.get_all_class_seperated_result, plain)
+    drpy_csv = {}
+    drpy_q = (("depth", "distance", "t3_est", "distance_GT", "cm", 100.0), ("roll", "roll", "roll_est", "roll_GT", "deg.", 1.0),
+              ("pitch", "pitch", "pitch_est", "pitch_GT", "deg.", 1.0), ("yaw", "yaw", "yaw_est", "yaw_GT", "deg.", 1.0),
+              ("LM_GT_error_average_normalize", "LM_GT_error_average_normalize", "LM_GT_error_average_normalize", None, "px_m", 1.0))
+    for name, cname, ek, gk, unit, sc in drpy_q:
+        sd = quiet(TTBX.get_drpy_statistic, dcd, class_name=cname, data_est_key=ek, data_GT_key=gk, unit=unit, unit_scale=sc)
+        todo = [("%s_mean(%s)" % (name, unit), "mean(%s)" % unit), ("%s_stddev(%s)" % (name, unit), "stddev(%s)" % unit)]
+        if name == "depth":
+            todo.append(("all_n_data", "n_data"))
+        for fkey, metric in todo:
+            quiet(TTBX.write_drpy_2_depth_statistic_CSV, sd, os.path.join(tmpd, "d.csv"), d_l, r_l, p_l, y_l, matric_label=metric)
+            drpy_csv[fkey] = open(os.path.join(tmpd, "d.csv"), newline="").read()
     np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, pattern=pt.pattern_array(pats[0]), uv=uv, gt=gt, R=R, t=t,
+                        **{"drpy_csv_" + k: np.array(v) for k, v in drpy_csv.items()},
                         euler=eul, res_norm=res, report=rep, flags=flags, max_idx=midx, depth_class=depth_class,
                         stats_all=stats_all, stats_by_depth=stats_depth, keys=np.array(keys), result_csv=np.array(result_csv),
                         **{"stat_txt_" + k: np.array(v) for k, v in stat_txt.items()},

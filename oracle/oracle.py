@@ -177,6 +177,26 @@ def report_batch(P, uv, K, R_est, t_est, euler_est, gt, bounds=(10.0, 10.0, 10.0
     return dict(report=rep, flags=flags, max_idx=midx)
 
 
+def drpy_stats(report, gt, bins):
+    """get_all_class_seperated_result + get_drpy_statistic (TEST_TOOLBOX.py:975-1066) on arrays:
+    stats_of per (distance, roll, pitch, yaw) class combination for depth, roll, pitch, yaw and
+    LM_GT_error_average_normalize.  bins: four ascending bin-edge lists (distance in cm).
+    Returns {name: [nd, nr, np, ny, 7]} with zeros where the combination holds no data."""
+    report, gt = np.asarray(report, np.float64), np.asarray(gt, np.float64)
+    cls = [np.digitize(gt[:, q] * (100.0 if q == 0 else 1.0), np.asarray(bins[q], np.float64)) for q in range(4)]
+    shape = tuple(len(b) + 1 for b in bins)
+    pairs = dict(depth=(report[:, 10], report[:, 11]), roll=(report[:, 12], gt[:, 1]), pitch=(report[:, 13], gt[:, 2]),
+                 yaw=(report[:, 14], gt[:, 3]), LM_GT_error_average_normalize=(report[:, 4], None))
+    out = {k: np.zeros(shape + (7,)) for k in pairs}
+    flat = np.ravel_multi_index(cls, shape)
+    for c in np.unique(flat):
+        m = flat == c
+        idx = np.unravel_index(c, shape)
+        for k, (e, g) in pairs.items():
+            out[k][idx] = stats_of(e[m], None if g is None else g[m])
+    return out
+
+
 def stats_of(est, gt=None):
     """TEST_TOOLBOX.get_statistic_of_result (TEST_TOOLBOX.py:892-937) on plain vectors.
 

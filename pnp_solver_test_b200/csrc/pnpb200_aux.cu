@@ -740,6 +740,89 @@ __global__ void __launch_bounds__(kStatLaneMaxWarps * 32) k_stats_lane(long long
     }
 }
 
+// The same two passes for MANY classes (the 12 x 5 x 5 x 5 distance / roll / pitch / yaw grid of
+// TEST_TOOLBOX.get_all_class_seperated_result, :975-1030): the tables do not fit shared memory, and with
+// ~1500 classes two problems rarely meet in one, so every problem adds straight into the global table
+// with FP64 reductions (RED.ADD.F64); the means of pass 2 are read from the pass-1 table.
+template <int PASS>
+__global__ void __launch_bounds__(256) k_stats_global(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
+                                                      const double* __restrict__ sums1, double* out, double* out_max)
+{
+    const int nq = in.nq, rows = n_class + 1;
+    double all[kStatMaxQ][4];
+#pragma unroll
+    for (int q = 0; q < kStatMaxQ; ++q) all[q][0] = all[q][1] = all[q][2] = all[q][3] = 0.0;
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        int c = cls ? cls[b] : 0;
+        if (c < 0 || c >= n_class) c = -1;
+#pragma unroll
+        for (int q = 0; q < kStatMaxQ; ++q) {
+            if (q < nq) {
+                const double ev = in.est[q][b * in.es[q]];
+                double ratio, err;
+                if (in.gt[q]) { const double g = in.gt[q][b * in.gs[q]]; ratio = ev / g; err = ev - g; }
+                else          { ratio = ev; err = ev; }
+                if (PASS == 1) {
+                    all[q][0] += 1.0; all[q][1] += ratio; all[q][2] += err;
+                    if (c >= 0) {
+                        double* o = out + ((size_t)q * rows + c) * 4;
+                        atomicAdd(o, 1.0); atomicAdd(o + 1, ratio); atomicAdd(o + 2, err);
+                    }
+                } else {
+                    const double na = sums1[((size_t)q * rows + n_class) * 4];
+                    const double da = err - (na > 0.0 ? sums1[((size_t)q * rows + n_class) * 4 + 2] / na : 0.0);
+                    all[q][0] += da * da; all[q][1] += fabs(err); all[q][2] += fabs(da); all[q][3] = fmax(all[q][3], fabs(da));
+                    if (c >= 0) {
+                        const double* s1 = sums1 + ((size_t)q * rows + c) * 4;
+                        const double d = err - (s1[0] > 0.0 ? s1[2] / s1[0] : 0.0);
+                        double* o = out + ((size_t)q * rows + c) * 4;
+                        atomicAdd(o, d * d); atomicAdd(o + 1, fabs(err)); atomicAdd(o + 2, fabs(d));
+                        atomic_max_double(out_max + (size_t)q * rows + c, fabs(d));
+                    }
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < kStatMaxQ; ++q) {                 // the "all" row
+        if (q < nq) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double a = all[q][k];
+                const bool is_max = (PASS == 2) && (k == 3);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double o = __shfl_xor_sync(0xffffffffu, a, off);
+                    a = is_max ? fmax(a, o) : a + o;
+                }
+                if (lane == 0) {
+                    if (is_max) atomic_max_double(out_max + (size_t)q * rows + n_class, a);
+                    else if (a != 0.0) atomicAdd(out + ((size_t)q * rows + n_class) * 4 + k, a);
+                }
+            }
+        }
+    }
+}
+
+// Combined class of the four ground-truth quantities, mixed radix in the order (distance, roll, pitch, yaw):
+// ((cd * nr + cr) * np + cp) * ny + cy with c = np.digitize(value * scale, bins) (classify_drpy :239-247)
+struct Bins4 { double b[4][32]; int n[4]; double scale[4]; };
+__global__ void k_classify_drpy(long long B, const double* __restrict__ gt, Bins4 bins, int32_t* cls)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int id = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double x = gt[b * 4 + q] * bins.scale[q];
+        int c = 0;
+        for (int i = 0; i < bins.n[q]; ++i) c += (bins.b[q][i] <= x) ? 1 : 0;
+        id = id * (bins.n[q] + 1) + c;
+    }
+    cls[b] = id;
+}
+
 struct Bins { double b[32]; int n; };
 __global__ void k_classify(long long B, const double* __restrict__ v, long long stride, double scale, Bins bins, int32_t* cls)
 {
@@ -945,7 +1028,7 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
                         const int64_t* gs, const int32_t* class_id, int n_class, const double* sums1, double* sums,
                         double* sums_max, cudaStream_t st)
 {
-    if (B < 0 || nq < 1 || nq > kStatMaxQ || !est || !es || !sums || n_class < 1 || n_class > kStatMaxClass) return PNPB200_EINVAL;
+    if (B < 0 || nq < 1 || nq > kStatMaxQ || !est || !es || !sums || n_class < 1 || n_class > (1 << 20)) return PNPB200_EINVAL;
     if (PASS == 2 && (!sums1 || !sums_max)) return PNPB200_EINVAL;
     StatIn in;
     in.nq = nq;
@@ -962,6 +1045,11 @@ static int stats_launch(int64_t B, int nq, const double* const* est, const int64
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc != PNPB200_OK) return rc;
+    if (n_class > kStatMaxClass) {                        // many classes: reductions straight into the global table
+        k_stats_global<PASS><<<stats_grid(B), 256, 0, st>>>(B, in, class_id, n_class, sums1, sums, sums_max); count_kernel_launches(1);
+        PNP_CUDA_OK(cudaGetLastError());
+        return PNPB200_OK;
+    }
     const size_t per_warp = sizeof(double) * (size_t)n_class * (PASS == 1 ? 3 : 4) * 32;
     int warps = (int)(((size_t)dp.max_smem_optin - 4096) / per_warp);
     if (warps > kStatLaneMaxWarps) warps = kStatLaneMaxWarps;
@@ -1006,6 +1094,26 @@ int pnpb200_classify(int64_t B, const double* values, int64_t stride, double sca
     bn.n = n_bins;
     for (int i = 0; i < 32; ++i) bn.b[i] = (i < n_bins) ? bins[i] : 0.0;
     k_classify<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, values, stride, scale, bn, class_id); count_kernel_launches(1);
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
+int pnpb200_classify_drpy(int64_t B, const double* gt, const double* const* bins, const int32_t* n_bins, const double* scale,
+                          int32_t* class_id, void* stream)
+{
+    if (B < 0 || !gt || !bins || !n_bins || !class_id) return PNPB200_EINVAL;
+    Bins4 b4;
+    long long total = 1;
+    for (int q = 0; q < 4; ++q) {
+        if (!bins[q] || n_bins[q] < 0 || n_bins[q] > 32) return PNPB200_EINVAL;
+        b4.n[q] = n_bins[q];
+        b4.scale[q] = scale ? scale[q] : 1.0;
+        for (int i = 0; i < 32; ++i) b4.b[q][i] = (i < n_bins[q]) ? bins[q][i] : 0.0;
+        total *= n_bins[q] + 1;
+    }
+    if (total > (1 << 20)) return PNPB200_EINVAL;
+    if (B == 0) return PNPB200_OK;
+    k_classify_drpy<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, gt, b4, class_id); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

@@ -226,6 +226,51 @@ def error_statistics(report, gt, group=None, distributed=True, lazy=False):
     return unpack(st)
 
 
+DRPY_ORDER = ("depth", "roll", "pitch", "yaw")
+DRPY_QUANTITIES = (("depth", "cm", 100.0), ("roll", "deg.", 1.0), ("pitch", "deg.", 1.0), ("yaw", "deg.", 1.0),
+                   ("LM_GT_error_average_normalize", "px_m", 1.0))
+
+
+def drpy_shape():
+    return tuple(len(CLASS_LABELS[q]) for q in DRPY_ORDER)
+
+
+def classify_drpy(gt):
+    """Combined (distance, roll, pitch, yaw) class of every problem, one kernel: the key of the nested
+    dict of TEST_TOOLBOX.get_all_class_seperated_result (:975-1030) as the mixed-radix integer
+    ((cd*nr + cr)*np + cp)*ny + cy.  gt [B,4] (depth m, roll, pitch, yaw deg.) contiguous CUDA FP64."""
+    assert gt.dtype == torch.float64 and gt.dim() == 2 and gt.shape[1] == 4 and gt.is_contiguous()
+    B = int(gt.shape[0])
+    cls = torch.empty((B,), dtype=torch.int32, device=gt.device)
+    PD = C.POINTER(C.c_double)
+    bins_np = [np.asarray(CLASS_BINS[q], np.float64) for q in DRPY_ORDER]
+    bins_a = (PD * 4)(*[b.ctypes.data_as(PD) for b in bins_np])
+    nb_a = (C.c_int32 * 4)(*[len(b) for b in bins_np])
+    scale_a = (C.c_double * 4)(100.0, 1.0, 1.0, 1.0)                  # the distance class is on centimetres
+    with torch.cuda.device(gt.device):
+        check(lib.pnpb200_classify_drpy(C.c_int64(B), C.cast(ptr(gt), PD), bins_a, nb_a, scale_a,
+                                        C.cast(ptr(cls), C.POINTER(C.c_int32)), _stream_ptr(gt.device)), "pnpb200_classify_drpy")
+    _lib.count_launch()
+    return cls
+
+
+def drpy_statistics(report, gt, group=None, distributed=True):
+    """get_drpy_statistic (TEST_TOOLBOX.py:1032-1066) for the five quantities data_analysis_and_saving
+    tabulates (:1218-1226), over ALL ranks' shards: statistics per (distance, roll, pitch, yaw) class
+    combination.  Returns {name: float64 CPU tensor [nd, nr, np, ny, 7]} (STAT_KEYS order; n = 0 where
+    the reference's nested dict has no entry)."""
+    cls = classify_drpy(gt)
+    shape = drpy_shape()
+    n_class = int(np.prod(shape))
+    st4 = statistics([report[:, 10], report[:, 12], report[:, 13], report[:, 14]], [report[:, 11], gt[:, 1], gt[:, 2], gt[:, 3]],
+                     cls, n_class, group, distributed, lazy=True)
+    st1 = statistics([report[:, 4]], [None], cls, n_class, group, distributed, lazy=True)
+    st4, st1 = st4.result(), st1.result()
+    out = {name: st4[q, :-1].reshape(shape + (7,)) for q, name in enumerate(DRPY_ORDER)}
+    out["LM_GT_error_average_normalize"] = st1[0, :-1].reshape(shape + (7,))
+    return out
+
+
 class _LazyDict(object):
     def __init__(self, pending, unpack):
         self._pending, self._unpack = pending, unpack
@@ -479,12 +524,84 @@ def write_statistic_csv(class_statistic_dict, path, is_horizontal=True):
     return rows
 
 
+def drpy_statistic_dict(stats5, unit, unit_scale):
+    """One quantity of drpy_statistics() as the nested {d: {r: {p: {y: statis_dict}}}} of
+    get_drpy_statistic (:1032-1066) plus the four sorted label lists get_all_class_seperated_result
+    returns (:1019-1028: labels that occur in the data, numeric order)."""
+    a = np.asarray(stats5, dtype=np.float64)
+    labs = [CLASS_LABELS[q] for q in DRPY_ORDER]
+    present = a[..., 0] > 0
+    lists = []
+    for ax in range(4):
+        occ = present.any(axis=tuple(i for i in range(4) if i != ax))
+        lists.append(sorted([labs[ax][i] for i in np.nonzero(occ)[0]], key=_class_order))
+    out = {}
+    for d, r, p, y in zip(*np.nonzero(present)):
+        v = [float(x) for x in a[d, r, p, y]]
+        out.setdefault(labs[0][d], {}).setdefault(labs[1][r], {}).setdefault(labs[2][p], {})[labs[3][y]] = {
+            "n_data": int(v[0]), "m_ratio": v[1], "mean(%s)" % unit: v[2] * unit_scale, "stddev(%s)" % unit: v[3] * unit_scale,
+            "max_dev(%s)" % unit: v[4] * unit_scale, "MAE_2_GT(%s)" % unit: v[5] * unit_scale, "MAE_2_mean(%s)" % unit: v[6] * unit_scale}
+    return (out,) + tuple(lists)
+
+
+def write_drpy_statistic_csv(drpy_dict, path, d_labels, r_labels, p_labels, y_labels, metric_label="mean(cm)"):
+    """TEST_TOOLBOX.write_drpy_2_depth_statistic_CSV (:822-887): one block of rows per roll label
+    ("r=.., y=.." per yaw label, then an empty row), one group of columns per distance label
+    ("d=..", then "d=.., p=.." per pitch label, then a "|count" separator); "-" where the class
+    combination holds no data.  Same csv.DictWriter, same text."""
+    import csv
+    fields, rows = [], []
+    def col(name):
+        if name not in fields:
+            fields.append(name)
+        return name
+    for r in r_labels:
+        for y in y_labels:
+            row, bars = {}, 0
+            for d in d_labels:
+                row[col("d=%s" % d)] = "r=%s, y=%s" % (r, y)
+                for p in p_labels:
+                    bars += 1
+                    leaf = drpy_dict.get(d, {}).get(r, {}).get(p, {}).get(y)
+                    row[col("d=%s, p=%s" % (d, p))] = leaf[metric_label] if leaf is not None and metric_label in leaf else "-"
+                row[col("|%d" % bars)] = ""
+            rows.append(row)
+        rows.append({})
+    with open(path, mode="w") as f:
+        w = csv.DictWriter(f, fieldnames=fields, extrasaction="ignore")
+        w.writeheader()
+        w.writerows(rows)
+    return rows
+
+
+def drpy_analysis_and_saving(report, gt, result_csv_dir_str, result_statistic_txt_file_prefix_str, data_file_str,
+                             group=None, distributed=True, stats=None):
+    """The second half of TEST_TOOLBOX.data_analysis_and_saving (:1215-1346): the eleven
+    "<prefix><stem>_drpy_to_<quantity>_<metric>.csv" tables (n_data once, mean and stddev for depth,
+    roll, pitch, yaw and LM_GT_error_average_normalize).  `stats` = a precomputed drpy_statistics()."""
+    st = stats if stats is not None else drpy_statistics(report, gt, group=group, distributed=distributed)
+    stem = result_csv_dir_str + result_statistic_txt_file_prefix_str + data_file_str[:-4] + "_drpy_to_"
+    dicts, paths = {}, []
+    for name, unit, scale in DRPY_QUANTITIES:
+        dicts[name] = drpy_statistic_dict(st[name], unit, scale)
+    dd, dl, rl, pl, yl = dicts["depth"]
+    paths.append(stem + "all_n_data.csv")
+    write_drpy_statistic_csv(dd, paths[-1], dl, rl, pl, yl, metric_label="n_data")
+    for metric in ("mean", "stddev"):
+        for name, unit, _ in DRPY_QUANTITIES:
+            label = "%s(%s)" % (metric, unit)
+            paths.append(stem + name + "_" + label + ".csv")
+            write_drpy_statistic_csv(dicts[name][0], paths[-1], dl, rl, pl, yl, metric_label=label)
+    return paths
+
+
 def data_analysis_and_saving(rep, res_norm, gt, key_names, result_csv_dir_str, result_csv_file_prefix_str,
                              result_statistic_txt_file_prefix_str, data_file_str, is_statistic_csv_horizontal=True,
-                             idx0=0, group=None, distributed=True):
-    """TEST_TOOLBOX.data_analysis_and_saving (:1070-1130) for a batch: the result CSV and, for depth,
-    roll, pitch and yaw per distance class, the statistic TXT and CSV files, with the reference's file
-    names.  rep = report_batch(...) dict.  Returns the four {label: statis_dict} dicts."""
+                             idx0=0, group=None, distributed=True, with_drpy=True):
+    """TEST_TOOLBOX.data_analysis_and_saving (:1070-1346) for a batch: the result CSV, for depth,
+    roll, pitch and yaw per distance class the statistic TXT and CSV files, and (with_drpy) the eleven
+    class-combination tables, with the reference's file names.  rep = report_batch(...) dict.
+    Returns the four {label: statis_dict} dicts."""
     stem = data_file_str[:-4]
     write_result_csv(result_csv_dir_str + result_csv_file_prefix_str + stem + ".csv", rep["report"], rep["flags"], rep["max_idx"],
                      res_norm, gt, key_names, idx0=idx0)
@@ -496,4 +613,7 @@ def data_analysis_and_saving(rep, res_norm, gt, key_names, result_csv_dir_str, r
         write_statistic_txt(d, base + ".txt", class_name="distance", statistic_data_name=name)
         write_statistic_csv(d, base + ".csv", is_horizontal=is_statistic_csv_horizontal)
         out[name] = d
+    if with_drpy:
+        drpy_analysis_and_saving(rep["report"], gt, result_csv_dir_str, result_statistic_txt_file_prefix_str, data_file_str,
+                                 group=group, distributed=distributed)
     return out

@@ -1,5 +1,7 @@
 """Parity of the kernels either side of the solve: Euler <-> R, projection, the synthetic
 workload generator, error reporting, classification and the two-pass statistics."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -147,6 +149,61 @@ def test_statistics_kernels_both_paths_match_numpy(n_class, nq):
             ref = np.array(orc.stats_of(est[sel, q], gt[sel, q]), dtype=np.float64)
             assert row[0] == ref[0]
             assert np.abs(row[1:] - ref[1:]).max() < 1e-11 * max(1.0, np.abs(ref[1:]).max()), (q, c, row, ref)
+
+
+def test_drpy_class_combination_statistics_match_reference(tmp_path):
+    """classify_drpy + the many-class statistics kernels (1500 classes, global FP64 reductions)
+    against the oracle on the reference's own result rows, the tables they produce against the
+    reference's files, and a large synthetic batch against the oracle (ragged B, dense classes)."""
+    from pnp_solver_test_b200 import workload as wl
+    import pnp_solver_test_b200 as pnp
+    g = load_golden("stress_report")
+    bins = [wl.CLASS_BINS[q] for q in wl.DRPY_ORDER]
+    rep, gt = dev(g["report"]), dev(g["gt"])
+    cls = wl.classify_drpy(gt).cpu().numpy()
+    ref_cls = np.ravel_multi_index([np.digitize(g["gt"][:, q] * (100.0 if q == 0 else 1.0), np.asarray(bins[q])) for q in range(4)],
+                                   wl.drpy_shape())
+    assert (cls == ref_cls).all()
+    st = wl.drpy_statistics(rep, gt, distributed=False)
+    ref = orc.drpy_stats(g["report"], g["gt"], bins)
+    for k in ref:
+        a = st[k].numpy()
+        assert (a[..., 0] == ref[k][..., 0]).all()
+        m = ref[k][..., 0] > 0
+        assert np.abs(a[m] - ref[k][m]).max() < 1e-11 * max(1.0, np.abs(ref[k][m]).max()), k
+    paths = wl.drpy_analysis_and_saving(rep, gt, str(tmp_path) + "/", "stat_", "data.txt", distributed=False)
+    import csv, io
+    for p in paths:
+        key = "drpy_csv_" + os.path.basename(p)[len("stat_data_drpy_to_"):-4]
+        mine = list(csv.reader(io.StringIO(open(p, newline="").read())))
+        want = list(csv.reader(io.StringIO(str(g[key]))))
+        assert len(mine) == len(want) and mine[0] == want[0], key
+        for ra, rb in zip(mine, want):
+            assert len(ra) == len(rb)
+            for x, y in zip(ra, rb):
+                try:
+                    fy = float(y)
+                except ValueError:
+                    assert x == y, (key, x, y)
+                    continue
+                assert abs(float(x) - fy) <= 1e-9 * max(1.0, abs(fy)), (key, x, y)
+    # dense classes: a synthetic batch, every combination hit many times
+    B = 200003
+    w = wl.synth_batch(0, B, g["pattern"], g["K"], cfg=pnp.default_synth(seed=5))
+    rng = np.random.default_rng(3)
+    gt_h = w["gt"].cpu().numpy()
+    rep_h = np.zeros((B, 16))
+    rep_h[:, 10] = gt_h[:, 0] * (1.0 + 0.01 * rng.normal(size=B)); rep_h[:, 11] = gt_h[:, 0]
+    for q in range(3):
+        rep_h[:, 12 + q] = gt_h[:, 1 + q] + rng.normal(size=B)
+    rep_h[:, 4] = np.abs(rng.normal(size=B))
+    st = wl.drpy_statistics(dev(rep_h), w["gt"], distributed=False)
+    ref = orc.drpy_stats(rep_h, gt_h, bins)
+    for k in ref:
+        a = st[k].numpy()
+        assert (a[..., 0] == ref[k][..., 0]).all() and a[..., 0].sum() == B
+        m = ref[k][..., 0] > 0
+        assert np.abs(a[m] - ref[k][m]).max() < 1e-10 * max(1.0, np.abs(ref[k][m]).max()), k
 
 
 def test_face_variation_workload_and_fragility_analysis_match_reference():

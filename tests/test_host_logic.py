@@ -156,6 +156,22 @@ def test_result_and_statistic_writers_match_reference(tmp_path):
         assert open(tmp_path / "s.csv", newline="").read() == str(g["stat_csv_" + name])
 
 
+def test_drpy_tables_match_reference(tmp_path):
+    """drpy_statistic_dict / write_drpy_statistic_csv against the eleven class-combination tables the
+    unmodified get_all_class_seperated_result / get_drpy_statistic / write_drpy_2_depth_statistic_CSV
+    wrote from the reference's result dicts (TEST_TOOLBOX.py:1215-1346)."""
+    from oracle import oracle as orc
+    from pnp_solver_test_b200 import workload as wl
+    g = load_golden("stress_report")
+    st = orc.drpy_stats(g["report"], g["gt"], [wl.CLASS_BINS[q] for q in wl.DRPY_ORDER])
+    assert st["depth"].shape == wl.drpy_shape() + (7,) and int(st["depth"][..., 0].sum()) == g["gt"].shape[0]
+    paths = wl.drpy_analysis_and_saving(None, None, str(tmp_path) + "/", "stat_", "data.txt", stats=st)
+    assert len(paths) == 11
+    for p in paths:
+        key = "drpy_csv_" + os.path.basename(p)[len("stat_data_drpy_to_"):-4]
+        assert open(p, newline="").read() == str(g[key]), key
+
+
 def _topk_worker(rank, world, port, q):
     import torch.distributed as dist
     from pnp_solver_test_b200 import workload as wl
