@@ -317,6 +317,12 @@ int pnpb200_fma_peak(int dtype, int iters, double* flops_per_s);
  */
 int pnpb200_selftest_math(int64_t n, const double* in, double* rcp, double* rsqrt, double* sqrt_out, void* stream);
 
+/*
+ * Test hook: the branch-free sine / cosine of bounded angles (radians, |x| < 1e4) that the report
+ * kernels build the ground-truth rotation with (csrc/pnpb200_math.cuh, sincos_bounded).
+ */
+int pnpb200_selftest_sincos(int64_t n, const double* in, double* sin_out, double* cos_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,33 @@ struct KernelKey {
 };
 }  // namespace
 
+int make_row_tensor_map(CUtensorMap* out, const void* uv, int elem_bytes, long long B, int n_total, int chunk_points)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn encode = []() -> EncodeFn {
+        if (getenv("PNPB200_NO_TENSOR_MAP")) return nullptr;                  // tuning / A-B comparisons only
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+        return (EncodeFn)fn;
+    }();
+    const unsigned long long row_bytes = (unsigned long long)n_total * 2ull * (unsigned long long)elem_bytes;
+    if (!encode || B < 1 || B > 0x7fffffffLL || chunk_points < 1 || chunk_points * 2 > 256 || (row_bytes & 15ull) ||
+        ((unsigned long long)chunk_points * 2ull * elem_bytes & 15ull) || ((uintptr_t)uv & 15u))
+        return 0;
+    const cuuint64_t dims[2] = { (cuuint64_t)n_total * 2u, (cuuint64_t)B };
+    const cuuint64_t strides[1] = { (cuuint64_t)row_bytes };
+    const cuuint32_t box[2] = { (cuuint32_t)chunk_points * 2u, 32u };
+    const cuuint32_t estr[2] = { 1u, 1u };
+    const CUresult r = encode(out, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                              const_cast<void*>(uv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
 cudaError_t set_dynamic_smem(const void* kernel, size_t bytes)
 {
     static std::mutex mu;

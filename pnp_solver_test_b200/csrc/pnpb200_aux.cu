@@ -250,7 +250,7 @@ __global__ void k_report(long long B, int n, const void* pattern, const void* uv
     const double roll_e = ld<T>(euler, b * 3), yaw_e = ld<T>(euler, b * 3 + 1), pitch_e = ld<T>(euler, b * 3 + 2);
     const double dist = gt[b * 4], roll_g = gt[b * 4 + 1], pitch_g = gt[b * 4 + 2], yaw_g = gt[b * 4 + 3];
     const double t3 = te[2];
-    R_from_euler(roll_g, yaw_g, pitch_g, true, Rg);       // random_stress_test.py:365
+    R_from_euler_deg_bounded(roll_g, yaw_g, pitch_g, Rg); // random_stress_test.py:365
 #pragma unroll
     for (int k = 0; k < 3; ++k) tg[k] = (te[k] / t3) * dist;   // :367-368
     double s0 = 0, s1 = 0, s2 = 0, m0 = 0, m1 = 0, m2 = 0;
@@ -298,6 +298,8 @@ struct ReportArgs {
     int n, row_pitch, use_tma;
     double K[9], bounds[4];
     double* report; int32_t* flags; int32_t* max_idx;
+    int use_tmap;
+    alignas(64) CUtensorMap tmap;   // uv as a 2-D tensor (RowStream), valid when use_tmap
 };
 
 PNP_DEV void fold_camera(const double* K, const double (&R)[9], const double (&t)[3], double (&M)[9], double (&m)[3])
@@ -337,6 +339,19 @@ PNP_DEV void landmark_errors(const double (&pe)[2], bool be, const double (&pg)[
 }
 
 template <typename T>
+PNP_DEV void load_report_pose(const ReportArgs<T>& a, long long b, double (&Re)[9], double (&te)[3], double (&eu)[3], double (&g4)[4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g4[k] = __ldg(a.gt + b * 4 + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) te[k] = (double)__ldg(a.t + b * 3 + k);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Re[k] = (double)__ldg(a.R + b * 9 + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) eu[k] = (double)__ldg(a.euler + b * 3 + k);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ ReportArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
         const double roll_e = (double)a.euler[b * 3], yaw_e = (double)a.euler[b * 3 + 1], pitch_e = (double)a.euler[b * 3 + 2];
         const double dist = a.gt[b * 4], roll_g = a.gt[b * 4 + 1], pitch_g = a.gt[b * 4 + 2], yaw_g = a.gt[b * 4 + 3];
         const double t3 = te[2];
-        R_from_euler(roll_g, yaw_g, pitch_g, true, Rg);   // random_stress_test.py:365
+        R_from_euler_deg_bounded(roll_g, yaw_g, pitch_g, Rg);   // random_stress_test.py:365
 #pragma unroll
         for (int k = 0; k < 3; ++k) tg[k] = (te[k] / t3) * dist;   // :367-368
         double Me[9], me[3], Mg[9], mg[3];
@@ -419,28 +434,29 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
     T* sP = sBuf + (size_t)2 * kTileProblems * a.row_pitch;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sP + (size_t)a.n * 3) - smem_raw)) + 7) & ~(size_t)7));
     const int lane = threadIdx.x;
-    RowStream<T> rs;
-    rs.init(sBuf, bars, a.uv, a.B, a.n, a.use_tma /* chunk */, a.row_pitch, lane);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     long long tile = blockIdx.x;
+    // the per-problem pose loads go out FIRST: their latency then overlaps the barrier set-up, the first
+    // bulk copies and the pattern staging instead of following them
+    long long b = tile * kTileProblems + lane;
+    bool ok = b < a.B;
+    if (!ok) b = a.B - 1;
+    double Re[9], te[3], eu[3], g4[4];
+    load_report_pose(a, b, Re, te, eu, g4);
+    RowStream<T> rs;
+    rs.init(sBuf, bars, a.uv, a.B, a.n, a.use_tma /* chunk */, a.row_pitch, lane, a.use_tmap ? &a.tmap : nullptr);
     if (tile < n_tiles) rs.begin_tile(tile, lane);
     for (int e = lane; e < a.n * 3; e += 32) sP[e] = a.pattern[e];
     __syncwarp();
     while (tile < n_tiles) {
-        long long b = tile * kTileProblems + lane;
-        const bool ok = b < a.B;
-        if (!ok) b = a.B - 1;
-        double Re[9], te[3], Rg[9], tg[3];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Re[k] = (double)a.R[b * 9 + k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) te[k] = (double)a.t[b * 3 + k];
-        const double roll_e = (double)a.euler[b * 3], yaw_e = (double)a.euler[b * 3 + 1], pitch_e = (double)a.euler[b * 3 + 2];
-        const double dist = a.gt[b * 4], roll_g = a.gt[b * 4 + 1], pitch_g = a.gt[b * 4 + 2], yaw_g = a.gt[b * 4 + 3];
+        double Rg[9], tg[3];
+        const double roll_e = eu[0], yaw_e = eu[1], pitch_e = eu[2];
+        const double dist = g4[0], roll_g = g4[1], pitch_g = g4[2], yaw_g = g4[3];
         const double t3 = te[2];
-        R_from_euler(roll_g, yaw_g, pitch_g, true, Rg);   // random_stress_test.py:365
+        R_from_euler_deg_bounded(roll_g, yaw_g, pitch_g, Rg);   // random_stress_test.py:365
+        const double s3 = t_rcp<double>(t3) * dist;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) tg[k] = (te[k] / t3) * dist;   // :367-368
+        for (int k = 0; k < 3; ++k) tg[k] = te[k] * s3;   // (t / t3) * distance_GT, :367-368
         double Me[9], me[3], Mg[9], mg[3];
         fold_camera(a.K, Re, te, Me, me);
         fold_camera(a.K, Rg, tg, Mg, mg);
@@ -484,6 +500,10 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
         if (tile < n_tiles) {
             fence_proxy_async();
             rs.begin_tile(tile, lane);
+            b = tile * kTileProblems + lane;
+            ok = b < a.B;
+            if (!ok) b = a.B - 1;
+            load_report_pose(a, b, Re, te, eu, g4);
         }
     }
 }
@@ -863,6 +883,13 @@ __global__ void k_selftest_math(long long n_signed, const double* __restrict__ i
     sq[i] = (i & 1) ? sqrt_nonneg(a) : t_sqrt_fast<double>(a, y);   // both square roots in use (report / LM constraint rows)
 }
 
+__global__ void k_selftest_sincos(long long n, const double* __restrict__ in, double* s, double* c)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sincos_bounded(in[i], s[i], c[i]);
+}
+
 }  // namespace pnpb200
 
 using namespace pnpb200;
@@ -981,6 +1008,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
             a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
+            a.use_tmap = (sg.pitch == sg.chunk * 2) ? make_row_tensor_map(&a.tmap, uv, (int)sizeof(TT), B, n, sg.chunk) : 0; \
             PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT>, csmem)); \
             k_report_chunk<TT><<<grid, 32, csmem, st>>>(a); count_kernel_launches(1);                                                             \
         }
@@ -996,7 +1024,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = g.row_pitch; a.use_tma = g.use_tma; \
             for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
-            a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
+            a.report = report; a.flags = flags; a.max_idx = max_idx; a.use_tmap = 0;                                    \
             PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_thread<TT>, smem)); \
             k_report_thread<TT><<<grid, 32, smem, st>>>(a); count_kernel_launches(1);                                                             \
         }
@@ -1123,6 +1151,15 @@ int pnpb200_selftest_math(int64_t n, const double* in, double* rcp, double* rsqr
     if (n < 0 || !in || !rcp || !rsqrt || !sqrt_out) return PNPB200_EINVAL;
     if (n == 0) return PNPB200_OK;
     k_selftest_math<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, in, rcp, rsqrt, sqrt_out); count_kernel_launches(1);
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
+int pnpb200_selftest_sincos(int64_t n, const double* in, double* sin_out, double* cos_out, void* stream)
+{
+    if (n < 0 || !in || !sin_out || !cos_out) return PNPB200_EINVAL;
+    if (n == 0) return PNPB200_OK;
+    k_selftest_sincos<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, in, sin_out, cos_out); count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

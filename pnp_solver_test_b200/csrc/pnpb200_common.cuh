@@ -1,5 +1,6 @@
 // pnpb200_common.cuh -- error plumbing and host helpers shared by the translation units.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through the runtime, no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -47,6 +48,9 @@ int get_device_props(DeviceProps* out);   // cached per device; defined in pnpb2
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy query, remembered per (device, kernel): both cost
 // tens of microseconds on the host, which is visible when a call is only a few hundred microseconds of kernels
 void count_kernel_launches(int n);   // kernels this library has launched (pnpb200_launch_count); defined in pnpb200_api.cu
+// 2-D tensor map over the pixel rows uv[B][n_total][2]: box = (chunk_points x 32 problems); returns 0 when
+// the driver entry point is missing or the shape does not qualify (callers keep the per-row copies).  pnpb200_api.cu
+int make_row_tensor_map(CUtensorMap* out, const void* uv, int elem_bytes, long long B, int n_total, int chunk_points);
 cudaError_t set_dynamic_smem(const void* kernel, size_t bytes);                                   // defined in pnpb200_api.cu
 cudaError_t blocks_per_sm(int* out, const void* kernel, int block_threads, size_t smem_bytes);   // defined in pnpb200_api.cu
 

@@ -251,6 +251,8 @@ struct MomArgs {
     T* mom; T* tail; T* patc;
     T* R; T* t; T* euler; T* res;
     int32_t* iters; int32_t* best;
+    int use_tmap;
+    alignas(64) CUtensorMap tmap;   // uv of this launch as a 2-D tensor (RowStream), valid when use_tmap
 };
 
 template <typename T>
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sP + (size_t)a.n * 3) - smem_raw)) + 7) & ~(size_t)7));
     const int lane = threadIdx.x;
     RowStream<T> rs;
-    rs.init(sBuf, bars, a.uv, a.B, a.n_total, a.use_tma /* chunk */, a.row_pitch, lane);
+    rs.init(sBuf, bars, a.uv, a.B, a.n_total, a.use_tma /* chunk */, a.row_pitch, lane, a.use_tmap ? &a.tmap : nullptr);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     long long tile = blockIdx.x;
     if (tile < n_tiles) rs.begin_tile(tile, lane);
@@ -794,6 +796,7 @@ static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, lo
     if (shape == 0) {                                         // chunked row streaming
         m.row_pitch = sg.pitch;
         m.use_tma = sg.chunk;                                 // RowStream: points per chunk
+        m.use_tmap = (sg.pitch == sg.chunk * 2) ? make_row_tensor_map(&m.tmap, m.uv, (int)sizeof(T), nb, m.n_total, sg.chunk) : 0;
         if (pass == 0) k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
         else           k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
         count_kernel_launches(1);
@@ -848,6 +851,7 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     m.prm = a.prm;
     m.mom = ws; m.tail = ws + (size_t)PNP_NMOM * a.B; m.patc = m.tail + (size_t)PNP_NTAIL * a.B;
     m.R = a.R; m.t = a.t; m.euler = a.euler; m.res = a.res; m.iters = a.iters; m.best = a.best;
+    m.use_tmap = 0;
 
     // kernel shape of the two streaming passes
     const StreamGeom sg = stream_geometry<T>(a.n_total);

@@ -321,4 +321,40 @@ PNP_DEV void R_from_euler(double roll, double yaw, double pitch, bool is_degree,
     R[6] = e6; R[7] = e7; R[8] = e8;
 }
 
+// sin and cos of a bounded angle (|x| < ~1e4 rad) without the library's large-argument slow path: the
+// same scheme as sincos() -- k = rint(x 2/pi), two-term Cody-Waite reduction with FMAs, the fdlibm
+// kernel polynomials on [-pi/4, pi/4], quadrant by selects -- but in ONE basic block, so that the three
+// angles of a rotation interleave instead of running as three serial ~60-instruction chains.  ~1 ulp.
+PNP_DEV void sincos_bounded(double x, double& s, double& c)
+{
+    const int k = __double2int_rn(x * 0.63661977236758134308);
+    const double q = (double)k;
+    double r = fma(-q, 1.57079632679489655800e+00, x);
+    r = fma(-q, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    ps = fma(ps, z, 2.75573137070700676789e-06);   pc = fma(pc, z, -2.75573143513906633035e-07);
+    ps = fma(ps, z, -1.98412698298579493134e-04);  pc = fma(pc, z, 2.48015872894767294178e-05);
+    ps = fma(ps, z, 8.33333333332248946124e-03);   pc = fma(pc, z, -1.38888888888741095749e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);  pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double sr = fma(r * z, ps, r);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+    s = (k & 2) ? -s0 : s0;
+    c = ((k + 1) & 2) ? -c0 : c0;
+}
+
+// R_from_euler for angles in degrees that are bounded (ground-truth poses): branch-free
+PNP_DEV void R_from_euler_deg_bounded(double roll, double yaw, double pitch, double (&R)[9])
+{
+    const double k = 3.14159265358979323846 / 180.0;
+    double s1, c1, s2, c2, s3, c3;
+    sincos_bounded(roll * k, s1, c1); sincos_bounded(-yaw * k, s2, c2); sincos_bounded(pitch * k, s3, c3);
+    const double e3 = s3 * s2, e5 = s3 * c2;
+    R[0] = c1 * c2 + s1 * e3; R[1] = s1 * c3; R[2] = c1 * -s2 + s1 * e5;
+    R[3] = -s1 * c2 + c1 * e3; R[4] = c1 * c3; R[5] = -s1 * -s2 + c1 * e5;
+    R[6] = c3 * s2; R[7] = -s3; R[8] = c3 * c2;
+}
+
 }  // namespace pnpb200

@@ -58,6 +58,14 @@ PNP_DEV void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// one TMA tensor copy of a (box_x x box_y) tile at element coordinates (x, y) of a 2-D tensor map (SASS: UTMALDG)
+PNP_DEV void tensor_copy_2d_g2s(void* dst_smem, const void* tmap, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
 PNP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
@@ -167,9 +175,12 @@ inline RowGeom row_geometry(int n_total)
 // ------------------------------------------------------------------------------------------
 // Row stream: the same 32 problems per warp, but for kernels that read every pixel ONCE
 // (moments, residual, error report).  Rows are streamed in chunks of `chunk` points through two
-// small shared-memory buffers (lane l bulk-copies its own row chunk; one mbarrier per buffer),
-// so a warp holds ~17 KB instead of a whole 35 KB tile and twice as many warps fit per SM, and
-// the copy of chunk c+1 overlaps the arithmetic on chunk c.
+// small shared-memory buffers (one mbarrier per buffer), so a warp holds ~17 KB instead of a whole
+// 35 KB tile and twice as many warps fit per SM, and the copy of chunk c+1 overlaps the arithmetic
+// on chunk c.  A chunk of all 32 rows is ONE TMA tensor copy (2-D tensor map over uv[B][2 n], box =
+// chunk x 32 rows, issued by lane 0; rows and columns past the end are zero-filled and counted) when
+// the buffer rows are dense (pitch = chunk, the normal case); otherwise lane l bulk-copies its own row
+// chunk, which the compiler serialises into 32 UBLKCP issues with a broadcast each.
 // ------------------------------------------------------------------------------------------
 struct StreamGeom { int chunk, pitch, use_stream; size_t buf_bytes; };
 constexpr int kStreamChunkUnits = 17;                     // 272-byte chunks
@@ -213,12 +224,15 @@ struct RowStream {
     long long B, b0;
     int n_total, chunk, pitch, n_chunks, valid;
     uint32_t phase;     // bit s = parity to wait for on buffer s
+    const void* tmap;   // tensor map of uv (kernel parameter space), or nullptr
 
     PNP_DEV T* buf(int s) const { return buf0 + (size_t)s * kTileProblems * pitch; }
 
-    PNP_DEV void init(T* smem, uint64_t* bars, const T* uv_, long long B_, int n_total_, int chunk_, int pitch_, int lane)
+    PNP_DEV void init(T* smem, uint64_t* bars, const T* uv_, long long B_, int n_total_, int chunk_, int pitch_, int lane,
+                      const void* tmap_ = nullptr)
     {
         buf0 = smem;
+        tmap = (pitch_ == chunk_ * 2) ? tmap_ : nullptr;
         bar = bars; uv = uv_; B = B_; n_total = n_total_; chunk = chunk_; pitch = pitch_;
         n_chunks = (n_total + chunk - 1) / chunk;
         phase = 0;
@@ -229,6 +243,13 @@ struct RowStream {
     PNP_DEV void issue(int c, int lane)
     {
         const int s = c & 1;
+        if (tmap) {
+            if (lane == 0) {
+                mbar_expect_tx(bar + s, (uint32_t)kTileProblems * (uint32_t)pitch * (uint32_t)sizeof(T));   // the full box
+                tensor_copy_2d_g2s(buf(s), tmap, c * chunk * 2, (int)b0, bar + s);
+            }
+            return;
+        }
         const uint32_t bytes = (uint32_t)count(c) * 2u * (uint32_t)sizeof(T);
         if (lane == 0) mbar_expect_tx(bar + s, bytes * (uint32_t)valid);
         __syncwarp();

@@ -302,6 +302,22 @@ def test_fast_reciprocals():
     assert np.abs(sq.astype(np.longdouble) / np.sqrt(al) - 1).max() <= 1.6 * ulp     # even: t_sqrt_fast, odd: sqrt_nonneg
 
 
+def test_bounded_sincos():
+    """sincos_bounded (the report kernels' ground-truth rotation) against NumPy: a few ulp of 1."""
+    import ctypes as C
+    from pnp_solver_test_b200 import _lib
+    rng = np.random.default_rng(6)
+    a = np.concatenate([rng.uniform(-7, 7, 200000), rng.uniform(-1000, 1000, 100000), rng.uniform(-1e-3, 1e-3, 1000),
+                        np.deg2rad(np.arange(-720.0, 721.0, 15.0)), np.array([0.0, np.pi / 2, -np.pi, np.pi / 4])])
+    x = dev(a)
+    s, c = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib.pnpb200_selftest_sincos(C.c_int64(a.size), C.c_void_p(x.data_ptr()), C.c_void_p(s.data_ptr()),
+                                                C.c_void_p(c.data_ptr()), None), "pnpb200_selftest_sincos")
+    torch.cuda.synchronize()
+    assert np.abs(s.cpu().numpy() - np.sin(a)).max() < 4.5e-16 and np.abs(c.cpu().numpy() - np.cos(a)).max() < 4.5e-16
+    assert float(s[-4]) == 0.0 and float(c[-4]) == 1.0
+
+
 @pytest.mark.parametrize("method,subset", [("lm", False), ("qeif", True), ("eif2", False)])
 def test_host_buffer_pipeline_equals_device_call(method, subset):
     """pnpb200_solve_batch_host (the end-to-end entry point: chunked H2D / solve / D2H on three
