@@ -318,8 +318,8 @@ PNP_DEV void project_folded(const double (&M)[9], const double (&m)[3], double x
     const double r0 = fma(M[0], x, fma(M[1], y, fma(M[2], z, m[0])));
     const double r1 = fma(M[3], x, fma(M[4], y, fma(M[5], z, m[1])));
     const double r2 = fma(M[6], x, fma(M[7], y, fma(M[8], z, m[2])));
-    const double inv = t_rcp<double>(fabs(r2));           // :4548 divides by |z|; branch-free, <= 0.5003 ulp
-    o[0] = r0 * inv; o[1] = r1 * inv;
+    const double inv = t_rcp<double>(r2);                 // :4548 divides by |z|; branch-free, <= 0.5003 ulp; the
+    o[0] = r0 * fabs(inv); o[1] = r1 * fabs(inv);         // absolute value rides on the multiplies as an operand modifier
     behind = __double2hiint(r2) < 0;
 }
 

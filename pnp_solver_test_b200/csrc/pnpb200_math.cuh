@@ -71,14 +71,16 @@ template <> PNP_DEV float t_sqrt_fast<float>(float a, float rs)
     const float s = a * rs;
     return fmaf(fmaf(-s, s, a), 0.5f * rs, s);
 }
-// branch-free sqrt for a >= 0 including exact zeros (distances): the seed sees a + 1e-300 (= a for every
-// a that matters, and 1e-300 for a = 0, where 0 * finite = 0 comes out).  s0 = a y0 carries the seed's
-// 2^-20 error e' = 1 - a y0^2; one third-order step s0 (1 + e'/2 + 3 e'^2 / 8) leaves ~e'^3: six FP64
-// instructions and the MUFU, ~1 ulp.
+// branch-free sqrt for a >= 0 including exact zeros (distances).  The seed of a = 0 is +inf; an integer min
+// on its high word turns it into the largest finite power of two (every other seed is far below it), so
+// that s0 = 0 * y is 0 instead of NaN -- one ALU instruction instead of an FP64 one.  s0 = a y0 carries
+// the seed's 2^-20 error e' = 1 - a y0^2; one third-order step s0 (1 + e'/2 + 3 e'^2 / 8) leaves ~e'^3:
+// five FP64 instructions and the MUFU, ~1 ulp.
 PNP_DEV double sqrt_nonneg(double a)
 {
     double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a + 1e-300));
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    y = __hiloint2double(min(__double2hiint(y), 0x7fe00000), __double2loint(y));
     const double s0 = a * y;
     const double e = fma(-s0, y, 1.0);
     const double p = fma(0.375, e, 0.5) * e;
