@@ -214,6 +214,18 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
                          double* report, int32_t* flags, int32_t* max_idx, void* stream);
 
 /*
+ * The same report into a strided array: value k of problem b goes to
+ * report[b * report_stride_problem + k * report_stride_column] (elements).  (16, 1) is the row layout
+ * of pnpb200_report_batch; (1, B) is the column layout the Python wrapper uses: the kernels' writes
+ * and the statistics' reads of one quantity are then contiguous.
+ */
+int pnpb200_report_batch_strided(int dtype, int64_t B, int n, const void* pattern, const void* uv,
+                                 const double* K, const void* R, const void* t, const void* euler_deg,
+                                 const double* gt, const double* bounds,
+                                 double* report, int64_t report_stride_problem, int64_t report_stride_column,
+                                 int32_t* flags, int32_t* max_idx, void* stream);
+
+/*
  * Error statistics, two passes so that shards can be combined with two small all-reduce phases
  * (TEST_TOOLBOX.get_statistic_of_result, TEST_TOOLBOX.py:892-937), for nq <= 4 quantities at once
  * (depth, roll, pitch, yaw in TEST_TOOLBOX.data_analysis_and_saving, :1070-1112), per class and,

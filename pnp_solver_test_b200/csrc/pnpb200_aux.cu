@@ -237,7 +237,7 @@ PNP_DEV void warp_sum_max(double& s, double& m, int& im)
 template <typename T>
 __global__ void k_report(long long B, int n, const void* pattern, const void* uv, KMat K, const void* R, const void* t,
                          const void* euler, const double* __restrict__ gt, Bounds bounds, double* report,
-                         int32_t* flags, int32_t* max_idx)
+                         long long rs_b, long long rs_k, int32_t* flags, int32_t* max_idx)
 {
     const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -271,12 +271,13 @@ __global__ void k_report(long long B, int n, const void* pattern, const void* uv
     }
     warp_sum_max(s0, m0, i0); warp_sum_max(s1, m1, i1); warp_sum_max(s2, m2, i2);
     if (lane == 0) {
-        double* rp = report + b * PNPB200_REPORT_WIDTH;
-        rp[0] = t3 - dist; rp[1] = roll_e - roll_g; rp[2] = pitch_e - pitch_g; rp[3] = yaw_e - yaw_g;
-        rp[4] = (s0 / n) * dist; rp[5] = m0 * dist;            // :452-453
-        rp[6] = (s1 / n) * dist; rp[7] = m1 * dist;
-        rp[8] = (s2 / n) * dist; rp[9] = m2 * dist;
-        rp[10] = t3; rp[11] = dist; rp[12] = roll_e; rp[13] = pitch_e; rp[14] = yaw_e; rp[15] = 0.0;
+        double* rp = report + b * rs_b;
+        const long long sk = rs_k;
+        rp[0] = t3 - dist; rp[sk] = roll_e - roll_g; rp[2 * sk] = pitch_e - pitch_g; rp[3 * sk] = yaw_e - yaw_g;
+        rp[4 * sk] = (s0 / n) * dist; rp[5 * sk] = m0 * dist;  // :452-453
+        rp[6 * sk] = (s1 / n) * dist; rp[7 * sk] = m1 * dist;
+        rp[8 * sk] = (s2 / n) * dist; rp[9 * sk] = m2 * dist;
+        rp[10 * sk] = t3; rp[11 * sk] = dist; rp[12 * sk] = roll_e; rp[13 * sk] = pitch_e; rp[14 * sk] = yaw_e; rp[15 * sk] = 0.0;
         if (flags) {                                           // check_if_the_sample_passed (:55-62), depth in cm
             flags[b * 4] = fabs(t3 * 100.0 - dist * 100.0) < bounds.b[0];
             flags[b * 4 + 1] = fabs(roll_e - roll_g) < bounds.b[1];
@@ -298,6 +299,7 @@ struct ReportArgs {
     int n, row_pitch, use_tma;
     double K[9], bounds[4];
     double* report; int32_t* flags; int32_t* max_idx;
+    long long rs_b, rs_k;           // element strides of report between problems / between columns
     int use_tmap;
     alignas(64) CUtensorMap tmap;   // uv as a 2-D tensor (RowStream), valid when use_tmap
 };
@@ -402,12 +404,13 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
             s2 += e2; if (e2 > m2) { m2 = e2; i2 = i; }
         }
         if (ok) {
-            double* rp = a.report + b * PNPB200_REPORT_WIDTH;
-            rp[0] = t3 - dist; rp[1] = roll_e - roll_g; rp[2] = pitch_e - pitch_g; rp[3] = yaw_e - yaw_g;
-            rp[4] = (s0 / a.n) * dist; rp[5] = m0 * dist;
-            rp[6] = (s1 / a.n) * dist; rp[7] = m1 * dist;
-            rp[8] = (s2 / a.n) * dist; rp[9] = m2 * dist;
-            rp[10] = t3; rp[11] = dist; rp[12] = roll_e; rp[13] = pitch_e; rp[14] = yaw_e; rp[15] = 0.0;
+            double* rp = a.report + b * a.rs_b;
+            const long long sk = a.rs_k;
+            rp[0] = t3 - dist; rp[sk] = roll_e - roll_g; rp[2 * sk] = pitch_e - pitch_g; rp[3 * sk] = yaw_e - yaw_g;
+            rp[4 * sk] = (s0 / a.n) * dist; rp[5 * sk] = m0 * dist;
+            rp[6 * sk] = (s1 / a.n) * dist; rp[7 * sk] = m1 * dist;
+            rp[8 * sk] = (s2 / a.n) * dist; rp[9 * sk] = m2 * dist;
+            rp[10 * sk] = t3; rp[11 * sk] = dist; rp[12 * sk] = roll_e; rp[13 * sk] = pitch_e; rp[14 * sk] = yaw_e; rp[15 * sk] = 0.0;
             if (a.flags) {
                 a.flags[b * 4] = fabs(t3 * 100.0 - dist * 100.0) < a.bounds[0];
                 a.flags[b * 4 + 1] = fabs(roll_e - roll_g) < a.bounds[1];
@@ -482,12 +485,13 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
             rs.done(c, lane);
         }
         if (ok) {
-            double* rp = a.report + b * PNPB200_REPORT_WIDTH;
-            rp[0] = t3 - dist; rp[1] = roll_e - roll_g; rp[2] = pitch_e - pitch_g; rp[3] = yaw_e - yaw_g;
-            rp[4] = (s0 / a.n) * dist; rp[5] = m0 * dist;
-            rp[6] = (s1 / a.n) * dist; rp[7] = m1 * dist;
-            rp[8] = (s2 / a.n) * dist; rp[9] = m2 * dist;
-            rp[10] = t3; rp[11] = dist; rp[12] = roll_e; rp[13] = pitch_e; rp[14] = yaw_e; rp[15] = 0.0;
+            double* rp = a.report + b * a.rs_b;
+            const long long sk = a.rs_k;
+            rp[0] = t3 - dist; rp[sk] = roll_e - roll_g; rp[2 * sk] = pitch_e - pitch_g; rp[3 * sk] = yaw_e - yaw_g;
+            rp[4 * sk] = (s0 / a.n) * dist; rp[5 * sk] = m0 * dist;
+            rp[6 * sk] = (s1 / a.n) * dist; rp[7 * sk] = m1 * dist;
+            rp[8 * sk] = (s2 / a.n) * dist; rp[9 * sk] = m2 * dist;
+            rp[10 * sk] = t3; rp[11 * sk] = dist; rp[12 * sk] = roll_e; rp[13 * sk] = pitch_e; rp[14 * sk] = yaw_e; rp[15 * sk] = 0.0;
             if (a.flags) {
                 a.flags[b * 4] = fabs(t3 * 100.0 - dist * 100.0) < a.bounds[0];
                 a.flags[b * 4 + 1] = fabs(roll_e - roll_g) < a.bounds[1];
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, co
 // fit per SM (one block per SM): the first version had 4 warps per SM doing all four quantities and
 // sat on exposed load / shared-memory latency (issue slots 18 % busy, 82 us for 36 MB).
 constexpr int kStatLaneMaxWarps = 16;
-constexpr int kStatUnroll = 4;
+constexpr int kStatUnroll = 8;
 
 template <int PASS>
 __global__ void __launch_bounds__(kStatLaneMaxWarps * 32) k_stats_lane(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
@@ -984,7 +988,18 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
                          const void* R, const void* t, const void* euler_deg, const double* gt, const double* bounds,
                          double* report, int32_t* flags, int32_t* max_idx, void* stream)
 {
+    return pnpb200_report_batch_strided(dtype, B, n, pattern, uv, K, R, t, euler_deg, gt, bounds, report, PNPB200_REPORT_WIDTH, 1,
+                                        flags, max_idx, stream);
+}
+
+int pnpb200_report_batch_strided(int dtype, int64_t B, int n, const void* pattern, const void* uv, const double* K,
+                                 const void* R, const void* t, const void* euler_deg, const double* gt, const double* bounds,
+                                 double* report, int64_t report_stride_problem, int64_t report_stride_column,
+                                 int32_t* flags, int32_t* max_idx, void* stream)
+{
     if (B < 0 || n < 1 || !pattern || !uv || !K || !R || !t || !euler_deg || !gt || !report) return PNPB200_EINVAL;
+    if (report_stride_problem < 1 || report_stride_column < 1) return PNPB200_EINVAL;
+    const long long rs_b = report_stride_problem, rs_k = report_stride_column;
     if (((uintptr_t)uv & 15u) != 0) return PNPB200_EINVAL;   // rows are staged with 16-byte bulk copies
     if (B == 0) return PNPB200_OK;
     KMat km;
@@ -1007,7 +1022,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = sg.pitch; a.use_tma = sg.chunk;  \
             for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
-            a.report = report; a.flags = flags; a.max_idx = max_idx;                                                    \
+            a.report = report; a.flags = flags; a.max_idx = max_idx; a.rs_b = rs_b; a.rs_k = rs_k;                      \
             a.use_tmap = (sg.pitch == sg.chunk * 2) ? make_row_tensor_map(&a.tmap, uv, (int)sizeof(TT), B, n, sg.chunk) : 0; \
             PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT>, csmem)); \
             k_report_chunk<TT><<<grid, 32, csmem, st>>>(a); count_kernel_launches(1);                                                             \
@@ -1024,7 +1039,7 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
             a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = g.row_pitch; a.use_tma = g.use_tma; \
             for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
             for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
-            a.report = report; a.flags = flags; a.max_idx = max_idx; a.use_tmap = 0;                                    \
+            a.report = report; a.flags = flags; a.max_idx = max_idx; a.use_tmap = 0; a.rs_b = rs_b; a.rs_k = rs_k;                                    \
             PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_thread<TT>, smem)); \
             k_report_thread<TT><<<grid, 32, smem, st>>>(a); count_kernel_launches(1);                                                             \
         }
@@ -1033,8 +1048,8 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
     } else {
         const unsigned grid = grid_for(B * 32, 256);
         DISPATCH_DTYPE(dtype,
-                       (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx)),
-                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, flags, max_idx))); count_kernel_launches(1);
+                       (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, rs_b, rs_k, flags, max_idx)),
+                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, rs_b, rs_k, flags, max_idx))); count_kernel_launches(1);
     }
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;

@@ -64,26 +64,33 @@ def synth_batch(b0, B, pattern, K, cfg=None, dtype=torch.float64, device=None, w
     return out
 
 
-def report_batch(pattern, uv, K, R, t, euler, gt, bounds=(10.0, 10.0, 10.0, 10.0)):
-    """Per-problem error report (pnpb200_report_batch): dict(report [B,16] f64, flags [B,4] int32,
-    max_idx [B,3] int32).  Column meaning: include/pnpb200.h.  pattern [n,3], uv [B,n,2]: every
-    landmark of the pattern, as in compare_result_and_generate_result_dict (TEST_TOOLBOX.py:291)."""
+def report_batch(pattern, uv, K, R, t, euler, gt, bounds=(10.0, 10.0, 10.0, 10.0), layout="columns"):
+    """Per-problem error report (pnpb200_report_batch_strided): dict(report [B,16] f64, flags [B,4]
+    int32, max_idx [B,3] int32).  Column meaning: include/pnpb200.h.  pattern [n,3], uv [B,n,2]: every
+    landmark of the pattern, as in compare_result_and_generate_result_dict (TEST_TOOLBOX.py:291).
+    layout="columns" (default): report is the transposed view of a [16,B] array, so report[:, k] is
+    contiguous (what the statistics read); layout="rows": a contiguous [B,16] array."""
     dev = uv.device
     pattern = torch.as_tensor(pattern, device=dev).to(uv.dtype).contiguous()
     B, n = int(uv.shape[0]), int(uv.shape[1])
-    rep = torch.empty((B, _lib.REPORT_WIDTH), dtype=torch.float64, device=dev)
+    if layout == "columns":
+        rep = torch.empty((_lib.REPORT_WIDTH, B), dtype=torch.float64, device=dev).t()
+    else:
+        assert layout == "rows"
+        rep = torch.empty((B, _lib.REPORT_WIDTH), dtype=torch.float64, device=dev)
+    rs_b, rs_k = max(int(rep.stride(0)), 1), max(int(rep.stride(1)), 1)
     flags = torch.empty((B, 4), dtype=torch.int32, device=dev)
     midx = torch.empty((B, 3), dtype=torch.int32, device=dev)
     Kh, Kp = _k_host(K)
     bd = (C.c_double * 4)(*[float(b) for b in bounds])
     gt = gt.to(torch.float64).contiguous()
     with torch.cuda.device(dev):
-        check(lib.pnpb200_report_batch(C.c_int(_dtype_code(uv.dtype)), C.c_int64(B), C.c_int(n), ptr(pattern), ptr(uv.contiguous()),
-                                       Kp, ptr(R.contiguous()), ptr(t.contiguous()), ptr(euler.contiguous()),
-                                       C.cast(ptr(gt), C.POINTER(C.c_double)), bd,
-                                       C.cast(ptr(rep), C.POINTER(C.c_double)),
-                                       C.cast(ptr(flags), C.POINTER(C.c_int32)), C.cast(ptr(midx), C.POINTER(C.c_int32)),
-                                       _stream_ptr(dev)), "pnpb200_report_batch")
+        check(lib.pnpb200_report_batch_strided(C.c_int(_dtype_code(uv.dtype)), C.c_int64(B), C.c_int(n), ptr(pattern),
+                                               ptr(uv.contiguous()), Kp, ptr(R.contiguous()), ptr(t.contiguous()),
+                                               ptr(euler.contiguous()), C.cast(ptr(gt), C.POINTER(C.c_double)), bd,
+                                               C.cast(ptr(rep), C.POINTER(C.c_double)), C.c_int64(rs_b), C.c_int64(rs_k),
+                                               C.cast(ptr(flags), C.POINTER(C.c_int32)), C.cast(ptr(midx), C.POINTER(C.c_int32)),
+                                               _stream_ptr(dev)), "pnpb200_report_batch_strided")
     _lib.count_launch()
     return dict(report=rep, flags=flags, max_idx=midx)
 

@@ -82,6 +82,12 @@ def test_report_classification_and_statistics_match_reference():
     g = load_golden("stress_report")
     rep = wl.report_batch(g["pattern"], dev(g["uv"]), g["K"], dev(g["R"]), dev(g["t"]), dev(g["euler"]), dev(g["gt"]))
     assert np.abs(rep["report"].cpu().numpy() - g["report"]).max() < 1e-10
+    assert rep["report"][:, 3].is_contiguous() and rep["report"].shape == (g["uv"].shape[0], 16)     # column layout
+    rows = wl.report_batch(g["pattern"], dev(g["uv"]), g["K"], dev(g["R"]), dev(g["t"]), dev(g["euler"]), dev(g["gt"]), layout="rows")
+    assert rows["report"].is_contiguous() and torch.equal(rows["report"], rep["report"])
+    assert torch.equal(rows["flags"], rep["flags"]) and torch.equal(rows["max_idx"], rep["max_idx"])
+    one = wl.report_batch(g["pattern"], dev(g["uv"][:1]), g["K"], dev(g["R"][:1]), dev(g["t"][:1]), dev(g["euler"][:1]), dev(g["gt"][:1]))
+    assert torch.equal(one["report"], rep["report"][:1])
     assert np.array_equal(rep["flags"].cpu().numpy(), g["flags"])
     assert np.array_equal(rep["max_idx"].cpu().numpy(), g["max_idx"])
     cls = wl.classify(dev(g["gt"])[:, 0], wl.CLASS_BINS["depth"], scale=100.0)
