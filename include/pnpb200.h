@@ -151,6 +151,27 @@ typedef struct pnpb200_pipeline pnpb200_pipeline;
 int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_problems, int n_total,
                             int n_patterns, int n_streams);
 int pnpb200_pipeline_destroy(pnpb200_pipeline* p);
+
+/*
+ * Packed pixel transfer for pnpb200_solve_batch_host.  Detected landmarks are whole pixels
+ * (random_stress_test.py projects with is_quantized=True, PNP_SOLVER_LIB.py:4549-4552) that the
+ * reference carries as float64.  With n_threads > 0 a second host thread takes chunks from the far end
+ * of the batch, converts each to int16 with n_threads workers (pnpb200_pack_i16) and, if that was exact
+ * for every value of the chunk, ships the int16 copy (a quarter of the PCIe bytes) and widens it on the
+ * device -- the solver sees the same values; chunks that are not whole numbers travel as they are.
+ * The calling thread keeps sending chunks unchanged from the near end, so PCIe and the CPU work at the
+ * same time and share the batch by their speeds.  n_threads = 0 switches it off (the default).
+ * pnpb200_pipeline_last_packed: how many chunks of the last call travelled packed, of how many.
+ */
+int pnpb200_pipeline_set_packing(pnpb200_pipeline* p, int n_threads);
+int pnpb200_pipeline_last_packed(const pnpb200_pipeline* p, int64_t* packed_chunks, int64_t* chunks);
+
+/*
+ * Host helper of the packed transfer: dst[i] = (int16) src[i] for n_values FP64 / FP32 values (dtype),
+ * on n_threads threads.  Returns 1 if every value was a whole number in [-32768, 32767] (the packing is
+ * lossless; -0.0 counts as 0), 0 if not (dst is then not to be used), < 0 on a bad argument.
+ */
+int pnpb200_pack_i16(int dtype, const void* src, int64_t n_values, int16_t* dst, int n_threads);
 int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n,
                              const void* uv_host, const void* pattern_host,
                              const int32_t* point_index, const double* K,

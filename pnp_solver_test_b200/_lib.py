@@ -25,7 +25,7 @@ EXPORTS = [
     "pnpb200_device_info", "pnpb200_workspace_bytes", "pnpb200_solve_batch", "pnpb200_pipeline_create", "pnpb200_pipeline_destroy",
     "pnpb200_solve_batch_host", "pnpb200_R_from_euler", "pnpb200_euler_from_R", "pnpb200_project",
     "pnpb200_synth_batch", "pnpb200_report_batch", "pnpb200_report_batch_strided", "pnpb200_stats_pass1", "pnpb200_stats_pass2",
-    "pnpb200_fma_peak", "pnpb200_selftest_math", "pnpb200_selftest_sincos", "pnpb200_synth_face_variation", "pnpb200_topk_histogram",
+    "pnpb200_fma_peak", "pnpb200_selftest_math", "pnpb200_selftest_sincos", "pnpb200_pipeline_set_packing", "pnpb200_pipeline_last_packed", "pnpb200_pack_i16", "pnpb200_synth_face_variation", "pnpb200_topk_histogram",
     "pnpb200_fragility_accumulate", "pnpb200_write_result_csv", "pnpb200_format_repr", "pnpb200_classify", "pnpb200_classify_drpy", "pnpb200_profile_reset", "pnpb200_profile_read",
 ]
 

@@ -19,7 +19,7 @@ HEADERS = ["pnpb200_common.cuh", "pnpb200_math.cuh", "pnpb200_solvers.cuh", "pnp
            os.path.join("..", "..", "include", "pnpb200.h")]
 # (object name, source, extra defines)
 UNITS = [("api", "pnpb200_api.cu", []), ("aux", "pnpb200_aux.cu", []), ("analysis", "pnpb200_analysis.cu", []),
-         ("writers", "pnpb200_writers.cpp", [])]
+         ("writers", "pnpb200_writers.cpp", []), ("pack", "pnpb200_pack.cpp", [])]
 UNITS += [("kernels_%s_g%d" % ("f64" if f64 else "f32", g), "pnpb200_kernels.cu", ["-DPNP_F64=%d" % f64, "-DPNP_GROUP=%d" % g])
           for f64 in (1, 0) for g in (3, 1, 0, 2)]
 EXTRA = os.environ.get("PNPB200_NVCC_EXTRA", "").split()

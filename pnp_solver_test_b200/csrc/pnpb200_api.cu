@@ -5,6 +5,7 @@
 #include <map>
 #include <mutex>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 #include "pnpb200_common.cuh"
@@ -244,17 +245,62 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, co
 // ------------------------------------------------------------------------------------------
 // host-buffer entry point: chunked, multi-stream H2D -> solve -> D2H pipeline
 // ------------------------------------------------------------------------------------------
+// One slot = a stream with every device buffer a chunk needs.  Slots [0, n_streams) carry chunks as they
+// are; the pack slots behind them carry chunks whose pixels went over PCIe as int16 (pnpb200_pack.cpp).
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    void *d_uv = nullptr, *d_R = nullptr, *d_t = nullptr, *d_e = nullptr, *d_res = nullptr, *d_ws = nullptr;
+    int32_t *d_it = nullptr, *d_best = nullptr;
+    int16_t *h_pack = nullptr, *d_pack = nullptr;        // pinned staging / device copy of the packed pixels
+    cudaEvent_t pack_free = nullptr;                      // the H2D copy out of h_pack has finished
+    cudaEvent_t h2d_done = nullptr;                       // the slot's last pixel copy has finished (back-pressure)
+};
+
 struct pnpb200_pipeline {
-    int dtype, n_total, n_patterns, n_streams;
+    int dtype, n_total, n_patterns, n_streams, device;
+    int pack_threads;                                     // 0: packed transfer off
     int64_t chunk;
     size_t esz;
-    std::vector<cudaStream_t> streams;
-    std::vector<void*> d_uv, d_R, d_t, d_e, d_res;
-    std::vector<int32_t*> d_it, d_best;
-    std::vector<void*> d_ws;
+    std::vector<PipeSlot> slots;                          // n_streams plain slots, then the pack slots
     size_t ws_bytes;
     void* d_pattern;
+    int64_t last_packed, last_chunks;                     // chunks of the last call that travelled packed / all of them
 };
+
+constexpr int kPackSlots = 4;
+
+static int alloc_slot(pnpb200_pipeline* p, PipeSlot& sl, bool pack)
+{
+    const size_t c = (size_t)p->chunk, esz = p->esz;
+    PNP_CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    PNP_CUDA_OK(cudaMalloc(&sl.d_uv, esz * c * p->n_total * 2));
+    PNP_CUDA_OK(cudaMalloc(&sl.d_R, esz * c * 9));
+    PNP_CUDA_OK(cudaMalloc(&sl.d_t, esz * c * 3));
+    PNP_CUDA_OK(cudaMalloc(&sl.d_e, esz * c * 3));
+    PNP_CUDA_OK(cudaMalloc(&sl.d_res, esz * c));
+    PNP_CUDA_OK(cudaMalloc((void**)&sl.d_it, sizeof(int32_t) * c));
+    PNP_CUDA_OK(cudaMalloc((void**)&sl.d_best, sizeof(int32_t) * c));
+    PNP_CUDA_OK(cudaMalloc(&sl.d_ws, p->ws_bytes));
+    PNP_CUDA_OK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    if (pack) {
+        const size_t pb = sizeof(int16_t) * (c * p->n_total * 2 + 8);
+        PNP_CUDA_OK(cudaMallocHost((void**)&sl.h_pack, pb));
+        PNP_CUDA_OK(cudaMalloc((void**)&sl.d_pack, pb));
+        PNP_CUDA_OK(cudaEventCreateWithFlags(&sl.pack_free, cudaEventDisableTiming));
+    }
+    return PNPB200_OK;
+}
+
+static void free_slot(PipeSlot& sl)
+{
+    if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    cudaFree(sl.d_uv); cudaFree(sl.d_R); cudaFree(sl.d_t); cudaFree(sl.d_e); cudaFree(sl.d_res); cudaFree(sl.d_ws);
+    cudaFree(sl.d_it); cudaFree(sl.d_best); cudaFree(sl.d_pack);
+    if (sl.h_pack) cudaFreeHost(sl.h_pack);
+    if (sl.pack_free) cudaEventDestroy(sl.pack_free);
+    if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+    sl = PipeSlot();
+}
 
 int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_problems, int n_total, int n_patterns,
                             int n_streams)
@@ -267,43 +313,97 @@ int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_pro
     p->chunk = chunk_problems;
     p->esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
     p->d_pattern = nullptr;
+    p->pack_threads = 0; p->last_packed = 0; p->last_chunks = 0;
     p->ws_bytes = ((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)chunk_problems + PNP_PATC) * p->esz;
     *out = p;
+    PNP_CUDA_OK(cudaGetDevice(&p->device));
     PNP_CUDA_OK(cudaMalloc(&p->d_pattern, p->esz * (size_t)n_patterns * n_total * 3));
+    p->slots.resize((size_t)n_streams);
     for (int s = 0; s < n_streams; ++s) {
-        cudaStream_t st;
-        PNP_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        p->streams.push_back(st);
-        void *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr, *e = nullptr, *f = nullptr, *g = nullptr;
-        PNP_CUDA_OK(cudaMalloc(&a, p->esz * (size_t)chunk_problems * n_total * 2)); p->d_uv.push_back(a);
-        PNP_CUDA_OK(cudaMalloc(&b, p->esz * (size_t)chunk_problems * 9)); p->d_R.push_back(b);
-        PNP_CUDA_OK(cudaMalloc(&c, p->esz * (size_t)chunk_problems * 3)); p->d_t.push_back(c);
-        PNP_CUDA_OK(cudaMalloc(&d, p->esz * (size_t)chunk_problems * 3)); p->d_e.push_back(d);
-        PNP_CUDA_OK(cudaMalloc(&e, p->esz * (size_t)chunk_problems)); p->d_res.push_back(e);
-        PNP_CUDA_OK(cudaMalloc(&f, sizeof(int32_t) * (size_t)chunk_problems)); p->d_it.push_back((int32_t*)f);
-        PNP_CUDA_OK(cudaMalloc(&g, sizeof(int32_t) * (size_t)chunk_problems)); p->d_best.push_back((int32_t*)g);
-        void* w = nullptr;
-        PNP_CUDA_OK(cudaMalloc(&w, p->ws_bytes)); p->d_ws.push_back(w);
+        const int rc = alloc_slot(p, p->slots[(size_t)s], false);
+        if (rc != PNPB200_OK) return rc;
     }
+    return PNPB200_OK;
+}
+
+int pnpb200_pipeline_set_packing(pnpb200_pipeline* p, int n_threads)
+{
+    if (!p || n_threads < 0 || n_threads > 256) return PNPB200_EINVAL;
+    if (n_threads > 0 && p->slots.size() == (size_t)p->n_streams) {       // first use: the pack slots
+        p->slots.resize((size_t)p->n_streams + kPackSlots);
+        for (size_t s = (size_t)p->n_streams; s < p->slots.size(); ++s) {
+            const int rc = alloc_slot(p, p->slots[s], true);
+            if (rc != PNPB200_OK) return rc;
+        }
+    }
+    p->pack_threads = n_threads;
+    return PNPB200_OK;
+}
+
+int pnpb200_pipeline_last_packed(const pnpb200_pipeline* p, int64_t* packed_chunks, int64_t* chunks)
+{
+    if (!p) return PNPB200_EINVAL;
+    if (packed_chunks) *packed_chunks = p->last_packed;
+    if (chunks) *chunks = p->last_chunks;
     return PNPB200_OK;
 }
 
 int pnpb200_pipeline_destroy(pnpb200_pipeline* p)
 {
     if (!p) return PNPB200_EINVAL;
-    for (cudaStream_t st : p->streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-    for (void* q : p->d_uv) cudaFree(q);
-    for (void* q : p->d_R) cudaFree(q);
-    for (void* q : p->d_t) cudaFree(q);
-    for (void* q : p->d_e) cudaFree(q);
-    for (void* q : p->d_res) cudaFree(q);
-    for (int32_t* q : p->d_it) cudaFree(q);
-    for (int32_t* q : p->d_best) cudaFree(q);
-    for (void* q : p->d_ws) cudaFree(q);
+    for (PipeSlot& sl : p->slots) free_slot(sl);
     if (p->d_pattern) cudaFree(p->d_pattern);
     delete p;
     return PNPB200_OK;
 }
+
+namespace {
+struct HostCall {
+    pnpb200_pipeline* p;
+    int method, n;
+    int64_t B;
+    const void* uv_host;
+    const int32_t* point_index;
+    const double* K;
+    const pnpb200_params* params;
+    void *R, *t, *euler_deg, *res_norm;
+    int32_t *iters, *best_pattern;
+};
+
+// queue one chunk on a slot: pixels host -> device (packed if `packed`), solve, results device -> host
+int submit_chunk(const HostCall& c, PipeSlot& sl, int64_t done, int64_t nb, bool packed)
+{
+    pnpb200_pipeline* p = c.p;
+    const size_t esz = p->esz;
+    cudaStream_t st = sl.stream;
+    const size_t values = (size_t)nb * p->n_total * 2;
+    if (packed) {
+        PNP_CUDA_OK(cudaMemcpyAsync(sl.d_pack, sl.h_pack, sizeof(int16_t) * values, cudaMemcpyHostToDevice, st));
+        PNP_CUDA_OK(cudaEventRecord(sl.pack_free, st));
+        const int rc = widen_i16_launch(p->dtype, (long long)values, sl.d_pack, sl.d_uv, st);
+        if (rc != PNPB200_OK) return rc;
+    } else {
+        const char* src = (const char*)c.uv_host + esz * (size_t)done * p->n_total * 2;
+        PNP_CUDA_OK(cudaMemcpyAsync(sl.d_uv, src, esz * values, cudaMemcpyHostToDevice, st));
+        PNP_CUDA_OK(cudaEventRecord(sl.h2d_done, st));
+    }
+    pnpb200_params prm;
+    if (c.params) prm = *c.params; else fill_default_params(&prm);
+    if (!prm.workspace) { prm.workspace = sl.d_ws; prm.workspace_bytes = (int64_t)p->ws_bytes; }
+    const int rc = pnpb200_solve_batch(c.method, p->dtype, nb, p->n_total, c.n, sl.d_uv, p->d_pattern, p->n_patterns,
+                                       c.point_index, c.K, &prm, c.R ? sl.d_R : nullptr, c.t ? sl.d_t : nullptr,
+                                       c.euler_deg ? sl.d_e : nullptr, c.res_norm ? sl.d_res : nullptr,
+                                       c.iters ? sl.d_it : nullptr, c.best_pattern ? sl.d_best : nullptr, st);
+    if (rc != PNPB200_OK) return rc;
+    if (c.R) PNP_CUDA_OK(cudaMemcpyAsync((char*)c.R + esz * (size_t)done * 9, sl.d_R, esz * (size_t)nb * 9, cudaMemcpyDeviceToHost, st));
+    if (c.t) PNP_CUDA_OK(cudaMemcpyAsync((char*)c.t + esz * (size_t)done * 3, sl.d_t, esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
+    if (c.euler_deg) PNP_CUDA_OK(cudaMemcpyAsync((char*)c.euler_deg + esz * (size_t)done * 3, sl.d_e, esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
+    if (c.res_norm) PNP_CUDA_OK(cudaMemcpyAsync((char*)c.res_norm + esz * (size_t)done, sl.d_res, esz * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    if (c.iters) PNP_CUDA_OK(cudaMemcpyAsync(c.iters + done, sl.d_it, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    if (c.best_pattern) PNP_CUDA_OK(cudaMemcpyAsync(c.best_pattern + done, sl.d_best, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    return PNPB200_OK;
+}
+}  // namespace
 
 int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, const void* uv_host,
                              const void* pattern_host, const int32_t* point_index, const double* K,
@@ -313,35 +413,68 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
     if (!p || !uv_host || !pattern_host || !K || B < 0) return PNPB200_EINVAL;
     const size_t esz = p->esz;
     PNP_CUDA_OK(cudaMemcpyAsync(p->d_pattern, pattern_host, esz * (size_t)p->n_patterns * p->n_total * 3,
-                                cudaMemcpyHostToDevice, p->streams[0]));
-    PNP_CUDA_OK(cudaStreamSynchronize(p->streams[0]));
-    int64_t done = 0;
-    int s = 0;
-    while (done < B) {
-        const int64_t nb = (B - done < p->chunk) ? (B - done) : p->chunk;
-        cudaStream_t st = p->streams[s];
-        const char* src = (const char*)uv_host + esz * (size_t)done * p->n_total * 2;
-        PNP_CUDA_OK(cudaMemcpyAsync(p->d_uv[s], src, esz * (size_t)nb * p->n_total * 2, cudaMemcpyHostToDevice, st));
-        pnpb200_params prm;
-        if (params) prm = *params; else fill_default_params(&prm);
-        if (!prm.workspace) { prm.workspace = p->d_ws[s]; prm.workspace_bytes = (int64_t)p->ws_bytes; }
-        int rc = pnpb200_solve_batch(method, p->dtype, nb, p->n_total, n, p->d_uv[s], p->d_pattern, p->n_patterns,
-                                     point_index, K, &prm, R ? p->d_R[s] : nullptr, t ? p->d_t[s] : nullptr,
-                                     euler_deg ? p->d_e[s] : nullptr, res_norm ? p->d_res[s] : nullptr,
-                                     iters ? p->d_it[s] : nullptr, best_pattern ? p->d_best[s] : nullptr, st);
-        if (rc != PNPB200_OK) return rc;
-        if (R) PNP_CUDA_OK(cudaMemcpyAsync((char*)R + esz * (size_t)done * 9, p->d_R[s], esz * (size_t)nb * 9, cudaMemcpyDeviceToHost, st));
-        if (t) PNP_CUDA_OK(cudaMemcpyAsync((char*)t + esz * (size_t)done * 3, p->d_t[s], esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
-        if (euler_deg) PNP_CUDA_OK(cudaMemcpyAsync((char*)euler_deg + esz * (size_t)done * 3, p->d_e[s], esz * (size_t)nb * 3, cudaMemcpyDeviceToHost, st));
-        if (res_norm) PNP_CUDA_OK(cudaMemcpyAsync((char*)res_norm + esz * (size_t)done, p->d_res[s], esz * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (iters) PNP_CUDA_OK(cudaMemcpyAsync(iters + done, p->d_it[s], sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (best_pattern) PNP_CUDA_OK(cudaMemcpyAsync(best_pattern + done, p->d_best[s], sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        done += nb;
-        s = (s + 1) % p->n_streams;
-        // a stream's buffers are reused n_streams chunks later; stream order protects them
+                                cudaMemcpyHostToDevice, p->slots[0].stream));
+    PNP_CUDA_OK(cudaStreamSynchronize(p->slots[0].stream));
+    const HostCall call = { p, method, n, B, uv_host, point_index, K, params, R, t, euler_deg, res_norm, iters, best_pattern };
+    const int64_t n_chunks = (B + p->chunk - 1) / p->chunk;
+    p->last_chunks = n_chunks; p->last_packed = 0;
+    // Chunks are handed out from both ends of the batch: this thread sends chunks as they are from the front
+    // (PCIe-bound), a second thread packs chunks from the back with the pack threads (CPU-bound) and sends
+    // those as int16; whichever is faster takes more of them, and they meet somewhere in the middle.
+    std::mutex mu;
+    int64_t lo = 0, hi = n_chunks - 1;
+    auto claim = [&](bool from_back) -> int64_t {
+        std::lock_guard<std::mutex> lk(mu);
+        if (lo > hi) return -1;
+        return from_back ? hi-- : lo++;
+    };
+    std::atomic<int> rc_pack{PNPB200_OK};
+    std::atomic<long long> n_packed{0};
+    std::thread packer;
+    const bool packing = p->pack_threads > 0 && p->slots.size() > (size_t)p->n_streams && n_chunks >= 2;
+    if (packing) {
+        const int64_t first = claim(true);                 // the last chunk is the packing thread's whatever the timing
+        packer = std::thread([&, first]() {
+            if (cudaSetDevice(p->device) != cudaSuccess) { rc_pack = PNPB200_ECUDA; return; }
+            size_t s = (size_t)p->n_streams;
+            for (int64_t c = first; c >= 0; c = claim(true)) {
+                PipeSlot& sl = p->slots[s];
+                const int64_t done = c * p->chunk, nb = (B - done < p->chunk) ? (B - done) : p->chunk;
+                if (cudaEventSynchronize(sl.pack_free) != cudaSuccess) { rc_pack = PNPB200_ECUDA; break; }   // staging buffer free again
+                const char* src = (const char*)uv_host + esz * (size_t)done * p->n_total * 2;
+                const int exact = pnpb200_pack_i16(p->dtype, src, nb * p->n_total * 2, sl.h_pack, p->pack_threads);
+                if (exact < 0) { rc_pack = exact; break; }
+                const int rc = submit_chunk(call, sl, done, nb, exact == 1);
+                if (rc != PNPB200_OK) { rc_pack = rc; break; }
+                if (exact == 1) n_packed.fetch_add(1);
+                s = (s + 1 < p->slots.size()) ? s + 1 : (size_t)p->n_streams;
+            }
+        });
     }
-    for (cudaStream_t st : p->streams) PNP_CUDA_OK(cudaStreamSynchronize(st));
-    return PNPB200_OK;
+    int rc_main = PNPB200_OK;
+    int s = 0;
+    // back-pressure: take the next chunk only when the pixel copy `depth` chunks back has left the host.  Copies of
+    // all streams share the host-to-device engine in submission order, so with packing on only one plain copy is
+    // kept queued -- a packed copy then waits for one chunk at most, and the rest of the batch stays open to the
+    // packing thread; without packing a slot is simply reused when its turn comes.
+    const int depth = packing ? 1 : p->n_streams;
+    for (;;) {
+        const int wait_slot = (s + p->n_streams - (depth % p->n_streams)) % p->n_streams;    // the slot used `depth` chunks ago
+        if (cudaEventSynchronize(p->slots[(size_t)wait_slot].h2d_done) != cudaSuccess) { rc_main = PNPB200_ECUDA; break; }
+        const int64_t c = claim(false);
+        if (c < 0) break;
+        const int64_t done = c * p->chunk, nb = (B - done < p->chunk) ? (B - done) : p->chunk;
+        rc_main = submit_chunk(call, p->slots[(size_t)s], done, nb, false);
+        if (rc_main != PNPB200_OK) break;
+        s = (s + 1) % p->n_streams;
+        // a slot's buffers are reused n_streams chunks later; stream order protects them
+    }
+    if (rc_main != PNPB200_OK) { std::lock_guard<std::mutex> lk(mu); lo = hi + 1; }    // stop the packer
+    if (packer.joinable()) packer.join();
+    p->last_packed = n_packed.load();
+    for (PipeSlot& sl : p->slots) PNP_CUDA_OK(cudaStreamSynchronize(sl.stream));
+    if (rc_main != PNPB200_OK) return rc_main;
+    return rc_pack.load();
 }
 
 }  // extern "C"

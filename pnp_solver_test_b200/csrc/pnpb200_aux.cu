@@ -887,6 +887,32 @@ __global__ void k_selftest_math(long long n_signed, const double* __restrict__ i
     sq[i] = (i & 1) ? sqrt_nonneg(a) : t_sqrt_fast<double>(a, y);   // both square roots in use (report / LM constraint rows)
 }
 
+// packed pixel transfer (pnpb200_pack.cpp): int16 -> T, eight values per thread (one 16-byte load)
+template <typename T>
+__global__ void __launch_bounds__(256) k_widen_i16(long long n, const int16_t* __restrict__ in, T* __restrict__ out)
+{
+    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (g >= n) return;
+    if (g + 8 <= n) {
+        const int4 v = *reinterpret_cast<const int4*>(in + g);
+        const int w[4] = { v.x, v.y, v.z, v.w };
+        T o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[2 * k] = (T)(int16_t)(w[k] & 0xffff); o[2 * k + 1] = (T)(int16_t)(w[k] >> 16); }
+        if (sizeof(T) == 8) {
+            double2* d = reinterpret_cast<double2*>(out + g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[k] = make_double2((double)o[2 * k], (double)o[2 * k + 1]);
+        } else {
+            float4* d = reinterpret_cast<float4*>(out + g);
+            d[0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+            d[1] = make_float4((float)o[4], (float)o[5], (float)o[6], (float)o[7]);
+        }
+    } else {
+        for (long long i = g; i < n; ++i) out[i] = (T)in[i];
+    }
+}
+
 __global__ void k_selftest_sincos(long long n, const double* __restrict__ in, double* s, double* c)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -894,6 +920,19 @@ __global__ void k_selftest_sincos(long long n, const double* __restrict__ in, do
     sincos_bounded(in[i], s[i], c[i]);
 }
 
+}  // namespace pnpb200
+
+namespace pnpb200 {
+int widen_i16_launch(int dtype, long long n_values, const int16_t* in, void* out, cudaStream_t stream)
+{
+    if (n_values <= 0) return PNPB200_OK;
+    const unsigned grid = grid_for((n_values + 7) / 8, 256);
+    if (dtype == PNPB200_DTYPE_F64) k_widen_i16<double><<<grid, 256, 0, stream>>>(n_values, in, (double*)out);
+    else                            k_widen_i16<float><<<grid, 256, 0, stream>>>(n_values, in, (float*)out);
+    count_kernel_launches(1);
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
 }  // namespace pnpb200
 
 using namespace pnpb200;

@@ -51,6 +51,7 @@ void count_kernel_launches(int n);   // kernels this library has launched (pnpb2
 // 2-D tensor map over the pixel rows uv[B][n_total][2]: box = (chunk_points x 32 problems); returns 0 when
 // the driver entry point is missing or the shape does not qualify (callers keep the per-row copies).  pnpb200_api.cu
 int make_row_tensor_map(CUtensorMap* out, const void* uv, int elem_bytes, long long B, int n_total, int chunk_points);
+int widen_i16_launch(int dtype, long long n_values, const int16_t* in, void* out, cudaStream_t stream);   // pnpb200_aux.cu
 cudaError_t set_dynamic_smem(const void* kernel, size_t bytes);                                   // defined in pnpb200_api.cu
 cudaError_t blocks_per_sm(int* out, const void* kernel, int block_threads, size_t smem_bytes);   // defined in pnpb200_api.cu
 

@@ -105,7 +105,10 @@ class HostPipeline(object):
     """Chunked H2D -> solve -> D2H pipeline over host (ideally pinned) buffers:
     pnpb200_pipeline_* / pnpb200_solve_batch_host.  This is the end-to-end call."""
 
-    def __init__(self, dtype, chunk_problems, n_total, n_patterns=1, n_streams=3, device=None):
+    def __init__(self, dtype, chunk_problems, n_total, n_patterns=1, n_streams=3, device=None, pack_threads=0):
+        """pack_threads > 0: chunks whose pixels are whole numbers (quantised detections) may travel as
+        int16 -- a second host thread packs chunks from the far end of the batch with that many workers
+        while this one sends chunks unchanged from the near end (pnpb200_pipeline_set_packing)."""
         self.dt = _dtype_code(dtype)
         self.n_total, self.n_patterns = int(n_total), int(n_patterns)
         self.chunk = int(chunk_problems)
@@ -115,6 +118,18 @@ class HostPipeline(object):
             check(lib.pnpb200_pipeline_create(C.byref(self._h), C.c_int(self.dt), C.c_int64(int(chunk_problems)),
                                               C.c_int(self.n_total), C.c_int(self.n_patterns), C.c_int(int(n_streams))),
                   "pnpb200_pipeline_create")
+            if pack_threads:
+                self.set_packing(pack_threads)
+
+    def set_packing(self, n_threads):
+        with torch.cuda.device(self.device):
+            check(lib.pnpb200_pipeline_set_packing(self._h, C.c_int(int(n_threads))), "pnpb200_pipeline_set_packing")
+
+    def last_packed(self):
+        """(chunks of the last solve() that travelled as int16, chunks of that call)"""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(lib.pnpb200_pipeline_last_packed(self._h, C.byref(a), C.byref(b)), "pnpb200_pipeline_last_packed")
+        return int(a.value), int(b.value)
 
     def close(self):
         if self._h:

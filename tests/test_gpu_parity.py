@@ -345,6 +345,50 @@ def test_host_buffer_pipeline_equals_device_call(method, subset):
             assert np.array_equal(outs[k].numpy().reshape(ref[k].shape), ref[k], equal_nan=True), (k, pinned)
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_packed_pixel_transfer_is_lossless(dtype):
+    """pnpb200_pipeline_set_packing: chunks of whole-pixel landmarks travel as int16 and give results
+    bit-identical to the unpacked pipeline; chunks that are not whole numbers travel as they are (same
+    results again); a batch with one fractional pixel packs every chunk but that one."""
+    import pnp_solver_test_b200 as pnp
+    P, K = pt.pattern_array(pt.synthetic_pattern(68)), pt.default_camera_matrix()
+    B, chunk = 12 * 512 + 77, 512
+    w = orc.synth(3, B, P, K)                                            # quantised pixels (random_stress_test.py)
+    assert np.array_equal(w["uv"], np.round(w["uv"]))
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    pat_h = torch.from_numpy(P.astype(npdt))[None].contiguous()
+
+    def run(uv, pack):
+        outs = {"R": torch.empty((B, 3, 3), dtype=dtype), "t": torch.empty((B, 3), dtype=dtype),
+                "euler": torch.empty((B, 3), dtype=dtype), "res_norm": torch.empty((B,), dtype=dtype),
+                "iters": torch.empty((B,), dtype=torch.int32)}
+        pipe = pnp.HostPipeline(dtype, chunk_problems=chunk, n_total=68, n_patterns=1, n_streams=3, pack_threads=pack)
+        pipe.solve("lm", torch.from_numpy(uv.astype(npdt)).pin_memory(), pat_h, K, outs)
+        packed = pipe.last_packed()
+        pipe.close()
+        return {k: v.numpy().copy() for k, v in outs.items()}, packed
+
+    ref, packed0 = run(w["uv"], 0)
+    assert packed0 == (0, 13)
+    got, packed = run(w["uv"], 3)
+    assert packed[1] == 13 and 1 <= packed[0] <= 13
+    for k in ref:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    noisy = w["uv"] + 0.25
+    ref_n, _ = run(noisy, 0)
+    got_n, packed_n = run(noisy, 3)
+    assert packed_n[0] == 0
+    for k in ref:
+        assert np.array_equal(got_n[k], ref_n[k], equal_nan=True), k
+    one = w["uv"].copy()
+    one[B - 5, 7, 1] += 0.5                                             # the last chunk is claimed by the packing thread first
+    ref_1, _ = run(one, 0)
+    got_1, packed_1 = run(one, 3)
+    assert packed_1[0] <= 12
+    for k in ref:
+        assert np.array_equal(got_1[k], ref_1[k], equal_nan=True), k
+
+
 @pytest.mark.parametrize("method,n,mapping", [("qeif", 15, 1), ("qeif", 15, 32), ("lm", 68, 2), ("lm", 68, 1), ("linear_f2", 68, 2),
                                              ("linear_f1", 15, 1), ("eif2", 15, 1), ("lm", 1024, 2), ("linear_f2", 1024, 2),
                                              ("lm", 15, 32)])

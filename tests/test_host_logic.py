@@ -156,6 +156,37 @@ def test_result_and_statistic_writers_match_reference(tmp_path):
         assert open(tmp_path / "s.csv", newline="").read() == str(g["stat_csv_" + name])
 
 
+def test_pixel_packing_is_exact_or_refused():
+    """pnpb200_pack_i16 (host side of the packed PCIe transfer): int16 copy and 'exact' verdict for
+    FP64 / FP32, one and several threads, lengths that are not a multiple of the vector width."""
+    import ctypes as C
+    from pnp_solver_test_b200 import _lib
+    rng = np.random.default_rng(9)
+
+    def pack(a, threads):
+        dst = np.full(a.shape, 12345, np.int16)
+        rc = _lib.lib.pnpb200_pack_i16(C.c_int(0 if a.dtype == np.float64 else 1), a.ctypes.data_as(C.c_void_p), C.c_int64(a.size),
+                                       dst.ctypes.data_as(C.POINTER(C.c_int16)), C.c_int(threads))
+        return rc, dst
+
+    for dt in (np.float64, np.float32):
+        for n in (0, 1, 15, 16, 17, 1000, 200003):
+            a = rng.integers(-32768, 32768, n).astype(dt)
+            if n > 2:
+                a[0], a[1], a[2] = -32768, 32767, -0.0
+            for th in (1, 4):
+                rc, dst = pack(a, th)
+                assert rc == 1 and np.array_equal(dst, a.astype(np.int16)), (dt, n, th)
+        base = rng.integers(-2000, 2000, 200003).astype(dt)
+        for pos in (0, 7, 16, 100000, 200002):
+            for bad in (0.5, 32768.0, -32769.0, 1e30, np.nan, np.inf, -np.inf, 1e-3):
+                a = base.copy()
+                a[pos] = bad
+                assert pack(a, 3)[0] == 0, (dt, pos, bad)
+        assert pack(base, 3)[0] == 1
+    assert _lib.lib.pnpb200_pack_i16(C.c_int(7), None, C.c_int64(4), None, C.c_int(1)) < 0
+
+
 def test_drpy_tables_match_reference(tmp_path):
     """drpy_statistic_dict / write_drpy_statistic_csv against the eleven class-combination tables the
     unmodified get_all_class_seperated_result / get_drpy_statistic / write_drpy_2_depth_statistic_CSV
