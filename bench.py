@@ -314,6 +314,32 @@ def run_ours(args):
             pack_threads = 0
         pipe = pnp.HostPipeline(torch.float64, chunk_problems=args.chunk, n_total=n, n_patterns=1, n_streams=3, device=dev,
                                 pack_threads=pack_threads)
+        def timed_e2e(k):
+            barrier()
+            t_ = time.perf_counter()
+            for _ in range(k):
+                pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)   # blocks until results are on the host
+            barrier()
+            tt_ = torch.tensor([time.perf_counter() - t_], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            return float(tt_[0]) / k
+
+        pack_choice = "off"
+        if pack_threads:
+            # warm-up decides: packing trades PCIe bytes for host memory traffic, which loses when all the ranks of a box
+            # share a host memory system that is already the limit (8 GPUs); every rank takes the same decision
+            timed_e2e(1)
+            t_on = timed_e2e(2)
+            pipe.set_packing(0)
+            timed_e2e(1)
+            t_off = timed_e2e(2)
+            pack_choice = "on (warm-up: %.1f ms packed, %.1f ms plain)" % (1e3 * t_on, 1e3 * t_off)
+            if t_on < t_off:
+                pipe.set_packing(pack_threads)
+            else:
+                pack_choice = "off (warm-up: %.1f ms packed, %.1f ms plain)" % (1e3 * t_on, 1e3 * t_off)
+                pack_threads = 0
         for _ in range(2):
             pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)
         barrier()
@@ -350,6 +376,7 @@ def run_ours(args):
                                      "pixels packed to int16 on the host inside the timed region, lossless" % (pack_threads, packed_chunks, n_chunks)
                          if pack_threads else ""),
                "host_pixel_bytes_per_step": host_bytes, "pack_threads": pack_threads, "packed_chunks": [packed_chunks, n_chunks],
+               "packing": pack_choice,
                "bound": {"what": "PCIe host->device copy of the FP64 pixels as they are (what the pipeline does without packing)",
                          "h2d_copy_alone_ms": copy_ms, "h2d_copy_alone_gbs": h2d_fp64 / (copy_ms * 1e-3) / 1e9,
                          "e2e_over_copy": e2e_ms / copy_ms}}
