@@ -505,7 +505,6 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            A[sidx<10>(U1 + a, U2 + b)] = T(0);
             A[sidx<10>(U1 + a, U3 + b)] = t_fma(m0p[a], mx[b], -m.gMx(s3(a, b)));
             A[sidx<10>(U2 + a, U3 + b)] = t_fma(m0p[a], my[b], -m.gMy(s3(a, b)));
         }
@@ -534,21 +533,43 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
         const T w1[3] = { u1[0] * ig, u1[1] * ig, u1[2] * ig };          // u / gamma
         const T w2[3] = { u2[0] * ig, u2[1] * ig, u2[2] * ig };
         const T w3[3] = { u3[0] * ig, u3[1] * ig, u3[2] * ig };
-        const T pw1[3] = { kq * w1[0], kq * w1[1], kq * w1[2] }, pw2[3] = { kq * w2[0], kq * w2[1], kq * w2[2] };
-        const T nw2[3] = { -kq * w2[0], -kq * w2[1], -kq * w2[2] }, nw3[3] = { -kq * w3[0], -kq * w3[1], -kq * w3[2] };
-        add_outer2<T, U1, U3>(A, g, w3, w1, T(0) - u13);          // u1.u3 = 0
-        add_outer2<T, U2, U3>(A, g, w3, w2, T(0) - u23);          // u2.u3 = 0
-        add_outer2<T, U1, U2>(A, g, w2, w1, T(0) - u12);          // u1.u2 = 0
-        add_outer2<T, U1, U3>(A, g, pw1, nw3, T(0) - (u11 - u33)); // reference rows use u, not 2u (:3808)
-        add_outer2<T, U2, U3>(A, g, pw2, nw3, T(0) - (u22 - u33));
-        add_outer2<T, U1, U2>(A, g, pw1, nw2, T(0) - (u11 - u22));
+        // The nine rows r_k (each with two non-zero blocks at most) enter as sum_k r_k^T r_k and sum_k r_k^T e_k.
+        // Collected per block instead of row by row:
+        //   diagonal block i:     w1 w1^T + w2 w2^T + w3 w3^T + (2 kq^2 + h_i^2 - 1) w_i w_i^T
+        //   block (i, j), i < j:  w_j w_i^T - kq^2 w_i w_j^T
+        //   right-hand side i:    sum_{j != i} w_j e_ij + w_i (kq (+-e_4..6) + h_i (1 - |u_i|))
+        // with h_i = 1 / (kn |u_i|): 36 FMAs less than nine rank-one updates, same sums.
         const T h1 = y1 * (T(1) / kn), h2 = y2 * (T(1) / kn), h3 = y3 * (T(1) / kn);
-        const T j1[3] = { w1[0] * h1, w1[1] * h1, w1[2] * h1 };   // u^T / (2 |u|) (:3819), over gamma
-        const T j2[3] = { w2[0] * h2, w2[1] * h2, w2[2] * h2 };
-        const T j3[3] = { w3[0] * h3, w3[1] * h3, w3[2] * h3 };
-        add_outer1<T, U1>(A, g, j1, T(1) - n1);
-        add_outer1<T, U2>(A, g, j2, T(1) - n2);
-        add_outer1<T, U3>(A, g, j3, T(1) - n3);
+        constexpr T kq2 = kq * kq;
+        const T e13 = -u13, e23 = -u23, e12 = -u12;
+        const T e4 = u33 - u11, e5 = u33 - u22, e6 = u22 - u11;       // rows 4-6: -(u_ii - u_jj)
+        const T c1 = t_fma(h1, h1, T(2) * kq2 - T(1)), c2 = t_fma(h2, h2, T(2) * kq2 - T(1)), c3 = t_fma(h3, h3, T(2) * kq2 - T(1));
+        const T q1[3] = { c1 * w1[0], c1 * w1[1], c1 * w1[2] };
+        const T q2[3] = { c2 * w2[0], c2 * w2[1], c2 * w2[2] };
+        const T q3[3] = { c3 * w3[0], c3 * w3[1], c3 * w3[2] };
+        const T k1[3] = { kq2 * w1[0], kq2 * w1[1], kq2 * w1[2] }, k2[3] = { kq2 * w2[0], kq2 * w2[1], kq2 * w2[2] };
+        const T f1c = t_fma(h1, T(1) - n1, kq * (e4 + e6));           // rows 4, 6 (+u1) and 7
+        const T f2c = t_fma(h2, T(1) - n2, kq * (e5 - e6));           // rows 5 (+u2), 6 (-u2) and 8
+        const T f3c = t_fma(h3, T(1) - n3, -kq * (e4 + e5));          // rows 4, 5 (-u3) and 9
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) {
+                const T W = t_fma(w1[a], w1[b], t_fma(w2[a], w2[b], w3[a] * w3[b]));
+                A[sidx<10>(U1 + a, U1 + b)] += t_fma(q1[a], w1[b], W);
+                A[sidx<10>(U2 + a, U2 + b)] += t_fma(q2[a], w2[b], W);
+                A[sidx<10>(U3 + a, U3 + b)] += t_fma(q3[a], w3[b], W);
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                A[sidx<10>(U1 + a, U3 + b)] = t_fma(w3[a], w1[b], t_fma(-k1[a], w3[b], A[sidx<10>(U1 + a, U3 + b)]));
+                A[sidx<10>(U2 + a, U3 + b)] = t_fma(w3[a], w2[b], t_fma(-k2[a], w3[b], A[sidx<10>(U2 + a, U3 + b)]));
+                A[sidx<10>(U1 + a, U2 + b)] = t_fma(w2[a], w1[b], -k1[a] * w2[b]);          // the core has no (u1, u2) block
+            }
+            g[U1 + a] = t_fma(w3[a], e13, t_fma(w2[a], e12, t_fma(w1[a], f1c, g[U1 + a])));
+            g[U2 + a] = t_fma(w3[a], e23, t_fma(w1[a], e12, t_fma(w2[a], f2c, g[U2 + a])));
+            g[U3 + a] = t_fma(w1[a], e13, t_fma(w2[a], e23, t_fma(w3[a], f3c, g[U3 + a])));
+        }
     }
     ldlt_factor<T, 10>(A);
     ldlt_solve<T, 10>(A, g);
