@@ -606,12 +606,13 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
 // memory ([PNP_NMOM][stride] columns, this thread's column at sMomCol) -> pose `out` and the 12 numbers the
 // residual pass needs (LM: the state before the last update; F2: its tail).
 template <typename T, int METHOD>
-__device__ __forceinline__ void iterate_core(const T* sMomCol, int stride, const T* sC, const SolverPrm<T>& prm,
+__device__ __forceinline__ void iterate_core(T* sMomCol, int stride, const T* sC, const SolverPrm<T>& prm,
                                              T (&st)[PNP_NTAIL], Result<T>& out)
 {
     MomentsRef<T> mom;
     mom.base = sMomCol;
     mom.stride = stride;
+    mom.core = sMomCol + PNP_NMOM * stride;               // [PNP_NCORE][stride] behind the moments (LM only)
     if (METHOD == PNPB200_METHOD_LM) {
         T xp[12];
         solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, prm, xp, out);
@@ -667,7 +668,8 @@ __device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
 {
     constexpr int kIterBlock = BLOCK;
     __shared__ T sC[PNP_PATC];
-    __shared__ T sMom[PNP_NMOM * kIterBlock];             // [moment][thread]: conflict-free columns
+    constexpr int kRows = PNP_NMOM + ((METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) ? PNP_NCORE : 0);
+    __shared__ T sMom[kRows * kIterBlock];                // [moment | constant LM blocks][thread]: conflict-free columns
     if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = b < a.B;

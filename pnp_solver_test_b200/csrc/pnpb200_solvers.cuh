@@ -138,6 +138,9 @@ struct Moments {
     PNP_DEV T gmw(int k) const { return mw[k]; }
     PNP_DEV T gsx0() const { return sx0; }
     PNP_DEV T gsy0() const { return sy0; }
+    static constexpr bool kHasCore = false;               // the constant blocks of the LM system are recomputed per iteration
+    PNP_DEV T gcore(int) const { return T(0); }
+    PNP_DEV void set_core(int, T) const {}
     // flat order used for the [PNP_NMOM][B] workspace of the moment mapping
     PNP_DEV T& at(int k)
     {
@@ -160,6 +163,12 @@ struct MomentsRef {
     PNP_DEV T gmw(int k) const { return base[(24 + k) * stride]; }
     PNP_DEV T gsx0() const { return base[27 * stride]; }
     PNP_DEV T gsy0() const { return base[28 * stride]; }
+    // the constant blocks of the delta-eliminated LM system (lm_step): S33 (6), S13 (9), S23 (9) behind the moments,
+    // computed once per problem by lm_core_from_moments; S11 = S22 depends on the pattern only (PNP_NCORE = 24)
+    static constexpr bool kHasCore = true;
+    volatile T* core;
+    PNP_DEV T gcore(int k) const { return core[k * stride]; }
+    PNP_DEV void set_core(int k, T v) const { core[k * stride] = v; }
 };
 
 template <typename T, int LPP, typename Pts, bool WITH_W = true>
@@ -463,6 +472,26 @@ PNP_DEV void add_outer1(T (&A)[55], T (&g)[10], const T (&va)[3], T e)
     }
 }
 
+// The per-problem constant blocks of lm_step's system, for moment containers that can hold them
+template <typename T, typename M>
+PNP_DEV void lm_core_from_moments(const M& m, const T* __restrict__ sC, T ip)
+{
+    if (!M::kHasCore) return;
+    const T m0[3] = { sC[6], sC[7], sC[8] };
+    const T mx[3] = { m.gmx(0), m.gmx(1), m.gmx(2) }, my[3] = { m.gmy(0), m.gmy(1), m.gmy(2) };
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+            m.set_core(s3(a, b), t_fma(-(mx[a] * ip), mx[b], t_fma(-(my[a] * ip), my[b], m.gMw(s3(a, b)))));
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            m.set_core(6 + a * 3 + b, t_fma(m0[a] * ip, mx[b], -m.gMx(s3(a, b))));
+            m.set_core(15 + a * 3 + b, t_fma(m0[a] * ip, my[b], -m.gMy(s3(a, b))));
+        }
+    }
+}
+
 // One damped Gauss-Newton step: A = J^T J + lambda I (:2666-2667) from the moments and the gamma
 // column, g = J^T (z - hx) (:2684) from `r`, the nine constraint rows, x += pinv(A) g (:2675, :2702).
 //
@@ -488,9 +517,7 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
     const T ig = t_rcp<T>(gam);
     const T lg = lambda * (ig * ig);                    // lambda I in the scaled variables
     const T m0[3] = { sC[6], sC[7], sC[8] };
-    const T m0p[3] = { m0[0] * ip, m0[1] * ip, m0[2] * ip };
     const T mx[3] = { m.gmx(0), m.gmx(1), m.gmx(2) }, my[3] = { m.gmy(0), m.gmy(1), m.gmy(2) };
-    const T mxp[3] = { mx[0] * ip, mx[1] * ip, mx[2] * ip }, myp[3] = { my[0] * ip, my[1] * ip, my[2] * ip };
     const T f1 = r.q1 * ip, f2 = r.q2 * ip, s1p = gc.s1 * ip, s2p = gc.s2 * ip;
     T A[55], g[10];
 #pragma unroll
@@ -498,15 +525,21 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
 #pragma unroll
         for (int b = a; b < 3; ++b) {
             const T lam = (a == b) ? lg : T(0);
-            const T s11 = t_fma(-m0p[a], m0[b], sC[s3(a, b)]) + lam;
+            const T s11 = t_fma(-(m0[a] * ip), m0[b], sC[s3(a, b)]) + lam;
             A[sidx<10>(U1 + a, U1 + b)] = s11;
             A[sidx<10>(U2 + a, U2 + b)] = s11;
-            A[sidx<10>(U3 + a, U3 + b)] = t_fma(-mxp[a], mx[b], t_fma(-myp[a], my[b], m.gMw(s3(a, b)))) + lam;
+            if (M::kHasCore) A[sidx<10>(U3 + a, U3 + b)] = m.gcore(s3(a, b)) + lam;
+            else A[sidx<10>(U3 + a, U3 + b)] = t_fma(-(mx[a] * ip), mx[b], t_fma(-(my[a] * ip), my[b], m.gMw(s3(a, b)))) + lam;
         }
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            A[sidx<10>(U1 + a, U3 + b)] = t_fma(m0p[a], mx[b], -m.gMx(s3(a, b)));
-            A[sidx<10>(U2 + a, U3 + b)] = t_fma(m0p[a], my[b], -m.gMy(s3(a, b)));
+            if (M::kHasCore) {
+                A[sidx<10>(U1 + a, U3 + b)] = m.gcore(6 + a * 3 + b);
+                A[sidx<10>(U2 + a, U3 + b)] = m.gcore(15 + a * 3 + b);
+            } else {
+                A[sidx<10>(U1 + a, U3 + b)] = t_fma(m0[a] * ip, mx[b], -m.gMx(s3(a, b)));
+                A[sidx<10>(U2 + a, U3 + b)] = t_fma(m0[a] * ip, my[b], -m.gMy(s3(a, b)));
+            }
         }
         A[sidx<10>(U1 + a, GG)] = t_fma(-m0[a], s1p, gc.sg1[a]);
         A[sidx<10>(U2 + a, GG)] = t_fma(-m0[a], s2p, gc.sg2[a]);
@@ -681,6 +714,7 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
 #pragma unroll
     for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
     const T ip = t_rcp<T>(sC[9] + prm.lm_lambda);
+    lm_core_from_moments<T, M>(mom, sC, ip);
     for (int it = 0; it < prm.max_it; ++it) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
@@ -987,6 +1021,7 @@ PNP_DEV void solve_lm_plus_from_moments(const M& mom, const Moments<T>& mom_regs
     bool done = false;
     int iters = 0;
     const T ip = t_rcp<T>(sC[9] + prm.lm_lambda);
+    lm_core_from_moments<T, M>(mom, sC, ip);
     for (int it = 0; it < prm.max_it; ++it) {
         if (__all_sync(0xffffffffu, done)) break;
         T xn[12];
