@@ -686,9 +686,10 @@ __device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
     write_pose<T>(a, b, out);
 }
 
-// Register budget per thread given directly: the 64 Ki registers of an SM hold 9 warps at 224 registers
-// (no spills for FP64 LM, which wants ~222), 10 at 200, 12 at 168 (spills ~40 doubles), 8 at 255.
-// Measured for 1 Mi x 68 LM FP64 on B200 (scaled step): 0.946 ms at 224 / 255, 0.963 at 200, 0.992 at 184, 1.010 at 168.
+// Register budget per thread given directly.  Warps live on one of the four sub-partitions of an SM, each with
+// 16 Ki registers: 2 warps per sub-partition from 169 to 255 registers, 3 at <= 168 (FP64 LM wants ~214 and spills
+// ~26 doubles at 168).  Measured for 1 Mi x 68 LM FP64 on B200 (final step): 0.886 ms at 224, 0.904 at 255 (240 used),
+// 0.912 at 184, 0.905 at 168, 0.931 at 160 -- the third warp does not pay for its spills.
 template <typename T, int METHOD, int BLOCK, int MAXREG>
 __global__ void __launch_bounds__(BLOCK) __maxnreg__(MAXREG) k_iterate(const __grid_constant__ MomArgs<T> a)
 {
@@ -706,11 +707,11 @@ static void launch_iterate(const MomArgs<T>& m, int tune, cudaStream_t stream)
 {
     switch (tune) {
 #if PNP_TUNE_VARIANTS
-    case 2:  launch_iterate_as<T, METHOD, 128, 255>(m, stream); break;   //  8 warps / SM
-    case 3:  launch_iterate_as<T, METHOD, 128, 168>(m, stream); break;   // 12 warps / SM
-    case 4:  launch_iterate_as<T, METHOD, 128, 128>(m, stream); break;   // 16 warps / SM
+    case 2:  launch_iterate_as<T, METHOD, 32, 255>(m, stream); break;    // no cap
     case 30: launch_iterate_as<T, METHOD, 64, 200>(m, stream); break;    // 10 warps / SM
     case 31: launch_iterate_as<T, METHOD, 32, 184>(m, stream); break;    // 11 warps / SM
+    case 32: launch_iterate_as<T, METHOD, 32, 168>(m, stream); break;    // 3 warps per sub-partition
+    case 33: launch_iterate_as<T, METHOD, 32, 160>(m, stream); break;
 #endif
     default: launch_iterate_as<T, METHOD, 32, 224>(m, stream); break;    //  9 warps / SM, no spills
     }
