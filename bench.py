@@ -251,16 +251,38 @@ def run_ours(args):
     ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     last = {}
 
+    # With several ranks the report and the statistics of a step (two small kernels, three tiny all-reduces whose cost
+    # is launch latency) go to a second stream: they need the step's solve, but the next step's solve does not need
+    # them, so the collectives' latency hides under the next solve instead of idling every GPU of the job.
+    overlap = world > 1 and not args.no_overlap
+    main_stream = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(device=dev) if overlap else None
+
+    def report_and_stats(out):
+        rep = wl.report_batch(P, uv, K, out["R"], out["t"], out["euler"], gt)
+        last["stats"] = wl.error_statistics(rep["report"], gt, lazy=True)   # two all-reduce phases; D2H of the sums is async
+        last["pass"] = rep["flags"]
+
     def step(i=None):
         if i is not None:
             ev_a[i].record()
         out = pnp.solve_batch(METHOD, uv, pat, K, params=params)
         if i is not None:
             ev_b[i].record()
-        rep = wl.report_batch(P, uv, K, out["R"], out["t"], out["euler"], gt)
-        last["stats"] = wl.error_statistics(rep["report"], gt, lazy=True)   # two all-reduce phases; D2H of the sums is async
-        last["pass"] = rep["flags"]
+        if overlap:
+            side.wait_stream(main_stream)
+            with torch.cuda.stream(side):
+                report_and_stats(out)
+            for v in out.values():
+                if torch.is_tensor(v):
+                    v.record_stream(side)                  # allocated on the main stream, last read on the side stream
+        else:
+            report_and_stats(out)
         return out
+
+    def join_side():
+        if overlap:
+            main_stream.wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -272,6 +294,7 @@ def run_ours(args):
     sampler.wait_first()
     for _ in range(max(args.warmup, 0)):
         step()
+    join_side()
     barrier()
     sampler.mark_begin()
     l0 = int(_lib.lib.pnpb200_launch_count())               # kernels the library launches, counted by the library itself
@@ -280,6 +303,7 @@ def run_ours(args):
     t_start.record()
     for i in range(args.steps):
         step(i)
+    join_side()                                           # the last steps' reports and statistics are inside the timed region
     t_end.record()
     barrier()
     sampler.mark_end()
@@ -428,7 +452,9 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: %d problems x %d-point face pattern per GPU, LM refinement (14 it), FP64, "
                                "random_stress_test pose distribution, integer-quantised pixels" % (B, n),
                    "method": METHOD, "n_points": n, "problems_per_gpu": B, "global_problems": world * B,
-                   "step": "solve (moments, iterate, residual kernels) + error-report kernel + error statistics (two all-reduce phases)",
+                   "step": "solve (moments, iterate, residual kernels) + error-report kernel + error statistics (two all-reduce phases)"
+                           + ("; report + statistics of step i run on a second stream under the solve of step i + 1, all K inside the timed region"
+                              if overlap else ""),
                    "l2": "inputs are %.2f GB per step, larger than the 126 MB L2" % (uv.numel() * 8 / 1e9),
                    "parallelism": "problems sharded by global index, no solve-path traffic"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
@@ -451,6 +477,7 @@ def main():
     ap.add_argument("--problems", type=int, default=B_PER_GPU, help="problems per GPU (default: the BASELINE config)")
     ap.add_argument("--chunk", type=int, default=1 << 17, help="e2e pipeline chunk (problems)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: keep report + statistics on the solve stream")
     ap.add_argument("--pack-threads", type=int, default=-1,
                     help="host threads packing whole-pixel chunks to int16 for the e2e transfer (-1: cpus/ranks - 1, at most 15; 0: off)")
     ap.add_argument("--no-cpu", action="store_true")
