@@ -442,36 +442,6 @@ PNP_DEV void lm_rhs_from_moments(const T (&x)[12], const M& m, const T* __restri
     r.qg = qa - gam * gc.sgg - d1 * gc.s1 - d2 * gc.s2;
 }
 
-// A += row row^T for a constraint row whose only non-zeros are va at block BA and vb at block BB
-template <typename T, int BA, int BB>
-PNP_DEV void add_outer2(T (&A)[55], T (&g)[10], const T (&va)[3], const T (&vb)[3], T e)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = a; b < 3; ++b) {
-            A[sidx<10>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<10>(BA + a, BA + b)]);
-            A[sidx<10>(BB + a, BB + b)] = t_fma(vb[a], vb[b], A[sidx<10>(BB + a, BB + b)]);
-        }
-#pragma unroll
-        for (int b = 0; b < 3; ++b)
-            A[sidx<10>(BA + a, BB + b)] = t_fma(va[a], vb[b], A[sidx<10>(BA + a, BB + b)]);
-        g[BA + a] = t_fma(va[a], e, g[BA + a]);
-        g[BB + a] = t_fma(vb[a], e, g[BB + a]);
-    }
-}
-template <typename T, int BA>
-PNP_DEV void add_outer1(T (&A)[55], T (&g)[10], const T (&va)[3], T e)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = a; b < 3; ++b)
-            A[sidx<10>(BA + a, BA + b)] = t_fma(va[a], va[b], A[sidx<10>(BA + a, BA + b)]);
-        g[BA + a] = t_fma(va[a], e, g[BA + a]);
-    }
-}
-
 // The per-problem constant blocks of lm_step's system, for moment containers that can hold them
 template <typename T, typename M>
 PNP_DEV void lm_core_from_moments(const M& m, const T* __restrict__ sC, T ip)
