@@ -1,5 +1,6 @@
 import os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+_TESTS = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(_TESTS)); sys.path.insert(0, _TESTS)
 import numpy as np, torch
 from gpu_util import cuda_solve
 from oracle import oracle as orc

@@ -2,8 +2,9 @@
 """Developer tool (GPU box): CUDA vs oracle on a larger fresh sample than the test suite uses; prints the largest
 deviation on the well-posed subset per method (the 1e-9 contract of DESIGN.md section 4)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+_TESTS = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(_TESTS))
+sys.path.insert(0, _TESTS)
 import numpy as np
 import torch
 from gpu_util import cuda_solve, oracle_stability
