@@ -65,11 +65,12 @@ def test_compute_fails_loudly_without_gpu():
 
 
 def test_product_never_touches_the_oracle():
-    """oracle/ is test infrastructure: nothing under the package may import or load it."""
-    pkg = os.path.join(ROOT, "pnp_solver_test_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, f)).read()
-                for needle in ("import oracle", "from oracle", "libpnp_oracle", "pnp_oracle_", "dlopen"):
-                    assert needle not in txt, (needle, os.path.join(dirpath, f))
+    """oracle/ is test infrastructure: nothing under the package, the workload runners or the developer
+    tools may import or load it (only tests/, smoke() and bench.py's CPU arm do)."""
+    for top in ("pnp_solver_test_b200", "workloads", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    for needle in ("import oracle", "from oracle", "libpnp_oracle", "pnp_oracle_", "dlopen"):
+                        assert needle not in txt, (needle, os.path.join(dirpath, f))
