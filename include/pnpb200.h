@@ -144,7 +144,7 @@ int pnpb200_profile_read(float* ms, int* n_calls);
 /*
  * Same, from HOST buffers (pageable or pinned), chunked and double-buffered through a
  * caller-created pipeline so that H2D copies, the solve kernel and D2H copies overlap.
- * This is the call the drop-in PNP_SOLVER.solve_pnp_batch() makes for NumPy inputs and what
+ * This is the call the drop-in PNP_SOLVER.solve_pnp_batch_host() makes for NumPy inputs and what
  * bench.py times as `e2e`.  Blocks until the results are in the host buffers.
  */
 typedef struct pnpb200_pipeline pnpb200_pipeline;

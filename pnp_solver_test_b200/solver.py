@@ -8,6 +8,7 @@ Host code here only packs arguments: every number is computed by libpnpb200.so o
 (PyTorch tensors are used for device memory and streams, nothing else).  No CPU fallback.
 """
 import copy
+import os
 import ctypes as C
 
 import numpy as np
@@ -371,6 +372,46 @@ class PNP_SOLVER(object):
             self._dev_cache[ck] = self._pack_patterns(self.np_point_3d_pretransfer_dict_list, all_keys)
         return solve_batch(method, uv, self._dev_cache[ck], self.np_K_camera_est, point_index=idx,
                            params=params if params is not None else self.params)
+
+    def solve_pnp_batch_host(self, uv, method=None, key_list="default", params=None, chunk_problems=1 << 16, pack_threads=None):
+        """solve_pnp_batch for data that lives on the HOST (what a script that loops over NumPy samples
+        has): uv [B, n_total, 2] NumPy array or CPU tensor in; dict of NumPy arrays R [B,3,3], t [B,3],
+        euler [B,3] (roll, yaw, pitch, deg.), res_norm [B], iters [B], best_pattern [B] out.  Runs the
+        chunked host pipeline (pnpb200_solve_batch_host: H2D, solve and D2H overlap on three streams);
+        pack_threads host threads (default: half the visible cores, at most 8) let chunks of whole-pixel
+        landmarks cross PCIe as int16 (lossless, checked per chunk; other chunks travel as they are)."""
+        method = method or self.method
+        all_keys = list(self.np_point_3d_pretransfer_dict_list[0].keys())
+        if isinstance(key_list, str) and key_list == "default":
+            key_list = self.LM_key_list if method == "qeif" else None
+        idx = None if key_list is None else [all_keys.index(k) for k in key_list]
+        tdt = self._tdtype()
+        uv_h = uv if torch.is_tensor(uv) else torch.from_numpy(np.ascontiguousarray(uv))
+        uv_h = uv_h.to(device="cpu", dtype=tdt).contiguous()
+        B, n_total = int(uv_h.shape[0]), int(uv_h.shape[1])
+        if n_total != len(all_keys):
+            raise ValueError("uv holds %d landmarks per problem, the stored patterns %d" % (n_total, len(all_keys)))
+        pats = np.stack([np.stack([np.asarray(d[k], dtype=np.float64).reshape(3) for k in all_keys])
+                         for d in self.np_point_3d_pretransfer_dict_list])
+        pat_h = torch.from_numpy(pats).to(dtype=tdt).contiguous()
+        if pack_threads is None:
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            pack_threads = min(8, cpus // 2)
+        chunk = int(max(1, min(chunk_problems, 1 << max(0, (B - 1).bit_length()))))    # small batches: next power of two
+        key = ("pipe", self.dtype_code, n_total, int(pat_h.shape[0]), chunk)
+        pipe = self._dev_cache.get(key)
+        if pipe is None:
+            pipe = HostPipeline(tdt, chunk_problems=chunk, n_total=n_total, n_patterns=int(pat_h.shape[0]), n_streams=3,
+                                device=self.device)
+            self._dev_cache[key] = pipe
+        pipe.set_packing(int(pack_threads) if B >= 2 * chunk else 0)
+        outs = {"R": torch.empty((B, 3, 3), dtype=tdt), "t": torch.empty((B, 3), dtype=tdt), "euler": torch.empty((B, 3), dtype=tdt),
+                "res_norm": torch.empty((B,), dtype=tdt), "iters": torch.empty((B,), dtype=torch.int32),
+                "best_pattern": torch.empty((B,), dtype=torch.int32)}
+        if B > 0:
+            pipe.solve(method, uv_h, pat_h, self.np_K_camera_est, outs, point_index=idx,
+                       params=params if params is not None else self.params)
+        return {k: v.numpy() for k, v in outs.items()}
 
     # ---------------------------------------------------------------- Euler <-> R (:4442-4517)
     def get_rotation_matrix_from_Euler(self, roll, yaw, pitch, is_degree=False):

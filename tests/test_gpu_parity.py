@@ -186,6 +186,15 @@ def test_pnp_solver_class_is_a_drop_in():
     # batched entry point == loop
     out = to_np(solver.solve_pnp_batch(g["uv"]))
     assert np.abs(out["R"] - g["R"]).max() < 1e-9 and (out["best_pattern"] == g["best_pattern"]).all()
+    # the same from host data through the chunked pipeline (several chunks, packed transfer on and off)
+    big = np.tile(g["uv"], (40, 1, 1))
+    ref_big = to_np(solver.solve_pnp_batch(big))
+    for pack in (0, 2):
+        host = solver.solve_pnp_batch_host(big, chunk_problems=512, pack_threads=pack)
+        assert isinstance(host["R"], np.ndarray) and host["R"].shape == (big.shape[0], 3, 3)
+        for k in ("R", "t", "euler", "res_norm", "iters", "best_pattern"):
+            assert np.array_equal(host[k].reshape(ref_big[k].shape), ref_big[k], equal_nan=True), (k, pack)
+    assert solver.solve_pnp_batch_host(big[:0])["R"].shape == (0, 3, 3)
     # Euler / projection members
     Rm = one.get_rotation_matrix_from_Euler(10.0, -20.0, 30.0, is_degree=True)
     assert np.abs(Rm - orc.R_from_euler(10.0, -20.0, 30.0, True)).max() < 1e-14
