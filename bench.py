@@ -39,17 +39,17 @@ UNIT = "solves/s"
 # Algorithmic work per solve of the LM path as implemented (DESIGN.md "Kernels"); FMA = 2 flops.
 # Moment mapping = three kernels:
 #   k_stream_chunk<.,LM,0>  moments: per point 6 theta*theta^T products, bx^2+by^2, 27 FMAs, 2 adds    65 flop/pt   (HBM-bound)
-#   k_iterate<.,LM>         14 x [gamma column 84 FMA = 168, rhs 37 FMA = 74, scaled set-up with the delta_1/delta_2
-#                           elimination folded into the constant 9x9 core (computed once per problem, re-read from
-#                           shared memory) 84, nine constraint rows collected per block
-#                           (dots, 3 rsqrt/sqrt, 6 + 9 + 9 block entries) 344, LDL^T 10x10 (165 FMA, 55 MUL, 10 reciprocals)
-#                           455, two triangular solves 190, delta back-substitution and update 46] = 14 x 1361
-#                           + constant core 90 + 3x3 SVD, t, Euler ~1000                            (FP64 pipe)
-#                           (cross-check: the SASS of one iteration is 603 DFMA + 123 DMUL + 32 DADD = 1361)
+#   k_iterate<.,LM>         14 x [gamma column S u of the reduced system from the constant 9x9 core (kept in shared
+#                           memory), its corner u^T S u, right-hand side c - gamma S u + lambda terms 275, nine constraint
+#                           rows collected per block (dots, 3 rsqrt/sqrt, 6 + 9 + 9 block entries) 344, LDL^T 10x10
+#                           (165 FMA, 55 MUL, 10 reciprocals) 455, two triangular solves 190, delta back-substitution and
+#                           update 46] = 14 x 1310
+#                           + constant core and c, once per problem 110 + 3x3 SVD, t, Euler ~1000   (FP64 pipe)
+#                           (cross-check: the SASS of one iteration is 575 DFMA + 125 DMUL + 35 DADD = 1310)
 #   k_stream_chunk<.,LM,1>  residual at the state before the last update: 34 flop/pt                   (HBM-bound)
 # ------------------------------------------------------------------------------------------------
 def lm_flops_iterate(max_it=14):
-    return max_it * (168 + 74 + 84 + 344 + 455 + 190 + 46) + 90 + 1000
+    return max_it * (275 + 344 + 455 + 190 + 46) + 110 + 1000
 
 
 def lm_flops_per_solve(n, max_it=14):

@@ -9,7 +9,7 @@
 // workspace layout of the moment mapping: [PNP_NMOM][B] moments, [PNP_NTAIL][B] state before the last
 // update (or the F2 tail), PNP_PATC pattern constants (see pnpb200_solvers.cuh)
 #define PNP_NMOM 29
-#define PNP_NCORE 24        // constant blocks of the LM system kept next to the moments by k_iterate (S33, S13, S23)
+#define PNP_NCORE 33        // constants of the LM system kept next to the moments by k_iterate (S33 6, S13 9, S23 9, c 9)
 #define PNP_NTAIL 12
 #define PNP_PATC 20
 // landmark selections up to this size travel inside the kernel arguments; larger ones through device memory

@@ -164,7 +164,7 @@ struct MomentsRef {
     PNP_DEV T gsx0() const { return base[27 * stride]; }
     PNP_DEV T gsy0() const { return base[28 * stride]; }
     // the constant blocks of the delta-eliminated LM system (lm_step): S33 (6), S13 (9), S23 (9) behind the moments,
-    // computed once per problem by lm_core_from_moments; S11 = S22 depends on the pattern only (PNP_NCORE = 24)
+    // computed once per problem by lm_core_from_moments, followed by the constant right-hand side c (9); S11 = S22 depends on the pattern only (PNP_NCORE = 33)
     static constexpr bool kHasCore = true;
     volatile T* core;
     PNP_DEV T gcore(int k) const { return core[k * stride]; }
@@ -460,6 +460,97 @@ PNP_DEV void lm_core_from_moments(const M& m, const T* __restrict__ sC, T ip)
             m.set_core(15 + a * 3 + b, t_fma(m0[a] * ip, my[b], -m.gMy(s3(a, b))));
         }
     }
+    // constant part of the reduced right-hand side (lm_step_core): c1 = mx - m0 sx0 / p, c2 = my - m0 sy0 / p,
+    // c3 = (mx sx0 + my sy0) / p - mw
+    const T sxp = m.gsx0() * ip, syp = m.gsy0() * ip;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        m.set_core(24 + a, t_fma(-m0[a], sxp, mx[a]));
+        m.set_core(27 + a, t_fma(-m0[a], syp, my[a]));
+        m.set_core(30 + a, t_fma(mx[a], sxp, t_fma(my[a], syp, -m.gmw(a))));
+    }
+}
+
+// Second half of an LM step, common to both ways of building the reduced system: the nine constraint
+// rows are added to A (10 x 10 packed, order y_u1, y_u2, y_u3, d gamma) and g, the system is solved, the
+// two deltas are back-substituted and the state is updated.  s_k, q_k: the delta_k column / right-hand side
+// of the measurement rows (s1 = sum g1, q1 = sum (z - hx)_x).  Returns max |dx|.
+template <typename T, bool TRUE_JAC>
+PNP_DEV T lm_finish(T (&x)[12], T (&A)[55], T (&g)[10], const T (&m0)[3], const T (&mx)[3], const T (&my)[3],
+                    T s1, T s2, T q1, T q2, T ig, T ip)
+{
+    constexpr int U1 = 0, U2 = 3, U3 = 6, GG = 9;
+    // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones), times 1 / gamma
+    {
+        const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
+        const T u11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
+        const T u22 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
+        const T u33 = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2];
+        const T u13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
+        const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
+        const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+        // |u| and 1 / (kn |u|) from one reciprocal square root each
+        const T y1 = t_rsqrt<T>(u11), y2 = t_rsqrt<T>(u22), y3 = t_rsqrt<T>(u33);
+        const T n1 = t_sqrt_fast<T>(u11, y1), n2 = t_sqrt_fast<T>(u22, y2), n3 = t_sqrt_fast<T>(u33, y3);
+        constexpr T kq = TRUE_JAC ? T(2) : T(1), kn = TRUE_JAC ? T(1) : T(2);
+        const T w1[3] = { u1[0] * ig, u1[1] * ig, u1[2] * ig };          // u / gamma
+        const T w2[3] = { u2[0] * ig, u2[1] * ig, u2[2] * ig };
+        const T w3[3] = { u3[0] * ig, u3[1] * ig, u3[2] * ig };
+        // The nine rows r_k (each with two non-zero blocks at most) enter as sum_k r_k^T r_k and sum_k r_k^T e_k.
+        // Collected per block instead of row by row:
+        //   diagonal block i:     w1 w1^T + w2 w2^T + w3 w3^T + (2 kq^2 + h_i^2 - 1) w_i w_i^T
+        //   block (i, j), i < j:  w_j w_i^T - kq^2 w_i w_j^T
+        //   right-hand side i:    sum_{j != i} w_j e_ij + w_i (kq (+-e_4..6) + h_i (1 - |u_i|))
+        // with h_i = 1 / (kn |u_i|): 36 FMAs less than nine rank-one updates, same sums.
+        const T h1 = y1 * (T(1) / kn), h2 = y2 * (T(1) / kn), h3 = y3 * (T(1) / kn);
+        constexpr T kq2 = kq * kq;
+        const T e13 = -u13, e23 = -u23, e12 = -u12;
+        const T e4 = u33 - u11, e5 = u33 - u22, e6 = u22 - u11;       // rows 4-6: -(u_ii - u_jj)
+        const T c1 = t_fma(h1, h1, T(2) * kq2 - T(1)), c2 = t_fma(h2, h2, T(2) * kq2 - T(1)), c3 = t_fma(h3, h3, T(2) * kq2 - T(1));
+        const T q1[3] = { c1 * w1[0], c1 * w1[1], c1 * w1[2] };
+        const T q2[3] = { c2 * w2[0], c2 * w2[1], c2 * w2[2] };
+        const T q3[3] = { c3 * w3[0], c3 * w3[1], c3 * w3[2] };
+        const T k1[3] = { kq2 * w1[0], kq2 * w1[1], kq2 * w1[2] }, k2[3] = { kq2 * w2[0], kq2 * w2[1], kq2 * w2[2] };
+        const T f1c = t_fma(h1, T(1) - n1, kq * (e4 + e6));           // rows 4, 6 (+u1) and 7
+        const T f2c = t_fma(h2, T(1) - n2, kq * (e5 - e6));           // rows 5 (+u2), 6 (-u2) and 8
+        const T f3c = t_fma(h3, T(1) - n3, -kq * (e4 + e5));          // rows 4, 5 (-u3) and 9
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = a; b < 3; ++b) {
+                const T W = t_fma(w1[a], w1[b], t_fma(w2[a], w2[b], w3[a] * w3[b]));
+                A[sidx<10>(U1 + a, U1 + b)] += t_fma(q1[a], w1[b], W);
+                A[sidx<10>(U2 + a, U2 + b)] += t_fma(q2[a], w2[b], W);
+                A[sidx<10>(U3 + a, U3 + b)] += t_fma(q3[a], w3[b], W);
+            }
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                A[sidx<10>(U1 + a, U3 + b)] = t_fma(w3[a], w1[b], t_fma(-k1[a], w3[b], A[sidx<10>(U1 + a, U3 + b)]));
+                A[sidx<10>(U2 + a, U3 + b)] = t_fma(w3[a], w2[b], t_fma(-k2[a], w3[b], A[sidx<10>(U2 + a, U3 + b)]));
+                A[sidx<10>(U1 + a, U2 + b)] = t_fma(w2[a], w1[b], -k1[a] * w2[b]);          // the core has no (u1, u2) block
+            }
+            g[U1 + a] = t_fma(w3[a], e13, t_fma(w2[a], e12, t_fma(w1[a], f1c, g[U1 + a])));
+            g[U2 + a] = t_fma(w3[a], e23, t_fma(w1[a], e12, t_fma(w2[a], f2c, g[U2 + a])));
+            g[U3 + a] = t_fma(w1[a], e13, t_fma(w2[a], e23, t_fma(w3[a], f3c, g[U3 + a])));
+        }
+    }
+    ldlt_factor<T, 10>(A);
+    ldlt_solve<T, 10>(A, g);
+    // ---- back-substitute the two deltas: d_k = (rhs_k - column_k . y) / p; the back substitution
+    // delivers g[9] first and g[0] last: consume them in that order
+    T e1 = t_fma(-s1, g[GG], q1), e2 = t_fma(-s2, g[GG], q2);
+#pragma unroll
+    for (int a = 2; a >= 0; --a) { e1 = t_fma(mx[a], g[U3 + a], e1); e2 = t_fma(my[a], g[U3 + a], e2); }
+#pragma unroll
+    for (int a = 2; a >= 0; --a) { e1 = t_fma(-m0[a], g[U1 + a], e1); e2 = t_fma(-m0[a], g[U2 + a], e2); }
+    T step = t_abs(g[GG]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) step = fmax(step, t_abs(g[i] * ig));
+    step = fmax(step, fmax(t_abs(e1 * ip), t_abs(e2 * ip)));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = t_fma(g[i], ig, x[i]);
+    x[9] += e1 * ip; x[10] += e2 * ip; x[11] += g[GG];
+    return step;
 }
 
 // One damped Gauss-Newton step: A = J^T J + lambda I (:2666-2667) from the moments and the gamma
@@ -520,77 +611,68 @@ PNP_DEV T lm_step(T (&x)[12], const M& m, const T* __restrict__ sC, const GammaC
     }
     A[sidx<10>(GG, GG)] = t_fma(-gc.s1, s1p, t_fma(-gc.s2, s2p, gc.sgg + lambda));
     g[GG] = t_fma(-gc.s1, f1, t_fma(-gc.s2, f2, r.qg));
-    // ---- the nine constraint rows (:3753-3772, Jacobians :3787-3823 incl. the halved ones), times 1 / gamma
-    {
-        const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
-        const T u11 = u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2];
-        const T u22 = u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2];
-        const T u33 = u3[0] * u3[0] + u3[1] * u3[1] + u3[2] * u3[2];
-        const T u13 = u1[0] * u3[0] + u1[1] * u3[1] + u1[2] * u3[2];
-        const T u23 = u2[0] * u3[0] + u2[1] * u3[1] + u2[2] * u3[2];
-        const T u12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
-        // |u| and 1 / (kn |u|) from one reciprocal square root each
-        const T y1 = t_rsqrt<T>(u11), y2 = t_rsqrt<T>(u22), y3 = t_rsqrt<T>(u33);
-        const T n1 = t_sqrt_fast<T>(u11, y1), n2 = t_sqrt_fast<T>(u22, y2), n3 = t_sqrt_fast<T>(u33, y3);
-        constexpr T kq = TRUE_JAC ? T(2) : T(1), kn = TRUE_JAC ? T(1) : T(2);
-        const T w1[3] = { u1[0] * ig, u1[1] * ig, u1[2] * ig };          // u / gamma
-        const T w2[3] = { u2[0] * ig, u2[1] * ig, u2[2] * ig };
-        const T w3[3] = { u3[0] * ig, u3[1] * ig, u3[2] * ig };
-        // The nine rows r_k (each with two non-zero blocks at most) enter as sum_k r_k^T r_k and sum_k r_k^T e_k.
-        // Collected per block instead of row by row:
-        //   diagonal block i:     w1 w1^T + w2 w2^T + w3 w3^T + (2 kq^2 + h_i^2 - 1) w_i w_i^T
-        //   block (i, j), i < j:  w_j w_i^T - kq^2 w_i w_j^T
-        //   right-hand side i:    sum_{j != i} w_j e_ij + w_i (kq (+-e_4..6) + h_i (1 - |u_i|))
-        // with h_i = 1 / (kn |u_i|): 36 FMAs less than nine rank-one updates, same sums.
-        const T h1 = y1 * (T(1) / kn), h2 = y2 * (T(1) / kn), h3 = y3 * (T(1) / kn);
-        constexpr T kq2 = kq * kq;
-        const T e13 = -u13, e23 = -u23, e12 = -u12;
-        const T e4 = u33 - u11, e5 = u33 - u22, e6 = u22 - u11;       // rows 4-6: -(u_ii - u_jj)
-        const T c1 = t_fma(h1, h1, T(2) * kq2 - T(1)), c2 = t_fma(h2, h2, T(2) * kq2 - T(1)), c3 = t_fma(h3, h3, T(2) * kq2 - T(1));
-        const T q1[3] = { c1 * w1[0], c1 * w1[1], c1 * w1[2] };
-        const T q2[3] = { c2 * w2[0], c2 * w2[1], c2 * w2[2] };
-        const T q3[3] = { c3 * w3[0], c3 * w3[1], c3 * w3[2] };
-        const T k1[3] = { kq2 * w1[0], kq2 * w1[1], kq2 * w1[2] }, k2[3] = { kq2 * w2[0], kq2 * w2[1], kq2 * w2[2] };
-        const T f1c = t_fma(h1, T(1) - n1, kq * (e4 + e6));           // rows 4, 6 (+u1) and 7
-        const T f2c = t_fma(h2, T(1) - n2, kq * (e5 - e6));           // rows 5 (+u2), 6 (-u2) and 8
-        const T f3c = t_fma(h3, T(1) - n3, -kq * (e4 + e5));          // rows 4, 5 (-u3) and 9
+    return lm_finish<T, TRUE_JAC>(x, A, g, m0, mx, my, gc.s1, gc.s2, r.q1, r.q2, ig, ip);
+}
+
+// The same step for moment containers that hold the constant blocks (k_iterate).  With S the constant
+// 9 x 9 core and u = (u1, u2, u3), the gamma column of the reduced system is S u, its corner is
+// u^T S u + lambda, and the reduced right-hand side is
+//   g_u = c - gamma S u + (lambda / p) (-d1 m0, -d2 m0, d1 mx + d2 my),   g_gamma = c.u - gamma u^T S u - (lambda / p) (d1 s1 + d2 s2)
+// with c constant per problem (lm_core_from_moments) -- algebraically what lm_gamma_column,
+// lm_rhs_from_moments and lm_step compute from the raw moments, in 45 fewer FP64 instructions.
+template <typename T, typename M, bool TRUE_JAC = false>
+PNP_DEV T lm_step_core(T (&x)[12], const M& m, const T* __restrict__ sC, T lambda, T ip)
+{
+    constexpr int U1 = 0, U2 = 3, U3 = 6, GG = 9;
+    const T gam = x[11], d1 = x[9], d2 = x[10];
+    const T ig = t_rcp<T>(gam);
+    const T lg = lambda * (ig * ig);
+    const T lp = lambda * ip;
+    const T m0[3] = { sC[6], sC[7], sC[8] };
+    const T mx[3] = { m.gmx(0), m.gmx(1), m.gmx(2) }, my[3] = { m.gmy(0), m.gmy(1), m.gmy(2) };
+    const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
+    T A[55], g[10];
+    T col1[3] = { T(0), T(0), T(0) }, col2[3] = { T(0), T(0), T(0) }, col3[3] = { T(0), T(0), T(0) };
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < 3; ++a) {
 #pragma unroll
-            for (int b = a; b < 3; ++b) {
-                const T W = t_fma(w1[a], w1[b], t_fma(w2[a], w2[b], w3[a] * w3[b]));
-                A[sidx<10>(U1 + a, U1 + b)] += t_fma(q1[a], w1[b], W);
-                A[sidx<10>(U2 + a, U2 + b)] += t_fma(q2[a], w2[b], W);
-                A[sidx<10>(U3 + a, U3 + b)] += t_fma(q3[a], w3[b], W);
+        for (int b = 0; b < 3; ++b) {
+            const T s11 = t_fma(-(m0[a] * ip), m0[b], sC[s3(a, b)]);
+            const T s33 = m.gcore(s3(a, b)), s13 = m.gcore(6 + a * 3 + b), s23 = m.gcore(15 + a * 3 + b);
+            if (b >= a) {
+                const T lam = (a == b) ? lg : T(0);
+                A[sidx<10>(U1 + a, U1 + b)] = s11 + lam;
+                A[sidx<10>(U2 + a, U2 + b)] = s11 + lam;
+                A[sidx<10>(U3 + a, U3 + b)] = s33 + lam;
             }
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-                A[sidx<10>(U1 + a, U3 + b)] = t_fma(w3[a], w1[b], t_fma(-k1[a], w3[b], A[sidx<10>(U1 + a, U3 + b)]));
-                A[sidx<10>(U2 + a, U3 + b)] = t_fma(w3[a], w2[b], t_fma(-k2[a], w3[b], A[sidx<10>(U2 + a, U3 + b)]));
-                A[sidx<10>(U1 + a, U2 + b)] = t_fma(w2[a], w1[b], -k1[a] * w2[b]);          // the core has no (u1, u2) block
-            }
-            g[U1 + a] = t_fma(w3[a], e13, t_fma(w2[a], e12, t_fma(w1[a], f1c, g[U1 + a])));
-            g[U2 + a] = t_fma(w3[a], e23, t_fma(w1[a], e12, t_fma(w2[a], f2c, g[U2 + a])));
-            g[U3 + a] = t_fma(w1[a], e13, t_fma(w2[a], e23, t_fma(w3[a], f3c, g[U3 + a])));
+            A[sidx<10>(U1 + a, U3 + b)] = s13;
+            A[sidx<10>(U2 + a, U3 + b)] = s23;
+            col1[a] = t_fma(s11, u1[b], t_fma(s13, u3[b], col1[a]));
+            col2[a] = t_fma(s11, u2[b], t_fma(s23, u3[b], col2[a]));
+            col3[b] = t_fma(s13, u1[a], t_fma(s23, u2[a], col3[b]));      // S13^T u1 + S23^T u2
+            col3[a] = t_fma(s33, u3[b], col3[a]);
         }
     }
-    ldlt_factor<T, 10>(A);
-    ldlt_solve<T, 10>(A, g);
-    // ---- back-substitute the two deltas: d_k = (rhs_k - column_k . y) / p; the back substitution
-    // delivers g[9] first and g[0] last: consume them in that order
-    T e1 = t_fma(-gc.s1, g[GG], r.q1), e2 = t_fma(-gc.s2, g[GG], r.q2);
+    T usu = T(0), cu = T(0), s1 = T(0), s2 = T(0);
 #pragma unroll
-    for (int a = 2; a >= 0; --a) { e1 = t_fma(mx[a], g[U3 + a], e1); e2 = t_fma(my[a], g[U3 + a], e2); }
-#pragma unroll
-    for (int a = 2; a >= 0; --a) { e1 = t_fma(-m0[a], g[U1 + a], e1); e2 = t_fma(-m0[a], g[U2 + a], e2); }
-    T step = t_abs(g[GG]);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) step = fmax(step, t_abs(g[i] * ig));
-    step = fmax(step, fmax(t_abs(e1 * ip), t_abs(e2 * ip)));
-#pragma unroll
-    for (int i = 0; i < 9; ++i) x[i] = t_fma(g[i], ig, x[i]);
-    x[9] += e1 * ip; x[10] += e2 * ip; x[11] += g[GG];
-    return step;
+    for (int a = 0; a < 3; ++a) {
+        const T c1 = m.gcore(24 + a), c2 = m.gcore(27 + a), c3 = m.gcore(30 + a);
+        usu = t_fma(u1[a], col1[a], t_fma(u2[a], col2[a], t_fma(u3[a], col3[a], usu)));
+        cu = t_fma(c1, u1[a], t_fma(c2, u2[a], t_fma(c3, u3[a], cu)));
+        s1 = t_fma(m0[a], u1[a], t_fma(-mx[a], u3[a], s1));
+        s2 = t_fma(m0[a], u2[a], t_fma(-my[a], u3[a], s2));
+        A[sidx<10>(U1 + a, GG)] = col1[a];
+        A[sidx<10>(U2 + a, GG)] = col2[a];
+        A[sidx<10>(U3 + a, GG)] = col3[a];
+        g[U1 + a] = t_fma(-gam, col1[a], t_fma(-(lp * d1), m0[a], c1));
+        g[U2 + a] = t_fma(-gam, col2[a], t_fma(-(lp * d2), m0[a], c2));
+        g[U3 + a] = t_fma(-gam, col3[a], t_fma(lp * d1, mx[a], t_fma(lp * d2, my[a], c3)));
+    }
+    A[sidx<10>(GG, GG)] = usu + lambda;
+    g[GG] = t_fma(-gam, usu, t_fma(-lp, t_fma(d1, s1, d2 * s2), cu));
+    const T q1 = t_fma(-gam, s1, t_fma(-sC[9], d1, m.gsx0()));          // sum (z - hx)_x = sx0 - gamma s1 - n d1
+    const T q2 = t_fma(-gam, s2, t_fma(-sC[9], d2, m.gsy0()));
+    return lm_finish<T, TRUE_JAC>(x, A, g, m0, mx, my, s1, s2, q1, q2, ig, ip);
 }
 
 // ||z - hx|| over the 2n measurement rows at state x, point by point (:2679-2681)
@@ -688,11 +770,15 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
     for (int it = 0; it < prm.max_it; ++it) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
-        GammaCol<T> gc;
-        LmRhs<T> r;
-        lm_gamma_column<T, M>(x, mom, sC, gc);
-        lm_rhs_from_moments<T, M>(x, mom, sC, gc, r);
-        lm_step<T, M>(x, mom, sC, gc, r, prm.lm_lambda, ip);
+        if (M::kHasCore) {
+            lm_step_core<T, M>(x, mom, sC, prm.lm_lambda, ip);
+        } else {
+            GammaCol<T> gc;
+            LmRhs<T> r;
+            lm_gamma_column<T, M>(x, mom, sC, gc);
+            lm_rhs_from_moments<T, M>(x, mom, sC, gc, r);
+            lm_step<T, M>(x, mom, sC, gc, r, prm.lm_lambda, ip);
+        }
     }
     lm_reconstruct<T>(x, out);
     out.res = T(0);
