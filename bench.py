@@ -59,7 +59,7 @@ def lm_flops_per_solve(n, max_it=14):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_iterate<double, LM> launch over 1,048,576 problems, from the
 # committed `ncu --set full` capture (bench.py cannot run ncu on itself); algorithmic bytes are 456 per problem
 # (29 moments in; state before the last update, R, t, Euler, iters, best out) = 478 MB.
-NCU_TRAFFIC = {"bytes": 243.45e6 + 192.98e6, "problems": 1 << 20, "source": "profiles/r01q_k_iterate_lm68_ncu.md"}
+NCU_TRAFFIC = {"bytes": 243.50e6 + 187.57e6, "problems": 1 << 20, "source": "profiles/r01r_k_iterate_lm68_ncu.md"}
 
 
 def lm_flops_survey(n, max_it=14):
