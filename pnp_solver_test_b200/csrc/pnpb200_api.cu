@@ -430,6 +430,7 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
     };
     std::atomic<int> rc_pack{PNPB200_OK};
     std::atomic<long long> n_packed{0};
+    char packer_error[sizeof(g_last_error)] = "";          // the packing thread's pnpb200_last_error(), handed to the caller
     std::thread packer;
     const bool packing = p->pack_threads > 0 && p->slots.size() > (size_t)p->n_streams && n_chunks >= 2;
     if (packing) {
@@ -449,6 +450,7 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
                 if (exact == 1) n_packed.fetch_add(1);
                 s = (s + 1 < p->slots.size()) ? s + 1 : (size_t)p->n_streams;
             }
+            if (rc_pack.load() != PNPB200_OK) memcpy(packer_error, g_last_error, sizeof(packer_error));   // thread-local there
         });
     }
     int rc_main = PNPB200_OK;
@@ -474,6 +476,7 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
     p->last_packed = n_packed.load();
     for (PipeSlot& sl : p->slots) PNP_CUDA_OK(cudaStreamSynchronize(sl.stream));
     if (rc_main != PNPB200_OK) return rc_main;
+    if (rc_pack.load() != PNPB200_OK) memcpy(g_last_error, packer_error, sizeof(g_last_error));
     return rc_pack.load();
 }
 
