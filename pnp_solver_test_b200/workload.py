@@ -216,13 +216,29 @@ def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=T
     return pending if lazy else pending.result()                                # .result() is the only synchronisation
 
 
-def error_statistics(report, gt, group=None, distributed=True, lazy=False):
+def approval_mask(gt, kind):
+    """TEST_TOOLBOX.approval_func_small_angle / approval_func_large_angle (:959-970) for a batch:
+    gt [B,4] = (depth, roll, pitch, yaw) tensor (any device) -> bool [B].  'small_angle': no ground-truth
+    angle beyond 30 degrees in magnitude; 'large_angle': the complement."""
+    small = (gt[:, 1].abs() <= 30) & (gt[:, 2].abs() <= 30) & (gt[:, 3].abs() <= 30)
+    if kind == "small_angle":
+        return small
+    if kind == "large_angle":
+        return ~small
+    raise ValueError("approval must be None, 'small_angle' or 'large_angle', not %r" % (kind,))
+
+
+def error_statistics(report, gt, group=None, distributed=True, lazy=False, approval=None):
     """The statistics block of TEST_TOOLBOX.data_analysis_and_saving (:1070-1112) for the four
     reported quantities, for class 'all' and per GT-depth class, in two kernels and two all-reduce
     phases.  report: [B,16] from report_batch; gt [B,4].
+    approval: None, 'small_angle' or 'large_angle' = the approval_func of get_classified_result
+    (:939-970): problems that fail it leave their distance class but stay in 'all', as there.
     Returns {quantity: {'all': stats[7], 'by_depth': stats[12,7]}} (CPU tensors, STAT_KEYS order);
     lazy=True returns an object whose .result() gives that dict (no host sync in this call)."""
     cls = classify(gt[:, 0], CLASS_BINS["depth"], scale=100.0)
+    if approval is not None:
+        cls = torch.where(approval_mask(gt, approval), cls, torch.full_like(cls, -1))
     # (estimate, GT): depth compares t3_est with distance_GT (:1073), the angles est vs GT
     est = [report[:, 10], report[:, 12], report[:, 13], report[:, 14]]
     ref = [report[:, 11], gt[:, 1], gt[:, 2], gt[:, 3]]

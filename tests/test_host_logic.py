@@ -187,6 +187,18 @@ def test_pixel_packing_is_exact_or_refused():
     assert _lib.lib.pnpb200_pack_i16(C.c_int(7), None, C.c_int64(4), None, C.c_int(1)) < 0
 
 
+def test_approval_masks():
+    """approval_mask = TEST_TOOLBOX.approval_func_small_angle / _large_angle (:959-970), thresholds inclusive."""
+    from pnp_solver_test_b200 import workload as wl
+    gt = torch.tensor([[1.0, 0.0, 0.0, 0.0], [1.0, 30.0, -30.0, 30.0], [1.0, 30.000001, 0.0, 0.0], [1.0, 0.0, -31.0, 0.0],
+                       [1.0, 0.0, 0.0, 45.0], [9.0, -29.9, 29.9, -29.9]], dtype=torch.float64)
+    small = wl.approval_mask(gt, "small_angle")
+    assert small.tolist() == [True, True, False, False, False, True]
+    assert wl.approval_mask(gt, "large_angle").tolist() == [not x for x in small.tolist()]
+    with pytest.raises(ValueError):
+        wl.approval_mask(gt, "medium")
+
+
 def test_drpy_tables_match_reference(tmp_path):
     """drpy_statistic_dict / write_drpy_statistic_csv against the eleven class-combination tables the
     unmodified get_all_class_seperated_result / get_drpy_statistic / write_drpy_2_depth_statistic_CSV
