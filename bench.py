@@ -195,9 +195,14 @@ def run_reference(args):
     from oracle import oracle as orc
     cores = orc.num_threads()
     r0, _ = cpu_rate(max(256, 64 * cores))
-    sample = int(max(256, min(B_PER_GPU, r0 * 8.0)))            # ~8 s per step
+    r0, _ = cpu_rate(int(max(256, r0 * 1.5)))                   # second calibration on ~1.5 s of work: thread start-up amortised
+    # a step = a bounded sample of the workload: ~8 s of CPU work, less when many steps are asked for, so that
+    # the K timed steps take ~90 s in all and the warm-up ~10 s whatever K and W are
+    per_step = min(8.0, 90.0 / max(1, args.steps))
+    sample = int(max(64, min(B_PER_GPU, r0 * per_step)))
+    warm = int(max(64, min(sample, r0 * min(1.0, 10.0 / max(1, args.warmup)))))
     for _ in range(args.warmup):
-        cpu_rate(max(64, sample // 8))
+        cpu_rate(warm)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_rate(sample)
