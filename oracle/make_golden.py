@@ -280,6 +280,12 @@ def stress_report_case(PNPS, TTBX, tag, B, seed):
     cdict = quiet(TTBX.get_classified_result, result_list, class_name='distance', approval_func=None)
     stats_all = np.array([stat(result_list, ek, gk) for _, ek, gk in quant], dtype=np.float64)
     stats_depth = np.array([[stat(cdict.get(lb, []), ek, gk) for lb in labels] for _, ek, gk in quant], dtype=np.float64)
+    # the same with the approval functions of get_classified_result (:939-970): only approved samples stay in their class
+    stats_depth_appr = {}
+    for nm, fn in (("small_angle", TTBX.approval_func_small_angle), ("large_angle", TTBX.approval_func_large_angle)):
+        cd_a = quiet(TTBX.get_classified_result, result_list, class_name='distance', approval_func=fn)
+        stats_depth_appr[nm] = np.array([[stat(cd_a.get(lb, []), ek, gk) for lb in labels] for _, ek, gk in quant], dtype=np.float64)
+        assert len(cd_a["all"]) == len(result_list)
     # the writers (TEST_TOOLBOX.py:693-820), unmodified, on the same result_list.  The six ndarray fields are
     # dropped from the dicts first (NumPy's multi-line str() of a matrix in a CSV cell is not reproduced), and the
     # NumPy scalars of this generator are turned into the Python floats the script's own draws would be under NumPy 1.x
@@ -325,6 +331,7 @@ def stress_report_case(PNPS, TTBX, tag, B, seed):
             drpy_csv[fkey] = open(os.path.join(tmpd, "d.csv"), newline="").read()
     np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, pattern=pt.pattern_array(pats[0]), uv=uv, gt=gt, R=R, t=t,
                         **{"drpy_csv_" + k: np.array(v) for k, v in drpy_csv.items()},
+                        **{"stats_by_depth_" + k: v for k, v in stats_depth_appr.items()},
                         euler=eul, res_norm=res, report=rep, flags=flags, max_idx=midx, depth_class=depth_class,
                         stats_all=stats_all, stats_by_depth=stats_depth, keys=np.array(keys), result_csv=np.array(result_csv),
                         **{"stat_txt_" + k: np.array(v) for k, v in stat_txt.items()},

@@ -197,6 +197,21 @@ def test_approval_masks():
     assert wl.approval_mask(gt, "large_angle").tolist() == [not x for x in small.tolist()]
     with pytest.raises(ValueError):
         wl.approval_mask(gt, "medium")
+    # against the reference's get_classified_result(approval_func=...) on its own result list: a sample that fails the
+    # approval leaves its distance class (class id -1 for the statistics kernels)
+    g = load_golden("stress_report")
+    cls = g["depth_class"].astype(np.int64)
+    pairs = [(g["report"][:, 10], g["report"][:, 11])] + [(g["report"][:, 12 + i], g["gt"][:, 1 + i]) for i in range(3)]
+    for kind in ("small_angle", "large_angle"):
+        keep = wl.approval_mask(torch.from_numpy(g["gt"]), kind).numpy()
+        ref = g["stats_by_depth_" + kind]
+        for q, (est, true) in enumerate(pairs):
+            for c in range(12):
+                m = (cls == c) & keep
+                if not m.any():
+                    assert np.isnan(ref[q, c, 0])
+                    continue
+                np.testing.assert_allclose(np.array(orc.stats_of(est[m], true[m])), ref[q, c], rtol=1e-12, atol=1e-14)
 
 
 def test_drpy_tables_match_reference(tmp_path):
