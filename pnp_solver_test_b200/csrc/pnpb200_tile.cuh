@@ -1,9 +1,11 @@
-// pnpb200_tile.cuh -- shared-memory row tiles filled by TMA bulk copies (cp.async.bulk + mbarrier).
+// pnpb200_tile.cuh -- shared-memory row tiles filled by TMA (cp.async.bulk[.tensor] + mbarrier).
 //
 // Used by every one-problem-per-thread kernel: a CTA is ONE warp that owns 32 consecutive
-// problems; lane l copies problem l's [n_total, 2] pixel row from HBM into a padded shared-memory
-// row with a single bulk copy.  The row pitch is an odd multiple of 16 bytes, so the per-lane
-// 16-byte reads that follow are bank-conflict free.
+// problems.  RowTile (multi-pass solvers): lane l copies problem l's whole [n_total, 2] pixel row from
+// HBM into a padded shared-memory row with a single bulk copy.  RowStream (single-pass kernels): the
+// rows go through two small buffers chunk by chunk, one 2-D tensor copy per chunk of all 32 rows.
+// The row pitch is an odd multiple of 16 bytes, so the per-lane 16-byte reads that follow are
+// bank-conflict free.
 #pragma once
 #include <stdint.h>
 #include <stdlib.h>
