@@ -399,6 +399,73 @@ def fragility_case(tag, B, seed):
                         uv=w["uv"], gt=w["gt"], perturb=w["perturb"], err=err, **out)
 
 
+def lm_trace_case(PNPS, tag, src_tag):
+    """Per-iteration outputs of the reference's LM (PNP_SOLVER_LIB.py:2642-2702) on the inputs of the golden
+    case `src_tag`: what solve_pnp_LM_single_pattern would return had its loop stopped after k = 1..14
+    iterations.  The loop count is a local literal (:2635), so the unmodified method is run once and
+    EKF2_get_hx_H (:3718) is wrapped on the instance: its k-th call receives the state x_{k-1} (copied; the
+    loop updates it in place) and returns hx(x_{k-1}), from which res_norm of a k-iteration run follows
+    (:2681); R_k, t_k are the reference's own EKF2_reconstruct_R_t_m1 (:3500) of the state of call k + 1
+    (k = 14: the method's return value).  The same for pixels * (1 +/- 1e-13): first_div[b] = the first k
+    at which either perturbed run differs from the unperturbed one by more than 1e-10 in max(|dR|, |dt|/t3)
+    (15 = never) -- up to there a 1e-9 parity statement is well-posed for problem b."""
+    from pnp_solver_test_b200 import patterns as pt
+    g = np.load(os.path.join(OUT, src_tag + ".npz"))
+    K, P, uv = g["K"], g["pattern"], g["uv"]
+    B, n = uv.shape[0], uv.shape[1]
+    keys = ["p%04d" % i for i in range(n)]
+    pat = {k: P[i].reshape(3, 1).copy() for i, k in enumerate(keys)}
+    solver = quiet(PNPS.PNP_SOLVER, K, [{k: P[i].tolist() for i, k in enumerate(keys)}], [1.0], verbose=False)
+
+    def run(uv_b):
+        calls = []
+        orig = solver.EKF2_get_hx_H
+
+        def wrapped(x, B_x, B_y, co_P, *a, **kw):
+            hx, J = orig(x, B_x, B_y, co_P, *a, **kw)
+            z = np.vstack([B_x, B_y])
+            calls.append((np.array(x, dtype=np.float64).copy(), float(np.linalg.norm(z - hx[:2 * n]))))
+            return hx, J
+        solver.EKF2_get_hx_H = wrapped
+        try:
+            r = quiet(solver.solve_pnp_LM_single_pattern, dict_from_uv(keys, uv_b), pat)
+        finally:
+            del solver.EKF2_get_hx_H
+        assert len(calls) == 14
+        Rk, tk, resk = np.zeros((14, 3, 3)), np.zeros((14, 3)), np.zeros(14)
+        for k in range(1, 15):
+            if k < 14:
+                Rr, tr, _ = quiet(solver.EKF2_reconstruct_R_t_m1, calls[k][0].copy())
+            else:
+                Rr, tr = r[0], r[1]
+            Rk[k - 1], tk[k - 1], resk[k - 1] = np.array(Rr), np.array(tr).reshape(3), calls[k - 1][1]
+        assert resk[13] == float(r[6])
+        return Rk, tk, resk
+
+    R_k, t_k, res_k = np.zeros((B, 14, 3, 3)), np.zeros((B, 14, 3)), np.zeros((B, 14))
+    sens_k = np.zeros((B, 14))
+    for b in range(B):
+        R_k[b], t_k[b], res_k[b] = run(uv[b])
+        for sgn in (+1.0, -1.0):
+            R2, t2, _ = run(uv[b] * (1.0 + sgn * 1e-13))
+            d = np.maximum(np.abs(R2 - R_k[b]).reshape(14, -1).max(axis=1), np.abs(t2 - t_k[b]).max(axis=1) / np.abs(t_k[b][:, 2]))
+            sens_k[b] = np.maximum(sens_k[b], np.nan_to_num(d, nan=np.inf))
+    bad = sens_k > 1e-10
+    first_div = np.where(bad.any(axis=1), bad.argmax(axis=1) + 1, 15).astype(np.int32)
+    assert np.abs(R_k[:, 13] - g["R"]).max() == 0.0 and np.abs(t_k[:, 13] - g["t"]).max() == 0.0
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), source=src_tag, K=K, pattern=P, uv=uv, R_k=R_k, t_k=t_k, res_k=res_k,
+                        sens_k=sens_k, first_div=first_div, stable=g["stable"])
+    from oracle import oracle as orc
+    worst = 0.0
+    for k in range(1, 15):
+        o = orc.solve_batch("lm", uv, P, K, params=orc.default_params(max_it=k))
+        m = first_div > k
+        d = np.maximum(np.abs(o["R"] - R_k[:, k - 1]).reshape(B, -1).max(axis=1), np.abs(o["t"] - t_k[:, k - 1]).max(axis=1) / np.abs(t_k[:, k - 1, 2]))
+        worst = max(worst, d[m].max() if m.any() else 0.0)
+    print("%-28s B=%4d | first_div histogram (k=1..15): %s | oracle vs reference over all k < first_div: %.2e"
+          % (tag, B, np.bincount(first_div, minlength=16)[1:].tolist(), worst))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     PNPS, TTBX = load_reference()
@@ -441,6 +508,9 @@ def main():
         stress_report_case(PNPS, TTBX, "stress_report", 256, 61)
     if not only or "fragility" in only:
         fragility_case("fragility", 600, 62)
+    if not only or "lm_trace" in only:
+        for src in ("lm_n15_q", "lm_n15_x", "lm_n68_q", "lm_n68_x"):
+            lm_trace_case(PNPS, src.replace("lm_", "lmtrace_"), src)
     if not only or "euler" in only:
         print("euler fixture:", euler_fixture(), "vectors")
 

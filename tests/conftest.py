@@ -14,7 +14,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 TOL_R = 1e-9          # max |dR| (entries of a rotation are O(1))
 TOL_T = 1e-9          # max |dt| / |t3|
 TOL_EULER_DEG = 1e-7  # degrees; 1e-9 rad is 5.7e-8 deg
-TOL_RES = 1e-9        # |d res| <= TOL_RES * max(res, 1e-6)
+TOL_RES = 1e-9        # |d res| <= TOL_RES * res + TOL_RES_ABS (SURVEY.md 7.2 asks for 1e-9 relative)
+TOL_RES_ABS = 5e-12   # with noise-free pixels res_norm itself is rounding noise (~1e-14 of 2n differences of O(1) numbers): the
+                      # oracle and the CUDA path then differ from the reference by <= 1.1e-12 absolute (measured over all goldens);
+                      # on quantised pixels (res ~ 1e-2) the measured relative difference is <= 8.2e-11
 
 
 def pytest_configure(config):
@@ -65,14 +68,49 @@ def compare_solutions(got, ref, mask=None, iters_mask=None, tol_scale=1.0, check
     dR = np.abs(got["R"].reshape(B, -1) - ref["R"].reshape(B, -1)).max(axis=1)
     dt = np.abs(got["t"] - ref["t"]).max(axis=1) / np.abs(ref["t"][:, 2])
     de = np.abs(got["euler"] - ref["euler"]).max(axis=1)
-    dres = np.abs(got["res_norm"] - ref["res_norm"]) / np.maximum(np.abs(ref["res_norm"]), 1e-6)
+    dres = np.maximum(np.abs(got["res_norm"] - ref["res_norm"]) - TOL_RES_ABS, 0.0) / np.maximum(np.abs(ref["res_norm"]), 1e-300)
     assert m.any()
     assert dR[m].max() <= TOL_R * tol_scale, "R: %g" % dR[m].max()
     assert dt[m].max() <= TOL_T * tol_scale, "t: %g" % dt[m].max()
     assert de[m].max() <= TOL_EULER_DEG * tol_scale, "euler: %g" % de[m].max()
-    assert dres[m].max() <= TOL_RES * tol_scale * 100, "res_norm: %g" % dres[m].max()
+    assert dres[m].max() <= TOL_RES * tol_scale, "res_norm: %g" % dres[m].max()
     if check_iters:
         im = m if iters_mask is None else (m & np.asarray(iters_mask, bool))
         im = im & (np.abs(ref["res_norm"]) > RES_NOISE_FLOOR)
         assert (got["iters"][im] == ref["iters"][im]).all(), "iteration counts differ"
     return dict(dR=dR[m].max(), dt=dt[m].max(), de=de[m].max(), dres=dres[m].max())
+
+
+LM_TRACE_GOLDENS = golden_names("lmtrace_")
+
+
+def compare_lm_trace(solve_k, g, label=""):
+    """Per-iteration parity of LM on EVERY problem, stable or not (PNP_SOLVER_LIB.py:2642-2702).
+
+    g: a tests/golden/lmtrace_*.npz (oracle/make_golden.py::lm_trace_case): what the unmodified reference
+    returns after k = 1..14 iterations (R_k, t_k, res_k) and first_div[b], the first k at which the
+    reference's OWN output moves by more than 1e-10 under a 1e-13 relative pixel perturbation (15 = never).
+    solve_k(k) -> dict(R, t, res_norm) of a run with max_it = k.  For every k < first_div[b] the pose must be
+    and res_norm must be within 1e-9 of the reference's.  Every problem is asserted on at least k = 1, 2."""
+    fd = g["first_div"]
+    B = fd.shape[0]
+    assert fd.min() >= 3
+    worst = np.zeros(3)
+    first_bad = np.full(B, 15, np.int64)                  # first k at which OUR state is > 1e-9 from the reference's
+    for k in range(1, 15):
+        o = solve_k(k)
+        Rk, tk, rk = g["R_k"][:, k - 1], g["t_k"][:, k - 1], g["res_k"][:, k - 1]
+        dR = np.abs(o["R"].reshape(B, -1) - Rk.reshape(B, -1)).max(axis=1)
+        dt = np.abs(o["t"] - tk).max(axis=1) / np.abs(tk[:, 2])
+        dres = np.maximum(np.abs(o["res_norm"] - rk) - TOL_RES_ABS, 0.0) / np.maximum(np.abs(rk), 1e-300)
+        with np.errstate(invalid="ignore"):
+            bad = ~((dR <= TOL_R) & (dt <= TOL_T))
+        first_bad = np.where(bad & (first_bad == 15), k, first_bad)
+        m = mr = fd > k
+        assert dR[m].max() <= TOL_R and dt[m].max() <= TOL_T, "%s k=%d: dR %g dt %g" % (label, k, dR[m].max(), dt[m].max())
+        assert dres[mr].max() <= TOL_RES, "%s k=%d: res_norm %g" % (label, k, dres[mr].max())
+        worst = np.maximum(worst, [dR[m].max(), dt[m].max(), dres[mr].max()])
+    assert (first_bad >= fd).all()
+    print("%s: reference first_div histogram (k = 1..15) %s; first k where this path leaves 1e-9: %s; worst dR %.1e dt %.1e dres %.1e"
+          % (label, np.bincount(fd, minlength=16)[1:].tolist(), np.bincount(first_bad, minlength=16)[1:].tolist(), *worst))
+    return worst
