@@ -59,7 +59,15 @@ def lm_flops_per_solve(n, max_it=14):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_iterate<double, LM> launch over 1,048,576 problems, from the
 # committed `ncu --set full` capture (bench.py cannot run ncu on itself); algorithmic bytes are 456 per problem
 # (29 moments in; state before the last update, R, t, Euler, iters, best out) = 478 MB.
-NCU_TRAFFIC = {"bytes": 243.50e6 + 187.57e6, "problems": 1 << 20, "source": "profiles/r01r_k_iterate_lm68_ncu.md"}
+NCU_TRAFFIC = {"bytes": 243.32e6 + 191.87e6, "problems": 1 << 20, "source": "profiles/r02a_n1024_fp32_ncu.md"}
+
+
+def hbm_peak_gbs():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
 def lm_flops_survey(n, max_it=14):
@@ -225,9 +233,184 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# The other BASELINE configs, FP32 mode and the alternative execution shapes: device-timed one by one after the
+# timed region of the headline, each with the SM clock seen while it ran.
+# ------------------------------------------------------------------------------------------------
+def extra_configs(dev, sampler_index=0, min_ms=200.0):
+    import ctypes as C
+    import torch
+    import pnp_solver_test_b200 as pnp
+    from pnp_solver_test_b200 import _lib, workload as wl, patterns as pt
+
+    sampler = ClockSampler(sampler_index)
+    sampler.start()
+    sampler.wait_first()
+    K = pt.default_camera_matrix()
+    hbm_peak, hbm_src = hbm_peak_gbs()
+
+    def timed(fn, profile=False):
+        """ms per call (CUDA events, >= min_ms of work after two warm-up calls), last output, per-kernel ms, clock sample"""
+        for _ in range(2):
+            out = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = fn(); e1.record()
+        torch.cuda.synchronize()
+        reps = int(max(3, min(400, min_ms / max(e0.elapsed_time(e1), 1e-3))))
+        if profile:
+            _lib.lib.pnpb200_profile_reset()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        kms = None
+        if profile:
+            k3, nc = (C.c_float * 3)(), C.c_int(0)
+            _lib.lib.pnpb200_profile_read(k3, C.byref(nc))
+            kms = [float(k3[0]), float(k3[1]), float(k3[2])]
+        rows = [r for ts, r in sampler.rows if t0 <= ts <= t1]
+        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        clock = {"sm_mhz": float(np.median(sm)) if sm else None, "samples": len(sm), "reps": reps}
+        return e0.elapsed_time(e1) / reps, out, kms, clock
+
+    res = {}
+    B1 = 1 << 20
+    # ---- configs[0]: the reference's live path (solve_pnp -> QEIF on 6 of 15 landmarks, PNP_SOLVER_LIB.py:156, :179)
+    pat15 = pt.get_golden_pattern("Alexander")
+    P15 = pt.pattern_array(pat15)
+    idx6 = [list(pat15).index(k) for k in pt.LM_KEY_LIST_6]
+    w15 = wl.synth_batch(0, B1, P15, K, device=dev)
+    pat15d = torch.from_numpy(P15).to(dev)[None].contiguous()
+    ms, o, _, ck = timed(lambda: pnp.solve_batch("qeif", w15["uv"], pat15d, K, point_index=idx6))
+
+    def stress_step():
+        so = wl.solve_report_batch("qeif", w15["uv"], pat15d, K, w15["gt"], point_index=idx6)
+        return so, wl.error_statistics(so["report"], w15["gt"], lazy="device")
+    ms_full, (so, st), _, ck2 = timed(stress_step)
+    st = st.result()
+    res["configs0_stress_qeif6"] = {
+        "workload": "random_stress_test.py: %d problems, Alexander 15 landmarks, QEIF on the 6-key subset (the reference's live solve_pnp), quantised pixels, FP64" % B1,
+        "solve_ms": ms, "solves_per_s": B1 / ms * 1e3, "mean_iters": float(o["iters"].double().mean()), "clocks": ck,
+        "solve_report_statistics_ms": ms_full, "samples_per_s_incl_report_statistics": B1 / ms_full * 1e3, "clocks_full": ck2,
+        "pass_rate_10cm_10deg": float(so["flags"].all(dim=1).double().mean()), "depth_MAE_cm": 100 * float(st["depth"]["all"][5]),
+        "yaw_MAE_deg": float(st["yaw"]["all"][5])}
+
+    # ---- configs[3]: n = 1024, 100 k problems: the moments and the residual passes against the measured HBM peak
+    n_big, B_big = 1024, 100000
+    Pb = pt.pattern_array(pt.synthetic_pattern(n_big))
+    wb = wl.synth_batch(0, B_big, Pb, K, device=dev)
+    patb = torch.from_numpy(Pb).to(dev)[None].contiguous()
+    prof = pnp.default_params(flags=_lib.FLAG_PROFILE)
+    big = {"workload": "%d problems x %d points, FP64" % (B_big, n_big), "bytes_per_solve_survey": 8 * (2 * n_big + 16) + 8,
+           "hbm_peak_gbs": hbm_peak, "peak_source": hbm_src}
+    for method in ("linear_f2", "lm"):
+        ms, o, kms, ck = timed(lambda: pnp.solve_batch(method, wb["uv"], patb, K, params=prof), profile=True)
+        b0 = B_big * (16 * n_big + 29 * 8)
+        b2 = B_big * (16 * n_big + 12 * 8 + 8)
+        big[method] = {"ms": ms, "solves_per_s": B_big / ms * 1e3, "algorithmic_gbs_whole_solve": B_big * big["bytes_per_solve_survey"] / ms / 1e6,
+                       "frac_whole_solve": B_big * big["bytes_per_solve_survey"] / ms / 1e6 / hbm_peak,
+                       "moments_pass": {"kernel_ms": kms[0], "achieved_gbs": b0 / kms[0] / 1e6, "frac": b0 / kms[0] / 1e6 / hbm_peak},
+                       "iterate_ms": kms[1],
+                       "residual_pass": {"kernel_ms": kms[2], "achieved_gbs": b2 / kms[2] / 1e6, "frac": b2 / kms[2] / 1e6 / hbm_peak},
+                       "clocks": ck}
+    res["configs3_n1024"] = big
+    del wb
+
+    # ---- configs[2]: FP32 against FP64 -- throughput, pipe roofline and accuracy; noise sweep 0..5 px
+    n68 = N_POINTS
+    P68 = pt.pattern_array(pt.synthetic_pattern(n68))
+    fp = {}
+    peaks = {}
+    for code, name in ((0, "f64"), (1, "f32")):
+        pk = C.c_double(0.0)
+        _lib.lib.pnpb200_fma_peak(code, 200000, C.byref(pk))
+        peaks[name] = pk.value / 1e12
+    outs = {}
+    for dt, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+        w68 = wl.synth_batch(0, B1, P68, K, dtype=dt, device=dev)
+        p68 = torch.from_numpy(P68).to(dev).to(dt)[None].contiguous()
+        ms, o, kms, ck = timed(lambda: pnp.solve_batch("lm", w68["uv"], p68, K, params=prof), profile=True)
+        outs["lm_" + name] = o
+        fp["lm68_" + name] = {"ms": ms, "solves_per_s": B1 / ms * 1e3, "kernel_ms": kms, "clocks": ck,
+                              "k_iterate_tflops": lm_flops_iterate() * B1 / kms[1] / 1e9, "fma_peak_tflops": peaks[name],
+                              "k_iterate_frac_of_fma_peak": lm_flops_iterate() * B1 / kms[1] / 1e9 / peaks[name]}
+        w6 = wl.synth_batch(0, B1, P15, K, dtype=dt, device=dev)
+        p6 = pat15d.to(dt)
+        ms, o, _, ck = timed(lambda: pnp.solve_batch("qeif", w6["uv"], p6, K, point_index=idx6))
+        outs["qeif_" + name] = o
+        fp["qeif6_" + name] = {"ms": ms, "solves_per_s": B1 / ms * 1e3, "mean_iters": float(o["iters"].double().mean()), "clocks": ck}
+    for m in ("lm", "qeif"):
+        a, b = outs[m + "_f64"], outs[m + "_f32"]
+        dR = (a["R"] - b["R"].double()).abs().flatten(1).max(dim=1).values
+        dtt = (a["t"] - b["t"].double()).abs().max(dim=1).values / a["t"][:, 2].abs()
+        ok = torch.isfinite(dR) & torch.isfinite(dtt)
+        q = torch.tensor([0.5, 0.9, 0.999], dtype=torch.float64, device=dev)
+        fp[m + "_f32_vs_f64"] = {"dR_median_p90_p999": [float(x) for x in torch.quantile(dR[ok][:1 << 20], q)],
+                                 "dt_over_t3_median_p90_p999": [float(x) for x in torch.quantile(dtt[ok][:1 << 20], q)],
+                                 "same_iteration_count_frac": float((a["iters"] == b["iters"]).double().mean())}
+    del outs
+    sweep = {"workload": "LM_noise_test.py: yaw 0, t = (0, 0, 1), grid 30/112 px, noise sigma x 30/112 px, %d draws per sigma, QEIF-6" % B1,
+             "sigma": [], "f64_yaw_MAE_deg": [], "f32_yaw_MAE_deg": [], "f64_solves_per_s": [], "f32_solves_per_s": []}
+    qg = 30.0 / 112.0
+    for sg in np.linspace(0.0, 5.0, 6):
+        sweep["sigma"].append(float(sg))
+        for dt, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+            cfg = pnp.default_synth(seed=42, angle_range_deg=0.0, yaw_center_deg=0.0, depth_min_m=1.0, depth_max_m=1.0,
+                                    fov_max_deg=0.0, is_quantized=1, quantize_q=qg, noise_sigma_px=float(sg) * qg)
+            ws = wl.synth_batch(0, B1, P15, K, cfg=cfg, dtype=dt, device=dev)
+            p6 = pat15d.to(dt)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pnp.solve_batch("qeif", ws["uv"], p6, K, point_index=idx6)
+            e0.record()
+            o = pnp.solve_batch("qeif", ws["uv"], p6, K, point_index=idx6)
+            e1.record()
+            torch.cuda.synchronize()
+            sweep[name + "_yaw_MAE_deg"].append(float(o["euler"][:, 1].double().abs().mean()))
+            sweep[name + "_solves_per_s"].append(B1 / e0.elapsed_time(e1) * 1e3)
+    fp["noise_sweep"] = sweep
+    res["configs2_fp32_vs_fp64"] = fp
+
+    # ---- the execution shapes head to head on the headline workload (north_star: one problem per warp; default: moments)
+    w68 = wl.synth_batch(0, B1, P68, K, device=dev)
+    p68 = torch.from_numpy(P68).to(dev)[None].contiguous()
+    shapes = {}
+    for name, mp in (("MAP_MOMENT (default: moments -> O(1) iterations -> point-wise residual, one problem per thread)", _lib.MAP_MOMENT),
+                     ("MAP_THREAD (one problem per thread, every iteration point-wise)", _lib.MAP_THREAD),
+                     ("MAP_WARP (one problem per warp, shuffle-reduced normal equations)", _lib.MAP_WARP)):
+        prm = pnp.default_params(mapping=mp)
+        ms, o, _, ck = timed(lambda: pnp.solve_batch("lm", w68["uv"], p68, K, params=prm))
+        shapes[name] = {"ms": ms, "solves_per_s": B1 / ms * 1e3, "clocks": ck}
+    res["mappings_lm68_1Mi"] = shapes
+
+    # ---- configs[4]: the per-GPU shard of the 64 M-problem batch on 8 GPUs (8 Mi problems, 9.1 GB of pixels)
+    B8 = 1 << 23
+    w8 = wl.synth_batch(0, B8, P68, K, device=dev)
+
+    def shard_step():
+        so = wl.solve_report_batch("lm", w8["uv"], p68, K, w8["gt"])
+        return wl.error_statistics(so["report"], w8["gt"], lazy="device")
+    ms, st, _, ck = timed(shard_step)
+    res["configs4_shard_8Mi"] = {"workload": "one GPU's shard of the 64 Mi x 68-point batch over 8 GPUs: %d problems, LM FP64 + report + statistics" % B8,
+                                 "ms": ms, "solves_per_s": B8 / ms * 1e3, "clocks": ck, "n_stat": float(st.result()["depth"]["all"][0])}
+    sampler.stop()
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def _largest_divisor(k, cap):
+    for d in range(min(k, cap), 0, -1):
+        if k % d == 0:
+            return d
+    return 1
+
+
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import pnp_solver_test_b200 as pnp
@@ -251,43 +434,41 @@ def run_ours(args):
     w = wl.synth_batch(rank * B, B, P, K, cfg=pnp.default_synth(seed=42), device=dev)
     uv, gt = w["uv"], w["gt"]
     torch.cuda.synchronize()
-
-    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     last = {}
 
-    # With several ranks the report and the statistics of a step (two small kernels, three tiny all-reduces whose cost
-    # is launch latency) go to a second stream: they need the step's solve, but the next step's solve does not need
-    # them, so the collectives' latency hides under the next solve instead of idling every GPU of the job.
+    # With several ranks the statistics of a step (two small kernels, two tiny exchanges whose cost is launch latency) go
+    # to a second stream: they need the step's report, but the next step's solve does not need them, so the collectives'
+    # latency hides under the next solve instead of idling every GPU of the job.
     overlap = world > 1 and not args.no_overlap
-    main_stream = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(device=dev) if overlap else None
+    keep = []
 
-    def report_and_stats(out):
-        rep = wl.report_batch(P, uv, K, out["R"], out["t"], out["euler"], gt)
-        last["stats"] = wl.error_statistics(rep["report"], gt, lazy=True)   # two all-reduce phases; D2H of the sums is async
-        last["pass"] = rep["flags"]
+    def stats_of(out):
+        last["stats"] = wl.error_statistics(out["report"], gt, lazy="device")   # two kernels, two exchange phases, nothing on the host
+        last["pass"] = out["flags"]
 
-    def step(i=None):
-        if i is not None:
-            ev_a[i].record()
-        out = pnp.solve_batch(METHOD, uv, pat, K, params=params)
-        if i is not None:
-            ev_b[i].record()
+    def step():
+        # solve (pattern constants, moments, 14 LM iterations + SO(3) projection + Euler) and the error report with the
+        # residual pass folded in: one library call, four kernels
+        out = wl.solve_report_batch(METHOD, uv, pat, K, gt, params=params)
         if overlap:
-            side.wait_stream(main_stream)
+            cur = torch.cuda.current_stream(dev)
+            side.wait_stream(cur)
             with torch.cuda.stream(side):
-                report_and_stats(out)
-            for v in out.values():
-                if torch.is_tensor(v):
-                    v.record_stream(side)                  # allocated on the main stream, last read on the side stream
+                stats_of(out)
+            if torch.cuda.is_current_stream_capturing():
+                keep.append(out)                           # inside a capture freed blocks are reused at once: keep every step's outputs
+            else:
+                for v in out.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(side)              # allocated on the solve stream, last read on the side stream
         else:
-            report_and_stats(out)
+            stats_of(out)
         return out
 
     def join_side():
         if overlap:
-            main_stream.wait_stream(side)
+            torch.cuda.current_stream(dev).wait_stream(side)
 
     def barrier():
         if world > 1:
@@ -301,34 +482,88 @@ def run_ours(args):
         step()
     join_side()
     barrier()
+
+    # ---- the K timed steps as replays of a CUDA graph of S steps (kernels, the side-stream fork / join and the NCCL
+    # exchanges captured once): the timed region then holds no Python, no allocator and no launch latency of the host, which
+    # is what separated 8 ranks sharing one host from a single rank.  Falls back to eager launches if the capture fails.
+    S = _largest_divisor(args.steps, 20)
+    graph, graph_note, per_graph_launches = None, "off (--no-graph)", 0
+    if not args.no_graph:
+        try:
+            _lib.check(_lib.lib.pnpb200_profile_reset(), "pnpb200_profile_reset")
+            cap_stream = torch.cuda.Stream(device=dev)
+            l0 = int(_lib.lib.pnpb200_launch_count())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cap_stream):
+                for _ in range(S):
+                    step()
+                join_side()
+            per_graph_launches = int(_lib.lib.pnpb200_launch_count()) - l0
+            g.replay()                                      # one untimed replay: graph upload, first-use costs
+            torch.cuda.synchronize()
+            graph, graph_note = g, "on: %d steps per graph" % S
+        except Exception as e:                              # noqa: BLE001
+            graph, graph_note = None, "off (capture failed: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
+            torch.cuda.synchronize()
+    barrier()
+    if world > 1:                                           # device-side rendezvous: every GPU leaves this all-reduce together, so the
+        dist.all_reduce(torch.zeros(1, device=dev))         # timed region starts aligned across ranks whatever the hosts' skew
     sampler.mark_begin()
     l0 = int(_lib.lib.pnpb200_launch_count())               # kernels the library launches, counted by the library itself
-    _lib.check(_lib.lib.pnpb200_profile_reset(), "pnpb200_profile_reset")
+    if graph is None:
+        _lib.check(_lib.lib.pnpb200_profile_reset(), "pnpb200_profile_reset")
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for i in range(args.steps):
-        step(i)
-    join_side()                                           # the last steps' reports and statistics are inside the timed region
+    if graph is not None:
+        for _ in range(args.steps // S):
+            graph.replay()
+    else:
+        for _ in range(args.steps):
+            step()
+        join_side()                                         # the last steps' statistics are inside the timed region
     t_end.record()
     barrier()
     sampler.mark_end()
-    import ctypes as C
     kms = (C.c_float * 3)()
     ncall = C.c_int(0)
-    _lib.check(_lib.lib.pnpb200_profile_read(kms, C.byref(ncall)), "pnpb200_profile_read")
-    params.flags = 0
-    launches = int(_lib.lib.pnpb200_launch_count()) - l0
+    kernel_times = "CUDA events around each kernel inside the timed region" + \
+                   (" (event-record nodes of the graph: the %d steps of its last replay)" % S if graph is not None else "")
+    rc = _lib.lib.pnpb200_profile_read(kms, C.byref(ncall))
+    if rc != 0 or ncall.value == 0 or not (kms[1] > 0):     # events recorded by graph nodes could not be read: time the kernels eagerly
+        _lib.check(_lib.lib.pnpb200_profile_reset(), "pnpb200_profile_reset")
+        for _ in range(S):
+            step()
+        join_side()
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib.pnpb200_profile_read(kms, C.byref(ncall)), "pnpb200_profile_read")
+        kernel_times = "CUDA events around each kernel, %d eager steps right after the timed region" % S
+    launches = per_graph_launches * (args.steps // S) if graph is not None else int(_lib.lib.pnpb200_launch_count()) - l0
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
-    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in zip(ev_a, ev_b)]))
+    ms_kernel = float(kms[0]) + float(kms[1]) + float(kms[2])
     tt = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_total, ms_kernel_max = float(tt[0]), float(tt[1])
     value = world * B * args.steps / (ms_total * 1e-3)
+    params.flags = 0
+    st = last["stats"].result()
+    pass_rate = float(last["pass"].all(dim=1).double().mean())
+
+    def timed_host(fn, k):
+        """wall-clock seconds per call of fn over k calls, barrier on both sides, max over ranks"""
+        barrier()
+        t_ = time.perf_counter()
+        for _ in range(k):
+            fn()
+        barrier()
+        tt_ = torch.tensor([time.perf_counter() - t_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        return float(tt_[0]) / k
 
     # ---- end to end through the host-buffer entry point (pinned host memory, copies timed)
-    e2e = None
+    e2e = e2e_i16 = None
     if not args.no_e2e:
         host_uv = torch.empty((B, n, 2), dtype=torch.float64).pin_memory()
         host_uv.copy_(uv)
@@ -344,62 +579,51 @@ def run_ours(args):
             pack_threads = 0
         pipe = pnp.HostPipeline(torch.float64, chunk_problems=args.chunk, n_total=n, n_patterns=1, n_streams=3, device=dev,
                                 pack_threads=pack_threads)
-        def timed_e2e(k):
-            barrier()
-            t_ = time.perf_counter()
-            for _ in range(k):
-                pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)   # blocks until results are on the host
-            barrier()
-            tt_ = torch.tensor([time.perf_counter() - t_], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
-            return float(tt_[0]) / k
-
+        solve_host = lambda: pipe.solve(METHOD, host_uv, host_pat, K, outs)     # blocks until the results are on the host
         pack_choice = "off"
         if pack_threads:
             # warm-up decides: packing trades PCIe bytes for host memory traffic, which loses when all the ranks of a box
             # share a host memory system that is already the limit (8 GPUs); every rank takes the same decision
-            timed_e2e(1)
-            t_on = timed_e2e(2)
+            timed_host(solve_host, 1)
+            t_on = timed_host(solve_host, 2)
             pipe.set_packing(0)
-            timed_e2e(1)
-            t_off = timed_e2e(2)
+            timed_host(solve_host, 1)
+            t_off = timed_host(solve_host, 2)
             pack_choice = "on (warm-up: %.1f ms packed, %.1f ms plain)" % (1e3 * t_on, 1e3 * t_off)
             if t_on < t_off:
                 pipe.set_packing(pack_threads)
             else:
                 pack_choice = "off (warm-up: %.1f ms packed, %.1f ms plain)" % (1e3 * t_on, 1e3 * t_off)
                 pack_threads = 0
-        for _ in range(2):
-            pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)
-        barrier()
-        t0 = time.perf_counter()
+        timed_host(solve_host, 2)
         e_steps = max(1, min(args.steps, 5))
-        for _ in range(e_steps):
-            pipe.solve(METHOD, host_uv, host_pat, K, outs, params=params)   # blocks until results are on the host
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = timed_host(solve_host, e_steps)
         packed_chunks, n_chunks = pipe.last_packed()
         chunk_bytes = args.chunk * n * 2 * 8
         host_bytes = host_uv.numel() * 8
         h2d = host_bytes - min(packed_chunks * chunk_bytes, host_bytes) * 3 // 4      # a packed chunk travels as int16: a quarter
         d2h = sum(v.numel() * v.element_size() for v in outs.values())
-        # what bounds it: the same pixels copied host -> device alone (pinned, one cudaMemcpyAsync per step)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        uv.copy_(host_uv, non_blocking=True)
-        barrier()
-        c0.record()
-        for _ in range(3):
-            uv.copy_(host_uv, non_blocking=True)
-        c1.record()
-        torch.cuda.synchronize()
-        copy_ms = c0.elapsed_time(c1) / 3
-        h2d_fp64 = host_bytes
-        e2e_ms = 1e3 * float(tt[0]) / e_steps
-        e2e = {"value": world * B * e_steps / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        assert torch.equal(outs["iters"], torch.full((B,), 14, dtype=torch.int32))
+        ref_R = outs["R"].clone()
+
+        # what bounds it: the same pixels copied host -> device alone by ALL ranks at once (pinned, one cudaMemcpyAsync per step)
+        def copy_alone(src):
+            dst = torch.empty(src.shape, dtype=src.dtype, device=dev)
+            dst.copy_(src, non_blocking=True)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            t_ = torch.tensor([c0.elapsed_time(c1) / 3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            return float(t_[0])
+        copy_ms = copy_alone(host_uv)
+        e2e_ms = 1e3 * e2e_s
+        e2e = {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e_steps, "ms_per_step": e2e_ms, "numa": numa,
                "api": "pnpb200_solve_batch_host via HostPipeline.solve (pinned FP64 host buffers, %d-problem chunks, 3 streams%s)"
                       % (args.chunk, "; packed pixel transfer with %d host threads: %d of the %d chunks of the last step were whole "
@@ -407,11 +631,39 @@ def run_ours(args):
                          if pack_threads else ""),
                "host_pixel_bytes_per_step": host_bytes, "pack_threads": pack_threads, "packed_chunks": [packed_chunks, n_chunks],
                "packing": pack_choice,
-               "bound": {"what": "PCIe host->device copy of the FP64 pixels as they are (what the pipeline does without packing)",
-                         "h2d_copy_alone_ms": copy_ms, "h2d_copy_alone_gbs": h2d_fp64 / (copy_ms * 1e-3) / 1e9,
-                         "e2e_over_copy": e2e_ms / copy_ms}}
-        assert torch.equal(outs["iters"], torch.full((B,), 14, dtype=torch.int32))
+               "bound": {"what": "host->device copy of the FP64 pixels as they are, all %d rank(s) copying at the same time (max over ranks)" % world,
+                         "h2d_copy_alone_ms": copy_ms, "h2d_copy_alone_gbs": host_bytes / (copy_ms * 1e-3) / 1e9,
+                         "e2e_over_copy": e2e_ms / copy_ms,
+                         "solves_per_s_if_copy_bound": world * B / (copy_ms * 1e-3)}}
+
+        # ---- the same end to end for a caller that keeps its detections as int16 (what a landmark detector delivers; the
+        # reference rounds its pixels itself): pnpb200_solve_batch_host_px, no host pass over the pixels at all
+        pipe.set_packing(0)
+        variants = {}
+        for name, wc in (("pinned", False), ("write_combined", True)):
+            hb = pnp.host_buffer((B, n, 2), torch.int16, write_combined=wc)
+            hb.copy_(host_uv.to(torch.int16))
+            fn = lambda: pipe.solve(METHOD, hb, host_pat, K, outs)
+            timed_host(fn, 2)
+            variants[name] = timed_host(fn, e_steps)
+            assert torch.equal(outs["R"].view(torch.int64), ref_R.view(torch.int64))   # bit-identical to the FP64 hand-over
+            if name == "write_combined":
+                copy16_ms = copy_alone(hb)
+            del hb
+        best = min(variants, key=variants.get)
+        e2e_i16 = {"value": world * B / variants[best], "unit": UNIT, "ms_per_step": 1e3 * variants[best], "steps": e_steps,
+                   "h2d_bytes_per_step": B * n * 2 * 2, "d2h_bytes_per_step": d2h, "host_buffer": best,
+                   "ms_per_step_by_host_buffer": {k: 1e3 * v for k, v in variants.items()},
+                   "api": "pnpb200_solve_batch_host_px(PNPB200_PIXEL_I16) via HostPipeline.solve: int16 pixels cross PCIe as they are and are "
+                          "widened on the device; results bit-identical to the FP64 hand-over (asserted)",
+                   "bound": {"h2d_copy_alone_ms": copy16_ms, "h2d_copy_alone_gbs": B * n * 4 / (copy16_ms * 1e-3) / 1e9}}
         pipe.close()
+        del host_uv, outs
+
+    # ---- the other BASELINE configs and the alternative execution shapes, outside the timed region, each device-timed
+    extra = None
+    if not args.no_extra and world == 1:
+        extra = extra_configs(dev, sampler_index=local)
 
     if rank != 0:
         if world > 1:
@@ -424,32 +676,28 @@ def run_ours(args):
     _lib.check(_lib.lib.pnpb200_fma_peak(0, 200000, C.byref(peak)), "pnpb200_fma_peak")
     fl = lm_flops_iterate()
     achieved_tf = fl * B / (ms_it * 1e-3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    hbm_peak, hbm_src = hbm_peak_gbs()
     mom_bytes = (2 * n * 8 + 29 * 8) * B          # read every pixel once, write 29 moments
-    res_bytes = (2 * n * 8 + 12 * 8 + 8) * B      # read every pixel and the 12-double state, write res_norm
+    rr_bytes = (2 * n * 8 + 12 * 8 + 15 * 8 + 4 * 8 + 8 + 16 * 8 + 28) * B   # pixels, state, pose, Euler, GT in; res_norm, report, flags, max_idx out
+    rr_flop = (34 + 120) * n                       # residual 34 flop/pt + report ~60 FP64 instructions/pt
     roofline = {"bound": "fp64_pipe", "kernel": "k_iterate<double, LM>", "achieved": achieved_tf, "peak": peak.value / 1e12,
                 "unit": "TFLOP/s", "frac": achieved_tf / (peak.value / 1e12),
                 "traffic": NCU_TRAFFIC["bytes"] * B / NCU_TRAFFIC["problems"], "traffic_unit": "bytes per launch (ncu dram read + write, %s)" % NCU_TRAFFIC["source"],
                 "algorithmic_bytes": 456 * B,
                 "peak_source": "measured in this run by pnpb200_fma_peak (FP64 FMA microbenchmark; MEASURED_PEAKS.json has no FP64 figure)",
-                "flops_per_solve": fl, "kernel_ms": ms_it, "timed_calls": int(ncall.value),
-                "solve_ms": ms_kernel_max, "flops_per_solve_whole_path": lm_flops_per_solve(n),
+                "flops_per_solve": fl, "kernel_ms": ms_it, "timed_calls": int(ncall.value), "kernel_times": kernel_times,
+                "solve_report_kernels_ms": ms_kernel_max, "flops_per_solve_whole_path": lm_flops_per_solve(n),
                 "flops_per_solve_survey_formula": lm_flops_survey(n),
                 "other_kernels": [
                     {"kernel": "k_stream_chunk<double, LM, 0> (moments)", "bound": "hbm", "kernel_ms": ms_mom,
                      "achieved": mom_bytes / (ms_mom * 1e-3) / 1e9 if ms_mom > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (mom_bytes / (ms_mom * 1e-3) / 1e9 / hbm_peak) if ms_mom > 0 else None, "peak_source": hbm_src},
-                    {"kernel": "k_stream_chunk<double, LM, 1> (residual)", "bound": "hbm", "kernel_ms": ms_res,
-                     "achieved": res_bytes / (ms_res * 1e-3) / 1e9 if ms_res > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": (res_bytes / (ms_res * 1e-3) / 1e9 / hbm_peak) if ms_res > 0 else None, "peak_source": hbm_src}]}
+                    {"kernel": "k_report_chunk<double, 1> (error report with the LM residual pass folded in: the pixel rows are read once for both)",
+                     "bound": "fp64_pipe (HBM second)", "kernel_ms": ms_res,
+                     "achieved": rr_bytes / (ms_res * 1e-3) / 1e9 if ms_res > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": (rr_bytes / (ms_res * 1e-3) / 1e9 / hbm_peak) if ms_res > 0 else None, "peak_source": hbm_src,
+                     "fp64_tflops_algorithmic": rr_flop * B / (ms_res * 1e-3) / 1e12 if ms_res > 0 else None}]}
     cpu = cpu_baseline_block() if (world == 1 and not args.no_cpu) else None
-    st = last["stats"].result()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -457,15 +705,18 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: %d problems x %d-point face pattern per GPU, LM refinement (14 it), FP64, "
                                "random_stress_test pose distribution, integer-quantised pixels" % (B, n),
                    "method": METHOD, "n_points": n, "problems_per_gpu": B, "global_problems": world * B,
-                   "step": "solve (moments, iterate, residual kernels) + error-report kernel + error statistics (two all-reduce phases)"
-                           + ("; report + statistics of step i run on a second stream under the solve of step i + 1, all K inside the timed region"
+                   "step": "pnpb200_solve_report_batch (pattern constants, moments, iterate, error report + residual: four kernels) + "
+                           "classification + error statistics (two kernels, two exchange phases: all_reduce SUM, all_gather of the phase-2 partials)"
+                           + ("; the statistics of step i run on a second stream under the solve of step i + 1, all K inside the timed region"
                               if overlap else ""),
+                   "cuda_graph": graph_note,
                    "l2": "inputs are %.2f GB per step, larger than the 126 MB L2" % (uv.numel() * 8 / 1e9),
                    "parallelism": "problems sharded by global index, no solve-path traffic"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "quality": {"pass_rate_10cm_10deg": float(last["pass"].all(dim=1).double().mean()),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_i16": e2e_i16, "gpu_launches": launches, "clocks": clocks,
+        "quality": {"pass_rate_10cm_10deg": pass_rate,
                     "depth_MAE_m": float(st["depth"]["all"][5]), "yaw_MAE_deg": float(st["yaw"]["all"][5]),
                     "n_stat": float(st["depth"]["all"][0])},
+        "extra_configs": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -486,6 +737,8 @@ def main():
     ap.add_argument("--pack-threads", type=int, default=-1,
                     help="host threads packing whole-pixel chunks to int16 for the e2e transfer (-1: cpus/ranks - 1, at most 15; 0: off)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs block (other BASELINE configs, FP32, mappings)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -172,12 +172,42 @@ int pnpb200_pipeline_last_packed(const pnpb200_pipeline* p, int64_t* packed_chun
  * lossless; -0.0 counts as 0), 0 if not (dst is then not to be used), < 0 on a bad argument.
  */
 int pnpb200_pack_i16(int dtype, const void* src, int64_t n_values, int16_t* dst, int n_threads);
+/* params->workspace must be NULL here (EINVAL otherwise): the chunks run concurrently and the pipeline owns one scratch per stream */
 int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n,
                              const void* uv_host, const void* pattern_host,
                              const int32_t* point_index, const double* K,
                              const pnpb200_params* params,
                              void* R, void* t, void* euler_deg, void* res_norm,
                              int32_t* iters, int32_t* best_pattern);
+
+/*
+ * The same for callers that hold their detections in a narrow type.  Landmark detectors deliver whole pixels
+ * (the reference rounds them itself: is_quantized=True, PNP_SOLVER_LIB.py:4549-4552, random_stress_test.py:290)
+ * and only the reference's dict-of-float64 convention makes them 16 bytes per landmark.  uv_host is
+ * [B, n_total, 2] of pixel_type; a half (float32) or a quarter (int16 / uint16) of the bytes cross PCIe and the
+ * values are widened on the device to the pipeline's arithmetic type -- exactly, so the results are bit-identical
+ * to those of the same values handed over in the pipeline's dtype.  PNPB200_PIXEL_NATIVE = pnpb200_solve_batch_host.
+ * No host pass, no packing thread: nothing on this path touches the pixels on the CPU.
+ */
+#define PNPB200_PIXEL_NATIVE 0   /* the pipeline's dtype */
+#define PNPB200_PIXEL_I16    1
+#define PNPB200_PIXEL_U16    2
+#define PNPB200_PIXEL_F32    3   /* float32 pixels, arithmetic in the pipeline's dtype */
+int pnpb200_solve_batch_host_px(pnpb200_pipeline* p, int method, int64_t B, int n, int pixel_type,
+                                const void* uv_host, const void* pattern_host,
+                                const int32_t* point_index, const double* K,
+                                const pnpb200_params* params,
+                                void* R, void* t, void* euler_deg, void* res_norm,
+                                int32_t* iters, int32_t* best_pattern);
+
+/*
+ * Page-locked host memory for the buffers of the two calls above (cudaHostAlloc): copies from / to pinned memory
+ * run asynchronously at full PCIe rate, pageable buffers are staged by the driver and block the submitting thread.
+ * write_combined = 1 for buffers the CPU only WRITES (the pixels): not snooped, faster for the device to read,
+ * very slow for the CPU to read back -- do not use it for the result buffers or with the packed transfer.
+ */
+int pnpb200_host_alloc(void** out, int64_t bytes, int write_combined);
+int pnpb200_host_free(void* ptr);
 
 /*
  * Euler <-> R, batched on the device.
@@ -233,6 +263,23 @@ int pnpb200_report_batch(int dtype, int64_t B, int n, const void* pattern, const
                          const double* K, const void* R, const void* t, const void* euler_deg,
                          const double* gt, const double* bounds,
                          double* report, int32_t* flags, int32_t* max_idx, void* stream);
+
+/*
+ * The solve and the error report of the same problems in one call: pnpb200_solve_batch (one pattern) followed by
+ * pnpb200_report_batch_strided over all n_total landmarks -- the body of the loop of random_stress_test.py:322-377
+ * (solve_pnp, then compare_result_and_generate_result_dict on its result).  When the solve runs as the moment
+ * mapping (LM / linear F2 / LM+, all landmarks) its last pass -- res_norm at the stored state, point by point -- is
+ * folded into the report kernel, so the pixel rows are read twice per problem (moments; residual + report) instead
+ * of three times; the results are those of the two separate calls.  Every other method / mapping runs the two calls
+ * back to back.  R, t, euler_deg, gt and report are required; res_norm, iters, flags, max_idx may be NULL.
+ */
+int pnpb200_solve_report_batch(int method, int dtype, int64_t B, int n_total, int n,
+                               const void* uv, const void* pattern, const int32_t* point_index, const double* K,
+                               const pnpb200_params* params,
+                               void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters,
+                               const double* gt, const double* bounds,
+                               double* report, int64_t report_stride_problem, int64_t report_stride_column,
+                               int32_t* flags, int32_t* max_idx, void* stream);
 
 /*
  * The same report into a strided array: value k of problem b goes to

@@ -566,7 +566,7 @@ ORACLE_API int pnp_oracle_eif2(int n, const double *P, const double *uv, const d
     double *by = bx + n, *hx = by + n, *J = hx + Z, *qinv = J + (size_t)Z * 12, *z = qinv + Z;
     double x[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1 };   /* :2058-2063 */
     double Omega[144], Sigma[144], Rk[144], tmp[144], zeta[12], work[144 + 12 + 144];
-    double res = 1e5, res_old = 1e-7;                         /* :2101-2102 */
+    double res = 1e5, res_old = prm->res_old0;                /* :2101-2102 (1e-7) */
 
     inv3(K, Kinv);
     normalise(n, uv, Kinv, bx, by);
@@ -584,7 +584,7 @@ ORACLE_API int pnp_oracle_eif2(int n, const double *P, const double *uv, const d
         qinv[r] = 1.0 / q;
     }
     for (i = 0; i < 144; ++i) Omega[i] = 0.0;
-    for (i = 0; i < 12; ++i) Omega[i * 12 + i] = 1e-5;        /* :2067 */
+    for (i = 0; i < 12; ++i) Omega[i * 12 + i] = prm->omega0;  /* :2067 (1e-5) */
     pinv_svd(12, 12, Omega, Sigma, work);                     /* eif_Omega_pinv :2068 */
 
     while (it < prm->max_it) {                                /* :2107 */

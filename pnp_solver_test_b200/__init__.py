@@ -14,10 +14,10 @@ from .patterns import get_golden_pattern, synthetic_pattern, LM_KEY_LIST_6  # no
 __version__ = "0.1.0"
 
 _LAZY = {
-    "_lib": ("._lib", None), "solver": (".solver", None), "workload": (".workload", None), "toolbox": (".toolbox", None),
+    "_lib": ("._lib", None), "solver": (".solver", None), "workload": (".workload", None),
     "METHODS": ("._lib", "METHODS"), "default_params": ("._lib", "default_params"),
     "default_synth": ("._lib", "default_synth"), "PnpB200Error": ("._lib", "PnpB200Error"),
-    "PNP_SOLVER": (".solver", "PNP_SOLVER"), "HostPipeline": (".solver", "HostPipeline"),
+    "PNP_SOLVER": (".solver", "PNP_SOLVER"), "HostPipeline": (".solver", "HostPipeline"), "host_buffer": (".solver", "host_buffer"),
     "solve_batch": (".solver", "solve_batch"), "R_from_euler_batch": (".solver", "R_from_euler_batch"),
     "euler_from_R_batch": (".solver", "euler_from_R_batch"), "project_batch": (".solver", "project_batch"),
 }

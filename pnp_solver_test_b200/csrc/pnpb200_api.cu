@@ -208,19 +208,16 @@ int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns
     return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
 }
 
-int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
-                        int n_patterns, const int32_t* point_index, const double* K, const pnpb200_params* params,
-                        void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters, int32_t* best_pattern,
-                        void* stream)
+static int solve_batch_impl(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
+                            int n_patterns, const int32_t* point_index, const double* K, const pnpb200_params& prm,
+                            void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters, int32_t* best_pattern,
+                            cudaStream_t st)
 {
     if (B < 0 || n_total < 1 || n < 1 || (!point_index && n != n_total) || !uv || !pattern || !K) return PNPB200_EINVAL;
     if (((uintptr_t)uv & 15u) != 0) return PNPB200_EINVAL;   // rows are staged with 16-byte bulk copies / vector loads
     if (n_patterns < 1 || n_patterns > PNPB200_MAX_PATTERNS) return PNPB200_EINVAL;
     if (method < 0 || method > 5 || (dtype != PNPB200_DTYPE_F64 && dtype != PNPB200_DTYPE_F32)) return PNPB200_EINVAL;
     if (B == 0) return PNPB200_OK;
-    pnpb200_params prm;
-    if (params) prm = *params; else fill_default_params(&prm);
-    cudaStream_t st = (cudaStream_t)stream;
     int32_t* idx_dev = nullptr;
     if (point_index) {
         for (int i = 0; i < n; ++i)
@@ -242,6 +239,71 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, co
     return rc;
 }
 
+int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
+                        int n_patterns, const int32_t* point_index, const double* K, const pnpb200_params* params,
+                        void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters, int32_t* best_pattern,
+                        void* stream)
+{
+    pnpb200_params prm;
+    if (params) prm = *params; else fill_default_params(&prm);
+    prm.flags &= ~PNP_FLAG_INTERNAL_NO_RESIDUAL;
+    return solve_batch_impl(method, dtype, B, n_total, n, uv, pattern, n_patterns, point_index, K, prm, R, t, euler_deg, res_norm,
+                            iters, best_pattern, (cudaStream_t)stream);
+}
+
+int pnpb200_solve_report_batch(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
+                               const int32_t* point_index, const double* K, const pnpb200_params* params,
+                               void* R, void* t, void* euler_deg, void* res_norm, int32_t* iters,
+                               const double* gt, const double* bounds, double* report, int64_t report_stride_problem,
+                               int64_t report_stride_column, int32_t* flags, int32_t* max_idx, void* stream)
+{
+    if (!R || !t || !euler_deg || !gt || !report) return PNPB200_EINVAL;          // the report reads the pose
+    pnpb200_params prm;
+    if (params) prm = *params; else fill_default_params(&prm);
+    prm.flags &= ~PNP_FLAG_INTERNAL_NO_RESIDUAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    // One pass over the pixel rows for res_norm AND the report when the solve runs as the moment mapping over all
+    // landmarks with chunk-streamed rows; every other shape is the two calls back to back.
+    const bool moment = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS) &&
+                        (prm.mapping == PNPB200_MAP_AUTO || prm.mapping == PNPB200_MAP_MOMENT);
+    const bool fuse = moment && !point_index && n == n_total && res_norm && B > 0 && ((prm.flags >> 8) & 0xff) != 9 &&
+                      (dtype == PNPB200_DTYPE_F64 || dtype == PNPB200_DTYPE_F32) && report_can_fuse(dtype, n_total);
+    if (!fuse) {
+        const int rc = solve_batch_impl(method, dtype, B, n_total, n, uv, pattern, 1, point_index, K, prm, R, t, euler_deg, res_norm,
+                                        iters, nullptr, st);
+        if (rc != PNPB200_OK) return rc;
+        return report_launch(dtype, B, n_total, pattern, uv, K, R, t, euler_deg, gt, bounds, report, report_stride_problem,
+                             report_stride_column, flags, max_idx, nullptr, st);
+    }
+    const size_t esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
+    const size_t ws_bytes = ((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)B + PNP_PATC) * esz;
+    void* ws = nullptr;
+    const bool own_ws = !(prm.workspace && prm.workspace_bytes >= (int64_t)ws_bytes);
+    if (own_ws) {
+        PNP_CUDA_OK(cudaMallocAsync(&ws, ws_bytes, st));
+        prm.workspace = ws; prm.workspace_bytes = (int64_t)ws_bytes;
+    }
+    prm.flags |= PNP_FLAG_INTERNAL_NO_RESIDUAL;
+    int rc = solve_batch_impl(method, dtype, B, n_total, n, uv, pattern, 1, nullptr, K, prm, R, t, euler_deg, res_norm, iters,
+                              nullptr, st);
+    if (rc == PNPB200_OK) {
+        ReportFuse f;
+        f.res_mode = (method == PNPB200_METHOD_LINEAR_F2) ? 2 : 1;
+        f.tail = (const char*)prm.workspace + (size_t)PNP_NMOM * (size_t)B * esz;
+        f.ld = B;
+        f.res = res_norm;
+        double Kinv[9];
+        host_inv3(K, Kinv);
+        for (int e = 0; e < 6; ++e) f.kinv[e] = Kinv[e];
+        const int slot = (prm.flags & PNPB200_FLAG_PROFILE) ? g_prof.last() : -1;
+        rc = report_launch(dtype, B, n_total, pattern, uv, K, R, t, euler_deg, gt, bounds, report, report_stride_problem,
+                           report_stride_column, flags, max_idx, &f, st);
+        g_prof.mark(slot, st);                            // third interval of the call's profile slot: the fused report + residual
+    }
+    if (own_ws) cudaFreeAsync(ws, st);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------
 // host-buffer entry point: chunked, multi-stream H2D -> solve -> D2H pipeline
 // ------------------------------------------------------------------------------------------
@@ -252,6 +314,7 @@ struct PipeSlot {
     void *d_uv = nullptr, *d_R = nullptr, *d_t = nullptr, *d_e = nullptr, *d_res = nullptr, *d_ws = nullptr;
     int32_t *d_it = nullptr, *d_best = nullptr;
     int16_t *h_pack = nullptr, *d_pack = nullptr;        // pinned staging / device copy of the packed pixels
+    void* d_narrow = nullptr;                             // device copy of a chunk of int16 / uint16 / float32 pixels (solve_batch_host_px)
     cudaEvent_t pack_free = nullptr;                      // the H2D copy out of h_pack has finished
     cudaEvent_t h2d_done = nullptr;                       // the slot's last pixel copy has finished (back-pressure)
 };
@@ -295,7 +358,7 @@ static void free_slot(PipeSlot& sl)
 {
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
     cudaFree(sl.d_uv); cudaFree(sl.d_R); cudaFree(sl.d_t); cudaFree(sl.d_e); cudaFree(sl.d_res); cudaFree(sl.d_ws);
-    cudaFree(sl.d_it); cudaFree(sl.d_best); cudaFree(sl.d_pack);
+    cudaFree(sl.d_it); cudaFree(sl.d_best); cudaFree(sl.d_pack); cudaFree(sl.d_narrow);
     if (sl.h_pack) cudaFreeHost(sl.h_pack);
     if (sl.pack_free) cudaEventDestroy(sl.pack_free);
     if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
@@ -348,6 +411,20 @@ int pnpb200_pipeline_last_packed(const pnpb200_pipeline* p, int64_t* packed_chun
     return PNPB200_OK;
 }
 
+int pnpb200_host_alloc(void** out, int64_t bytes, int write_combined)
+{
+    if (!out || bytes < 0) return PNPB200_EINVAL;
+    *out = nullptr;
+    PNP_CUDA_OK(cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    return PNPB200_OK;
+}
+
+int pnpb200_host_free(void* ptr)
+{
+    if (ptr) PNP_CUDA_OK(cudaFreeHost(ptr));
+    return PNPB200_OK;
+}
+
 int pnpb200_pipeline_destroy(pnpb200_pipeline* p)
 {
     if (!p) return PNPB200_EINVAL;
@@ -358,9 +435,11 @@ int pnpb200_pipeline_destroy(pnpb200_pipeline* p)
 }
 
 namespace {
+size_t pixel_bytes(int pixel_type) { return pixel_type == PNPB200_PIXEL_F32 ? 4 : 2; }
+
 struct HostCall {
     pnpb200_pipeline* p;
-    int method, n;
+    int method, n, pixel_type;
     int64_t B;
     const void* uv_host;
     const int32_t* point_index;
@@ -380,7 +459,15 @@ int submit_chunk(const HostCall& c, PipeSlot& sl, int64_t done, int64_t nb, bool
     if (packed) {
         PNP_CUDA_OK(cudaMemcpyAsync(sl.d_pack, sl.h_pack, sizeof(int16_t) * values, cudaMemcpyHostToDevice, st));
         PNP_CUDA_OK(cudaEventRecord(sl.pack_free, st));
-        const int rc = widen_i16_launch(p->dtype, (long long)values, sl.d_pack, sl.d_uv, st);
+        const int rc = widen_launch(PNPB200_PIXEL_I16, p->dtype, (long long)values, sl.d_pack, sl.d_uv, st);
+        if (rc != PNPB200_OK) return rc;
+    } else if (c.pixel_type != PNPB200_PIXEL_NATIVE) {
+        // narrow detections as the caller holds them: a half / a quarter of the bytes cross PCIe, widened on the device
+        const size_t psz = pixel_bytes(c.pixel_type);
+        const char* src = (const char*)c.uv_host + psz * (size_t)done * p->n_total * 2;
+        PNP_CUDA_OK(cudaMemcpyAsync(sl.d_narrow, src, psz * values, cudaMemcpyHostToDevice, st));
+        PNP_CUDA_OK(cudaEventRecord(sl.h2d_done, st));
+        const int rc = widen_launch(c.pixel_type, p->dtype, (long long)values, sl.d_narrow, sl.d_uv, st);
         if (rc != PNPB200_OK) return rc;
     } else {
         const char* src = (const char*)c.uv_host + esz * (size_t)done * p->n_total * 2;
@@ -389,7 +476,8 @@ int submit_chunk(const HostCall& c, PipeSlot& sl, int64_t done, int64_t nb, bool
     }
     pnpb200_params prm;
     if (c.params) prm = *c.params; else fill_default_params(&prm);
-    if (!prm.workspace) { prm.workspace = sl.d_ws; prm.workspace_bytes = (int64_t)p->ws_bytes; }
+    // always the slot's own scratch: chunks run concurrently on several streams, one caller workspace would be shared by them
+    prm.workspace = sl.d_ws; prm.workspace_bytes = (int64_t)p->ws_bytes;
     const int rc = pnpb200_solve_batch(c.method, p->dtype, nb, p->n_total, c.n, sl.d_uv, p->d_pattern, p->n_patterns,
                                        c.point_index, c.K, &prm, c.R ? sl.d_R : nullptr, c.t ? sl.d_t : nullptr,
                                        c.euler_deg ? sl.d_e : nullptr, c.res_norm ? sl.d_res : nullptr,
@@ -410,12 +498,33 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
                              const pnpb200_params* params, void* R, void* t, void* euler_deg, void* res_norm,
                              int32_t* iters, int32_t* best_pattern)
 {
+    return pnpb200_solve_batch_host_px(p, method, B, n, PNPB200_PIXEL_NATIVE, uv_host, pattern_host, point_index, K, params, R, t,
+                                       euler_deg, res_norm, iters, best_pattern);
+}
+
+int pnpb200_solve_batch_host_px(pnpb200_pipeline* p, int method, int64_t B, int n, int pixel_type, const void* uv_host,
+                                const void* pattern_host, const int32_t* point_index, const double* K,
+                                const pnpb200_params* params, void* R, void* t, void* euler_deg, void* res_norm,
+                                int32_t* iters, int32_t* best_pattern)
+{
     if (!p || !uv_host || !pattern_host || !K || B < 0) return PNPB200_EINVAL;
+    if (n < 1 || n > p->n_total || (!point_index && n != p->n_total)) return PNPB200_EINVAL;
+    if (pixel_type == PNPB200_PIXEL_F32 && p->dtype == PNPB200_DTYPE_F32) pixel_type = PNPB200_PIXEL_NATIVE;
+    if (pixel_type != PNPB200_PIXEL_NATIVE && pixel_type != PNPB200_PIXEL_I16 && pixel_type != PNPB200_PIXEL_U16 &&
+        pixel_type != PNPB200_PIXEL_F32)
+        return PNPB200_EINVAL;
+    if (params && params->workspace) return PNPB200_EINVAL;   // the pipeline owns one scratch per stream
     const size_t esz = p->esz;
+    if (pixel_type != PNPB200_PIXEL_NATIVE) {                  // first narrow call: the per-slot staging buffers
+        for (int s = 0; s < p->n_streams; ++s) {
+            PipeSlot& sl = p->slots[(size_t)s];
+            if (!sl.d_narrow) PNP_CUDA_OK(cudaMalloc(&sl.d_narrow, 4 * ((size_t)p->chunk * p->n_total * 2 + 8)));
+        }
+    }
     PNP_CUDA_OK(cudaMemcpyAsync(p->d_pattern, pattern_host, esz * (size_t)p->n_patterns * p->n_total * 3,
                                 cudaMemcpyHostToDevice, p->slots[0].stream));
     PNP_CUDA_OK(cudaStreamSynchronize(p->slots[0].stream));
-    const HostCall call = { p, method, n, B, uv_host, point_index, K, params, R, t, euler_deg, res_norm, iters, best_pattern };
+    const HostCall call = { p, method, n, pixel_type, B, uv_host, point_index, K, params, R, t, euler_deg, res_norm, iters, best_pattern };
     const int64_t n_chunks = (B + p->chunk - 1) / p->chunk;
     p->last_chunks = n_chunks; p->last_packed = 0;
     // Chunks are handed out from both ends of the batch: this thread sends chunks as they are from the front
@@ -432,7 +541,8 @@ int pnpb200_solve_batch_host(pnpb200_pipeline* p, int method, int64_t B, int n, 
     std::atomic<long long> n_packed{0};
     char packer_error[sizeof(g_last_error)] = "";          // the packing thread's pnpb200_last_error(), handed to the caller
     std::thread packer;
-    const bool packing = p->pack_threads > 0 && p->slots.size() > (size_t)p->n_streams && n_chunks >= 2;
+    // narrow pixels are already as small as the packed transfer makes them: nothing to pack
+    const bool packing = p->pack_threads > 0 && p->slots.size() > (size_t)p->n_streams && n_chunks >= 2 && pixel_type == PNPB200_PIXEL_NATIVE;
     if (packing) {
         const int64_t first = claim(true);                 // the last chunk is the packing thread's whatever the timing
         packer = std::thread([&, first]() {

@@ -300,6 +300,9 @@ struct ReportArgs {
     double K[9], bounds[4];
     double* report; int32_t* flags; int32_t* max_idx;
     long long rs_b, rs_k;           // element strides of report between problems / between columns
+    // fused residual pass of the moment mapping (k_report_chunk<T, RES != 0>): the 12 numbers per problem that
+    // k_iterate left in the workspace ([12][ld], LM: the state before the last update; F2: its tail) -> res_norm
+    const T* tail; long long ld; T* res; double kinv[6];
     int use_tmap;
     alignas(64) CUtensorMap tmap;   // uv as a 2-D tensor (RowStream), valid when use_tmap
 };
@@ -428,8 +431,11 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
 }
 
 // Streaming variant of k_report_thread: the rows go through two small chunk buffers (RowStream).
-template <typename T>
-__global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ ReportArgs<T> a)
+// RES != 0 fuses the last pass of the moment mapping into it (pnpb200_solve_report_batch): the rows are streamed ONCE
+// for the error report and for res_norm = ||z - hx|| at the state k_iterate stored (RES = 1: LM, PNP_SOLVER_LIB.py:2679-2681;
+// RES = 2: linear F2, :3368-3374) -- the same arithmetic, in the same order, as k_stream_chunk<T, METHOD, 1>.
+template <typename T, int RES>
+__global__ void __launch_bounds__(32, 12) k_report_chunk(const __grid_constant__ ReportArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Vec2<T>::type V2;
@@ -445,12 +451,19 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
     bool ok = b < a.B;
     if (!ok) b = a.B - 1;
     double Re[9], te[3], eu[3], g4[4];
+    T st[RES ? PNP_NTAIL : 1];
     load_report_pose(a, b, Re, te, eu, g4);
+    if (RES) {
+#pragma unroll
+        for (int k = 0; k < PNP_NTAIL; ++k) st[k] = __ldg(a.tail + (size_t)k * a.ld + b);
+    }
     RowStream<T> rs;
     rs.init(sBuf, bars, a.uv, a.B, a.n, a.use_tma /* chunk */, a.row_pitch, lane, a.use_tmap ? &a.tmap : nullptr);
     if (tile < n_tiles) rs.begin_tile(tile, lane);
     for (int e = lane; e < a.n * 3; e += 32) sP[e] = a.pattern[e];
     __syncwarp();
+    const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
+    const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
     while (tile < n_tiles) {
         double Rg[9], tg[3];
         const double roll_e = eu[0], yaw_e = eu[1], pitch_e = eu[2];
@@ -465,13 +478,15 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
         fold_camera(a.K, Rg, tg, Mg, mg);
         double s0 = 0, s1 = 0, s2 = 0, m0 = 0, m1 = 0, m2 = 0;
         int i0 = -1, i1 = -1, i2 = -1;
+        T acc0 = T(0), acc1 = T(0);
         for (int c = 0; c < rs.n_chunks; ++c) {
             const V2* row = rs.wait(c, lane);
             const int cnt = rs.count(c), base = c * rs.chunk;
 #pragma unroll 2
             for (int k = 0; k < cnt; ++k) {
                 const int i = base + k;
-                const double x = (double)sP[3 * i], y = (double)sP[3 * i + 1], z = (double)sP[3 * i + 2];
+                const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
+                const double x = (double)th[0], y = (double)th[1], z = (double)th[2];
                 double pe[2], pg[2], e0, e1, e2;
                 bool be, bg;
                 project_folded(Me, me, x, y, z, pe, be);  // TEST_TOOLBOX.py:312
@@ -481,6 +496,24 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
                 s0 += e0; if (e0 > m0) { m0 = e0; i0 = i; }
                 s1 += e1; if (e1 > m1) { m1 = e1; i1 = i; }
                 s2 += e2; if (e2 > m2) { m2 = e2; i2 = i; }
+                if (RES) {
+                    const T bx = k00 * px.x + k01 * px.y + k02;   // nu = K^-1 [u, v, 1]^T (:3305)
+                    const T by = k10 * px.x + k11 * px.y + k12;
+                    if (RES == 1) {
+                        const T aa = th[0] * st[0] + th[1] * st[1] + th[2] * st[2];
+                        const T bb = th[0] * st[3] + th[1] * st[4] + th[2] * st[5];
+                        const T cc = th[0] * st[6] + th[1] * st[7] + th[2] * st[8];
+                        const T rx = bx - (st[11] * (aa - bx * cc) + st[9]);    // z - hx (:3750, :2679)
+                        const T ry = by - (st[11] * (bb - by * cc) + st[10]);
+                        acc0 = t_fma(rx, rx, t_fma(ry, ry, acc0));
+                    } else {
+                        const T db = T(1) + (th[0] * st[0] + th[1] * st[1] + th[2] * st[2]);
+                        const T dx = th[0] * st[3] + th[1] * st[4] + th[2] * st[5] + st[6];
+                        const T dy = th[0] * st[7] + th[1] * st[8] + th[2] * st[9] + st[10];
+                        const T ex = bx * db - dx, ey = by * db - dy;
+                        acc0 = t_fma(ex, ex, acc0); acc1 = t_fma(ey, ey, acc1);
+                    }
+                }
             }
             rs.done(c, lane);
         }
@@ -499,6 +532,10 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
                 a.flags[b * 4 + 3] = fabs(yaw_e - yaw_g) < a.bounds[3];
             }
             if (a.max_idx) { a.max_idx[b * 3] = i0; a.max_idx[b * 3 + 1] = i1; a.max_idx[b * 3 + 2] = i2; }
+            if (RES && a.res) {
+                if (RES == 1) a.res[b] = t_sqrt(acc0);                                                       // :2681
+                else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
+            }
         }
         tile += gridDim.x;
         if (tile < n_tiles) {
@@ -508,6 +545,10 @@ __global__ void __launch_bounds__(32) k_report_chunk(const __grid_constant__ Rep
             ok = b < a.B;
             if (!ok) b = a.B - 1;
             load_report_pose(a, b, Re, te, eu, g4);
+            if (RES) {
+#pragma unroll
+                for (int k = 0; k < PNP_NTAIL; ++k) st[k] = __ldg(a.tail + (size_t)k * a.ld + b);
+            }
         }
     }
 }
@@ -887,26 +928,46 @@ __global__ void k_selftest_math(long long n_signed, const double* __restrict__ i
     sq[i] = (i & 1) ? sqrt_nonneg(a) : t_sqrt_fast<double>(a, y);   // both square roots in use (report / LM constraint rows)
 }
 
-// packed pixel transfer (pnpb200_pack.cpp): int16 -> T, eight values per thread (one 16-byte load)
-template <typename T>
-__global__ void __launch_bounds__(256) k_widen_i16(long long n, const int16_t* __restrict__ in, T* __restrict__ out)
+// Narrow pixels -> T (int16 of the packed transfer, pnpb200_pack.cpp; int16 / uint16 / float32 detections handed to
+// pnpb200_solve_batch_host_px): every thread widens the 16 bytes of one vector load, 8 or 4 values.
+template <typename Tin> PNP_DEV void unpack16(const int4& v, double (&o)[8]);
+template <> PNP_DEV void unpack16<int16_t>(const int4& v, double (&o)[8])
 {
-    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    if (g >= n) return;
-    if (g + 8 <= n) {
-        const int4 v = *reinterpret_cast<const int4*>(in + g);
-        const int w[4] = { v.x, v.y, v.z, v.w };
-        T o[8];
+    const int w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { o[2 * k] = (T)(int16_t)(w[k] & 0xffff); o[2 * k + 1] = (T)(int16_t)(w[k] >> 16); }
-        if (sizeof(T) == 8) {
+    for (int k = 0; k < 4; ++k) { o[2 * k] = (double)(int16_t)(w[k] & 0xffff); o[2 * k + 1] = (double)(int16_t)(w[k] >> 16); }
+}
+template <> PNP_DEV void unpack16<uint16_t>(const int4& v, double (&o)[8])
+{
+    const unsigned w[4] = { (unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[2 * k] = (double)(w[k] & 0xffffu); o[2 * k + 1] = (double)(w[k] >> 16); }
+}
+template <> PNP_DEV void unpack16<float>(const int4& v, double (&o)[8])
+{
+    o[0] = (double)__int_as_float(v.x); o[1] = (double)__int_as_float(v.y);
+    o[2] = (double)__int_as_float(v.z); o[3] = (double)__int_as_float(v.w);
+    o[4] = o[5] = o[6] = o[7] = 0.0;
+}
+
+template <typename Tin, typename T>
+__global__ void __launch_bounds__(256) k_widen(long long n, const Tin* __restrict__ in, T* __restrict__ out)
+{
+    constexpr int kPer = 16 / (int)sizeof(Tin);                // values per 16-byte load
+    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kPer;
+    if (g >= n) return;
+    if (g + kPer <= n) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in + g));
+        double o[8];
+        unpack16<Tin>(v, o);                                   // exact: every int16 / uint16 / float32 is a double (and the
+        if (sizeof(T) == 8) {                                  // 16-bit integers are floats)
             double2* d = reinterpret_cast<double2*>(out + g);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) d[k] = make_double2((double)o[2 * k], (double)o[2 * k + 1]);
+            for (int k = 0; k < kPer / 2; ++k) d[k] = make_double2(o[2 * k], o[2 * k + 1]);
         } else {
             float4* d = reinterpret_cast<float4*>(out + g);
-            d[0] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
-            d[1] = make_float4((float)o[4], (float)o[5], (float)o[6], (float)o[7]);
+#pragma unroll
+            for (int k = 0; k < kPer / 4; ++k) d[k] = make_float4((float)o[4 * k], (float)o[4 * k + 1], (float)o[4 * k + 2], (float)o[4 * k + 3]);
         }
     } else {
         for (long long i = g; i < n; ++i) out[i] = (T)in[i];
@@ -923,15 +984,27 @@ __global__ void k_selftest_sincos(long long n, const double* __restrict__ in, do
 }  // namespace pnpb200
 
 namespace pnpb200 {
-int widen_i16_launch(int dtype, long long n_values, const int16_t* in, void* out, cudaStream_t stream)
+template <typename Tin>
+static int widen_typed(int dtype, long long n_values, const void* in, void* out, cudaStream_t stream)
 {
-    if (n_values <= 0) return PNPB200_OK;
-    const unsigned grid = grid_for((n_values + 7) / 8, 256);
-    if (dtype == PNPB200_DTYPE_F64) k_widen_i16<double><<<grid, 256, 0, stream>>>(n_values, in, (double*)out);
-    else                            k_widen_i16<float><<<grid, 256, 0, stream>>>(n_values, in, (float*)out);
+    constexpr int kPer = 16 / (int)sizeof(Tin);
+    const unsigned grid = grid_for((n_values + kPer - 1) / kPer, 256);
+    if (dtype == PNPB200_DTYPE_F64) k_widen<Tin, double><<<grid, 256, 0, stream>>>(n_values, (const Tin*)in, (double*)out);
+    else                            k_widen<Tin, float><<<grid, 256, 0, stream>>>(n_values, (const Tin*)in, (float*)out);
     count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
+}
+
+int widen_launch(int pixel_type, int dtype, long long n_values, const void* in, void* out, cudaStream_t stream)
+{
+    if (n_values <= 0) return PNPB200_OK;
+    switch (pixel_type) {
+    case PNPB200_PIXEL_I16: return widen_typed<int16_t>(dtype, n_values, in, out, stream);
+    case PNPB200_PIXEL_U16: return widen_typed<uint16_t>(dtype, n_values, in, out, stream);
+    case PNPB200_PIXEL_F32: return widen_typed<float>(dtype, n_values, in, out, stream);
+    default: return PNPB200_EINVAL;
+    }
 }
 }  // namespace pnpb200
 
@@ -941,6 +1014,94 @@ using namespace pnpb200;
     if ((dtype) == PNPB200_DTYPE_F64) { CALL_F64; }          \
     else if ((dtype) == PNPB200_DTYPE_F32) { CALL_F32; }     \
     else return PNPB200_EINVAL;
+
+namespace pnpb200 {
+
+bool report_can_fuse(int dtype, int n)
+{
+    const RowGeom g = (dtype == PNPB200_DTYPE_F64) ? row_geometry<double>(n) : row_geometry<float>(n);
+    const StreamGeom sg = (dtype == PNPB200_DTYPE_F64) ? stream_geometry<double>(n) : stream_geometry<float>(n);
+    return g.tile_bytes <= 48 * 1024 && sg.use_stream;
+}
+
+// fuse != nullptr (only where report_can_fuse): the streaming report kernel also evaluates res_norm from the state in the workspace
+int report_launch(int dtype, int64_t B, int n, const void* pattern, const void* uv, const double* K,
+                  const void* R, const void* t, const void* euler_deg, const double* gt, const double* bounds,
+                  double* report, int64_t report_stride_problem, int64_t report_stride_column,
+                  int32_t* flags, int32_t* max_idx, const ReportFuse* fuse, cudaStream_t st)
+{
+    if (B < 0 || n < 1 || !pattern || !uv || !K || !R || !t || !euler_deg || !gt || !report) return PNPB200_EINVAL;
+    if (report_stride_problem < 1 || report_stride_column < 1) return PNPB200_EINVAL;
+    const long long rs_b = report_stride_problem, rs_k = report_stride_column;
+    if (((uintptr_t)uv & 15u) != 0) return PNPB200_EINVAL;   // rows are staged with 16-byte bulk copies
+    if (fuse && !report_can_fuse(dtype, n)) return PNPB200_EINVAL;
+    if (B == 0) return PNPB200_OK;
+    KMat km;
+    for (int e = 0; e < 9; ++e) km.k[e] = K[e];
+    Bounds bd;
+    for (int e = 0; e < 4; ++e) bd.b[e] = bounds ? bounds[e] : 10.0;
+    const size_t esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
+    const RowGeom g = (dtype == PNPB200_DTYPE_F64) ? row_geometry<double>(n) : row_geometry<float>(n);
+    const size_t smem = g.tile_bytes + (size_t)n * 3 * esz + 16;
+    const StreamGeom sg = (dtype == PNPB200_DTYPE_F64) ? stream_geometry<double>(n) : stream_geometry<float>(n);
+    if (g.tile_bytes <= 48 * 1024 && sg.use_stream) {
+        const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
+        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
+        const size_t csmem = 2 * sg.buf_bytes + (size_t)n * 3 * esz + 32;
+        const int res_mode = fuse ? fuse->res_mode : 0;
+#define LAUNCH_REPORT_CHUNK(TT)                                                                                         \
+        {                                                                                                               \
+            ReportArgs<TT> a;                                                                                           \
+            a.pattern = (const TT*)pattern; a.uv = (const TT*)uv; a.R = (const TT*)R; a.t = (const TT*)t;              \
+            a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = sg.pitch; a.use_tma = sg.chunk;  \
+            for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
+            for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
+            a.report = report; a.flags = flags; a.max_idx = max_idx; a.rs_b = rs_b; a.rs_k = rs_k;                      \
+            a.tail = fuse ? (const TT*)fuse->tail : nullptr; a.ld = fuse ? fuse->ld : 0; a.res = fuse ? (TT*)fuse->res : nullptr; \
+            for (int e = 0; e < 6; ++e) a.kinv[e] = fuse ? fuse->kinv[e] : 0.0;                                         \
+            a.use_tmap = (sg.pitch == sg.chunk * 2) ? make_row_tensor_map(&a.tmap, uv, (int)sizeof(TT), B, n, sg.chunk) : 0; \
+            if (res_mode == 1) {                                                                                        \
+                PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT, 1>, csmem));                               \
+                k_report_chunk<TT, 1><<<grid, 32, csmem, st>>>(a);                                                      \
+            } else if (res_mode == 2) {                                                                                 \
+                PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT, 2>, csmem));                               \
+                k_report_chunk<TT, 2><<<grid, 32, csmem, st>>>(a);                                                      \
+            } else {                                                                                                    \
+                PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT, 0>, csmem));                               \
+                k_report_chunk<TT, 0><<<grid, 32, csmem, st>>>(a);                                                      \
+            }                                                                                                           \
+            count_kernel_launches(1);                                                                                   \
+        }
+        DISPATCH_DTYPE(dtype, LAUNCH_REPORT_CHUNK(double), LAUNCH_REPORT_CHUNK(float));
+#undef LAUNCH_REPORT_CHUNK
+    } else if (g.tile_bytes <= 48 * 1024) {
+        const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
+        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
+#define LAUNCH_REPORT_THREAD(TT)                                                                                        \
+        {                                                                                                               \
+            ReportArgs<TT> a;                                                                                           \
+            a.pattern = (const TT*)pattern; a.uv = (const TT*)uv; a.R = (const TT*)R; a.t = (const TT*)t;              \
+            a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = g.row_pitch; a.use_tma = g.use_tma; \
+            for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
+            for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
+            a.report = report; a.flags = flags; a.max_idx = max_idx; a.use_tmap = 0; a.rs_b = rs_b; a.rs_k = rs_k;      \
+            a.tail = nullptr; a.ld = 0; a.res = nullptr;                                                                \
+            PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_thread<TT>, smem));                                      \
+            k_report_thread<TT><<<grid, 32, smem, st>>>(a); count_kernel_launches(1);                                   \
+        }
+        DISPATCH_DTYPE(dtype, LAUNCH_REPORT_THREAD(double), LAUNCH_REPORT_THREAD(float));
+#undef LAUNCH_REPORT_THREAD
+    } else {
+        const unsigned grid = grid_for(B * 32, 256);
+        DISPATCH_DTYPE(dtype,
+                       (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, rs_b, rs_k, flags, max_idx)),
+                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, rs_b, rs_k, flags, max_idx))); count_kernel_launches(1);
+    }
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
+}  // namespace pnpb200
 
 extern "C" {
 
@@ -1036,62 +1197,8 @@ int pnpb200_report_batch_strided(int dtype, int64_t B, int n, const void* patter
                                  double* report, int64_t report_stride_problem, int64_t report_stride_column,
                                  int32_t* flags, int32_t* max_idx, void* stream)
 {
-    if (B < 0 || n < 1 || !pattern || !uv || !K || !R || !t || !euler_deg || !gt || !report) return PNPB200_EINVAL;
-    if (report_stride_problem < 1 || report_stride_column < 1) return PNPB200_EINVAL;
-    const long long rs_b = report_stride_problem, rs_k = report_stride_column;
-    if (((uintptr_t)uv & 15u) != 0) return PNPB200_EINVAL;   // rows are staged with 16-byte bulk copies
-    if (B == 0) return PNPB200_OK;
-    KMat km;
-    for (int e = 0; e < 9; ++e) km.k[e] = K[e];
-    Bounds bd;
-    for (int e = 0; e < 4; ++e) bd.b[e] = bounds ? bounds[e] : 10.0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
-    const RowGeom g = (dtype == PNPB200_DTYPE_F64) ? row_geometry<double>(n) : row_geometry<float>(n);
-    const size_t smem = g.tile_bytes + (size_t)n * 3 * esz + 16;
-    const StreamGeom sg = (dtype == PNPB200_DTYPE_F64) ? stream_geometry<double>(n) : stream_geometry<float>(n);
-    if (g.tile_bytes <= 48 * 1024 && sg.use_stream) {
-        const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
-        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
-        const size_t csmem = 2 * sg.buf_bytes + (size_t)n * 3 * esz + 32;
-#define LAUNCH_REPORT_CHUNK(TT)                                                                                         \
-        {                                                                                                               \
-            ReportArgs<TT> a;                                                                                           \
-            a.pattern = (const TT*)pattern; a.uv = (const TT*)uv; a.R = (const TT*)R; a.t = (const TT*)t;              \
-            a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = sg.pitch; a.use_tma = sg.chunk;  \
-            for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
-            for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
-            a.report = report; a.flags = flags; a.max_idx = max_idx; a.rs_b = rs_b; a.rs_k = rs_k;                      \
-            a.use_tmap = (sg.pitch == sg.chunk * 2) ? make_row_tensor_map(&a.tmap, uv, (int)sizeof(TT), B, n, sg.chunk) : 0; \
-            PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_chunk<TT>, csmem)); \
-            k_report_chunk<TT><<<grid, 32, csmem, st>>>(a); count_kernel_launches(1);                                                             \
-        }
-        DISPATCH_DTYPE(dtype, LAUNCH_REPORT_CHUNK(double), LAUNCH_REPORT_CHUNK(float));
-#undef LAUNCH_REPORT_CHUNK
-    } else if (g.tile_bytes <= 48 * 1024) {
-        const long long n_tiles = (B + kTileProblems - 1) / kTileProblems;
-        const unsigned grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
-#define LAUNCH_REPORT_THREAD(TT)                                                                                        \
-        {                                                                                                               \
-            ReportArgs<TT> a;                                                                                           \
-            a.pattern = (const TT*)pattern; a.uv = (const TT*)uv; a.R = (const TT*)R; a.t = (const TT*)t;              \
-            a.euler = (const TT*)euler_deg; a.gt = gt; a.B = B; a.n = n; a.row_pitch = g.row_pitch; a.use_tma = g.use_tma; \
-            for (int e = 0; e < 9; ++e) a.K[e] = K[e];                                                                  \
-            for (int e = 0; e < 4; ++e) a.bounds[e] = bd.b[e];                                                          \
-            a.report = report; a.flags = flags; a.max_idx = max_idx; a.use_tmap = 0; a.rs_b = rs_b; a.rs_k = rs_k;                                    \
-            PNP_CUDA_OK(set_dynamic_smem((const void*)k_report_thread<TT>, smem)); \
-            k_report_thread<TT><<<grid, 32, smem, st>>>(a); count_kernel_launches(1);                                                             \
-        }
-        DISPATCH_DTYPE(dtype, LAUNCH_REPORT_THREAD(double), LAUNCH_REPORT_THREAD(float));
-#undef LAUNCH_REPORT_THREAD
-    } else {
-        const unsigned grid = grid_for(B * 32, 256);
-        DISPATCH_DTYPE(dtype,
-                       (k_report<double><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, rs_b, rs_k, flags, max_idx)),
-                       (k_report<float><<<grid, 256, 0, st>>>(B, n, pattern, uv, km, R, t, euler_deg, gt, bd, report, rs_b, rs_k, flags, max_idx))); count_kernel_launches(1);
-    }
-    PNP_CUDA_OK(cudaGetLastError());
-    return PNPB200_OK;
+    return report_launch(dtype, B, n, pattern, uv, K, R, t, euler_deg, gt, bounds, report, report_stride_problem,
+                         report_stride_column, flags, max_idx, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

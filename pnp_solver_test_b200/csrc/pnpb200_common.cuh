@@ -14,6 +14,8 @@
 #define PNP_PATC 20
 // landmark selections up to this size travel inside the kernel arguments; larger ones through device memory
 #define PNP_MAX_INLINE_IDX 96
+// internal bit of pnpb200_params.flags (masked off at the C ABI): the moment mapping skips its residual pass
+#define PNP_FLAG_INTERNAL_NO_RESIDUAL (1 << 30)
 
 namespace pnpb200 {
 
@@ -52,7 +54,14 @@ void count_kernel_launches(int n);   // kernels this library has launched (pnpb2
 // 2-D tensor map over the pixel rows uv[B][n_total][2]: box = (chunk_points x 32 problems); returns 0 when
 // the driver entry point is missing or the shape does not qualify (callers keep the per-row copies).  pnpb200_api.cu
 int make_row_tensor_map(CUtensorMap* out, const void* uv, int elem_bytes, long long B, int n_total, int chunk_points);
-int widen_i16_launch(int dtype, long long n_values, const int16_t* in, void* out, cudaStream_t stream);   // pnpb200_aux.cu
+// narrow pixels (PNPB200_PIXEL_I16 / U16 / F32) -> the arithmetic type, on the device; pnpb200_aux.cu
+int widen_launch(int pixel_type, int dtype, long long n_values, const void* in, void* out, cudaStream_t stream);
+// error report (pnpb200_aux.cu); with `fuse` the streaming report kernel also evaluates res_norm of the moment mapping
+struct ReportFuse { int res_mode; /* 1: LM, 2: linear F2 */ const void* tail; long long ld; void* res; double kinv[6]; };
+bool report_can_fuse(int dtype, int n);
+int report_launch(int dtype, int64_t B, int n, const void* pattern, const void* uv, const double* K, const void* R, const void* t,
+                  const void* euler_deg, const double* gt, const double* bounds, double* report, int64_t report_stride_problem,
+                  int64_t report_stride_column, int32_t* flags, int32_t* max_idx, const ReportFuse* fuse, cudaStream_t st);
 cudaError_t set_dynamic_smem(const void* kernel, size_t bytes);                                   // defined in pnpb200_api.cu
 cudaError_t blocks_per_sm(int* out, const void* kernel, int block_threads, size_t smem_bytes);   // defined in pnpb200_api.cu
 
@@ -80,9 +89,16 @@ struct ProfileRing {
         used[s] = 0;
         return s;
     }
+    int last() const { return count ? (next + kSlots - 1) % kSlots : -1; }   // the slot of the most recent begin()
+    // Inside a stream capture the record becomes an event-record NODE of the graph (cudaEventRecordExternal): every
+    // replay of the graph re-records the event, so the times read afterwards are those of the last replay.
     void mark(int slot, cudaStream_t st)
     {
-        if (slot >= 0 && used[slot] < 4) cudaEventRecord(ev[slot][used[slot]++], st);
+        if (slot < 0 || used[slot] >= 4) return;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+        cudaEventRecordWithFlags(ev[slot][used[slot]++], st,
+                                 cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
     }
 };
 extern thread_local ProfileRing g_prof;            // defined in pnpb200_api.cu

@@ -57,6 +57,7 @@ struct SolveArgs {
     int32_t* iters; int32_t* best;
     void* ws; size_t ws_bytes;   // optional caller scratch (moment mapping)
     int profile, tune;
+    int skip_residual;           // moment mapping: leave res_norm to the caller's fused report pass (pnpb200_solve_report_batch)
 };
 
 // raw pixels of one problem in global memory, normalised on the fly (warp mapping)
@@ -845,6 +846,10 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     const bool own_ws = !(a.ws && a.ws_bytes >= ws_elems * sizeof(T));
     if (own_ws) PNP_CUDA_OK(cudaMallocAsync((void**)&ws, ws_elems * sizeof(T), stream));
     else ws = (T*)a.ws;
+    struct WsGuard {                                          // every return below hands the scratch back to the pool
+        void* p; cudaStream_t st;
+        ~WsGuard() { if (p) cudaFreeAsync(p, st); }
+    } ws_guard = { own_ws ? (void*)ws : nullptr, stream };
     MomArgs<T> m;
     m.uv = a.uv; m.pattern = a.pattern; m.idx = a.idx; m.idx_mode = a.idx_mode;
     for (int e = 0; e < PNP_MAX_INLINE_IDX; ++e) m.idx_inline[e] = a.idx_inline[e];
@@ -889,10 +894,9 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     g_prof.mark(slot, stream);
     launch_moment_pass<T, METHOD>(1, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
     g_prof.mark(slot, stream);
-    if (a.res) launch_moment_pass<T, METHOD>(2, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
-    g_prof.mark(slot, stream);
+    if (a.res && !a.skip_residual) launch_moment_pass<T, METHOD>(2, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    if (!a.skip_residual) g_prof.mark(slot, stream);      // (the fused report + residual pass is marked by its launcher)
     PNP_CUDA_OK(cudaGetLastError());
-    if (own_ws) PNP_CUDA_OK(cudaFreeAsync(ws, stream));
     return PNPB200_OK;
 }
 
@@ -958,10 +962,13 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     a.row_pitch = 0; a.use_tma = 0;
     double Kinv[9];
     host_inv3(K, Kinv);
+    for (int e = 0; e < 9; ++e)
+        if (!(Kinv[e] - Kinv[e] == 0.0)) return PNPB200_EINVAL;   // singular or non-finite camera matrix (np.linalg.inv raises there)
     for (int e = 0; e < 6; ++e) a.kinv[e] = Kinv[e];
     a.prm = make_prm<T>(prm);
     a.R = (T*)R; a.t = (T*)t; a.euler = (T*)euler; a.res = (T*)res; a.iters = iters; a.best = best;
     a.profile = (prm.flags & PNPB200_FLAG_PROFILE) ? 1 : 0;
+    a.skip_residual = (prm.flags & PNP_FLAG_INTERNAL_NO_RESIDUAL) ? 1 : 0;
     a.tune = (prm.flags >> 8) & 0xff;                     // undocumented tuning knob (register budget of k_iterate, slice size)
     a.ws = prm.workspace; a.ws_bytes = (prm.workspace && prm.workspace_bytes > 0) ? (size_t)prm.workspace_bytes : 0;
     switch (method) {

@@ -837,8 +837,8 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
 #pragma unroll
     for (int e = 0; e < 78; ++e) Om[e] = T(0);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) Om[sidx<12>(i, i)] = T(1e5);         // pinv(1e-5 I) (:2067-2068)
-    T res_old = T(1e-7), res = T(1e5);                               // :2101-2102
+    for (int i = 0; i < 12; ++i) Om[sidx<12>(i, i)] = prm.sigma0;     // pinv(1e-5 I) (:2067-2068)
+    T res_old = prm.res_old0, res = T(1e5);                          // :2101-2102
     bool done = false;
     int iters = 0;
     const T w = prm.meas_w;                                          // 1 / (9 / f^2) (:2080-2083)

@@ -143,11 +143,43 @@ class HostPipeline(object):
         except Exception:
             pass
 
+    _PIXEL_TYPES = {torch.int16: _lib.PIXEL_I16, torch.uint16: _lib.PIXEL_U16, torch.float32: _lib.PIXEL_F32}
+    _OUT_SHAPES = {"R": (9, None), "t": (3, None), "euler": (3, None), "res_norm": (1, None), "iters": (1, torch.int32),
+                   "best_pattern": (1, torch.int32)}
+
     def solve(self, method, uv_host, patterns_host, K, out, point_index=None, params=None):
-        """uv_host [B,n_total,2], patterns_host [P,n_total,3]: CPU torch tensors (pinned for overlap).
-        out: dict of CPU tensors to fill among R, t, euler, res_norm, iters, best_pattern."""
+        """uv_host [B,n_total,2], patterns_host [P,n_total,3]: contiguous CPU torch tensors (pinned for overlap).
+        uv_host may also be int16, uint16 or float32 whatever the pipeline's dtype (detections as a detector
+        delivers them: pnpb200_solve_batch_host_px ships them as they are and widens them on the device).
+        out: dict of contiguous CPU tensors to fill among R [B,3,3] / [B,9], t [B,3], euler [B,3], res_norm [B]
+        (pipeline dtype), iters [B], best_pattern [B] (int32).  Everything is checked here: the C side reads and
+        writes B * (row size) elements through the raw pointers."""
         m = _lib.METHODS[method] if isinstance(method, str) else int(method)
+        tdt = _TORCH_DTYPE[self.dt]
+        if not (torch.is_tensor(uv_host) and torch.is_tensor(patterns_host)):
+            raise ValueError("uv_host and patterns_host must be CPU torch tensors")
+        if uv_host.is_cuda or patterns_host.is_cuda or not uv_host.is_contiguous() or not patterns_host.is_contiguous():
+            raise ValueError("uv_host and patterns_host must be contiguous CPU tensors")
+        if uv_host.dim() != 3 or tuple(uv_host.shape[1:]) != (self.n_total, 2):
+            raise ValueError("uv_host must be [B, %d, 2], not %s" % (self.n_total, tuple(uv_host.shape)))
+        if uv_host.dtype == tdt:
+            px = _lib.PIXEL_NATIVE
+        elif uv_host.dtype in self._PIXEL_TYPES and not (uv_host.dtype == torch.float32 and tdt == torch.float32):
+            px = self._PIXEL_TYPES[uv_host.dtype]
+        else:
+            raise ValueError("uv_host must be %s, int16, uint16 or float32, not %s" % (tdt, uv_host.dtype))
+        if patterns_host.dtype != tdt or tuple(patterns_host.shape) != (self.n_patterns, self.n_total, 3):
+            raise ValueError("patterns_host must be %s [%d, %d, 3]" % (tdt, self.n_patterns, self.n_total))
         B = int(uv_host.shape[0])
+        for k, v in out.items():
+            if k not in self._OUT_SHAPES:
+                raise ValueError("unknown output %r" % (k,))
+            width, dt_k = self._OUT_SHAPES[k]
+            if not torch.is_tensor(v) or v.is_cuda or not v.is_contiguous() or v.dtype != (dt_k or tdt) or v.numel() != B * width \
+                    or (B and int(v.shape[0]) != B):
+                raise ValueError("out[%r] must be a contiguous CPU %s tensor of %d x %d elements" % (k, dt_k or tdt, B, width))
+        if params is not None and params.workspace:
+            raise ValueError("params.workspace is not used by the host pipeline (it owns one scratch per stream)")
         if point_index is None:
             n, idx_p = self.n_total, None
         else:
@@ -155,14 +187,32 @@ class HostPipeline(object):
             n, idx_p = int(idx.shape[0]), idx.ctypes.data_as(C.POINTER(C.c_int32))
         Kh, Kp = _k_host(K)
         with torch.cuda.device(self.device):
-            rc = lib.pnpb200_solve_batch_host(
-                self._h, C.c_int(m), C.c_int64(B), C.c_int(n), ptr(uv_host), ptr(patterns_host), idx_p, Kp,
+            rc = lib.pnpb200_solve_batch_host_px(
+                self._h, C.c_int(m), C.c_int64(B), C.c_int(n), C.c_int(px), ptr(uv_host), ptr(patterns_host), idx_p, Kp,
                 C.byref(params) if params is not None else None,
                 ptr(out.get("R")), ptr(out.get("t")), ptr(out.get("euler")), ptr(out.get("res_norm")),
                 ptr(out.get("iters")), ptr(out.get("best_pattern")))
-        check(rc, "pnpb200_solve_batch_host")
+        check(rc, "pnpb200_solve_batch_host_px")
         _lib.count_launch((B + self.chunk - 1) // self.chunk)
         return out
+
+
+def host_buffer(shape, dtype, write_combined=False):
+    """A page-locked CPU tensor from pnpb200_host_alloc (cudaHostAlloc); write_combined=True for pixel buffers
+    the CPU only writes (faster for the device to read, very slow for the CPU to read back).  The memory is
+    released when the tensor is garbage-collected."""
+    dtype = torch.empty((), dtype=dtype).dtype
+    esz = torch.empty((), dtype=dtype).element_size()
+    n = 1
+    for d in shape:
+        n *= int(d)
+    p = C.c_void_p()
+    check(lib.pnpb200_host_alloc(C.byref(p), C.c_int64(n * esz), C.c_int(int(bool(write_combined)))), "pnpb200_host_alloc")
+    buf = (C.c_char * max(n * esz, 1)).from_address(p.value)
+    t = torch.frombuffer(buf, dtype=dtype, count=n).view(*shape) if n else torch.empty(shape, dtype=dtype)
+    import weakref
+    weakref.finalize(buf, lib.pnpb200_host_free, C.c_void_p(p.value))
+    return t
 
 
 def R_from_euler_batch(euler, is_degree=False):
@@ -376,7 +426,8 @@ class PNP_SOLVER(object):
     def solve_pnp_batch_host(self, uv, method=None, key_list="default", params=None, chunk_problems=1 << 16, pack_threads=None):
         """solve_pnp_batch for data that lives on the HOST (what a script that loops over NumPy samples
         has): uv [B, n_total, 2] NumPy array or CPU tensor in; dict of NumPy arrays R [B,3,3], t [B,3],
-        euler [B,3] (roll, yaw, pitch, deg.), res_norm [B], iters [B], best_pattern [B] out.  Runs the
+        euler [B,3] (roll, yaw, pitch, deg.), res_norm [B], iters [B], best_pattern [B] out.  uv may be int16,
+        uint16 or float32 (a detector's own output type): it then crosses PCIe as it is.  Runs the
         chunked host pipeline (pnpb200_solve_batch_host: H2D, solve and D2H overlap on three streams);
         pack_threads host threads (default: half the visible cores, at most 8) let chunks of whole-pixel
         landmarks cross PCIe as int16 (lossless, checked per chunk; other chunks travel as they are)."""
@@ -386,8 +437,12 @@ class PNP_SOLVER(object):
             key_list = self.LM_key_list if method == "qeif" else None
         idx = None if key_list is None else [all_keys.index(k) for k in key_list]
         tdt = self._tdtype()
-        uv_h = uv if torch.is_tensor(uv) else torch.from_numpy(np.ascontiguousarray(uv))
-        uv_h = uv_h.to(device="cpu", dtype=tdt).contiguous()
+        if not torch.is_tensor(uv):
+            uv = np.ascontiguousarray(uv)
+            uv = torch.from_numpy(uv.view(np.int16)).view(torch.uint16) if uv.dtype == np.uint16 else torch.from_numpy(uv)
+        # int16 / uint16 / float32 detections stay what they are (no FP64 round trip): the pipeline widens them on the device
+        narrow = uv.dtype in (torch.int16, torch.uint16) or (uv.dtype == torch.float32 and tdt == torch.float64)
+        uv_h = uv.to(device="cpu").contiguous() if narrow else uv.to(device="cpu", dtype=tdt).contiguous()
         B, n_total = int(uv_h.shape[0]), int(uv_h.shape[1])
         if n_total != len(all_keys):
             raise ValueError("uv holds %d landmarks per problem, the stored patterns %d" % (n_total, len(all_keys)))
@@ -404,14 +459,23 @@ class PNP_SOLVER(object):
             pipe = HostPipeline(tdt, chunk_problems=chunk, n_total=n_total, n_patterns=int(pat_h.shape[0]), n_streams=3,
                                 device=self.device)
             self._dev_cache[key] = pipe
-        pipe.set_packing(int(pack_threads) if B >= 2 * chunk else 0)
-        outs = {"R": torch.empty((B, 3, 3), dtype=tdt), "t": torch.empty((B, 3), dtype=tdt), "euler": torch.empty((B, 3), dtype=tdt),
-                "res_norm": torch.empty((B,), dtype=tdt), "iters": torch.empty((B,), dtype=torch.int32),
-                "best_pattern": torch.empty((B,), dtype=torch.int32)}
+        pipe.set_packing(int(pack_threads) if (B >= 2 * chunk and not narrow) else 0)
+        # results land in page-locked buffers (kept per batch size), so the D2H copies of a chunk are asynchronous and
+        # overlap the next chunks' H2D and solve; the arrays handed back are copies the caller owns
+        okey = ("host_out", self.dtype_code, B)
+        outs = self._dev_cache.get(okey)
+        if outs is None:
+            for k_old in [k for k in self._dev_cache if k[0] == "host_out"]:
+                del self._dev_cache[k_old]
+            pin = (lambda t_: t_.pin_memory()) if B > 0 else (lambda t_: t_)
+            outs = {"R": pin(torch.empty((B, 3, 3), dtype=tdt)), "t": pin(torch.empty((B, 3), dtype=tdt)),
+                    "euler": pin(torch.empty((B, 3), dtype=tdt)), "res_norm": pin(torch.empty((B,), dtype=tdt)),
+                    "iters": pin(torch.empty((B,), dtype=torch.int32)), "best_pattern": pin(torch.empty((B,), dtype=torch.int32))}
+            self._dev_cache[okey] = outs
         if B > 0:
             pipe.solve(method, uv_h, pat_h, self.np_K_camera_est, outs, point_index=idx,
                        params=params if params is not None else self.params)
-        return {k: v.numpy() for k, v in outs.items()}
+        return {k: v.numpy().copy() for k, v in outs.items()}
 
     # ---------------------------------------------------------------- Euler <-> R (:4442-4517)
     def get_rotation_matrix_from_Euler(self, roll, yaw, pitch, is_degree=False):

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import lib, check, ptr
-from .solver import _dtype_code, _k_host, _stream_ptr
+from .solver import _copy_params, _dtype_code, _k_host, _stream_ptr
 
 # TEST_TOOLBOX.get_classification_parameters("drpy_expand") (TEST_TOOLBOX.py:133-162)
 CLASS_BINS = {
@@ -95,6 +95,55 @@ def report_batch(pattern, uv, K, R, t, euler, gt, bounds=(10.0, 10.0, 10.0, 10.0
     return dict(report=rep, flags=flags, max_idx=midx)
 
 
+def solve_report_batch(method, uv, pattern, K, gt, params=None, bounds=(10.0, 10.0, 10.0, 10.0), point_index=None):
+    """pnpb200_solve_report_batch: solve_batch (one pattern) and report_batch (column layout) of the same problems in
+    one call -- the body of the loop of random_stress_test.py:322-377.  With LM / linear F2 over all landmarks the
+    residual pass of the solve rides in the report kernel (the pixel rows are read twice instead of three times);
+    the results are those of the two separate calls.  uv [B,n,2], pattern [n,3] (or [1,n,3]) CUDA tensors of one
+    dtype, gt [B,4] FP64.  Returns the union of both dicts."""
+    m = _lib.METHODS[method] if isinstance(method, str) else int(method)
+    dev = uv.device
+    uv = uv.contiguous()
+    pattern = torch.as_tensor(pattern, device=dev).to(uv.dtype).reshape(-1, 3).contiguous()
+    B, n_total = int(uv.shape[0]), int(uv.shape[1])
+    if uv.dim() != 3 or uv.shape[2] != 2 or pattern.shape[0] != n_total:
+        raise ValueError("shape mismatch: uv [B,n,2], pattern [n,3]")
+    dt = _dtype_code(uv.dtype)
+    if point_index is None:
+        n, idx_p = n_total, None
+    else:
+        idx = np.ascontiguousarray(np.asarray(point_index, dtype=np.int32))
+        n, idx_p = int(idx.shape[0]), idx.ctypes.data_as(C.POINTER(C.c_int32))
+    o = dict(R=torch.empty((B, 3, 3), dtype=uv.dtype, device=dev), t=torch.empty((B, 3), dtype=uv.dtype, device=dev),
+             euler=torch.empty((B, 3), dtype=uv.dtype, device=dev), res_norm=torch.empty((B,), dtype=uv.dtype, device=dev),
+             iters=torch.empty((B,), dtype=torch.int32, device=dev),
+             report=torch.empty((_lib.REPORT_WIDTH, B), dtype=torch.float64, device=dev).t(),
+             flags=torch.empty((B, 4), dtype=torch.int32, device=dev), max_idx=torch.empty((B, 3), dtype=torch.int32, device=dev))
+    if B == 0:
+        return o
+    prm = _lib.default_params() if params is None else params
+    ws_bytes = int(lib.pnpb200_workspace_bytes(C.c_int(m), C.c_int(dt), C.c_int64(B), C.c_int(1), C.c_int(int(prm.mapping))))
+    ws = None
+    if ws_bytes > 0 and not prm.workspace:                 # scratch from torch's caching allocator (stream-ordered, no driver call)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        prm = _copy_params(prm)
+        prm.workspace, prm.workspace_bytes = ws.data_ptr(), ws_bytes
+    Kh, Kp = _k_host(K)
+    bd = (C.c_double * 4)(*[float(b) for b in bounds])
+    gt = gt.to(torch.float64).contiguous()
+    PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    rep = o["report"]
+    with torch.cuda.device(dev):
+        check(lib.pnpb200_solve_report_batch(C.c_int(m), C.c_int(dt), C.c_int64(B), C.c_int(n_total), C.c_int(n), ptr(uv), ptr(pattern),
+                                             idx_p, Kp, C.byref(prm), ptr(o["R"]), ptr(o["t"]), ptr(o["euler"]), ptr(o["res_norm"]),
+                                             C.cast(ptr(o["iters"]), PI), C.cast(ptr(gt), PD), bd, C.cast(ptr(rep), PD),
+                                             C.c_int64(max(int(rep.stride(0)), 1)), C.c_int64(max(int(rep.stride(1)), 1)),
+                                             C.cast(ptr(o["flags"]), PI), C.cast(ptr(o["max_idx"]), PI), _stream_ptr(dev)),
+              "pnpb200_solve_report_batch")
+    _lib.count_launch(2)
+    return o
+
+
 def classify(values, bins, scale=1.0):
     """np.digitize(values*scale, bins) on the device (TEST_TOOLBOX.classify_drpy, :239-247).
     values: 1-D (possibly strided) FP64 CUDA tensor view."""
@@ -124,12 +173,25 @@ def reduce_phase1(s1, group=None):
     return s1
 
 
-def reduce_phase2(s2, mx, group=None):
-    """Phase 2: all_reduce(SUM) of [..., 4] = (sum (e-m)^2, sum |e|, sum |e-m|, 0) and
-    all_reduce(MAX) of max |e-m|, in place."""
+def reduce_phase2(s2, mx, group=None, flat23=None):
+    """Phase 2: SUM over ranks of [..., 4] = (sum (e-m)^2, sum |e|, sum |e-m|, 0) and MAX over ranks of max |e-m|,
+    in place.  With `flat23` (the contiguous buffer that holds s2 followed by mx, as `statistics` allocates them) the
+    two reductions are ONE exchange: an all_gather of the ranks' partials (a few KB) and a local fold -- one collective
+    launch instead of two, and the SUM is then taken in rank order on every rank (bit-identical everywhere)."""
     import torch.distributed as dist
-    _all_reduce(s2, dist.ReduceOp.SUM, group)
-    _all_reduce(mx, dist.ReduceOp.MAX, group)
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return s2, mx
+    if flat23 is None:
+        _all_reduce(s2, dist.ReduceOp.SUM, group)
+        _all_reduce(mx, dist.ReduceOp.MAX, group)
+        return s2, mx
+    world = dist.get_world_size(group)
+    gathered = torch.empty((world * flat23.numel(),), dtype=flat23.dtype, device=flat23.device)
+    dist.all_gather_into_tensor(gathered, flat23.reshape(-1), group=group)
+    gathered = gathered.view(world, flat23.numel())
+    n2 = s2.numel()
+    s2.copy_(gathered[:, :n2].sum(dim=0).view_as(s2))
+    mx.copy_(gathered[:, n2:].max(dim=0).values.view_as(mx))
     return s2, mx
 
 
@@ -168,6 +230,19 @@ class PendingStats(object):
             PendingStats._pinned[int(h.numel())].append(h)
             self._host = None
         return self._out
+
+
+class DeviceStats(object):
+    """Statistics whose reduced sums stay on the device (lazy="device"): nothing but kernels and collectives is
+    queued, so the call can be captured in a CUDA graph; `.result()` copies and finalises (synchronises)."""
+
+    def __init__(self, flat, nq, rows):
+        self.flat, self.nq, self.rows = flat, nq, rows
+
+    def result(self):
+        nq, rows, h = self.nq, self.rows, self.flat.cpu()
+        return finalize_stats(h[:nq * rows * 4].view(nq, rows, 4), h[nq * rows * 4:nq * rows * 8].view(nq, rows, 4),
+                              h[nq * rows * 8:].view(nq, rows))
 
 
 def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=True, lazy=False):
@@ -211,7 +286,9 @@ def statistics(est, gt=None, class_id=None, n_class=1, group=None, distributed=T
                                       dp(s1), dp(s2), dp(mx), _stream_ptr(dev)), "pnpb200_stats_pass2")
     _lib.count_launch()
     if distributed:
-        reduce_phase2(s2, mx, group)
+        reduce_phase2(s2, mx, group, flat23=flat[nq * rows * 4:])
+    if lazy == "device":                                                        # capturable in a CUDA graph: no host buffer, no event
+        return DeviceStats(flat, nq, rows)
     pending = PendingStats(flat, nq, rows)
     return pending if lazy else pending.result()                                # .result() is the only synchronisation
 

@@ -140,6 +140,13 @@ def test_parameters_are_honoured():
         out = cuda_solve(method, w["uv"], P, K, max_it=6, exit_tol=5e-2, f_weight=200.0, lm_lambda=1e-3)
         _, stable, it_stable = oracle_stability(method, w["uv"], P, K, ref=None)
         compare_solutions(out, ref, mask=stable if method == "lm" else None)
+    # the initial information and the initial "previous residual" are read by both filters (QEIF :2836, :2863; EIF2 :2067, :2101)
+    for method in ("qeif", "eif2"):
+        ref0 = orc.solve_batch(method, w["uv"], P, K)
+        ref = orc.solve_batch(method, w["uv"], P, K, params=orc.default_params(omega0=1e-3, res_old0=5e-3))
+        out = cuda_solve(method, w["uv"], P, K, omega0=1e-3, res_old0=5e-3)
+        assert np.abs(ref["R"] - ref0["R"]).max() > 1e-6 or (ref["iters"] != ref0["iters"]).any()
+        compare_solutions(out, ref)
 
 
 @pytest.mark.parametrize("method,tolR,tolT", [("qeif", 5e-4, 2e-4), ("linear_f2", 5e-3, 5e-3), ("linear_f1", 5e-3, 5e-3)])
@@ -407,6 +414,115 @@ def test_packed_pixel_transfer_is_lossless(dtype):
     assert packed_1[0] <= 12
     for k in ref:
         assert np.array_equal(got_1[k], ref_1[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("pix", ["int16", "uint16", "float32"])
+def test_narrow_pixel_host_entry_is_bit_identical(pix):
+    """pnpb200_solve_batch_host_px: detections held as int16 / uint16 / float32 (what a detector delivers; the reference
+    rounds its pixels itself, PNP_SOLVER_LIB.py:4549-4552) cross PCIe as they are and are widened on the device -- the
+    results are bit-identical to those of the same values handed over as FP64, with no pass over them on the host."""
+    import pnp_solver_test_b200 as pnp
+    P, K = pt.pattern_array(pt.synthetic_pattern(68)), pt.default_camera_matrix()
+    B, chunk = 9 * 512 + 33, 512
+    w = orc.synth(5, B, P, K)
+    uv64 = w["uv"].copy()
+    if pix == "uint16":
+        uv64 = np.abs(uv64)                                              # any values will do: the comparison is with the same values in FP64
+    if pix == "float32":
+        uv64 = (uv64 + 0.375).astype(np.float32).astype(np.float64)      # fractional pixels that a float32 holds exactly
+    narrow = uv64.astype({"int16": np.int16, "uint16": np.uint16, "float32": np.float32}[pix])
+    assert np.array_equal(narrow.astype(np.float64), uv64)
+    pat_h = torch.from_numpy(P)[None].contiguous()
+
+    def run(uv_t, method):
+        outs = {"R": torch.empty((B, 3, 3), dtype=torch.float64), "t": torch.empty((B, 3), dtype=torch.float64),
+                "euler": torch.empty((B, 3), dtype=torch.float64), "res_norm": torch.empty((B,), dtype=torch.float64),
+                "iters": torch.empty((B,), dtype=torch.int32)}
+        pipe = pnp.HostPipeline(torch.float64, chunk_problems=chunk, n_total=68, n_patterns=1, n_streams=3, pack_threads=2)
+        pipe.solve(method, uv_t, pat_h, K, outs)
+        packed = pipe.last_packed()
+        pipe.close()
+        return {k: v.numpy().copy() for k, v in outs.items()}, packed
+
+    if pix == "uint16":
+        t_narrow = torch.from_numpy(narrow.view(np.int16)).view(torch.uint16)
+    else:
+        t_narrow = torch.from_numpy(narrow)
+    for method in ("lm", "qeif"):
+        ref, _ = run(torch.from_numpy(uv64), method)
+        got, packed = run(t_narrow.pin_memory(), method)
+        assert packed[0] == 0                                            # nothing to pack: no host thread touched the pixels
+        for k in ref:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), (k, method)
+    # the drop-in class takes the narrow array as it is; FP32 arithmetic with int16 pixels works the same way
+    solver = pnp.PNP_SOLVER(K, [pt.synthetic_pattern(68)], verbose=False, method="lm")
+    a = solver.solve_pnp_batch_host(narrow, chunk_problems=1024)
+    b = solver.solve_pnp_batch_host(uv64, chunk_problems=1024, pack_threads=0)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    if pix == "int16":
+        s32 = pnp.PNP_SOLVER(K, [pt.synthetic_pattern(68)], verbose=False, method="qeif", dtype="f32")
+        a = s32.solve_pnp_batch_host(narrow, chunk_problems=1024, key_list=None)
+        b = s32.solve_pnp_batch_host(uv64.astype(np.float32), chunk_problems=1024, key_list=None, pack_threads=0)
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_host_pipeline_rejects_mismatched_buffers():
+    """HostPipeline.solve hands raw pointers to the C side, so dtype, shape, contiguity and device of every buffer are
+    checked first; the C entry point itself rejects a landmark count that disagrees with the pipeline and a caller
+    workspace (its chunks run concurrently)."""
+    import ctypes as C
+    import pnp_solver_test_b200 as pnp
+    from pnp_solver_test_b200 import _lib
+    P, K = pt.pattern_array(pt.get_golden_pattern()), pt.default_camera_matrix()
+    B = 64
+    uv = torch.from_numpy(orc.synth(0, B, P, K)["uv"])
+    pat = torch.from_numpy(P)[None].contiguous()
+    good = lambda: {"R": torch.empty((B, 3, 3), dtype=torch.float64), "iters": torch.empty((B,), dtype=torch.int32)}
+    pipe = pnp.HostPipeline(torch.float64, chunk_problems=32, n_total=15, n_patterns=1)
+    pipe.solve("qeif", uv, pat, K, good())
+    bad_calls = [
+        (uv.to(torch.float16), pat, good()),                                             # pixel type the pipeline cannot widen
+        (uv[:, :14].contiguous(), pat, good()),                                          # wrong landmark count
+        (uv.transpose(1, 2), pat, good()),                                               # not [B, n, 2]
+        (uv[::2], pat, {"R": torch.empty((B // 2, 3, 3), dtype=torch.float64)}),         # not contiguous
+        (uv, pat.float(), good()),                                                       # pattern dtype
+        (uv, torch.cat([pat, pat]), good()),                                             # pattern count
+        (uv, pat, {"R": torch.empty((B - 1, 3, 3), dtype=torch.float64)}),               # short output
+        (uv, pat, {"R": torch.empty((B, 3, 3), dtype=torch.float32)}),                   # output dtype
+        (uv, pat, {"iters": torch.empty((B,), dtype=torch.int64)}),                      # iters must be int32
+        (uv, pat, {"R": torch.empty((B, 3, 3), dtype=torch.float64, device="cuda")}),    # output on the device
+        (uv.cuda(), pat, good()),                                                        # pixels on the device
+    ]
+    for u, p_, o in bad_calls:
+        with pytest.raises(ValueError):
+            pipe.solve("qeif", u, p_, K, o)
+    ws = torch.empty((1 << 20,), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        pipe.solve("lm", uv, pat, K, good(), params=pnp.default_params(workspace=ws.data_ptr(), workspace_bytes=1 << 20))
+    Kh = (C.c_double * 9)(*np.asarray(K, np.float64).reshape(-1))
+    out = torch.empty((B, 9), dtype=torch.float64)
+    args = lambda n, prm: (pipe._h, C.c_int(0), C.c_int64(B), C.c_int(n), C.c_void_p(uv.data_ptr()), C.c_void_p(pat.data_ptr()), None, Kh,
+                           prm, C.c_void_p(out.data_ptr()), None, None, None, None, None)
+    assert _lib.lib.pnpb200_solve_batch_host(*args(14, None)) == -1                    # n != n_total without a selection
+    prm = pnp.default_params(workspace=ws.data_ptr(), workspace_bytes=1 << 20)
+    assert _lib.lib.pnpb200_solve_batch_host(*args(15, C.byref(prm))) == -1
+    assert _lib.lib.pnpb200_solve_batch_host(*args(15, None)) == 0
+    pipe.close()
+    # a singular camera matrix is an argument error, not a batch of NaNs
+    with pytest.raises(pnp.PnpB200Error):
+        pnp.solve_batch("qeif", dev(uv.numpy()), dev(P)[None], np.zeros((3, 3)))
+    # pinned buffers from the library itself (write-combined for the pixels)
+    hb = pnp.host_buffer((B, 15, 2), torch.int16, write_combined=True)
+    hb.copy_(uv.to(torch.int16))
+    o = good()
+    pipe = pnp.HostPipeline(torch.float64, chunk_problems=32, n_total=15, n_patterns=1)
+    pipe.solve("qeif", hb, pat, K, o)
+    ref = good()
+    pipe.solve("qeif", uv, pat, K, ref)
+    pipe.close()
+    assert torch.equal(o["R"], ref["R"]) and torch.equal(o["iters"], ref["iters"])
 
 
 @pytest.mark.parametrize("method,n,mapping", [("qeif", 15, 1), ("qeif", 15, 32), ("lm", 68, 2), ("lm", 68, 1), ("linear_f2", 68, 2),

@@ -250,3 +250,37 @@ def test_face_variation_workload_and_fragility_analysis_match_reference():
         assert np.array_equal(res[q]["fragile_point_count"], np.array([ref["fragile_point_count_dict"][k] for k in kk]))
         assert np.abs(res[q]["top_similarity"] / ref["top_similarity"] - 1).max() < 1e-10
         assert res[q]["value_max"] == ref["value_max"] and abs(res[q]["top_value_mean"] - ref["top_value_mean"]) < 1e-12
+
+
+@pytest.mark.parametrize("method,n,dtype,subset", [("lm", 68, torch.float64, False), ("linear_f2", 68, torch.float64, False),
+                                                 ("lm", 15, torch.float64, False), ("lm", 68, torch.float32, False),
+                                                 ("lm_plus", 68, torch.float64, False), ("qeif", 15, torch.float64, True),
+                                                 ("lm", 1024, torch.float64, False), ("eif2", 15, torch.float64, False)])
+def test_fused_solve_report_equals_the_two_calls(method, n, dtype, subset):
+    """pnpb200_solve_report_batch (the residual pass of the moment mapping folded into the report kernel, the pixel rows
+    read twice instead of three times) returns what pnpb200_solve_batch followed by pnpb200_report_batch_strided return --
+    bit for bit, for a ragged batch, for every method and shape (those that cannot fuse run the two calls inside)."""
+    import pnp_solver_test_b200 as pnp
+    from pnp_solver_test_b200 import workload as wl
+    pat = pt.get_golden_pattern() if n == 15 else pt.synthetic_pattern(n)
+    P, K = pt.pattern_array(pat), pt.default_camera_matrix()
+    B = 3 * 1024 + 45 if n < 1024 else 77
+    w = wl.synth_batch(7, B, P, K, dtype=dtype)
+    idx = [list(pat).index(k) for k in pt.LM_KEY_LIST_6] if subset else None
+    patd = dev(P, dtype)[None]
+    a = pnp.solve_batch(method, w["uv"], patd, K, point_index=idx)
+    r = wl.report_batch(P, w["uv"], K, a["R"], a["t"], a["euler"], w["gt"])
+    f = wl.solve_report_batch(method, w["uv"], patd, K, w["gt"], point_index=idx)
+    torch.cuda.synchronize()
+    bits = lambda x: x.contiguous().view(torch.int64 if x.element_size() == 8 else torch.int32)
+    for k in ("R", "t", "euler", "res_norm", "iters"):
+        assert torch.equal(bits(f[k]), bits(a[k])), k
+    for k in ("report", "flags", "max_idx"):
+        assert torch.equal(bits(f[k]), bits(r[k])), k
+    # res_norm against the oracle where parity is well-posed (LM: first 512 problems)
+    if dtype == torch.float64 and method in ("lm", "linear_f2") and n < 1024:
+        from gpu_util import oracle_stability
+        uv = w["uv"][:512].cpu().numpy()
+        ref, stable, _ = oracle_stability(method, uv, P, K)
+        d = np.abs(f["res_norm"][:512].cpu().numpy() - ref["res_norm"])[stable] / ref["res_norm"][stable]
+        assert d.max() < 1e-9

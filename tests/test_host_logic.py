@@ -70,8 +70,12 @@ def _stats_worker(rank, world_size, port, q):
         d = (e[m] - t[m]) - mean[k]
         s2[k] = [(d * d).sum(), np.abs(e[m] - t[m]).sum(), np.abs(d).sum(), 0.0]
         mx[k] = np.abs(d).max() if m.any() else 0.0
+    # the exchange as `statistics` does it (ONE all_gather of s2 | max and a local fold) and as two all-reduces
+    flat = torch.cat([torch.from_numpy(s2).flatten(), torch.from_numpy(mx)]).contiguous()
+    s2m, mxm = wl.reduce_phase2(flat[:n_class * 4].view(n_class, 4), flat[n_class * 4:], flat23=flat)
     s2, mx = wl.reduce_phase2(torch.from_numpy(s2), torch.from_numpy(mx))
-    out = wl.finalize_stats(torch.from_numpy(s1), s2, mx).numpy()
+    assert torch.allclose(s2m, s2, rtol=1e-15, atol=0) and torch.equal(mxm, mx)
+    out = wl.finalize_stats(torch.from_numpy(s1), s2m, mxm).numpy()
     if rank == 0:
         q.put(out)
     dist.barrier()

@@ -44,23 +44,45 @@ for r in rows[2:]:
         print("| %s | %.3f |" % (h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v))
     print()
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
-if len(rows) > 3:
-    hdr = rows[1]
-    ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) >= len(hdr) and r[ix["# Samples"]] != "# Samples"]
+# the source page lists the launches one after the other, each introduced by a "Kernel Name" row and a header row
+blocks, cur = [], None
+for r in csv.reader(io.StringIO(src)):
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1], "hdr": None, "rows": []}
+        blocks.append(cur)
+    elif cur is not None and cur["hdr"] is None:
+        cur["hdr"] = r
+    elif cur is not None and len(r) >= len(cur["hdr"]):
+        cur["rows"].append(r)
+top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+seen = set()
+for b in blocks:
+    key = (b["name"], len(b["rows"]), b["rows"][0][1] if b["rows"] else "")
+    if key in seen:                                        # every launch is listed twice (the same SASS under two views)
+        continue
+    seen.add(key)
+    ix = {h: i for i, h in enumerate(b["hdr"])}
     byop, ex = collections.Counter(), collections.Counter()
-    for r in data:
+    hot = []
+    for r in b["rows"]:
         s = r[ix["Source"]].strip()
         if not s:
             continue
         op = (s.split()[1] if s.startswith("@") else s.split()[0]).split(".")[0]
-        byop[op] += int(r[ix["# Samples"]] or 0)
-        ex[op] += int(r[ix["Instructions Executed"]] or 0)
+        n_s, n_e = int(r[ix["# Samples"]] or 0), int(r[ix["Instructions Executed"]] or 0)
+        byop[op] += n_s
+        ex[op] += n_e
+        hot.append((n_s, n_e, s))
     tot, te = sum(byop.values()) or 1, sum(ex.values()) or 1
-    print("SASS opcode mix of the first captured launch (warp-level instructions executed, stall samples):\n")
+    print("### SASS of `%s`\n" % b["name"][:110])
+    print("%d SASS instructions, %d warp-level instructions executed, %d stall samples.\n" % (len(hot), te, tot))
     print("| opcode | executed | share | stall samples |\n|---|---|---|---|")
-    for op, c in ex.most_common(14):
+    for op, c in ex.most_common(12):
         print("| %s | %d | %.1f%% | %.1f%% |" % (op, c, 100.0 * c / te, 100.0 * byop[op] / tot))
     tma = [op for op in ex if op.startswith(("UBLKCP", "UTMA", "SYNCS"))]
-    print("\nTMA / mbarrier opcodes present: %s" % (", ".join(sorted(tma)) or "none"))
+    print("\nTMA / mbarrier opcodes present: %s\n" % (", ".join(sorted(tma)) or "none"))
+    print("Hottest instructions (stall samples, share, times executed):\n")
+    print("| samples | share | executed | instruction |\n|---|---|---|---|")
+    for n_s, n_e, s in sorted(hot, key=lambda x: -x[0])[:top_n]:
+        print("| %d | %.1f%% | %d | `%s` |" % (n_s, 100.0 * n_s / tot, n_e, s[:90]))
+    print()
