@@ -37,7 +37,7 @@ extern "C" {
 #define PNPB200_METHOD_LINEAR_F1  3  /* solve_pnp_single_pattern,               PNP_SOLVER_LIB.py:205-430   */
 #define PNPB200_METHOD_LM_PLUS    4  /* NOT in the reference (non-parity extra): linear F2 initial pose, then LM's 12-state
                                         damped Gauss-Newton with the true constraint gradients and a convergence test
-                                        (max |dx| <= 1e-10); res_norm at the returned state; one pattern, moment mapping */
+                                        (max |dx| <= 1e-10); res_norm at the returned state; moment mapping only */
 #define PNPB200_METHOD_EIF2       5  /* solve_pnp_EIF2_single_pattern,          PNP_SOLVER_LIB.py:2001-2276: iterated information filter
                                         on LM's 12-state model with EKF2_get_process_covariance_R (:3668-3716) and QEIF's early exit */
 
@@ -47,8 +47,9 @@ extern "C" {
 /* execution shape (0 = let the library choose from n) */
 #define PNPB200_MAP_AUTO    0
 #define PNPB200_MAP_THREAD  1   /* one problem per thread, correspondences staged in shared memory */
-#define PNPB200_MAP_MOMENT  2   /* LM / linear F2, one pattern: moments -> O(1) iterations ->      */
-                                /* point-wise residual, as three streaming kernels (default there) */
+#define PNPB200_MAP_MOMENT  2   /* LM / linear F2: moments -> O(1) iterations -> point-wise        */
+                                /* residual, as three streaming kernels (default there); several   */
+                                /* patterns: one such solve per pattern, arg-min in between        */
 #define PNPB200_MAP_WARP    32  /* one problem per warp, shuffle-reduced normal equations          */
 
 #define PNPB200_OK          0
@@ -131,6 +132,15 @@ int pnpb200_solve_batch(int method, int dtype, int64_t B, int n_total, int n,
                         const pnpb200_params* params,
                         void* R, void* t, void* euler_deg, void* res_norm,
                         int32_t* iters, int32_t* best_pattern, void* stream);
+
+/*
+ * Image points whose homogeneous coordinate is not 1.  The reference's packing stage multiplies the (3,1) vector it is
+ * given by K^-1 without looking at its third entry (f2_get_B_xy, PNP_SOLVER_LIB.py:3305-3307), and its own projection
+ * emits w = -1 for points behind the camera (perspective_projection :4548).  This entry computes that product for
+ * n_points points, uvw [n_points, 3] -> uv_normalised [n_points, 2] = rows 0, 1 of K^-1 [u, v, w]^T (both device, dtype);
+ * pnpb200_solve_batch is then called on uv_normalised with K = identity.  (Pixels with w = 1 need none of this.)
+ */
+int pnpb200_normalise_uvw(int dtype, int64_t n_points, const void* uvw, const double* K, void* uv_normalised, void* stream);
 
 /*
  * Per-kernel device times of the pnpb200_solve_batch calls made by this thread with

@@ -466,6 +466,39 @@ def lm_trace_case(PNPS, tag, src_tag):
           % (tag, B, np.bincount(first_div, minlength=16)[1:].tolist(), worst))
 
 
+def homogeneous_case(PNPS, tag, B, seed):
+    """Image points whose homogeneous coordinate is not 1: f2_get_B_xy multiplies the (3,1) vector it is given by K^-1
+    (PNP_SOLVER_LIB.py:3305-3307) and perspective_projection emits (x, y, z) / |z|, i.e. w = -1, behind the camera (:4548).
+    The stress workload's points with two of the fifteen vectors negated (u, v, 1) -> (-u, -v, -1) -- the same ray -- and
+    one scaled by 2, solved by the unmodified reference (solve_pnp = QEIF on the 6-key subset, and linear F2 on all)."""
+    from pnp_solver_test_b200 import patterns as pt
+    K = pt.default_camera_matrix()
+    pat = pt.get_golden_pattern("Alexander")
+    solver_gt = quiet(PNPS.PNP_SOLVER, K, [pat], [1.0], verbose=False)
+    solver = quiet(PNPS.PNP_SOLVER, K, [pat], [1.0], verbose=False)
+    keys = list(pat.keys())
+    rng = np.random.default_rng(seed)
+    uvw = np.zeros((B, 15, 3))
+    out = {m: dict(R=np.zeros((B, 3, 3)), t=np.zeros((B, 3)), euler=np.zeros((B, 3)), res_norm=np.zeros(B)) for m in ("qeif6", "linear_f2")}
+    flip = [keys.index("eye_l_96"), keys.index("chin_t_16")]
+    for b in range(B):
+        roll, pitch, yaw, depth, tt = draw_pose(rng)
+        R_gt = solver_gt.get_rotation_matrix_from_Euler(roll, yaw, pitch, is_degree=True)
+        pts = quiet(solver_gt.perspective_projection_golden_landmarks, R_gt, tt, is_quantized=True)
+        for j in flip:
+            pts[keys[j]] = -pts[keys[j]]
+        pts[keys[3]] = 2.0 * pts[keys[3]]
+        uvw[b] = np.array([pts[k].reshape(3) for k in keys])
+        for m, fn in (("qeif6", lambda: solver.solve_pnp(pts)),
+                      ("linear_f2", lambda: solver.solve_pnp_formulation_2_single_pattern(pts, solver.np_point_3d_pretransfer_dict_list[0]))):
+            Rb, tb, t3, r_, y_, p_, rn = quiet(fn)
+            out[m]["R"][b], out[m]["t"][b], out[m]["euler"][b], out[m]["res_norm"][b] = Rb, np.array(tb).reshape(3), (r_, y_, p_), rn
+    np.savez_compressed(os.path.join(OUT, tag + ".npz"), K=K, pattern=pt.pattern_array(pat), uvw=uvw,
+                        key_index=np.array([keys.index(k) for k in pt.LM_KEY_LIST_6], np.int32),
+                        **{"%s_%s" % (m, k): v for m, d in out.items() for k, v in d.items()})
+    print("%-28s B=%4d | points with w != 1 per problem: %d" % (tag, B, int((uvw[0, :, 2] != 1).sum())))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     PNPS, TTBX = load_reference()
@@ -511,6 +544,8 @@ def main():
     if not only or "lm_trace" in only:
         for src in ("lm_n15_q", "lm_n15_x", "lm_n68_q", "lm_n68_x"):
             lm_trace_case(PNPS, src.replace("lm_", "lmtrace_"), src)
+    if not only or "homogeneous" in only:
+        homogeneous_case(PNPS, "homogeneous_n15", 48, 63)
     if not only or "euler" in only:
         print("euler fixture:", euler_fixture(), "vectors")
 

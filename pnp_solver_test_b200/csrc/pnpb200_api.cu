@@ -202,7 +202,8 @@ int pnpb200_profile_read(float* ms, int* n_calls)
 
 int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping)
 {
-    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS) && n_patterns == 1;
+    (void)n_patterns;                                       // several patterns are solved one after the other with the same scratch
+    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS);
     if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
     const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
     return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;

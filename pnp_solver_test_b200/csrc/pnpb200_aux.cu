@@ -974,6 +974,19 @@ __global__ void __launch_bounds__(256) k_widen(long long n, const Tin* __restric
     }
 }
 
+// f2_get_B_xy (PNP_SOLVER_LIB.py:3291-3312) for image points whose homogeneous coordinate is not 1: nu = K^-1 [u, v, w]^T,
+// (B_x, B_y) = (nu_0, nu_1) -- the reference multiplies whatever it is given (:3307), and perspective_projection emits
+// w = -1 for points behind the camera (:4548).  The solve kernels then run with K = I on these normalised coordinates.
+template <typename T>
+__global__ void __launch_bounds__(256) k_normalise_uvw(long long n, const T* __restrict__ uvw, KMat kinv, T* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double u = (double)uvw[3 * i], v = (double)uvw[3 * i + 1], w = (double)uvw[3 * i + 2];
+    out[2 * i] = (T)(kinv.k[0] * u + kinv.k[1] * v + kinv.k[2] * w);
+    out[2 * i + 1] = (T)(kinv.k[3] * u + kinv.k[4] * v + kinv.k[5] * w);
+}
+
 __global__ void k_selftest_sincos(long long n, const double* __restrict__ in, double* s, double* c)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1303,6 +1316,22 @@ int pnpb200_classify_drpy(int64_t B, const double* gt, const double* const* bins
     if (total > (1 << 20)) return PNPB200_EINVAL;
     if (B == 0) return PNPB200_OK;
     k_classify_drpy<<<grid_for(B, 256), 256, 0, (cudaStream_t)stream>>>(B, gt, b4, class_id); count_kernel_launches(1);
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
+int pnpb200_normalise_uvw(int dtype, int64_t n_points, const void* uvw, const double* K, void* uv_normalised, void* stream)
+{
+    if (n_points < 0 || !uvw || !K || !uv_normalised) return PNPB200_EINVAL;
+    if (n_points == 0) return PNPB200_OK;
+    KMat ki;
+    host_inv3(K, ki.k);
+    for (int e = 0; e < 9; ++e)
+        if (!(ki.k[e] - ki.k[e] == 0.0)) return PNPB200_EINVAL;
+    const unsigned grid = grid_for(n_points, 256);
+    DISPATCH_DTYPE(dtype, (k_normalise_uvw<double><<<grid, 256, 0, (cudaStream_t)stream>>>(n_points, (const double*)uvw, ki, (double*)uv_normalised)),
+                   (k_normalise_uvw<float><<<grid, 256, 0, (cudaStream_t)stream>>>(n_points, (const float*)uvw, ki, (float*)uv_normalised)));
+    count_kernel_launches(1);
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;
 }

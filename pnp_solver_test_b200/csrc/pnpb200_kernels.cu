@@ -900,6 +900,68 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     return PNPB200_OK;
 }
 
+// solve_pnp's arg-min over patterns (:166-199) for the moment mapping, which solves one pattern per pass: the candidate of
+// pattern p replaces the best so far where its res_norm is strictly smaller (first wins; a NaN never wins, as `<` in the reference)
+template <typename T>
+__global__ void __launch_bounds__(256) k_merge_best(long long B, int p, const T* __restrict__ cR, const T* __restrict__ ct,
+                                                    const T* __restrict__ ce, const T* __restrict__ cres, const int32_t* __restrict__ cit,
+                                                    T* R, T* t, T* e, T* res, int32_t* it, int32_t* best, T* best_res)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const T r = cres[b];
+    if (!(r < best_res[b])) return;
+    best_res[b] = r;
+    if (res) res[b] = r;
+    if (R) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[b * 9 + k] = cR[b * 9 + k];
+    }
+    if (t) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[b * 3 + k] = ct[b * 3 + k];
+    }
+    if (e) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e[b * 3 + k] = ce[b * 3 + k];
+    }
+    if (it) it[b] = cit[b];
+    if (best) best[b] = p;
+}
+
+// LM / linear F2 over several stored patterns: one moment-mapping solve per pattern, arg-min on res_norm in between
+template <typename T, int METHOD>
+static int launch_moment_patterns(const SolveArgs<T>& a, const DeviceProps& dp, cudaStream_t stream)
+{
+    const size_t B = (size_t)a.B;
+    // candidate outputs of patterns 1.., and the running minimum when the caller did not ask for res_norm
+    const size_t elems = B * (9 + 3 + 3 + 1 + 1);
+    T* buf = nullptr;
+    PNP_CUDA_OK(cudaMallocAsync((void**)&buf, elems * sizeof(T) + B * sizeof(int32_t), stream));
+    struct Guard { void* p; cudaStream_t st; ~Guard() { cudaFreeAsync(p, st); } } guard = { buf, stream };
+    T *cR = buf, *ct = cR + B * 9, *ce = ct + B * 3, *cres = ce + B * 3, *own_res = cres + B;
+    int32_t* cit = reinterpret_cast<int32_t*>(own_res + B);
+    for (int p = 0; p < a.n_patterns; ++p) {
+        SolveArgs<T> one = a;
+        one.n_patterns = 1;
+        one.pattern = a.pattern + (size_t)p * a.n_total * 3;
+        if (p == 0) {
+            one.res = a.res ? a.res : own_res;
+        } else {
+            one.R = cR; one.t = ct; one.euler = a.euler ? ce : nullptr; one.res = cres; one.iters = cit; one.best = nullptr;
+        }
+        const int rc = launch_moment<T, METHOD>(one, dp, stream);
+        if (rc != PNPB200_OK) return rc;
+        if (p > 0) {
+            k_merge_best<T><<<(unsigned)((a.B + 255) / 256), 256, 0, stream>>>(a.B, p, cR, ct, ce, cres, cit, a.R, a.t, a.euler, a.res, a.iters,
+                                                                               a.best, a.res ? a.res : own_res);
+            count_kernel_launches(1);
+        }
+    }
+    PNP_CUDA_OK(cudaGetLastError());
+    return PNPB200_OK;
+}
+
 template <typename T, int METHOD>
 static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
 {
@@ -913,12 +975,13 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     const size_t thread_smem = g.tile_bytes + pat_bytes + idx_bytes + 16;
     const size_t warp_smem = pat_bytes + idx_bytes;
     if (mapping == PNPB200_MAP_AUTO) {
-        if (has_moment_form && a.n_patterns == 1) mapping = PNPB200_MAP_MOMENT;
+        if (has_moment_form) mapping = PNPB200_MAP_MOMENT;
         else mapping = (g.tile_bytes <= 48 * 1024 && thread_smem <= (size_t)dp.max_smem_optin) ? PNPB200_MAP_THREAD : PNPB200_MAP_WARP;
     }
     if (mapping == PNPB200_MAP_MOMENT) {
-        if (!has_moment_form || a.n_patterns != 1) return PNPB200_EINVAL;
-        if (has_moment_form) return launch_moment<T, has_moment_form ? METHOD : PNPB200_METHOD_LM>(a, dp, stream);
+        if (!has_moment_form) return PNPB200_EINVAL;
+        if (a.n_patterns == 1) return launch_moment<T, has_moment_form ? METHOD : PNPB200_METHOD_LM>(a, dp, stream);
+        return launch_moment_patterns<T, has_moment_form ? METHOD : PNPB200_METHOD_LM>(a, dp, stream);
     }
     if (mapping == PNPB200_MAP_THREAD) {
         if (thread_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
@@ -981,10 +1044,11 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
     case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
     case PNPB200_METHOD_LM_PLUS: {
         // non-parity extra: exists in the moment mapping only, one pattern
-        if (n_patterns != 1 || (prm.mapping != PNPB200_MAP_AUTO && prm.mapping != PNPB200_MAP_MOMENT)) return PNPB200_EINVAL;
+        if (prm.mapping != PNPB200_MAP_AUTO && prm.mapping != PNPB200_MAP_MOMENT) return PNPB200_EINVAL;
         DeviceProps dp;
         int rc = get_device_props(&dp);
         if (rc != PNPB200_OK) return rc;
+        if (n_patterns > 1) return launch_moment_patterns<T, PNPB200_METHOD_LM_PLUS>(a, dp, stream);
         return launch_moment<T, PNPB200_METHOD_LM_PLUS>(a, dp, stream);
     }
 #elif PNP_GROUP == 2

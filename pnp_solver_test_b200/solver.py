@@ -343,14 +343,31 @@ class PNP_SOLVER(object):
         return torch.from_numpy(arr).to(device=self.device, dtype=self._tdtype())
 
     def _pack_image_points(self, np_point_image_dict, keys):
-        """[1, n, 2] device tensor (f2_get_B_xy's input, :3291).  The homogeneous coordinate must be 1."""
-        pts = np.zeros((1, len(keys), 2))
+        """(uv [1, n, 2] device tensor, K to solve with) -- f2_get_B_xy's input (:3291).  Points are (3,1) homogeneous
+        vectors; when a third entry is not 1 (the reference's own projection emits -1 behind the camera, :4548) the
+        product K^-1 [u, v, w]^T that the reference forms (:3307) is taken on the device and the solve runs on the
+        normalised coordinates with K = I.  Never raises on the numeric path, like the reference."""
+        pts = np.zeros((1, len(keys), 3))
         for i, k in enumerate(keys):
             v = np.asarray(np_point_image_dict[k], dtype=np.float64).reshape(-1)
-            if v.shape[0] >= 3 and v[2] != 1.0:
-                raise ValueError("image point %r has homogeneous coordinate %r != 1" % (k, v[2]))
             pts[0, i, 0], pts[0, i, 1] = v[0], v[1]
-        return torch.from_numpy(pts).to(device=self.device, dtype=self._tdtype())
+            pts[0, i, 2] = v[2] if v.shape[0] >= 3 else 1.0
+        return self._uv_and_K(torch.from_numpy(pts).to(device=self.device, dtype=self._tdtype()))
+
+    def _uv_and_K(self, pts):
+        """pts [B, n, 2] or [B, n, 3] device tensor -> (uv [B, n, 2], K): see _pack_image_points"""
+        if pts.shape[-1] == 2:
+            return pts.contiguous(), self.np_K_camera_est
+        if bool((pts[..., 2] == 1).all()):
+            return pts[..., :2].contiguous(), self.np_K_camera_est
+        pts = pts.contiguous()
+        out = torch.empty(pts.shape[:-1] + (2,), dtype=pts.dtype, device=pts.device)
+        Kh, Kp = _k_host(self.np_K_camera_est)
+        with torch.cuda.device(pts.device):
+            check(lib.pnpb200_normalise_uvw(C.c_int(_dtype_code(pts.dtype)), C.c_int64(int(pts.numel() // 3)), ptr(pts), Kp, ptr(out),
+                                            _stream_ptr(pts.device)), "pnpb200_normalise_uvw")
+        _lib.count_launch()
+        return out, np.eye(3)
 
     def _finish_single(self, out):
         """device outputs of a B=1 solve -> the reference's 7-tuple, plus its side effects."""
@@ -364,9 +381,9 @@ class PNP_SOLVER(object):
         return (R, t, float(t[2, 0]), float(e[0]), float(e[1]), float(e[2]), res)
 
     def _solve_single(self, method, np_point_image_dict, np_point_3d_pretransfer_dict, keys):
-        uv = self._pack_image_points(np_point_image_dict, keys)
+        uv, K = self._pack_image_points(np_point_image_dict, keys)
         pat = self._pack_patterns([np_point_3d_pretransfer_dict], keys)
-        out = solve_batch(method, uv, pat, self.np_K_camera_est, params=self.params)
+        out = solve_batch(method, uv, pat, K, params=self.params)
         return self._finish_single(out)
 
     # ---------------------------------------------------------------- solvers
@@ -375,9 +392,9 @@ class PNP_SOLVER(object):
         keys = list(self.LM_key_list) if self.LM_key_list is not None else list(self.np_point_3d_pretransfer_dict_list[0].keys())
         if self.method != "qeif":   # only the QEIF solver honours LM_key_list (:2576 vs :2784)
             keys = list(np_point_image_dict.keys())
-        uv = self._pack_image_points(np_point_image_dict, keys)
+        uv, K = self._pack_image_points(np_point_image_dict, keys)
         pat = self._pack_patterns(self.np_point_3d_pretransfer_dict_list, keys)
-        out = solve_batch(self.method, uv, pat, self.np_K_camera_est, params=self.params)
+        out = solve_batch(self.method, uv, pat, K, params=self.params)
         self.set_golden_pattern_id(int(out["best_pattern"][0].item()))     # :199
         return self._finish_single(out)
 
@@ -405,8 +422,9 @@ class PNP_SOLVER(object):
     def solve_pnp_batch(self, uv, method=None, key_list="default", params=None):
         """The per-problem script loop as one launch.
 
-        uv: [B, n_total, 2] pixels in the key order of the stored patterns -- a CUDA tensor, or a
-        NumPy array / CPU tensor (copied to the device).  key_list: landmark subset; "default" =
+        uv: [B, n_total, 2] pixels (or [B, n_total, 3] homogeneous image points, third entry as the reference's
+        dicts carry it) in the key order of the stored patterns -- a CUDA tensor, or a NumPy array / CPU tensor
+        (copied to the device).  key_list: landmark subset; "default" =
         the 6 keys of solve_pnp() for 'qeif', all points otherwise.  Returns a dict of CUDA
         tensors (see solve_batch) and, like solve_pnp, works over every stored pattern."""
         method = method or self.method
@@ -416,11 +434,11 @@ class PNP_SOLVER(object):
         idx = None if key_list is None else [all_keys.index(k) for k in key_list]
         if not torch.is_tensor(uv):
             uv = torch.from_numpy(np.ascontiguousarray(uv))
-        uv = uv.to(device=self.device, dtype=self._tdtype())
+        uv, K = self._uv_and_K(uv.to(device=self.device, dtype=self._tdtype()))
         ck = ("all", self.dtype_code)
         if ck not in self._dev_cache:
             self._dev_cache[ck] = self._pack_patterns(self.np_point_3d_pretransfer_dict_list, all_keys)
-        return solve_batch(method, uv, self._dev_cache[ck], self.np_K_camera_est, point_index=idx,
+        return solve_batch(method, uv, self._dev_cache[ck], K, point_index=idx,
                            params=params if params is not None else self.params)
 
     def solve_pnp_batch_host(self, uv, method=None, key_list="default", params=None, chunk_problems=1 << 16, pack_threads=None):

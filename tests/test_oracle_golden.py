@@ -139,3 +139,17 @@ def test_ekf2_and_ukf2_have_no_well_posed_parity_target():
         assert s["UKF2"].max() < 1e-8                                       # ... so a stated 1e-7 bound would be assertable
         assert s["EIF2"].max() < 1e-11
         assert (s["LM"] < 1e-10).mean() >= 0.8                              # LM: well-posed on most inputs, chaotic on the rest
+
+
+def test_oracle_on_image_points_with_homogeneous_coordinate_not_one():
+    """The reference multiplies the (3,1) image vector it is given by K^-1 whatever its third entry (PNP_SOLVER_LIB.py:3307;
+    its projection emits w = -1 behind the camera, :4548).  The drop-in forms the same product and solves on the normalised
+    coordinates with K = I: checked here with the oracle against the unmodified reference's outputs."""
+    g = load_golden("homogeneous_n15")
+    nu = np.einsum("ij,bnj->bni", np.linalg.inv(g["K"]), g["uvw"])[..., :2]
+    idx = g["key_index"]
+    o = orc.solve_batch("qeif", nu[:, idx], g["pattern"][idx], np.eye(3))
+    assert np.abs(o["R"] - g["qeif6_R"]).max() < 1e-9 and np.abs(o["t"] - g["qeif6_t"]).max() < 1e-9
+    assert np.abs(o["res_norm"] - g["qeif6_res_norm"]).max() < 1e-11
+    o = orc.solve_batch("linear_f2", nu, g["pattern"], np.eye(3))
+    assert np.abs(o["R"] - g["linear_f2_R"]).max() < 1e-9 and np.abs(o["t"] - g["linear_f2_t"]).max() < 1e-9
