@@ -487,7 +487,7 @@ def run_ours(args):
     # exchanges captured once): the timed region then holds no Python, no allocator and no launch latency of the host, which
     # is what separated 8 ranks sharing one host from a single rank.  Falls back to eager launches if the capture fails.
     S = _largest_divisor(args.steps, 20)
-    graph, graph_note, per_graph_launches = None, "off (--no-graph)", 0
+    graph, graph_note, per_graph_launches, g = None, "off (--no-graph)", 0, None
     if not args.no_graph:
         try:
             _lib.check(_lib.lib.pnpb200_profile_reset(), "pnpb200_profile_reset")
@@ -505,6 +505,7 @@ def run_ours(args):
         except Exception as e:                              # noqa: BLE001
             graph, graph_note = None, "off (capture failed: %s)" % (str(e).splitlines()[0][:120] if str(e) else type(e).__name__)
             torch.cuda.synchronize()
+    g = None
     barrier()
     if world > 1:                                           # device-side rendezvous: every GPU leaves this all-reduce together, so the
         dist.all_reduce(torch.zeros(1, device=dev))         # timed region starts aligned across ranks whatever the hosts' skew
@@ -665,9 +666,21 @@ def run_ours(args):
     if not args.no_extra and world == 1:
         extra = extra_configs(dev, sampler_index=local)
 
-    if rank != 0:
+    def leave():
+        """A process group whose collectives were captured in a still-alive CUDA graph does not tear down reliably
+        (observed: destroy_process_group never returned after a 2-rank graph run).  Drop the graph, let every rank
+        reach this point, and leave without the destructor chain."""
+        nonlocal graph
+        graph = None
+        keep.clear()
+        sys.stdout.flush()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return 0
 
     # ---- roofline of the dominant kernel (k_iterate<double, LM>): FP64 FMA pipe
@@ -719,8 +732,7 @@ def run_ours(args):
         "extra_configs": extra,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
     return 0
 
 

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnpb200.so")
+# PNPB200_LIB selects another build of the same library (tools/build_variant.py: A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("PNPB200_LIB") or os.path.join(_HERE, "libpnpb200.so")
 
 METHOD_QEIF, METHOD_LM, METHOD_LINEAR_F2, METHOD_LINEAR_F1 = 0, 1, 2, 3
 METHOD_LM_PLUS = 4

@@ -206,7 +206,7 @@ int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns
     const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS);
     if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
     const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
-    return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
+    return ((((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC + 1) & ~(int64_t)1) + (int64_t)PNP_PTAB_W * PNP_PTAB_MAX_N) * esz;
 }
 
 static int solve_batch_impl(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,
@@ -277,7 +277,7 @@ int pnpb200_solve_report_batch(int method, int dtype, int64_t B, int n_total, in
                              report_stride_column, flags, max_idx, nullptr, st);
     }
     const size_t esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
-    const size_t ws_bytes = ((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)B + PNP_PATC) * esz;
+    const size_t ws_bytes = (size_t)pnpb200_workspace_bytes(method, dtype, B, 1, PNPB200_MAP_MOMENT);
     void* ws = nullptr;
     const bool own_ws = !(prm.workspace && prm.workspace_bytes >= (int64_t)ws_bytes);
     if (own_ws) {
@@ -378,7 +378,7 @@ int pnpb200_pipeline_create(pnpb200_pipeline** out, int dtype, int64_t chunk_pro
     p->esz = (dtype == PNPB200_DTYPE_F64) ? 8 : 4;
     p->d_pattern = nullptr;
     p->pack_threads = 0; p->last_packed = 0; p->last_chunks = 0;
-    p->ws_bytes = ((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)chunk_problems + PNP_PATC) * p->esz;
+    p->ws_bytes = (size_t)pnpb200_workspace_bytes(PNPB200_METHOD_LM, dtype, chunk_problems, 1, PNPB200_MAP_MOMENT);
     *out = p;
     PNP_CUDA_OK(cudaGetDevice(&p->device));
     PNP_CUDA_OK(cudaMalloc(&p->d_pattern, p->esz * (size_t)n_patterns * n_total * 3));

@@ -434,8 +434,15 @@ __global__ void __launch_bounds__(32) k_report_thread(const __grid_constant__ Re
 // RES != 0 fuses the last pass of the moment mapping into it (pnpb200_solve_report_batch): the rows are streamed ONCE
 // for the error report and for res_norm = ||z - hx|| at the state k_iterate stored (RES = 1: LM, PNP_SOLVER_LIB.py:2679-2681;
 // RES = 2: linear F2, :3368-3374) -- the same arithmetic, in the same order, as k_stream_chunk<T, METHOD, 1>.
+#ifndef PNP_REPORT_UNROLL
+#define PNP_REPORT_UNROLL 2       // landmarks in flight per thread
+#endif
+#ifndef PNP_REPORT_MINBLOCKS
+#define PNP_REPORT_MINBLOCKS 12   // one-warp CTAs per SM the register allocation must allow (12 -> <= 168 registers, 3 warps per sub-partition)
+#endif
+constexpr int kReportUnroll = PNP_REPORT_UNROLL;
 template <typename T, int RES>
-__global__ void __launch_bounds__(32, 12) k_report_chunk(const __grid_constant__ ReportArgs<T> a)
+__global__ void __launch_bounds__(32, PNP_REPORT_MINBLOCKS) k_report_chunk(const __grid_constant__ ReportArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Vec2<T>::type V2;
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(32, 12) k_report_chunk(const __grid_constant__
         for (int c = 0; c < rs.n_chunks; ++c) {
             const V2* row = rs.wait(c, lane);
             const int cnt = rs.count(c), base = c * rs.chunk;
-#pragma unroll 2
+#pragma unroll kReportUnroll
             for (int k = 0; k < cnt; ++k) {
                 const int i = base + k;
                 const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
@@ -497,8 +504,8 @@ __global__ void __launch_bounds__(32, 12) k_report_chunk(const __grid_constant__
                 s1 += e1; if (e1 > m1) { m1 = e1; i1 = i; }
                 s2 += e2; if (e2 > m2) { m2 = e2; i2 = i; }
                 if (RES) {
-                    const T bx = k00 * px.x + k01 * px.y + k02;   // nu = K^-1 [u, v, 1]^T (:3305)
-                    const T by = k10 * px.x + k11 * px.y + k12;
+                    T bx, by;                                     // nu = K^-1 [u, v, 1]^T (:3305)
+                    normalise_px<T>(px.x, px.y, k00, k01, k02, k10, k11, k12, bx, by);
                     if (RES == 1) {
                         const T aa = th[0] * st[0] + th[1] * st[1] + th[2] * st[2];
                         const T bb = th[0] * st[3] + th[1] * st[4] + th[2] * st[5];

@@ -95,6 +95,14 @@ template <typename T> PNP_DEV T t_fma(T a, T b, T c);
 template <> PNP_DEV double t_fma<double>(double a, double b, double c) { return fma(a, b, c); }
 template <> PNP_DEV float t_fma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
+// nu = K^-1 [u, v, 1]^T, first two rows (f2_get_B_xy, PNP_SOLVER_LIB.py:3305): two FMAs per coordinate, the same in every kernel
+template <typename T>
+PNP_DEV void normalise_px(T u, T v, T k00, T k01, T k02, T k10, T k11, T k12, T& bx, T& by)
+{
+    bx = t_fma(k00, u, t_fma(k01, v, k02));
+    by = t_fma(k10, u, t_fma(k11, v, k12));
+}
+
 // In-place LDL^T of a packed SPD matrix.  On return A(j,j) holds 1/d_j and A(j,i), i > j,
 // holds L(i,j).  Replaces the SVD-based np.linalg.pinv of the reference for the SPD systems
 // (PNP_SOLVER_LIB.py:2675, :2887, :2924); equivalent to ~1e-13 at the condition numbers seen

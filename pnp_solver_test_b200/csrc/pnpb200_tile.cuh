@@ -135,8 +135,7 @@ struct RowTile {
             for (int i = 0; i < n_total; ++i) {
                 const V2 px = r2[i];
                 V2 o;
-                o.x = k00 * px.x + k01 * px.y + k02;
-                o.y = k10 * px.x + k11 * px.y + k12;
+                normalise_px<T>(px.x, px.y, k00, k01, k02, k10, k11, k12, o.x, o.y);
                 r2[i] = o;
             }
         }
