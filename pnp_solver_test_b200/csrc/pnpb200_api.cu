@@ -206,7 +206,7 @@ int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns
     const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS);
     if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
     const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
-    return ((((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC + 1) & ~(int64_t)1) + (int64_t)PNP_PTAB_W * PNP_PTAB_MAX_N) * esz;
+    return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
 }
 
 static int solve_batch_impl(int method, int dtype, int64_t B, int n_total, int n, const void* uv, const void* pattern,

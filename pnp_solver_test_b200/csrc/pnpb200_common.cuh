@@ -12,9 +12,6 @@
 #define PNP_NCORE 33        // constants of the LM system kept next to the moments by k_iterate (S33 6, S13 9, S23 9, c 9)
 #define PNP_NTAIL 12
 #define PNP_PATC 20
-// per-point table behind the pattern constants (moment mapping): theta (3), theta theta^T (6), pad; for patterns up to PNP_PTAB_MAX_N points
-#define PNP_PTAB_W 10
-#define PNP_PTAB_MAX_N 2048
 // landmark selections up to this size travel inside the kernel arguments; larger ones through device memory
 #define PNP_MAX_INLINE_IDX 96
 // internal bit of pnpb200_params.flags (masked off at the C ABI): the moment mapping skips its residual pass

@@ -249,7 +249,6 @@ struct MomArgs {
     double kinv[6];
     SolverPrm<T> prm;
     T* mom; T* tail; T* patc;
-    T* ptab;                // [n][PNP_PTAB_W] per-point table (theta, theta theta^T) or nullptr
     T* R; T* t; T* euler; T* res;
     int32_t* iters; int32_t* best;
     int use_tmap;
@@ -271,12 +270,6 @@ __global__ void __launch_bounds__(32) k_pattern_constants(const __grid_constant_
     for (int i = lane; i < n; i += 32) {
         const int j = idx ? idx[i] : i;
         const double th[3] = { (double)pattern[3 * j], (double)pattern[3 * j + 1], (double)pattern[3 * j + 2] };
-        if (a.ptab) {                                         // in T, exactly what Moments::add would form per problem
-            const T t0 = pattern[3 * j], t1 = pattern[3 * j + 1], t2 = pattern[3 * j + 2];
-            T* g = a.ptab + (size_t)PNP_PTAB_W * i;
-            g[0] = t0; g[1] = t1; g[2] = t2;
-            g[3] = t0 * t0; g[4] = t0 * t1; g[5] = t0 * t2; g[6] = t1 * t1; g[7] = t1 * t2; g[8] = t2 * t2; g[9] = T(0);
-        }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -367,30 +360,26 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
 
 // Streaming variant of k_stream_thread (all landmarks, rows a multiple of 16 bytes): chunks of the
 // rows go through two small buffers (RowStream), K^-1 is applied on the fly.
-// PAT_GLOBAL: the pattern comes from the table k_pattern_constants leaves in the workspace -- per point theta and the six
-// products theta_a theta_b that every problem's moments multiply -- read through L1 (warp-uniform addresses: one broadcast
-// transaction per 16 bytes) instead of a per-CTA copy of the pattern in shared memory.  Six FP64 multiplies per point
-// fewer (the products are the same numbers, so the sums are bit-identical), ~2 KB (n = 68) ... 24 KB (n = 1024) less
-// shared memory per one-warp CTA, hence more resident warps.
-template <typename T, int METHOD, int PASS, bool PAT_GLOBAL = false>
+#ifndef PNP_STREAM_UNROLL
+#define PNP_STREAM_UNROLL 2       // points in flight per thread in the chunk-streaming passes
+#endif
+constexpr int kStreamUnroll = PNP_STREAM_UNROLL;
+template <typename T, int METHOD, int PASS>
 __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ MomArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Vec2<T>::type V2;
     T* sBuf = reinterpret_cast<T*>(smem_raw);
-    T* sPs = sBuf + (size_t)2 * kTileProblems * a.row_pitch;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sPs + (PAT_GLOBAL ? 0 : (size_t)a.n * 3)) - smem_raw)) + 7) & ~(size_t)7));
-    const T* __restrict__ sP = sPs;
+    T* sP = sBuf + (size_t)2 * kTileProblems * a.row_pitch;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ((((size_t)((unsigned char*)(sP + (size_t)a.n * 3) - smem_raw)) + 7) & ~(size_t)7));
     const int lane = threadIdx.x;
     RowStream<T> rs;
     rs.init(sBuf, bars, a.uv, a.B, a.n_total, a.use_tma /* chunk */, a.row_pitch, lane, a.use_tmap ? &a.tmap : nullptr);
     const long long n_tiles = (a.B + kTileProblems - 1) / kTileProblems;
     long long tile = blockIdx.x;
     if (tile < n_tiles) rs.begin_tile(tile, lane);
-    if (!PAT_GLOBAL) {
-        for (int e = lane; e < a.n * 3; e += 32) sPs[e] = a.pattern[e];
-        __syncwarp();
-    }
+    for (int e = lane; e < a.n * 3; e += 32) sP[e] = a.pattern[e];
+    __syncwarp();
     const T k00 = (T)a.kinv[0], k01 = (T)a.kinv[1], k02 = (T)a.kinv[2];
     const T k10 = (T)a.kinv[3], k11 = (T)a.kinv[4], k12 = (T)a.kinv[5];
     while (tile < n_tiles) {
@@ -419,26 +408,14 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
         for (int c = 0; c < rs.n_chunks; ++c) {
             const V2* row = rs.wait(c, lane);
             const int cnt = rs.count(c), i0 = c * rs.chunk;
-#pragma unroll 2
+#pragma unroll kStreamUnroll
             for (int k = 0; k < cnt; ++k) {
                 const V2 px = row[k];
                 T bx, by;                                     // nu = K^-1 [u, v, 1]^T (:3305)
                 normalise_px<T>(px.x, px.y, k00, k01, k02, k10, k11, k12, bx, by);
-                T th[3], qq[6];
-                if (PAT_GLOBAL) {                             // [th0 th1 | th2 q00 | q01 q02 | q11 q12 | q22 -] of point i0 + k
-                    const V2* g = reinterpret_cast<const V2*>(a.ptab + (size_t)PNP_PTAB_W * (i0 + k));
-                    const V2 g0 = __ldg(g), g1 = __ldg(g + 1);
-                    th[0] = g0.x; th[1] = g0.y; th[2] = g1.x;
-                    if (PASS == 0) {
-                        const V2 g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4);
-                        qq[0] = g1.y; qq[1] = g2.x; qq[2] = g2.y; qq[3] = g3.x; qq[4] = g3.y; qq[5] = g4.x;
-                    }
-                } else {
-                    th[0] = sP[3 * (i0 + k)]; th[1] = sP[3 * (i0 + k) + 1]; th[2] = sP[3 * (i0 + k) + 2];
-                }
+                const T th[3] = { sP[3 * (i0 + k)], sP[3 * (i0 + k) + 1], sP[3 * (i0 + k) + 2] };
                 if (PASS == 0) {
-                    if (PAT_GLOBAL) mom.template add_q<METHOD != PNPB200_METHOD_LINEAR_F2>(th, qq, bx, by);
-                    else            mom.template add<METHOD != PNPB200_METHOD_LINEAR_F2>(th, bx, by);
+                    mom.template add<METHOD != PNPB200_METHOD_LINEAR_F2>(th, bx, by);
                 } else if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
                     const T aa = th[0] * x[0] + th[1] * x[1] + th[2] * x[2];
                     const T bb = th[0] * x[3] + th[1] * x[4] + th[2] * x[5];
@@ -823,17 +800,12 @@ static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, lo
     if (pass == 1) { launch_iterate<T, METHOD>(m, tune, stream); return PNPB200_OK; }
     const long long n_tiles = (nb + kTileProblems - 1) / kTileProblems;
     const unsigned tile_grid = (unsigned)(n_tiles < 0x7fffffffLL ? n_tiles : 0x7fffffffLL);
-    if (shape == 0 || shape == 4) {                           // chunked row streaming (4: large pattern, read through L1)
+    if (shape == 0) {                                         // chunked row streaming
         m.row_pitch = sg.pitch;
         m.use_tma = sg.chunk;                                 // RowStream: points per chunk
         m.use_tmap = (sg.pitch == sg.chunk * 2) ? make_row_tensor_map(&m.tmap, m.uv, (int)sizeof(T), nb, m.n_total, sg.chunk) : 0;
-        if (shape == 0) {
-            if (pass == 0) k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
-            else           k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
-        } else {
-            if (pass == 0) k_stream_chunk<T, METHOD, 0, true><<<tile_grid, 32, smem, stream>>>(m);
-            else           k_stream_chunk<T, METHOD, 1, true><<<tile_grid, 32, smem, stream>>>(m);
-        }
+        if (pass == 0) k_stream_chunk<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
+        else           k_stream_chunk<T, METHOD, 1><<<tile_grid, 32, smem, stream>>>(m);
         count_kernel_launches(1);
     } else if (shape == 1) {                                  // whole-row tiles
         if (pass == 0) k_stream_thread<T, METHOD, 0><<<tile_grid, 32, smem, stream>>>(m);
@@ -873,9 +845,7 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     if (!by_thread && warp_smem > (size_t)dp.max_smem_optin) return PNPB200_ETOOLARGE;
 
     T* ws = nullptr;
-    const size_t ptab_off = (((size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)a.B + PNP_PATC) + 1) & ~(size_t)1;   // 16-byte aligned in T
-    const bool want_ptab = !a.idx_mode && a.n_total <= PNP_PTAB_MAX_N && a.tune != 6;
-    const size_t ws_elems = ptab_off + (want_ptab ? (size_t)PNP_PTAB_W * PNP_PTAB_MAX_N : 0);
+    const size_t ws_elems = (size_t)(PNP_NMOM + PNP_NTAIL) * (size_t)a.B + PNP_PATC;
     const bool own_ws = !(a.ws && a.ws_bytes >= ws_elems * sizeof(T));
     if (own_ws) PNP_CUDA_OK(cudaMallocAsync((void**)&ws, ws_elems * sizeof(T), stream));
     else ws = (T*)a.ws;
@@ -891,7 +861,6 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     for (int e = 0; e < 6; ++e) m.kinv[e] = a.kinv[e];
     m.prm = a.prm;
     m.mom = ws; m.tail = ws + (size_t)PNP_NMOM * a.B; m.patc = m.tail + (size_t)PNP_NTAIL * a.B;
-    m.ptab = want_ptab ? ws + ptab_off : nullptr;
     m.R = a.R; m.t = a.t; m.euler = a.euler; m.res = a.res; m.iters = a.iters; m.best = a.best;
     m.use_tmap = 0;
 
@@ -899,11 +868,7 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     const StreamGeom sg = stream_geometry<T>(a.n_total);
     int shape, per_sm = 1;
     size_t smem;
-    if (by_thread && !a.idx_mode && sg.use_stream && a.tune != 9 && want_ptab) {
-        shape = 4; smem = 2 * sg.buf_bytes + 32;              // rows chunk-streamed, pattern table through L1
-        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 0, true>, smem));
-        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 1, true>, smem));
-    } else if (by_thread && !a.idx_mode && sg.use_stream && a.tune != 9) {
+    if (by_thread && !a.idx_mode && sg.use_stream && a.tune != 9) {
         shape = 0; smem = 2 * sg.buf_bytes + pat_bytes + 32;
         PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 0>, smem));
         PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 1>, smem));
@@ -911,12 +876,6 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
         shape = 1; smem = thread_smem;
         PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_thread<T, METHOD, 0>, smem));
         PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_thread<T, METHOD, 1>, smem));
-    } else if (want_ptab && sg.use_stream && a.tune != 9 && a.tune != 8 && a.B >= (long long)kTileProblems * 2 * dp.sm_count) {
-        // rows too long for a whole-row tile, enough problems to fill the GPU with one problem per thread: the same chunk
-        // streaming as for small n (no shuffle reductions, a third fewer instructions per point than one problem per warp)
-        shape = 4; smem = 2 * sg.buf_bytes + 32;
-        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 0, true>, smem));
-        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_chunk<T, METHOD, 1, true>, smem));
     } else if (!a.idx_mode && ((size_t)a.n_total * 2 * sizeof(T)) % 16 == 0 && a.tune != 9 &&
                a.n_total >= kRingPoints) {
         shape = 3;
@@ -931,16 +890,6 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
         PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_stream_warp<T, METHOD, 0>, 256, smem));
     }
 
-    // (tuning only, tune = 7: chunk streaming for the moments, the one-problem-per-warp ring for the residual)
-    int shape2 = shape, per_sm2 = per_sm;
-    size_t smem2 = smem;
-    if (shape == 4 && a.tune == 7 && ((size_t)a.n_total * 2 * sizeof(T)) % 16 == 0 && a.n_total >= kRingPoints) {
-        shape2 = 3;
-        smem2 = (size_t)kRingWarps * kRingSlots * (kRingPoints * 2 * sizeof(T) + 8);
-        PNP_CUDA_OK(set_dynamic_smem((const void*)k_stream_warp_tma<T, METHOD, 1>, smem2));
-        PNP_CUDA_OK(blocks_per_sm(&per_sm2, (const void*)k_stream_warp_tma<T, METHOD, 1>, kRingWarps * 32, smem2));
-    }
-
     k_pattern_constants<T><<<1, 32, 0, stream>>>(m); count_kernel_launches(1);
     const int slot = a.profile ? g_prof.begin() : -1;
     g_prof.mark(slot, stream);
@@ -948,7 +897,7 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     g_prof.mark(slot, stream);
     launch_moment_pass<T, METHOD>(1, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
     g_prof.mark(slot, stream);
-    if (a.res && !a.skip_residual) launch_moment_pass<T, METHOD>(2, m, 0, a.B, shape2, sg, smem2, per_sm2, dp, a.tune, stream);
+    if (a.res && !a.skip_residual) launch_moment_pass<T, METHOD>(2, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
     if (!a.skip_residual) g_prof.mark(slot, stream);      // (the fused report + residual pass is marked by its launcher)
     PNP_CUDA_OK(cudaGetLastError());
     return PNPB200_OK;

@@ -122,25 +122,6 @@ struct Moments {
         }
         sx0 += bx; sy0 += by;
     }
-    // the same with the products theta_a theta_b taken from the pattern table (packed like Mx): identical sums
-    template <bool WITH_W = true>
-    PNP_DEV void add_q(const T (&th)[3], const T (&q)[6], T bx, T by)
-    {
-        const T ww = WITH_W ? (bx * bx + by * by) : T(0);
-#pragma unroll
-        for (int e = 0; e < 6; ++e) {
-            Mx[e] = t_fma(bx, q[e], Mx[e]);
-            My[e] = t_fma(by, q[e], My[e]);
-            if (WITH_W) Mw[e] = t_fma(ww, q[e], Mw[e]);
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            mx[a] = t_fma(bx, th[a], mx[a]);
-            my[a] = t_fma(by, th[a], my[a]);
-            if (WITH_W) mw[a] = t_fma(ww, th[a], mw[a]);
-        }
-        sx0 += bx; sy0 += by;
-    }
     template <int LPP, bool WITH_W = true>
     PNP_DEV void reduce()
     {

@@ -627,27 +627,3 @@ def test_moment_mapping_over_several_patterns(method):
     assert (direct["best_pattern"][m] == out["best_pattern"][m]).all()
     compare_solutions(out, direct, mask=m)
 
-
-@pytest.mark.parametrize("method", ["lm", "linear_f2"])
-def test_large_n_streams_one_problem_per_thread_when_the_batch_is_large(method):
-    """n = 1024 with enough problems to fill the GPU: the moments / residual passes run one problem per thread with
-    chunk-streamed rows and the pattern table through L1 (the shape of the 68-point case) instead of one problem per warp.
-    Same results as the warp ring (forced with the tuning flag) to rounding, and oracle parity on a sample."""
-    from pnp_solver_test_b200 import workload as wl
-    n, B = 1024, 9600
-    P, K = pt.pattern_array(pt.synthetic_pattern(n)), pt.default_camera_matrix()
-    w = wl.synth_batch(5, B, P, K)
-    uv = w["uv"].cpu().numpy()
-    a = cuda_solve(method, uv, P, K)
-    ring = cuda_solve(method, uv, P, K, flags=8 << 8)
-    sample = np.arange(0, B, 200)
-    ref, stable, _ = oracle_stability(method, uv[sample], P, K)
-    got = {k: v[sample] for k, v in a.items()}
-    compare_solutions(got, ref, mask=stable)
-    m = np.zeros(B, bool)
-    m[sample] = stable
-    compare_solutions(a, ring, mask=m)
-    old = cuda_solve(method, uv[:4096, :68].copy(), P[:68], K, flags=6 << 8)      # 68 points: pattern in shared memory (previous shape)
-    new = cuda_solve(method, uv[:4096, :68].copy(), P[:68], K)                    # ... and from the table: the same sums
-    for k in ("R", "t", "res_norm"):
-        assert np.array_equal(old[k], new[k], equal_nan=True), k
