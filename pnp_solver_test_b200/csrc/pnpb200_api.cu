@@ -203,7 +203,8 @@ int pnpb200_profile_read(float* ms, int* n_calls)
 int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping)
 {
     (void)n_patterns;                                       // several patterns are solved one after the other with the same scratch
-    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS);
+    const bool moment_form = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS ||
+                              ((method == PNPB200_METHOD_EIF2 || method == PNPB200_METHOD_QEIF) && dtype == PNPB200_DTYPE_F64));   // (QEIF: from 12 landmarks on)
     if (B <= 0 || !moment_form || (mapping != PNPB200_MAP_AUTO && mapping != PNPB200_MAP_MOMENT)) return 0;
     const int64_t esz = (dtype == PNPB200_DTYPE_F32) ? 4 : 8;
     return ((int64_t)(PNP_NMOM + PNP_NTAIL) * B + PNP_PATC) * esz;
@@ -265,7 +266,9 @@ int pnpb200_solve_report_batch(int method, int dtype, int64_t B, int n_total, in
     cudaStream_t st = (cudaStream_t)stream;
     // One pass over the pixel rows for res_norm AND the report when the solve runs as the moment mapping over all
     // landmarks with chunk-streamed rows; every other shape is the two calls back to back.
-    const bool moment = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS) &&
+    const bool moment = (method == PNPB200_METHOD_LM || method == PNPB200_METHOD_LINEAR_F2 || method == PNPB200_METHOD_LM_PLUS ||
+                         (dtype == PNPB200_DTYPE_F64 && (method == PNPB200_METHOD_EIF2 ||
+                          (method == PNPB200_METHOD_QEIF && n >= PNP_QEIF_HYBRID_MIN_N && !(prm.flags & PNPB200_FLAG_QEIF_DIRECT))))) &&
                         (prm.mapping == PNPB200_MAP_AUTO || prm.mapping == PNPB200_MAP_MOMENT);
     const bool fuse = moment && !point_index && n == n_total && res_norm && B > 0 && ((prm.flags >> 8) & 0xff) != 9 &&
                       (dtype == PNPB200_DTYPE_F64 || dtype == PNPB200_DTYPE_F32) && report_can_fuse(dtype, n_total);

@@ -8,12 +8,15 @@
 
 // workspace layout of the moment mapping: [PNP_NMOM][B] moments, [PNP_NTAIL][B] state before the last
 // update (or the F2 tail), PNP_PATC pattern constants (see pnpb200_solvers.cuh)
-#define PNP_NMOM 29
+#define PNP_NMOM 30        // rows of the moment workspace: the 29 moments LM / linear F2 use + sum (bx^2 + by^2) (filters' residual)
+#define PNP_NMOM_LM 29     // ... of which LM, LM+ and linear F2 read and write the first 29
 #define PNP_NCORE 33        // constants of the LM system kept next to the moments by k_iterate (S33 6, S13 9, S23 9, c 9)
 #define PNP_NTAIL 12
 #define PNP_PATC 20
 // landmark selections up to this size travel inside the kernel arguments; larger ones through device memory
 #define PNP_MAX_INLINE_IDX 96
+// QEIF takes H^T H, H^T v (and, in the moment mapping, the residual of its exit test) from the moments from this many landmarks on
+#define PNP_QEIF_HYBRID_MIN_N 12
 // internal bit of pnpb200_params.flags (masked off at the C ABI): the moment mapping skips its residual pass
 #define PNP_FLAG_INTERNAL_NO_RESIDUAL (1 << 30)
 

@@ -38,7 +38,13 @@ namespace pnpb200 {
 // ------------------------------------------------------------------------------------------
 // internal kernel variant: QEIF with H^T H / H^T v from the moments (chosen for n >= 12 landmarks)
 #define PNP_METHOD_QEIF_HYBRID 100
-#define PNP_QEIF_HYBRID_MIN_N 12
+
+// what a method's passes of the moment mapping compute
+__host__ __device__ constexpr bool method_with_w(int m) { return m != PNPB200_METHOD_LINEAR_F2; }                              // the (bx^2 + by^2)-weighted moments
+__host__ __device__ constexpr bool method_with_s(int m) { return m == PNP_METHOD_QEIF_HYBRID || m == PNPB200_METHOD_EIF2; }   // sum (bx^2 + by^2): the filters' residual
+__host__ __device__ constexpr int method_nmom(int m) { return method_with_s(m) ? PNP_NMOM : PNP_NMOM_LM; }                    // rows of the moment workspace in use
+__host__ __device__ constexpr bool method_lm_residual(int m) { return m != PNPB200_METHOD_LINEAR_F2; }                         // residual of the 12-number measurement model (else: F2's)
+__host__ __device__ constexpr bool method_has_core(int m) { return m == PNPB200_METHOD_LM || m == PNPB200_METHOD_LM_PLUS; }   // k_iterate parks the constant LM blocks in shared memory
 
 template <typename T>
 struct SolveArgs {
@@ -128,12 +134,13 @@ template <typename T, int METHOD, int LPP, typename Pts>
 PNP_DEV void solve_all_patterns(const Pts& pts, const T* sP, const T* sC, int n, int n_patterns, int sub,
                                 const SolverPrm<T>& prm, Result<T>& best, int& best_p)
 {
-    run_method<T, METHOD, LPP, Pts>(pts, sP, sC, n, sub, prm, best);
+    // ONE inlined copy of the solver (a separate first call doubled every kernel's code: 12 416 instructions for EIF2)
     best_p = 0;
-    for (int p = 1; p < n_patterns; ++p) {
+#pragma unroll 1
+    for (int p = 0; p < n_patterns; ++p) {
         Result<T> cand;
         run_method<T, METHOD, LPP, Pts>(pts, sP + (size_t)p * n * 3, sC + p * PNP_PATC, n, sub, prm, cand);
-        if (cand.res < best.res) { best = cand; best_p = p; }
+        if (p == 0 || cand.res < best.res) { best = cand; best_p = p; }
     }
 }
 
@@ -328,14 +335,14 @@ __global__ void __launch_bounds__(32) k_stream_thread(const __grid_constant__ Mo
         pts.idx = sel ? sIdx : nullptr;
         if (PASS == 0) {
             Moments<T> mom;
-            accumulate_moments<T, 1, PtsRow<T>, METHOD != PNPB200_METHOD_LINEAR_F2>(pts, sP, a.n, 0, mom);
+            accumulate_moments<T, 1, PtsRow<T>, method_with_w(METHOD), method_with_s(METHOD)>(pts, sP, a.n, 0, mom);
             if (ok) {
 #pragma unroll
-                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.ld + b] = mom.at(k);
+                for (int k = 0; k < method_nmom(METHOD); ++k) a.mom[(size_t)k * a.ld + b] = mom.at(k);
             }
         } else {
             T res;
-            if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
+            if (method_lm_residual(METHOD)) {
                 T x[12];
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = st[k];
@@ -395,7 +402,7 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
             T st[PNP_NTAIL];
 #pragma unroll
             for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.ld + b];
-            if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
+            if (method_lm_residual(METHOD)) {
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = st[k];
             } else {
@@ -415,8 +422,8 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
                 normalise_px<T>(px.x, px.y, k00, k01, k02, k10, k11, k12, bx, by);
                 const T th[3] = { sP[3 * (i0 + k)], sP[3 * (i0 + k) + 1], sP[3 * (i0 + k) + 2] };
                 if (PASS == 0) {
-                    mom.template add<METHOD != PNPB200_METHOD_LINEAR_F2>(th, bx, by);
-                } else if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
+                    mom.template add<method_with_w(METHOD), method_with_s(METHOD)>(th, bx, by);
+                } else if (method_lm_residual(METHOD)) {
                     const T aa = th[0] * x[0] + th[1] * x[1] + th[2] * x[2];
                     const T bb = th[0] * x[3] + th[1] * x[4] + th[2] * x[5];
                     const T cc = th[0] * x[6] + th[1] * x[7] + th[2] * x[8];
@@ -436,9 +443,9 @@ __global__ void __launch_bounds__(32) k_stream_chunk(const __grid_constant__ Mom
         if (ok) {
             if (PASS == 0) {
 #pragma unroll
-                for (int k = 0; k < PNP_NMOM; ++k) a.mom[(size_t)k * a.ld + b] = mom.at(k);
+                for (int k = 0; k < method_nmom(METHOD); ++k) a.mom[(size_t)k * a.ld + b] = mom.at(k);
             } else if (a.res) {
-                if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) a.res[b] = t_sqrt(acc0);   // :2681
+                if (method_lm_residual(METHOD)) a.res[b] = t_sqrt(acc0);   // :2681
                 else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
             }
         }
@@ -467,15 +474,15 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
         pts.row = a.uv + (size_t)b * a.n_total * 2;
         if (PASS == 0) {
             Moments<T> mom;
-            accumulate_moments<T, 32, PtsGlobal<T>, METHOD != PNPB200_METHOD_LINEAR_F2>(pts, sP, a.n, lane, mom);
+            accumulate_moments<T, 32, PtsGlobal<T>, method_with_w(METHOD), method_with_s(METHOD)>(pts, sP, a.n, lane, mom);
             // after the butterfly every lane holds every sum: lane k writes moment k
             T mine = T(0);
 #pragma unroll
-            for (int k = 0; k < PNP_NMOM; ++k) if (lane == k) mine = mom.at(k);
-            if (lane < PNP_NMOM) a.mom[(size_t)lane * a.ld + b] = mine;
+            for (int k = 0; k < method_nmom(METHOD); ++k) if (lane == k) mine = mom.at(k);
+            if (lane < method_nmom(METHOD)) a.mom[(size_t)lane * a.ld + b] = mine;
         } else {
             T res;
-            if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
+            if (method_lm_residual(METHOD)) {
                 T x[12];
 #pragma unroll
                 for (int k = 0; k < 12; ++k) x[k] = a.tail[(size_t)k * a.ld + b];
@@ -573,8 +580,8 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
                 normalise_px<T>(px.x, px.y, k00, k01, k02, k10, k11, k12, bx, by);
                 const T th[3] = { __ldg(gP + 3 * i), __ldg(gP + 3 * i + 1), __ldg(gP + 3 * i + 2) };
                 if (PASS == 0) {
-                    mom.template add<METHOD != PNPB200_METHOD_LINEAR_F2>(th, bx, by);
-                } else if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) {
+                    mom.template add<method_with_w(METHOD), method_with_s(METHOD)>(th, bx, by);
+                } else if (method_lm_residual(METHOD)) {
                     const T aa = th[0] * st[0] + th[1] * st[1] + th[2] * st[2];
                     const T bb = th[0] * st[3] + th[1] * st[4] + th[2] * st[5];
                     const T cc = th[0] * st[6] + th[1] * st[7] + th[2] * st[8];
@@ -591,15 +598,15 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
             }
         }
         if (PASS == 0) {
-            mom.template reduce<32, METHOD != PNPB200_METHOD_LINEAR_F2>();
+            mom.template reduce<32, method_with_w(METHOD), method_with_s(METHOD)>();
             T mine = T(0);                                                    // after the butterfly every lane holds every sum
 #pragma unroll
-            for (int k = 0; k < PNP_NMOM; ++k) if (lane == k) mine = mom.at(k);
-            if (lane < PNP_NMOM) a.mom[(size_t)lane * a.ld + b] = mine;
+            for (int k = 0; k < method_nmom(METHOD); ++k) if (lane == k) mine = mom.at(k);
+            if (lane < method_nmom(METHOD)) a.mom[(size_t)lane * a.ld + b] = mine;
         } else {
             acc0 = group_sum<32>(acc0); acc1 = group_sum<32>(acc1);
             if (lane == 0 && a.res) {
-                if (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) a.res[b] = t_sqrt(acc0);   // :2681
+                if (method_lm_residual(METHOD)) a.res[b] = t_sqrt(acc0);   // :2681
                 else { const T nx = t_sqrt(acc0), ny = t_sqrt(acc1); a.res[b] = t_sqrt(nx * nx + ny * ny); }   // :3374
             }
         }
@@ -622,10 +629,24 @@ __device__ __forceinline__ void iterate_core(T* sMomCol, int stride, const T* sC
         solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, prm, xp, out);
 #pragma unroll
         for (int k = 0; k < 12; ++k) st[k] = xp[k];
+    } else if (METHOD == PNP_METHOD_QEIF_HYBRID) {
+        Moments<T> mr;                                        // 6 x 6 system: the moments fit in registers next to it
+#pragma unroll
+        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMomCol[k * stride];
+        T xt[12];
+        solve_qeif_from_moments<T>(mr, sC, prm, xt, out);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st[k] = xt[k];
+    } else if (METHOD == PNPB200_METHOD_EIF2) {
+        T xt[12];
+        solve_eif2_from_moments<T, MomentsRef<T> >(mom, sC, prm, xt, out);   // 12 x 12 system: moments stay in shared memory
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st[k] = xt[k];
     } else if (METHOD == PNPB200_METHOD_LM_PLUS) {
         Moments<T> mr;
 #pragma unroll
-        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMomCol[k * stride];
+        for (int k = 0; k < PNP_NMOM_LM; ++k) mr.at(k) = sMomCol[k * stride];
+        mr.sw0 = T(0);
         T xf[12];
         solve_lm_plus_from_moments<T, MomentsRef<T> >(mom, mr, sC, prm, xf, out);
 #pragma unroll
@@ -633,7 +654,8 @@ __device__ __forceinline__ void iterate_core(T* sMomCol, int stride, const T* sC
     } else {
         Moments<T> mr;
 #pragma unroll
-        for (int k = 0; k < PNP_NMOM; ++k) mr.at(k) = sMomCol[k * stride];
+        for (int k = 0; k < PNP_NMOM_LM; ++k) mr.at(k) = sMomCol[k * stride];
+        mr.sw0 = T(0);
         F2Tail<T> f;
         solve_f2_from_moments<T>(mr, sC, prm, f, out);
 #pragma unroll
@@ -672,14 +694,14 @@ __device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
 {
     constexpr int kIterBlock = BLOCK;
     __shared__ T sC[PNP_PATC];
-    constexpr int kRows = PNP_NMOM + ((METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LM_PLUS) ? PNP_NCORE : 0);
+    constexpr int kRows = PNP_NMOM + (method_has_core(METHOD) ? PNP_NCORE : 0);
     __shared__ T sMom[kRows * kIterBlock];                // [moment | constant LM blocks][thread]: conflict-free columns
     if (threadIdx.x < PNP_PATC) sC[threadIdx.x] = a.patc[threadIdx.x];
     long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool ok = b < a.B;
     if (!ok) b = a.B - 1;
 #pragma unroll
-    for (int k = 0; k < PNP_NMOM; ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.ld + b];
+    for (int k = 0; k < method_nmom(METHOD); ++k) sMom[k * kIterBlock + threadIdx.x] = a.mom[(size_t)k * a.ld + b];
     __syncthreads();
     Result<T> out;
     T st[PNP_NTAIL];
@@ -717,7 +739,11 @@ static void launch_iterate(const MomArgs<T>& m, int tune, cudaStream_t stream)
     case 32: launch_iterate_as<T, METHOD, 32, 168>(m, stream); break;    // 3 warps per sub-partition
     case 33: launch_iterate_as<T, METHOD, 32, 160>(m, stream); break;
 #endif
-    default: launch_iterate_as<T, METHOD, 32, 224>(m, stream); break;    //  9 warps / SM, no spills
+    default:
+        // LM: 224 registers (2 warps per sub-partition, no spills); EIF2 carries a 12 x 12 matrix (156 registers) and QEIF's
+        // moment form of H^T H a hundred temporaries: no cap (any cap below 255 spills: 684 bytes at 168, 1164 at 128)
+        launch_iterate_as<T, METHOD, 32, (METHOD == PNPB200_METHOD_EIF2 || METHOD == PNP_METHOD_QEIF_HYBRID) ? 255 : 224>(m, stream);
+        break;
     }
 }
 
@@ -971,7 +997,9 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     DeviceProps dp;
     int rc = get_device_props(&dp);
     if (rc != PNPB200_OK) return rc;
-    constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNPB200_METHOD_LM_PLUS);
+    // (the filters' exit test from the moments needs FP64: in FP32 the moment-form residual is noise at res / |z| ~ 1e-3)
+    constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNPB200_METHOD_LM_PLUS ||
+                                      ((METHOD == PNP_METHOD_QEIF_HYBRID || METHOD == PNPB200_METHOD_EIF2) && sizeof(T) == 8));
     const RowGeom g = row_geometry<T>(a.n_total);
     const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
     const size_t idx_bytes = a.idx_mode ? (size_t)a.n * sizeof(int32_t) : 0;

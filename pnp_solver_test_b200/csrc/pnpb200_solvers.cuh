@@ -94,19 +94,22 @@ PNP_DEV void block_reconstruct(const T (&phi)[8], T (&R)[9], T (&t)[3], T& t3)
 template <typename T>
 struct Moments {
     T Mx[6], My[6], Mw[6], mx[3], my[3], mw[3], sx0, sy0;
+    T sw0;                                                // sum (bx^2 + by^2): only the filters' moment-form residual reads it
     PNP_DEV void zero()
     {
 #pragma unroll
         for (int e = 0; e < 6; ++e) { Mx[e] = T(0); My[e] = T(0); Mw[e] = T(0); }
 #pragma unroll
         for (int e = 0; e < 3; ++e) { mx[e] = T(0); my[e] = T(0); mw[e] = T(0); }
-        sx0 = T(0); sy0 = T(0);
+        sx0 = T(0); sy0 = T(0); sw0 = T(0);
     }
-    // WITH_W = false skips the (bx^2 + by^2)-weighted moments, which the linear stage F2 never reads
-    template <bool WITH_W = true>
+    // WITH_W = false skips the (bx^2 + by^2)-weighted moments, which the linear stage F2 never reads;
+    // WITH_S adds sum (bx^2 + by^2) itself (QEIF / EIF2 in the moment mapping)
+    template <bool WITH_W = true, bool WITH_S = false>
     PNP_DEV void add(const T (&th)[3], T bx, T by)
     {
         const T ww = WITH_W ? (bx * bx + by * by) : T(0);
+        if (WITH_S) sw0 += ww;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -122,13 +125,14 @@ struct Moments {
         }
         sx0 += bx; sy0 += by;
     }
-    template <int LPP, bool WITH_W = true>
+    template <int LPP, bool WITH_W = true, bool WITH_S = false>
     PNP_DEV void reduce()
     {
         group_sum_arr<LPP>(Mx); group_sum_arr<LPP>(My);
         group_sum_arr<LPP>(mx); group_sum_arr<LPP>(my);
         if (WITH_W) { group_sum_arr<LPP>(Mw); group_sum_arr<LPP>(mw); }
         sx0 = group_sum<LPP>(sx0); sy0 = group_sum<LPP>(sy0);
+        if (WITH_S) sw0 = group_sum<LPP>(sw0);
     }
     PNP_DEV T gMx(int k) const { return Mx[k]; }
     PNP_DEV T gMy(int k) const { return My[k]; }
@@ -138,6 +142,7 @@ struct Moments {
     PNP_DEV T gmw(int k) const { return mw[k]; }
     PNP_DEV T gsx0() const { return sx0; }
     PNP_DEV T gsy0() const { return sy0; }
+    PNP_DEV T gsw0() const { return sw0; }
     static constexpr bool kHasCore = false;               // the constant blocks of the LM system are recomputed per iteration
     PNP_DEV T gcore(int) const { return T(0); }
     PNP_DEV void set_core(int, T) const {}
@@ -145,7 +150,7 @@ struct Moments {
     PNP_DEV T& at(int k)
     {
         return k < 6 ? Mx[k] : k < 12 ? My[k - 6] : k < 18 ? Mw[k - 12] : k < 21 ? mx[k - 18] : k < 24 ? my[k - 21]
-               : k < 27 ? mw[k - 24] : (k == 27 ? sx0 : sy0);
+               : k < 27 ? mw[k - 24] : (k == 27 ? sx0 : (k == 28 ? sy0 : sw0));
     }
 };
 
@@ -163,6 +168,7 @@ struct MomentsRef {
     PNP_DEV T gmw(int k) const { return base[(24 + k) * stride]; }
     PNP_DEV T gsx0() const { return base[27 * stride]; }
     PNP_DEV T gsy0() const { return base[28 * stride]; }
+    PNP_DEV T gsw0() const { return base[29 * stride]; }
     // the constant blocks of the delta-eliminated LM system (lm_step): S33 (6), S13 (9), S23 (9) behind the moments,
     // computed once per problem by lm_core_from_moments, followed by the constant right-hand side c (9); S11 = S22 depends on the pattern only (PNP_NCORE = 33)
     static constexpr bool kHasCore = true;
@@ -171,7 +177,7 @@ struct MomentsRef {
     PNP_DEV void set_core(int k, T v) const { core[k * stride] = v; }
 };
 
-template <typename T, int LPP, typename Pts, bool WITH_W = true>
+template <typename T, int LPP, typename Pts, bool WITH_W = true, bool WITH_S = false>
 PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n, int sub, Moments<T>& mom)
 {
     mom.zero();
@@ -180,9 +186,9 @@ PNP_DEV void accumulate_moments(const Pts& pts, const T* __restrict__ sP, int n,
         const T th[3] = { sP[3 * i], sP[3 * i + 1], sP[3 * i + 2] };
         T bx, by;
         pts.get(i, bx, by);
-        mom.template add<WITH_W>(th, bx, by);
+        mom.template add<WITH_W, WITH_S>(th, bx, by);
     }
-    mom.template reduce<LPP, WITH_W>();
+    mom.template reduce<LPP, WITH_W, WITH_S>();
 }
 
 template <typename T>
@@ -193,6 +199,29 @@ PNP_DEV void sym3_mv(const T (&M)[6], const T (&v)[3], T (&o)[3])
 }
 template <typename T>
 PNP_DEV T dot3(const T (&a)[3], const T (&b)[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// ||z - hx||^2 over the 2n measurement rows from the moments (filters in the moment mapping).  With g1 = P u1 - bx o P u3,
+// g2 = P u2 - by o P u3 the residual is (bx - d1 - gamma g1, by - d2 - gamma g2), so
+//   res^2 = sum (bx - d1)^2 + (by - d2)^2  -  2 gamma sum [(bx - d1) g1 + (by - d2) g2]  +  gamma^2 sum (g1^2 + g2^2)
+//         = sw0 - 2 (d1 sx0 + d2 sy0) + n (d1^2 + d2^2) - 2 gamma (qa - d1 s1 - d2 s2) + gamma^2 sgg
+// with s_k = sum g_k, sgg = sum g1^2 + g2^2, qa = sum bx g1 + by g2 = mx.u1 + my.u2 - mw.u3 (QEIF: u = phi(q), gamma = 1).
+// A difference of terms ~|z|^2 / res^2 larger than the result: good to ~1e-10 relative on detected (quantised / noisy) pixels,
+// where res ~ 1e-2 |z| -- far inside what the filters' early-exit test (|d res / res| < 1e-2, :2952, :2202) needs; rounding
+// noise where the residual itself is (noise-free pixels, res ~ 1e-14), exactly as the reference's own decision is there.
+// The reported res_norm never comes from here: it is evaluated point by point in the residual pass.
+// Below this fraction of sum (bx^2 + by^2) the moment-form res^2 is rounding noise (its error is ~30 eps sum |z|^2, the exit test
+// needs res^2 to ~2e-3 relative): the exit test is then not taken and the filter keeps iterating -- at its fixed point, so the
+// result does not move.  Reached only by noise-free pixels (res / |z| < 1e-5); detected pixels sit at res / |z| ~ 1e-3.
+#define kResMomFloor T(1e-10)
+
+template <typename T>
+PNP_DEV T res2_combine(T sw0, T sx0, T sy0, T n, T d1, T d2, T gam, T qa, T s1, T s2, T sgg)
+{
+    const T a0 = t_fma(n, t_fma(d1, d1, d2 * d2), t_fma(T(-2), t_fma(d1, sx0, d2 * sy0), sw0));
+    const T a1 = qa - t_fma(d1, s1, d2 * s2);
+    const T r2 = t_fma(gam * gam, sgg, t_fma(T(-2) * gam, a1, a0));
+    return r2 > T(0) ? r2 : T(0);
+}
 
 // -------------------------------------------------------------------------------------------
 // QEIF -- solve_pnp_QEIF_single_pattern :2771-3025, QEKF_get_hx_H :3902-3983,
@@ -216,13 +245,19 @@ PNP_DEV void qekf_phi(const T (&x)[6], T (&p1)[3], T (&p2)[3], T (&p3)[3], T& ga
 // iteration (best for the 6-landmark subset).  HYBRID = true: they are bilinear forms of the 29
 // moments (Q_j q = 2 phi_j, so z - hx + H x = b + (P phi_1 - b o P phi_3): no cancellation), and only
 // the residual ||z - hx|| that drives the early-exit test is still evaluated point by point.
-template <typename T, int LPP, typename Pts, bool HYBRID>
-PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
-                        const SolverPrm<T>& prm, Result<T>& out)
+// RES_MOM (moment mapping, implies HYBRID): the residual of the early-exit test comes from the moments too
+// (res2_combine), no point is touched inside the loop; x_tail receives what the residual pass needs to evaluate the
+// reported res_norm point by point -- the measurement model at the state BEFORE the lane's last update, in the
+// 12-number form of LM's residual (phi_1, phi_2, phi_3, delta_1, delta_2, gamma = 1).
+template <typename T, int LPP, typename Pts, bool HYBRID, bool RES_MOM>
+PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                       const SolverPrm<T>& prm, const Moments<T>& mom, T (&x_tail)[12], Result<T>& out)
 {
-    Moments<T> mom;
-    if (HYBRID) accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T x[6] = { T(1), T(0), T(0), T(0), T(0), T(0) };      // :2831-2833
+    if (RES_MOM) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) x_tail[e] = (e == 0 || e == 4 || e == 8 || e == 11) ? T(1) : T(0);
+    }
     // One 6 x 6 array carries Sigma from one iteration to the next and Omega inside it.  Lanes that have
     // left the loop (done) keep their x, res and iters; what their matrix becomes no longer matters.
     T Om[21];
@@ -253,6 +288,7 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
         const T Q2[12] = { k2, j2, i2, r2, r2, -i2, j2, -k2, -i2, -r2, k2, j2 };     // :3949
         const T Q3[12] = { -j2, k2, -r2, i2, i2, r2, k2, j2, r2, -i2, -j2, k2 };     // :3953
         T qq[10], qd1[4], qd2[4], hv[6], res2 = T(0);
+        bool res_trusted = true;
         if (!HYBRID) {
 #pragma unroll
             for (int e = 0; e < 10; ++e) qq[e] = T(0);
@@ -297,20 +333,22 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
             group_sum_arr<LPP>(qq); group_sum_arr<LPP>(qd1); group_sum_arr<LPP>(qd2); group_sum_arr<LPP>(hv);
             res2 = group_sum<LPP>(res2);
         } else {
-            // ---- residual, point by point (:2905-2907)
+            if (!RES_MOM) {
+                // ---- residual, point by point (:2905-2907)
 #pragma unroll 4
-            for (int i = sub; i < n; i += LPP) {
-                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
-                T bx, by;
-                pts.get(i, bx, by);
-                const T P1 = th0 * p1[0] + th1 * p1[1] + th2 * p1[2];
-                const T P2 = th0 * p2[0] + th1 * p2[1] + th2 * p2[2];
-                const T P3 = th0 * p3[0] + th1 * p3[1] + th2 * p3[2];
-                const T dzx = bx - (P1 - bx * P3 + x[4]);
-                const T dzy = by - (P2 - by * P3 + x[5]);
-                res2 = t_fma(dzx, dzx, t_fma(dzy, dzy, res2));
+                for (int i = sub; i < n; i += LPP) {
+                    const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+                    T bx, by;
+                    pts.get(i, bx, by);
+                    const T P1 = th0 * p1[0] + th1 * p1[1] + th2 * p1[2];
+                    const T P2 = th0 * p2[0] + th1 * p2[1] + th2 * p2[2];
+                    const T P3 = th0 * p3[0] + th1 * p3[1] + th2 * p3[2];
+                    const T dzx = bx - (P1 - bx * P3 + x[4]);
+                    const T dzy = by - (P2 - by * P3 + x[5]);
+                    res2 = t_fma(dzx, dzx, t_fma(dzy, dzy, res2));
+                }
+                res2 = group_sum<LPP>(res2);
             }
-            res2 = group_sum<LPP>(res2);
             // ---- H^T H and H^T (z - hx + H x) from the moments
             const T M0[6] = { sC[0], sC[1], sC[2], sC[3], sC[4], sC[5] };
             const T m0[3] = { sC[6], sC[7], sC[8] };
@@ -343,8 +381,15 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) hv[c] = dot3<T>(q1[c], e1) + dot3<T>(q2[c], e2) - dot3<T>(q3[c], e3);
-            hv[4] = mom.sx0 + dot3<T>(m0, p1) - dot3<T>(mom.mx, p3);
-            hv[5] = mom.sy0 + dot3<T>(m0, p2) - dot3<T>(mom.my, p3);
+            const T s1 = dot3<T>(m0, p1) - dot3<T>(mom.mx, p3), s2 = dot3<T>(m0, p2) - dot3<T>(mom.my, p3);
+            hv[4] = mom.sx0 + s1;
+            hv[5] = mom.sy0 + s2;
+            if (RES_MOM) {                                    // ||z - hx||^2 from the moments (:2905-2907)
+                const T qa = dot3<T>(mom.mx, p1) + dot3<T>(mom.my, p2) - dot3<T>(mom.mw, p3);
+                const T sgg = dot3<T>(p1, t1) - T(2) * dot3<T>(p1, t2) + dot3<T>(p2, t3v) - T(2) * dot3<T>(p2, t4) + dot3<T>(p3, t7);
+                res2 = res2_combine<T>(mom.sw0, mom.sx0, mom.sy0, nT, x[4], x[5], T(1), qa, s1, s2, sgg);
+                res_trusted = res2 > kResMomFloor * mom.sw0;
+            }
         }
         // ---- update: Omega += H^T Q^-1 H, zeta += H^T Q^-1 (z - hx + H x) (:2896-2898)
 #pragma unroll
@@ -364,13 +409,18 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
         T xn[6];
         sym_matvec<T, 6>(Om, zeta, xn);
         if (!done) {
+            if (RES_MOM) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { x_tail[k] = p1[k]; x_tail[3 + k] = p2[k]; x_tail[6 + k] = p3[k]; }
+                x_tail[9] = x[4]; x_tail[10] = x[5]; x_tail[11] = T(1);
+            }
 #pragma unroll
             for (int e = 0; e < 6; ++e) x[e] = xn[e];
             res = res_new;
             ++iters;
             const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference    // :2945
             res_old = res;
-            if (t_abs(ratio) < prm.exit_tol) done = true; // :2952
+            if (t_abs(ratio) < prm.exit_tol && res_trusted) done = true; // :2952
         }
     }
     // ---- QEKF_reconstruct_R_t_m1 :3590-3605
@@ -382,6 +432,29 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
     out.t[0] = x[4] * t3; out.t[1] = x[5] * t3; out.t[2] = t3;
     out.res = res;
     out.iters = iters;
+}
+
+template <typename T, int LPP, typename Pts, bool HYBRID>
+PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                        const SolverPrm<T>& prm, Result<T>& out)
+{
+    Moments<T> mom;
+    if (HYBRID) accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    T unused[12];
+    qeif_loop<T, LPP, Pts, HYBRID, false>(pts, sP, sC, n, sub, prm, mom, unused, out);
+}
+
+// No points inside the loop (moment mapping)
+struct NoPts {
+    template <typename T> PNP_DEV void get(int, T& bx, T& by) const { bx = T(0); by = T(0); }
+};
+
+template <typename T>
+PNP_DEV void solve_qeif_from_moments(const Moments<T>& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, T (&x_tail)[12],
+                                     Result<T>& out)
+{
+    NoPts none;
+    qeif_loop<T, 1, NoPts, true, true>(none, nullptr, sC, (int)sC[9], 0, prm, mom, x_tail, out);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -415,6 +488,12 @@ PNP_DEV void lm_gamma_column(const T (&x)[12], const M& m, const T* __restrict__
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) gc.sgg = t_fma(x[k], gc.sg1[k], t_fma(x[3 + k], gc.sg2[k], t_fma(-x[6 + k], gc.sg3[k], gc.sgg)));
+}
+
+template <typename T, typename M>
+PNP_DEV T res2_from_moments(const M& m, const T* __restrict__ sC, const GammaCol<T>& gc, T qa, T gam, T d1, T d2)
+{
+    return res2_combine<T>(m.gsw0(), m.gsx0(), m.gsy0(), sC[9], d1, d2, gam, qa, gc.s1, gc.s2, gc.sgg);
 }
 
 // J^T (z - hx) of the 2n measurement rows
@@ -794,44 +873,19 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
 // rows are added one by one with their own weights; ||z - hx|| that drives the exit test is evaluated
 // point by point.  State order as in the reference: [u1, u2, u3, delta_1, delta_2, gamma].
 // -------------------------------------------------------------------------------------------
-// Omega += w c c^T, zeta += w c (z - h + c.x) for a row with non-zeros va at block BA, vb at block BB
-template <typename T, int BA, int BB>
-PNP_DEV void eif2_row2(T (&Om)[78], T (&zeta)[12], const T (&va)[3], const T (&vb)[3], T v, T w)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const T wa = w * va[a], wb = w * vb[a];
-#pragma unroll
-        for (int b = a; b < 3; ++b) {
-            Om[sidx<12>(BA + a, BA + b)] = t_fma(wa, va[b], Om[sidx<12>(BA + a, BA + b)]);
-            Om[sidx<12>(BB + a, BB + b)] = t_fma(wb, vb[b], Om[sidx<12>(BB + a, BB + b)]);
-        }
-#pragma unroll
-        for (int b = 0; b < 3; ++b) Om[sidx<12>(BA + a, BB + b)] = t_fma(wa, vb[b], Om[sidx<12>(BA + a, BB + b)]);
-        zeta[BA + a] = t_fma(wa, v, zeta[BA + a]);
-        zeta[BB + a] = t_fma(wb, v, zeta[BB + a]);
-    }
-}
-template <typename T, int BA>
-PNP_DEV void eif2_row1(T (&Om)[78], T (&zeta)[12], const T (&va)[3], T v, T w)
-{
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const T wa = w * va[a];
-#pragma unroll
-        for (int b = a; b < 3; ++b) Om[sidx<12>(BA + a, BA + b)] = t_fma(wa, va[b], Om[sidx<12>(BA + a, BA + b)]);
-        zeta[BA + a] = t_fma(wa, v, zeta[BA + a]);
-    }
-}
-
-template <typename T, int LPP, typename Pts>
-PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
-                        const SolverPrm<T>& prm, Result<T>& out)
+// M: the moment container (registers in the direct mappings, shared-memory columns in k_iterate).  RES_MOM (moment
+// mapping): the residual of the early-exit test comes from the moments (res2_from_moments) and x_tail receives the state
+// before the lane's last update, at which the residual pass evaluates the reported res_norm point by point.
+template <typename T, int LPP, typename Pts, typename M, bool RES_MOM>
+PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                       const SolverPrm<T>& prm, const M& mom, T (&x_tail)[12], Result<T>& out)
 {
     constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
-    Moments<T> mom;
-    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2058-2063
+    if (RES_MOM) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) x_tail[e] = x[e];
+    }
     // One 12 x 12 array carries Sigma from one iteration to the next and Omega inside it (see solve_qeif)
     T Om[78];
 #pragma unroll
@@ -845,17 +899,28 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
     const T wc1 = T(1.0 / (1e-2 * 16.0)), wc2 = T(1.0 / (4.0 * 1e-2 * 16.0)), wc3 = T(1);   // :2085-2091
     const T sth = T(60.0 * (3.14159265358979323846 / 180.0));
     const T sth2 = sth * sth, st12 = T(0.05 * 0.05), st3 = T(4.0);   // :3686-3689
+    T zeta[12], res_new = T(0);
+    bool res_trusted = true;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) zeta[e] = T(0);
 
-    for (int it = 0; it < prm.max_it; ++it) {
-        if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
-        else          { if (done) break; }
+    // An iteration inverts two 12 x 12 matrices (Sigma + R_k -> Omega_bar, :2146-2150; Omega -> Sigma, :2184) and
+    // multiplies each inverse by a vector (zeta = Omega_bar x, :2152; x = Sigma zeta, :2185).  The loop below runs
+    // one HALF iteration per trip -- predict-side work, THE inversion, THE product, then update-side work or the
+    // state update -- so that the unrolled inversion (the bulk of the kernel's instructions) exists once: the first
+    // version, with both inversions unrolled in one body, missed the 32 KB instruction cache on every iteration
+    // (ncu: 1.26 instruction-fetch stalls per issued instruction, FP64 pipe 42 % busy).
+    for (int half = 0; half < 2 * prm.max_it; ++half) {
+        const bool update_half = (half & 1) != 0;                    // warp-uniform
         const T u1[3] = { x[0], x[1], x[2] }, u2[3] = { x[3], x[4], x[5] }, u3[3] = { x[6], x[7], x[8] };
         const T gam = x[GG], d1 = x[D1], d2 = x[D2];
         const T u11 = dot3<T>(u1, u1), u22 = dot3<T>(u2, u2), u33 = dot3<T>(u3, u3);
         const T u13 = dot3<T>(u1, u3), u23 = dot3<T>(u2, u3), u12 = dot3<T>(u1, u2);
-        // ---- predict: Omega = pinv(Sigma + R_k) (:2146-2150), zeta = Omega x (:2152)
-        // R_k's u blocks: so3(u_i) sigma^2 so3(u_j)^T = sigma^2 ((u_i . u_j) I - u_j u_i^T)   (:3690-3696)
-        {
+        if (!update_half) {
+            if (LPP == 1) { if (__all_sync(0xffffffffu, done)) break; }
+            else          { if (done) break; }
+            // ---- predict: Omega = pinv(Sigma + R_k) (:2146-2150)
+            // R_k's u blocks: so3(u_i) sigma^2 so3(u_j)^T = sigma^2 ((u_i . u_j) I - u_j u_i^T)   (:3690-3696)
             const T* uu[3] = { u1, u2, u3 };
             const T dd[3][3] = { { u11, u12, u13 }, { u12, u22, u23 }, { u13, u23, u33 } };
 #pragma unroll
@@ -870,105 +935,156 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
                             const T v = ((a == b) ? dd[bi][bj] : T(0)) - uu[bj][a] * uu[bi][b];
                             Om[sidx<12>(3 * bi + a, 3 * bj + b)] = t_fma(sth2, v, Om[sidx<12>(3 * bi + a, 3 * bj + b)]);
                         }
+            Om[sidx<12>(D1, D1)] += t_abs(gam) * st12;               // :3700
+            Om[sidx<12>(D2, D2)] += t_abs(gam) * st12;
+            Om[sidx<12>(GG, GG)] += (gam * gam) * st3;               // :3701
         }
-        Om[sidx<12>(D1, D1)] += t_abs(gam) * st12;                   // :3700
-        Om[sidx<12>(D2, D2)] += t_abs(gam) * st12;
-        Om[sidx<12>(GG, GG)] += (gam * gam) * st3;                   // :3701
         spd_inverse<T, 12>(Om);
-        T zeta[12];
-        sym_matvec<T, 12>(Om, x, zeta);
+        T y[12];
+        {
+            T v[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) v[e] = update_half ? zeta[e] : x[e];
+            sym_matvec<T, 12>(Om, v, y);                             // zeta = Omega x (:2152)  |  x = pinv(Omega) zeta (:2184-2185)
+        }
+        if (update_half) {
+            if (!done) {
+                if (RES_MOM) {
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) x_tail[e] = x[e];
+                }
+#pragma unroll
+                for (int e = 0; e < 12; ++e) x[e] = y[e];
+                res = res_new;
+                ++iters;
+                const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference               // :2196
+                res_old = res;
+                if (t_abs(ratio) < prm.exit_tol && res_trusted) done = true;        // :2202
+            }
+            continue;
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) zeta[e] = y[e];
         // ---- residual over the 2n measurement rows, point by point (:2176-2178)
         T res2 = T(0);
+        if (!RES_MOM) {
 #pragma unroll 4
-        for (int i = sub; i < n; i += LPP) {
-            const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
-            T bx, by;
-            pts.get(i, bx, by);
-            const T a = th0 * u1[0] + th1 * u1[1] + th2 * u1[2];
-            const T b = th0 * u2[0] + th1 * u2[1] + th2 * u2[2];
-            const T c = th0 * u3[0] + th1 * u3[1] + th2 * u3[2];
-            const T rx = bx - (gam * (a - bx * c) + d1);
-            const T ry = by - (gam * (b - by * c) + d2);
-            res2 = t_fma(rx, rx, t_fma(ry, ry, res2));
+            for (int i = sub; i < n; i += LPP) {
+                const T th0 = sP[3 * i], th1 = sP[3 * i + 1], th2 = sP[3 * i + 2];
+                T bx, by;
+                pts.get(i, bx, by);
+                const T a = th0 * u1[0] + th1 * u1[1] + th2 * u1[2];
+                const T b = th0 * u2[0] + th1 * u2[1] + th2 * u2[2];
+                const T c = th0 * u3[0] + th1 * u3[1] + th2 * u3[2];
+                const T rx = bx - (gam * (a - bx * c) + d1);
+                const T ry = by - (gam * (b - by * c) + d2);
+                res2 = t_fma(rx, rx, t_fma(ry, ry, res2));
+            }
+            res2 = group_sum<LPP>(res2);
         }
-        res2 = group_sum<LPP>(res2);
         // ---- update, measurement rows from the moments (:2157-2164)
         {
             GammaCol<T> gc;
-            lm_gamma_column<T, Moments<T> >(x, mom, sC, gc);
+            lm_gamma_column<T, M>(x, mom, sC, gc);
             const T wg = w * gam, wgg = wg * gam;
+            const T mxv[3] = { mom.gmx(0), mom.gmx(1), mom.gmx(2) }, myv[3] = { mom.gmy(0), mom.gmy(1), mom.gmy(2) };
+            const T mwv[3] = { mom.gmw(0), mom.gmw(1), mom.gmw(2) };
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
 #pragma unroll
                 for (int b = a; b < 3; ++b) {
                     Om[sidx<12>(U1 + a, U1 + b)] = t_fma(wgg, sC[s3(a, b)], Om[sidx<12>(U1 + a, U1 + b)]);
                     Om[sidx<12>(U2 + a, U2 + b)] = t_fma(wgg, sC[s3(a, b)], Om[sidx<12>(U2 + a, U2 + b)]);
-                    Om[sidx<12>(U3 + a, U3 + b)] = t_fma(wgg, mom.Mw[s3(a, b)], Om[sidx<12>(U3 + a, U3 + b)]);
+                    Om[sidx<12>(U3 + a, U3 + b)] = t_fma(wgg, mom.gMw(s3(a, b)), Om[sidx<12>(U3 + a, U3 + b)]);
                 }
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
-                    Om[sidx<12>(U1 + a, U3 + b)] = t_fma(-wgg, mom.Mx[s3(a, b)], Om[sidx<12>(U1 + a, U3 + b)]);
-                    Om[sidx<12>(U2 + a, U3 + b)] = t_fma(-wgg, mom.My[s3(a, b)], Om[sidx<12>(U2 + a, U3 + b)]);
+                    Om[sidx<12>(U1 + a, U3 + b)] = t_fma(-wgg, mom.gMx(s3(a, b)), Om[sidx<12>(U1 + a, U3 + b)]);
+                    Om[sidx<12>(U2 + a, U3 + b)] = t_fma(-wgg, mom.gMy(s3(a, b)), Om[sidx<12>(U2 + a, U3 + b)]);
                 }
                 Om[sidx<12>(U1 + a, D1)] = t_fma(wg, sC[6 + a], Om[sidx<12>(U1 + a, D1)]);
                 Om[sidx<12>(U2 + a, D2)] = t_fma(wg, sC[6 + a], Om[sidx<12>(U2 + a, D2)]);
-                Om[sidx<12>(U3 + a, D1)] = t_fma(-wg, mom.mx[a], Om[sidx<12>(U3 + a, D1)]);
-                Om[sidx<12>(U3 + a, D2)] = t_fma(-wg, mom.my[a], Om[sidx<12>(U3 + a, D2)]);
+                Om[sidx<12>(U3 + a, D1)] = t_fma(-wg, mxv[a], Om[sidx<12>(U3 + a, D1)]);
+                Om[sidx<12>(U3 + a, D2)] = t_fma(-wg, myv[a], Om[sidx<12>(U3 + a, D2)]);
                 Om[sidx<12>(U1 + a, GG)] = t_fma(wg, gc.sg1[a], Om[sidx<12>(U1 + a, GG)]);
                 Om[sidx<12>(U2 + a, GG)] = t_fma(wg, gc.sg2[a], Om[sidx<12>(U2 + a, GG)]);
                 Om[sidx<12>(U3 + a, GG)] = t_fma(-wg, gc.sg3[a], Om[sidx<12>(U3 + a, GG)]);
                 // H^T Q^-1 (z - hx + H x), z - hx + H x = (bx + gamma g1, by + gamma g2)
-                zeta[U1 + a] = t_fma(wg, mom.mx[a] + gam * gc.sg1[a], zeta[U1 + a]);
-                zeta[U2 + a] = t_fma(wg, mom.my[a] + gam * gc.sg2[a], zeta[U2 + a]);
-                zeta[U3 + a] = t_fma(-wg, mom.mw[a] + gam * gc.sg3[a], zeta[U3 + a]);
+                zeta[U1 + a] = t_fma(wg, mxv[a] + gam * gc.sg1[a], zeta[U1 + a]);
+                zeta[U2 + a] = t_fma(wg, myv[a] + gam * gc.sg2[a], zeta[U2 + a]);
+                zeta[U3 + a] = t_fma(-wg, mwv[a] + gam * gc.sg3[a], zeta[U3 + a]);
             }
             Om[sidx<12>(D1, D1)] = t_fma(w, sC[9], Om[sidx<12>(D1, D1)]);
             Om[sidx<12>(D2, D2)] = t_fma(w, sC[9], Om[sidx<12>(D2, D2)]);
             Om[sidx<12>(D1, GG)] = t_fma(w, gc.s1, Om[sidx<12>(D1, GG)]);
             Om[sidx<12>(D2, GG)] = t_fma(w, gc.s2, Om[sidx<12>(D2, GG)]);
             Om[sidx<12>(GG, GG)] = t_fma(w, gc.sgg, Om[sidx<12>(GG, GG)]);
-            const T qa = dot3<T>(mom.mx, u1) + dot3<T>(mom.my, u2) - dot3<T>(mom.mw, u3);
-            zeta[D1] = t_fma(w, mom.sx0 + gam * gc.s1, zeta[D1]);
-            zeta[D2] = t_fma(w, mom.sy0 + gam * gc.s2, zeta[D2]);
+            const T qa = dot3<T>(mxv, u1) + dot3<T>(myv, u2) - dot3<T>(mwv, u3);
+            zeta[D1] = t_fma(w, mom.gsx0() + gam * gc.s1, zeta[D1]);
+            zeta[D2] = t_fma(w, mom.gsy0() + gam * gc.s2, zeta[D2]);
             zeta[GG] = t_fma(w, qa + gam * gc.sgg, zeta[GG]);
+            if (RES_MOM) {                                           // :2176-2178 from the moments
+                res2 = res2_from_moments<T, M>(mom, sC, gc, qa, gam, d1, d2);
+                res_trusted = res2 > kResMomFloor * mom.gsw0();
+            }
         }
-        // ---- update, the nine constraint rows (:3753-3772, Jacobians :3787-3823); v = z - h + c.x
+        // ---- update, the nine constraint rows (:3753-3772, Jacobians :3787-3823), collected per 3 x 3 block.  Row k adds
+        // w_k c_k c_k^T to Omega and w_k c_k (z_k - h_k + c_k . x) to zeta; with the rows
+        //   1-3 (weight wc1): (u3 | u1) on blocks (U1, U3), (u3 | u2) on (U2, U3), (u2 | u1) on (U1, U2),   v = u_i . u_j
+        //   4-6 (weight wc2): (u1 | -u3) on (U1, U3), (u2 | -u3) on (U2, U3), (u1 | -u2) on (U1, U2),     v = 0
+        //   7-9 (weight wc3): j_i = u_i / (2 |u_i|) on block U_i,                                         v = 1 - |u_i| + j_i . u_i
+        // the diagonal blocks are combinations of the three outer products P_i = u_i u_i^T and the off-diagonal ones of
+        // u_i u_j^T: 60 % fewer instructions than nine rank-one updates, same sums up to the order of the additions.
         {
-            const T nu2[3] = { -u2[0], -u2[1], -u2[2] }, nu3[3] = { -u3[0], -u3[1], -u3[2] };
-            eif2_row2<T, U1, U3>(Om, zeta, u3, u1, T(0) - u13 + (u13 + u13), wc1);
-            eif2_row2<T, U2, U3>(Om, zeta, u3, u2, T(0) - u23 + (u23 + u23), wc1);
-            eif2_row2<T, U1, U2>(Om, zeta, u2, u1, T(0) - u12 + (u12 + u12), wc1);
-            eif2_row2<T, U1, U3>(Om, zeta, u1, nu3, T(0) - (u11 - u33) + (u11 - u33), wc2);
-            eif2_row2<T, U2, U3>(Om, zeta, u2, nu3, T(0) - (u22 - u33) + (u22 - u33), wc2);
-            eif2_row2<T, U1, U2>(Om, zeta, u1, nu2, T(0) - (u11 - u22) + (u11 - u22), wc2);
             const T y1 = t_rsqrt<T>(u11), y2 = t_rsqrt<T>(u22), y3 = t_rsqrt<T>(u33);
             const T n1 = t_sqrt_fast<T>(u11, y1), n2 = t_sqrt_fast<T>(u22, y2), n3 = t_sqrt_fast<T>(u33, y3);
-            const T h1 = T(0.5) * y1, h2 = T(0.5) * y2, h3 = T(0.5) * y3;
-            const T j1[3] = { u1[0] * h1, u1[1] * h1, u1[2] * h1 };   // u^T / (2 |u|) (:3819)
-            const T j2[3] = { u2[0] * h2, u2[1] * h2, u2[2] * h2 };
-            const T j3[3] = { u3[0] * h3, u3[1] * h3, u3[2] * h3 };
-            eif2_row1<T, U1>(Om, zeta, j1, T(1) - n1 + dot3<T>(j1, u1), wc3);
-            eif2_row1<T, U2>(Om, zeta, j2, T(1) - n2 + dot3<T>(j2, u2), wc3);
-            eif2_row1<T, U3>(Om, zeta, j3, T(1) - n3 + dot3<T>(j3, u3), wc3);
-        }
-        const T res_new = t_sqrt_nn<T>(res2);
-        // ---- x = pinv(Omega) zeta (:2184-2185)
-        spd_inverse<T, 12>(Om);
-        T xn[12];
-        sym_matvec<T, 12>(Om, zeta, xn);
-        if (!done) {
+            const T h1 = T(0.5) * y1, h2 = T(0.5) * y2, h3 = T(0.5) * y3;             // j_i = h_i u_i (:3819)
+            const T c1 = t_fma(wc3 * h1, h1, T(2) * wc2), c2 = t_fma(wc3 * h2, h2, T(2) * wc2), c3 = t_fma(wc3 * h3, h3, T(2) * wc2);
+            // zeta: rows 1-3 carry v = u_i . u_j, rows 7-9 v_i = 1 - |u_i| + h_i |u_i|^2 (times h_i), rows 4-6 nothing
+            const T g1 = wc3 * h1 * (T(1) - n1 + h1 * u11), g2 = wc3 * h2 * (T(1) - n2 + h2 * u22), g3 = wc3 * h3 * (T(1) - n3 + h3 * u33);
+            const T v13 = wc1 * u13, v23 = wc1 * u23, v12 = wc1 * u12;
 #pragma unroll
-            for (int e = 0; e < 12; ++e) x[e] = xn[e];
-            res = res_new;
-            ++iters;
-            const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference               // :2196
-            res_old = res;
-            if (t_abs(ratio) < prm.exit_tol) done = true;            // :2202
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    const T p1 = u1[a] * u1[b], p2 = u2[a] * u2[b], p3 = u3[a] * u3[b];
+                    Om[sidx<12>(U1 + a, U1 + b)] += t_fma(c1, p1, wc1 * (p2 + p3));
+                    Om[sidx<12>(U2 + a, U2 + b)] += t_fma(c2, p2, wc1 * (p1 + p3));
+                    Om[sidx<12>(U3 + a, U3 + b)] += t_fma(c3, p3, wc1 * (p1 + p2));
+                }
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    Om[sidx<12>(U1 + a, U3 + b)] = t_fma(wc1 * u3[a], u1[b], t_fma(-wc2 * u1[a], u3[b], Om[sidx<12>(U1 + a, U3 + b)]));
+                    Om[sidx<12>(U2 + a, U3 + b)] = t_fma(wc1 * u3[a], u2[b], t_fma(-wc2 * u2[a], u3[b], Om[sidx<12>(U2 + a, U3 + b)]));
+                    Om[sidx<12>(U1 + a, U2 + b)] = t_fma(wc1 * u2[a], u1[b], t_fma(-wc2 * u1[a], u2[b], Om[sidx<12>(U1 + a, U2 + b)]));
+                }
+                zeta[U1 + a] = t_fma(v13, u3[a], t_fma(v12, u2[a], t_fma(g1, u1[a], zeta[U1 + a])));
+                zeta[U2 + a] = t_fma(v23, u3[a], t_fma(v12, u1[a], t_fma(g2, u2[a], zeta[U2 + a])));
+                zeta[U3 + a] = t_fma(v13, u1[a], t_fma(v23, u2[a], t_fma(g3, u3[a], zeta[U3 + a])));
+            }
         }
+        res_new = t_sqrt_nn<T>(res2);
     }
     lm_reconstruct<T>(x, out);
     out.res = res;
     out.iters = iters;
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                        const SolverPrm<T>& prm, Result<T>& out)
+{
+    Moments<T> mom;
+    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    T unused[12];
+    eif2_loop<T, LPP, Pts, Moments<T>, false>(pts, sP, sC, n, sub, prm, mom, unused, out);
+}
+
+template <typename T, typename M>
+PNP_DEV void solve_eif2_from_moments(const M& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, T (&x_tail)[12], Result<T>& out)
+{
+    NoPts none;
+    eif2_loop<T, 1, NoPts, M, true>(none, nullptr, sC, (int)sC[9], 0, prm, mom, x_tail, out);
 }
 
 // -------------------------------------------------------------------------------------------

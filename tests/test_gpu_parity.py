@@ -14,7 +14,7 @@ from pnp_solver_test_b200 import patterns as pt
 
 pytestmark = pytest.mark.gpu
 MAP_THREAD, MAP_MOMENT, MAP_WARP = 1, 2, 32
-HAS_MOMENT_FORM = ("lm", "linear_f2")
+HAS_MOMENT_FORM = ("lm", "linear_f2", "qeif", "eif2")     # QEIF: from 12 landmarks on
 
 
 @pytest.mark.parametrize("mapping", [MAP_THREAD, MAP_MOMENT, MAP_WARP])
@@ -23,8 +23,8 @@ def test_cuda_matches_reference_goldens(name, mapping):
     g = load_golden(name)
     if mapping == MAP_THREAD and g["pattern"].shape[0] > 256:
         pytest.skip("thread mapping holds the tile in shared memory: n <= ~380")
-    if mapping == MAP_MOMENT and str(g["method"]) not in HAS_MOMENT_FORM:
-        pytest.skip("moment mapping exists for LM and linear F2")
+    if mapping == MAP_MOMENT and (str(g["method"]) not in HAS_MOMENT_FORM or (str(g["method"]) == "qeif" and g["pattern"].shape[0] < 12)):
+        pytest.skip("no moment mapping for linear F1, nor for QEIF below 12 landmarks")
     out = cuda_solve(str(g["method"]), g["uv"], g["pattern"], g["K"], mapping=mapping)
     compare_solutions(out, g, mask=g["stable"], iters_mask=g["iters_stable"])
 
@@ -63,7 +63,7 @@ def _workload(n, B, seed, quantized=True, noise=0.0):
                                         (1024, 96, MAP_MOMENT)])
 def test_cuda_matches_oracle_on_fresh_inputs(method, n, B, mapping):
     if mapping == MAP_MOMENT and method not in HAS_MOMENT_FORM:
-        pytest.skip("moment mapping exists for LM and linear F2")
+        pytest.skip("no moment mapping for linear F1")
     P, K, w = _workload(n, B, seed=1000 + n)
     ref, stable, it_stable = oracle_stability(method, w["uv"], P, K)
     out = cuda_solve(method, w["uv"], P, K, mapping=mapping)
@@ -83,7 +83,7 @@ def test_cuda_matches_oracle_with_pixel_noise(method):
 
 def test_moment_mapping_with_landmark_subset_and_ragged_batches():
     P, K, w = _workload(15, 1000, seed=13)
-    idx = np.array([0, 1, 3, 4, 5, 6, 9, 12], np.int32)
+    idx = np.array([0, 1, 3, 4, 5, 6, 9, 12, 14, 2, 11, 8], np.int32)      # 12 landmarks: QEIF has a moment form from there on
     for method in HAS_MOMENT_FORM:
         for B in (1, 33, 1000):
             ref, stable, _ = oracle_stability(method, w["uv"][:B, idx], P[idx], K)
