@@ -306,7 +306,7 @@ def extra_configs(dev, sampler_index=0, min_ms=200.0):
     prof = pnp.default_params(flags=_lib.FLAG_PROFILE)
     big = {"workload": "%d problems x %d points, FP64" % (B_big, n_big), "bytes_per_solve_survey": 8 * (2 * n_big + 16) + 8,
            "hbm_peak_gbs": hbm_peak, "peak_source": hbm_src}
-    for method in ("linear_f2", "lm"):
+    for method in ("linear_f2", "lm", "qeif", "eif2"):
         ms, o, kms, ck = timed(lambda: pnp.solve_batch(method, wb["uv"], patb, K, params=prof), profile=True)
         b0 = B_big * (16 * n_big + 29 * 8)
         b2 = B_big * (16 * n_big + 12 * 8 + 8)
