@@ -511,12 +511,47 @@ __global__ void __launch_bounds__(256) k_stream_warp(const __grid_constant__ Mom
 // pattern (24 KB for 1024 points) is read through L1 instead of taking shared memory from the ring.
 // Requires all landmarks (no selection) and rows that are a multiple of 16 bytes.
 // ------------------------------------------------------------------------------------------
-constexpr int kRingSlots = 3;
-constexpr int kRingPoints = 256;          // 4 KB per slot in FP64: 8 points per lane between two barrier waits
-constexpr int kRingWarps = 8;
+// Sum v[k] over the 32 lanes of a warp so that lane k ends up with the total of v[k] in v[0] (k < N; N <= 32 values, the rest
+// structurally zero): five halving steps -- at offset h a lane keeps the half of the index range that contains its own index
+// and receives the partner's partial sums of that half -- 31 shuffled values and 31 additions instead of the 32 x 5 of a
+// butterfly that leaves every sum in every lane.
+template <typename T, int N>
+PNP_DEV void warp_reduce_scatter(T (&v)[32], int lane)
+{
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool hi = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            if (h < 16 || i + h < N) {
+                const T send = hi ? v[i] : v[i + h];
+                const T keep = hi ? v[i + h] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            } else {
+                v[i] += __shfl_xor_sync(0xffffffffu, v[i], h);   // the upper half does not exist: only the lower lanes' sums matter
+            }
+        }
+    }
+}
+
+#ifndef PNP_RING_SLOTS
+#define PNP_RING_SLOTS 3
+#endif
+#ifndef PNP_RING_POINTS
+#define PNP_RING_POINTS 256
+#endif
+#ifndef PNP_RING_WARPS
+#define PNP_RING_WARPS 8
+#endif
+#ifndef PNP_RING_MINBLOCKS
+#define PNP_RING_MINBLOCKS 1
+#endif
+constexpr int kRingSlots = PNP_RING_SLOTS;
+constexpr int kRingPoints = PNP_RING_POINTS;   // 4 KB per slot in FP64: 8 points per lane between two barrier waits
+constexpr int kRingWarps = PNP_RING_WARPS;
 
 template <typename T, int METHOD, int PASS>
-__global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __grid_constant__ MomArgs<T> a)
+__global__ void __launch_bounds__(kRingWarps * 32, PNP_RING_MINBLOCKS) k_stream_warp_tma(const __grid_constant__ MomArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Vec2<T>::type V2;
@@ -570,15 +605,16 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
             }
             mbar_wait(bar + slot, (phase >> slot) & 1u);
             phase ^= (1u << slot);
-            const V2* row = reinterpret_cast<const V2*>(ring + (size_t)slot * kRingPoints * 2);
+            const V2* row = reinterpret_cast<const V2*>(ring + (size_t)slot * kRingPoints * 2) + lane;
             const int cnt = (n - c * kRingPoints < kRingPoints) ? (n - c * kRingPoints) : kRingPoints;
-#pragma unroll 4
-            for (int k = lane; k < cnt; k += 32) {
-                const V2 px = row[k];
-                const int i = c * kRingPoints + k;
+            const T* __restrict__ gPl = gP + 3 * (c * kRingPoints + lane);
+            // a full slot is kRingPoints / 32 points per lane at compile-time offsets (no loop counter, no bounds test)
+            const int per_lane = (cnt == kRingPoints) ? kRingPoints / 32 : (cnt - lane + 31) / 32;
+            auto point = [&](int j) {
+                const V2 px = row[32 * j];
                 T bx, by;                                                     // nu = K^-1 [u, v, 1]^T (:3305)
                 normalise_px<T>(px.x, px.y, k00, k01, k02, k10, k11, k12, bx, by);
-                const T th[3] = { __ldg(gP + 3 * i), __ldg(gP + 3 * i + 1), __ldg(gP + 3 * i + 2) };
+                const T th[3] = { __ldg(gPl + 96 * j), __ldg(gPl + 96 * j + 1), __ldg(gPl + 96 * j + 2) };
                 if (PASS == 0) {
                     mom.template add<method_with_w(METHOD), method_with_s(METHOD)>(th, bx, by);
                 } else if (method_lm_residual(METHOD)) {
@@ -595,14 +631,20 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
                     const T ex = bx * db - dx, ey = by * db - dy;
                     acc0 = t_fma(ex, ex, acc0); acc1 = t_fma(ey, ey, acc1);
                 }
+            };
+            if (cnt == kRingPoints) {
+#pragma unroll
+                for (int j = 0; j < kRingPoints / 32; ++j) point(j);
+            } else {
+                for (int j = 0; j < per_lane; ++j) point(j);
             }
         }
         if (PASS == 0) {
-            mom.template reduce<32, method_with_w(METHOD), method_with_s(METHOD)>();
-            T mine = T(0);                                                    // after the butterfly every lane holds every sum
+            T v[32];                                                          // lane k leaves with the total of moment k
 #pragma unroll
-            for (int k = 0; k < method_nmom(METHOD); ++k) if (lane == k) mine = mom.at(k);
-            if (lane < method_nmom(METHOD)) a.mom[(size_t)lane * a.ld + b] = mine;
+            for (int k = 0; k < 32; ++k) v[k] = (k < method_nmom(METHOD)) ? mom.at(k) : T(0);
+            warp_reduce_scatter<T, method_nmom(METHOD)>(v, lane);
+            if (lane < method_nmom(METHOD)) a.mom[(size_t)lane * a.ld + b] = v[0];
         } else {
             acc0 = group_sum<32>(acc0); acc1 = group_sum<32>(acc1);
             if (lane == 0 && a.res) {

@@ -163,12 +163,19 @@ def test_fp32_mode_within_stated_bound(method, tolR, tolT):
         assert (out["iters"] == ref["iters"]).mean() > 0.98
 
 
-def test_fp32_lm_tracks_fp64_where_well_posed():
-    P, K, w = _workload(68, 2048, seed=22)
+@pytest.mark.parametrize("n", [15, 68])
+def test_fp32_lm_tracks_fp64_where_well_posed(n):
+    """FP32 LM against the FP64 reference algorithm on the well-posed subset, stated bound: |dR| and |dt| / t3 at most
+    5e-5 at the median, 5e-4 at the 90th and 2e-2 at the 99th percentile (measured 9e-6 / 5e-5 / 2e-3: LM's 14 undamped-ish
+    steps amplify single-precision rounding on the problems that are close to its stability edge)."""
+    P, K, w = _workload(n, 4096, seed=22)
     ref, stable, _ = oracle_stability("lm", w["uv"], P, K)
     out = cuda_solve("lm", w["uv"], P, K, dtype=torch.float32)
     dR = np.abs(out["R"] - ref["R"]).reshape(len(ref["R"]), -1).max(axis=1)[stable]
-    assert np.median(dR) < 1e-3, np.median(dR)
+    dt = (np.abs(out["t"] - ref["t"]).max(axis=1) / np.abs(ref["t"][:, 2]))[stable]
+    for d in (dR, dt):
+        q = np.quantile(d, [0.5, 0.9, 0.99])
+        assert q[0] < 5e-5 and q[1] < 5e-4 and q[2] < 2e-2, q
 
 
 def test_pnp_solver_class_is_a_drop_in():
