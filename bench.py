@@ -661,11 +661,6 @@ def run_ours(args):
         pipe.close()
         del host_uv, outs
 
-    # ---- the other BASELINE configs and the alternative execution shapes, outside the timed region, each device-timed
-    extra = None
-    if not args.no_extra and world == 1:
-        extra = extra_configs(dev, sampler_index=local)
-
     def leave():
         """A process group whose collectives were captured in a still-alive CUDA graph does not tear down reliably
         (observed: destroy_process_group never returned after a 2-rank graph run).  Drop the graph, let every rank
@@ -674,7 +669,10 @@ def run_ours(args):
         graph = None
         keep.clear()
         sys.stdout.flush()
-        torch.cuda.synchronize()
+        try:
+            torch.cuda.synchronize()
+        except Exception:                                   # noqa: BLE001
+            pass
         if world > 1:
             dist.barrier()
             os._exit(0)
@@ -711,6 +709,14 @@ def run_ours(args):
                      "frac": (rr_bytes / (ms_res * 1e-3) / 1e9 / hbm_peak) if ms_res > 0 else None, "peak_source": hbm_src,
                      "fp64_tflops_algorithmic": rr_flop * B / (ms_res * 1e-3) / 1e12 if ms_res > 0 else None}]}
     cpu = cpu_baseline_block() if (world == 1 and not args.no_cpu) else None
+    # ---- the other BASELINE configs and the alternative execution shapes, outside the timed region, each device-timed.
+    # Last, and fenced: nothing the headline line needs depends on it any more.
+    extra = None
+    if not args.no_extra and world == 1:
+        try:
+            extra = extra_configs(dev, sampler_index=local)
+        except Exception as e:                              # noqa: BLE001
+            extra = {"error": (str(e).splitlines() or [type(e).__name__])[0][:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -534,24 +534,15 @@ PNP_DEV void warp_reduce_scatter(T (&v)[32], int lane)
     }
 }
 
-#ifndef PNP_RING_SLOTS
-#define PNP_RING_SLOTS 3
-#endif
-#ifndef PNP_RING_POINTS
-#define PNP_RING_POINTS 256
-#endif
-#ifndef PNP_RING_WARPS
-#define PNP_RING_WARPS 8
-#endif
-#ifndef PNP_RING_MINBLOCKS
-#define PNP_RING_MINBLOCKS 1
-#endif
-constexpr int kRingSlots = PNP_RING_SLOTS;
-constexpr int kRingPoints = PNP_RING_POINTS;   // 4 KB per slot in FP64: 8 points per lane between two barrier waits
-constexpr int kRingWarps = PNP_RING_WARPS;
+// Fixed shape.  (Other shapes were tried on 100 k x 1024 points, tools/build_variant.py: 3 slots x 128 points 0.57 ms, 16 warps
+// per CTA 0.39 ms against 0.42 ms for this one; EVEN slot counts -- 2 x 256, 4 x 128, 6 x 128 -- faulted intermittently with an
+// illegal address, in the round-1 form of this kernel as well, cause not found: they are not offered.)
+constexpr int kRingSlots = 3;
+constexpr int kRingPoints = 256;          // 4 KB per slot in FP64: 8 points per lane between two barrier waits
+constexpr int kRingWarps = 8;
 
 template <typename T, int METHOD, int PASS>
-__global__ void __launch_bounds__(kRingWarps * 32, PNP_RING_MINBLOCKS) k_stream_warp_tma(const __grid_constant__ MomArgs<T> a)
+__global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __grid_constant__ MomArgs<T> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     typedef typename Vec2<T>::type V2;
