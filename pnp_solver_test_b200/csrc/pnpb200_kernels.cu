@@ -561,21 +561,27 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
     const long long w0 = (long long)blockIdx.x * kRingWarps + warp, wstride = (long long)gridDim.x * kRingWarps;
     const long long my_problems = (w0 < a.B) ? (a.B - w0 + wstride - 1) / wstride : 0;
     const long long total = my_problems * cpp;                                // chunks this warp will consume
-    // chunk g of this warp = chunk (g % cpp) of problem w0 + (g / cpp) * wstride
-    auto issue = [&](long long g) {
+    // The copy stream runs kRingSlots - 1 chunks ahead of the arithmetic, straight across problem boundaries: chunk g of
+    // this warp = chunk (g % cpp) of problem w0 + (g / cpp) * wstride, kept as running (row pointer, chunk, slot) instead
+    // of 64-bit divisions per chunk.
+    const T* irow = a.uv + (size_t)w0 * n * 2;                               // row of the problem whose chunks are being issued
+    const size_t irow_step = (size_t)wstride * n * 2;
+    int ic = 0, islot = 0;
+    long long issued = 0;
+    auto issue_next = [&]() {
         if (lane == 0) {
-            const long long b = w0 + (g / cpp) * wstride;
-            const int c = (int)(g % cpp);
-            const int cnt = (n - c * kRingPoints < kRingPoints) ? (n - c * kRingPoints) : kRingPoints;
+            const int cnt = (n - ic * kRingPoints < kRingPoints) ? (n - ic * kRingPoints) : kRingPoints;
             const uint32_t bytes = (uint32_t)cnt * 2u * (uint32_t)sizeof(T);
-            const int slot = (int)(g % kRingSlots);
-            mbar_expect_tx(bar + slot, bytes);
-            bulk_copy_g2s(ring + (size_t)slot * kRingPoints * 2, a.uv + ((size_t)b * n + (size_t)c * kRingPoints) * 2, bytes, bar + slot);
+            mbar_expect_tx(bar + islot, bytes);
+            bulk_copy_g2s(ring + (size_t)islot * kRingPoints * 2, irow + (size_t)ic * kRingPoints * 2, bytes, bar + islot);
         }
+        ++issued;
+        if (++ic == cpp) { ic = 0; irow += irow_step; }
+        if (++islot == kRingSlots) islot = 0;
     };
-    for (long long g = 0; g < kRingSlots - 1 && g < total; ++g) issue(g);
+    for (int k = 0; k < kRingSlots - 1 && issued < total; ++k) issue_next();
     uint32_t phase = 0;                                                      // bit s = parity to wait for on slot s
-    long long g = 0;
+    int slot = 0;
     for (long long p = 0; p < my_problems; ++p) {
         const long long b = w0 + p * wstride;
         Moments<T> mom;
@@ -586,13 +592,12 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
 #pragma unroll
             for (int k = 0; k < PNP_NTAIL; ++k) st[k] = a.tail[(size_t)k * a.ld + b];
         }
-        for (int c = 0; c < cpp; ++c, ++g) {
-            const int slot = (int)(g % kRingSlots);
+        for (int c = 0; c < cpp; ++c) {
             // refill the slot that was consumed one step ago, then wait for this one
-            if (g + kRingSlots - 1 < total) {
+            if (issued < total) {
                 __syncwarp();
                 fence_proxy_async();
-                issue(g + kRingSlots - 1);
+                issue_next();
             }
             mbar_wait(bar + slot, (phase >> slot) & 1u);
             phase ^= (1u << slot);
@@ -629,6 +634,7 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
             } else {
                 for (int j = 0; j < per_lane; ++j) point(j);
             }
+            if (++slot == kRingSlots) slot = 0;
         }
         if (PASS == 0) {
             T v[32];                                                          // lane k leaves with the total of moment k
