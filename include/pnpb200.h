@@ -60,6 +60,10 @@ extern "C" {
 
 #define PNPB200_FLAG_PROFILE 1  /* record CUDA events around each kernel of the call (pnpb200_profile_read) */
 #define PNPB200_FLAG_QEIF_DIRECT 2 /* QEIF: accumulate H^T H point by point even for n >= 12 (default there: from the moments) */
+#define PNPB200_FLAG_LM_TRUE_JACOBIAN 4 /* method LM only, NOT a parity mode: the reference's loop (identity start, max_it iterations,
+                                           constant lambda) with the true gradients of its nine constraint rows (2u for the quadratic rows,
+                                           u/|u| for the norm rows) in place of the halved ones it uses (PNP_SOLVER_LIB.py:3787-3823);
+                                           moment mapping only */
 
 #define PNPB200_MAX_PATTERNS 8
 #define PNPB200_REPORT_WIDTH 16

@@ -19,6 +19,7 @@ MAP_AUTO, MAP_THREAD, MAP_MOMENT, MAP_WARP = 0, 1, 2, 32
 REPORT_WIDTH = 16
 FLAG_PROFILE = 1
 FLAG_QEIF_DIRECT = 2
+FLAG_LM_TRUE_JACOBIAN = 4
 MAX_PATTERNS = 8
 PIXEL_NATIVE, PIXEL_I16, PIXEL_U16, PIXEL_F32 = 0, 1, 2, 3
 

@@ -38,13 +38,16 @@ namespace pnpb200 {
 // ------------------------------------------------------------------------------------------
 // internal kernel variant: QEIF with H^T H / H^T v from the moments (chosen for n >= 12 landmarks)
 #define PNP_METHOD_QEIF_HYBRID 100
+// internal kernel variant: LM exactly as the reference runs it (identity start, 14 iterations, constant lambda) but with the TRUE
+// gradients of the nine constraint rows (PNPB200_FLAG_LM_TRUE_JACOBIAN; not a parity mode)
+#define PNP_METHOD_LM_TRUEJAC 101
 
 // what a method's passes of the moment mapping compute
 __host__ __device__ constexpr bool method_with_w(int m) { return m != PNPB200_METHOD_LINEAR_F2; }                              // the (bx^2 + by^2)-weighted moments
 __host__ __device__ constexpr bool method_with_s(int m) { return m == PNP_METHOD_QEIF_HYBRID || m == PNPB200_METHOD_EIF2; }   // sum (bx^2 + by^2): the filters' residual
 __host__ __device__ constexpr int method_nmom(int m) { return method_with_s(m) ? PNP_NMOM : PNP_NMOM_LM; }                    // rows of the moment workspace in use
 __host__ __device__ constexpr bool method_lm_residual(int m) { return m != PNPB200_METHOD_LINEAR_F2; }                         // residual of the 12-number measurement model (else: F2's)
-__host__ __device__ constexpr bool method_has_core(int m) { return m == PNPB200_METHOD_LM || m == PNPB200_METHOD_LM_PLUS; }   // k_iterate parks the constant LM blocks in shared memory
+__host__ __device__ constexpr bool method_has_core(int m) { return m == PNPB200_METHOD_LM || m == PNPB200_METHOD_LM_PLUS || m == PNP_METHOD_LM_TRUEJAC; }   // k_iterate parks the constant LM blocks in shared memory
 
 template <typename T>
 struct SolveArgs {
@@ -668,6 +671,11 @@ __device__ __forceinline__ void iterate_core(T* sMomCol, int stride, const T* sC
         solve_lm_from_moments<T, MomentsRef<T> >(mom, sC, prm, xp, out);
 #pragma unroll
         for (int k = 0; k < 12; ++k) st[k] = xp[k];
+    } else if (METHOD == PNP_METHOD_LM_TRUEJAC) {
+        T xp[12];
+        solve_lm_from_moments<T, MomentsRef<T>, true>(mom, sC, prm, xp, out);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) st[k] = xp[k];
     } else if (METHOD == PNP_METHOD_QEIF_HYBRID) {
         Moments<T> mr;                                        // 6 x 6 system: the moments fit in registers next to it
 #pragma unroll
@@ -1038,6 +1046,7 @@ static int launch_solve(const SolveArgs<T>& a, int mapping, cudaStream_t stream)
     if (rc != PNPB200_OK) return rc;
     // (the filters' exit test from the moments needs FP64: in FP32 the moment-form residual is noise at res / |z| ~ 1e-3)
     constexpr bool has_moment_form = (METHOD == PNPB200_METHOD_LM || METHOD == PNPB200_METHOD_LINEAR_F2 || METHOD == PNPB200_METHOD_LM_PLUS ||
+                                      METHOD == PNP_METHOD_LM_TRUEJAC ||
                                       ((METHOD == PNP_METHOD_QEIF_HYBRID || METHOD == PNPB200_METHOD_EIF2) && sizeof(T) == 8));
     const RowGeom g = row_geometry<T>(a.n_total);
     const size_t pat_bytes = ((size_t)a.n_patterns * a.n * 3 + (size_t)a.n_patterns * PNP_PATC) * sizeof(T);
@@ -1111,7 +1120,12 @@ static int solve_typed(int method, long long B, int n_total, int n, const void* 
         return launch_solve<T, PNPB200_METHOD_QEIF>(a, prm.mapping, stream);
     case PNPB200_METHOD_LINEAR_F1: return launch_solve<T, PNPB200_METHOD_LINEAR_F1>(a, prm.mapping, stream);
 #elif PNP_GROUP == 1
-    case PNPB200_METHOD_LM:        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
+    case PNPB200_METHOD_LM:
+        if (prm.flags & PNPB200_FLAG_LM_TRUE_JACOBIAN) {     // non-parity extra: exists in the moment mapping only
+            if (prm.mapping != PNPB200_MAP_AUTO && prm.mapping != PNPB200_MAP_MOMENT) return PNPB200_EINVAL;
+            return launch_solve<T, PNP_METHOD_LM_TRUEJAC>(a, PNPB200_MAP_MOMENT, stream);
+        }
+        return launch_solve<T, PNPB200_METHOD_LM>(a, prm.mapping, stream);
     case PNPB200_METHOD_LM_PLUS: {
         // non-parity extra: exists in the moment mapping only, one pattern
         if (prm.mapping != PNPB200_MAP_AUTO && prm.mapping != PNPB200_MAP_MOMENT) return PNPB200_EINVAL;

@@ -837,7 +837,7 @@ PNP_DEV void solve_lm(const Pts& pts, const T* __restrict__ sP, const T* __restr
 
 // Moment form (moment mapping): every iteration is O(1) in the moments; x_prev receives the state
 // before the last update, at which the caller evaluates res_norm point by point.
-template <typename T, typename M>
+template <typename T, typename M, bool TRUE_JAC = false>
 PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const SolverPrm<T>& prm, T (&x_prev)[12],
                                    Result<T>& out)
 {
@@ -850,13 +850,13 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
 #pragma unroll
         for (int e = 0; e < 12; ++e) x_prev[e] = x[e];
         if (M::kHasCore) {
-            lm_step_core<T, M>(x, mom, sC, prm.lm_lambda, ip);
+            lm_step_core<T, M, TRUE_JAC>(x, mom, sC, prm.lm_lambda, ip);
         } else {
             GammaCol<T> gc;
             LmRhs<T> r;
             lm_gamma_column<T, M>(x, mom, sC, gc);
             lm_rhs_from_moments<T, M>(x, mom, sC, gc, r);
-            lm_step<T, M>(x, mom, sC, gc, r, prm.lm_lambda, ip);
+            lm_step<T, M, TRUE_JAC>(x, mom, sC, gc, r, prm.lm_lambda, ip);
         }
     }
     lm_reconstruct<T>(x, out);
