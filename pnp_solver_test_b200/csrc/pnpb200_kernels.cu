@@ -261,6 +261,8 @@ struct MomArgs {
     T* mom; T* tail; T* patc;
     T* R; T* t; T* euler; T* res;
     int32_t* iters; int32_t* best;
+    int fix_warp_max;       // filters: up to this many marked tiles the fix-up runs one problem per WARP (latency), above per thread
+    int32_t* fix_list;      // filters: [0] = number of 32-problem tiles with a marked problem, [1..] = those tiles (k_iterate appends)
     int use_tmap;
     alignas(64) CUtensorMap tmap;   // uv of this launch as a 2-D tensor (RowStream), valid when use_tmap
 };
@@ -655,6 +657,101 @@ __global__ void __launch_bounds__(kRingWarps * 32) k_stream_warp_tma(const __gri
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fix-up pass of the filters' moment mapping.  k_iterate takes the early-exit decisions of QEIF / EIF2 from the moment form of
+// the residual and certifies each of them against the rounding error of that form (exit_decision_uncertain); a problem with a
+// decision it cannot certify leaves k_iterate marked (iters = -1).  These kernels re-solve the marked problems with the direct
+// mappings' arithmetic -- residual point by point in every iteration, the reference's decisions exactly -- and overwrite their
+// pose, iteration count and the state the residual pass (or the fused report) evaluates res_norm at.  A tile / warp whose
+// problems are all unmarked reads 32 / 1 flags and leaves.
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void write_pose(const MomArgs<T>& a, long long b, const Result<T>& out);
+
+template <typename T, int METHOD, int LPP, typename Pts>
+PNP_DEV void run_filter_with_tail(const Pts& pts, const T* sP, const T* sC, int n, int sub, const SolverPrm<T>& prm, T (&xt)[12],
+                                  Result<T>& out)
+{
+    if (METHOD == PNP_METHOD_QEIF_HYBRID) solve_qeif_with_tail<T, LPP, Pts>(pts, sP, sC, n, sub, prm, xt, out);
+    else                                  solve_eif2_with_tail<T, LPP, Pts>(pts, sP, sC, n, sub, prm, xt, out);
+}
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(32) k_fixup_thread(const __grid_constant__ MomArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* sRows = reinterpret_cast<T*>(smem_raw);
+    T* sP = sRows + (size_t)kTileProblems * a.row_pitch;
+    T* sC = sP + (size_t)a.n * 3;
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sC + PNP_PATC);
+    const int lane = threadIdx.x;
+    const int32_t* sel = selection_of(a);
+    const int n_marked = a.fix_list[0];                       // (complete: k_iterate has finished)
+    if (n_marked <= a.fix_warp_max) return;                   // few marked tiles: k_fixup_warp takes them
+    bool staged = false;
+    RowTile<T> tile_buf;
+    for (int i = blockIdx.x; i < n_marked; i += gridDim.x) {
+        const long long tile = a.fix_list[1 + i];
+        const long long b = tile * kTileProblems + lane;
+        const bool marked = (b < a.B) && (a.iters[b] < 0);
+        if (!staged) {                                        // first marked tile of this CTA: pattern, constants, barrier
+            tile_buf.init(sRows, carve_bar<T>(smem_raw, sIdx + (sel ? a.n : 0)), a.uv, a.B, a.n_total, a.row_pitch, a.use_tma, a.kinv, lane);
+            load_pattern<T>(a.pattern, sel, a.n_total, a.n, 1, sP, sIdx, lane, 32);
+            pattern_constants<T>(sP, a.n, sC, lane);
+            __syncwarp();
+            staged = true;
+        } else {
+            tile_buf.release();
+        }
+        const int valid = tile_buf.issue(tile, lane);
+        PtsRow<T> pts;
+        pts.row = tile_buf.acquire(lane, valid);
+        pts.idx = sel ? sIdx : nullptr;
+        Result<T> out;
+        T xt[12];
+        run_filter_with_tail<T, METHOD, 1, PtsRow<T> >(pts, sP, sC, a.n, 0, a.prm, xt, out);
+        if (marked) {
+#pragma unroll
+            for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.ld + b] = xt[k];
+            write_pose<T>(a, b, out);
+        }
+    }
+}
+
+template <typename T, int METHOD>
+__global__ void __launch_bounds__(256) k_fixup_warp(const __grid_constant__ MomArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* sP = reinterpret_cast<T*>(smem_raw);
+    T* sC = sP + (size_t)a.n * 3;
+    int32_t* sIdx = reinterpret_cast<int32_t*>(sC + PNP_PATC);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int32_t* sel = selection_of(a);
+    const int n_marked = a.fix_list[0];                       // marked tiles (complete: k_iterate has finished)
+    if ((int)blockIdx.x >= n_marked || n_marked > a.fix_warp_max) return;   // CTA i takes the marked tiles i, i + gridDim.x, ...; many: k_fixup_thread
+    load_pattern<T>(a.pattern, sel, a.n_total, a.n, 1, sP, sIdx, threadIdx.x, blockDim.x);
+    if (warp == 0) pattern_constants<T>(sP, a.n, sC, lane);
+    __syncthreads();
+    PtsGlobal<T> pts;
+    pts.idx = sel ? sIdx : nullptr;
+    pts.k00 = (T)a.kinv[0]; pts.k01 = (T)a.kinv[1]; pts.k02 = (T)a.kinv[2];
+    pts.k10 = (T)a.kinv[3]; pts.k11 = (T)a.kinv[4]; pts.k12 = (T)a.kinv[5];
+    for (long long w = (long long)blockIdx.x * kTileProblems + warp; w < (long long)n_marked * kTileProblems;
+         w = ((w % kTileProblems) + nwarps < kTileProblems) ? w + nwarps : (w / kTileProblems + gridDim.x) * kTileProblems + warp) {
+        // warp-item w = problem (w % 32) of the marked tile (w / 32): a CTA takes whole tiles, its warps the problems of each
+        const long long b = (long long)a.fix_list[1 + (int)(w / kTileProblems)] * kTileProblems + (w % kTileProblems);
+        if (b >= a.B || a.iters[b] >= 0) continue;
+        pts.row = a.uv + (size_t)b * a.n_total * 2;
+        Result<T> out;
+        T xt[12];
+        run_filter_with_tail<T, METHOD, 32, PtsGlobal<T> >(pts, sP, sC, a.n, lane, a.prm, xt, out);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.ld + b] = xt[k];
+            write_pose<T>(a, b, out);
+        }
+    }
+}
+
 // The O(1)-per-iteration part of the moment mapping for one problem per thread: moments parked in shared
 // memory ([PNP_NMOM][stride] columns, this thread's column at sMomCol) -> pose `out` and the 12 numbers the
 // residual pass needs (LM: the state before the last update; F2: its tail).
@@ -753,6 +850,10 @@ __device__ __forceinline__ void iterate_body(const MomArgs<T>& a)
     Result<T> out;
     T st[PNP_NTAIL];
     iterate_core<T, METHOD>(sMom + threadIdx.x, kIterBlock, sC, a.prm, st, out);
+    if (method_with_s(METHOD) && BLOCK == 32 && a.fix_list) {    // a block is one 32-problem tile: list it if any of its problems is marked
+        const bool marked = ok && out.iters < 0;
+        if (__any_sync(0xffffffffu, marked) && threadIdx.x == 0) a.fix_list[1 + atomicAdd(a.fix_list, 1)] = (int32_t)blockIdx.x;
+    }
     if (!ok) return;
 #pragma unroll
     for (int k = 0; k < PNP_NTAIL; ++k) a.tail[(size_t)k * a.ld + b] = st[k];
@@ -898,6 +999,38 @@ static int launch_moment_pass(int pass, const MomArgs<T>& full, long long b0, lo
     return PNPB200_OK;
 }
 
+// A handful of marked tiles (the normal case on detected pixels) is latency: one problem per warp finishes them in a few
+// microseconds; thousands of them (noise-free pixels) is throughput: one problem per thread.  Both kernels read the count and
+// exactly one of them acts (rows too long for a tile: always per warp).
+template <typename T, int METHOD>
+static int launch_filter_fixup(const MomArgs<T>& m, const RowGeom& g, bool by_thread, size_t thread_smem, size_t warp_smem,
+                               const DeviceProps& dp, cudaStream_t stream)
+{
+    MomArgs<T> f = m;
+    const long long n_tiles = (m.B + kTileProblems - 1) / kTileProblems;
+    f.fix_warp_max = by_thread ? dp.sm_count : 0x7fffffff;
+    {
+        const size_t smem = warp_smem + PNP_PATC * sizeof(T);
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_fixup_warp<T, METHOD>, smem));
+        int per_sm = 1;
+        PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_fixup_warp<T, METHOD>, 256, smem));
+        const unsigned grid = (unsigned)persistent_grid(n_tiles, dp.sm_count, per_sm);   // CTAs beyond the number of marked tiles leave at once
+        k_fixup_warp<T, METHOD><<<grid, 256, smem, stream>>>(f);
+        count_kernel_launches(1);
+    }
+    if (by_thread) {
+        f.row_pitch = g.row_pitch; f.use_tma = g.use_tma;
+        const size_t smem = thread_smem + PNP_PATC * sizeof(T);
+        PNP_CUDA_OK(set_dynamic_smem((const void*)k_fixup_thread<T, METHOD>, smem));
+        int per_sm = 1;
+        PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_fixup_thread<T, METHOD>, 32, smem));
+        const unsigned grid = (unsigned)persistent_grid(n_tiles, dp.sm_count, per_sm);
+        k_fixup_thread<T, METHOD><<<grid, 32, smem, stream>>>(f);
+        count_kernel_launches(1);
+    }
+    return PNPB200_OK;
+}
+
 // LM / linear F2 with one pattern: moments -> iterate -> residual (see the kernels' header).
 // (Measured and rejected: (1) cutting the batch into slices that flow through the three passes on
 // different streams -- the kernels do overlap, but k_iterate fills the register file, so the
@@ -936,6 +1069,18 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     m.mom = ws; m.tail = ws + (size_t)PNP_NMOM * a.B; m.patc = m.tail + (size_t)PNP_NTAIL * a.B;
     m.R = a.R; m.t = a.t; m.euler = a.euler; m.res = a.res; m.iters = a.iters; m.best = a.best;
     m.use_tmap = 0;
+    struct ItersGuard { void* p; cudaStream_t st; ~ItersGuard() { if (p) cudaFreeAsync(p, st); } } iters_guard = { nullptr, stream }, list_guard = { nullptr, stream };
+    m.fix_list = nullptr; m.fix_warp_max = 0;
+    if (method_with_s(METHOD)) {
+        if (!m.iters) {                                       // the marks of the fix-up pass travel in the iteration counts
+            PNP_CUDA_OK(cudaMallocAsync((void**)&m.iters, sizeof(int32_t) * (size_t)a.B, stream));
+            iters_guard.p = m.iters;
+        }
+        const size_t n_tiles = ((size_t)a.B + kTileProblems - 1) / kTileProblems;
+        PNP_CUDA_OK(cudaMallocAsync((void**)&m.fix_list, sizeof(int32_t) * (n_tiles + 1), stream));
+        list_guard.p = m.fix_list;
+        PNP_CUDA_OK(cudaMemsetAsync(m.fix_list, 0, sizeof(int32_t), stream));
+    }
 
     // kernel shape of the two streaming passes
     const StreamGeom sg = stream_geometry<T>(a.n_total);
@@ -969,6 +1114,10 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
     launch_moment_pass<T, METHOD>(0, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
     g_prof.mark(slot, stream);
     launch_moment_pass<T, METHOD>(1, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    if (method_with_s(METHOD)) {                              // filters: re-solve what k_iterate could not certify (see k_fixup_*)
+        const int rc = launch_filter_fixup<T, METHOD>(m, g, by_thread, thread_smem, warp_smem, dp, stream);
+        if (rc != PNPB200_OK) return rc;
+    }
     g_prof.mark(slot, stream);
     if (a.res && !a.skip_residual) launch_moment_pass<T, METHOD>(2, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
     if (!a.skip_residual) g_prof.mark(slot, stream);      // (the fused report + residual pass is marked by its launcher)

@@ -209,10 +209,19 @@ PNP_DEV T dot3(const T (&a)[3], const T (&b)[3]) { return a[0] * b[0] + a[1] * b
 // where res ~ 1e-2 |z| -- far inside what the filters' early-exit test (|d res / res| < 1e-2, :2952, :2202) needs; rounding
 // noise where the residual itself is (noise-free pixels, res ~ 1e-14), exactly as the reference's own decision is there.
 // The reported res_norm never comes from here: it is evaluated point by point in the residual pass.
-// Below this fraction of sum (bx^2 + by^2) the moment-form res^2 is rounding noise (its error is ~30 eps sum |z|^2, the exit test
-// needs res^2 to ~2e-3 relative): the exit test is then not taken and the filter keeps iterating -- at its fixed point, so the
-// result does not move.  Reached only by noise-free pixels (res / |z| < 1e-5); detected pixels sit at res / |z| ~ 1e-3.
-#define kResMomFloor T(1e-10)
+// The moment-form res^2 carries an absolute error of about res2_error_bound() -- the moments are sums of n products (worst
+// case n eps / 2 relative each) combined with cancellation -- so an exit decision taken from it is CERTIFIED only when
+// | |ratio| - tol | exceeds the error that bound implies for the ratio; otherwise the lane stops and marks its problem
+// (iters = -1), and the fix-up pass of the moment mapping re-solves the marked problems point by point with the direct
+// kernel's arithmetic.  On detected pixels a few problems per million are marked; on noise-free pixels, where the
+// residual falls to rounding noise, most are -- the result is the direct mapping's either way.
+template <typename T>
+PNP_DEV T res2_error_bound(T n, T sw0, T gam, T d1, T d2, T tr_m0, T tr_mw, T u11_plus_u22, T u33)
+{
+    const T scale = sw0 + (gam * gam) * t_fma(tr_m0, u11_plus_u22, tr_mw * u33) + n * t_fma(d1, d1, d2 * d2);
+    const T eps = (sizeof(T) == 8) ? T(1.1102230246251565e-16) : T(5.9604645e-8);
+    return (T(2) * n + T(16)) * eps * scale;
+}
 
 template <typename T>
 PNP_DEV T res2_combine(T sw0, T sx0, T sy0, T n, T d1, T d2, T gam, T qa, T s1, T s2, T sgg)
@@ -221,6 +230,16 @@ PNP_DEV T res2_combine(T sw0, T sx0, T sy0, T n, T d1, T d2, T gam, T qa, T s1, 
     const T a1 = qa - t_fma(d1, s1, d2 * s2);
     const T r2 = t_fma(gam * gam, sgg, t_fma(T(-2) * gam, a1, a0));
     return r2 > T(0) ? r2 : T(0);
+}
+
+// is the decision |ratio| < tol safe against the error bounds e_new, e_old of the two squared residuals behind the ratio?
+template <typename T>
+PNP_DEV bool exit_decision_uncertain(T ratio_abs, T tol, T r2_new, T e_new, T r2_old, T e_old)
+{
+    if (!(r2_new > T(4) * e_new)) return true;                 // the residual itself is noise (or NaN)
+    const T dn = e_new * t_rcp<T>(r2_new);
+    const T dold = (e_old > T(0)) ? e_old * t_rcp<T>(r2_old) : T(0);
+    return !(t_abs(ratio_abs - tol) > (T(1) + ratio_abs) * (dn + dold));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -249,15 +268,17 @@ PNP_DEV void qekf_phi(const T (&x)[6], T (&p1)[3], T (&p2)[3], T (&p3)[3], T& ga
 // (res2_combine), no point is touched inside the loop; x_tail receives what the residual pass needs to evaluate the
 // reported res_norm point by point -- the measurement model at the state BEFORE the lane's last update, in the
 // 12-number form of LM's residual (phi_1, phi_2, phi_3, delta_1, delta_2, gamma = 1).
-template <typename T, int LPP, typename Pts, bool HYBRID, bool RES_MOM>
+template <typename T, int LPP, typename Pts, bool HYBRID, bool RES_MOM, bool WANT_TAIL = RES_MOM>
 PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
                        const SolverPrm<T>& prm, const Moments<T>& mom, T (&x_tail)[12], Result<T>& out)
 {
     T x[6] = { T(1), T(0), T(0), T(0), T(0), T(0) };      // :2831-2833
-    if (RES_MOM) {
+    if (WANT_TAIL) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) x_tail[e] = (e == 0 || e == 4 || e == 8 || e == 11) ? T(1) : T(0);
     }
+    bool flagged = false;                                 // RES_MOM: an exit decision could not be certified
+    T r2_old = T(0), e_old = T(0);
     // One 6 x 6 array carries Sigma from one iteration to the next and Omega inside it.  Lanes that have
     // left the loop (done) keep their x, res and iters; what their matrix becomes no longer matters.
     T Om[21];
@@ -287,8 +308,7 @@ PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
         const T Q1[12] = { r2, i2, -j2, -k2, -k2, j2, i2, -r2, j2, k2, r2, i2 };     // :3945
         const T Q2[12] = { k2, j2, i2, r2, r2, -i2, j2, -k2, -i2, -r2, k2, j2 };     // :3949
         const T Q3[12] = { -j2, k2, -r2, i2, i2, r2, k2, j2, r2, -i2, -j2, k2 };     // :3953
-        T qq[10], qd1[4], qd2[4], hv[6], res2 = T(0);
-        bool res_trusted = true;
+        T qq[10], qd1[4], qd2[4], hv[6], res2 = T(0), res2_err = T(0);
         if (!HYBRID) {
 #pragma unroll
             for (int e = 0; e < 10; ++e) qq[e] = T(0);
@@ -388,7 +408,8 @@ PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
                 const T qa = dot3<T>(mom.mx, p1) + dot3<T>(mom.my, p2) - dot3<T>(mom.mw, p3);
                 const T sgg = dot3<T>(p1, t1) - T(2) * dot3<T>(p1, t2) + dot3<T>(p2, t3v) - T(2) * dot3<T>(p2, t4) + dot3<T>(p3, t7);
                 res2 = res2_combine<T>(mom.sw0, mom.sx0, mom.sy0, nT, x[4], x[5], T(1), qa, s1, s2, sgg);
-                res_trusted = res2 > kResMomFloor * mom.sw0;
+                res2_err = res2_error_bound<T>(nT, mom.sw0, T(1), x[4], x[5], M0[0] + M0[3] + M0[5], mom.Mw[0] + mom.Mw[3] + mom.Mw[5],
+                                               dot3<T>(p1, p1) + dot3<T>(p2, p2), dot3<T>(p3, p3));
             }
         }
         // ---- update: Omega += H^T Q^-1 H, zeta += H^T Q^-1 (z - hx + H x) (:2896-2898)
@@ -409,7 +430,7 @@ PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
         T xn[6];
         sym_matvec<T, 6>(Om, zeta, xn);
         if (!done) {
-            if (RES_MOM) {
+            if (WANT_TAIL) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { x_tail[k] = p1[k]; x_tail[3 + k] = p2[k]; x_tail[6 + k] = p3[k]; }
                 x_tail[9] = x[4]; x_tail[10] = x[5]; x_tail[11] = T(1);
@@ -420,7 +441,11 @@ PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
             ++iters;
             const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference    // :2945
             res_old = res;
-            if (t_abs(ratio) < prm.exit_tol && res_trusted) done = true; // :2952
+            if (t_abs(ratio) < prm.exit_tol) done = true; // :2952
+            if (RES_MOM) {
+                if (exit_decision_uncertain<T>(t_abs(ratio), prm.exit_tol, res2, res2_err, r2_old, e_old)) { flagged = true; done = true; }
+                r2_old = res2; e_old = res2_err;
+            }
         }
     }
     // ---- QEKF_reconstruct_R_t_m1 :3590-3605
@@ -431,7 +456,7 @@ PNP_DEV void qeif_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
     const T t3 = T(1) / gamma;
     out.t[0] = x[4] * t3; out.t[1] = x[5] * t3; out.t[2] = t3;
     out.res = res;
-    out.iters = iters;
+    out.iters = flagged ? -1 : iters;
 }
 
 template <typename T, int LPP, typename Pts, bool HYBRID>
@@ -442,6 +467,15 @@ PNP_DEV void solve_qeif(const Pts& pts, const T* __restrict__ sP, const T* __res
     if (HYBRID) accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T unused[12];
     qeif_loop<T, LPP, Pts, HYBRID, false>(pts, sP, sC, n, sub, prm, mom, unused, out);
+}
+
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_qeif_with_tail(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                                  const SolverPrm<T>& prm, T (&x_tail)[12], Result<T>& out)
+{
+    Moments<T> mom;
+    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    qeif_loop<T, LPP, Pts, true, false, true>(pts, sP, sC, n, sub, prm, mom, x_tail, out);
 }
 
 // No points inside the loop (moment mapping)
@@ -876,16 +910,18 @@ PNP_DEV void solve_lm_from_moments(const M& mom, const T* __restrict__ sC, const
 // M: the moment container (registers in the direct mappings, shared-memory columns in k_iterate).  RES_MOM (moment
 // mapping): the residual of the early-exit test comes from the moments (res2_from_moments) and x_tail receives the state
 // before the lane's last update, at which the residual pass evaluates the reported res_norm point by point.
-template <typename T, int LPP, typename Pts, typename M, bool RES_MOM>
+template <typename T, int LPP, typename Pts, typename M, bool RES_MOM, bool WANT_TAIL = RES_MOM>
 PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
                        const SolverPrm<T>& prm, const M& mom, T (&x_tail)[12], Result<T>& out)
 {
     constexpr int U1 = 0, U2 = 3, U3 = 6, D1 = 9, D2 = 10, GG = 11;
     T x[12] = { T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(1) };   // :2058-2063
-    if (RES_MOM) {
+    if (WANT_TAIL) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) x_tail[e] = x[e];
     }
+    bool flagged = false;                                            // RES_MOM: an exit decision could not be certified
+    T r2_new = T(0), e_new = T(0), r2_old = T(0), e_old = T(0);
     // One 12 x 12 array carries Sigma from one iteration to the next and Omega inside it (see solve_qeif)
     T Om[78];
 #pragma unroll
@@ -900,7 +936,6 @@ PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
     const T sth = T(60.0 * (3.14159265358979323846 / 180.0));
     const T sth2 = sth * sth, st12 = T(0.05 * 0.05), st3 = T(4.0);   // :3686-3689
     T zeta[12], res_new = T(0);
-    bool res_trusted = true;
 #pragma unroll
     for (int e = 0; e < 12; ++e) zeta[e] = T(0);
 
@@ -949,7 +984,7 @@ PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
         }
         if (update_half) {
             if (!done) {
-                if (RES_MOM) {
+                if (WANT_TAIL) {
 #pragma unroll
                     for (int e = 0; e < 12; ++e) x_tail[e] = x[e];
                 }
@@ -959,7 +994,11 @@ PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
                 ++iters;
                 const T ratio = (res - res_old) * t_rcp<T>(res_old);   // 0 / 0 and x / 0 both end up not-below-tolerance, as in the reference               // :2196
                 res_old = res;
-                if (t_abs(ratio) < prm.exit_tol && res_trusted) done = true;        // :2202
+                if (t_abs(ratio) < prm.exit_tol) done = true;        // :2202
+                if (RES_MOM) {
+                    if (exit_decision_uncertain<T>(t_abs(ratio), prm.exit_tol, r2_new, e_new, r2_old, e_old)) { flagged = true; done = true; }
+                    r2_old = r2_new; e_old = e_new;
+                }
             }
             continue;
         }
@@ -1025,7 +1064,9 @@ PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
             zeta[GG] = t_fma(w, qa + gam * gc.sgg, zeta[GG]);
             if (RES_MOM) {                                           // :2176-2178 from the moments
                 res2 = res2_from_moments<T, M>(mom, sC, gc, qa, gam, d1, d2);
-                res_trusted = res2 > kResMomFloor * mom.gsw0();
+                r2_new = res2;
+                e_new = res2_error_bound<T>(sC[9], mom.gsw0(), gam, d1, d2, sC[0] + sC[3] + sC[5],
+                                            mom.gMw(0) + mom.gMw(3) + mom.gMw(5), u11 + u22, u33);
             }
         }
         // ---- update, the nine constraint rows (:3753-3772, Jacobians :3787-3823), collected per 3 x 3 block.  Row k adds
@@ -1067,7 +1108,7 @@ PNP_DEV void eif2_loop(const Pts& pts, const T* __restrict__ sP, const T* __rest
     }
     lm_reconstruct<T>(x, out);
     out.res = res;
-    out.iters = iters;
+    out.iters = flagged ? -1 : iters;
 }
 
 template <typename T, int LPP, typename Pts>
@@ -1078,6 +1119,16 @@ PNP_DEV void solve_eif2(const Pts& pts, const T* __restrict__ sP, const T* __res
     accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
     T unused[12];
     eif2_loop<T, LPP, Pts, Moments<T>, false>(pts, sP, sC, n, sub, prm, mom, unused, out);
+}
+
+// Direct arithmetic (point-wise residual) with the tail the residual pass needs: the fix-up of the moment mapping
+template <typename T, int LPP, typename Pts>
+PNP_DEV void solve_eif2_with_tail(const Pts& pts, const T* __restrict__ sP, const T* __restrict__ sC, int n, int sub,
+                                  const SolverPrm<T>& prm, T (&x_tail)[12], Result<T>& out)
+{
+    Moments<T> mom;
+    accumulate_moments<T, LPP, Pts>(pts, sP, n, sub, mom);
+    eif2_loop<T, LPP, Pts, Moments<T>, false, true>(pts, sP, sC, n, sub, prm, mom, x_tail, out);
 }
 
 template <typename T, typename M>
