@@ -7,12 +7,13 @@
 Workload (config.workload): BASELINE.json configs[1] -- 1,048,576 problems x 68-point face
 pattern, LM refinement, FP64, per GPU (weak scaling: rank r owns problems [r*B, (r+1)*B) of one
 global counter-based synthetic stream, so a sharded run is the slice of the unsharded one).
-A "step" is one pass of the hot path over the rank's batch: the solve (three kernels: packing, K^-1
-normalisation and moments; 14 LM iterations, SO(3) projection, Euler; point-wise residual), the
-error-report kernel, and the error statistics with their two all-reduces (NCCL over NVLink; the only
-inter-GPU traffic).
+A "step" is one pass of the hot path over the rank's batch: pnpb200_solve_report_batch (four kernels: pattern
+constants; packing, K^-1 normalisation and moments; 14 LM iterations, SO(3) projection, Euler; error report with the
+point-wise residual folded in), classification, and the error statistics with their two exchanges (NCCL over NVLink;
+the only inter-GPU traffic).  The K timed steps are replays of a CUDA graph of up to 20 captured steps.
 Inputs are resident in HBM for `value`; `e2e` runs the same solve through the host-buffer entry
-point (pinned host memory -> H2D -> solve -> D2H of all results) inside the timed region.
+point (pinned host memory -> H2D -> solve -> D2H of all results) inside the timed region; `e2e_i16` the same
+for a caller that holds its detections as int16; `extra_configs` (one GPU) times the other BASELINE configs.
 """
 import argparse
 import json
@@ -373,9 +374,20 @@ def extra_configs(dev, sampler_index=0, min_ms=200.0):
     fp["noise_sweep"] = sweep
     res["configs2_fp32_vs_fp64"] = fp
 
-    # ---- the execution shapes head to head on the headline workload (north_star: one problem per warp; default: moments)
+    # ---- the filters on all 68 landmarks (moment mapping, certified exit decisions) beside LM
     w68 = wl.synth_batch(0, B1, P68, K, device=dev)
     p68 = torch.from_numpy(P68).to(dev)[None].contiguous()
+    filt = {}
+    for method in ("qeif", "eif2", "lm"):
+        def filt_step():
+            return wl.solve_report_batch(method, w68["uv"], p68, K, w68["gt"], params=prof)
+        ms, so, kms, ck = timed(filt_step, profile=True)
+        filt[method] = {"solve_report_ms": ms, "solves_per_s_incl_report": B1 / ms * 1e3, "kernel_ms_moments_iterate_report": kms,
+                        "mean_iters": float(so["iters"].double().mean()),
+                        "pass_rate_10cm_10deg": float(so["flags"].all(dim=1).double().mean()), "clocks": ck}
+    res["filters_68_1Mi"] = filt
+
+    # ---- the execution shapes head to head on the headline workload (north_star: one problem per warp; default: moments)
     shapes = {}
     for name, mp in (("MAP_MOMENT (default: moments -> O(1) iterations -> point-wise residual, one problem per thread)", _lib.MAP_MOMENT),
                      ("MAP_THREAD (one problem per thread, every iteration point-wise)", _lib.MAP_THREAD),
