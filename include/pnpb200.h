@@ -47,9 +47,11 @@ extern "C" {
 /* execution shape (0 = let the library choose from n) */
 #define PNPB200_MAP_AUTO    0
 #define PNPB200_MAP_THREAD  1   /* one problem per thread, correspondences staged in shared memory */
-#define PNPB200_MAP_MOMENT  2   /* LM / linear F2: moments -> O(1) iterations -> point-wise        */
-                                /* residual, as three streaming kernels (default there); several   */
-                                /* patterns: one such solve per pattern, arg-min in between        */
+#define PNPB200_MAP_MOMENT  2   /* moments -> O(1) iterations -> point-wise residual, as three      */
+                                /* streaming kernels: LM, LM+, linear F2 and, in FP64, EIF2 and     */
+                                /* QEIF from 12 landmarks on (their exit decisions certified, the   */
+                                /* rest re-solved point-wise by a fix-up pass).  The default there; */
+                                /* several patterns: one such solve per pattern, arg-min in between */
 #define PNPB200_MAP_WARP    32  /* one problem per warp, shuffle-reduced normal equations          */
 
 #define PNPB200_OK          0
@@ -59,7 +61,8 @@ extern "C" {
 #define PNPB200_ETOOLARGE  -4   /* n exceeds what the selected mapping can hold                    */
 
 #define PNPB200_FLAG_PROFILE 1  /* record CUDA events around each kernel of the call (pnpb200_profile_read) */
-#define PNPB200_FLAG_QEIF_DIRECT 2 /* QEIF: accumulate H^T H point by point even for n >= 12 (default there: from the moments) */
+#define PNPB200_FLAG_QEIF_DIRECT 2 /* QEIF in the direct mappings: accumulate H^T H point by point even for n >= 12 (default there: from
+                                      the moments); with PNPB200_MAP_AUTO it also keeps QEIF out of the moment mapping */
 #define PNPB200_FLAG_LM_TRUE_JACOBIAN 4 /* method LM only, NOT a parity mode: the reference's loop (identity start, max_it iterations,
                                            constant lambda) with the true gradients of its nine constraint rows (2u for the quadratic rows,
                                            u/|u| for the norm rows) in place of the halved ones it uses (PNP_SOLVER_LIB.py:3787-3823);
@@ -108,7 +111,8 @@ const char* pnpb200_last_error(void);          /* text of the last CUDA error se
 int pnpb200_default_params(pnpb200_params* p);
 int pnpb200_default_synth(pnpb200_synth* s);
 int pnpb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
-/* scratch bytes pnpb200_solve_batch needs for this call shape (0 for the direct mappings) */
+/* scratch bytes pnpb200_solve_batch needs for this call shape (0 for the direct mappings; QEIF: sized for the
+   moment mapping, which it uses from 12 landmarks on) */
 int64_t pnpb200_workspace_bytes(int method, int dtype, int64_t B, int n_patterns, int mapping);
 
 /*
