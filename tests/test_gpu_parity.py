@@ -598,7 +598,7 @@ def test_image_points_with_homogeneous_coordinate_not_one():
     assert np.array_equal(a["R"], b_["R"])
 
 
-@pytest.mark.parametrize("method", ["lm", "linear_f2", "lm_plus"])
+@pytest.mark.parametrize("method", ["lm", "linear_f2", "lm_plus", "qeif", "eif2"])
 def test_moment_mapping_over_several_patterns(method):
     """solve_pnp's loop over the stored patterns with the strict-< arg-min (PNP_SOLVER_LIB.py:166-199) in the moment mapping:
     one moment solve per pattern and a merge in between, equal to the direct mappings' fused loop and to the oracle."""
@@ -606,15 +606,20 @@ def test_moment_mapping_over_several_patterns(method):
                      1.07 * pt.pattern_array(pt.get_golden_pattern("Alexander"))])
     K = pt.default_camera_matrix()
     w = orc.synth(0, 2000, pats[1], K, orc.default_synth(seed=71))
+    w["uv"][1000:] = orc.synth(1000, 1000, pats[0], K, orc.default_synth(seed=71))["uv"]   # half the batch shows the other face
     ref = orc.solve_batch(method, w["uv"], pats, K)
     out = cuda_solve(method, w["uv"], pats, K, mapping=MAP_MOMENT)
     auto = cuda_solve(method, w["uv"], pats, K)                       # default mapping = moments, also with several patterns
     for k in out:
         assert np.array_equal(out[k], auto[k], equal_nan=True), k
+    # the minimum must not be a near-tie (a 7 % scaled copy of the face that generated the pixels fits them equally well)
+    rs = np.stack([orc.solve_batch(method, w["uv"], pats[p], K)["res_norm"] for p in range(3)], axis=1)
+    srt = np.sort(rs, axis=1)
+    clear = (srt[:, 1] - srt[:, 0]) > 1e-9 * srt[:, 0]
     if method == "lm_plus":
         ok = (ref["iters"] < 14) & (out["iters"] < 14) & (ref["best_pattern"] == out["best_pattern"])
-        assert ok.mean() > 0.9
-        assert np.quantile(np.abs(out["R"] - ref["R"]).reshape(2000, -1).max(axis=1)[ok], 0.995) < 1e-8
+        assert clear.mean() > 0.4 and ok[clear].mean() > 0.9
+        assert np.quantile(np.abs(out["R"] - ref["R"]).reshape(2000, -1).max(axis=1)[ok & clear], 0.995) < 1e-8
         return
     # well-posed problems: every pattern's own solve is stable (tag per pattern with the oracle)
     stable = np.ones(2000, bool)
@@ -622,12 +627,8 @@ def test_moment_mapping_over_several_patterns(method):
         for p in range(3):
             _, st, _ = oracle_stability(method, w["uv"], pats[p], K)
             stable &= st
-    clear = np.ones(2000, bool)                                          # and the minimum is not a near-tie
-    rs = np.stack([orc.solve_batch(method, w["uv"], pats[p], K)["res_norm"] for p in range(3)], axis=1)
-    srt = np.sort(rs, axis=1)
-    clear &= (srt[:, 1] - srt[:, 0]) > 1e-9 * srt[:, 0]
     m = stable & clear
-    assert m.mean() > 0.5 and (out["best_pattern"][m] == ref["best_pattern"][m]).all()
+    assert m.mean() > 0.3 and (out["best_pattern"][m] == ref["best_pattern"][m]).all()
     assert len(set(out["best_pattern"][m].tolist())) >= 2
     compare_solutions(out, ref, mask=m)
     direct = cuda_solve(method, w["uv"], pats, K, mapping=MAP_THREAD)
