@@ -294,6 +294,7 @@ class PNP_SOLVER(object):
         self.params = None          # optional _lib.Params override
         self.LM_key_list = list(LM_KEY_LIST_6)   # PNP_SOLVER_LIB.py:156
         self.last_iters = None
+        self._last_best = 0
         self._dev_cache = {}
 
     # ---------------------------------------------------------------- pattern store (:66-135)
@@ -352,6 +353,8 @@ class PNP_SOLVER(object):
             v = np.asarray(np_point_image_dict[k], dtype=np.float64).reshape(-1)
             pts[0, i, 0], pts[0, i, 1] = v[0], v[1]
             pts[0, i, 2] = v[2] if v.shape[0] >= 3 else 1.0
+        if (pts[..., 2] == 1.0).all():                           # the ordinary case, decided on the host: no extra device round trip
+            return torch.from_numpy(np.ascontiguousarray(pts[..., :2])).to(device=self.device, dtype=self._tdtype()), self.np_K_camera_est
         return self._uv_and_K(torch.from_numpy(pts).to(device=self.device, dtype=self._tdtype()))
 
     def _uv_and_K(self, pts):
@@ -370,12 +373,16 @@ class PNP_SOLVER(object):
         return out, np.eye(3)
 
     def _finish_single(self, out):
-        """device outputs of a B=1 solve -> the reference's 7-tuple, plus its side effects."""
-        R = out["R"][0].double().cpu().numpy()
-        t = out["t"][0].double().cpu().numpy().reshape(3, 1)
-        e = out["euler"][0].double().cpu().numpy()
-        res = float(out["res_norm"][0].item())
-        self.last_iters = int(out["iters"][0].item())
+        """device outputs of a B=1 solve -> the reference's 7-tuple, plus its side effects.  One device-to-host
+        copy for everything (the scripts call this once per sample)."""
+        flat = torch.cat([out["R"].reshape(-1).double(), out["t"].reshape(-1).double(), out["euler"].reshape(-1).double(),
+                          out["res_norm"].reshape(-1).double(), out["iters"].double(), out["best_pattern"].double()]).cpu().numpy()
+        R = flat[0:9].reshape(3, 3).copy()
+        t = flat[9:12].reshape(3, 1).copy()
+        e = flat[12:15]
+        res = float(flat[15])
+        self.last_iters = int(flat[16])
+        self._last_best = int(flat[17])
         self.np_R_c_a_est = copy.deepcopy(R)          # :2986-2987
         self.np_t_c_a_est = copy.deepcopy(t)
         return (R, t, float(t[2, 0]), float(e[0]), float(e[1]), float(e[2]), res)
@@ -395,8 +402,9 @@ class PNP_SOLVER(object):
         uv, K = self._pack_image_points(np_point_image_dict, keys)
         pat = self._pack_patterns(self.np_point_3d_pretransfer_dict_list, keys)
         out = solve_batch(self.method, uv, pat, K, params=self.params)
-        self.set_golden_pattern_id(int(out["best_pattern"][0].item()))     # :199
-        return self._finish_single(out)
+        ret = self._finish_single(out)
+        self.set_golden_pattern_id(self._last_best)                        # :199
+        return ret
 
     def solve_pnp_QEIF_single_pattern(self, np_point_image_dict, np_point_3d_pretransfer_dict, LM_key_list=None):
         """PNP_SOLVER_LIB.py:2771-3025"""
