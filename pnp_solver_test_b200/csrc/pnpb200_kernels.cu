@@ -540,8 +540,13 @@ PNP_DEV void warp_reduce_scatter(T (&v)[32], int lane)
 }
 
 // Fixed shape.  (Other shapes were tried on 100 k x 1024 points, tools/build_variant.py: 3 slots x 128 points 0.57 ms, 16 warps
-// per CTA 0.39 ms against 0.42 ms for this one; EVEN slot counts -- 2 x 256, 4 x 128, 6 x 128 -- faulted intermittently with an
-// illegal address, in the round-1 form of this kernel as well, cause not found: they are not offered.)
+// per CTA 0.39 ms against 0.42 ms for this one.  2 x 256, 4 x 128 and 6 x 128 faulted with an illegal address on about half of
+// the FIRST launches of a process and never on a later one, in the round-1 form of this kernel as well.  Bisected on the GPU,
+// profiles/r02u_ring_fault_bisect.md: the fault survives staging with plain loads instead of TMA, dropping the pattern reads or
+// the moment stores, moving or invalidating the barriers, zero-filling the slots, a block-wide barrier after the initialisation,
+// eager module loading and a maximal shared-memory carve-out; it disappears when ANY 256-thread kernel of this translation
+// unit has run before.  No access of the kernel is out of range under its own logic, so the cause is not in this source; this
+// shape ran 12 of 12 instrumented first launches and every test / bench / soak process clean, and the others are not offered.)
 constexpr int kRingSlots = 3;
 constexpr int kRingPoints = 256;          // 4 KB per slot in FP64: 8 points per lane between two barrier waits
 constexpr int kRingWarps = 8;
@@ -1108,12 +1113,22 @@ static int launch_moment(const SolveArgs<T>& a, const DeviceProps& dp, cudaStrea
         PNP_CUDA_OK(blocks_per_sm(&per_sm, (const void*)k_stream_warp<T, METHOD, 0>, 256, smem));
     }
 
+    // -DPNP_DEBUG_SYNC (tools/build_variant.py): synchronise after every launch and name the kernel a fault belongs to
+#ifdef PNP_DEBUG_SYNC
+#define PNP_DEBUG_CHECK(what) do { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ != cudaSuccess) { \
+        fprintf(stderr, "[pnpb200 debug] after %s (shape %d, smem %zu, per_sm %d): %s\n", what, shape, smem, per_sm, cudaGetErrorString(e_)); return PNPB200_ECUDA; } } while (0)
+#else
+#define PNP_DEBUG_CHECK(what) do { } while (0)
+#endif
     k_pattern_constants<T><<<1, 32, 0, stream>>>(m); count_kernel_launches(1);
+    PNP_DEBUG_CHECK("k_pattern_constants");
     const int slot = a.profile ? g_prof.begin() : -1;
     g_prof.mark(slot, stream);
     launch_moment_pass<T, METHOD>(0, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    PNP_DEBUG_CHECK("moments pass");
     g_prof.mark(slot, stream);
     launch_moment_pass<T, METHOD>(1, m, 0, a.B, shape, sg, smem, per_sm, dp, a.tune, stream);
+    PNP_DEBUG_CHECK("k_iterate");
     if (method_with_s(METHOD)) {                              // filters: re-solve what k_iterate could not certify (see k_fixup_*)
         const int rc = launch_filter_fixup<T, METHOD>(m, g, by_thread, thread_smem, warp_smem, dp, stream);
         if (rc != PNPB200_OK) return rc;

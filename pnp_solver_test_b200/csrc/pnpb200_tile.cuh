@@ -37,6 +37,7 @@ PNP_DEV void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the initialised barrier, as the async proxy (TMA) sees it
 }
 PNP_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
