@@ -321,6 +321,7 @@ struct PipeSlot {
     void* d_narrow = nullptr;                             // device copy of a chunk of int16 / uint16 / float32 pixels (solve_batch_host_px)
     cudaEvent_t pack_free = nullptr;                      // the H2D copy out of h_pack has finished
     cudaEvent_t h2d_done = nullptr;                       // the slot's last pixel copy has finished (back-pressure)
+    cudaEvent_t piece_done[2] = { nullptr, nullptr };     // parts of a plain chunk's pixel copy, two in flight (submit_chunk)
 };
 
 struct pnpb200_pipeline {
@@ -335,6 +336,10 @@ struct pnpb200_pipeline {
 };
 
 constexpr int kPackSlots = 4;
+#ifndef PNP_PLAIN_PIECES
+#define PNP_PLAIN_PIECES 8
+#endif
+constexpr int kPlainPieces = PNP_PLAIN_PIECES;   // parts of a plain chunk's pixel copy beside the packing thread (submit_chunk)
 
 static int alloc_slot(pnpb200_pipeline* p, PipeSlot& sl, bool pack)
 {
@@ -349,6 +354,7 @@ static int alloc_slot(pnpb200_pipeline* p, PipeSlot& sl, bool pack)
     PNP_CUDA_OK(cudaMalloc((void**)&sl.d_best, sizeof(int32_t) * c));
     PNP_CUDA_OK(cudaMalloc(&sl.d_ws, p->ws_bytes));
     PNP_CUDA_OK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+    for (cudaEvent_t& e : sl.piece_done) PNP_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (pack) {
         const size_t pb = sizeof(int16_t) * (c * p->n_total * 2 + 8);
         PNP_CUDA_OK(cudaMallocHost((void**)&sl.h_pack, pb));
@@ -366,6 +372,7 @@ static void free_slot(PipeSlot& sl)
     if (sl.h_pack) cudaFreeHost(sl.h_pack);
     if (sl.pack_free) cudaEventDestroy(sl.pack_free);
     if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+    for (cudaEvent_t e : sl.piece_done) if (e) cudaEventDestroy(e);
     sl = PipeSlot();
 }
 
@@ -453,8 +460,11 @@ struct HostCall {
     int32_t *iters, *best_pattern;
 };
 
-// queue one chunk on a slot: pixels host -> device (packed if `packed`), solve, results device -> host
-int submit_chunk(const HostCall& c, PipeSlot& sl, int64_t done, int64_t nb, bool packed)
+// queue one chunk on a slot: pixels host -> device (packed if `packed`), solve, results device -> host.
+// pieces > 1 (plain FP64 / FP32 pixels beside a packing thread): the pixel copy goes out in that many parts and each
+// part only when the one before has left the host, so that this thread never holds more than one part's worth of the
+// host-to-device engine ahead of a packed chunk.
+int submit_chunk(const HostCall& c, PipeSlot& sl, int64_t done, int64_t nb, bool packed, int pieces = 1)
 {
     pnpb200_pipeline* p = c.p;
     const size_t esz = p->esz;
@@ -475,7 +485,15 @@ int submit_chunk(const HostCall& c, PipeSlot& sl, int64_t done, int64_t nb, bool
         if (rc != PNPB200_OK) return rc;
     } else {
         const char* src = (const char*)c.uv_host + esz * (size_t)done * p->n_total * 2;
-        PNP_CUDA_OK(cudaMemcpyAsync(sl.d_uv, src, esz * values, cudaMemcpyHostToDevice, st));
+        const int64_t per = (nb + pieces - 1) / pieces;
+        int k = 0;
+        for (int64_t b0 = 0; b0 < nb; b0 += per, ++k) {
+            const int64_t pn = (nb - b0 < per) ? (nb - b0) : per;
+            const size_t off = esz * (size_t)b0 * p->n_total * 2;
+            if (k >= 2) PNP_CUDA_OK(cudaEventSynchronize(sl.piece_done[k & 1]));      // part k - 2 has left the host
+            PNP_CUDA_OK(cudaMemcpyAsync((char*)sl.d_uv + off, src + off, esz * (size_t)pn * p->n_total * 2, cudaMemcpyHostToDevice, st));
+            if (pieces > 1) PNP_CUDA_OK(cudaEventRecord(sl.piece_done[k & 1], st));
+        }
         PNP_CUDA_OK(cudaEventRecord(sl.h2d_done, st));
     }
     pnpb200_params prm;
@@ -580,7 +598,7 @@ int pnpb200_solve_batch_host_px(pnpb200_pipeline* p, int method, int64_t B, int 
         const int64_t c = claim(false);
         if (c < 0) break;
         const int64_t done = c * p->chunk, nb = (B - done < p->chunk) ? (B - done) : p->chunk;
-        rc_main = submit_chunk(call, p->slots[(size_t)s], done, nb, false);
+        rc_main = submit_chunk(call, p->slots[(size_t)s], done, nb, false, packing ? kPlainPieces : 1);
         if (rc_main != PNPB200_OK) break;
         s = (s + 1) % p->n_streams;
         // a slot's buffers are reused n_streams chunks later; stream order protects them

@@ -191,6 +191,57 @@ def test_pixel_packing_is_exact_or_refused():
     assert _lib.lib.pnpb200_pack_i16(C.c_int(7), None, C.c_int64(4), None, C.c_int(1)) < 0
 
 
+def test_pack_workers_are_reused_across_calls_and_survive_a_fork():
+    """The packing threads outlive a call (pnpb200_pack.cpp, PackPool): many calls with changing thread counts and sizes give
+    the same bytes as one thread, concurrent callers are serialised, and a forked child -- which inherits the pool object
+    but none of its threads -- packs with a pool of its own instead of waiting for workers that do not exist."""
+    import ctypes as C
+    import os
+    import threading
+    from pnp_solver_test_b200 import _lib
+    rng = np.random.default_rng(10)
+    a = rng.integers(-3000, 3000, 700001).astype(np.float64)
+    want = a.astype(np.int16)
+
+    def pack(src, threads):
+        dst = np.zeros(src.shape, np.int16)
+        rc = _lib.lib.pnpb200_pack_i16(C.c_int(0), src.ctypes.data_as(C.c_void_p), C.c_int64(src.size),
+                                       dst.ctypes.data_as(C.POINTER(C.c_int16)), C.c_int(threads))
+        return rc, dst
+
+    for rep in range(40):
+        th = (1, 7, 2, 16, 3)[rep % 5]
+        n = (700001, 65536, 32769, 5)[rep % 4]
+        rc, dst = pack(a[:n], th)
+        assert rc == 1 and np.array_equal(dst, want[:n]), (rep, th, n)
+    results = []
+    callers = [threading.Thread(target=lambda: results.append(pack(a, 5))) for _ in range(4)]
+    for t in callers:
+        t.start()
+    for t in callers:
+        t.join()
+    assert len(results) == 4 and all(rc == 1 and np.array_equal(dst, want) for rc, dst in results)
+    pid = os.fork()
+    if pid == 0:                                            # child: exit code = verdict, no pytest machinery
+        ok = False
+        try:
+            rc, dst = pack(a, 6)
+            ok = rc == 1 and np.array_equal(dst, want)
+        finally:
+            os._exit(0 if ok else 1)
+    for _ in range(600):                                    # a child waiting for threads it does not have would hang: bounded wait
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        import time
+        time.sleep(0.05)
+    else:
+        os.kill(pid, 9)
+        os.waitpid(pid, 0)
+        pytest.fail("the forked child hung in pnpb200_pack_i16")
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
 def test_approval_masks():
     """approval_mask = TEST_TOOLBOX.approval_func_small_angle / _large_angle (:959-970), thresholds inclusive."""
     from pnp_solver_test_b200 import workload as wl
