@@ -179,8 +179,18 @@ def cpu_rate(sample, n_threads=0, method=METHOD, n=N_POINTS, seed=42):
     P = pt.pattern_array(pt.synthetic_pattern(n))
     K = pt.default_camera_matrix()
     w = orc.synth(0, sample, P, K, orc.default_synth(seed=seed))
+    from pnp_solver_test_b200 import workload as wl
+    edges = np.asarray(wl.CLASS_BINS["depth"], np.float64)
     t0 = time.perf_counter()
-    orc.solve_batch(method, w["uv"], P, K, n_threads=n_threads)
+    # the same step as the GPU arm: solve, error report, statistics of the four quantities for 'all' and per depth class
+    o = orc.solve_batch(method, w["uv"], P, K, n_threads=n_threads)
+    rep = orc.report_batch(P, w["uv"], K, o["R"], o["t"], o["euler"], w["gt"], n_threads=n_threads)["report"]
+    cls = np.digitize(w["gt"][:, 0] * 100.0, edges)
+    pairs = ((rep[:, 10], rep[:, 11]), (rep[:, 12], w["gt"][:, 1]), (rep[:, 13], w["gt"][:, 2]), (rep[:, 14], w["gt"][:, 3]))
+    for est, ref in pairs:
+        orc.stats_of(est, ref)
+        for c in np.unique(cls):
+            orc.stats_of(est[cls == c], ref[cls == c])
     dt = time.perf_counter() - t0
     return sample / dt, dt
 
@@ -192,7 +202,7 @@ def cpu_baseline_block(target_seconds=12.0):
     sample = int(max(256, min(B_PER_GPU, r0 * target_seconds)))
     rate, dt = cpu_rate(sample)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of the %d problems of the workload (first %d of the seeded stream), %.1f s on %d threads; "
+            "sample": "%d of the %d problems of the workload (first %d of the seeded stream), solve + report + statistics, %.1f s on %d threads; "
                       "oracle/pnp_oracle.c = C port of the reference's NumPy algorithm incl. SVD-based pinv"
                       % (sample, B_PER_GPU, sample, dt, cores)}
 
@@ -221,11 +231,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "68-point LM PnP solves, FP64, random_stress_test pose distribution, quantised pixels",
+        "config": {"workload": "BASELINE configs[1]: %d-point face pattern, LM refinement (14 it), FP64, random_stress_test pose "
+                               "distribution, integer-quantised pixels; a step = solve + error report + statistics of a bounded sample "
+                               "(%d problems) of the 1048576-problem batch" % (N_POINTS, sample),
                    "method": METHOD, "n_points": N_POINTS, "problems_per_step": sample},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d problems per step x %d steps on %d host threads (oracle/pnp_oracle.c; the reference "
-                                   "is pure Python and is not on this box)" % (sample, args.steps, cores)},
+                         "sample": "%d problems per step x %d steps on %d host threads, solve + report + statistics (oracle/pnp_oracle.c; "
+                                   "the reference is pure Python and is not on this box)" % (sample, args.steps, cores)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
