@@ -38,4 +38,5 @@ def oracle_stability(method, uv, pattern, K, ref=None):
                        np.abs(o["t"] - ref["t"]).max(axis=1) / np.abs(ref["t"][:, 2]))
         worst = np.maximum(worst, d)
         it_stable &= (o["iters"] == ref["iters"])
+    oracle_stability.last_worst = worst                     # the sensitivities themselves, for tools that want more than the tag
     return ref, worst < 1e-10, it_stable

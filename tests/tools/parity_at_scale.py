@@ -24,6 +24,14 @@ for n in (15, 68):
             dR = np.abs(out["R"] - ref["R"]).reshape(B, -1).max(axis=1)
             dt = np.abs(out["t"] - ref["t"]).max(axis=1) / np.abs(ref["t"][:, 2])
             ok_it = it_stable & (np.abs(ref["res_norm"]) > 1e-10)
+            if method == "lm":
+                # how the deviation relates to the reference-side sensitivity the `stable` tag is cut from (threshold 1e-10)
+                sens, dev = oracle_stability.last_worst, np.maximum(dR, dt)
+                over = stable & (dev > 1e-9)
+                print("      lm: %d of %d stable problems above 1e-9 (their own sensitivity to the 1e-13 perturbation: %s); max deviation where "
+                      "the sensitivity is below 1e-11: %.2e (%d problems)"
+                      % (over.sum(), stable.sum(), ", ".join("%.1e" % v for v in np.sort(sens[over])[::-1][:5]) or "-",
+                         dev[sens < 1e-11].max(), (sens < 1e-11).sum()), flush=True)
             print("n=%-3d %-9s %-9s stable %.3f | max dR %.2e  max dt/t3 %.2e | iters equal %d / %d"
                   % (n, "quantised" if quant else "exact", method, stable.mean(), dR[stable].max(), dt[stable].max(),
                      (out["iters"][ok_it] == ref["iters"][ok_it]).sum(), ok_it.sum()), flush=True)
