@@ -37,7 +37,7 @@ bool pack_scalar(const T* s, int64_t n, int16_t* d)
 
 // One core streams ~9 GB/s with demand loads alone (its fill buffers); prefetching 4 KB ahead lifts that to ~15 GB/s and
 // non-temporal stores spare the read-for-ownership of the destination: 81 -> 111 GB/s of FP64 read on 15 threads
-// (tools/pack_probe.py on the GPU box's 16-core Xeon).
+// (tools/pack_speed.py on the GPU box's 16-core Xeon).
 constexpr int kPackPrefetchBytes = 4096;
 __attribute__((target("avx2"))) bool pack_f64_avx2(const double* s, int64_t n, int16_t* d)
 {
