@@ -705,7 +705,10 @@ __global__ void __launch_bounds__(kStatBlock) k_stats(long long B, StatIn in, co
 // fit per SM (one block per SM): the first version had 4 warps per SM doing all four quantities and
 // sat on exposed load / shared-memory latency (issue slots 18 % busy, 82 us for 36 MB).
 constexpr int kStatLaneMaxWarps = 16;
-constexpr int kStatUnroll = 8;
+#ifndef PNP_STAT_UNROLL
+#define PNP_STAT_UNROLL 8
+#endif
+constexpr int kStatUnroll = PNP_STAT_UNROLL;
 
 template <int PASS>
 __global__ void __launch_bounds__(kStatLaneMaxWarps * 32) k_stats_lane(long long B, StatIn in, const int32_t* __restrict__ cls, int n_class,
@@ -779,9 +782,17 @@ __global__ void __launch_bounds__(kStatLaneMaxWarps * 32) k_stats_lane(long long
 #pragma unroll
         for (int u = 0; u < kStatUnroll; ++u) account(has_cls ? c[u] : 0, ev[u], gv[u]);
     }
-    for (; b0 < B; b0 += stride) {                        // the ragged end: fewer than kStatUnroll elements left for this lane
-        account(has_cls ? *pc : 0, *pe, *pg);
-        pc += sc; pe += se; pg += sg;
+    if (b0 < B) {                                         // the ragged end as ONE more batch: its loads are in flight together too
+        int c[kStatUnroll];
+        double ev[kStatUnroll], gv[kStatUnroll];
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) {
+            c[u] = -2; ev[u] = 0.0; gv[u] = 1.0;          // -2: no problem there
+            if (b0 + u * stride < B) { c[u] = has_cls ? *pc : 0; ev[u] = *pe; gv[u] = *pg; }
+            pc += sc; pe += se; pg += sg;
+        }
+#pragma unroll
+        for (int u = 0; u < kStatUnroll; ++u) account(c[u], ev[u], gv[u]);
     }
     __syncthreads();
     // classes: entry e = (quantity, class, value): add the warps that worked on that quantity per lane, then across lanes
