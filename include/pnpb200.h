@@ -177,8 +177,9 @@ int pnpb200_pipeline_destroy(pnpb200_pipeline* p);
  * of the batch, converts each to int16 with n_threads workers (pnpb200_pack_i16) and, if that was exact
  * for every value of the chunk, ships the int16 copy (a quarter of the PCIe bytes) and widens it on the
  * device -- the solver sees the same values; chunks that are not whole numbers travel as they are.
- * The calling thread keeps sending chunks unchanged from the near end, so PCIe and the CPU work at the
- * same time and share the batch by their speeds.  n_threads = 0 switches it off (the default).
+ * The calling thread keeps sending chunks unchanged from the near end (in eighths, two in flight, so that a
+ * packed copy never queues behind a whole plain chunk), so PCIe and the CPU work at the same time and share
+ * the batch by their speeds.  n_threads = 0 switches it off (the default).
  * pnpb200_pipeline_last_packed: how many chunks of the last call travelled packed, of how many.
  */
 int pnpb200_pipeline_set_packing(pnpb200_pipeline* p, int n_threads);
@@ -186,7 +187,8 @@ int pnpb200_pipeline_last_packed(const pnpb200_pipeline* p, int64_t* packed_chun
 
 /*
  * Host helper of the packed transfer: dst[i] = (int16) src[i] for n_values FP64 / FP32 values (dtype),
- * on n_threads threads.  Returns 1 if every value was a whole number in [-32768, 32767] (the packing is
+ * on n_threads threads (the calling thread and n_threads - 1 workers that stay alive, asleep, between calls;
+ * concurrent calls take turns).  Returns 1 if every value was a whole number in [-32768, 32767] (the packing is
  * lossless; -0.0 counts as 0), 0 if not (dst is then not to be used), < 0 on a bad argument.
  */
 int pnpb200_pack_i16(int dtype, const void* src, int64_t n_values, int16_t* dst, int n_threads);
