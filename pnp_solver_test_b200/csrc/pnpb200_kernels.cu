@@ -546,7 +546,7 @@ PNP_DEV void warp_reduce_scatter(T (&v)[32], int lane)
 // the moment stores, moving or invalidating the barriers, zero-filling the slots, a block-wide barrier after the initialisation,
 // eager module loading and a maximal shared-memory carve-out; it disappears when ANY 256-thread kernel of this translation
 // unit has run before.  No access of the kernel is out of range under its own logic, so the cause is not in this source; this
-// shape ran 12 of 12 instrumented first launches and every test / bench / soak process clean, and the others are not offered.)
+// shape ran 100 of 100 first launches (tools/first_launch_soak.py) and every test / bench / soak process clean; the others are not offered.)
 constexpr int kRingSlots = 3;
 constexpr int kRingPoints = 256;          // 4 KB per slot in FP64: 8 points per lane between two barrier waits
 constexpr int kRingWarps = 8;
