@@ -221,25 +221,39 @@ def test_pack_workers_are_reused_across_calls_and_survive_a_fork():
     for t in callers:
         t.join()
     assert len(results) == 4 and all(rc == 1 and np.array_equal(dst, want) for rc, dst in results)
-    pid = os.fork()
-    if pid == 0:                                            # child: exit code = verdict, no pytest machinery
-        ok = False
-        try:
-            rc, dst = pack(a, 6)
-            ok = rc == 1 and np.array_equal(dst, want)
-        finally:
-            os._exit(0 if ok else 1)
-    for _ in range(600):                                    # a child waiting for threads it does not have would hang: bounded wait
-        done, status = os.waitpid(pid, os.WNOHANG)
-        if done:
-            break
-        import time
-        time.sleep(0.05)
-    else:
-        os.kill(pid, 9)
-        os.waitpid(pid, 0)
-        pytest.fail("the forked child hung in pnpb200_pack_i16")
-    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+    # the fork check in a process of its own (numpy + the library, nothing else): the only threads alive at the fork are
+    # the pool's sleeping workers, whatever this pytest process happens to run beside the test
+    script = r"""
+import ctypes as C, os, sys, time
+import numpy as np
+lib = C.CDLL(sys.argv[1])
+a = np.random.default_rng(10).integers(-3000, 3000, 700001).astype(np.float64)
+want = a.astype(np.int16)
+def pack(threads):
+    dst = np.zeros(a.shape, np.int16)
+    rc = lib.pnpb200_pack_i16(C.c_int(0), a.ctypes.data_as(C.c_void_p), C.c_int64(a.size), dst.ctypes.data_as(C.POINTER(C.c_int16)), C.c_int(threads))
+    return rc == 1 and np.array_equal(dst, want)
+assert pack(6)                                   # the parent's pool exists now
+pid = os.fork()
+if pid == 0:
+    ok = False
+    try:
+        ok = pack(6)
+    finally:
+        os._exit(0 if ok else 1)
+for _ in range(400):                             # a child waiting for threads it does not have would hang: bounded wait
+    done, status = os.waitpid(pid, os.WNOHANG)
+    if done:
+        sys.exit(0 if (os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0) else 3)
+    time.sleep(0.05)
+os.kill(pid, 9)
+os.waitpid(pid, 0)
+sys.exit(4)                                      # hung
+"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", script, _lib.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, "forked child: %s" % {3: "wrong result", 4: "hung in pnpb200_pack_i16"}.get(r.returncode, r.stderr[-300:])
 
 
 def test_approval_masks():
